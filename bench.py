@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — group-by aggregation throughput on B200 (BASELINE.json metric).
+
+One "step" = one fused pass of the hot path (stages 1-3 + merge + emit) over one batch of synthetic
+rows: int64 key, fp64 value, sum + mean + count, N rows per GPU, G groups.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--rows R] [--groups G] [--sweep]
+  python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how every field is derived.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+AGGS = ["sum", "mean", "count"]
+SWEEP_AGGS = ["sum", "min", "max", "count"]
+SWEEP_G = [16, 256, 4096, 65536, 1 << 20, 1 << 24, 100_000_000]
+METRIC = "groupby_agg_rows_per_s"
+UNIT = "rows/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
+    ap.add_argument("--groups", type=int, default=1000)
+    ap.add_argument("--sweep", action="store_true", help="also run the config-2 cardinality sweep (device resident)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=10_000_000, help="rows of the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(n_rows: int, n_groups: int, n_aggs: int) -> float:
+    # 16 B/row in (int64 key + fp64 value) + G x (8 B key + 8 B per aggregate) out
+    return 16.0 * n_rows + n_groups * (8.0 + 8.0 * n_aggs)
+
+
+def cpu_reference(rows: int, groups: int, repeats: int = 1) -> dict:
+    """The reference's CPU path (oracle port of its Arrow call sequence) on this box's host cores:
+    GroupBy ctor (hash + groupings + gathers of index and every column + per-group map inserts:
+    single-threaded, as in the reference) followed by sum/mean/count with the over-groups loop on all
+    cores (OpenMP standing in for TBB)."""
+    import pyarrow as pa
+    from oracle import oracle as orc
+    from pandasarrow_b200 import hostgen as hg
+    threads = os.cpu_count() or 1
+    rb = pa.record_batch({"k": pa.array(hg.keys(rows, groups)), "v": pa.array(hg.vals(rows))})
+    index = pa.array(range(rows), pa.int64())
+    best = None
+    detail = {}
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        g = orc.OracleGroupBy(rb, "k", index=index, materialize=True)
+        t1 = time.perf_counter()
+        for a in AGGS:
+            g.agg(a, "v", nthreads=threads)
+        t2 = time.perf_counter()
+        tm = g.timing_ms()
+        g.close()
+        if best is None or (t2 - t0) < best:
+            best = t2 - t0
+            detail = {"ctor_s": t1 - t0, "aggs_s": t2 - t1, "consume_ms": tm["consume"], "groupings_ms": tm["groupings"],
+                      "gather_ms": tm["gather"]}
+    return {"value": rows / best, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{rows} rows x {groups} groups, int64 key + fp64 value, GroupBy ctor (1 thread, as the reference) "
+                      f"+ sum/mean/count ({threads} threads); ctor {detail['ctor_s']:.3f}s aggs {detail['aggs_s']:.3f}s",
+            "seconds": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(args.steps, 1), args.warmup
+    rows = min(args.cpu_rows, args.rows)
+    for _ in range(min(warm, 1)):
+        cpu_reference(min(rows, 1_000_000), args.groups)
+    t0 = time.perf_counter()
+    vals = [cpu_reference(rows, args.groups) for _ in range(steps)]
+    dt = time.perf_counter() - t0
+    secs = sorted(v["seconds"] for v in vals)
+    med = secs[len(secs) // 2]
+    value = rows / med
+    base = vals[0]
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"group_by(int64 key, {args.groups} groups).sum/mean/count, fp64 value; CPU sample of "
+                                   f"{rows} rows (the reference path needs ~4x input RAM and int32 row ids)",
+                       "rows_per_step": rows, "groups": args.groups},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": dt}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import pyarrow as pa
+    import pandasarrow_b200 as pab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n, G = args.rows, args.groups
+    first_row = rank * n                        # row-range shard of a world*n-row data set (weak scaling)
+    stream = torch.cuda.Stream(device=dev)
+
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    vals = torch.empty(n, dtype=torch.float64, device=dev)
+    pab.synth.keys(keys, G, first_row)
+    pab.synth.vals(vals, first_row)
+    torch.cuda.synchronize()
+    dk, dv = pab.DeviceColumn.from_torch(keys), pab.DeviceColumn.from_torch(vals)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    gb = pab.GroupBy("k", {"k": dk, "v": dv}, stream=stream.cuda_stream, device=local)
+    scan_ms, launches = [], 0
+    for _ in range(args.warmup):
+        gb.aggregate(dv, AGGS, fetch=False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        gb.aggregate(dv, AGGS, fetch=False)
+        t = gb.timing()
+        scan_ms.append(t["scan_ms"]); launches += t["launches"]
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_per_step = tms.item() / args.steps
+    path = gb.timing()["path"]
+    n_groups_found = gb.groupSize()
+    value = world * n / (ms_per_step * 1e-3)
+    scan = sorted(scan_ms)[len(scan_ms) // 2]
+    peak, peak_src = peaks()
+    alg = algorithmic_bytes(n, n_groups_found, len(AGGS))
+    achieved = alg / (scan * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_lowcard_scan" if path == "lowcard" else "k_gtable_scan",
+                "kernel_ms": scan, "algorithmic_bytes": alg, "peak_source": peak_src,
+                "frac_of_step": scan / ms_per_step}
+
+    # ---------------- optional cardinality sweep (config 2), device resident ----------------
+    sweep = None
+    if args.sweep and rank == 0:
+        sweep = []
+        for g_ in SWEEP_G:
+            if g_ > n:
+                continue
+            pab.synth.keys(keys, g_, first_row)
+            torch.cuda.synchronize()
+            h = pab.GroupBy("k", {"k": dk, "v": dv}, stream=stream.cuda_stream, device=local, expected_groups=g_)
+            for _ in range(2):
+                h.aggregate(dv, SWEEP_AGGS, fetch=False)
+            ts = []
+            for _ in range(3):
+                h.aggregate(dv, SWEEP_AGGS, fetch=False)
+                ts.append(h.timing())
+            ts.sort(key=lambda t: t["total_ms"])
+            t = ts[len(ts) // 2]
+            ab = algorithmic_bytes(n, h.groupSize(), len(SWEEP_AGGS))
+            sweep.append({"groups": g_, "found": h.groupSize(), "path": t["path"], "total_ms": t["total_ms"],
+                          "scan_ms": t["scan_ms"], "rows_per_s": n / (t["total_ms"] * 1e-3),
+                          "scan_GBps": ab / (t["scan_ms"] * 1e-3) / 1e9, "frac": ab / (t["scan_ms"] * 1e-3) / 1e9 / peak})
+            h.close()
+        pab.synth.keys(keys, G, first_row)
+        torch.cuda.synchronize()
+
+    # ---------------- end to end through the C ABI with HOST buffers (`e2e`) ----------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hk = torch.empty(n, dtype=torch.int64, pin_memory=True)
+            hv = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            hk.copy_(keys); hv.copy_(vals)
+            torch.cuda.synchronize()
+            ak = pa.Array.from_buffers(pa.int64(), n, [None, pa.py_buffer(hk.numpy())])
+            av = pa.Array.from_buffers(pa.float64(), n, [None, pa.py_buffer(hv.numpy())])
+
+            def e2e_step():
+                with pab.GroupBy("k", {"k": ak, "v": av}, device=local) as h:
+                    r = h.aggregate(av, AGGS)                      # H2D of keys + values, kernels, D2H of results
+                    return sum(len(x) * 8 for x in r.values())
+
+            e2e_steps = max(2, min(args.steps, 3))
+            d2h = e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            barrier()
+            dt = (time.perf_counter() - t0) / e2e_steps
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e = {"value": world * n / tt.item(), "unit": UNIT, "h2d_bytes_per_step": 16 * n,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": tt.item() * 1e3, "steps": e2e_steps,
+                   "note": "pinned host Arrow buffers -> pa_groupby_create/aggregate/fetch; wall clock around synchronous calls"}
+            del hk, hv, ak, av
+        except Exception as ex:  # noqa: BLE001
+            e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:300]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_reference(min(args.cpu_rows, n), G)
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"value": None, "error": repr(ex)[:300]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"group_by(int64 key, {G} groups).sum/mean/count over {n} rows per GPU, fp64 value "
+                                       f"(BASELINE configs[1] row count at configs[0] cardinality)",
+                           "rows_per_gpu": n, "groups": G, "aggs": AGGS, "path": path,
+                           "l2": "inputs (16 B/row x rows) far exceed the 126 MB L2; no explicit flush",
+                           "hbm_GBps_whole_step": alg / (ms_per_step * 1e-3) / 1e9},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        if sweep is not None:
+            line["sweep"] = sweep
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,193 @@
+/* pa_b200.h — C ABI of the B200-native group-by / resample hot path.
+ *
+ * This is the drop-in boundary for PandasArrow's group-by hash aggregation.
+ * The reference has no FFI of its own: its boundary is the C++ class surface
+ *   pd::GroupBy            /root/reference/src/group_by.h:22-247
+ *   pd::Resampler          /root/reference/src/group_by.h:255-299
+ *   pd::resample           /root/reference/src/resample.h:51-122
+ *   DataFrame::group_by / resample / downsample   /root/reference/src/dataframe.cpp:1227-1290
+ * directly on top of arrow::compute.  The entry points below are what those classes bind to
+ * instead of arrow::compute::Grouper / CallFunction; pandasarrow_b200/csrc/host/pd_groupby.h
+ * is that binding (same class and method names as the reference), INTEGRATION.md shows the
+ * patch a maintainer of the reference would apply.
+ *
+ * Data crosses the boundary as Arrow C Data Interface structs (arrow/c/abi.h): plain pointers
+ * and sizes, no C++ or torch types.  Inputs are ArrowDeviceArray: device_type ARROW_DEVICE_CPU
+ * buffers are copied host->device by the library, ARROW_DEVICE_CUDA buffers are used in place
+ * (zero copy).  buffers[0] = validity bitmap (LSB first, may be NULL), buffers[1] = values;
+ * `offset` and `null_count` are honoured.  Inputs are borrowed for the duration of the call that
+ * receives them and until pa_groupby_destroy() for keys; the library never calls release() on an
+ * input.  Outputs are host ArrowArray/ArrowSchema pairs owned by the caller (call release()).
+ *
+ * There is no CPU fallback: every call that computes fails with PA_ERR_CUDA when no CUDA device
+ * is present.  All functions return 0 on success; pa_last_error() gives the thread-local message.
+ */
+#ifndef PA_B200_H
+#define PA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Arrow C Data Interface (verbatim ABI; guarded so arrow/c/abi.h may be included too) ---- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+#define ARROW_FLAG_DICTIONARY_ORDERED 1
+#define ARROW_FLAG_NULLABLE 2
+#define ARROW_FLAG_MAP_KEYS_SORTED 4
+struct ArrowSchema {
+  const char* format;
+  const char* name;
+  const char* metadata;
+  int64_t flags;
+  int64_t n_children;
+  struct ArrowSchema** children;
+  struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*);
+  void* private_data;
+};
+struct ArrowArray {
+  int64_t length;
+  int64_t null_count;
+  int64_t offset;
+  int64_t n_buffers;
+  int64_t n_children;
+  const void** buffers;
+  struct ArrowArray** children;
+  struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*);
+  void* private_data;
+};
+#endif /* ARROW_C_DATA_INTERFACE */
+
+#ifndef ARROW_C_DEVICE_DATA_INTERFACE
+#define ARROW_C_DEVICE_DATA_INTERFACE
+typedef int32_t ArrowDeviceType;
+#define ARROW_DEVICE_CPU 1
+#define ARROW_DEVICE_CUDA 2
+#define ARROW_DEVICE_CUDA_HOST 3
+struct ArrowDeviceArray {
+  struct ArrowArray array;
+  int64_t device_id;
+  ArrowDeviceType device_type;
+  void* sync_event;
+  int64_t reserved[3];
+};
+#endif /* ARROW_C_DEVICE_DATA_INTERFACE */
+
+/* ---- status codes ---- */
+#define PA_OK 0
+#define PA_ERR_INVALID 1     /* bad argument / unsupported type (message says which) */
+#define PA_ERR_CUDA 2        /* CUDA runtime failure, or no device */
+#define PA_ERR_NOT_IMPLEMENTED 3
+#define PA_ERR_STATE 4       /* call order violated (e.g. fetch before aggregate) */
+
+/* ---- aggregate selection: bit mask, outputs are produced in ascending bit order ----
+ * Semantics follow the reference's per-group arrow::compute calls
+ * (pd_core_macros.h:5-147, dataframe.cpp:1602-1806):
+ *   SUM    int*->int64 (wraps), uint*->uint64, float/double->double; null for an all-null group
+ *   MEAN   double (ints are accumulated in double); null for an all-null group
+ *   COUNT  int64 number of non-null values
+ *   MIN/MAX input dtype; NaN skipped unless the group is all-NaN; null for an all-null group
+ *   FIRST/LAST value at the first/last row of the group, nulls NOT skipped (positional)
+ */
+#define PA_AGG_SUM 1u
+#define PA_AGG_MEAN 2u
+#define PA_AGG_COUNT 4u
+#define PA_AGG_MIN 8u
+#define PA_AGG_MAX 16u
+#define PA_AGG_FIRST 32u
+#define PA_AGG_LAST 64u
+#define PA_AGG_ALL 127u
+
+/* ---- kernel path selection (pa_options.path); AUTO is what a caller wants ---- */
+#define PA_PATH_AUTO 0
+#define PA_PATH_LOWCARD 1   /* shared-memory privatised tables only; fails if they overflow */
+#define PA_PATH_GLOBAL 2    /* global-memory table with L2 atomics */
+
+typedef struct pa_options {
+  int32_t device;            /* CUDA device ordinal; -1 = current device */
+  int32_t path;              /* PA_PATH_* */
+  int64_t expected_groups;   /* hint for table sizing; 0 = unknown */
+  void* cuda_stream;         /* cudaStream_t to run on; NULL = a stream owned by the handle */
+  int64_t row_base;          /* global row number of local row 0 (multi-GPU row-range shards) */
+  int64_t reserved[4];
+} pa_options;
+
+typedef struct pa_groupby pa_groupby;      /* opaque: key columns + device group table */
+
+const char* pa_last_error(void);
+int pa_version(void);                       /* major*10000 + minor*100 + patch */
+void pa_options_init(pa_options* opt);      /* fills defaults */
+int pa_device_count(int* out);
+
+/* pd::GroupBy::GroupBy / makeGroups (group_by.h:24-31, dataframe.cpp:1571-1600), stages 1-2.
+ * keys[i] with key_schemas[i] describe the i-th key column (all the same length).  Supported key
+ * formats: l L i I (int64/uint64/int32/uint32), ts* / tt* / td* (64-bit temporal), and
+ * dictionary-encoded columns (the int32 indices are the key; the dictionary is not read).
+ * Null keys form their own group.  Composite keys must pack into 64 bits.
+ * Work is lazy: the table is built by the first aggregate (fused with it) or by
+ * pa_groupby_num_groups / pa_groupby_unique. */
+int pa_groupby_create(const struct ArrowDeviceArray* keys, const struct ArrowSchema* key_schemas,
+                      int32_t n_keys, const pa_options* opt, pa_groupby** out);
+
+/* GroupBy::groupSize (group_by.h:33-36) */
+int pa_groupby_num_groups(pa_groupby* g, int64_t* out);
+
+/* GroupBy::unique (group_by.h:52-55): the key_i-th key column of the unique keys, in
+ * first-appearance order, same type as the input key (dictionary keys: the int32 indices). */
+int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* Stage 3, fused with stages 1-2: one pass over keys + values computing every aggregate in
+ * agg_mask (GroupBy::sum/mean/count/min/max/first/last, pd_core_macros.h:5-147,
+ * dataframe.cpp:1698-1806).  Value formats: g f l L i I s S c C (double, float, (u)int64/32/16/8)
+ * and 64-bit temporal types.  Results stay on the device until fetched. */
+int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values,
+                         const struct ArrowSchema* value_schema, uint32_t agg_mask);
+
+/* Copies one finished aggregate (a single PA_AGG_* bit of the last aggregate call) to a host
+ * Arrow array of length num_groups, first-appearance order. */
+int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* Grouper::Consume equivalent (dataframe.cpp:1584): uint32 group id of every row, ids numbered in
+ * first-appearance order.  Host array of length n_rows. */
+int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* Device time (ms, CUDA events on the handle's stream) of the last aggregate call: total and
+ * per stage.  stage_ms[0]=key packing, [1]=scan kernel(s), [2]=merge/finalise, [3]=emit. */
+int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]);
+/* Which path the last aggregate took (PA_PATH_LOWCARD / PA_PATH_GLOBAL) and how many of this
+ * library's kernels it launched. */
+int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches);
+/* Blocks until everything queued on the handle's stream has finished. */
+int pa_groupby_sync(pa_groupby* g);
+
+void pa_groupby_destroy(pa_groupby* g);
+
+/* pd::resample with a fixed-width rule (resample.h:91-122, resample.cpp:85-295): time-bucket
+ * specialisation.  `index` is a sorted, null-free timestamp/int64 column; buckets are
+ * [first + k*freq, first + (k+1)*freq) (closed_right: (..]) where `first` is anchored as
+ * adjustDatesAnchored does (origin: 0 epoch, 1 start, 2 start_day, 3 end, 4 end_day, 5 custom).
+ * Only non-empty buckets appear (the reference groups on per-row labels).  The returned handle
+ * is a pa_groupby whose unique key is the bucket label: aggregate/fetch/unique work as above, on
+ * a sorted-run segmented-reduction kernel instead of a hash table.  Throws-equivalents:
+ * PA_ERR_INVALID for unsorted input, PA_ERR_NOT_IMPLEMENTED for up-sampling rules. */
+int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowSchema* index_schema,
+                       int64_t freq_ns, int32_t closed_right, int32_t label_right, int32_t origin,
+                       int64_t origin_custom_ns, int64_t offset_ns, const pa_options* opt,
+                       pa_groupby** out);
+
+/* ---- synthetic workload generator, used by bench.py and the tests so that the
+ * same counter-based splitmix64 streams exist on host and device without PCIe staging.
+ * All pointers are DEVICE pointers; `first_row` offsets the counter (row-range shards). ---- */
+int pa_synth_keys_i64(void* dev_out, int64_t n, int64_t first_row, uint64_t n_groups, uint64_t seed, void* cuda_stream);
+int pa_synth_vals_f64(void* dev_out, int64_t n, int64_t first_row, uint64_t seed, void* cuda_stream);
+int pa_synth_validity(void* dev_bitmap_out, int64_t n, int64_t first_row, uint64_t seed, uint32_t null_every, void* cuda_stream);
+int pa_synth_timestamps(void* dev_out, int64_t n, int64_t first_row, int64_t t0_ns, int64_t step_ns, uint64_t seed, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PA_B200_H */

@@ -1,0 +1,850 @@
+// C ABI of the B200 group-by path (include/pa_b200.h).  Host-side orchestration only: column
+// marshalling from the Arrow C Data Interface, path selection, kernel launches, result export.
+// No computation happens on the host and there is no CPU fallback.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pa_b200.h"
+#include "emit.cuh"
+#include "gtable.cuh"
+#include "lowcard.cuh"
+
+using namespace pa;
+
+namespace {
+
+thread_local std::string g_err;
+
+int set_err(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return set_err(PA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define PA_TRY(expr)        \
+  do {                      \
+    int rc__ = (expr);      \
+    if (rc__ != PA_OK) return rc__; \
+  } while (0)
+
+// Stream-ordered device allocation; the pool keeps freed memory so that repeated aggregate
+// calls (bench steps) do not pay cudaMalloc.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { reset(); p = o.p; bytes = o.bytes; s = o.s; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { reset(); }
+  void reset() {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    bytes = 0;
+  }
+  int alloc(size_t n, cudaStream_t stream) {
+    reset();
+    s = stream;
+    if (n == 0) n = 16;
+    CUDA_TRY(cudaMallocAsync(&p, n, stream));
+    bytes = n;
+    return PA_OK;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct Column {
+  const void* data = nullptr;       // device pointer, already advanced by `offset` elements
+  const uint8_t* valid = nullptr;   // device validity bitmap (not advanced) or null
+  int64_t bit_off = 0;
+  int64_t n = 0;
+  int width = 0;                    // bytes per element
+  int vc = VC_I;                    // value class (value columns)
+  std::string format;               // Arrow format string of the (index) type
+  bool is_dict = false;
+  int64_t dict_len = 0;
+  DevBuf own_data, own_valid;       // set when the input lived on the host
+};
+
+int parse_format(const char* f, int* width, int* vc) {
+  if (!f) return set_err(PA_ERR_INVALID, "schema has no format string");
+  switch (f[0]) {
+    case 'g': *width = 8; *vc = VC_F; return PA_OK;
+    case 'f': *width = 4; *vc = VC_F; return PA_OK;
+    case 'l': *width = 8; *vc = VC_I; return PA_OK;
+    case 'L': *width = 8; *vc = VC_U; return PA_OK;
+    case 'i': *width = 4; *vc = VC_I; return PA_OK;
+    case 'I': *width = 4; *vc = VC_U; return PA_OK;
+    case 's': *width = 2; *vc = VC_I; return PA_OK;
+    case 'S': *width = 2; *vc = VC_U; return PA_OK;
+    case 'c': *width = 1; *vc = VC_I; return PA_OK;
+    case 'C': *width = 1; *vc = VC_U; return PA_OK;
+    case 't':
+      // tss/tsm/tsu/tsn timestamps, tD* durations, ttu/ttn time64, tdm date64: 64-bit; tdD date32, tts/ttm: 32-bit
+      if (f[1] == 's' || f[1] == 'D') { *width = 8; *vc = VC_I; return PA_OK; }
+      if (f[1] == 't') { *width = (f[2] == 'u' || f[2] == 'n') ? 8 : 4; *vc = VC_I; return PA_OK; }
+      if (f[1] == 'd') { *width = (f[2] == 'm') ? 8 : 4; *vc = VC_I; return PA_OK; }
+      break;
+    default: break;
+  }
+  return set_err(PA_ERR_INVALID, "unsupported Arrow format '%s' (fixed-width numeric / temporal only)", f);
+}
+
+// Bring one primitive Arrow array onto the device (or borrow it when it already is there).
+int load_column(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t st, int device, Column* out) {
+  const ArrowArray& a = da->array;
+  if (a.n_buffers < 2) return set_err(PA_ERR_INVALID, "expected a primitive array with 2 buffers, got %lld", (long long)a.n_buffers);
+  PA_TRY(parse_format(sc->format, &out->width, &out->vc));
+  out->format = sc->format;
+  out->is_dict = sc->dictionary != nullptr;
+  out->dict_len = (a.dictionary != nullptr) ? a.dictionary->length : 0;
+  out->n = a.length;
+  const bool has_nulls = a.null_count != 0 && a.buffers[0] != nullptr;
+  const char* values = static_cast<const char*>(a.buffers[1]);
+  if (da->device_type == ARROW_DEVICE_CUDA) {
+    if (da->device_id != device) return set_err(PA_ERR_INVALID, "array lives on device %lld, handle on %d", (long long)da->device_id, device);
+    out->data = values ? values + a.offset * out->width : nullptr;
+    out->valid = has_nulls ? static_cast<const uint8_t*>(a.buffers[0]) : nullptr;
+    out->bit_off = a.offset;
+    if (da->sync_event) CUDA_TRY(cudaStreamWaitEvent(st, *static_cast<cudaEvent_t*>(da->sync_event), 0));
+  } else if (da->device_type == ARROW_DEVICE_CPU || da->device_type == ARROW_DEVICE_CUDA_HOST) {
+    const size_t bytes = static_cast<size_t>(a.length) * out->width;
+    PA_TRY(out->own_data.alloc(bytes, st));
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(out->own_data.p, values + a.offset * out->width, bytes, cudaMemcpyHostToDevice, st));
+    out->data = out->own_data.p;
+    if (has_nulls) {
+      // copy the bytes that cover bits [offset, offset+length); keep the sub-byte offset
+      const int64_t first_byte = a.offset / 8;
+      const size_t nbytes = static_cast<size_t>((a.offset + a.length + 7) / 8 - first_byte);
+      PA_TRY(out->own_valid.alloc(nbytes, st));
+      CUDA_TRY(cudaMemcpyAsync(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, cudaMemcpyHostToDevice, st));
+      out->valid = out->own_valid.as<uint8_t>();
+      out->bit_off = a.offset % 8;
+    }
+  } else {
+    return set_err(PA_ERR_INVALID, "unsupported device_type %d", (int)da->device_type);
+  }
+  return PA_OK;
+}
+
+struct KeyField {
+  int width = 8, bits = 64, shift = 0, nullable = 0;
+};
+
+struct AggOut {
+  uint32_t bit = 0;
+  std::string format;
+  int width = 8;
+  bool nullable = true;
+  DevBuf values, valid;
+};
+
+}  // namespace
+
+struct pa_groupby {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  pa_options opt{};
+  int64_t n = 0;
+  // keys
+  std::vector<Column> keys;
+  std::vector<KeyField> fields;
+  bool packed = false;
+  DevBuf packed_keys;
+  const void* key_data = nullptr;   // what the scan kernels read
+  const uint8_t* key_valid = nullptr;
+  int64_t key_bit_off = 0;
+  int key_width = 8;
+  // resample mode (time-bucket specialisation)
+  bool resample = false;
+  std::string index_format;
+  // group table in first-appearance order
+  bool have_groups = false;
+  uint32_t G = 0;
+  uint32_t res_cap = 0;
+  DevBuf r_key, r_kind, r_sum, r_dsum, r_count, r_first, r_last, r_min, r_max;
+  GroupResult res{};
+  // outputs of the last aggregate
+  std::vector<AggOut> outs;
+  // bookkeeping
+  DevBuf status;
+  int last_path = 0, last_launches = 0;
+  float last_total_ms = 0;
+  float stage_ms[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[6] = {};
+};
+
+namespace {
+
+int alloc_result(pa_groupby* g, uint32_t cap, bool wide, bool need_dsum) {
+  cudaStream_t st = g->stream;
+  if (cap == 0) cap = 1;
+  g->res_cap = cap;
+  PA_TRY(g->r_key.alloc(sizeof(uint64_t) * cap, st));
+  PA_TRY(g->r_kind.alloc(cap, st));
+  PA_TRY(g->r_sum.alloc(sizeof(uint64_t) * cap, st));
+  PA_TRY(g->r_count.alloc(sizeof(uint32_t) * cap, st));
+  PA_TRY(g->r_first.alloc(sizeof(uint32_t) * cap, st));
+  PA_TRY(g->r_last.alloc(sizeof(uint32_t) * cap, st));
+  g->res = GroupResult{};
+  g->res.key = g->r_key.as<uint64_t>();
+  g->res.key_kind = g->r_kind.as<uint8_t>();
+  g->res.sum = g->r_sum.as<uint64_t>();
+  g->res.count = g->r_count.as<uint32_t>();
+  g->res.first_row = g->r_first.as<uint32_t>();
+  g->res.last_row = g->r_last.as<uint32_t>();
+  if (wide) {
+    PA_TRY(g->r_min.alloc(sizeof(uint64_t) * cap, st));
+    PA_TRY(g->r_max.alloc(sizeof(uint64_t) * cap, st));
+    g->res.min_ord = g->r_min.as<uint64_t>();
+    g->res.max_ord = g->r_max.as<uint64_t>();
+    if (need_dsum) {
+      PA_TRY(g->r_dsum.alloc(sizeof(double) * cap, st));
+      g->res.dsum = g->r_dsum.as<double>();
+    }
+  }
+  return PA_OK;
+}
+
+int run_resample(pa_groupby* g, const Column* val, uint32_t mask, bool wide);
+
+bool is_wide(uint32_t mask, int vc) {
+  return (mask & (AGG_MIN | AGG_MAX | AGG_LAST)) || ((mask & AGG_MEAN) && vc != VC_F);
+}
+
+// ------------------------------ low-cardinality path ------------------------------
+template <int VC, int VW, int KW, bool WIDE>
+int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid) {
+  using L = LcSmem<WIDE>;
+  const size_t smem = L::total(KW, VW);
+  auto scan = k_lowcard_scan<VC, VW, KW, WIDE>;
+  CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  scan<<<grid, LC_THREADS, smem, g->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
+  k_lowcard_merge<VC, WIDE><<<1, LM_THREADS, 0, g->stream>>>(m);
+  CUDA_TRY(cudaGetLastError());
+  g->last_launches += 2;
+  return PA_OK;
+}
+
+template <int VC, int VW, bool WIDE>
+int launch_lowcard_k(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid) {
+  return g->key_width == 8 ? launch_lowcard_t<VC, VW, 8, WIDE>(g, a, m, grid) : launch_lowcard_t<VC, VW, 4, WIDE>(g, a, m, grid);
+}
+
+template <bool WIDE>
+int launch_lowcard_w(pa_groupby* g, int vc, int vw, const LcArgs& a, const LmArgs& m, int grid) {
+  if (vc == VC_F) return vw == 8 ? launch_lowcard_k<VC_F, 8, WIDE>(g, a, m, grid) : launch_lowcard_k<VC_F, 4, WIDE>(g, a, m, grid);
+  if (vc == VC_I) return vw == 8 ? launch_lowcard_k<VC_I, 8, WIDE>(g, a, m, grid) : launch_lowcard_k<VC_I, 4, WIDE>(g, a, m, grid);
+  return vw == 8 ? launch_lowcard_k<VC_U, 8, WIDE>(g, a, m, grid) : launch_lowcard_k<VC_U, 4, WIDE>(g, a, m, grid);
+}
+
+// returns PA_OK and sets *overflow when the shared-memory tables were too small
+int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool* overflow) {
+  cudaStream_t st = g->stream;
+  const int grid = g->num_sms;
+  const int gp = wide ? LcCfg<true>::GP : LcCfg<false>::GP;
+  const size_t np = static_cast<size_t>(grid) * gp;
+  DevBuf p_key, p_sum, p_dsum, p_count, p_first, p_last, p_min, p_max, p_nids, inv;
+  PA_TRY(p_key.alloc(np * 8, st));
+  PA_TRY(p_sum.alloc(np * 8, st));
+  PA_TRY(p_count.alloc(np * 4, st));
+  PA_TRY(p_first.alloc(np * 4, st));
+  PA_TRY(p_nids.alloc(sizeof(uint32_t) * grid, st));
+  if (wide) {
+    PA_TRY(p_dsum.alloc(np * 8, st));
+    PA_TRY(p_last.alloc(np * 4, st));
+    PA_TRY(p_min.alloc(np * 8, st));
+    PA_TRY(p_max.alloc(np * 8, st));
+  }
+  PA_TRY(inv.alloc(np * 2, st));
+  CUDA_TRY(cudaMemsetAsync(inv.p, 0xFF, np * 2, st));
+  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  const int vc = val ? val->vc : VC_I;
+  const int vw = val ? val->width : 8;
+  PA_TRY(alloc_result(g, gp, wide, vc != VC_F));
+
+  LcArgs a{};
+  a.keys = g->key_data;
+  a.kvalid = g->key_valid;
+  a.koff = g->key_bit_off;
+  a.vals = val ? val->data : nullptr;
+  a.vvalid = val ? val->valid : nullptr;
+  a.voff = val ? val->bit_off : 0;
+  a.n = g->n;
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0) && (!a.vals || reinterpret_cast<uintptr_t>(a.vals) % 16 == 0);
+  a.n_bulk = aligned ? (g->n / LC_CHUNK) * LC_CHUNK : 0;
+  a.agg_mask = mask;
+  a.p_key = p_key.as<uint64_t>();
+  a.p_sum = p_sum.as<uint64_t>();
+  a.p_dsum = p_dsum.as<double>();
+  a.p_count = p_count.as<uint32_t>();
+  a.p_first = p_first.as<uint32_t>();
+  a.p_last = p_last.as<uint32_t>();
+  a.p_min = p_min.as<uint64_t>();
+  a.p_max = p_max.as<uint64_t>();
+  a.p_nids = p_nids.as<uint32_t>();
+  a.status = g->status.as<uint32_t>();
+  LmArgs m{};
+  m.part = a;
+  m.grid = grid;
+  m.inv = inv.as<uint16_t>();
+  m.out = g->res;
+  m.status = a.status;
+  CUDA_TRY(cudaEventRecord(g->ev[1], st));
+  if (wide) PA_TRY(launch_lowcard_w<true>(g, vc, vw, a, m, grid));
+  else PA_TRY(launch_lowcard_w<false>(g, vc, vw, a, m, grid));
+  CUDA_TRY(cudaEventRecord(g->ev[3], st));
+  uint32_t h_status[ST_WORDS];
+  CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *overflow = h_status[ST_OVERFLOW] != 0;
+  if (!*overflow) g->G = h_status[ST_NGROUPS];
+  return PA_OK;
+}
+
+// ------------------------------ global-table path ------------------------------
+template <int VC, bool WIDE>
+int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
+  using SlotT = typename SlotOf<WIDE>::type;
+  cudaStream_t st = g->stream;
+  uint64_t want = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : std::min<uint64_t>(static_cast<uint64_t>(g->n), 1ull << 20);
+  uint64_t cap = 1024;
+  while (cap < want * 2) cap <<= 1;
+  const uint64_t cap_limit = [&] { uint64_t c = 1024; while (c < static_cast<uint64_t>(g->n) * 2) c <<= 1; return c; }();
+  if (cap > cap_limit) cap = cap_limit;
+  DevBuf table;
+  const int grid_full = g->num_sms * 8;
+  CUDA_TRY(cudaEventRecord(g->ev[1], st));
+  for (;;) {
+    const uint64_t nslots = cap + 2;
+    PA_TRY(table.alloc(nslots * sizeof(SlotT), st));
+    CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+    const int init_grid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+    k_gtable_init<WIDE><<<init_grid, 256, 0, st>>>(table.as<SlotT>(), nslots);
+    CUDA_TRY(cudaGetLastError());
+    GScanArgs a{};
+    a.keys = g->key_data;
+    a.kvalid = g->key_valid;
+    a.koff = g->key_bit_off;
+    a.kw = g->key_width;
+    a.vals = val ? val->data : nullptr;
+    a.vvalid = val ? val->valid : nullptr;
+    a.voff = val ? val->bit_off : 0;
+    a.vw = val ? val->width : 8;
+    a.n = g->n;
+    a.table = table.p;
+    a.cap_mask = cap - 1;
+    a.status = g->status.as<uint32_t>();
+    a.agg_mask = mask;
+    const int64_t ntiles = (g->n + 1023) / 1024;
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, grid_full)));
+    k_gtable_scan<VC, WIDE><<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 2;
+    uint32_t h_status[ST_WORDS];
+    CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!h_status[ST_OVERFLOW]) break;
+    if (cap >= cap_limit) return set_err(PA_ERR_CUDA, "global group table overflowed at capacity %llu", (unsigned long long)cap);
+    cap = std::min(cap * 8, cap_limit);
+  }
+  CUDA_TRY(cudaEventRecord(g->ev[2], st));
+  // compact occupied slots, order them by first row, gather
+  const uint64_t nslots = cap + 2;
+  const uint64_t max_groups = std::min<uint64_t>(nslots, static_cast<uint64_t>(g->n) + 2);
+  DevBuf c_first, c_slot, s_first, s_slot, cub_tmp;
+  PA_TRY(c_first.alloc(max_groups * 4, st));
+  PA_TRY(c_slot.alloc(max_groups * 4, st));
+  const int cgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+  k_gtable_compact<WIDE><<<cgrid, 256, 0, st>>>(table.as<SlotT>(), nslots, c_first.as<uint32_t>(), c_slot.as<uint32_t>(), g->status.as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  g->last_launches += 1;
+  uint32_t G = 0;
+  CUDA_TRY(cudaMemcpyAsync(&G, g->status.as<uint32_t>() + ST_COUNTER, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  g->G = G;
+  PA_TRY(alloc_result(g, G, WIDE, VC != VC_F));
+  if (G > 0) {
+    PA_TRY(s_first.alloc(static_cast<size_t>(G) * 4, st));
+    PA_TRY(s_slot.alloc(static_cast<size_t>(G) * 4, st));
+    size_t tmp_bytes = 0;
+    // ordering G (first_row, slot) pairs is bookkeeping, not one of the three hot stages: CUB's
+    // radix sort (library code) is used for it and counted as such in DESIGN.md.
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
+    PA_TRY(cub_tmp.alloc(tmp_bytes, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
+    k_gtable_gather<WIDE><<<(G + 255) / 256, 256, 0, st>>>(table.as<SlotT>(), cap, s_slot.as<uint32_t>(), G, g->res);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 1;
+  }
+  CUDA_TRY(cudaEventRecord(g->ev[3], st));
+  return PA_OK;
+}
+
+int run_global(pa_groupby* g, const Column* val, uint32_t mask, bool wide) {
+  const int vc = val ? val->vc : VC_I;
+  if (wide) {
+    if (vc == VC_F) return run_global_t<VC_F, true>(g, val, mask);
+    if (vc == VC_I) return run_global_t<VC_I, true>(g, val, mask);
+    return run_global_t<VC_U, true>(g, val, mask);
+  }
+  if (vc == VC_F) return run_global_t<VC_F, false>(g, val, mask);
+  if (vc == VC_I) return run_global_t<VC_I, false>(g, val, mask);
+  return run_global_t<VC_U, false>(g, val, mask);
+}
+
+// ------------------------------ emit ------------------------------
+const char* sum_format(int vc) { return vc == VC_F ? "g" : (vc == VC_I ? "l" : "L"); }
+
+int run_emit(pa_groupby* g, const Column* val, uint32_t mask) {
+  cudaStream_t st = g->stream;
+  g->outs.clear();
+  const uint32_t G = g->G;
+  const size_t words = (static_cast<size_t>(G) + 31) / 32 + 1;
+  EmitArgs e{};
+  e.r = g->res;
+  e.G = G;
+  e.vc = val ? val->vc : VC_I;
+  e.vw = val ? val->width : 8;
+  e.vals = val ? val->data : nullptr;
+  e.vvalid = val ? val->valid : nullptr;
+  e.voff = val ? val->bit_off : 0;
+  auto add = [&](uint32_t bit, const std::string& fmt, int width, bool nullable, void** vptr, uint32_t** bptr) -> int {
+    g->outs.emplace_back();
+    AggOut& o = g->outs.back();
+    o.bit = bit;
+    o.format = fmt;
+    o.width = width;
+    o.nullable = nullable;
+    PA_TRY(o.values.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * width, st));
+    *vptr = o.values.p;
+    if (nullable) {
+      PA_TRY(o.valid.alloc(words * 4, st));
+      *bptr = o.valid.as<uint32_t>();
+    }
+    return PA_OK;
+  };
+  g->outs.reserve(8);
+  void* v;
+  uint32_t* b;
+  const std::string vfmt = val ? val->format : "l";
+  if (mask & AGG_SUM) { PA_TRY(add(AGG_SUM, sum_format(e.vc), 8, true, &v, &b)); e.o_sum = v; e.o_sum_valid = b; }
+  if (mask & AGG_MEAN) { PA_TRY(add(AGG_MEAN, "g", 8, true, &v, &b)); e.o_mean = static_cast<double*>(v); e.o_mean_valid = b; }
+  if (mask & AGG_COUNT) { PA_TRY(add(AGG_COUNT, "l", 8, false, &v, &b)); e.o_count = static_cast<int64_t*>(v); }
+  if (mask & AGG_MIN) { PA_TRY(add(AGG_MIN, vfmt, e.vw, true, &v, &b)); e.o_min = v; e.o_min_valid = b; }
+  if (mask & AGG_MAX) { PA_TRY(add(AGG_MAX, vfmt, e.vw, true, &v, &b)); e.o_max = v; e.o_max_valid = b; }
+  if (mask & AGG_FIRST) { PA_TRY(add(AGG_FIRST, vfmt, e.vw, true, &v, &b)); e.o_first = v; e.o_first_valid = b; }
+  if (mask & AGG_LAST) { PA_TRY(add(AGG_LAST, vfmt, e.vw, true, &v, &b)); e.o_last = v; e.o_last_valid = b; }
+  if (G > 0 && mask) {
+    k_emit<<<(G + 255) / 256, 256, 0, st>>>(e);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 1;
+  }
+  return PA_OK;
+}
+
+// ------------------------------ Arrow export ------------------------------
+struct ExportPriv {
+  void* bufs[2] = {nullptr, nullptr};
+  const void* ptrs[2] = {nullptr, nullptr};
+  std::string format;
+};
+
+void release_array(ArrowArray* a) {
+  auto* p = static_cast<ExportPriv*>(a->private_data);
+  if (p) {
+    free(p->bufs[0]);
+    free(p->bufs[1]);
+    delete p;
+  }
+  a->release = nullptr;
+}
+void release_schema(ArrowSchema* s) {
+  delete static_cast<std::string*>(s->private_data);
+  s->release = nullptr;
+}
+
+int export_host(cudaStream_t st, const std::string& format, int width, uint32_t G, const void* d_values,
+                const uint32_t* d_valid, ArrowArray* out, ArrowSchema* out_schema) {
+  auto* priv = new ExportPriv();
+  const size_t vbytes = static_cast<size_t>(G) * width;
+  priv->bufs[1] = malloc(std::max<size_t>(vbytes, 64));
+  const size_t words = (static_cast<size_t>(G) + 31) / 32;
+  int64_t null_count = 0;
+  if (G > 0) {
+    cudaError_t e = cudaMemcpyAsync(priv->bufs[1], d_values, vbytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && d_valid) {
+      priv->bufs[0] = malloc(std::max<size_t>(words * 4, 64));
+      e = cudaMemcpyAsync(priv->bufs[0], d_valid, words * 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      free(priv->bufs[0]); free(priv->bufs[1]); delete priv;
+      return set_err(PA_ERR_CUDA, "result copy failed: %s", cudaGetErrorString(e));
+    }
+    if (d_valid) {
+      const uint32_t* w = static_cast<const uint32_t*>(priv->bufs[0]);
+      int64_t set = 0;
+      for (size_t i = 0; i < words; ++i) set += __builtin_popcount(w[i]);
+      null_count = static_cast<int64_t>(G) - set;
+      if (null_count == 0) { free(priv->bufs[0]); priv->bufs[0] = nullptr; }
+    }
+  }
+  priv->ptrs[0] = priv->bufs[0];
+  priv->ptrs[1] = priv->bufs[1];
+  memset(out, 0, sizeof *out);
+  out->length = G;
+  out->null_count = null_count;
+  out->offset = 0;
+  out->n_buffers = 2;
+  out->buffers = priv->ptrs;
+  out->release = release_array;
+  out->private_data = priv;
+  memset(out_schema, 0, sizeof *out_schema);
+  auto* f = new std::string(format);
+  out_schema->format = f->c_str();
+  out_schema->name = "";
+  out_schema->flags = ARROW_FLAG_NULLABLE;
+  out_schema->release = release_schema;
+  out_schema->private_data = f;
+  return PA_OK;
+}
+
+int ensure_device(pa_groupby* g) {
+  CUDA_TRY(cudaSetDevice(g->device));
+  return PA_OK;
+}
+
+int bits_for(uint64_t n_values) {  // bits needed to represent values 0..n_values-1
+  int b = 1;
+  while (b < 64 && (1ull << b) < n_values) ++b;
+  return b;
+}
+
+int setup_keys(pa_groupby* g) {
+  const int nk = static_cast<int>(g->keys.size());
+  g->fields.assign(nk, KeyField{});
+  if (nk == 1) {
+    const Column& k = g->keys[0];
+    if (k.width != 4 && k.width != 8) return set_err(PA_ERR_INVALID, "key columns must be 32- or 64-bit (format '%s')", k.format.c_str());
+    g->packed = false;
+    g->key_data = k.data;
+    g->key_valid = k.valid;
+    g->key_bit_off = k.bit_off;
+    g->key_width = k.width;
+    g->fields[0].width = k.width;
+    return PA_OK;
+  }
+  if (nk > kMaxKeyCols) return set_err(PA_ERR_INVALID, "at most %d key columns", kMaxKeyCols);
+  int shift = 0;
+  KeyPackArgs a{};
+  for (int j = 0; j < nk; ++j) {
+    const Column& k = g->keys[j];
+    if (k.width != 4 && k.width != 8) return set_err(PA_ERR_INVALID, "key columns must be 32- or 64-bit (format '%s')", k.format.c_str());
+    KeyField& f = g->fields[j];
+    f.width = k.width;
+    f.bits = (k.is_dict && k.dict_len > 0) ? bits_for(static_cast<uint64_t>(k.dict_len)) : k.width * 8;
+    f.nullable = k.valid != nullptr;
+    f.shift = shift;
+    shift += f.bits + f.nullable;
+    a.col[j] = k.data; a.valid[j] = k.valid; a.off[j] = k.bit_off; a.width[j] = k.width;
+    a.bits[j] = f.bits; a.shift[j] = f.shift; a.nullable[j] = f.nullable;
+  }
+  if (shift > 64) return set_err(PA_ERR_NOT_IMPLEMENTED, "composite key needs %d bits; only keys that pack into 64 bits are supported", shift);
+  PA_TRY(g->packed_keys.alloc(static_cast<size_t>(g->n) * 8, g->stream));
+  a.n_cols = nk;
+  a.n = g->n;
+  a.out = g->packed_keys.as<uint64_t>();
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->n + 255) / 256, g->num_sms * 16)));
+  k_pack_keys<<<grid, 256, 0, g->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  g->packed = true;
+  g->key_data = g->packed_keys.p;
+  g->key_valid = nullptr;
+  g->key_bit_off = 0;
+  g->key_width = 8;
+  return PA_OK;
+}
+
+int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
+  cudaStream_t st = g->stream;
+  g->last_launches = 0;
+  const int vc = val ? val->vc : VC_I;
+  const bool wide = is_wide(mask, vc);
+  CUDA_TRY(cudaEventRecord(g->ev[0], st));
+  if (g->resample) {
+    CUDA_TRY(cudaEventRecord(g->ev[1], st));
+    PA_TRY(run_resample(g, val, mask, wide));
+    g->last_path = 3;
+  } else {
+    const bool lowcard_types = !val || val->width == 4 || val->width == 8;
+    const int gmax = wide ? LC_GMAX_WIDE : LC_GMAX_NARROW;
+    bool try_low = g->opt.path != PA_PATH_GLOBAL && lowcard_types &&
+                   (g->opt.expected_groups == 0 || g->opt.expected_groups <= gmax || g->opt.path == PA_PATH_LOWCARD);
+    bool done = false;
+    if (try_low) {
+      bool overflow = false;
+      PA_TRY(run_lowcard(g, val, mask, wide, &overflow));
+      if (!overflow) { done = true; g->last_path = PA_PATH_LOWCARD; }
+      else if (g->opt.path == PA_PATH_LOWCARD) return set_err(PA_ERR_INVALID, "more groups than the shared-memory path holds (%d)", gmax);
+    }
+    if (!done) {
+      PA_TRY(run_global(g, val, mask, wide));
+      g->last_path = PA_PATH_GLOBAL;
+    }
+  }
+  g->have_groups = true;
+  PA_TRY(run_emit(g, val, mask));
+  CUDA_TRY(cudaEventRecord(g->ev[4], st));
+  return PA_OK;
+}
+
+}  // namespace
+
+namespace {
+int run_resample(pa_groupby*, const Column*, uint32_t, bool) {
+  return set_err(PA_ERR_NOT_IMPLEMENTED, "resample path not built yet");
+}
+}  // namespace
+
+extern "C" {
+
+const char* pa_last_error(void) { return g_err.c_str(); }
+int pa_version(void) { return 100; }
+
+void pa_options_init(pa_options* opt) {
+  memset(opt, 0, sizeof *opt);
+  opt->device = -1;
+  opt->path = PA_PATH_AUTO;
+}
+
+int pa_device_count(int* out) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *out = 0; return set_err(PA_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+  *out = n;
+  return PA_OK;
+}
+
+static int handle_init(pa_groupby* g, const pa_options* opt) {
+  if (opt) g->opt = *opt; else pa_options_init(&g->opt);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err(PA_ERR_CUDA, "no CUDA device: pandasarrow_b200 has no CPU fallback");
+  if (g->opt.device < 0) CUDA_TRY(cudaGetDevice(&g->device)); else g->device = g->opt.device;
+  CUDA_TRY(cudaSetDevice(g->device));
+  CUDA_TRY(cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, g->device));
+  if (g->opt.cuda_stream) { g->stream = static_cast<cudaStream_t>(g->opt.cuda_stream); g->own_stream = false; }
+  else { CUDA_TRY(cudaStreamCreate(&g->stream)); g->own_stream = true; }
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g->device));
+  uint64_t keep = UINT64_MAX;
+  CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  for (auto& e : g->ev) CUDA_TRY(cudaEventCreate(&e));
+  PA_TRY(g->status.alloc(sizeof(uint32_t) * ST_WORDS, g->stream));
+  return PA_OK;
+}
+
+int pa_groupby_create(const struct ArrowDeviceArray* keys, const struct ArrowSchema* key_schemas, int32_t n_keys,
+                      const pa_options* opt, pa_groupby** out) {
+  if (!keys || !key_schemas || n_keys < 1 || !out) return set_err(PA_ERR_INVALID, "pa_groupby_create: null argument");
+  std::unique_ptr<pa_groupby> g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  g->keys.resize(n_keys);
+  for (int i = 0; i < n_keys; ++i) {
+    PA_TRY(load_column(&keys[i], &key_schemas[i], g->stream, g->device, &g->keys[i]));
+    if (g->keys[i].n != g->keys[0].n) return set_err(PA_ERR_INVALID, "key columns differ in length");
+  }
+  g->n = g->keys[0].n;
+  if (g->n >= 0xFFFFFFFEll) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-2 rows per call; shard by row range");
+  PA_TRY(setup_keys(g.get()));
+  *out = g.release();
+  return PA_OK;
+}
+
+static int ensure_groups(pa_groupby* g) {
+  if (g->have_groups) return PA_OK;
+  PA_TRY(ensure_device(g));
+  return aggregate_impl(g, nullptr, 0);
+}
+
+int pa_groupby_num_groups(pa_groupby* g, int64_t* out) {
+  if (!g || !out) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(ensure_groups(g));
+  *out = g->G;
+  return PA_OK;
+}
+
+int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  if (!g || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(ensure_groups(g));
+  PA_TRY(ensure_device(g));
+  if (g->resample) {
+    if (key_i != 0) return set_err(PA_ERR_INVALID, "key index %d out of range", key_i);
+    return export_host(g->stream, g->index_format, 8, g->G, g->res.key, nullptr, out, out_schema);
+  }
+  if (key_i < 0 || key_i >= static_cast<int>(g->keys.size())) return set_err(PA_ERR_INVALID, "key index %d out of range", key_i);
+  const KeyField& f = g->fields[key_i];
+  const uint32_t G = g->G;
+  DevBuf vals, valid;
+  PA_TRY(vals.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * f.width, g->stream));
+  PA_TRY(valid.alloc(((static_cast<size_t>(G) + 31) / 32 + 1) * 4, g->stream));
+  if (G > 0) {
+    KeyEmitArgs a{};
+    a.key = g->res.key; a.key_kind = g->res.key_kind; a.G = G;
+    a.width = f.width; a.bits = f.bits; a.shift = f.shift; a.nullable = f.nullable; a.packed = g->packed;
+    a.out = vals.p; a.out_valid = valid.as<uint32_t>();
+    k_emit_key<<<(G + 255) / 256, 256, 0, g->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return export_host(g->stream, g->keys[key_i].format, f.width, G, vals.p, valid.as<uint32_t>(), out, out_schema);
+}
+
+int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
+                         uint32_t agg_mask) {
+  if (!g || !values || !value_schema) return set_err(PA_ERR_INVALID, "null argument");
+  if (agg_mask == 0 || (agg_mask & ~PA_AGG_ALL)) return set_err(PA_ERR_INVALID, "bad aggregate mask 0x%x", agg_mask);
+  PA_TRY(ensure_device(g));
+  Column val;
+  PA_TRY(load_column(values, value_schema, g->stream, g->device, &val));
+  if (val.n != g->n) return set_err(PA_ERR_INVALID, "value column has %lld rows, keys have %lld", (long long)val.n, (long long)g->n);
+  if (value_schema->dictionary) return set_err(PA_ERR_INVALID, "dictionary-encoded value columns are not aggregatable");
+  const uint32_t prev_G = g->G;
+  const bool had = g->have_groups;
+  PA_TRY(aggregate_impl(g, &val, agg_mask));
+  if (had && prev_G != g->G) return set_err(PA_ERR_STATE, "group count changed between passes (%u vs %u)", prev_G, g->G);
+  // `val` may own device copies of host data: make sure the kernels reading them are done
+  if (val.own_data.p) CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return PA_OK;
+}
+
+int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  if (!g || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(ensure_device(g));
+  for (auto& o : g->outs) {
+    if (o.bit == agg_bit)
+      return export_host(g->stream, o.format, o.width, g->G, o.values.p, o.nullable ? o.valid.as<uint32_t>() : nullptr, out, out_schema);
+  }
+  return set_err(PA_ERR_STATE, "aggregate 0x%x was not part of the last pa_groupby_aggregate call", agg_bit);
+}
+
+int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  (void)g; (void)out; (void)out_schema;
+  return set_err(PA_ERR_NOT_IMPLEMENTED, "pa_groupby_row_ids: group materialisation is a SURVEY §8(f) 'next' row");
+}
+
+int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]) {
+  if (!g) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(ensure_device(g));
+  CUDA_TRY(cudaEventSynchronize(g->ev[4]));
+  float t = 0;
+  CUDA_TRY(cudaEventElapsedTime(&t, g->ev[0], g->ev[4]));
+  if (total_ms) *total_ms = t;
+  if (stage_ms) {
+    float a = 0, b = 0, c = 0, d = 0;
+    CUDA_TRY(cudaEventElapsedTime(&a, g->ev[0], g->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&b, g->ev[1], g->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&c, g->ev[2], g->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&d, g->ev[3], g->ev[4]));
+    stage_ms[0] = a; stage_ms[1] = b; stage_ms[2] = c; stage_ms[3] = d;
+  }
+  return PA_OK;
+}
+
+int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches) {
+  if (!g) return set_err(PA_ERR_INVALID, "null argument");
+  if (path) *path = g->last_path;
+  if (kernel_launches) *kernel_launches = g->last_launches;
+  return PA_OK;
+}
+
+int pa_groupby_sync(pa_groupby* g) {
+  if (!g) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(ensure_device(g));
+  CUDA_TRY(cudaStreamSynchronize(g->stream));
+  return PA_OK;
+}
+
+void pa_groupby_destroy(pa_groupby* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaStreamSynchronize(g->stream);
+  g->outs.clear();
+  cudaStream_t st = g->stream;
+  const bool own = g->own_stream;
+  for (auto& e : g->ev) if (e) cudaEventDestroy(e);
+  delete g;   // DevBufs free on `st`
+  if (own) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+}
+
+int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowSchema* index_schema, int64_t freq_ns,
+                       int32_t closed_right, int32_t label_right, int32_t origin, int64_t origin_custom_ns,
+                       int64_t offset_ns, const pa_options* opt, pa_groupby** out) {
+  (void)index; (void)index_schema; (void)freq_ns; (void)closed_right; (void)label_right; (void)origin;
+  (void)origin_custom_ns; (void)offset_ns; (void)opt; (void)out;
+  return set_err(PA_ERR_NOT_IMPLEMENTED, "resample path not built yet");
+}
+
+// ---- synthetic generator ----
+static int synth_grid(int64_t n) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(sms) * 16)));
+}
+int pa_synth_keys_i64(void* dev_out, int64_t n, int64_t first_row, uint64_t n_groups, uint64_t seed, void* cuda_stream) {
+  if (!dev_out || n_groups == 0) return set_err(PA_ERR_INVALID, "bad argument");
+  k_synth_keys<<<synth_grid(n), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(static_cast<int64_t*>(dev_out), n, first_row, n_groups, seed);
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;
+}
+int pa_synth_vals_f64(void* dev_out, int64_t n, int64_t first_row, uint64_t seed, void* cuda_stream) {
+  if (!dev_out) return set_err(PA_ERR_INVALID, "bad argument");
+  k_synth_vals<<<synth_grid(n), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(static_cast<double*>(dev_out), n, first_row, seed);
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;
+}
+int pa_synth_validity(void* dev_bitmap_out, int64_t n, int64_t first_row, uint64_t seed, uint32_t null_every, void* cuda_stream) {
+  if (!dev_bitmap_out || null_every == 0) return set_err(PA_ERR_INVALID, "bad argument");
+  k_synth_validity<<<synth_grid((n + 7) / 8), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(static_cast<uint8_t*>(dev_bitmap_out), n, first_row, seed, null_every);
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;
+}
+int pa_synth_timestamps(void* dev_out, int64_t n, int64_t first_row, int64_t t0_ns, int64_t step_ns, uint64_t seed, void* cuda_stream) {
+  if (!dev_out || step_ns <= 0) return set_err(PA_ERR_INVALID, "bad argument");
+  k_synth_ts<<<synth_grid(n), 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(static_cast<int64_t*>(dev_out), n, first_row, t0_ns, step_ns, seed);
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,30 @@
+// Device-side result of stages 1-3: one entry per group, first-appearance order.
+#pragma once
+#include "common.cuh"
+
+namespace pa {
+
+// key_kind values
+constexpr uint8_t KK_REGULAR = 0;   // key[] holds the packed 64-bit key
+constexpr uint8_t KK_NULL = 1;      // the null-key group (single-key mode)
+
+struct GroupResult {
+  uint64_t* key;        // packed key
+  uint8_t* key_kind;    // KK_*
+  uint64_t* sum;        // raw bits: double (VC_F) or wrapping (u)int64
+  double* dsum;         // sum of values converted to double (VC_I / VC_U mean); may be null for VC_F
+  uint32_t* count;      // non-null values
+  uint32_t* first_row;  // local row index of the first / last row of the group
+  uint32_t* last_row;
+  uint64_t* min_ord;    // order-mapped min / max over non-null, non-NaN values
+  uint64_t* max_ord;
+};
+
+// status words shared by the scan / merge kernels and read back by the host
+constexpr int ST_OVERFLOW = 0;   // table capacity exceeded -> caller retries on a bigger path
+constexpr int ST_NGROUPS = 1;
+constexpr int ST_UNSORTED = 2;   // resample: timestamps not sorted
+constexpr int ST_COUNTER = 3;    // scratch append counter
+constexpr int ST_WORDS = 8;
+
+}  // namespace pa

@@ -1,0 +1,537 @@
+// Low-cardinality path (stages 1-3 fused): one persistent CTA per SM.
+//
+//  * Every warp streams its own row chunks HBM -> shared memory with 1-D bulk async copies
+//    (cp.async.bulk, the TMA engine) through a private 3-stage mbarrier ring, so the memory
+//    pipeline depth does not depend on occupancy (8 warps / SM).
+//  * Keys are resolved to dense CTA-local group ids through a CTA-shared open-addressing table
+//    in shared memory (insert = one ATOMS.CAS.64 during warm-up, read-only afterwards).
+//  * Accumulators are WARP-PRIVATE arrays in shared memory, updated without atomics: lanes of a
+//    warp that hit the same group are combined first with a shuffle-based segmented reduction in
+//    ascending lane (= row) order, then the lowest lane does one read-modify-write.  The order of
+//    floating-point additions is therefore a fixed function of (n_rows, grid size): results are
+//    run-to-run deterministic.
+//  * At the end each CTA folds its warps in warp order and writes a partial table; a single-CTA
+//    merge kernel joins the partial tables by key, folds them in CTA order, ranks the groups by
+//    first row and writes the GroupResult.
+// If a CTA sees more than GMAX distinct keys the pass aborts (status[ST_OVERFLOW]) and the host
+// reruns the global-table path.
+//
+// Replaces Grouper::Consume + MakeGroupings + ApplyGroupings + per-group CallFunction
+// (/root/reference/src/dataframe.cpp:1571-1600, pd_core_macros.h:5-147).
+#pragma once
+#include "group_result.cuh"
+
+namespace pa {
+
+constexpr int LC_WARPS = 8;
+constexpr int LC_THREADS = LC_WARPS * 32;
+constexpr int LC_TCAP_LOG2 = 11;
+constexpr int LC_TCAP = 1 << LC_TCAP_LOG2;   // CTA key-table slots
+constexpr int LC_STAGES = 3;
+constexpr int LC_CHUNK = 256;                // rows per warp per stage
+constexpr uint32_t LC_UNSEEN = 0xFFFFFFFFu;  // count sentinel: warp has not met this id yet
+constexpr uint16_t LC_ID_UNSET = 0xFFFFu;
+constexpr uint16_t LC_ID_OVF = 0xFFFEu;
+constexpr uint32_t LC_NOID = 0xFFFFFFFFu;
+
+constexpr int LC_GMAX_NARROW = 1024;   // sum / mean / count / first  (12 B per id per warp)
+constexpr int LC_GMAX_WIDE = 320;      // + min / max / last / dsum    (40 B per id per warp)
+
+template <bool WIDE>
+struct LcCfg {
+  static constexpr int GMAX = WIDE ? LC_GMAX_WIDE : LC_GMAX_NARROW;
+  static constexpr int GP = GMAX + 2;             // + null-key group + (key == kEmptyKey) group
+  static constexpr int ID_NULL = GMAX;
+  static constexpr int ID_EMPTYKEY = GMAX + 1;
+};
+
+struct LcArgs {
+  const void* keys;
+  const void* vals;        // may be null (keys-only pass)
+  const uint8_t* kvalid;
+  const uint8_t* vvalid;
+  int64_t koff, voff;
+  int64_t n;
+  int64_t n_bulk;          // rows [0, n_bulk) are streamed with bulk copies (multiple of LC_CHUNK; 0 disables)
+  uint32_t agg_mask;
+  // per-CTA partial tables, [grid][GP]
+  uint64_t* p_key;
+  uint64_t* p_sum;
+  double* p_dsum;
+  uint32_t* p_count;
+  uint32_t* p_first;
+  uint32_t* p_last;
+  uint64_t* p_min;
+  uint64_t* p_max;
+  uint32_t* p_nids;        // [grid]
+  uint32_t* status;
+};
+
+template <bool WIDE>
+struct LcSmem {
+  using Cfg = LcCfg<WIDE>;
+  // byte offsets inside the dynamic shared memory block
+  static constexpr size_t stage_bytes(int kw, int vw) { return static_cast<size_t>(LC_CHUNK) * (kw + vw); }
+  static constexpr size_t OFF_BAR = 0;                                           // LC_WARPS*LC_STAGES u64
+  static constexpr size_t OFF_TKEYS = 256;                                       // LC_TCAP u64
+  static constexpr size_t OFF_TIDS = OFF_TKEYS + LC_TCAP * 8;                    // LC_TCAP u16
+  static constexpr size_t OFF_FIRST = OFF_TIDS + LC_TCAP * 2;                    // GP u32 (CTA shared)
+  static constexpr size_t OFF_MISC = OFF_FIRST + ((Cfg::GP * 4 + 15) / 16) * 16; // next_id, ovf
+  static constexpr size_t OFF_ACC = OFF_MISC + 16;
+  static constexpr size_t ACC_PER_ID = WIDE ? 40 : 12;
+  static constexpr size_t ACC_PER_WARP = ((Cfg::GP * ACC_PER_ID + 15) / 16) * 16;
+  static constexpr size_t OFF_STAGE = OFF_ACC + ACC_PER_WARP * LC_WARPS;
+  static constexpr size_t total(int kw, int vw) { return OFF_STAGE + stage_bytes(kw, vw) * LC_STAGES * LC_WARPS; }
+};
+
+// Warp-private accumulator views (struct-of-arrays inside the warp's block).
+template <bool WIDE>
+struct LcAcc {
+  using Cfg = LcCfg<WIDE>;
+  uint64_t* sum;   // GP
+  uint32_t* cnt;   // GP
+  uint32_t* last;  // GP (WIDE)
+  uint64_t* mn;    // GP (WIDE)
+  uint64_t* mx;    // GP (WIDE)
+  double* dsum;    // GP (WIDE)
+  __device__ __forceinline__ explicit LcAcc(unsigned char* base) {
+    sum = reinterpret_cast<uint64_t*>(base);
+    if constexpr (WIDE) {
+      mn = sum + Cfg::GP;
+      mx = mn + Cfg::GP;
+      dsum = reinterpret_cast<double*>(mx + Cfg::GP);
+      cnt = reinterpret_cast<uint32_t*>(dsum + Cfg::GP);
+      last = cnt + Cfg::GP;
+    } else {
+      cnt = reinterpret_cast<uint32_t*>(sum + Cfg::GP);
+      last = nullptr; mn = nullptr; mx = nullptr; dsum = nullptr;
+    }
+  }
+};
+
+// Resolve a key to its CTA-local dense id (insert on first sight).  LC_NOID on overflow.
+template <bool WIDE>
+__device__ __forceinline__ uint32_t lc_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
+                                               uint32_t* misc, uint32_t* status) {
+  using Cfg = LcCfg<WIDE>;
+  uint32_t slot = hash_key(key) >> (32 - LC_TCAP_LOG2);
+  for (int probe = 0; probe < LC_TCAP; ++probe) {
+    const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(tkeys + slot);
+    bool found = (k == key);
+    if (!found && k == kEmptyKey) {
+      const uint64_t old = atomicCAS(tkeys + slot, static_cast<unsigned long long>(kEmptyKey),
+                                     static_cast<unsigned long long>(key));
+      if (old == kEmptyKey) {  // this lane inserted the key: hand out the next dense id
+        const uint32_t nid = atomicAdd(misc, 1u);
+        if (nid >= static_cast<uint32_t>(Cfg::GMAX)) {
+          tids[slot] = LC_ID_OVF;
+          misc[1] = 1u;
+          atomicExch(status + ST_OVERFLOW, 1u);
+          return LC_NOID;
+        }
+        tids[slot] = static_cast<uint16_t>(nid);
+        return nid;
+      }
+      found = (old == key);
+    }
+    if (found) {
+      uint16_t id;
+      do { id = tids[slot]; } while (id == LC_ID_UNSET);   // inserter publishes the id right after its CAS
+      return id == LC_ID_OVF ? LC_NOID : id;
+    }
+    slot = (slot + 1) & (LC_TCAP - 1);
+  }
+  misc[1] = 1u;
+  atomicExch(status + ST_OVERFLOW, 1u);
+  return LC_NOID;
+}
+
+// Process 32 rows (one per lane).  All 32 lanes must call this (warp-synchronous).
+template <int VC, bool WIDE>
+__device__ __forceinline__ void lc_process_batch(bool active, uint64_t key, bool kvalid, uint64_t vbits, bool vvalid,
+                                                 uint32_t row, uint32_t agg_mask, unsigned long long* tkeys,
+                                                 volatile uint16_t* tids, uint32_t* cta_first, uint32_t* misc,
+                                                 uint32_t* status, const LcAcc<WIDE>& acc) {
+  using Cfg = LcCfg<WIDE>;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = lane_id();
+  uint32_t id = LC_NOID;
+  if (active) {
+    if (!kvalid) id = Cfg::ID_NULL;
+    else if (key == kEmptyKey) id = Cfg::ID_EMPTYKEY;
+    else id = lc_resolve<WIDE>(key, tkeys, tids, misc, status);
+  }
+  __syncwarp();
+  // ---- segmented reduction over lanes with equal id, ascending lane order ----
+  const uint32_t peers = __match_any_sync(FULL, id);
+  const uint32_t leader_lane = __ffs(peers) - 1;
+  uint64_t c_sum = 0;           // double bits (VC_F) or wrapping integer
+  uint32_t c_cnt = 0;
+  double c_dsum = 0.0;
+  uint64_t c_min = kMinInit, c_max = kMaxInit;
+  if (vvalid && id != LC_NOID) {
+    c_sum = vbits;
+    c_cnt = 1;
+    if constexpr (WIDE) {
+      if constexpr (VC != VC_F) c_dsum = Wide<VC>::as_double(vbits);
+      if (!Wide<VC>::is_nan(vbits)) { c_min = Wide<VC>::ord(vbits); c_max = c_min; }
+    }
+  } else if constexpr (VC == VC_F) {
+    c_sum = 0;  // +0.0
+  }
+  uint32_t rem = peers & ~(1u << leader_lane);
+  if (lane != leader_lane) rem = 0;  // only leaders pull
+  while (__any_sync(FULL, rem != 0)) {
+    const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
+    const uint64_t o_sum = __shfl_sync(FULL, c_sum, src);
+    const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, src);
+    double o_dsum = 0.0;
+    uint64_t o_min = kMinInit, o_max = kMaxInit;
+    if constexpr (WIDE) {
+      if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, src);
+      o_min = __shfl_sync(FULL, c_min, src);
+      o_max = __shfl_sync(FULL, c_max, src);
+    }
+    if (rem) {
+      if constexpr (VC == VC_F) {
+        c_sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(c_sum)) +
+                                                           __longlong_as_double(static_cast<long long>(o_sum))));
+      } else {
+        c_sum += o_sum;
+      }
+      c_cnt += o_cnt;
+      if constexpr (WIDE) {
+        c_dsum += o_dsum;
+        c_min = o_min < c_min ? o_min : c_min;
+        c_max = o_max > c_max ? o_max : c_max;
+      }
+      rem &= rem - 1;
+    }
+  }
+  // ---- one non-atomic read-modify-write per distinct id, by the lowest lane ----
+  if (lane == leader_lane && id != LC_NOID) {
+    uint32_t old = acc.cnt[id];
+    if (old == LC_UNSEEN) {  // first time this warp meets the id: candidate for the CTA's first row
+      old = 0;
+      atomicMin(cta_first + id, row);
+    }
+    acc.cnt[id] = old + c_cnt;
+    if constexpr (VC == VC_F) {
+      double* s = reinterpret_cast<double*>(acc.sum + id);
+      *s = *s + __longlong_as_double(static_cast<long long>(c_sum));
+    } else {
+      acc.sum[id] += c_sum;
+    }
+    if constexpr (WIDE) {
+      acc.last[id] = row + (31 - __clz(peers)) - lane;   // row of the highest peer lane
+      if constexpr (VC != VC_F) acc.dsum[id] += c_dsum;
+      if (c_min < acc.mn[id]) acc.mn[id] = c_min;
+      if (c_max > acc.mx[id]) acc.mx[id] = c_max;
+    }
+  }
+  __syncwarp();
+}
+
+template <int VC, int VW, int KW, bool WIDE>
+__global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
+  using Cfg = LcCfg<WIDE>;
+  using L = LcSmem<WIDE>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  unsigned long long* tkeys = reinterpret_cast<unsigned long long*>(smem + L::OFF_TKEYS);
+  volatile uint16_t* tids = reinterpret_cast<volatile uint16_t*>(smem + L::OFF_TIDS);
+  uint32_t* cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + L::OFF_MISC);   // [0] next id, [1] overflow seen
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  LcAcc<WIDE> acc(smem + L::OFF_ACC + L::ACC_PER_WARP * warp);
+  constexpr size_t STAGE_BYTES = static_cast<size_t>(LC_CHUNK) * (KW + VW);
+  unsigned char* my_stage = smem + L::OFF_STAGE + STAGE_BYTES * LC_STAGES * warp;
+  uint64_t* my_bar = bars + warp * LC_STAGES;
+
+  // ---- init shared state ----
+  for (int i = threadIdx.x; i < LC_TCAP; i += LC_THREADS) {
+    tkeys[i] = kEmptyKey;
+    tids[i] = LC_ID_UNSET;
+  }
+  for (int i = threadIdx.x; i < Cfg::GP; i += LC_THREADS) cta_first[i] = kNoRow;
+  if (threadIdx.x < 4) misc[threadIdx.x] = 0;
+  for (int i = lane; i < Cfg::GP; i += 32) {
+    acc.sum[i] = 0;
+    acc.cnt[i] = LC_UNSEEN;
+    if constexpr (WIDE) { acc.last[i] = 0; acc.mn[i] = kMinInit; acc.mx[i] = kMaxInit; acc.dsum[i] = 0.0; }
+  }
+  if (lane == 0) {
+    for (int s = 0; s < LC_STAGES; ++s) mbar_init(my_bar + s, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const bool have_vals = a.vals != nullptr;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * LC_WARPS + warp;
+  const int64_t nw = static_cast<int64_t>(gridDim.x) * LC_WARPS;
+  const int64_t nchunks = a.n_bulk / LC_CHUNK;
+  const char* kbase = static_cast<const char*>(a.keys);
+  const char* vbase = static_cast<const char*>(a.vals);
+
+  auto issue = [&](int64_t chunk, int s) {  // lane 0 only
+    unsigned char* dst = my_stage + STAGE_BYTES * s;
+    const uint32_t kbytes = LC_CHUNK * KW, vbytes = have_vals ? LC_CHUNK * VW : 0;
+    mbar_expect_tx(my_bar + s, kbytes + vbytes);
+    bulk_g2s(dst, kbase + chunk * (LC_CHUNK * KW), kbytes, my_bar + s);
+    if (have_vals) bulk_g2s(dst + LC_CHUNK * KW, vbase + chunk * (LC_CHUNK * VW), vbytes, my_bar + s);
+  };
+
+  // ---- streamed part: chunks gw, gw + nw, ... (fixed chunk -> warp map) ----
+  // Every issued bulk copy is waited for before the CTA may exit (also on overflow), so no copy
+  // can land in shared memory that already belongs to another CTA.
+  if (gw < nchunks) {
+    int64_t last_issued = gw;
+    for (int s = 0; s < LC_STAGES; ++s) {
+      const int64_t c = gw + static_cast<int64_t>(s) * nw;
+      if (c < nchunks) {
+        if (lane == 0) issue(c, s);
+        last_issued = c;
+      }
+    }
+    int s = 0;
+    uint32_t phase = 0;
+    for (int64_t c = gw; c <= last_issued; c += nw) {
+      mbar_wait(my_bar + s, phase);
+      const bool ovf = __any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(misc + 1) != 0 ||
+                                                   *reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW) != 0);
+      if (!ovf) {
+        const unsigned char* st = my_stage + STAGE_BYTES * s;
+        const int64_t row0 = c * LC_CHUNK;
+#pragma unroll 2
+        for (int b = 0; b < LC_CHUNK / 32; ++b) {
+          const int r = b * 32 + lane;
+          uint64_t key;
+          if constexpr (KW == 8) key = reinterpret_cast<const uint64_t*>(st)[r];
+          else key = reinterpret_cast<const uint32_t*>(st)[r];
+          uint64_t vb = 0;
+          bool vv = false;
+          const int64_t row = row0 + r;
+          if (have_vals) {
+            vb = load_wide<VC, VW>(st + LC_CHUNK * KW, r);
+            vv = a.vvalid ? bit_at(a.vvalid, a.voff + row) : true;
+          }
+          const bool kv = a.kvalid ? bit_at(a.kvalid, a.koff + row) : true;
+          lc_process_batch<VC, WIDE>(true, key, kv, vb, vv, static_cast<uint32_t>(row), a.agg_mask, tkeys, tids,
+                                     cta_first, misc, a.status, acc);
+        }
+      }
+      __syncwarp();
+      const int64_t cn = c + static_cast<int64_t>(LC_STAGES) * nw;
+      if (!ovf && cn < nchunks) {
+        if (lane == 0) {
+          fence_proxy_async();
+          issue(cn, s);
+        }
+        last_issued = cn;
+      }
+      if (++s == LC_STAGES) { s = 0; phase ^= 1; }
+    }
+  }
+
+  // ---- remainder rows [n_bulk, n): direct loads, warps of the whole grid take 32-row batches ----
+  for (int64_t r0 = a.n_bulk + gw * 32; r0 < a.n; r0 += nw * 32) {
+    if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(misc + 1) != 0)) break;
+    const int64_t row = r0 + lane;
+    const bool active = row < a.n;
+    uint64_t key = 0, vb = 0;
+    bool kv = true, vv = false;
+    if (active) {
+      key = load_key<KW>(a.keys, row);
+      if (a.kvalid) kv = bit_at(a.kvalid, a.koff + row);
+      if (have_vals) {
+        vb = load_wide<VC, VW>(a.vals, row);
+        vv = a.vvalid ? bit_at(a.vvalid, a.voff + row) : true;
+      }
+    }
+    lc_process_batch<VC, WIDE>(active, key, kv, vb, vv, static_cast<uint32_t>(row), a.agg_mask, tkeys, tids,
+                               cta_first, misc, a.status, acc);
+  }
+  __syncthreads();
+  if (misc[1]) return;
+
+  // ---- fold the warps in warp order and write this CTA's partial table ----
+  const size_t pbase = static_cast<size_t>(blockIdx.x) * Cfg::GP;
+  for (int id = threadIdx.x; id < Cfg::GP; id += LC_THREADS) {
+    uint64_t sum = 0;
+    double fsum = 0.0, dsum = 0.0;
+    uint32_t cnt = 0, last = 0;
+    uint64_t mn = kMinInit, mx = kMaxInit;
+    for (int w = 0; w < LC_WARPS; ++w) {
+      LcAcc<WIDE> o(smem + L::OFF_ACC + L::ACC_PER_WARP * w);
+      const uint32_t c = o.cnt[id];
+      if (c == LC_UNSEEN) continue;
+      cnt += c;
+      if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(o.sum[id]));
+      else sum += o.sum[id];
+      if constexpr (WIDE) {
+        dsum += o.dsum[id];
+        last = o.last[id] > last ? o.last[id] : last;
+        mn = o.mn[id] < mn ? o.mn[id] : mn;
+        mx = o.mx[id] > mx ? o.mx[id] : mx;
+      }
+    }
+    if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(fsum));
+    a.p_sum[pbase + id] = sum;
+    a.p_count[pbase + id] = cnt;
+    a.p_first[pbase + id] = cta_first[id];
+    if constexpr (WIDE) {
+      a.p_dsum[pbase + id] = dsum;
+      a.p_last[pbase + id] = last;
+      a.p_min[pbase + id] = mn;
+      a.p_max[pbase + id] = mx;
+    }
+  }
+  for (int slot = threadIdx.x; slot < LC_TCAP; slot += LC_THREADS) {
+    const uint16_t id = tids[slot];
+    if (id < Cfg::GMAX) a.p_key[pbase + id] = tkeys[slot];
+  }
+  if (threadIdx.x == 0) a.p_nids[blockIdx.x] = misc[0] < static_cast<uint32_t>(Cfg::GMAX) ? misc[0] : Cfg::GMAX;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge: one CTA.  Joins the per-CTA partial tables by key, folds them in CTA order, ranks the
+// merged groups by first row, writes the GroupResult and status[ST_NGROUPS].
+// ---------------------------------------------------------------------------------------------
+constexpr int LM_THREADS = 1024;
+constexpr int LM_TCAP_LOG2 = 12;
+constexpr int LM_TCAP = 1 << LM_TCAP_LOG2;
+
+struct LmArgs {
+  LcArgs part;          // partial tables written by the scan
+  int grid;             // number of scan CTAs
+  uint16_t* inv;        // [GP][grid] scratch, pre-filled with 0xFFFF: merged id, CTA -> CTA-local id
+  GroupResult out;
+  uint32_t* status;
+};
+
+template <int VC, bool WIDE>
+__global__ void __launch_bounds__(LM_THREADS, 1) k_lowcard_merge(LmArgs a) {
+  using Cfg = LcCfg<WIDE>;
+  __shared__ unsigned long long mkeys[LM_TCAP];
+  __shared__ uint16_t mids[LM_TCAP];
+  __shared__ uint32_t sfirst[Cfg::GP];
+  __shared__ uint32_t m_next, m_ovf;
+  if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) return;
+  for (int i = threadIdx.x; i < LM_TCAP; i += LM_THREADS) { mkeys[i] = kEmptyKey; mids[i] = LC_ID_UNSET; }
+  for (int i = threadIdx.x; i < Cfg::GP; i += LM_THREADS) sfirst[i] = kNoRow;
+  if (threadIdx.x == 0) { m_next = 0; m_ovf = 0; }
+  __syncthreads();
+  const int grid = a.grid;
+  // phase 1: join by key
+  for (int idx = threadIdx.x; idx < grid * Cfg::GMAX; idx += LM_THREADS) {
+    const int b = idx / Cfg::GMAX, id = idx - b * Cfg::GMAX;
+    if (static_cast<uint32_t>(id) >= a.part.p_nids[b]) continue;
+    const uint64_t key = a.part.p_key[static_cast<size_t>(b) * Cfg::GP + id];
+    uint32_t slot = hash_key(key) >> (32 - LM_TCAP_LOG2);
+    uint32_t mid = LC_NOID;
+    for (int probe = 0; probe < LM_TCAP; ++probe) {
+      const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(mkeys + slot);
+      bool found = (k == key);
+      if (!found && k == kEmptyKey) {
+        const uint64_t old = atomicCAS(mkeys + slot, static_cast<unsigned long long>(kEmptyKey),
+                                       static_cast<unsigned long long>(key));
+        if (old == kEmptyKey) {
+          const uint32_t nid = atomicAdd(&m_next, 1u);
+          if (nid >= static_cast<uint32_t>(Cfg::GMAX)) { m_ovf = 1; *reinterpret_cast<volatile uint16_t*>(mids + slot) = LC_ID_OVF; break; }
+          *reinterpret_cast<volatile uint16_t*>(mids + slot) = static_cast<uint16_t>(nid);
+          mid = nid;
+          break;
+        }
+        found = (old == key);
+      }
+      if (found) {
+        uint16_t v;
+        do { v = *reinterpret_cast<volatile uint16_t*>(mids + slot); } while (v == LC_ID_UNSET);
+        mid = (v == LC_ID_OVF) ? LC_NOID : v;
+        break;
+      }
+      slot = (slot + 1) & (LM_TCAP - 1);
+    }
+    if (mid != LC_NOID) a.inv[static_cast<size_t>(mid) * grid + b] = static_cast<uint16_t>(id);
+  }
+  __syncthreads();
+  if (m_ovf) {
+    if (threadIdx.x == 0) atomicExch(a.status + ST_OVERFLOW, 1u);
+    return;
+  }
+  const int M = m_next;
+  __threadfence_block();
+  __syncthreads();
+  // phase 2: fold partials in CTA order (merged groups M and M+1 are the two special groups);
+  // up to two merged groups per thread (GMAX + 2 may exceed the block size)
+  constexpr int U = (Cfg::GP + LM_THREADS - 1) / LM_THREADS;
+  uint64_t r_sum[U], r_key[U], r_min[U], r_max[U];
+  double r_dsum[U];
+  uint32_t r_cnt[U], r_first[U], r_last[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int m = threadIdx.x + u * LM_THREADS;
+    r_sum[u] = 0; r_key[u] = 0; r_min[u] = kMinInit; r_max[u] = kMaxInit; r_dsum[u] = 0.0;
+    r_cnt[u] = 0; r_first[u] = kNoRow; r_last[u] = 0;
+    if (m >= M + 2) continue;
+    double fsum = 0.0;
+    for (int b = 0; b < grid; ++b) {
+      int id;
+      if (m < M) {
+        const uint16_t v = a.inv[static_cast<size_t>(m) * grid + b];
+        if (v == LC_ID_UNSET) continue;
+        id = v;
+      } else {
+        id = (m == M) ? Cfg::ID_NULL : Cfg::ID_EMPTYKEY;
+      }
+      const size_t p = static_cast<size_t>(b) * Cfg::GP + id;
+      const uint32_t f = a.part.p_first[p];
+      if (f == kNoRow) continue;
+      if (m < M) r_key[u] = a.part.p_key[p];
+      r_first[u] = f < r_first[u] ? f : r_first[u];
+      r_cnt[u] += a.part.p_count[p];
+      if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(a.part.p_sum[p]));
+      else r_sum[u] += a.part.p_sum[p];
+      if constexpr (WIDE) {
+        r_dsum[u] += a.part.p_dsum[p];
+        const uint32_t l = a.part.p_last[p];
+        r_last[u] = l > r_last[u] ? l : r_last[u];
+        const uint64_t mn = a.part.p_min[p], mx = a.part.p_max[p];
+        r_min[u] = mn < r_min[u] ? mn : r_min[u];
+        r_max[u] = mx > r_max[u] ? mx : r_max[u];
+      }
+    }
+    if constexpr (VC == VC_F) r_sum[u] = static_cast<uint64_t>(__double_as_longlong(fsum));
+    if (m == M + 1) r_key[u] = kEmptyKey;
+    sfirst[m] = r_first[u];
+  }
+  __syncthreads();
+  // phase 3: rank by first row (first rows are distinct: a row belongs to exactly one group)
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int m = threadIdx.x + u * LM_THREADS;
+    if (m >= M + 2 || r_first[u] == kNoRow) continue;
+    uint32_t rank = 0;
+    for (int j = 0; j < M + 2; ++j) rank += sfirst[j] < r_first[u];
+    a.out.key[rank] = r_key[u];
+    a.out.key_kind[rank] = (m == M) ? KK_NULL : KK_REGULAR;
+    a.out.sum[rank] = r_sum[u];
+    a.out.count[rank] = r_cnt[u];
+    a.out.first_row[rank] = r_first[u];
+    if constexpr (WIDE) {
+      a.out.last_row[rank] = r_last[u];
+      a.out.min_ord[rank] = r_min[u];
+      a.out.max_ord[rank] = r_max[u];
+      if (a.out.dsum) a.out.dsum[rank] = r_dsum[u];
+    }
+  }
+  if (threadIdx.x == 0) {
+    uint32_t G = M;
+    G += sfirst[M] != kNoRow;
+    G += sfirst[M + 1] != kNoRow;
+    a.status[ST_NGROUPS] = G;
+  }
+}
+
+}  // namespace pa

@@ -1,0 +1,343 @@
+"""Host-side harness over the C ABI, shaped like the reference's classes:
+
+    pd::GroupBy   (/root/reference/src/group_by.h:22-247)    -> GroupBy
+    pd::Resampler (/root/reference/src/group_by.h:255-299)   -> Resampler
+    pd::resample  (/root/reference/src/resample.h:91-122)    -> resample()
+
+Method names, argument meaning (a column name -> one array, a list of names -> one array per name
+indexed by the unique keys) and error behaviour follow the reference.  Everything computes in
+libpa_b200.so on the GPU; columns may be pyarrow arrays (host memory, copied by the library) or
+DeviceColumn views of CUDA memory (zero copy).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Union
+
+import pyarrow as pa
+
+from . import _lib
+from ._lib import (ARROW_DEVICE_CPU, ARROW_DEVICE_CUDA, PA_AGG, ArrowArray, ArrowDeviceArray, ArrowSchema,
+                   PaOptions)
+
+_RELEASE_ARRAY = C.CFUNCTYPE(None, C.POINTER(ArrowArray))
+_RELEASE_SCHEMA = C.CFUNCTYPE(None, C.POINTER(ArrowSchema))
+_PATHS = {"auto": 0, "lowcard": 1, "global": 2}
+ORIGIN = {"epoch": 0, "start": 1, "start_day": 2, "end": 3, "end_day": 4, "custom": 5}
+
+
+class PaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[pa_b200 {code}] {msg}")
+        self.code = code
+
+
+def _check(rc):
+    if rc != 0:
+        raise PaError(rc, _lib.load().pa_last_error().decode())
+
+
+class DeviceColumn:
+    """A primitive Arrow column whose buffers live in CUDA memory (borrowed, not owned)."""
+
+    def __init__(self, data_ptr: int, length: int, fmt: str, device_id: int = 0, valid_ptr: Optional[int] = None,
+                 null_count: int = 0, offset: int = 0, keepalive=None):
+        self.data_ptr, self.length, self.fmt, self.device_id = int(data_ptr), int(length), fmt, int(device_id)
+        self.valid_ptr, self.null_count, self.offset = valid_ptr, int(null_count), int(offset)
+        self.keepalive = keepalive
+
+    @staticmethod
+    def from_torch(t, fmt: Optional[str] = None, valid=None, null_count: int = 0) -> "DeviceColumn":
+        import torch
+        fmts = {torch.int64: "l", torch.float64: "g", torch.int32: "i", torch.float32: "f",
+                torch.int16: "s", torch.int8: "c", torch.uint8: "C"}
+        assert t.is_cuda and t.is_contiguous()
+        return DeviceColumn(t.data_ptr(), t.numel(), fmt or fmts[t.dtype], t.device.index,
+                            valid_ptr=None if valid is None else valid.data_ptr(), null_count=null_count,
+                            keepalive=(t, valid))
+
+
+class _CArg:
+    """ArrowDeviceArray + ArrowSchema pair ready to pass to the library; releases exports on close."""
+
+    def __init__(self, col):
+        self.dev = ArrowDeviceArray()
+        self.schema = ArrowSchema()
+        self._exported = False
+        self._keep = []
+        if isinstance(col, DeviceColumn):
+            bufs = (C.c_void_p * 2)(col.valid_ptr, col.data_ptr)
+            fmt = C.c_char_p(col.fmt.encode())
+            self._keep += [bufs, fmt, col.keepalive]
+            a = self.dev.array
+            a.length, a.null_count, a.offset, a.n_buffers, a.n_children = col.length, col.null_count, col.offset, 2, 0
+            a.buffers = C.cast(bufs, C.POINTER(C.c_void_p))
+            self.dev.device_id, self.dev.device_type = col.device_id, ARROW_DEVICE_CUDA
+            self.schema.format = fmt
+            self.schema.name = b""
+            self.schema.flags = 2
+        else:
+            if isinstance(col, pa.ChunkedArray):
+                col = col.combine_chunks()
+            if not isinstance(col, pa.Array):
+                col = pa.array(col)
+            col._export_to_c(C.addressof(self.dev), C.addressof(self.schema))
+            self._keep.append(col)
+            self._exported = True
+            self.dev.device_id, self.dev.device_type = -1, ARROW_DEVICE_CPU
+
+    def close(self):
+        if self._exported:
+            if self.dev.array.release:
+                _RELEASE_ARRAY(self.dev.array.release)(C.byref(self.dev.array))
+            if self.schema.release:
+                _RELEASE_SCHEMA(self.schema.release)(C.byref(self.schema))
+            self._exported = False
+
+
+def _pack_args(cols):
+    args = [_CArg(c) for c in cols]
+    devs = (ArrowDeviceArray * len(args))()
+    schemas = (ArrowSchema * len(args))()
+    for i, a in enumerate(args):
+        C.memmove(C.addressof(devs[i]), C.addressof(a.dev), C.sizeof(ArrowDeviceArray))
+        C.memmove(C.addressof(schemas[i]), C.addressof(a.schema), C.sizeof(ArrowSchema))
+    return args, devs, schemas
+
+
+def _import(out_a, out_s) -> pa.Array:
+    return pa.Array._import_from_c(C.addressof(out_a), C.addressof(out_s))
+
+
+def _options(expected_groups=0, path="auto", device=None, stream=None) -> PaOptions:
+    o = PaOptions()
+    _lib.load().pa_options_init(C.byref(o))
+    o.expected_groups = int(expected_groups)
+    o.path = _PATHS[path]
+    if device is not None:
+        o.device = int(device)
+    if stream is not None:
+        o.cuda_stream = int(stream)
+    return o
+
+
+Column = Union[pa.Array, DeviceColumn]
+
+
+class GroupBy:
+    """pd::GroupBy: hash group-by on one (or several 64-bit-packable) key column(s).
+
+    `frame` maps column names to columns (pyarrow RecordBatch/Table, or a dict of pa.Array /
+    DeviceColumn); `key` names the key column(s) — or pass key arrays directly with `key_arrays`
+    (DataFrame::group_by(ArrayPtr), dataframe.cpp:1231-1235)."""
+
+    def __init__(self, key, frame=None, *, key_arrays: Optional[Sequence[Column]] = None, expected_groups: int = 0,
+                 path: str = "auto", device: Optional[int] = None, stream: Optional[int] = None, _handle=None):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self._frame = self._as_dict(frame)
+        self._dicts: List[Optional[pa.Array]] = []
+        if _handle is not None:
+            self._h = _handle
+            self.key_names = ["__resampler_idx__"]
+            self._dicts = [None]
+            return
+        self.key_names = [key] if isinstance(key, str) else list(key)
+        if key_arrays is None:
+            try:
+                key_arrays = [self._frame[k] for k in self.key_names]
+            except KeyError as e:
+                raise RuntimeError(f"Invalid column: {e.args[0]}")   # std::runtime_error in the reference ctor
+        key_arrays = [self._normalise_key(k) for k in key_arrays]
+        args, devs, schemas = _pack_args(key_arrays)
+        self._key_args = args          # keys are borrowed until destroy
+        opt = _options(expected_groups, path, device, stream)
+        try:
+            _check(self._L.pa_groupby_create(devs, schemas, len(args), C.byref(opt), C.byref(self._h)))
+        except Exception:
+            for a in args:
+                a.close()
+            raise
+
+    def _normalise_key(self, k):
+        if isinstance(k, pa.ChunkedArray):
+            k = k.combine_chunks()
+        if isinstance(k, pa.Array) and (pa.types.is_string(k.type) or pa.types.is_large_string(k.type)):
+            # utf8 keys are dictionary-encoded first (a data-format conversion, first-appearance ordered);
+            # hashing raw strings on the GPU is a SURVEY §8(f) "next" row.
+            k = k.dictionary_encode()
+        self._dicts.append(k.dictionary if isinstance(k, pa.DictionaryArray) else None)
+        return k
+
+    @staticmethod
+    def _as_dict(frame) -> Dict[str, Column]:
+        if frame is None:
+            return {}
+        if isinstance(frame, (pa.RecordBatch, pa.Table)):
+            return {n: frame.column(n) for n in frame.schema.names}
+        return dict(frame)
+
+    # ---- lifetime ----
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.pa_groupby_destroy(self._h)
+            self._h = C.c_void_p()
+            for a in getattr(self, "_key_args", []):
+                a.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- group_by.h:33-60 ----
+    def groupSize(self) -> int:
+        n = C.c_int64()
+        _check(self._L.pa_groupby_num_groups(self._h, C.byref(n)))
+        return n.value
+
+    num_groups = property(groupSize)
+
+    def unique(self, key_i: int = 0) -> pa.Array:
+        a, s = ArrowArray(), ArrowSchema()
+        _check(self._L.pa_groupby_unique(self._h, key_i, C.byref(a), C.byref(s)))
+        out = _import(a, s)
+        d = self._dicts[key_i] if key_i < len(self._dicts) else None
+        if d is not None:
+            out = pa.DictionaryArray.from_arrays(out, d)
+        return out
+
+    # ---- aggregation core ----
+    def aggregate(self, values: Column, aggs: Sequence[str], fetch: bool = True) -> Dict[str, pa.Array]:
+        mask = 0
+        for a in aggs:
+            mask |= PA_AGG[a]
+        arg = _CArg(values)
+        try:
+            _check(self._L.pa_groupby_aggregate(self._h, C.byref(arg.dev), C.byref(arg.schema), mask))
+        finally:
+            arg.close()
+        if not fetch:
+            return {}
+        return {a: self.fetch(a) for a in aggs}
+
+    def fetch(self, agg: str) -> pa.Array:
+        a, s = ArrowArray(), ArrowSchema()
+        _check(self._L.pa_groupby_fetch(self._h, PA_AGG[agg], C.byref(a), C.byref(s)))
+        return _import(a, s)
+
+    def sync(self):
+        _check(self._L.pa_groupby_sync(self._h))
+
+    def timing(self) -> dict:
+        total = C.c_double()
+        st = (C.c_double * 4)()
+        _check(self._L.pa_groupby_last_timing(self._h, C.byref(total), st))
+        path, launches = C.c_int32(), C.c_int32()
+        _check(self._L.pa_groupby_last_path(self._h, C.byref(path), C.byref(launches)))
+        return {"total_ms": total.value, "pack_ms": st[0], "scan_ms": st[1], "merge_ms": st[2], "emit_ms": st[3],
+                "path": {1: "lowcard", 2: "global", 3: "resample"}.get(path.value, "?"), "launches": launches.value}
+
+    # ---- the reference's method surface (group_by.h:85-139): name -> array, [names] -> {name: array} ----
+    def _agg(self, agg: str, arg):
+        if isinstance(arg, str):
+            return self.aggregate(self._column(arg), [agg])[agg]
+        if isinstance(arg, (list, tuple)):
+            return {name: self.aggregate(self._column(name), [agg])[agg] for name in arg}
+        return self.aggregate(arg, [agg])[agg]        # a column object
+
+    def _column(self, name: str):
+        try:
+            return self._frame[name]
+        except KeyError:
+            raise RuntimeError(f"Invalid column: {name}")
+
+    def sum(self, arg): return self._agg("sum", arg)
+    def mean(self, arg): return self._agg("mean", arg)
+    def count(self, arg): return self._agg("count", arg)
+    def min(self, arg): return self._agg("min", arg)
+    def max(self, arg): return self._agg("max", arg)
+    def first(self, arg): return self._agg("first", arg)
+    def last(self, arg): return self._agg("last", arg)
+
+    def min_max(self, arg):
+        """GroupBy::min_max (dataframe.cpp:1602-1696): one pass, two columns."""
+        if isinstance(arg, str):
+            r = self.aggregate(self._column(arg), ["min", "max"])
+            return {"min": r["min"], "max": r["max"]}
+        out = {}
+        for name in arg:
+            r = self.aggregate(self._column(name), ["min", "max"])
+            out[name + "_min"], out[name + "_max"] = r["min"], r["max"]
+        return out
+
+
+class Resampler(GroupBy):
+    """pd::Resampler (group_by.h:255-299): every aggregate runs over all columns of the frame and
+    the result is indexed by the bucket labels (`index()`)."""
+
+    def index(self) -> pa.Array:
+        return self.unique()
+
+    def data(self):
+        return self._frame
+
+    def _all(self, agg):
+        return {name: self.aggregate(col, [agg])[agg] for name, col in self._frame.items()}
+
+    def sum(self, arg=None): return self._all("sum") if arg is None else super().sum(arg)
+    def mean(self, arg=None): return self._all("mean") if arg is None else super().mean(arg)
+    def count(self, arg=None): return self._all("count") if arg is None else super().count(arg)
+    def min(self, arg=None): return self._all("min") if arg is None else super().min(arg)
+    def max(self, arg=None): return self._all("max") if arg is None else super().max(arg)
+    def first(self, arg=None): return self._all("first") if arg is None else super().first(arg)
+    def last(self, arg=None): return self._all("last") if arg is None else super().last(arg)
+
+
+def resample(frame, index: Column, freq_ns: int, closed_right: bool = False, label_right: bool = False,
+             origin: str = "start_day", origin_custom_ns: int = 0, offset_ns: int = 0, *, device=None,
+             stream=None) -> Resampler:
+    """pd::resample(df, time_duration rule, ...) (resample.h:91-122) on a sorted timestamp index."""
+    L = _lib.load()
+    arg = _CArg(index)
+    h = C.c_void_p()
+    opt = _options(0, "auto", device, stream)
+    try:
+        _check(L.pa_resample_create(C.byref(arg.dev), C.byref(arg.schema), int(freq_ns), int(closed_right),
+                                    int(label_right), ORIGIN[origin], int(origin_custom_ns), int(offset_ns),
+                                    C.byref(opt), C.byref(h)))
+    except Exception:
+        arg.close()
+        raise
+    r = Resampler(None, frame, _handle=h)
+    r._key_args = [arg]
+    return r
+
+
+class synth:
+    """Device-side synthetic workload; mirrors bench.py's host generator."""
+    SEED_K, SEED_V, SEED_N, SEED_T = 42, 1337, 7, 99
+    T0_NS = 1577836800 * 10**9
+
+    @staticmethod
+    def keys(t, n_groups: int, first_row: int = 0, seed: int = SEED_K):
+        _check(_lib.load().pa_synth_keys_i64(t.data_ptr(), t.numel(), first_row, n_groups, seed, None))
+
+    @staticmethod
+    def vals(t, first_row: int = 0, seed: int = SEED_V):
+        _check(_lib.load().pa_synth_vals_f64(t.data_ptr(), t.numel(), first_row, seed, None))
+
+    @staticmethod
+    def validity(t, n_rows: int, first_row: int = 0, seed: int = SEED_N, null_every: int = 10):
+        _check(_lib.load().pa_synth_validity(t.data_ptr(), n_rows, first_row, seed, null_every, None))
+
+    @staticmethod
+    def timestamps(t, first_row: int = 0, t0_ns: int = T0_NS, step_ns: int = 60_000, seed: int = SEED_T):
+        _check(_lib.load().pa_synth_timestamps(t.data_ptr(), t.numel(), first_row, t0_ns, step_ns, seed, None))

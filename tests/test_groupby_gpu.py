@@ -1,0 +1,251 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Needs a GPU: -m gpu."""
+import os
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["sum", "mean", "count", "min", "max", "first", "last"]
+NARROW = ["sum", "mean", "count", "first"]
+
+
+@pytest.fixture(scope="module")
+def pab():
+    import pandasarrow_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _both(pab, orc, frame, key, **kw):
+    rb = frame if isinstance(frame, pa.RecordBatch) else pa.record_batch(frame)
+    return pab.GroupBy(key, rb, **kw), orc.OracleGroupBy(rb, key), rb
+
+
+# ---------------- the reference's own golden vectors, through the C ABI ----------------
+def test_reference_golden_people(pab):
+    # /root/reference/tests/cudf_examples/dataframe_resample_test.cpp:71-250
+    ids = ["allen", "victor", "hannah", "allen", "victor", "hannah", "allen", "victor", "hannah", "allen"]
+    gender = ["male", "female", "male", "male", "female", "male", "male", "female", "male", "male"]
+    rb = pa.record_batch({"id": pa.array(ids), "gender": pa.array(gender),
+                          "age": pa.array([16, 10, 10, 20, 30, 40, 15, 25, 35, 45], pa.int32()),
+                          "height": pa.array([9, 9, 9, 9, 9, 8, 8, 8, 8, 8], pa.int32())})
+    g = pab.GroupBy("gender", rb)
+    assert g.groupSize() == 2
+    assert g.unique().to_pylist() == ["male", "female"]
+    m = g.mean(["age", "height"])
+    assert m["age"].to_pylist() == [25.857142857142858, 21.666666666666668]
+    assert m["height"].to_pylist() == [8.428571428571429, 8.666666666666666]
+    mm = g.min_max("age")
+    assert mm["min"].type == pa.int32() and mm["min"].to_pylist() == [10, 10] and mm["max"].to_pylist() == [45, 30]
+    mm = g.min_max(["age", "height"])
+    assert mm["height_min"].to_pylist() == [8, 8] and mm["height_max"].to_pylist() == [9, 9]
+    assert g.max("age").to_pylist() == [45, 30] and g.min("age").to_pylist() == [10, 10]
+    s = g.sum(["age", "height"])
+    assert s["age"].type == pa.int64() and s["age"].to_pylist() == [181, 65] and s["height"].to_pylist() == [59, 26]
+    c = g.count("age")
+    assert c.type == pa.int64() and c.to_pylist() == [7, 3]
+    g2 = pab.GroupBy("id", rb)
+    assert g2.unique().to_pylist() == ["allen", "victor", "hannah"]   # :38-41 first-appearance order
+
+
+def test_reference_golden_apply_sums_and_ohlc(pab):
+    # dataframe_iterator_test.cpp:11-76
+    rb = pa.record_batch({"a": pa.array([1, 1, 3, 1, 1, 1, 3, 8, 2, 2], pa.int32()),
+                          "b": pa.array([10, 9, 8, 7, 6, 5, 4, 3, 2, 1], pa.int32())})
+    g = pab.GroupBy("a", rb)
+    assert g.groupSize() == 4 and g.unique().to_pylist() == [1, 3, 8, 2]
+    assert g.sum("a").to_pylist() == [5, 6, 8, 4] and g.sum("b").to_pylist() == [37, 12, 3, 3]
+    # cudf_examples/dataframe_resample_test.cpp:252-305
+    f32 = lambda xs: [float(np.float32(x)) for x in xs]
+    rb = pa.record_batch({
+        "high": pa.array([11.1, 20.2, 21.0, 15, 20], pa.float32()), "low": pa.array([9.1, 9.2, 10.0, 5, 10], pa.float32()),
+        "close": pa.array([10.1, 15.2, 20.0, 15, 15], pa.float32()), "open": pa.array([10, 20.2, 10.0, 15, 10], pa.float32()),
+        "volume": pa.array([100, 200, 210, 1, 2], pa.uint64()), "day": pa.array([1, 1, 2, 2, 5], pa.int64())})
+    g = pab.GroupBy("day", rb)
+    assert g.unique().to_pylist() == [1, 2, 5]
+    assert g.first("open").to_pylist() == f32([10, 10.0, 10]) and g.last("close").to_pylist() == f32([15.2, 15, 15])
+    assert g.max("high").to_pylist() == f32([20.2, 21.0, 20]) and g.min("low").to_pylist() == f32([9.1, 5, 10])
+    v = g.sum("volume")
+    assert v.type == pa.uint64() and v.to_pylist() == [300, 211, 2]
+
+
+# ---------------- seeded parity against the oracle ----------------
+@pytest.mark.parametrize("path", ["auto", "global"])
+@pytest.mark.parametrize("n,G", [(1_000_000, 1000), (300_000, 16), (300_000, 256), (500_007, 4096),
+                                 (600_000, 65536), (400_000, 250_000)])
+def test_config1_2_int64_key_f64_val(pab, orc, path, n, G):
+    from pandasarrow_b200 import hostgen as hg
+    from util import compare_all
+    frame = {"k": pa.array(hg.keys(n, G)), "v": pa.array(hg.vals(n))}
+    gb, ora, rb = _both(pab, orc, frame, "k", path=path, expected_groups=G if path == "global" else 0)
+    assert gb.groupSize() == ora.num_groups
+    compare_all(gb, ora, rb, "v", ["sum", "mean", "count"], f"n={n} G={G} {path} narrow")
+    t = gb.timing()
+    if path == "auto" and G <= 1000:
+        assert t["path"] == "lowcard"
+    compare_all(gb, ora, rb, "v", ALL, f"n={n} G={G} {path} all")
+    # count invariants: sum of counts = n
+    assert sum(gb.count("v").to_pylist()) == n
+
+
+@pytest.mark.parametrize("path", ["auto", "global"])
+@pytest.mark.parametrize("vtype", [pa.float64(), pa.float32(), pa.int64(), pa.int32(), pa.uint64(), pa.uint32(),
+                                   pa.int16(), pa.uint8()])
+def test_value_types_with_nulls(pab, orc, path, vtype):
+    from util import compare_all
+    rng = np.random.default_rng(5)
+    n, G = 200_003, 300
+    k = rng.integers(0, G, n)
+    if pa.types.is_floating(vtype):
+        v = rng.standard_normal(n) * 1e3
+    elif pa.types.is_unsigned_integer(vtype):
+        v = rng.integers(0, 200, n)
+    else:
+        v = rng.integers(-100, 100, n)
+    mask = rng.random(n) < 0.1
+    # one group is all-null
+    mask |= (k == 7)
+    frame = {"k": pa.array(k, pa.int64()), "v": pa.array(v, vtype, mask=mask)}
+    gb, ora, rb = _both(pab, orc, frame, "k", path=path)
+    compare_all(gb, ora, rb, "v", ALL, f"{vtype} {path}")
+
+
+@pytest.mark.parametrize("path", ["auto", "global"])
+def test_null_keys_int32_key_and_sentinel_key(pab, orc, path):
+    from util import compare_all
+    rng = np.random.default_rng(11)
+    n = 100_001
+    k = rng.integers(-50, 50, n).astype(np.int32)
+    kmask = rng.random(n) < 0.01
+    frame = {"k": pa.array(k, pa.int32(), mask=kmask), "v": pa.array(rng.random(n))}
+    gb, ora, rb = _both(pab, orc, frame, "k", path=path)
+    compare_all(gb, ora, rb, "v", ALL, f"int32 nullable key {path}")
+    # a real key equal to the table's empty sentinel, INT64_MIN/MAX, -1, 0
+    sentinel = np.array([0x9E3779B97F4A7C15], dtype=np.uint64).view(np.int64)[0]
+    special = np.array([sentinel, np.iinfo(np.int64).min, np.iinfo(np.int64).max, -1, 0], dtype=np.int64)
+    k = special[rng.integers(0, len(special), n)]
+    frame = {"k": pa.array(k), "v": pa.array(rng.random(n))}
+    gb, ora, rb = _both(pab, orc, frame, "k", path=path)
+    compare_all(gb, ora, rb, "v", ALL, f"sentinel keys {path}")
+    # uint64 keys and timestamp keys
+    frame = {"k": pa.array(k.view(np.uint64)), "v": pa.array(rng.random(n))}
+    gb, ora, rb = _both(pab, orc, frame, "k", path=path)
+    compare_all(gb, ora, rb, "v", NARROW, f"uint64 keys {path}")
+    frame = {"k": pa.array(np.abs(k) % 1000, pa.timestamp("ns")), "v": pa.array(rng.random(n))}
+    gb, ora, rb = _both(pab, orc, frame, "k", path=path)
+    compare_all(gb, ora, rb, "v", NARROW, f"timestamp keys {path}")
+
+
+@pytest.mark.parametrize("path", ["auto", "global"])
+def test_nan_inf_and_all_nan_groups(pab, orc, path):
+    from util import compare_all
+    k = pa.array([1, 1, 2, 2, 3, 3, 4, 4, 5], pa.int64())
+    v = pa.array([1.0, float("nan"), float("nan"), float("nan"), float("inf"), 1.0, float("-inf"), float("inf"), None])
+    gb, ora, rb = _both(pab, orc, {"k": k, "v": v}, "k", path=path)
+    compare_all(gb, ora, rb, "v", ALL, f"nan/inf {path}")
+
+
+@pytest.mark.parametrize("path", ["auto", "global"])
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 256, 257, 1023, 4097])
+def test_edge_sizes(pab, orc, path, n):
+    from util import compare_all
+    rng = np.random.default_rng(n)
+    frame = {"k": pa.array(rng.integers(0, 5, n), pa.int64()), "v": pa.array(rng.random(n))}
+    gb, ora, rb = _both(pab, orc, frame, "k", path=path)
+    assert gb.groupSize() == ora.num_groups
+    if n:
+        compare_all(gb, ora, rb, "v", ALL, f"n={n} {path}")
+
+
+@pytest.mark.parametrize("path", ["auto", "global"])
+def test_sliced_unaligned_inputs(pab, orc, path):
+    # Arrow `offset` must be honoured: values and validity bit offsets
+    from util import compare_all
+    rng = np.random.default_rng(3)
+    n = 50_000
+    k = pa.array(rng.integers(0, 100, n), pa.int64())
+    v = pa.array(rng.random(n), mask=rng.random(n) < 0.2)
+    for off in (1, 3, 8, 13):
+        frame = {"k": k.slice(off, n - off - 5), "v": v.slice(off, n - off - 5)}
+        gb, ora, rb = _both(pab, orc, frame, "k", path=path)
+        compare_all(gb, ora, rb, "v", ALL, f"offset {off} {path}")
+
+
+@pytest.mark.parametrize("path", ["auto", "global"])
+def test_config3_multi_key_dictionary_nullable(pab, orc, path):
+    # config 3: int32 key x dictionary-encoded string key, nullable fp64 and int64 values, 1 % null keys
+    from util import compare_all
+    rng = np.random.default_rng(17)
+    n = 300_000
+    k1 = pa.array(rng.integers(0, 50, n).astype(np.int32), mask=rng.random(n) < 0.01)
+    words = np.array([f"sym{i:02d}" for i in range(16)])
+    k2 = pa.array(words[rng.integers(0, 16, n)], mask=rng.random(n) < 0.01).dictionary_encode()
+    frame = {"k1": k1, "k2": k2, "f": pa.array(rng.random(n), mask=rng.random(n) < 0.1),
+             "i": pa.array(rng.integers(-1000, 1000, n), pa.int64(), mask=rng.random(n) < 0.1)}
+    rb = pa.record_batch(frame)
+    gb = pab.GroupBy(["k1", "k2"], rb, path=path)
+    ora = orc.OracleGroupBy(rb, ["k1", "k2"])
+    assert gb.groupSize() == ora.num_groups
+    compare_all(gb, ora, rb, "f", ALL, f"multi-key f64 {path}")
+    compare_all(gb, ora, rb, "i", ALL, f"multi-key i64 {path}")
+
+
+def test_device_resident_inputs_and_generator(pab, orc):
+    # zero-copy CUDA buffers (ARROW_DEVICE_CUDA) + device generator == host generator
+    import torch
+    from pandasarrow_b200 import hostgen as hg
+    from util import compare_all
+    n, G = 2_000_003, 1000
+    k = torch.empty(n, dtype=torch.int64, device="cuda"); v = torch.empty(n, dtype=torch.float64, device="cuda")
+    bits = torch.empty((n + 7) // 8, dtype=torch.uint8, device="cuda")
+    pab.synth.keys(k, G); pab.synth.vals(v); pab.synth.validity(bits, n)
+    torch.cuda.synchronize()
+    assert np.array_equal(k.cpu().numpy(), hg.keys(n, G))
+    assert np.array_equal(v.cpu().numpy(), hg.vals(n))
+    assert np.array_equal(np.unpackbits(bits.cpu().numpy(), bitorder="little")[:n].astype(bool), hg.valid_mask(n))
+    nulls = int(n - hg.valid_mask(n).sum())
+    frame_h = pa.record_batch({"k": pa.array(hg.keys(n, G)), "v": pa.array(hg.vals(n), mask=~hg.valid_mask(n))})
+    ora = orc.OracleGroupBy(frame_h, "k")
+    dk = pab.DeviceColumn.from_torch(k)
+    dv = pab.DeviceColumn.from_torch(v, valid=bits, null_count=nulls)
+    gb = pab.GroupBy("k", {"k": dk, "v": dv})
+    res = gb.aggregate(dv, ALL)
+    host = pab.GroupBy("k", frame_h).aggregate(frame_h.column("v"), ALL)
+    for a in ALL:
+        assert res[a].equals(host[a]), a          # device-resident and host-staged inputs agree bit for bit
+    compare_all(pab.GroupBy("k", frame_h), ora, frame_h, "v", ALL, "device generator")
+
+
+def test_run_to_run_determinism_lowcard(pab):
+    from pandasarrow_b200 import hostgen as hg
+    n, G = 3_000_000, 1000
+    rb = pa.record_batch({"k": pa.array(hg.keys(n, G)), "v": pa.array(hg.vals(n))})
+    first = None
+    for _ in range(3):
+        g = pab.GroupBy("k", rb)
+        r = g.aggregate(rb.column("v"), ["sum", "mean"])
+        assert g.timing()["path"] == "lowcard"
+        if first is None:
+            first = r
+        else:
+            assert r["sum"].equals(first["sum"]) and r["mean"].equals(first["mean"])
+
+
+def test_errors(pab):
+    with pytest.raises(RuntimeError):
+        pab.GroupBy("nope", pa.record_batch({"k": pa.array([1, 2])}))
+    g = pab.GroupBy("k", pa.record_batch({"k": pa.array([1, 2]), "v": pa.array([1.0, 2.0])}))
+    with pytest.raises(pab.PaError):
+        g.aggregate(pa.array([1.0, 2.0, 3.0]), ["sum"])          # length mismatch
+    with pytest.raises(pab.PaError):
+        g.fetch("max")                                            # not computed
+    with pytest.raises(pab.PaError):
+        pab.GroupBy("k", pa.record_batch({"k": pa.array([1.5, 2.5])})).groupSize() if False else \
+            pab.GroupBy("k", pa.record_batch({"k": pa.array([[1], [2]])}))   # unsupported key type

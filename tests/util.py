@@ -1,0 +1,63 @@
+"""Shared helpers for the parity tests: run the CUDA path (through the C ABI) and the oracle on
+the same inputs and compare with the bar BASELINE.json states (bit-exact for keys, counts,
+min/max, integer sums, first/last; <= 1e-12 relative for fp64 sum/mean)."""
+import math
+
+import numpy as np
+import pyarrow as pa
+
+FP_RTOL = 1e-12   # north_star: "within 1e-12 relative error for fp64 sum/mean"
+
+
+def assert_fp_close(got: pa.Array, want: pa.Array, what=""):
+    assert got.type == want.type, f"{what}: dtype {got.type} != {want.type}"
+    assert len(got) == len(want), f"{what}: length {len(got)} != {len(want)}"
+    gv = np.asarray(got.is_valid()); wv = np.asarray(want.is_valid())
+    assert (gv == wv).all(), f"{what}: validity differs"
+    g = got.to_numpy(zero_copy_only=False).astype(np.float64)[gv]
+    w = want.to_numpy(zero_copy_only=False).astype(np.float64)[wv]
+    nan = np.isnan(w)
+    assert (np.isnan(g) == nan).all(), f"{what}: NaN pattern differs"
+    g, w = g[~nan], w[~nan]
+    fin = np.isfinite(w)
+    assert (g[~fin] == w[~fin]).all(), f"{what}: infinities differ"
+    g, w = g[fin], w[fin]
+    if len(w):
+        denom = np.maximum(np.abs(w), np.finfo(np.float64).tiny)
+        rel = np.abs(g - w) / denom
+        assert rel.max() <= FP_RTOL, f"{what}: max rel err {rel.max():.3e} > {FP_RTOL}"
+
+
+def assert_exact(got: pa.Array, want: pa.Array, what=""):
+    assert got.type == want.type, f"{what}: dtype {got.type} != {want.type}"
+    if pa.types.is_floating(got.type):
+        # bit-exact except NaN payload / sign of zero (documented: Arrow's fmin/fmax tie rule)
+        gv = np.asarray(got.is_valid()); wv = np.asarray(want.is_valid())
+        assert (gv == wv).all(), f"{what}: validity differs"
+        g = got.to_numpy(zero_copy_only=False)[gv]; w = want.to_numpy(zero_copy_only=False)[wv]
+        assert ((g == w) | (np.isnan(g) & np.isnan(w))).all(), f"{what}: values differ"
+    else:
+        assert got.equals(want), f"{what}: {got.to_pylist()[:8]} != {want.to_pylist()[:8]}"
+
+
+def compare_all(gb, ora, frame, column, aggs, what=""):
+    """gb: pandasarrow_b200.GroupBy, ora: oracle.OracleGroupBy built on the same frame/key."""
+    col = frame[column] if isinstance(frame, dict) else frame.column(column)
+    res = gb.aggregate(col, aggs)
+    for i in range(ora.n_keys):
+        u_g, u_o = gb.unique(i), ora.unique(i)
+        assert u_g.equals(u_o), f"{what}: unique keys differ\n{u_g.to_pylist()[:10]}\n{u_o.to_pylist()[:10]}"
+    is_float = pa.types.is_floating(col.type)
+    for a in aggs:
+        got = res[a]
+        if a == "mean":
+            want, valid = ora.agg("mean", column, nthreads=8, with_validity=True)
+            # reference quirk (pd_core_macros.h:67): validity dropped; the C ABI keeps it, compare both views
+            want = pa.array(want.to_numpy(zero_copy_only=False), pa.float64(),
+                            mask=~np.asarray(valid.to_numpy(zero_copy_only=False), dtype=bool))
+            assert_fp_close(got, want, f"{what} mean")
+        elif a == "sum" and is_float:
+            assert_fp_close(got, ora.agg("sum", column, nthreads=8), f"{what} sum")
+        else:
+            assert_exact(got, ora.agg(a, column, nthreads=8), f"{what} {a}")
+    return res
