@@ -3,13 +3,18 @@
 //  * Every warp streams its own row chunks HBM -> shared memory with 1-D bulk async copies
 //    (cp.async.bulk, the TMA engine) through a private 3-stage mbarrier ring, so the memory
 //    pipeline depth does not depend on occupancy (8 warps / SM).
-//  * Keys are resolved to dense CTA-local group ids through a CTA-shared open-addressing table
-//    in shared memory (insert = one ATOMS.CAS.64 during warm-up, read-only afterwards).
-//  * Accumulators are WARP-PRIVATE arrays in shared memory, updated without atomics: lanes of a
-//    warp that hit the same group are combined first with a shuffle-based segmented reduction in
-//    ascending lane (= row) order, then the lowest lane does one read-modify-write.  The order of
-//    floating-point additions is therefore a fixed function of (n_rows, grid size): results are
-//    run-to-run deterministic.
+//  * Keys are resolved to dense CTA-local group ids through a CTA-shared hash table in shared
+//    memory: 2048 buckets of two 8-byte keys, one LDS.128 per lookup; the steady state is
+//    read-only (plain loads, no atomics), a rare out-of-line slow path inserts new keys with
+//    ATOMS.CAS.64 and handles null keys / the sentinel-valued key / bucket overflow.
+//  * Accumulators are WARP-PRIVATE arrays in shared memory, updated without atomics (sm_100a has
+//    no native 64-bit shared-memory atomics: f64/u64 adds compile to CAS spin loops).  Lanes of a
+//    warp that hit the same group (MATCH.ANY) are first combined with a shuffle-based segmented
+//    reduction in ascending lane (= row) order, then the lowest lane does one read-modify-write.
+//    The order of floating-point additions is therefore a fixed function of (n_rows, grid size):
+//    results are run-to-run deterministic.
+//  * Two 32-row batches are processed interleaved per step so that two independent lookup chains
+//    are in flight per warp.
 //  * At the end each CTA folds its warps in warp order and writes a partial table; a single-CTA
 //    merge kernel joins the partial tables by key, folds them in CTA order, ranks the groups by
 //    first row and writes the GroupResult.
@@ -25,17 +30,18 @@ namespace pa {
 
 constexpr int LC_WARPS = 8;
 constexpr int LC_THREADS = LC_WARPS * 32;
-constexpr int LC_TCAP_LOG2 = 11;
-constexpr int LC_TCAP = 1 << LC_TCAP_LOG2;   // CTA key-table slots
+constexpr int LC_NB_LOG2 = 11;
+constexpr int LC_NBUCKET = 1 << LC_NB_LOG2;  // buckets of two keys
+constexpr int LC_TCAP = LC_NBUCKET * 2;      // key slots
 constexpr int LC_STAGES = 3;
-constexpr int LC_CHUNK = 256;                // rows per warp per stage
+constexpr int LC_CHUNK = 192;                // rows per warp per stage (3 steps of 2 x 32 rows)
 constexpr uint32_t LC_UNSEEN = 0xFFFFFFFFu;  // count sentinel: warp has not met this id yet
 constexpr uint16_t LC_ID_UNSET = 0xFFFFu;
 constexpr uint16_t LC_ID_OVF = 0xFFFEu;
 constexpr uint32_t LC_NOID = 0xFFFFFFFFu;
 
 constexpr int LC_GMAX_NARROW = 1024;   // sum / mean / count / first  (12 B per id per warp)
-constexpr int LC_GMAX_WIDE = 320;      // + min / max / last / dsum    (40 B per id per warp)
+constexpr int LC_GMAX_WIDE = 352;      // + min / max / last / dsum    (40 B per id per warp)
 
 template <bool WIDE>
 struct LcCfg {
@@ -109,107 +115,122 @@ struct LcAcc {
   }
 };
 
-// Resolve a key to its CTA-local dense id (insert on first sight).  LC_NOID on overflow.
+__device__ __forceinline__ uint32_t lc_bucket(uint64_t key) {
+  const uint32_t lo = static_cast<uint32_t>(key), hi = static_cast<uint32_t>(key >> 32);
+  return ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u) ^ (lo >> 15)) * 0x2C1B3C6Du >> (32 - LC_NB_LOG2);
+}
+
+// Steady-state lookup: one LDS.128 (both keys of the home bucket) + one LDS.U16.  Returns a value
+// >= LC_ID_OVF when the row must take the slow path (key not in its home bucket, id not published
+// yet, or the row's key equals the empty sentinel).
+__device__ __forceinline__ uint32_t lc_lookup(uint64_t key, const unsigned long long* tkeys, const uint16_t* tids) {
+  const uint32_t b = lc_bucket(key);
+  const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(tkeys + 2 * b);
+  const bool h1 = kk.y == key;
+  const bool hit = (kk.x == key) | h1;
+  const uint32_t id = tids[2 * b + (h1 ? 1u : 0u)];
+  return hit ? id : static_cast<uint32_t>(LC_ID_UNSET);
+}
+
+// Slow path: null / sentinel-valued keys, insertion on first sight, keys displaced from their home
+// bucket.  Per-lane (divergent) code, kept out of line.  LC_NOID on overflow.
 template <bool WIDE>
-__device__ __forceinline__ uint32_t lc_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
-                                               uint32_t* misc, uint32_t* status) {
+__device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, bool kvalid, unsigned long long* tkeys,
+                                                 volatile uint16_t* tids, uint32_t* misc, uint32_t* status) {
   using Cfg = LcCfg<WIDE>;
-  uint32_t slot = hash_key(key) >> (32 - LC_TCAP_LOG2);
-  for (int probe = 0; probe < LC_TCAP; ++probe) {
-    const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(tkeys + slot);
-    bool found = (k == key);
-    if (!found && k == kEmptyKey) {
-      const uint64_t old = atomicCAS(tkeys + slot, static_cast<unsigned long long>(kEmptyKey),
+  if (!kvalid) return Cfg::ID_NULL;
+  if (key == kEmptyKey) return Cfg::ID_EMPTYKEY;
+  uint32_t b = lc_bucket(key);
+  for (int probe = 0; probe < 4 * LC_NBUCKET; ++probe) {
+    const uint64_t k0 = *reinterpret_cast<volatile unsigned long long*>(tkeys + 2 * b);
+    const uint64_t k1 = *reinterpret_cast<volatile unsigned long long*>(tkeys + 2 * b + 1);
+    uint32_t slot;
+    if (k0 == key) slot = 2 * b;
+    else if (k1 == key) slot = 2 * b + 1;
+    else if (k0 == kEmptyKey || k1 == kEmptyKey) {
+      const uint32_t s = (k0 == kEmptyKey) ? 2 * b : 2 * b + 1;   // lowest empty slot of the bucket
+      const uint64_t old = atomicCAS(tkeys + s, static_cast<unsigned long long>(kEmptyKey),
                                      static_cast<unsigned long long>(key));
       if (old == kEmptyKey) {  // this lane inserted the key: hand out the next dense id
         const uint32_t nid = atomicAdd(misc, 1u);
         if (nid >= static_cast<uint32_t>(Cfg::GMAX)) {
-          tids[slot] = LC_ID_OVF;
+          tids[s] = LC_ID_OVF;
           misc[1] = 1u;
           atomicExch(status + ST_OVERFLOW, 1u);
           return LC_NOID;
         }
-        tids[slot] = static_cast<uint16_t>(nid);
+        tids[s] = static_cast<uint16_t>(nid);
         return nid;
       }
-      found = (old == key);
+      if (old != key) continue;   // lost the slot to another key: look at the same bucket again
+      slot = s;
+    } else {
+      b = (b + 1) & (LC_NBUCKET - 1);
+      continue;
     }
-    if (found) {
-      uint16_t id;
-      do { id = tids[slot]; } while (id == LC_ID_UNSET);   // inserter publishes the id right after its CAS
-      return id == LC_ID_OVF ? LC_NOID : id;
-    }
-    slot = (slot + 1) & (LC_TCAP - 1);
+    uint16_t id;
+    do { id = tids[slot]; } while (id == LC_ID_UNSET);   // inserter publishes the id right after its CAS
+    return id == LC_ID_OVF ? LC_NOID : id;
   }
   misc[1] = 1u;
   atomicExch(status + ST_OVERFLOW, 1u);
   return LC_NOID;
 }
 
-// Process 32 rows (one per lane).  All 32 lanes must call this (warp-synchronous).
+// Accumulate one 32-row batch whose ids are known.  Warp-synchronous.
 template <int VC, bool WIDE>
-__device__ __forceinline__ void lc_process_batch(bool active, uint64_t key, bool kvalid, uint64_t vbits, bool vvalid,
-                                                 uint32_t row, uint32_t agg_mask, unsigned long long* tkeys,
-                                                 volatile uint16_t* tids, uint32_t* cta_first, uint32_t* misc,
-                                                 uint32_t* status, const LcAcc<WIDE>& acc) {
-  using Cfg = LcCfg<WIDE>;
+__device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row,
+                                              uint32_t* cta_first, const LcAcc<WIDE>& acc) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = lane_id();
-  uint32_t id = LC_NOID;
-  if (active) {
-    if (!kvalid) id = Cfg::ID_NULL;
-    else if (key == kEmptyKey) id = Cfg::ID_EMPTYKEY;
-    else id = lc_resolve<WIDE>(key, tkeys, tids, misc, status);
-  }
-  __syncwarp();
-  // ---- segmented reduction over lanes with equal id, ascending lane order ----
+  const uint32_t lanebit = 1u << lane;
   const uint32_t peers = __match_any_sync(FULL, id);
-  const uint32_t leader_lane = __ffs(peers) - 1;
-  uint64_t c_sum = 0;           // double bits (VC_F) or wrapping integer
+  const bool leader = (peers & (lanebit - 1u)) == 0;
+  uint64_t c_sum = 0;           // double bits (VC_F, +0.0) or wrapping integer
   uint32_t c_cnt = 0;
   double c_dsum = 0.0;
   uint64_t c_min = kMinInit, c_max = kMaxInit;
-  if (vvalid && id != LC_NOID) {
+  if (vvalid) {
     c_sum = vbits;
     c_cnt = 1;
     if constexpr (WIDE) {
       if constexpr (VC != VC_F) c_dsum = Wide<VC>::as_double(vbits);
       if (!Wide<VC>::is_nan(vbits)) { c_min = Wide<VC>::ord(vbits); c_max = c_min; }
     }
-  } else if constexpr (VC == VC_F) {
-    c_sum = 0;  // +0.0
   }
-  uint32_t rem = peers & ~(1u << leader_lane);
-  if (lane != leader_lane) rem = 0;  // only leaders pull
-  while (__any_sync(FULL, rem != 0)) {
-    const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
-    const uint64_t o_sum = __shfl_sync(FULL, c_sum, src);
-    const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, src);
-    double o_dsum = 0.0;
-    uint64_t o_min = kMinInit, o_max = kMaxInit;
-    if constexpr (WIDE) {
-      if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, src);
-      o_min = __shfl_sync(FULL, c_min, src);
-      o_max = __shfl_sync(FULL, c_max, src);
-    }
-    if (rem) {
-      if constexpr (VC == VC_F) {
-        c_sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(c_sum)) +
-                                                           __longlong_as_double(static_cast<long long>(o_sum))));
-      } else {
-        c_sum += o_sum;
-      }
-      c_cnt += o_cnt;
+  if (__any_sync(FULL, peers != lanebit)) {
+    // segmented reduction: every leader pulls its peers' contributions in ascending lane order
+    uint32_t rem = leader ? (peers & ~lanebit) : 0u;
+    while (__any_sync(FULL, rem != 0)) {
+      const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
+      const uint64_t o_sum = __shfl_sync(FULL, c_sum, src);
+      const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, src);
+      double o_dsum = 0.0;
+      uint64_t o_min = kMinInit, o_max = kMaxInit;
       if constexpr (WIDE) {
-        c_dsum += o_dsum;
-        c_min = o_min < c_min ? o_min : c_min;
-        c_max = o_max > c_max ? o_max : c_max;
+        if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, src);
+        o_min = __shfl_sync(FULL, c_min, src);
+        o_max = __shfl_sync(FULL, c_max, src);
       }
-      rem &= rem - 1;
+      if (rem) {
+        if constexpr (VC == VC_F) {
+          c_sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(c_sum)) +
+                                                             __longlong_as_double(static_cast<long long>(o_sum))));
+        } else {
+          c_sum += o_sum;
+        }
+        c_cnt += o_cnt;
+        if constexpr (WIDE) {
+          c_dsum += o_dsum;
+          c_min = o_min < c_min ? o_min : c_min;
+          c_max = o_max > c_max ? o_max : c_max;
+        }
+        rem &= rem - 1;
+      }
     }
   }
-  // ---- one non-atomic read-modify-write per distinct id, by the lowest lane ----
-  if (lane == leader_lane && id != LC_NOID) {
+  // one non-atomic read-modify-write per distinct id, by the lowest lane
+  if (leader && id != LC_NOID) {
     uint32_t old = acc.cnt[id];
     if (old == LC_UNSEEN) {  // first time this warp meets the id: candidate for the CTA's first row
       old = 0;
@@ -229,6 +250,30 @@ __device__ __forceinline__ void lc_process_batch(bool active, uint64_t key, bool
       if (c_max > acc.mx[id]) acc.mx[id] = c_max;
     }
   }
+}
+
+// Two 32-row batches (A: rows rowA + lane, B: rows rowA + 32 + lane), interleaved.
+template <int VC, bool WIDE>
+__device__ __forceinline__ void lc_process_pair(bool actA, bool actB, uint64_t keyA, uint64_t keyB, bool kvA, bool kvB,
+                                                uint64_t vbA, uint64_t vbB, bool vvA, bool vvB, uint32_t rowA,
+                                                unsigned long long* tkeys, uint16_t* tids, uint32_t* cta_first,
+                                                uint32_t* misc, uint32_t* status, const LcAcc<WIDE>& acc) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  uint32_t idA = lc_lookup(keyA, tkeys, tids);
+  uint32_t idB = lc_lookup(keyB, tkeys, tids);
+  const bool slowA = actA && (idA >= LC_ID_OVF || !kvA);
+  const bool slowB = actB && (idB >= LC_ID_OVF || !kvB);
+  if (__any_sync(FULL, slowA || slowB)) {
+    if (slowA) idA = lc_slow_resolve<WIDE>(keyA, kvA, tkeys, tids, misc, status);
+    __syncwarp();
+    if (slowB) idB = lc_slow_resolve<WIDE>(keyB, kvB, tkeys, tids, misc, status);
+    __syncwarp();
+  }
+  if (!actA) idA = LC_NOID;
+  if (!actB) idB = LC_NOID;
+  lc_accumulate<VC, WIDE>(idA, vbA, vvA && actA && idA != LC_NOID, rowA, cta_first, acc);
+  __syncwarp();
+  lc_accumulate<VC, WIDE>(idB, vbB, vvB && actB && idB != LC_NOID, rowA + 32u, cta_first, acc);
   __syncwarp();
 }
 
@@ -239,7 +284,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   unsigned long long* tkeys = reinterpret_cast<unsigned long long*>(smem + L::OFF_TKEYS);
-  volatile uint16_t* tids = reinterpret_cast<volatile uint16_t*>(smem + L::OFF_TIDS);
+  uint16_t* tids = reinterpret_cast<uint16_t*>(smem + L::OFF_TIDS);
   uint32_t* cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
   uint32_t* misc = reinterpret_cast<uint32_t*>(smem + L::OFF_MISC);   // [0] next id, [1] overflow seen
   const int warp = threadIdx.x >> 5;
@@ -268,6 +313,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
   __syncthreads();
 
   const bool have_vals = a.vals != nullptr;
+  const bool have_kvalid = a.kvalid != nullptr, have_vvalid = a.vvalid != nullptr;
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * LC_WARPS + warp;
   const int64_t nw = static_cast<int64_t>(gridDim.x) * LC_WARPS;
   const int64_t nchunks = a.n_bulk / LC_CHUNK;
@@ -303,22 +349,29 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
       if (!ovf) {
         const unsigned char* st = my_stage + STAGE_BYTES * s;
         const int64_t row0 = c * LC_CHUNK;
-#pragma unroll 2
-        for (int b = 0; b < LC_CHUNK / 32; ++b) {
-          const int r = b * 32 + lane;
-          uint64_t key;
-          if constexpr (KW == 8) key = reinterpret_cast<const uint64_t*>(st)[r];
-          else key = reinterpret_cast<const uint32_t*>(st)[r];
-          uint64_t vb = 0;
-          bool vv = false;
-          const int64_t row = row0 + r;
-          if (have_vals) {
-            vb = load_wide<VC, VW>(st + LC_CHUNK * KW, r);
-            vv = a.vvalid ? bit_at(a.vvalid, a.voff + row) : true;
+#pragma unroll 1
+        for (int step = 0; step < LC_CHUNK / 64; ++step) {
+          const int rA = step * 64 + lane, rB = rA + 32;
+          uint64_t keyA, keyB;
+          if constexpr (KW == 8) {
+            keyA = reinterpret_cast<const uint64_t*>(st)[rA];
+            keyB = reinterpret_cast<const uint64_t*>(st)[rB];
+          } else {
+            keyA = reinterpret_cast<const uint32_t*>(st)[rA];
+            keyB = reinterpret_cast<const uint32_t*>(st)[rB];
           }
-          const bool kv = a.kvalid ? bit_at(a.kvalid, a.koff + row) : true;
-          lc_process_batch<VC, WIDE>(true, key, kv, vb, vv, static_cast<uint32_t>(row), a.agg_mask, tkeys, tids,
-                                     cta_first, misc, a.status, acc);
+          uint64_t vbA = 0, vbB = 0;
+          bool vvA = false, vvB = false, kvA = true, kvB = true;
+          const int64_t rowA = row0 + rA;
+          if (have_vals) {
+            vbA = load_wide<VC, VW>(st + LC_CHUNK * KW, rA);
+            vbB = load_wide<VC, VW>(st + LC_CHUNK * KW, rB);
+            vvA = vvB = true;
+            if (have_vvalid) { vvA = bit_at(a.vvalid, a.voff + rowA); vvB = bit_at(a.vvalid, a.voff + rowA + 32); }
+          }
+          if (have_kvalid) { kvA = bit_at(a.kvalid, a.koff + rowA); kvB = bit_at(a.kvalid, a.koff + rowA + 32); }
+          lc_process_pair<VC, WIDE>(true, true, keyA, keyB, kvA, kvB, vbA, vbB, vvA, vvB, static_cast<uint32_t>(rowA),
+                                    tkeys, tids, cta_first, misc, a.status, acc);
         }
       }
       __syncwarp();
@@ -334,23 +387,25 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
     }
   }
 
-  // ---- remainder rows [n_bulk, n): direct loads, warps of the whole grid take 32-row batches ----
-  for (int64_t r0 = a.n_bulk + gw * 32; r0 < a.n; r0 += nw * 32) {
+  // ---- remainder rows [n_bulk, n): direct loads, warps of the whole grid take 64-row steps ----
+  for (int64_t r0 = a.n_bulk + gw * 64; r0 < a.n; r0 += nw * 64) {
     if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(misc + 1) != 0)) break;
-    const int64_t row = r0 + lane;
-    const bool active = row < a.n;
-    uint64_t key = 0, vb = 0;
-    bool kv = true, vv = false;
-    if (active) {
-      key = load_key<KW>(a.keys, row);
-      if (a.kvalid) kv = bit_at(a.kvalid, a.koff + row);
-      if (have_vals) {
-        vb = load_wide<VC, VW>(a.vals, row);
-        vv = a.vvalid ? bit_at(a.vvalid, a.voff + row) : true;
-      }
+    const int64_t rowA = r0 + lane, rowB = rowA + 32;
+    const bool actA = rowA < a.n, actB = rowB < a.n;
+    uint64_t keyA = 0, keyB = 0, vbA = 0, vbB = 0;
+    bool kvA = true, kvB = true, vvA = false, vvB = false;
+    if (actA) {
+      keyA = load_key<KW>(a.keys, rowA);
+      if (have_kvalid) kvA = bit_at(a.kvalid, a.koff + rowA);
+      if (have_vals) { vbA = load_wide<VC, VW>(a.vals, rowA); vvA = have_vvalid ? bit_at(a.vvalid, a.voff + rowA) : true; }
     }
-    lc_process_batch<VC, WIDE>(active, key, kv, vb, vv, static_cast<uint32_t>(row), a.agg_mask, tkeys, tids,
-                               cta_first, misc, a.status, acc);
+    if (actB) {
+      keyB = load_key<KW>(a.keys, rowB);
+      if (have_kvalid) kvB = bit_at(a.kvalid, a.koff + rowB);
+      if (have_vals) { vbB = load_wide<VC, VW>(a.vals, rowB); vvB = have_vvalid ? bit_at(a.vvalid, a.voff + rowB) : true; }
+    }
+    lc_process_pair<VC, WIDE>(actA, actB, keyA, keyB, kvA, kvB, vbA, vbB, vvA, vvB, static_cast<uint32_t>(rowA), tkeys,
+                              tids, cta_first, misc, a.status, acc);
   }
   __syncthreads();
   if (misc[1]) return;
