@@ -245,7 +245,7 @@ template <int VC, int VW, int KW, bool WIDE>
 int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid) {
   using L = LcSmem<WIDE>;
   const size_t smem = L::total(KW, VW);
-  auto scan = k_lowcard_scan<VC, VW, KW, WIDE>;
+  auto scan = (a.kvalid || a.vvalid) ? k_lowcard_scan<VC, VW, KW, WIDE, true> : k_lowcard_scan<VC, VW, KW, WIDE, false>;
   CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   scan<<<grid, LC_THREADS, smem, g->stream>>>(a);
   CUDA_TRY(cudaGetLastError());

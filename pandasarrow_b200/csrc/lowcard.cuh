@@ -120,11 +120,11 @@ __device__ __forceinline__ uint32_t lc_bucket(uint64_t key) {
   return ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u) ^ (lo >> 15)) * 0x2C1B3C6Du >> (32 - LC_NB_LOG2);
 }
 
-// Steady-state lookup: one LDS.128 (both keys of the home bucket) + one LDS.U16.  Returns a value
-// >= LC_ID_OVF when the row must take the slow path (key not in its home bucket, id not published
-// yet, or the row's key equals the empty sentinel).
-__device__ __forceinline__ uint32_t lc_lookup(uint64_t key, const unsigned long long* tkeys, const uint16_t* tids) {
-  const uint32_t b = lc_bucket(key);
+// Steady-state lookup of bucket `b`: one LDS.128 (both keys of the bucket) + one LDS.U16.  Returns a
+// value >= LC_ID_OVF when the key is not in this bucket, its id is not published yet, or the row's
+// key equals the empty sentinel.
+__device__ __forceinline__ uint32_t lc_lookup(uint64_t key, uint32_t b, const unsigned long long* tkeys,
+                                              const uint16_t* tids) {
   const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(tkeys + 2 * b);
   const bool h1 = kk.y == key;
   const bool hit = (kk.x == key) | h1;
@@ -177,15 +177,29 @@ __device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, bool kvalid, unsi
   return LC_NOID;
 }
 
+constexpr uint32_t LC_CNT_MASK = 0x00FFFFFFu;   // count field of an accumulator count word; byte 3 = claim tag
+
 // Accumulate one 32-row batch whose ids are known.  Warp-synchronous.
+//
+// Duplicate ids inside the batch are found without MATCH.ANY (whose latency grows with the number
+// of distinct values, ~360 cycles at 32): every lane stores its lane number into the top byte of
+// its group's count word, then loads the word back — one lane per group reads its own number (the
+// "winner"), the others learn who won.  Winners then fold the losers' contributions in ascending
+// lane order (their own value at its own lane position, so the result does not depend on which
+// lane the hardware let win), and do one non-atomic read-modify-write.
 template <int VC, bool WIDE>
 __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row,
                                               uint32_t* cta_first, const LcAcc<WIDE>& acc) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = lane_id();
-  const uint32_t lanebit = 1u << lane;
-  const uint32_t peers = __match_any_sync(FULL, id);
-  const bool leader = (peers & (lanebit - 1u)) == 0;
+  const bool live = id != LC_NOID;
+  uint32_t* cw = acc.cnt + (live ? id : 0u);
+  if (live) reinterpret_cast<volatile uint8_t*>(cw)[3] = static_cast<uint8_t>(lane);
+  __syncwarp();
+  const uint32_t word = live ? *reinterpret_cast<volatile uint32_t*>(cw) : 0u;
+  const uint32_t w = word >> 24;
+  const bool winner = live && (w == lane);
+  const uint32_t losers = __ballot_sync(FULL, live && !winner);
   uint64_t c_sum = 0;           // double bits (VC_F, +0.0) or wrapping integer
   uint32_t c_cnt = 0;
   double c_dsum = 0.0;
@@ -198,45 +212,95 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
       if (!Wide<VC>::is_nan(vbits)) { c_min = Wide<VC>::ord(vbits); c_max = c_min; }
     }
   }
-  if (__any_sync(FULL, peers != lanebit)) {
-    // segmented reduction: every leader pulls its peers' contributions in ascending lane order
-    uint32_t rem = leader ? (peers & ~lanebit) : 0u;
-    while (__any_sync(FULL, rem != 0)) {
-      const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
-      const uint64_t o_sum = __shfl_sync(FULL, c_sum, src);
-      const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, src);
-      double o_dsum = 0.0;
-      uint64_t o_min = kMinInit, o_max = kMaxInit;
+  uint32_t lo_lane = lane, hi_lane = lane;   // lowest / highest lane of my group (meaningful for the doer)
+  bool doer = winner;                        // the lane that performs the read-modify-write
+  if (losers) {
+    auto add_to = [&](uint64_t& t_sum, uint32_t& t_cnt, double& t_dsum, uint64_t& t_min, uint64_t& t_max,
+                      uint64_t x_sum, uint32_t x_cnt, double x_dsum, uint64_t x_min, uint64_t x_max) {
+      if constexpr (VC == VC_F) {
+        t_sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(t_sum)) +
+                                                           __longlong_as_double(static_cast<long long>(x_sum))));
+      } else {
+        t_sum += x_sum;
+      }
+      t_cnt += x_cnt;
       if constexpr (WIDE) {
-        if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, src);
-        o_min = __shfl_sync(FULL, c_min, src);
-        o_max = __shfl_sync(FULL, c_max, src);
+        t_dsum += x_dsum;
+        t_min = x_min < t_min ? x_min : t_min;
+        t_max = x_max > t_max ? x_max : t_max;
       }
-      if (rem) {
-        if constexpr (VC == VC_F) {
-          c_sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(c_sum)) +
-                                                             __longlong_as_double(static_cast<long long>(o_sum))));
-        } else {
-          c_sum += o_sum;
-        }
-        c_cnt += o_cnt;
-        if constexpr (WIDE) {
-          c_dsum += o_dsum;
-          c_min = o_min < c_min ? o_min : c_min;
-          c_max = o_max > c_max ? o_max : c_max;
-        }
+    };
+    if (__popc(losers) <= 4) {
+      // few duplicates: one warp-uniform iteration per loser lane, ascending
+      uint64_t f_sum = 0;
+      uint32_t f_cnt = 0;
+      double f_dsum = 0.0;
+      uint64_t f_min = kMinInit, f_max = kMaxInit;
+      bool own_added = false;
+      uint32_t rem = losers;
+      while (rem) {
+        const int L = __ffs(rem) - 1;
         rem &= rem - 1;
+        const uint32_t tw = __shfl_sync(FULL, w, L);
+        const uint64_t o_sum = __shfl_sync(FULL, c_sum, L);
+        const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, L);
+        double o_dsum = 0.0;
+        uint64_t o_min = kMinInit, o_max = kMaxInit;
+        if constexpr (WIDE) {
+          if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, L);
+          o_min = __shfl_sync(FULL, c_min, L);
+          o_max = __shfl_sync(FULL, c_max, L);
+        }
+        if (winner && tw == lane) {
+          if (!own_added && static_cast<uint32_t>(L) > lane) {
+            add_to(f_sum, f_cnt, f_dsum, f_min, f_max, c_sum, c_cnt, c_dsum, c_min, c_max);
+            own_added = true;
+          }
+          add_to(f_sum, f_cnt, f_dsum, f_min, f_max, o_sum, o_cnt, o_dsum, o_min, o_max);
+          lo_lane = static_cast<uint32_t>(L) < lo_lane ? static_cast<uint32_t>(L) : lo_lane;
+          hi_lane = static_cast<uint32_t>(L) > hi_lane ? static_cast<uint32_t>(L) : hi_lane;
+        }
       }
+      if (winner) {
+        if (!own_added) add_to(f_sum, f_cnt, f_dsum, f_min, f_max, c_sum, c_cnt, c_dsum, c_min, c_max);
+        c_sum = f_sum; c_cnt = f_cnt; c_dsum = f_dsum; c_min = f_min; c_max = f_max;
+      }
+    } else {
+      // many duplicates = few distinct ids, where MATCH.ANY is cheap: the lowest lane of every group
+      // pulls its peers in ascending lane order and does the read-modify-write
+      const uint32_t peers = __match_any_sync(FULL, id);
+      const uint32_t lanebit = 1u << lane;
+      const bool leader = (peers & (lanebit - 1u)) == 0;
+      uint32_t rem = leader ? (peers & ~lanebit) : 0u;
+      while (__any_sync(FULL, rem != 0)) {
+        const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
+        const uint64_t o_sum = __shfl_sync(FULL, c_sum, src);
+        const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, src);
+        double o_dsum = 0.0;
+        uint64_t o_min = kMinInit, o_max = kMaxInit;
+        if constexpr (WIDE) {
+          if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, src);
+          o_min = __shfl_sync(FULL, c_min, src);
+          o_max = __shfl_sync(FULL, c_max, src);
+        }
+        if (rem) {
+          add_to(c_sum, c_cnt, c_dsum, c_min, c_max, o_sum, o_cnt, o_dsum, o_min, o_max);
+          rem &= rem - 1;
+        }
+      }
+      doer = live && leader;
+      lo_lane = lane;
+      hi_lane = 31 - __clz(peers);
     }
   }
-  // one non-atomic read-modify-write per distinct id, by the lowest lane
-  if (leader && id != LC_NOID) {
-    uint32_t old = acc.cnt[id];
-    if (old == LC_UNSEEN) {  // first time this warp meets the id: candidate for the CTA's first row
+  // one non-atomic read-modify-write per distinct id
+  if (doer) {
+    uint32_t old = word & LC_CNT_MASK;
+    if (old == LC_CNT_MASK) {  // first time this warp meets the id: candidate for the CTA's first row
       old = 0;
-      atomicMin(cta_first + id, row);
+      atomicMin(cta_first + id, row - lane + lo_lane);
     }
-    acc.cnt[id] = old + c_cnt;
+    *cw = old + c_cnt;   // also clears the claim tag
     if constexpr (VC == VC_F) {
       double* s = reinterpret_cast<double*>(acc.sum + id);
       *s = *s + __longlong_as_double(static_cast<long long>(c_sum));
@@ -244,7 +308,7 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
       acc.sum[id] += c_sum;
     }
     if constexpr (WIDE) {
-      acc.last[id] = row + (31 - __clz(peers)) - lane;   // row of the highest peer lane
+      acc.last[id] = row - lane + hi_lane;
       if constexpr (VC != VC_F) acc.dsum[id] += c_dsum;
       if (c_min < acc.mn[id]) acc.mn[id] = c_min;
       if (c_max > acc.mx[id]) acc.mx[id] = c_max;
@@ -259,10 +323,17 @@ __device__ __forceinline__ void lc_process_pair(bool actA, bool actB, uint64_t k
                                                 unsigned long long* tkeys, uint16_t* tids, uint32_t* cta_first,
                                                 uint32_t* misc, uint32_t* status, const LcAcc<WIDE>& acc) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
-  uint32_t idA = lc_lookup(keyA, tkeys, tids);
-  uint32_t idB = lc_lookup(keyB, tkeys, tids);
-  const bool slowA = actA && (idA >= LC_ID_OVF || !kvA);
-  const bool slowB = actB && (idB >= LC_ID_OVF || !kvB);
+  const uint32_t bA = lc_bucket(keyA), bB = lc_bucket(keyB);
+  uint32_t idA = lc_lookup(keyA, bA, tkeys, tids);
+  uint32_t idB = lc_lookup(keyB, bB, tkeys, tids);
+  bool missA = actA && idA >= LC_ID_OVF, missB = actB && idB >= LC_ID_OVF;
+  if (__any_sync(FULL, missA || missB)) {   // keys displaced by one bucket: second inline probe
+    if (missA) idA = lc_lookup(keyA, (bA + 1) & (LC_NBUCKET - 1), tkeys, tids);
+    if (missB) idB = lc_lookup(keyB, (bB + 1) & (LC_NBUCKET - 1), tkeys, tids);
+    missA = actA && idA >= LC_ID_OVF;
+    missB = actB && idB >= LC_ID_OVF;
+  }
+  const bool slowA = missA || (actA && !kvA), slowB = missB || (actB && !kvB);
   if (__any_sync(FULL, slowA || slowB)) {
     if (slowA) idA = lc_slow_resolve<WIDE>(keyA, kvA, tkeys, tids, misc, status);
     __syncwarp();
@@ -277,7 +348,7 @@ __device__ __forceinline__ void lc_process_pair(bool actA, bool actB, uint64_t k
   __syncwarp();
 }
 
-template <int VC, int VW, int KW, bool WIDE>
+template <int VC, int VW, int KW, bool WIDE, bool NULLS>
 __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
   using Cfg = LcCfg<WIDE>;
   using L = LcSmem<WIDE>;
@@ -313,7 +384,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
   __syncthreads();
 
   const bool have_vals = a.vals != nullptr;
-  const bool have_kvalid = a.kvalid != nullptr, have_vvalid = a.vvalid != nullptr;
+  const bool have_kvalid = NULLS && a.kvalid != nullptr, have_vvalid = NULLS && a.vvalid != nullptr;
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * LC_WARPS + warp;
   const int64_t nw = static_cast<int64_t>(gridDim.x) * LC_WARPS;
   const int64_t nchunks = a.n_bulk / LC_CHUNK;
@@ -419,8 +490,8 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
     uint64_t mn = kMinInit, mx = kMaxInit;
     for (int w = 0; w < LC_WARPS; ++w) {
       LcAcc<WIDE> o(smem + L::OFF_ACC + L::ACC_PER_WARP * w);
-      const uint32_t c = o.cnt[id];
-      if (c == LC_UNSEEN) continue;
+      const uint32_t c = o.cnt[id] & LC_CNT_MASK;
+      if (c == LC_CNT_MASK) continue;
       cnt += c;
       if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(o.sum[id]));
       else sum += o.sum[id];

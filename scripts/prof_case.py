@@ -12,10 +12,14 @@ ap.add_argument("--aggs", default="sum,mean,count")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--path", default="auto")
 ap.add_argument("--hint", type=int, default=0)
+ap.add_argument("--hashed", action="store_true", help="scramble the dense key ids into random-looking 64-bit keys")
 a = ap.parse_args()
 n = a.rows
 k = torch.empty(n, dtype=torch.int64, device="cuda"); v = torch.empty(n, dtype=torch.float64, device="cuda")
-pab.synth.keys(k, a.groups); pab.synth.vals(v); torch.cuda.synchronize()
+pab.synth.keys(k, a.groups); pab.synth.vals(v)
+if a.hashed:
+    k.mul_(-7046029254386353131).bitwise_xor_(0x5DEECE66D)
+torch.cuda.synchronize()
 dk, dv = pab.DeviceColumn.from_torch(k), pab.DeviceColumn.from_torch(v)
 g = pab.GroupBy("k", {"k": dk, "v": dv}, path=a.path, expected_groups=a.hint)
 for i in range(a.iters):
