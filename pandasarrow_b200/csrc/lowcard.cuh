@@ -415,8 +415,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
     uint32_t phase = 0;
     for (int64_t c = gw; c <= last_issued; c += nw) {
       mbar_wait(my_bar + s, phase);
-      const bool ovf = __any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(misc + 1) != 0 ||
-                                                   *reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW) != 0);
+      // (only the CTA-local flag is polled: a global poll costs one system-scope load per chunk, and
+      //  every CTA meets the same key population, so each one notices an overflow by itself)
+      const bool ovf = __any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(misc + 1) != 0);
       if (!ovf) {
         const unsigned char* st = my_stage + STAGE_BYTES * s;
         const int64_t row0 = c * LC_CHUNK;
