@@ -17,6 +17,7 @@
 #include "emit.cuh"
 #include "gtable.cuh"
 #include "lowcard.cuh"
+#include "resample.cuh"
 
 using namespace pa;
 
@@ -186,6 +187,7 @@ struct pa_groupby {
   // resample mode (time-bucket specialisation)
   bool resample = false;
   std::string index_format;
+  ResampleSpec rs{};
   // group table in first-appearance order
   bool have_groups = false;
   uint32_t G = 0;
@@ -632,9 +634,126 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
 }  // namespace
 
 namespace {
-int run_resample(pa_groupby*, const Column*, uint32_t, bool) {
-  return set_err(PA_ERR_NOT_IMPLEMENTED, "resample path not built yet");
+
+template <int VC, bool WIDE>
+int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
+  using SlotT = typename SlotOf<WIDE>::type;
+  cudaStream_t st = g->stream;
+  const int64_t nbins = g->rs.nbins;
+  const uint64_t nslots = static_cast<uint64_t>(nbins) + 2;
+  DevBuf table, bnd;
+  PA_TRY(table.alloc(nslots * sizeof(SlotT), st));
+  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  const int init_grid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+  k_gtable_init<WIDE><<<init_grid, 256, 0, st>>>(table.as<SlotT>(), nslots);
+  CUDA_TRY(cudaGetLastError());
+  const int64_t nchunks = (g->n + RS_CHUNK - 1) / RS_CHUNK;
+  PA_TRY(bnd.alloc(static_cast<size_t>(std::max<int64_t>(nchunks, 1)) * 2 * sizeof(RsPartial), st));
+  if (nchunks > 0) {
+    k_rs_init_bnd<<<static_cast<int>((nchunks * 2 + 255) / 256), 256, 0, st>>>(bnd.as<RsPartial>(), nchunks * 2);
+    CUDA_TRY(cudaGetLastError());
+  }
+  RsArgs a{};
+  a.ts = static_cast<const int64_t*>(g->key_data);
+  a.vals = val ? val->data : nullptr;
+  a.vvalid = val ? val->valid : nullptr;
+  a.voff = val ? val->bit_off : 0;
+  a.vw = val ? val->width : 8;
+  a.n = g->n;
+  a.spec = g->rs;
+  a.table = table.p;
+  a.bnd = bnd.as<RsPartial>();
+  a.nchunks = nchunks;
+  a.status = g->status.as<uint32_t>();
+  a.agg_mask = mask;
+  if (nchunks > 0) {
+    const int64_t warps_per_block = RS_THREADS / 32;
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((nchunks + warps_per_block - 1) / warps_per_block,
+                                                                           static_cast<int64_t>(g->num_sms) * 8)));
+    k_resample_scan<VC, WIDE><<<grid, RS_THREADS, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(g->ev[2], st));
+    k_resample_fixup<VC, WIDE><<<static_cast<int>((nchunks * 2 + 255) / 256), 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 4;
+  } else {
+    CUDA_TRY(cudaEventRecord(g->ev[2], st));
+  }
+  // occupied buckets -> first-appearance (= time) order -> GroupResult
+  const uint64_t max_groups = std::min<uint64_t>(nslots, static_cast<uint64_t>(g->n) + 2);
+  DevBuf c_first, c_slot, s_first, s_slot, cub_tmp;
+  PA_TRY(c_first.alloc(max_groups * 4, st));
+  PA_TRY(c_slot.alloc(max_groups * 4, st));
+  const int cgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+  k_gtable_compact<WIDE><<<cgrid, 256, 0, st>>>(table.as<SlotT>(), nslots, c_first.as<uint32_t>(), c_slot.as<uint32_t>(), g->status.as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  g->last_launches += 1;
+  uint32_t h_status[ST_WORDS];
+  CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_status[ST_UNSORTED]) return set_err(PA_ERR_INVALID, "resample: the index must be sorted ascending (Values falls before first bin / after last bin)");
+  const uint32_t G = h_status[ST_COUNTER];
+  g->G = G;
+  PA_TRY(alloc_result(g, G, WIDE, VC != VC_F));
+  if (G > 0) {
+    PA_TRY(s_first.alloc(static_cast<size_t>(G) * 4, st));
+    PA_TRY(s_slot.alloc(static_cast<size_t>(G) * 4, st));
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
+    PA_TRY(cub_tmp.alloc(tmp_bytes, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
+    k_gtable_gather<WIDE><<<(G + 255) / 256, 256, 0, st>>>(table.as<SlotT>(), static_cast<uint64_t>(nbins), s_slot.as<uint32_t>(), G, g->res);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 1;
+  }
+  CUDA_TRY(cudaEventRecord(g->ev[3], st));
+  return PA_OK;
 }
+
+int run_resample(pa_groupby* g, const Column* val, uint32_t mask, bool wide) {
+  const int vc = val ? val->vc : VC_I;
+  if (val && val->vc == VC_F && val->width != 4 && val->width != 8) return set_err(PA_ERR_INVALID, "bad float width");
+  if (wide) {
+    if (vc == VC_F) return run_resample_t<VC_F, true>(g, val, mask);
+    if (vc == VC_I) return run_resample_t<VC_I, true>(g, val, mask);
+    return run_resample_t<VC_U, true>(g, val, mask);
+  }
+  if (vc == VC_F) return run_resample_t<VC_F, false>(g, val, mask);
+  if (vc == VC_I) return run_resample_t<VC_I, false>(g, val, mask);
+  return run_resample_t<VC_U, false>(g, val, mask);
+}
+
+int64_t floor_div(int64_t a, int64_t b) {
+  int64_t q = a / b;
+  if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+  return q;
+}
+
+// adjustDatesAnchored (/root/reference/src/resample.cpp:85-178) on integer ticks; tz is not supported.
+void anchor_range(int64_t start, int64_t end, int64_t freq, bool closed_right, int origin, int64_t origin_custom,
+                  int64_t offset, int64_t ticks_per_day, int64_t* first, int64_t* last) {
+  int64_t f = start, l = end, o = 0;
+  switch (origin) {
+    case 1: o = f; break;                                            // Start
+    case 2: o = floor_div(f, ticks_per_day) * ticks_per_day; break;  // StartDay (default)
+    case 3: o = l; break;                                            // End
+    case 4: o = floor_div(l, ticks_per_day) * ticks_per_day; break;  // EndDay
+    case 5: o = origin_custom; break;                                // Custom
+    default: o = 0;                                                  // Epoch
+  }
+  o += offset;
+  const int64_t fo = (f - o) % freq, lo = (l - o) % freq;            // truncating %, like the reference
+  if (closed_right) {
+    f -= (fo > 0) ? fo : freq;
+    if (lo > 0) l += freq - lo;
+  } else {
+    if (fo > 0) f -= fo;
+    l += (lo > 0) ? freq - lo : freq;
+  }
+  *first = f;
+  *last = l;
+}
+
 }  // namespace
 
 extern "C" {
@@ -810,9 +929,53 @@ void pa_groupby_destroy(pa_groupby* g) {
 int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowSchema* index_schema, int64_t freq_ns,
                        int32_t closed_right, int32_t label_right, int32_t origin, int64_t origin_custom_ns,
                        int64_t offset_ns, const pa_options* opt, pa_groupby** out) {
-  (void)index; (void)index_schema; (void)freq_ns; (void)closed_right; (void)label_right; (void)origin;
-  (void)origin_custom_ns; (void)offset_ns; (void)opt; (void)out;
-  return set_err(PA_ERR_NOT_IMPLEMENTED, "resample path not built yet");
+  if (!index || !index_schema || !out) return set_err(PA_ERR_INVALID, "pa_resample_create: null argument");
+  if (freq_ns <= 0) return set_err(PA_ERR_INVALID, "FREQ must be positive");   // core.cpp:319-322
+  std::unique_ptr<pa_groupby> g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  g->keys.resize(1);
+  Column& ix = g->keys[0];
+  PA_TRY(load_column(index, index_schema, g->stream, g->device, &ix));
+  const char* f = index_schema->format;
+  const bool is_ts = f && f[0] == 't' && f[1] == 's';
+  if (!(is_ts || (f && f[0] == 'l')) || ix.width != 8)
+    return set_err(PA_ERR_INVALID, "axis must be a TimestampArray but got array of type '%s'", f ? f : "?");  // resample.cpp:213-216
+  if (ix.valid) return set_err(PA_ERR_NOT_IMPLEMENTED, "resample: null timestamps are not supported");
+  int64_t ticks_per_day = 86400LL * 1000000000LL;
+  if (is_ts) {
+    switch (f[2]) {
+      case 's': ticks_per_day = 86400LL; break;
+      case 'm': ticks_per_day = 86400LL * 1000; break;
+      case 'u': ticks_per_day = 86400LL * 1000000; break;
+      default: break;
+    }
+  }
+  g->n = ix.n;
+  if (g->n >= 0xFFFFFFFELL) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-2 rows per call; shard by row range");
+  g->resample = true;
+  g->index_format = f;
+  g->fields.assign(1, KeyField{});
+  g->key_data = ix.data;
+  g->key_width = 8;
+  g->rs = ResampleSpec{};
+  g->rs.freq = freq_ns;
+  g->rs.closed_right = closed_right != 0;
+  g->rs.label_off = label_right ? freq_ns : 0;
+  if (g->n > 0) {
+    int64_t ends[2];
+    CUDA_TRY(cudaMemcpyAsync(&ends[0], ix.data, 8, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(&ends[1], static_cast<const int64_t*>(ix.data) + (g->n - 1), 8, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    if (ends[1] < ends[0]) return set_err(PA_ERR_INVALID, "resample: the index must be sorted ascending");
+    int64_t first, last;
+    anchor_range(ends[0], ends[1], freq_ns, closed_right != 0, origin, origin_custom_ns, offset_ns, ticks_per_day, &first, &last);
+    if (first >= last) return set_err(PA_ERR_INVALID, "start date has to be less than end date");  // core.cpp:314-317
+    g->rs.first = first;
+    g->rs.nbins = (last - first) / freq_ns;
+    if (g->n < g->rs.nbins) return set_err(PA_ERR_NOT_IMPLEMENTED, "upSampling is not implemented.");  // resample.h:102-105
+  }
+  *out = g.release();
+  return PA_OK;
 }
 
 // ---- synthetic generator ----

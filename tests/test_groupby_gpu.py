@@ -24,8 +24,9 @@ def orc():
 
 
 def _both(pab, orc, frame, key, **kw):
+    from util import with_abs
     rb = frame if isinstance(frame, pa.RecordBatch) else pa.record_batch(frame)
-    return pab.GroupBy(key, rb, **kw), orc.OracleGroupBy(rb, key), rb
+    return pab.GroupBy(key, rb, **kw), orc.OracleGroupBy(with_abs(rb), key), rb
 
 
 def _cmp(gb, ora, rb, column, aggs, what, keys=("k",)):
@@ -189,7 +190,8 @@ def test_config3_multi_key_dictionary_nullable(pab, orc, path):
              "i": pa.array(rng.integers(-1000, 1000, n), pa.int64(), mask=rng.random(n) < 0.1)}
     rb = pa.record_batch(frame)
     gb = pab.GroupBy(["k1", "k2"], rb, path=path)
-    ora = orc.OracleGroupBy(rb, ["k1", "k2"])
+    from util import with_abs
+    ora = orc.OracleGroupBy(with_abs(rb), ["k1", "k2"])
     assert gb.groupSize() == ora.num_groups
     _cmp(gb, ora, rb, "f", ALL, f"multi-key f64 {path}", keys=("k1", "k2"))
     _cmp(gb, ora, rb, "i", ALL, f"multi-key i64 {path}", keys=("k1", "k2"))

@@ -1,0 +1,145 @@
+"""Time-bucket specialisation (pd::resample) on the GPU vs the oracle's restatement of
+resample.cpp / resample.h.  Needs a GPU: -m gpu."""
+import datetime as dt
+
+import numpy as np
+import pyarrow as pa
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+OHLC = ["first", "max", "min", "last", "sum"]
+ALL = ["sum", "mean", "count", "min", "max", "first", "last"]
+MIN = 60 * 10**9
+
+
+@pytest.fixture(scope="module")
+def pab():
+    import pandasarrow_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _minute_index(n):
+    base = int((dt.datetime(2000, 1, 1) - dt.datetime(1970, 1, 1)).total_seconds()) * 10**9
+    return pa.array([base + i * MIN for i in range(n)], pa.timestamp("ns"))
+
+
+def _ts(s):
+    return dt.datetime.strptime(s, "%Y-%m-%d %H:%M:%S")
+
+
+@pytest.mark.parametrize("closed_right,label_right,labels,sums", [
+    # /root/reference/tests/series_resample_test.cpp:17-30, :32-47, :49-69
+    (False, False, ["2000-01-01 00:00:00", "2000-01-01 00:03:00", "2000-01-01 00:06:00"], [3, 12, 21]),
+    (False, True, ["2000-01-01 00:03:00", "2000-01-01 00:06:00", "2000-01-01 00:09:00"], [3, 12, 21]),
+    (True, True, ["2000-01-01 00:00:00", "2000-01-01 00:03:00", "2000-01-01 00:06:00", "2000-01-01 00:09:00"],
+     [0, 6, 15, 15]),
+])
+def test_reference_golden_resample(pab, closed_right, label_right, labels, sums):
+    idx = _minute_index(9)
+    r = pab.resample({"v": pa.array(range(9), pa.int64())}, idx, 3 * MIN, closed_right=closed_right, label_right=label_right)
+    got = r.sum()
+    assert [t.replace(tzinfo=None) for t in r.index().to_pylist()] == [_ts(s) for s in labels]
+    assert got["v"].type == pa.int64() and got["v"].to_pylist() == sums
+    # series_resample_test.cpp:72-85: apply(sum + 5)
+    if not closed_right and not label_right:
+        assert [s + 5 for s in got["v"].to_pylist()] == [8, 17, 26]
+
+
+def _compare(pab, orc, ts, frame, freq, aggs, **kw):
+    """Bucket ORDER: the CUDA path emits buckets in time order (= strict first appearance).  The
+    reference inherits arrow::compute::Grouper's id order, which may swap buckets that first appear
+    inside the same internal mini-batch, so results are aligned by label before comparing.  When the
+    reference's own bin generation throws (resample.cpp:28-41), the CUDA path must fail as well."""
+    from util import abs_scale, assert_exact, assert_fp_close, with_abs
+    idx = pa.array(ts, pa.timestamp("ns"))
+    rb = with_abs(frame)
+    try:
+        ora = orc.resample(rb, idx, freq, **kw)
+    except orc.OracleError as e:
+        with pytest.raises(pab.PaError):
+            pab.resample(frame, idx, freq, **kw).sum()
+        return None
+    r = pab.resample(frame, idx, freq, **kw)
+    assert r.groupSize() == ora.num_groups
+    ours = r.index().cast(pa.int64()).to_numpy()
+    theirs = ora.unique().cast(pa.int64()).to_numpy()
+    assert r.index().type == ora.unique().type
+    assert (np.diff(ours) > 0).all(), "buckets must come out in time order"
+    assert np.array_equal(ours, np.sort(theirs)), "bucket labels differ"
+    perm = pa.array(np.searchsorted(ours, theirs))
+    for name in frame:
+        col = frame[name]
+        res = r.aggregate(col, aggs)
+        assert r.timing()["path"] == "resample"
+        for a in aggs:
+            got = res[a].take(perm)
+            if a == "mean":
+                want, valid = ora.agg("mean", name, nthreads=8, with_validity=True)
+                want = pa.array(want.to_numpy(zero_copy_only=False), pa.float64(), mask=~np.asarray(valid.to_numpy(zero_copy_only=False), dtype=bool))
+                assert_fp_close(got, want, f"{name} mean", abs_scale(ora, name, mean=True))
+            elif a == "sum" and pa.types.is_floating(col.type):
+                assert_fp_close(got, ora.agg("sum", name, nthreads=8), f"{name} sum", abs_scale(ora, name))
+            else:
+                assert_exact(got, ora.agg(a, name, nthreads=8), f"{name} {a}")
+    return r
+
+
+@pytest.mark.parametrize("closed_right", [False, True])
+@pytest.mark.parametrize("label_right", [False, True])
+@pytest.mark.parametrize("origin", ["start_day", "epoch", "start", "end", "end_day"])
+def test_resample_options(pab, orc, closed_right, label_right, origin):
+    from pandasarrow_b200 import hostgen as hg
+    n = 200_000
+    ts = hg.timestamps(n, step_ns=3_000_000_000)   # ~20 ticks per minute
+    rng = np.random.default_rng(1)
+    frame = {"px": pa.array(rng.random(n) * 100), "qty": pa.array(rng.integers(0, 1000, n), pa.int64())}
+    _compare(pab, orc, ts, frame, MIN, OHLC + ["count", "mean"], closed_right=closed_right, label_right=label_right,
+             origin=origin, offset_ns=7 * 10**9 if origin == "epoch" else 0)
+
+
+@pytest.mark.parametrize("n,step,freq", [(1, 1000, MIN), (31, 10**9, MIN), (33, 10**9, 5 * 10**9), (1025, 10**8, 10**9),
+                                         (5000, 60_000, MIN), (300_001, 60_000, MIN), (100_000, 10**9, 3600 * 10**9)])
+def test_config4_ticks_ohlc(pab, orc, n, step, freq):
+    # config 4: sorted timestamp[ns], fixed-width buckets, OHLC + sum on one fp64 column
+    from pandasarrow_b200 import hostgen as hg
+    ts = hg.timestamps(n, step_ns=step)
+    frame = {"px": pa.array(hg.vals(n))}
+    _compare(pab, orc, ts, frame, freq, OHLC)
+
+
+def test_resample_gaps_nulls_and_types(pab, orc):
+    rng = np.random.default_rng(9)
+    n = 120_000
+    # irregular: bursts and long gaps -> many empty buckets (which must not appear), duplicates in the index
+    gaps = rng.choice([1, 10**6, 10**9, 400 * 10**9], size=n, p=[0.3, 0.4, 0.29, 0.01])
+    ts = 1_600_000_000 * 10**9 + np.cumsum(gaps)
+    ts[1000:1100] = ts[1000]
+    frame = {"f": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.2),
+             "f32": pa.array(rng.standard_normal(n).astype(np.float32)),
+             "i": pa.array(rng.integers(-50, 50, n), pa.int32(), mask=rng.random(n) < 0.1),
+             "u": pa.array(rng.integers(0, 2**40, n).astype(np.uint64))}
+    _compare(pab, orc, ts, frame, MIN, ALL)
+
+
+def test_resample_errors(pab):
+    idx = _minute_index(9)
+    with pytest.raises(pab.PaError, match="upSampling"):       # resample.h:102-105
+        pab.resample({"v": pa.array(range(9), pa.int64())}, idx, 30 * 10**9)
+    with pytest.raises(pab.PaError, match="TimestampArray"):   # resample.cpp:213-216
+        pab.resample({"v": pa.array([1.0, 2.0])}, pa.array([1.5, 2.5]), MIN)
+    with pytest.raises(pab.PaError, match="positive"):
+        pab.resample({"v": pa.array(range(9), pa.int64())}, idx, 0)
+    ts = np.arange(5000, dtype=np.int64) * 10**9
+    ts[2500], ts[2600] = ts[2600], ts[2500]                    # unsorted in the middle
+    r = pab.resample({"v": pa.array(np.ones(5000))}, pa.array(ts, pa.timestamp("ns")), MIN)
+    with pytest.raises(pab.PaError, match="sorted"):
+        r.sum()
+    empty = pab.resample({"v": pa.array([], pa.float64())}, pa.array([], pa.timestamp("ns")), MIN)
+    assert empty.groupSize() == 0 and len(empty.sum()["v"]) == 0

