@@ -155,6 +155,10 @@ int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, st
  * first-appearance order.  Host array of length n_rows. */
 int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema);
 
+/* Global row number (pa_options.row_base + local row) of the first row of every group, uint64, in
+ * result order.  For merged handles: the minimum over all ranks. */
+int pa_groupby_first_rows(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema);
+
 /* Device time (ms, CUDA events on the handle's stream) of the last aggregate call: total and
  * per stage.  stage_ms[0]=key packing, [1]=scan kernel(s), [2]=merge/finalise, [3]=emit. */
 int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]);
@@ -178,6 +182,25 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
                        int64_t freq_ns, int32_t closed_right, int32_t label_right, int32_t origin,
                        int64_t origin_custom_ns, int64_t offset_ns, const pa_options* opt,
                        pa_groupby** out);
+
+/* ---- multi-GPU: row-range shards, hash-partitioned partial aggregates, merge ----
+ * The reference has no multi-device path.  Each rank aggregates its shard (pa_options.row_base =
+ * global row number of its first row), buckets its groups by owner = hash(key) % n_parts into
+ * fixed-size records, exchanges them with an all-to-all (NCCL over NVLink; the caller owns the
+ * communicator — see pandasarrow_b200/distributed.py), and merges what it received.  A record is
+ * PA_PARTIAL_WORDS 64-bit words. */
+#define PA_PARTIAL_WORDS 11
+/* Number of this handle's groups owned by each of n_parts ranks (host array, after an aggregate). */
+int pa_groupby_partials_count(pa_groupby* g, int32_t n_parts, int64_t* counts_host);
+/* Writes the records, grouped by owner rank in ascending order, into caller-provided DEVICE memory
+ * (capacity_records >= sum of counts).  Must follow pa_groupby_partials_count with the same n_parts. */
+int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records, int64_t capacity_records);
+/* Joins received records (DEVICE memory, grouped by source rank; counts_by_source on the host) by key,
+ * folds them in source-rank order and orders the groups by global first row.  The returned handle
+ * answers num_groups / unique / fetch for the aggregates in agg_mask.  value_format / key_format are
+ * the Arrow format strings of the value and (single) key column. */
+int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, int32_t n_sources, uint32_t agg_mask,
+                    const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out);
 
 /* ---- synthetic workload generator, used by bench.py and the tests so that the
  * same counter-based splitmix64 streams exist on host and device without PCIe staging.

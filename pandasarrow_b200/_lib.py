@@ -13,13 +13,15 @@ ARROW_DEVICE_CUDA = 2
 
 PA_AGG = {"sum": 1, "mean": 2, "count": 4, "min": 8, "max": 16, "first": 32, "last": 64}
 PA_PATH_AUTO, PA_PATH_LOWCARD, PA_PATH_GLOBAL = 0, 1, 2
+PA_PARTIAL_WORDS = 11
 
 # every symbol include/pa_b200.h declares
 EXPORTS = [
     "pa_last_error", "pa_version", "pa_options_init", "pa_device_count", "pa_groupby_create",
     "pa_groupby_num_groups", "pa_groupby_unique", "pa_groupby_aggregate", "pa_groupby_fetch",
     "pa_groupby_row_ids", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_sync",
-    "pa_groupby_destroy", "pa_resample_create", "pa_synth_keys_i64", "pa_synth_vals_f64",
+    "pa_groupby_destroy", "pa_resample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
+    "pa_merge_create", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
     "pa_synth_validity", "pa_synth_timestamps",
 ]
 
@@ -79,6 +81,7 @@ def load():
     L.pa_groupby_unique.argtypes = [P, C.c_int32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_aggregate.argtypes = [P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32]
     L.pa_groupby_fetch.argtypes = [P, C.c_uint32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
+    L.pa_groupby_first_rows.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_row_ids.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_last_timing.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pa_groupby_last_path.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -87,6 +90,10 @@ def load():
     L.pa_groupby_destroy.restype = None
     L.pa_resample_create.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_int64, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(PaOptions), C.POINTER(P)]
+    L.pa_groupby_partials_count.argtypes = [P, C.c_int32, C.POINTER(C.c_int64)]
+    L.pa_groupby_partials_export.argtypes = [P, C.c_int32, P, C.c_int64]
+    L.pa_merge_create.argtypes = [P, C.POINTER(C.c_int64), C.c_int32, C.c_uint32, C.c_char_p, C.c_char_p,
+                                  C.POINTER(PaOptions), C.POINTER(P)]
     L.pa_synth_keys_i64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, P]
     L.pa_synth_vals_f64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, P]
     L.pa_synth_validity.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32, P]

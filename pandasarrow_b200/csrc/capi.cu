@@ -17,6 +17,7 @@
 #include "emit.cuh"
 #include "gtable.cuh"
 #include "lowcard.cuh"
+#include "merge.cuh"
 #include "resample.cuh"
 
 using namespace pa;
@@ -196,6 +197,14 @@ struct pa_groupby {
   GroupResult res{};
   // outputs of the last aggregate
   std::vector<AggOut> outs;
+  bool last_wide = false;
+  int last_vc = VC_I, last_vw = 8;
+  std::string last_vfmt = "l";
+  // multi-GPU
+  int parts_n = 0;
+  std::vector<int64_t> parts_counts;
+  bool merged = false;
+  DevBuf m_count64, m_first_val, m_last_val, m_first_valid, m_last_valid, m_first_row_g;
   // bookkeeping
   DevBuf status;
   int last_path = 0, last_launches = 0;
@@ -441,6 +450,11 @@ int run_emit(pa_groupby* g, const Column* val, uint32_t mask) {
   e.vals = val ? val->data : nullptr;
   e.vvalid = val ? val->valid : nullptr;
   e.voff = val ? val->bit_off : 0;
+  if (g->merged) {
+    e.vc = g->last_vc; e.vw = g->last_vw;
+    e.m_first_val = g->m_first_val.as<uint64_t>(); e.m_last_val = g->m_last_val.as<uint64_t>();
+    e.m_first_valid = g->m_first_valid.as<uint8_t>(); e.m_last_valid = g->m_last_valid.as<uint8_t>();
+  }
   auto add = [&](uint32_t bit, const std::string& fmt, int width, bool nullable, void** vptr, uint32_t** bptr) -> int {
     g->outs.emplace_back();
     AggOut& o = g->outs.back();
@@ -459,7 +473,7 @@ int run_emit(pa_groupby* g, const Column* val, uint32_t mask) {
   g->outs.reserve(8);
   void* v;
   uint32_t* b;
-  const std::string vfmt = val ? val->format : "l";
+  const std::string vfmt = g->merged ? g->last_vfmt : (val ? val->format : "l");
   if (mask & AGG_SUM) { PA_TRY(add(AGG_SUM, sum_format(e.vc), 8, true, &v, &b)); e.o_sum = v; e.o_sum_valid = b; }
   if (mask & AGG_MEAN) { PA_TRY(add(AGG_MEAN, "g", 8, true, &v, &b)); e.o_mean = static_cast<double*>(v); e.o_mean_valid = b; }
   if (mask & AGG_COUNT) { PA_TRY(add(AGG_COUNT, "l", 8, false, &v, &b)); e.o_count = static_cast<int64_t*>(v); }
@@ -626,6 +640,11 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
     }
   }
   g->have_groups = true;
+  g->last_wide = wide;
+  g->last_vc = vc;
+  g->last_vw = val ? val->width : 8;
+  g->last_vfmt = val ? val->format : "l";
+  g->parts_n = 0;
   PA_TRY(run_emit(g, val, mask));
   CUDA_TRY(cudaEventRecord(g->ev[4], st));
   return PA_OK;
@@ -882,6 +901,27 @@ int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema
   return set_err(PA_ERR_NOT_IMPLEMENTED, "pa_groupby_row_ids: group materialisation is a SURVEY §8(f) 'next' row");
 }
 
+int pa_groupby_first_rows(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  if (!g || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(ensure_groups(g));
+  PA_TRY(ensure_device(g));
+  if (g->merged) return export_host(g->stream, "L", 8, g->G, g->m_first_row_g.p, nullptr, out, out_schema);
+  PA_TRY(export_host(g->stream, "I", 4, g->G, g->res.first_row, nullptr, out, out_schema));
+  // widen to uint64 and add the shard's row base on the host (G values)
+  auto* priv = static_cast<ExportPriv*>(out->private_data);
+  const uint32_t* src = static_cast<const uint32_t*>(priv->bufs[1]);
+  uint64_t* wide = static_cast<uint64_t*>(malloc(std::max<size_t>(static_cast<size_t>(g->G) * 8, 64)));
+  for (uint32_t i = 0; i < g->G; ++i) wide[i] = static_cast<uint64_t>(g->opt.row_base) + src[i];
+  free(priv->bufs[1]);
+  priv->bufs[1] = wide;
+  priv->ptrs[1] = wide;
+  delete static_cast<std::string*>(out_schema->private_data);
+  auto* f = new std::string("L");
+  out_schema->format = f->c_str();
+  out_schema->private_data = f;
+  return PA_OK;
+}
+
 int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]) {
   if (!g) return set_err(PA_ERR_INVALID, "null argument");
   PA_TRY(ensure_device(g));
@@ -974,6 +1014,159 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
     g->rs.nbins = (last - first) / freq_ns;
     if (g->n < g->rs.nbins) return set_err(PA_ERR_NOT_IMPLEMENTED, "upSampling is not implemented.");  // resample.h:102-105
   }
+  *out = g.release();
+  return PA_OK;
+}
+
+// ---- multi-GPU partial export / merge ----
+int pa_groupby_partials_count(pa_groupby* g, int32_t n_parts, int64_t* counts_host) {
+  if (!g || !counts_host || n_parts < 1 || n_parts > 64) return set_err(PA_ERR_INVALID, "bad argument (1 <= n_parts <= 64)");
+  if (!g->have_groups || g->merged) return set_err(PA_ERR_STATE, "partials need a finished local aggregate");
+  if (g->keys.size() != 1 && !g->resample) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of composite keys");
+  PA_TRY(ensure_device(g));
+  cudaStream_t st = g->stream;
+  DevBuf counts;
+  PA_TRY(counts.alloc(sizeof(uint64_t) * n_parts, st));
+  CUDA_TRY(cudaMemsetAsync(counts.p, 0, sizeof(uint64_t) * n_parts, st));
+  PartialsArgs a{};
+  a.r = g->res; a.G = g->G; a.nparts = n_parts; a.counts = counts.as<unsigned long long>();
+  if (g->G) {
+    k_partials_count<<<(g->G + 255) / 256, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
+  std::vector<uint64_t> h(n_parts);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), counts.p, sizeof(uint64_t) * n_parts, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  g->parts_n = n_parts;
+  g->parts_counts.assign(h.begin(), h.end());
+  for (int i = 0; i < n_parts; ++i) counts_host[i] = static_cast<int64_t>(h[i]);
+  return PA_OK;
+}
+
+int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records, int64_t capacity_records) {
+  if (!g || !dev_records) return set_err(PA_ERR_INVALID, "null argument");
+  if (g->parts_n != n_parts) return set_err(PA_ERR_STATE, "call pa_groupby_partials_count(n_parts=%d) first", n_parts);
+  if (capacity_records < static_cast<int64_t>(g->G)) return set_err(PA_ERR_INVALID, "record buffer too small");
+  PA_TRY(ensure_device(g));
+  cudaStream_t st = g->stream;
+  std::vector<uint64_t> prefix(n_parts, 0);
+  for (int i = 1; i < n_parts; ++i) prefix[i] = prefix[i - 1] + static_cast<uint64_t>(g->parts_counts[i - 1]);
+  DevBuf cursor;
+  PA_TRY(cursor.alloc(sizeof(uint64_t) * n_parts, st));
+  CUDA_TRY(cudaMemcpyAsync(cursor.p, prefix.data(), sizeof(uint64_t) * n_parts, cudaMemcpyHostToDevice, st));
+  PartialsArgs a{};
+  a.r = g->res; a.G = g->G; a.nparts = n_parts; a.row_base = g->opt.row_base;
+  a.vw = g->last_vw; a.wide = g->last_wide;
+  for (auto& o : g->outs) {
+    if (o.bit == AGG_FIRST) { a.first_vals = o.values.p; a.first_valid = o.valid.as<uint32_t>(); }
+    if (o.bit == AGG_LAST) { a.last_vals = o.values.p; a.last_valid = o.valid.as<uint32_t>(); }
+  }
+  a.cursor = cursor.as<unsigned long long>();
+  a.records = static_cast<uint64_t*>(dev_records);
+  if (g->G) {
+    k_partials_scatter<<<(g->G + 255) / 256, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));   // `prefix` and `cursor` die here; records are complete for the caller's collective
+  return PA_OK;
+}
+
+int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, int32_t n_sources, uint32_t agg_mask,
+                    const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out) {
+  if (!counts_by_source || n_sources < 1 || !value_format || !key_format || !out) return set_err(PA_ERR_INVALID, "null argument");
+  if (agg_mask & ~PA_AGG_ALL) return set_err(PA_ERR_INVALID, "bad aggregate mask");
+  std::unique_ptr<pa_groupby> g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  cudaStream_t st = g->stream;
+  g->merged = true;
+  g->keys.resize(1);
+  int kw = 8, kvc = VC_I;
+  PA_TRY(parse_format(key_format, &kw, &kvc));
+  g->keys[0].format = key_format;
+  g->keys[0].width = kw;
+  g->fields.assign(1, KeyField{});
+  g->fields[0].width = kw;
+  g->index_format = key_format;
+  PA_TRY(parse_format(value_format, &g->last_vw, &g->last_vc));
+  g->last_vfmt = value_format;
+  std::vector<uint64_t> off(n_sources + 1, 0);
+  for (int i = 0; i < n_sources; ++i) {
+    if (counts_by_source[i] < 0) return set_err(PA_ERR_INVALID, "negative record count");
+    off[i + 1] = off[i] + static_cast<uint64_t>(counts_by_source[i]);
+  }
+  const uint64_t nrec = off[n_sources];
+  if (nrec && !dev_records) return set_err(PA_ERR_INVALID, "null record buffer");
+  if (nrec >= 0xFFFFFFFFull) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-1 partial records per rank");
+  uint64_t cap = 1024;
+  while (cap < nrec * 2) cap <<= 1;
+  const uint64_t nslots = cap + 2;
+  DevBuf d_off, tkeys, idx, m_first, m_slot, s_first, s_slot, cub_tmp;
+  PA_TRY(d_off.alloc(sizeof(uint64_t) * (n_sources + 1), st));
+  CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(uint64_t) * (n_sources + 1), cudaMemcpyHostToDevice, st));
+  PA_TRY(tkeys.alloc(nslots * 8, st));
+  PA_TRY(idx.alloc(nslots * n_sources * 4, st));
+  const int fgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+  k_fill_u64<<<fgrid, 256, 0, st>>>(tkeys.as<unsigned long long>(), nslots, kEmptyKey);
+  CUDA_TRY(cudaMemsetAsync(idx.p, 0xFF, nslots * n_sources * 4, st));
+  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  PA_TRY(m_first.alloc(std::max<uint64_t>(nrec, 1) * 8, st));
+  PA_TRY(m_slot.alloc(std::max<uint64_t>(nrec, 1) * 4, st));
+  MergeArgs a{};
+  a.records = static_cast<const uint64_t*>(dev_records);
+  a.src_offset = d_off.as<uint64_t>();
+  a.nsrc = n_sources; a.nrec = nrec;
+  a.tkeys = tkeys.as<unsigned long long>(); a.cap_mask = cap - 1; a.idx = idx.as<uint32_t>();
+  a.status = g->status.as<uint32_t>();
+  a.m_first_row = m_first.as<uint64_t>(); a.m_slot = m_slot.as<uint32_t>();
+  a.vc = g->last_vc;
+  CUDA_TRY(cudaEventRecord(g->ev[0], st));
+  CUDA_TRY(cudaEventRecord(g->ev[1], st));
+  if (nrec) {
+    k_merge_insert<<<static_cast<int>((nrec + 255) / 256), 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
+  k_merge_compact<<<static_cast<int>((nslots + 255) / 256), 256, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(g->ev[2], st));
+  uint32_t h_status[ST_WORDS];
+  CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_status[ST_OVERFLOW]) return set_err(PA_ERR_CUDA, "merge table overflow");
+  const uint32_t G = h_status[ST_COUNTER];
+  g->G = G;
+  const bool wide = is_wide(agg_mask, g->last_vc);
+  g->last_wide = wide;
+  PA_TRY(alloc_result(g.get(), G, true, true));
+  PA_TRY(g->m_count64.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * 8, st));
+  g->res.count64 = g->m_count64.as<uint64_t>();
+  PA_TRY(g->m_first_val.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * 8, st));
+  PA_TRY(g->m_first_row_g.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * 8, st));
+  PA_TRY(g->m_last_val.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * 8, st));
+  PA_TRY(g->m_first_valid.alloc(std::max<uint32_t>(G, 1), st));
+  PA_TRY(g->m_last_valid.alloc(std::max<uint32_t>(G, 1), st));
+  if (G) {
+    PA_TRY(s_first.alloc(static_cast<size_t>(G) * 8, st));
+    PA_TRY(s_slot.alloc(static_cast<size_t>(G) * 4, st));
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, m_first.as<uint64_t>(), s_first.as<uint64_t>(), m_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 64, st));
+    PA_TRY(cub_tmp.alloc(tmp_bytes, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, m_first.as<uint64_t>(), s_first.as<uint64_t>(), m_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 64, st));
+    a.order = s_slot.as<uint32_t>();
+    a.G = G;
+    a.out = g->res;
+    a.o_first_val = g->m_first_val.as<uint64_t>(); a.o_last_val = g->m_last_val.as<uint64_t>();
+    a.o_first_valid = g->m_first_valid.as<uint8_t>(); a.o_last_valid = g->m_last_valid.as<uint8_t>();
+    a.o_first_row_g = g->m_first_row_g.as<uint64_t>();
+    k_merge_fold<<<(G + 255) / 256, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
+  CUDA_TRY(cudaEventRecord(g->ev[3], st));
+  g->have_groups = true;
+  g->last_launches = 4;
+  g->last_path = 4;
+  PA_TRY(run_emit(g.get(), nullptr, agg_mask));
+  CUDA_TRY(cudaEventRecord(g->ev[4], st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // local scratch (table, idx, sort buffers) is released after this point
   *out = g.release();
   return PA_OK;
 }

@@ -27,7 +27,19 @@ struct EmitArgs {
   void* o_max; uint32_t* o_max_valid;
   void* o_first; uint32_t* o_first_valid;
   void* o_last; uint32_t* o_last_valid;
+  // merged (multi-GPU) results carry first/last values with them instead of row numbers
+  const uint64_t* m_first_val; const uint64_t* m_last_val;
+  const uint8_t* m_first_valid; const uint8_t* m_last_valid;
 };
+
+__device__ __forceinline__ void store_raw(void* out, uint32_t g, uint64_t bits, int vw) {
+  switch (vw) {
+    case 8: static_cast<uint64_t*>(out)[g] = bits; break;
+    case 4: static_cast<uint32_t*>(out)[g] = static_cast<uint32_t>(bits); break;
+    case 2: static_cast<uint16_t*>(out)[g] = static_cast<uint16_t>(bits); break;
+    default: static_cast<uint8_t*>(out)[g] = static_cast<uint8_t>(bits); break;
+  }
+}
 
 __device__ __forceinline__ void store_narrow(void* out, uint32_t g, uint64_t bits, int vc, int vw) {
   // `bits` is the widened 64-bit representation (double bits for VC_F)
@@ -63,7 +75,7 @@ __device__ __forceinline__ uint64_t ord_to_wide(uint64_t o, int vc) {
 __global__ void __launch_bounds__(256) k_emit(EmitArgs a) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = g < a.G;
-  const uint32_t cnt = in ? a.r.count[g] : 0;
+  const uint64_t cnt = in ? (a.r.count64 ? a.r.count64[g] : static_cast<uint64_t>(a.r.count[g])) : 0;
   const bool has = cnt > 0;
   if (a.o_sum) {
     if (in) static_cast<uint64_t*>(a.o_sum)[g] = a.r.sum[g];
@@ -97,7 +109,10 @@ __global__ void __launch_bounds__(256) k_emit(EmitArgs a) {
     }
     store_valid_bit(a.o_max_valid, g, a.G, has);
   }
-  if (a.o_first) {
+  if (a.o_first && a.m_first_val) {
+    if (in) store_raw(a.o_first, g, a.m_first_val[g], a.vw);
+    store_valid_bit(a.o_first_valid, g, a.G, in && a.m_first_valid[g]);
+  } else if (a.o_first) {
     bool v = false;
     if (in) {
       const uint32_t row = a.r.first_row[g];
@@ -106,7 +121,10 @@ __global__ void __launch_bounds__(256) k_emit(EmitArgs a) {
     }
     store_valid_bit(a.o_first_valid, g, a.G, v);
   }
-  if (a.o_last) {
+  if (a.o_last && a.m_last_val) {
+    if (in) store_raw(a.o_last, g, a.m_last_val[g], a.vw);
+    store_valid_bit(a.o_last_valid, g, a.G, in && a.m_last_valid[g]);
+  } else if (a.o_last) {
     bool v = false;
     if (in) {
       const uint32_t row = a.r.last_row[g];

@@ -14,6 +14,7 @@ struct GroupResult {
   uint64_t* sum;        // raw bits: double (VC_F) or wrapping (u)int64
   double* dsum;         // sum of values converted to double (VC_I / VC_U mean); may be null for VC_F
   uint32_t* count;      // non-null values
+  uint64_t* count64;    // merged (multi-GPU) results only: 64-bit counts, overrides `count` when non-null
   uint32_t* first_row;  // local row index of the first / last row of the group
   uint32_t* last_row;
   uint64_t* min_ord;    // order-mapped min / max over non-null, non-NaN values

@@ -1,0 +1,98 @@
+"""Multi-GPU group-by: one process per GPU, rows sharded by contiguous range.
+
+    local aggregate (stages 1-3 on this rank's shard)
+      -> partial records bucketed by owner = hash(key) % world   (CUDA, pa_groupby_partials_*)
+      -> all-to-all of counts, then of records                   (torch.distributed: NCCL over NVLink)
+      -> merge by key in source-rank order + order by global first row   (CUDA, pa_merge_create)
+
+Each rank ends up owning the groups with hash(key) % world == rank; `gather_result` concatenates
+the owners' results on every rank and restores global first-appearance order.
+
+torch.distributed is plumbing only (rendezvous + the collective); the exchange helpers work on any
+backend, which is what the world_size-2 gloo tests exercise on CPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import PA_PARTIAL_WORDS
+
+REC_KEY, REC_FLAGS, REC_SUM, REC_DSUM, REC_COUNT, REC_FIRST_ROW = 0, 1, 2, 3, 4, 5
+
+
+def shard_rows(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range [begin, end) of `rank` (rank r owns rows [r*N/P, (r+1)*N/P))."""
+    return (rank * n_total) // world, ((rank + 1) * n_total) // world
+
+
+def _mix64(k: np.ndarray) -> np.ndarray:
+    """Host twin of hash_key64 (csrc/common.cuh)."""
+    k = k.astype(np.uint64, copy=True)
+    with np.errstate(over="ignore"):
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xFF51AFD7ED558CCD)
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xC4CEB9FE1A85EC53)
+        k ^= k >> np.uint64(33)
+    return k
+
+
+def owner_of(keys: np.ndarray, world: int, is_null: Optional[np.ndarray] = None) -> np.ndarray:
+    """Owner rank of every key (null keys live on rank 0) — must match owner_of() in csrc/merge.cuh."""
+    o = (_mix64(np.asarray(keys).view(np.uint64) if np.asarray(keys).dtype.itemsize == 8 else np.asarray(keys)) %
+         np.uint64(world)).astype(np.int64)
+    if is_null is not None:
+        o[np.asarray(is_null, dtype=bool)] = 0
+    return o
+
+
+def exchange_records(send, send_counts: Sequence[int], group=None):
+    """All-to-all of fixed-size records.  `send`: int64 tensor [sum(send_counts), PA_PARTIAL_WORDS],
+    grouped by destination rank.  Returns (recv tensor grouped by source rank, recv_counts)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    assert len(send_counts) == world
+    dev = send.device
+    sc = torch.tensor(list(send_counts), dtype=torch.int64, device=dev)
+    rc = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.tolist()]
+    recv = torch.empty((sum(recv_counts), PA_PARTIAL_WORDS), dtype=torch.int64, device=dev)
+    w = PA_PARTIAL_WORDS
+    dist.all_to_all_single(recv.view(-1), send.reshape(-1), output_split_sizes=[c * w for c in recv_counts],
+                           input_split_sizes=[int(c) * w for c in send_counts], group=group)
+    return recv, recv_counts
+
+
+def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_format: str, group=None, stream=None):
+    """Run the whole multi-GPU step for this rank.  `gb` is this rank's GroupBy over its row shard
+    (created with row_base = first global row of the shard).  Returns the owner-side MergedGroupBy."""
+    import torch
+    import torch.distributed as dist
+    from .groupby import MergedGroupBy
+    world = dist.get_world_size(group)
+    gb.aggregate(values, aggs, fetch=False)
+    counts = gb.partials_count(world)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    send = torch.empty((max(sum(counts), 1), PA_PARTIAL_WORDS), dtype=torch.int64, device=dev)
+    gb.partials_export(world, send.data_ptr(), send.shape[0])
+    recv, recv_counts = exchange_records(send[:sum(counts)], counts, group)
+    torch.cuda.synchronize()
+    merged = MergedGroupBy(recv.data_ptr(), recv_counts, aggs, value_format, key_format, device=dev.index, stream=stream)
+    merged._keep = (send, recv)
+    return merged
+
+
+def gather_result(local: Dict[str, "np.ndarray"], first_rows: "np.ndarray", group=None) -> Dict[str, "np.ndarray"]:
+    """All-gather the owners' result columns and restore global first-appearance order
+    (stable sort by global first row).  Host-side convenience for tests / small results."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts: List = [None] * world
+    dist.all_gather_object(parts, (local, first_rows), group=group)
+    fr = np.concatenate([p[1] for p in parts])
+    order = np.argsort(fr, kind="stable")
+    return {k: np.concatenate([p[0][k] for p in parts])[order] for k in local}

@@ -109,10 +109,11 @@ def _import(out_a, out_s) -> pa.Array:
     return pa.Array._import_from_c(C.addressof(out_a), C.addressof(out_s))
 
 
-def _options(expected_groups=0, path="auto", device=None, stream=None) -> PaOptions:
+def _options(expected_groups=0, path="auto", device=None, stream=None, row_base=0) -> PaOptions:
     o = PaOptions()
     _lib.load().pa_options_init(C.byref(o))
     o.expected_groups = int(expected_groups)
+    o.row_base = int(row_base)
     o.path = _PATHS[path]
     if device is not None:
         o.device = int(device)
@@ -132,7 +133,8 @@ class GroupBy:
     (DataFrame::group_by(ArrayPtr), dataframe.cpp:1231-1235)."""
 
     def __init__(self, key, frame=None, *, key_arrays: Optional[Sequence[Column]] = None, expected_groups: int = 0,
-                 path: str = "auto", device: Optional[int] = None, stream: Optional[int] = None, _handle=None):
+                 path: str = "auto", device: Optional[int] = None, stream: Optional[int] = None, row_base: int = 0,
+                 _handle=None):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self._frame = self._as_dict(frame)
@@ -151,7 +153,7 @@ class GroupBy:
         key_arrays = [self._normalise_key(k) for k in key_arrays]
         args, devs, schemas = _pack_args(key_arrays)
         self._key_args = args          # keys are borrowed until destroy
-        opt = _options(expected_groups, path, device, stream)
+        opt = _options(expected_groups, path, device, stream, row_base)
         try:
             _check(self._L.pa_groupby_create(devs, schemas, len(args), C.byref(opt), C.byref(self._h)))
         except Exception:
@@ -214,6 +216,12 @@ class GroupBy:
             out = pa.DictionaryArray.from_arrays(out, d)
         return out
 
+    def first_rows(self) -> pa.Array:
+        """Global row number of the first row of every group (result order)."""
+        a, s = ArrowArray(), ArrowSchema()
+        _check(self._L.pa_groupby_first_rows(self._h, C.byref(a), C.byref(s)))
+        return _import(a, s)
+
     # ---- aggregation core ----
     def aggregate(self, values: Column, aggs: Sequence[str], fetch: bool = True) -> Dict[str, pa.Array]:
         mask = 0
@@ -235,6 +243,15 @@ class GroupBy:
 
     def sync(self):
         _check(self._L.pa_groupby_sync(self._h))
+
+    # ---- multi-GPU: hash-partitioned partial aggregates (include/pa_b200.h) ----
+    def partials_count(self, n_parts: int) -> List[int]:
+        counts = (C.c_int64 * n_parts)()
+        _check(self._L.pa_groupby_partials_count(self._h, n_parts, counts))
+        return list(counts)
+
+    def partials_export(self, n_parts: int, records_ptr: int, capacity_records: int):
+        _check(self._L.pa_groupby_partials_export(self._h, n_parts, records_ptr, capacity_records))
 
     def timing(self) -> dict:
         total = C.c_double()
@@ -277,6 +294,23 @@ class GroupBy:
             r = self.aggregate(self._column(name), ["min", "max"])
             out[name + "_min"], out[name + "_max"] = r["min"], r["max"]
         return out
+
+
+class MergedGroupBy(GroupBy):
+    """Owner-side result of the multi-GPU merge: the groups whose hash(key) % world == rank."""
+
+    def __init__(self, records_ptr: int, counts_by_source: Sequence[int], aggs: Sequence[str], value_format: str,
+                 key_format: str, device: Optional[int] = None, stream: Optional[int] = None):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        self._frame, self._dicts, self.key_names, self._key_args = {}, [None], ["key"], []
+        mask = 0
+        for a in aggs:
+            mask |= PA_AGG[a]
+        counts = (C.c_int64 * len(counts_by_source))(*[int(c) for c in counts_by_source])
+        opt = _options(0, "auto", device, stream)
+        _check(self._L.pa_merge_create(records_ptr, counts, len(counts_by_source), mask, value_format.encode(),
+                                       key_format.encode(), C.byref(opt), C.byref(self._h)))
 
 
 class Resampler(GroupBy):
