@@ -1,0 +1,378 @@
+// Host-side façade over the C ABI — see pd_groupby.h.  No computation on the path happens here:
+// columns are exported through the Arrow C Data Interface, results imported back.
+#include "pd_groupby.h"
+
+#include <arrow/c/bridge.h>
+#include <arrow/compute/api.h>
+
+#include <algorithm>
+#include <cctype>
+#include <stdexcept>
+
+#include "../../../include/pa_b200.h"
+
+namespace pd {
+
+namespace {
+
+[[noreturn]] void throw_pa(const char* what) { throw std::runtime_error(std::string(what) + ": " + pa_last_error()); }
+
+arrow::Status pa_status(const char* what) { return arrow::Status::Invalid(what, ": ", pa_last_error()); }
+
+// RAII export of one host Arrow array as ArrowDeviceArray(CPU) + ArrowSchema
+struct Exported {
+  ArrowDeviceArray dev{};
+  ArrowSchema schema{};
+  explicit Exported(const arrow::Array& a) {
+    ThrowOnFailure(arrow::ExportArray(a, &dev.array, &schema));
+    dev.device_id = -1;
+    dev.device_type = ARROW_DEVICE_CPU;
+  }
+  ~Exported() {
+    if (dev.array.release) dev.array.release(&dev.array);
+    if (schema.release) schema.release(&schema);
+  }
+  Exported(const Exported&) = delete;
+};
+
+arrow::Result<ArrayPtr> import_result(ArrowArray* a, ArrowSchema* s) { return arrow::ImportArray(a, s); }
+
+ArrayPtr strip_validity(const ArrayPtr& a) {
+  // GROUPBY_NUMERIC_AGG (pd_core_macros.h:32,67) copies `.value` of every per-group scalar into a plain
+  // std::vector<T>, so nulls (all-null groups) come out as valid zeros.
+  if (a->null_count() == 0) return a;
+  auto d = a->data()->Copy();
+  d->buffers[0] = nullptr;
+  d->null_count = 0;
+  return arrow::MakeArray(d);
+}
+
+constexpr uint32_t kSum = PA_AGG_SUM, kMean = PA_AGG_MEAN, kCount = PA_AGG_COUNT, kMin = PA_AGG_MIN, kMax = PA_AGG_MAX,
+                   kFirst = PA_AGG_FIRST, kLast = PA_AGG_LAST;
+
+int origin_code(TimeGrouperOrigin::Type t) {
+  switch (t) {
+    case TimeGrouperOrigin::Epoch: return 0;
+    case TimeGrouperOrigin::Start: return 1;
+    case TimeGrouperOrigin::StartDay: return 2;
+    case TimeGrouperOrigin::End: return 3;
+    case TimeGrouperOrigin::EndDay: return 4;
+    default: return 5;
+  }
+}
+
+}  // namespace
+
+std::pair<std::string, int> splitTimeSpan(std::string const& freq) {
+  auto it = std::find_if(freq.begin(), freq.end(), [](unsigned char c) { return std::isalpha(c); });
+  std::string unit(it, freq.end());
+  int value = 1;
+  if (it != freq.begin()) value = std::stoi(std::string(freq.begin(), it));
+  else if (std::any_of(freq.begin(), freq.end(), [](unsigned char c) { return std::isdigit(c); }))
+    throw std::runtime_error("Invalid time offset " + freq);
+  return {unit, value};
+}
+
+// ------------------------------ containers ------------------------------
+DataFrame::DataFrame(std::shared_ptr<arrow::RecordBatch> rb, ArrayPtr index) : m_array(std::move(rb)), m_index(std::move(index)) {
+  if (m_array && !m_index) m_index = range(0, m_array->num_rows());
+}
+
+DataFrame::DataFrame(std::shared_ptr<arrow::Schema> const& schema, int64_t num_rows, arrow::ArrayVector const& arrays, ArrayPtr index)
+    : m_array(arrow::RecordBatch::Make(schema, num_rows, arrays)), m_index(std::move(index)) {
+  if (!m_index) m_index = range(0, num_rows);
+}
+
+void DataFrame::init(std::shared_ptr<arrow::Schema> schema, arrow::ArrayVector const& arrays) {
+  const int64_t n = arrays.empty() ? 0 : arrays[0]->length();
+  m_array = arrow::RecordBatch::Make(std::move(schema), n, arrays);
+  if (!m_index) m_index = range(0, n);
+}
+
+Series DataFrame::operator[](std::string const& name) const {
+  auto col = m_array->GetColumnByName(name);
+  if (!col) throw std::runtime_error("Invalid column: " + name);
+  return Series(col, m_index, name);
+}
+
+GroupBy DataFrame::group_by(const std::string& key) const { return GroupBy(key, *this); }
+
+GroupBy DataFrame::group_by(const ArrayPtr& keyArray) const {
+  const auto key = "__RESERVED_GROUP_KEY__";
+  auto rb = ReturnOrThrowOnFailure(m_array->AddColumn(static_cast<int>(num_columns()), key, keyArray));
+  return GroupBy(key, DataFrame(rb, m_index));
+}
+
+GroupBy Series::group_by(const ArrayPtr& key) const {
+  DataFrame df(arrow::schema({arrow::field(m_name, m_array->type())}), m_array->length(), {m_array}, m_index);
+  return df.group_by(key);
+}
+
+Resampler DataFrame::resample(std::string const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                              time_duration const& offset, std::string const& tz) const {
+  return pd::resample(*this, rule, closed_right, label_right, origin, offset, tz);
+}
+
+Resampler Series::resample(std::string const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                           time_duration const& offset, std::string const& tz) const {
+  return pd::resample(*this, rule, closed_right, label_right, origin, offset, tz);
+}
+
+Resampler DataFrame::downsample(std::string const& rule, bool closed_label_right, bool weekStartsMonday, bool startEpoch) const {
+  // dataframe.cpp:1265-1290: per-row label = Floor/CeilTemporal(index) — the same Arrow call as the
+  // reference (a host-side element-wise relabel; moving it onto the GPU is SURVEY §8f-3) — then the
+  // GPU hash group-by on the labels.
+  namespace ac = arrow::compute;
+  static const bool init = [] { return ac::Initialize().ok(); }();
+  (void)init;
+  const auto [unit, value] = splitTimeSpan(rule);
+  ac::CalendarUnit cu;
+  switch (unit.empty() ? ' ' : unit[0]) {
+    case 'N': cu = ac::CalendarUnit::NANOSECOND; break;
+    case 'U': cu = ac::CalendarUnit::MICROSECOND; break;
+    case 'L': cu = ac::CalendarUnit::MILLISECOND; break;
+    case 'S': cu = ac::CalendarUnit::SECOND; break;
+    case 'T': cu = ac::CalendarUnit::MINUTE; break;
+    case 'H': cu = ac::CalendarUnit::HOUR; break;
+    case 'D': cu = ac::CalendarUnit::DAY; break;
+    case 'W': cu = ac::CalendarUnit::WEEK; break;
+    case 'M': cu = ac::CalendarUnit::MONTH; break;
+    case 'Q': cu = ac::CalendarUnit::QUARTER; break;
+    case 'Y': cu = ac::CalendarUnit::YEAR; break;
+    default: throw std::runtime_error("Invalid time offset " + rule);
+  }
+  ac::RoundTemporalOptions opt(value, cu, weekStartsMonday, false, startEpoch);
+  auto binned = ReturnOrThrowOnFailure(closed_label_right ? ac::CeilTemporal(m_index, opt) : ac::FloorTemporal(m_index, opt)).make_array();
+  if ((!unit.empty() && unit.back() == 'E') || unit == "M" || unit == "W" || unit == "Y" || unit == "Q") {
+    auto one_day = arrow::MakeScalar(arrow::date32(), 1L).MoveValueUnsafe();
+    auto d = ReturnOrThrowOnFailure(ac::Subtract(binned, one_day));
+    d = ReturnOrThrowOnFailure(ac::Cast(d, arrow::int64()));
+    binned = ReturnOrThrowOnFailure(ac::Cast(d, arrow::timestamp(arrow::TimeUnit::NANO))).make_array();
+  }
+  return Resampler(DataFrame(m_array, binned));
+}
+
+// ------------------------------ GroupBy ------------------------------
+GroupBy::GroupBy(const std::string& key, DataFrame frame) : df(std::move(frame)) {
+  if (!df.m_array) return;   // dataframe.cpp:1574-1576
+  if (key == "__resampler_idx__") key_array = df.indexArray();
+  else key_array = df[key].array();   // throws std::runtime_error for an unknown column
+  if (!key_array) throw std::runtime_error("frame has no index");
+  ArrayPtr to_export = key_array;
+  if (key_array->type_id() == arrow::Type::STRING || key_array->type_id() == arrow::Type::LARGE_STRING) {
+    // utf8 keys: dictionary-encode (first-appearance ordered) and group on the indices; hashing raw
+    // strings on the GPU is SURVEY §8f.
+    static const bool init = [] { return arrow::compute::Initialize().ok(); }();
+    (void)init;
+    auto enc = ReturnOrThrowOnFailure(arrow::compute::DictionaryEncode(key_array)).make_array();
+    to_export = enc;
+  }
+  if (to_export->type_id() == arrow::Type::DICTIONARY) {
+    auto d = std::static_pointer_cast<arrow::DictionaryArray>(to_export);
+    key_dictionary = d->dictionary();
+    key_array = to_export;
+  }
+  Exported k(*to_export);
+  pa_options opt;
+  pa_options_init(&opt);
+  if (pa_groupby_create(&k.dev, &k.schema, 1, &opt, &handle) != PA_OK) throw_pa("GroupBy");
+}
+
+GroupBy::GroupBy(GroupBy&& o) noexcept { *this = std::move(o); }
+GroupBy& GroupBy::operator=(GroupBy&& o) noexcept {
+  if (this != &o) {
+    if (handle) pa_groupby_destroy(handle);
+    df = std::move(o.df); handle = o.handle; o.handle = nullptr;
+    key_array = std::move(o.key_array); key_dictionary = std::move(o.key_dictionary); uniqueKeys = std::move(o.uniqueKeys);
+  }
+  return *this;
+}
+GroupBy::~GroupBy() {
+  if (handle) pa_groupby_destroy(handle);
+}
+
+size_t GroupBy::groupSize() const {
+  if (!handle) return 0;
+  int64_t n = 0;
+  if (pa_groupby_num_groups(handle, &n) != PA_OK) throw_pa("groupSize");
+  return static_cast<size_t>(n);
+}
+
+ArrayPtr GroupBy::unique() const {
+  if (uniqueKeys || !handle) return uniqueKeys;
+  ArrowArray a;
+  ArrowSchema s;
+  if (pa_groupby_unique(handle, 0, &a, &s) != PA_OK) throw_pa("unique");
+  auto arr = ReturnOrThrowOnFailure(import_result(&a, &s));
+  if (key_dictionary) {
+    // back to the key's own type: take(dictionary, indices) — G elements
+    static const bool init = [] { return arrow::compute::Initialize().ok(); }();
+    (void)init;
+    arr = ReturnOrThrowOnFailure(arrow::compute::Take(key_dictionary, arr)).make_array();
+  }
+  uniqueKeys = arr;
+  return uniqueKeys;
+}
+
+arrow::Result<arrow::ArrayVector> GroupBy::aggregate(std::string const& column, uint32_t mask, bool drop_validity) {
+  if (!handle) return arrow::Status::Invalid("GroupBy on an empty frame");
+  auto col = df.m_array->GetColumnByName(column);
+  if (!col) return arrow::Status::KeyError("Invalid column: ", column);
+  Exported v(*col);
+  if (pa_groupby_aggregate(handle, &v.dev, &v.schema, mask) != PA_OK) return pa_status("aggregate");
+  arrow::ArrayVector out;
+  for (uint32_t bit = 1; bit <= PA_AGG_LAST; bit <<= 1) {
+    if (!(mask & bit)) continue;
+    ArrowArray a;
+    ArrowSchema s;
+    if (pa_groupby_fetch(handle, bit, &a, &s) != PA_OK) return pa_status("fetch");
+    ARROW_ASSIGN_OR_RAISE(auto arr, import_result(&a, &s));
+    out.push_back(drop_validity ? strip_validity(arr) : arr);
+  }
+  return out;
+}
+
+arrow::Result<DataFrame> GroupBy::frameOf(std::vector<std::string> const& args, uint32_t bit, bool drop_validity, bool with_index) {
+  arrow::FieldVector fields;
+  arrow::ArrayVector arrays;
+  for (auto const& arg : args) {
+    ARROW_ASSIGN_OR_RAISE(auto r, aggregate(arg, bit, drop_validity));
+    // the reference labels the result with the INPUT field (pd_core_macros.h:11,44,85,111) even when the
+    // aggregate widened the dtype; the data dtype is authoritative (its tests read through the data)
+    fields.push_back(arrow::field(arg, r[0]->type()));
+    arrays.push_back(r[0]);
+  }
+  return DataFrame(arrow::schema(fields), static_cast<int64_t>(groupSize()), arrays, with_index ? unique() : nullptr);
+}
+
+arrow::Result<Series> GroupBy::seriesOf(std::string const& arg, uint32_t bit, bool drop_validity, bool with_index) {
+  ARROW_ASSIGN_OR_RAISE(auto r, aggregate(arg, bit, drop_validity));
+  return Series(r[0], with_index ? unique() : nullptr, arg);
+}
+
+// GROUPBY_NUMERIC_AGG(mean,double) / (count,int64_t): dataframe.cpp:1512,1526
+arrow::Result<DataFrame> GroupBy::mean(std::vector<std::string> const& args) { return frameOf(args, kMean, true, true); }
+arrow::Result<Series> GroupBy::mean(std::string const& arg) { return seriesOf(arg, kMean, true, true); }
+arrow::Result<DataFrame> GroupBy::count(std::vector<std::string> const& args) { return frameOf(args, kCount, true, true); }
+arrow::Result<Series> GroupBy::count(std::string const& arg) { return seriesOf(arg, kCount, true, true); }
+// GROUPBY_AGG(max|min|sum): dataframe.cpp:1530-1534
+arrow::Result<DataFrame> GroupBy::max(std::vector<std::string> const& args) { return frameOf(args, kMax, false, true); }
+arrow::Result<Series> GroupBy::max(std::string const& arg) { return seriesOf(arg, kMax, false, true); }
+arrow::Result<DataFrame> GroupBy::min(std::vector<std::string> const& args) { return frameOf(args, kMin, false, true); }
+arrow::Result<Series> GroupBy::min(std::string const& arg) { return seriesOf(arg, kMin, false, true); }
+arrow::Result<DataFrame> GroupBy::sum(std::vector<std::string> const& args) { return frameOf(args, kSum, false, true); }
+arrow::Result<Series> GroupBy::sum(std::string const& arg) { return seriesOf(arg, kSum, false, true); }
+// dataframe.cpp:1698-1806: first(vector) is indexed by the keys, first(string) is not (:1748),
+// last(vector) is not (:1781), last(string) is (:1805)
+arrow::Result<DataFrame> GroupBy::first(std::vector<std::string> const& args) { return frameOf(args, kFirst, false, true); }
+arrow::Result<Series> GroupBy::first(std::string const& arg) { return seriesOf(arg, kFirst, false, false); }
+arrow::Result<DataFrame> GroupBy::last(std::vector<std::string> const& args) { return frameOf(args, kLast, false, false); }
+arrow::Result<Series> GroupBy::last(std::string const& arg) { return seriesOf(arg, kLast, false, true); }
+
+// dataframe.cpp:1602-1696: one pass, two columns; no key index
+arrow::Result<DataFrame> GroupBy::min_max(std::vector<std::string> const& args) {
+  arrow::FieldVector fields;
+  arrow::ArrayVector arrays;
+  for (auto const& arg : args) {
+    ARROW_ASSIGN_OR_RAISE(auto r, aggregate(arg, kMin | kMax, false));
+    fields.push_back(arrow::field(arg + "_min", r[0]->type()));
+    fields.push_back(arrow::field(arg + "_max", r[1]->type()));
+    arrays.push_back(r[0]);
+    arrays.push_back(r[1]);
+  }
+  return DataFrame(arrow::schema(fields), static_cast<int64_t>(groupSize()), arrays);
+}
+arrow::Result<DataFrame> GroupBy::min_max(std::string const& arg) {
+  ARROW_ASSIGN_OR_RAISE(auto r, aggregate(arg, kMin | kMax, false));
+  return DataFrame(arrow::schema({arrow::field("min", r[0]->type()), arrow::field("max", r[1]->type())}),
+                   static_cast<int64_t>(groupSize()), {r[0], r[1]});
+}
+
+// ------------------------------ Resampler ------------------------------
+Resampler::Resampler(DataFrame const& _df) : GroupBy("__resampler_idx__", _df) {}
+
+Resampler::Resampler(DataFrame const& _df, int64_t freq_ns, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                     int64_t offset_ns) {
+  df = _df;
+  key_array = df.indexArray();
+  if (!key_array) throw std::runtime_error("frame has no index");
+  Exported k(*key_array);
+  pa_options opt;
+  pa_options_init(&opt);
+  if (pa_resample_create(&k.dev, &k.schema, freq_ns, closed_right, label_right, origin_code(origin.type), origin.custom_ns,
+                         offset_ns, &opt, &handle) != PA_OK)
+    throw_pa("resample");
+}
+
+arrow::Result<DataFrame> Resampler::frameOfAll(std::string const& name) {
+  // RESAMPLE_GROUP_BY_FUNCTION (group_by.h:249-253): GroupBy::name(all columns)->setIndex(unique())
+  const auto cols = getDF().columnNames();
+  arrow::Result<DataFrame> r = arrow::Status::NotImplemented(name);
+  if (name == "mean") r = GroupBy::mean(cols);
+  else if (name == "count") r = GroupBy::count(cols);
+  else if (name == "max") r = GroupBy::max(cols);
+  else if (name == "min") r = GroupBy::min(cols);
+  else if (name == "sum") r = GroupBy::sum(cols);
+  else if (name == "first") r = GroupBy::first(cols);
+  else if (name == "last") r = GroupBy::last(cols);
+  ARROW_RETURN_NOT_OK(r.status());
+  return r->setIndex(unique());
+}
+
+namespace {
+time_duration rule_to_duration(std::string const& rule) {
+  auto [unit, value] = splitTimeSpan(rule);   // resample.h:61-86
+  if (unit == "T" || unit == "min") return minutes(value);
+  if (unit == "S") return seconds(value);
+  if (unit == "L" || unit == "ms") return milliseconds(value);
+  if (unit == "U" || unit == "us") return microseconds(value);
+  if (unit == "N" || unit == "ns") return nanoseconds(value);
+  throw std::runtime_error("DateOffset rules (" + rule + ") are not part of the B200 resample path yet (SURVEY 8f-3)");
+}
+}  // namespace
+
+Resampler resample(DataFrame const& df, time_duration const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                   time_duration const& offset, std::string const& tz) {
+  if (!tz.empty()) throw std::runtime_error("resample: tz is not supported");
+  return Resampler(df, rule.count(), closed_right, label_right, origin, offset.count());
+}
+Resampler resample(DataFrame const& df, std::string const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                   time_duration const& offset, std::string const& tz) {
+  return resample(df, rule_to_duration(rule), closed_right, label_right, origin, offset, tz);
+}
+Resampler resample(Series const& s, time_duration const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                   time_duration const& offset, std::string const& tz) {
+  // resample.h:109-115
+  DataFrame df(arrow::schema({arrow::field(s.name(), s.dtype())}), s.size(), {s.array()}, s.indexArray());
+  return resample(df, rule, closed_right, label_right, origin, offset, tz);
+}
+Resampler resample(Series const& s, std::string const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                   time_duration const& offset, std::string const& tz) {
+  return resample(s, rule_to_duration(rule), closed_right, label_right, origin, offset, tz);
+}
+
+// ------------------------------ helpers ------------------------------
+ArrayPtr range(int64_t start, int64_t end) {
+  arrow::Int64Builder b;
+  ThrowOnFailure(b.Reserve(std::max<int64_t>(end - start, 0)));
+  for (int64_t i = start; i < end; ++i) b.UnsafeAppend(i);
+  return ReturnOrThrowOnFailure(b.Finish());
+}
+
+ArrayPtr date_range(int64_t start_ns, int periods, time_duration freq) {
+  arrow::TimestampBuilder b(arrow::timestamp(arrow::TimeUnit::NANO), arrow::default_memory_pool());
+  for (int i = 0; i < periods; ++i) ThrowOnFailure(b.Append(start_ns + i * freq.count()));
+  return ReturnOrThrowOnFailure(b.Finish());
+}
+
+int64_t ns_from_ymd(int y, int m, int d) {
+  // days from civil (Howard Hinnant)
+  y -= m <= 2;
+  const int64_t era = (y >= 0 ? y : y - 399) / 400;
+  const unsigned yoe = static_cast<unsigned>(y - era * 400);
+  const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return (era * 146097 + static_cast<int64_t>(doe) - 719468) * 86400LL * 1000000000LL;
+}
+
+}  // namespace pd

@@ -1,0 +1,276 @@
+// pd_groupby.h — host-side C++ façade with the reference's class surface for the hot path, bound
+// to the CUDA library through the C ABI (include/pa_b200.h) instead of arrow::compute.
+//
+//   pd::GroupBy     <- /root/reference/src/group_by.h:22-247, dataframe.cpp:1512-1806
+//   pd::Resampler   <- /root/reference/src/group_by.h:255-299
+//   pd::resample    <- /root/reference/src/resample.h:51-122
+//   pd::DataFrame::group_by / resample / downsample   <- dataframe.cpp:1227-1290
+//   pd::Series::resample / group_by                   <- series.cpp:351-359 (+ north_star: Series::group_by)
+//
+// Same names, argument meaning, result shapes and error behaviour (constructors throw
+// std::runtime_error, aggregations return arrow::Result) as the reference.  pd::DataFrame and
+// pd::Series here are only the thin containers the path needs (a RecordBatch / Array plus an
+// index), not the reference's ~300-method wrappers (out of scope).
+//
+// Not carried over (SURVEY.md §8f "next"): group materialisation (group(), MakeSubDataFrame,
+// apply*, orderedGroups) and the aggregates outside sum/mean/count/min/max/first/last/min_max;
+// those methods exist and return arrow::Status::NotImplemented.
+#pragma once
+#include <arrow/api.h>
+
+#include <chrono>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+struct pa_groupby;
+
+namespace pd {
+
+using ArrayPtr = std::shared_ptr<arrow::Array>;
+using ScalarPtr = std::shared_ptr<arrow::Scalar>;
+using time_duration = std::chrono::nanoseconds;   // boost::posix_time::time_duration in the reference
+
+inline time_duration minutes(int64_t n) { return std::chrono::minutes(n); }
+inline time_duration seconds(int64_t n) { return std::chrono::seconds(n); }
+inline time_duration milliseconds(int64_t n) { return std::chrono::milliseconds(n); }
+inline time_duration microseconds(int64_t n) { return std::chrono::microseconds(n); }
+inline time_duration nanoseconds(int64_t n) { return std::chrono::nanoseconds(n); }
+
+// core.h:79-91
+struct TimeGrouperOrigin {
+  enum Type { Epoch, Start, StartDay, End, EndDay, Custom } type{StartDay};
+  int64_t custom_ns{0};
+};
+
+// core.h:181-194
+template <class T>
+T ReturnOrThrowOnFailure(arrow::Result<T>&& result) {
+  if (result.ok()) return result.MoveValueUnsafe();
+  throw std::runtime_error(result.status().ToString());
+}
+inline void ThrowOnFailure(arrow::Status&& status) {
+  if (!status.ok()) throw std::runtime_error(status.ToString());
+}
+
+// core.cpp:110-133
+std::pair<std::string, int> splitTimeSpan(std::string const& freq);
+
+// scalar.h:62-241 (reading results only)
+class Scalar {
+ public:
+  Scalar() = default;
+  explicit Scalar(ScalarPtr s) : scalar(std::move(s)) {}
+  template <class T>
+  T as() const;
+  bool isValid() const { return scalar && scalar->is_valid; }
+  ScalarPtr value() const { return scalar; }
+  bool operator==(int64_t v) const { return isValid() && as<int64_t>() == v; }
+  bool operator==(double v) const { return isValid() && as<double>() == v; }
+  ScalarPtr scalar;
+};
+
+class GroupBy;
+class Resampler;
+class DataFrame;
+
+class Series {
+ public:
+  Series() = default;
+  Series(ArrayPtr array, ArrayPtr index, std::string name = "") : m_array(std::move(array)), m_index(std::move(index)), m_name(std::move(name)) {}
+  const ArrayPtr& array() const { return m_array; }
+  const ArrayPtr& indexArray() const { return m_index; }
+  const std::string& name() const { return m_name; }
+  std::shared_ptr<arrow::DataType> dtype() const { return m_array->type(); }
+  int64_t size() const { return m_array ? m_array->length() : 0; }
+  Scalar operator[](int64_t i) const { return Scalar(ReturnOrThrowOnFailure(m_array->GetScalar(i))); }
+  template <class T>
+  std::vector<T> values() const;
+  // series.cpp:351-359
+  Resampler resample(std::string const& rule, bool closed_right = false, bool label_right = false,
+                     TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0),
+                     std::string const& tz = "") const;
+  // north_star: Series::group_by — the analogue of resample.h:109-115 (wrap into a one-column frame)
+  GroupBy group_by(const ArrayPtr& key) const;
+
+ private:
+  ArrayPtr m_array, m_index;
+  std::string m_name;
+};
+
+class DataFrame {
+ public:
+  DataFrame() = default;
+  explicit DataFrame(std::shared_ptr<arrow::RecordBatch> rb, ArrayPtr index = nullptr);
+  // dataframe.h:87-93
+  DataFrame(std::shared_ptr<arrow::Schema> const& schema, int64_t num_rows, arrow::ArrayVector const& arrays, ArrayPtr index = nullptr);
+  // (index, pair{name, vector}...) — the form the reference's tests use
+  template <class... Pairs>
+  DataFrame(ArrayPtr index, Pairs&&... cols) : m_index(std::move(index)) {
+    arrow::FieldVector fields;
+    arrow::ArrayVector arrays;
+    (addColumn(fields, arrays, cols.first, cols.second), ...);
+    init(arrow::schema(fields), arrays);
+  }
+  template <class T>
+  explicit DataFrame(std::map<std::string, std::vector<T>> const& cols) {
+    arrow::FieldVector fields;
+    arrow::ArrayVector arrays;
+    for (auto const& [name, v] : cols) addColumn(fields, arrays, name, v);
+    init(arrow::schema(fields), arrays);
+  }
+
+  const std::shared_ptr<arrow::RecordBatch>& array() const { return m_array; }
+  const ArrayPtr& indexArray() const { return m_index; }
+  int64_t num_rows() const { return m_array ? m_array->num_rows() : 0; }
+  int64_t num_columns() const { return m_array ? m_array->num_columns() : 0; }
+  std::vector<std::string> columnNames() const { return m_array->schema()->field_names(); }
+  Series operator[](std::string const& name) const;
+  Scalar at(int64_t row, int64_t col) const { return Scalar(ReturnOrThrowOnFailure(m_array->column(static_cast<int>(col))->GetScalar(row))); }
+  DataFrame setIndex(ArrayPtr const& index) const { return DataFrame(m_array, index); }
+
+  // dataframe.cpp:1227-1235
+  GroupBy group_by(const std::string& key) const;
+  GroupBy group_by(const ArrayPtr& keyArray) const;
+  // dataframe.cpp:1254-1262
+  Resampler resample(std::string const& rule, bool closed_right = false, bool label_right = false,
+                     TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0),
+                     std::string const& tz = "") const;
+  // dataframe.cpp:1265-1290 (fixed-width units N U L S T H D; calendar units are a "next" row)
+  Resampler downsample(std::string const& rule, bool closed_label_right = true, bool weekStartsMonday = true,
+                       bool startEpoch = true) const;
+
+  std::shared_ptr<arrow::RecordBatch> m_array;
+  ArrayPtr m_index;
+
+ private:
+  template <class T>
+  static void addColumn(arrow::FieldVector& fields, arrow::ArrayVector& arrays, std::string const& name, std::vector<T> const& v);
+  void init(std::shared_ptr<arrow::Schema> schema, arrow::ArrayVector const& arrays);
+};
+
+class GroupBy {
+ public:
+  // group_by.h:24-31 — throws std::runtime_error when the key cannot be grouped
+  GroupBy(const std::string& key, DataFrame df);
+  GroupBy(GroupBy&&) noexcept;
+  GroupBy& operator=(GroupBy&&) noexcept;
+  GroupBy(const GroupBy&) = delete;
+  ~GroupBy();
+
+  size_t groupSize() const;                                   // group_by.h:33-36
+  ArrayPtr unique() const;                                    // group_by.h:52-55
+  ScalarPtr GetKeyByIndex(int64_t i) const { return ReturnOrThrowOnFailure(unique()->GetScalar(i)); }
+
+  arrow::Result<DataFrame> mean(std::vector<std::string> const& args);
+  arrow::Result<Series> mean(std::string const& arg);
+  arrow::Result<DataFrame> count(std::vector<std::string> const& args);
+  arrow::Result<Series> count(std::string const& arg);
+  arrow::Result<DataFrame> first(std::vector<std::string> const& args);
+  arrow::Result<Series> first(std::string const& arg);
+  arrow::Result<DataFrame> last(std::vector<std::string> const& args);
+  arrow::Result<Series> last(std::string const& arg);
+  arrow::Result<DataFrame> max(std::vector<std::string> const& args);
+  arrow::Result<Series> max(std::string const& arg);
+  arrow::Result<DataFrame> min(std::vector<std::string> const& args);
+  arrow::Result<Series> min(std::string const& arg);
+  arrow::Result<DataFrame> min_max(std::vector<std::string> const& args);
+  arrow::Result<DataFrame> min_max(std::string const& arg);
+  arrow::Result<DataFrame> sum(std::vector<std::string> const& args);
+  arrow::Result<Series> sum(std::string const& arg);
+
+  // declared by the reference, outside this path's CUDA scope
+#define PD_NOT_ON_GPU(name)                                                                                   \
+  arrow::Result<DataFrame> name(std::vector<std::string> const&) { return arrow::Status::NotImplemented(#name " is not part of the B200 group-by path"); } \
+  arrow::Result<Series> name(std::string const&) { return arrow::Status::NotImplemented(#name " is not part of the B200 group-by path"); }
+  PD_NOT_ON_GPU(all) PD_NOT_ON_GPU(any) PD_NOT_ON_GPU(approximate_median) PD_NOT_ON_GPU(count_distinct)
+  PD_NOT_ON_GPU(product) PD_NOT_ON_GPU(mode) PD_NOT_ON_GPU(stddev) PD_NOT_ON_GPU(variance) PD_NOT_ON_GPU(tdigest)
+#undef PD_NOT_ON_GPU
+  arrow::Result<Series> apply(std::function<ScalarPtr(DataFrame const&)>) { return arrow::Status::NotImplemented("apply needs group materialisation (SURVEY 8f-2)"); }
+
+ protected:
+  GroupBy() = default;
+  const DataFrame& getDF() const { return df; }
+  // one fused pass for `column`, returns the arrays of the aggregates in `mask` (ascending bit order)
+  arrow::Result<arrow::ArrayVector> aggregate(std::string const& column, uint32_t mask, bool drop_validity);
+  arrow::Result<DataFrame> frameOf(std::vector<std::string> const& args, uint32_t bit, bool drop_validity, bool with_index);
+  arrow::Result<Series> seriesOf(std::string const& arg, uint32_t bit, bool drop_validity, bool with_index);
+
+  DataFrame df;
+  pa_groupby* handle = nullptr;
+  ArrayPtr key_array;                          // kept alive: the C ABI borrows the key buffers
+  std::shared_ptr<arrow::Array> key_dictionary;  // for dictionary / utf8 keys
+  mutable ArrayPtr uniqueKeys;
+  friend class Resampler;
+};
+
+// group_by.h:255-299
+class Resampler : protected GroupBy {
+ public:
+  explicit Resampler(DataFrame const& _df);    // hash group-by on the index ("__resampler_idx__")
+  // time-bucket specialisation: sorted index + fixed width (pd::resample)
+  Resampler(DataFrame const& _df, int64_t freq_ns, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+            int64_t offset_ns);
+  ArrayPtr index() const { return this->unique(); }
+  const DataFrame& data() const { return this->getDF(); }
+#define PD_RESAMPLE_FN(name) \
+  arrow::Result<DataFrame> name() { return frameOfAll(#name); }
+  PD_RESAMPLE_FN(mean) PD_RESAMPLE_FN(count) PD_RESAMPLE_FN(max) PD_RESAMPLE_FN(min) PD_RESAMPLE_FN(sum)
+  PD_RESAMPLE_FN(first) PD_RESAMPLE_FN(last)
+#undef PD_RESAMPLE_FN
+  arrow::Result<DataFrame> min_max() { return GroupBy::min_max(getDF().columnNames()); }
+  using GroupBy::apply;
+  using GroupBy::groupSize;
+
+ private:
+  arrow::Result<DataFrame> frameOfAll(std::string const& name);
+};
+
+// resample.h:51-122
+Resampler resample(DataFrame const& df, std::string const& rule, bool closed_right = false, bool label_right = false,
+                   TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0), std::string const& tz = "");
+Resampler resample(DataFrame const& df, time_duration const& rule, bool closed_right = false, bool label_right = false,
+                   TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0), std::string const& tz = "");
+Resampler resample(Series const& s, std::string const& rule, bool closed_right = false, bool label_right = false,
+                   TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0), std::string const& tz = "");
+Resampler resample(Series const& s, time_duration const& rule, bool closed_right = false, bool label_right = false,
+                   TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0), std::string const& tz = "");
+
+// helpers the reference's tests use (core.cpp:174-425)
+ArrayPtr range(int64_t start, int64_t end);                                   // int64 array [start, end)
+ArrayPtr date_range(int64_t start_ns, int periods, time_duration freq = std::chrono::minutes(1));
+int64_t ns_from_ymd(int y, int m, int d);
+
+// ---------------------------------------------------------------------------------------------
+template <class T>
+void DataFrame::addColumn(arrow::FieldVector& fields, arrow::ArrayVector& arrays, std::string const& name, std::vector<T> const& v) {
+  typename arrow::CTypeTraits<T>::BuilderType b;
+  ThrowOnFailure(b.AppendValues(v));
+  ArrayPtr a;
+  ThrowOnFailure(b.Finish(&a));
+  fields.push_back(arrow::field(name, a->type()));
+  arrays.push_back(a);
+}
+
+template <class T>
+T Scalar::as() const {
+  if (!scalar) throw std::runtime_error("empty scalar");
+  if constexpr (std::is_same_v<T, std::string>) {
+    return scalar->ToString();
+  } else {
+    auto cast = ReturnOrThrowOnFailure(scalar->CastTo(arrow::CTypeTraits<T>::type_singleton()));
+    return static_cast<const typename arrow::CTypeTraits<T>::ScalarType&>(*cast).value;
+  }
+}
+
+template <class T>
+std::vector<T> Series::values() const {
+  std::vector<T> out(m_array->length());
+  for (int64_t i = 0; i < m_array->length(); ++i) out[i] = Scalar(ReturnOrThrowOnFailure(m_array->GetScalar(i))).as<T>();
+  return out;
+}
+
+}  // namespace pd

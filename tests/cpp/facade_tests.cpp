@@ -1,0 +1,222 @@
+// C++ tests of the pd:: façade, written the way the reference's Catch2 tests are
+// (/root/reference/tests/cudf_examples/dataframe_resample_test.cpp, series_resample_test.cpp,
+// dataframe_iterator_test.cpp) so that they read like the reference's own; Catch2 is not installed,
+// hence the tiny REQUIRE harness.  Needs a GPU (run by tests/test_facade_gpu.py).
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <string>
+
+#include "../../pandasarrow_b200/csrc/host/pd_groupby.h"
+
+using namespace std::string_literals;
+
+static int g_fail = 0, g_checks = 0;
+#define REQUIRE(cond)                                                              \
+  do {                                                                             \
+    ++g_checks;                                                                    \
+    if (!(cond)) { ++g_fail; std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); } \
+  } while (0)
+#define REQUIRE_THROWS(expr)                                  \
+  do {                                                        \
+    ++g_checks;                                               \
+    bool threw__ = false;                                     \
+    try { expr; } catch (std::exception const&) { threw__ = true; } \
+    if (!threw__) { ++g_fail; std::printf("FAILED %s:%d  expected throw: %s\n", __FILE__, __LINE__, #expr); } \
+  } while (0)
+
+static std::string str_at(const pd::ArrayPtr& a, int64_t i) { return pd::ReturnOrThrowOnFailure(a->GetScalar(i))->ToString(); }
+
+static pd::DataFrame people() {
+  return pd::DataFrame{pd::range(0L, 10L),
+                       std::pair{"id"s, std::vector{"allen"s, "victor"s, "hannah"s, "allen"s, "victor"s, "hannah"s, "allen"s, "victor"s, "hannah"s, "allen"s}},
+                       std::pair{"gender"s, std::vector{"male"s, "female"s, "male"s, "male"s, "female"s, "male"s, "male"s, "female"s, "male"s, "male"s}},
+                       std::pair{"age"s, std::vector{16, 10, 10, 20, 30, 40, 15, 25, 35, 45}},
+                       std::pair{"height"s, std::vector{9, 9, 9, 9, 9, 8, 8, 8, 8, 8}}};
+}
+
+// dataframe_resample_test.cpp:8-69 (grouping + order) and :71-250 (aggregates)
+static void test_make_groups_and_aggregates() {
+  auto df = people();
+  pd::GroupBy by_id("id", df);
+  REQUIRE(by_id.groupSize() == 3);
+  REQUIRE(by_id.unique()->length() == 3);
+  REQUIRE(str_at(by_id.unique(), 0) == "allen");
+  REQUIRE(str_at(by_id.unique(), 1) == "victor");
+  REQUIRE(str_at(by_id.unique(), 2) == "hannah");
+
+  pd::GroupBy groupby("gender", df);
+  REQUIRE(groupby.groupSize() == 2);
+  REQUIRE(str_at(groupby.unique(), 0) == "male");
+  REQUIRE(str_at(groupby.unique(), 1) == "female");
+
+  auto age_mean = pd::ReturnOrThrowOnFailure(groupby.mean("age"));
+  REQUIRE(std::fabs(age_mean[0].as<double>() - 25.857) < 1e-3);
+  REQUIRE(std::fabs(age_mean[1].as<double>() - 21.667) < 1e-3);
+  auto age_height_mean = pd::ReturnOrThrowOnFailure(groupby.mean({"age"s, "height"s}));
+  REQUIRE(age_height_mean["age"][0].as<double>() == 25.857142857142858);
+  REQUIRE(age_height_mean["age"][1].as<double>() == 21.666666666666668);
+  REQUIRE(age_height_mean["height"][0].as<double>() == 8.428571428571429);
+  REQUIRE(age_height_mean["height"][1].as<double>() == 8.666666666666666);
+
+  auto age_mm = pd::ReturnOrThrowOnFailure(groupby.min_max("age"));
+  REQUIRE(age_mm["min"][0].as<int32_t>() == 10);
+  REQUIRE(age_mm["min"][1].as<int32_t>() == 10);
+  REQUIRE(age_mm["max"][0].as<int32_t>() == 45);
+  REQUIRE(age_mm["max"][1].as<int32_t>() == 30);
+  auto ah_mm = pd::ReturnOrThrowOnFailure(groupby.min_max({"age"s, "height"s}));
+  REQUIRE(ah_mm["age_min"][0].as<int32_t>() == 10);
+  REQUIRE(ah_mm["age_max"][1].as<int32_t>() == 30);
+  REQUIRE(ah_mm["height_min"][0].as<int32_t>() == 8);
+  REQUIRE(ah_mm["height_max"][1].as<int32_t>() == 9);
+
+  auto age_max = pd::ReturnOrThrowOnFailure(groupby.max("age"));
+  REQUIRE(age_max[0].as<int32_t>() == 45);
+  REQUIRE(age_max[1].as<int32_t>() == 30);
+  auto ah_max = pd::ReturnOrThrowOnFailure(groupby.max({"age"s, "height"s}));
+  REQUIRE(ah_max["height"][0].as<int32_t>() == 9);
+  REQUIRE(ah_max["height"][1].as<int32_t>() == 9);
+  auto age_min = pd::ReturnOrThrowOnFailure(groupby.min("age"));
+  REQUIRE(age_min[0].as<int32_t>() == 10);
+  REQUIRE(age_min[1].as<int32_t>() == 10);
+
+  auto age_sum = pd::ReturnOrThrowOnFailure(groupby.sum("age"));
+  REQUIRE(age_sum[0].as<int64_t>() == 181);
+  REQUIRE(age_sum[1].as<int64_t>() == 65);
+  REQUIRE(age_sum.dtype()->id() == arrow::Type::INT64);
+  auto ah_sum = pd::ReturnOrThrowOnFailure(groupby.sum({"age"s, "height"s}));
+  REQUIRE(ah_sum["height"][0].as<int64_t>() == 59);
+  REQUIRE(ah_sum["height"][1].as<int64_t>() == 26);
+
+  auto age_count = pd::ReturnOrThrowOnFailure(groupby.count("age"));
+  REQUIRE(age_count[0].as<int64_t>() == 7);
+  REQUIRE(age_count[1].as<int64_t>() == 3);
+
+  REQUIRE_THROWS(pd::GroupBy("nope", df));                                 // group_by.h:27-30
+  REQUIRE(!groupby.sum("nope").ok());
+  REQUIRE(groupby.stddev("age").status().IsNotImplemented());
+}
+
+// dataframe_resample_test.cpp:252-305 — OHLC bars through group_by
+static void test_bardata() {
+  pd::DataFrame bardata{pd::range(0L, 5L),
+                        std::pair("high"s, std::vector<float>{11.1f, 20.2f, 21.f, 15.f, 20.f}),
+                        std::pair("low"s, std::vector<float>{9.1f, 9.2f, 10.f, 5.f, 10.f}),
+                        std::pair("close"s, std::vector<float>{10.1f, 15.2f, 20.f, 15.f, 15.f}),
+                        std::pair("open"s, std::vector<float>{10.f, 20.2f, 10.f, 15.f, 10.f}),
+                        std::pair("volume"s, std::vector<uint64_t>{100, 200, 210, 1, 2}),
+                        std::pair("day"s, std::vector<int64_t>{1, 1, 2, 2, 5})};
+  auto grouper = bardata.group_by("day");
+  REQUIRE(grouper.unique()->length() == 3);
+  auto open = pd::ReturnOrThrowOnFailure(grouper.first("open"));
+  auto close = pd::ReturnOrThrowOnFailure(grouper.last("close"));
+  auto high = pd::ReturnOrThrowOnFailure(grouper.max("high"));
+  auto low = pd::ReturnOrThrowOnFailure(grouper.min("low"));
+  auto volume = pd::ReturnOrThrowOnFailure(grouper.sum("volume"));
+  REQUIRE(open.values<float>() == (std::vector<float>{10.f, 10.f, 10.f}));
+  REQUIRE(close.values<float>() == (std::vector<float>{15.2f, 15.f, 15.f}));
+  REQUIRE(high.values<float>() == (std::vector<float>{20.2f, 21.f, 20.f}));
+  REQUIRE(low.values<float>() == (std::vector<float>{9.1f, 5.f, 10.f}));
+  REQUIRE(volume.values<uint64_t>() == (std::vector<uint64_t>{300, 211, 2}));
+  REQUIRE(open.indexArray() == nullptr);      // dataframe.cpp:1748 quirk: first(string) has no key index
+  REQUIRE(close.indexArray() != nullptr);
+}
+
+// dataframe_iterator_test.cpp:11-76 — per-group column sums
+static void test_apply_sums() {
+  auto df = pd::DataFrame(std::map<std::string, std::vector<int32_t>>{{"a", {1, 1, 3, 1, 1, 1, 3, 8, 2, 2}}, {"b", {10, 9, 8, 7, 6, 5, 4, 3, 2, 1}}});
+  auto groupby = df.group_by("a"s);
+  REQUIRE(groupby.groupSize() == 4);
+  auto result = pd::ReturnOrThrowOnFailure(groupby.sum({"a"s, "b"s}));
+  REQUIRE(result.num_rows() == 4);
+  REQUIRE(result.num_columns() == 2);
+  REQUIRE(result["a"].values<int64_t>() == (std::vector<int64_t>{5, 6, 8, 4}));
+  REQUIRE(result["b"].values<int64_t>() == (std::vector<int64_t>{37, 12, 3, 3}));
+  // group_by(ArrayPtr) (dataframe.cpp:1231-1235) and Series::group_by
+  auto g2 = df.group_by(df["a"].array());
+  REQUIRE(pd::ReturnOrThrowOnFailure(g2.sum("b")).values<int64_t>() == (std::vector<int64_t>{37, 12, 3, 3}));
+  auto g3 = df["b"].group_by(df["a"].array());
+  REQUIRE(pd::ReturnOrThrowOnFailure(g3.sum("b")).values<int64_t>() == (std::vector<int64_t>{37, 12, 3, 3}));
+}
+
+// series_resample_test.cpp:12-70
+static void test_resample_series() {
+  auto index = pd::date_range(pd::ns_from_ymd(2000, 1, 1), 9);
+  auto series = pd::Series(pd::range(0L, 9L), index, "v");
+  {
+    auto resampler = pd::resample(series, pd::minutes(3));
+    auto gi = resampler.index();
+    REQUIRE(str_at(gi, 0) == "2000-01-01 00:00:00.000000000");
+    REQUIRE(str_at(gi, 1) == "2000-01-01 00:03:00.000000000");
+    REQUIRE(str_at(gi, 2) == "2000-01-01 00:06:00.000000000");
+    auto sum = pd::ReturnOrThrowOnFailure(resampler.sum());
+    REQUIRE(sum.at(0, 0) == int64_t(3));
+    REQUIRE(sum.at(1, 0) == int64_t(12));
+    REQUIRE(sum.at(2, 0) == int64_t(21));
+  }
+  {
+    auto resampler = pd::resample(series, pd::minutes(3), false, true);
+    auto gi = resampler.index();
+    REQUIRE(str_at(gi, 0) == "2000-01-01 00:03:00.000000000");
+    REQUIRE(str_at(gi, 2) == "2000-01-01 00:09:00.000000000");
+    auto sum = pd::ReturnOrThrowOnFailure(resampler.sum());
+    REQUIRE(sum.at(2, 0) == int64_t(21));
+  }
+  {
+    auto resampler = pd::resample(series, pd::minutes(3), true, true);
+    auto gi = resampler.index();
+    REQUIRE(gi->length() == 4);
+    REQUIRE(str_at(gi, 0) == "2000-01-01 00:00:00.000000000");
+    REQUIRE(str_at(gi, 3) == "2000-01-01 00:09:00.000000000");
+    auto sum = pd::ReturnOrThrowOnFailure(resampler.sum());
+    REQUIRE(sum.at(0, 0) == int64_t(0));
+    REQUIRE(sum.at(1, 0) == int64_t(6));
+    REQUIRE(sum.at(2, 0) == int64_t(15));
+    REQUIRE(sum.at(3, 0) == int64_t(15));
+  }
+  {
+    auto sum = pd::ReturnOrThrowOnFailure(series.resample("3T").sum());      // string rule, series.cpp:351-359
+    REQUIRE(sum.at(1, 0) == int64_t(12));
+    REQUIRE_THROWS(pd::resample(series, pd::seconds(30)));                    // upsampling, resample.h:102-105
+  }
+}
+
+// series_resample_test.cpp:87-130 — DataFrame::downsample
+static void test_downsample() {
+  auto index = pd::date_range(pd::ns_from_ymd(2000, 1, 1), 9);
+  pd::DataFrame df(arrow::schema({arrow::field("i", arrow::int64())}), 9, {pd::range(0L, 9L)}, index);
+  {
+    auto resampler = df.downsample("3T", false);
+    auto gi = resampler.index();
+    auto sum = pd::ReturnOrThrowOnFailure(resampler.sum());
+    REQUIRE(gi->length() == 3);
+    REQUIRE(str_at(gi, 1) == "2000-01-01 00:03:00.000000000");
+    REQUIRE(sum.at(0, 0) == int64_t(3));
+    REQUIRE(sum.at(2, 0) == int64_t(21));
+  }
+  {
+    auto resampler = df.downsample("3T", true);
+    auto gi = resampler.index();
+    auto sum = pd::ReturnOrThrowOnFailure(resampler.sum());
+    REQUIRE(gi->length() == 4);
+    REQUIRE(str_at(gi, 3) == "2000-01-01 00:09:00.000000000");
+    REQUIRE(sum.at(0, 0) == int64_t(0));
+    REQUIRE(sum.at(1, 0) == int64_t(6));
+    REQUIRE(sum.at(3, 0) == int64_t(15));
+  }
+}
+
+int main() {
+  try {
+    test_make_groups_and_aggregates();
+    test_bardata();
+    test_apply_sums();
+    test_resample_series();
+    test_downsample();
+  } catch (std::exception const& e) {
+    std::printf("EXCEPTION: %s\n", e.what());
+    return 2;
+  }
+  std::printf("%d checks, %d failed\n", g_checks, g_fail);
+  return g_fail ? 1 : 0;
+}
