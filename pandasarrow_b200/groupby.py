@@ -373,5 +373,5 @@ class synth:
         _check(_lib.load().pa_synth_validity(t.data_ptr(), n_rows, first_row, seed, null_every, None))
 
     @staticmethod
-    def timestamps(t, first_row: int = 0, t0_ns: int = T0_NS, step_ns: int = 60_000, seed: int = SEED_T):
+    def timestamps(t, first_row: int = 0, t0_ns: int = T0_NS, step_ns: int = 60_000_000, seed: int = SEED_T):
         _check(_lib.load().pa_synth_timestamps(t.data_ptr(), t.numel(), first_row, t0_ns, step_ns, seed, None))

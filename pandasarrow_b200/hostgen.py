@@ -38,7 +38,7 @@ def valid_mask(n: int, first_row: int = 0, seed: int = SEED_N, null_every: int =
     return (r % np.uint64(null_every)) != 0
 
 
-def timestamps(n: int, first_row: int = 0, t0_ns: int = T0_NS, step_ns: int = 60_000, seed: int = SEED_T) -> np.ndarray:
+def timestamps(n: int, first_row: int = 0, t0_ns: int = T0_NS, step_ns: int = 60_000_000, seed: int = SEED_T) -> np.ndarray:
     rows = _rows(n, first_row)
     with np.errstate(over="ignore"):
         jitter = splitmix64(rows + np.uint64(seed)) % np.uint64(step_ns)
