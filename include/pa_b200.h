@@ -113,7 +113,8 @@ typedef struct pa_options {
   int64_t expected_groups;   /* hint for table sizing; 0 = unknown */
   void* cuda_stream;         /* cudaStream_t to run on; NULL = a stream owned by the handle */
   int64_t row_base;          /* global row number of local row 0 (multi-GPU row-range shards) */
-  int64_t reserved[4];
+  int64_t lowcard_no_dense;  /* 1 = the shared-memory path never uses dense (key - base) addressing, always hashes */
+  int64_t reserved[3];
 } pa_options;
 
 typedef struct pa_groupby pa_groupby;      /* opaque: key columns + device group table */

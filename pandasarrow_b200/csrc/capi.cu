@@ -252,70 +252,79 @@ bool is_wide(uint32_t mask, int vc) {
 }
 
 // ------------------------------ low-cardinality path ------------------------------
-template <int VC, int VW, int KW, bool WIDE>
-int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid) {
-  using L = LcSmem<WIDE>;
-  const size_t smem = L::total(KW, VW);
-  auto scan = (a.kvalid || a.vvalid) ? k_lowcard_scan<VC, VW, KW, WIDE, true> : k_lowcard_scan<VC, VW, KW, WIDE, false>;
-  CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  scan<<<grid, LC_THREADS, smem, g->stream>>>(a);
+enum LcOutcome { LC_DONE = 0, LC_DENSE_MISS = 1, LC_OVERFLOW = 2 };
+
+// the kernel's WIDE variant: min/max slots (+ a double sum for the mean of integers); `last` is free
+bool lc_is_wide(uint32_t mask, int vc) { return (mask & (AGG_MIN | AGG_MAX)) || ((mask & AGG_MEAN) && vc != VC_F); }
+
+template <int VC, bool WIDE>
+int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast) {
+  using L = LcSmem<VC, WIDE>;
+  using Cfg = LcCfg<VC, WIDE>;
+  cudaStream_t st = g->stream;
+  auto scan = fast ? k_lowcard_scan<VC, WIDE, true> : k_lowcard_scan<VC, WIDE, false>;
+  CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL)));
+  k_lowcard_prep<<<LC_PREP_GRID, 256, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(g->ev[2], g->stream));
-  k_lowcard_merge<VC, WIDE><<<1, LM_THREADS, 0, g->stream>>>(m);
+  scan<<<grid, LC_THREADS, L::TOTAL, st>>>(a);
   CUDA_TRY(cudaGetLastError());
-  g->last_launches += 2;
+  CUDA_TRY(cudaEventRecord(g->ev[2], st));
+  k_lowcard_merge<VC, WIDE><<<(Cfg::GP + 7) / 8, 256, 0, st>>>(m);
+  CUDA_TRY(cudaGetLastError());
+  k_lowcard_rank<VC, WIDE><<<1, LR_THREADS, 0, st>>>(m);
+  CUDA_TRY(cudaGetLastError());
+  g->last_launches += 4;
   return PA_OK;
 }
 
-template <int VC, int VW, bool WIDE>
-int launch_lowcard_k(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid) {
-  return g->key_width == 8 ? launch_lowcard_t<VC, VW, 8, WIDE>(g, a, m, grid) : launch_lowcard_t<VC, VW, 4, WIDE>(g, a, m, grid);
-}
-
-template <bool WIDE>
-int launch_lowcard_w(pa_groupby* g, int vc, int vw, const LcArgs& a, const LmArgs& m, int grid) {
-  if (vc == VC_F) return vw == 8 ? launch_lowcard_k<VC_F, 8, WIDE>(g, a, m, grid) : launch_lowcard_k<VC_F, 4, WIDE>(g, a, m, grid);
-  if (vc == VC_I) return vw == 8 ? launch_lowcard_k<VC_I, 8, WIDE>(g, a, m, grid) : launch_lowcard_k<VC_I, 4, WIDE>(g, a, m, grid);
-  return vw == 8 ? launch_lowcard_k<VC_U, 8, WIDE>(g, a, m, grid) : launch_lowcard_k<VC_U, 4, WIDE>(g, a, m, grid);
-}
-
-// returns PA_OK and sets *overflow when the shared-memory tables were too small
-int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool* overflow) {
+int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool force_hash, LcOutcome* outcome) {
   cudaStream_t st = g->stream;
   const int grid = g->num_sms;
-  const int gp = wide ? LcCfg<true>::GP : LcCfg<false>::GP;
+  const int vc = val ? val->vc : VC_I;
+  const bool kwide = lc_is_wide(mask, vc);
+  const bool dsum = kwide && vc != VC_F;
+  const int gp = lc_gmax(vc, kwide) + 2;
   const size_t np = static_cast<size_t>(grid) * gp;
-  DevBuf p_key, p_sum, p_dsum, p_count, p_first, p_last, p_min, p_max, p_nids, inv;
-  PA_TRY(p_key.alloc(np * 8, st));
+  DevBuf p_sum, p_dsum, p_count, p_first, p_last, p_min, p_max, merged, dir;
   PA_TRY(p_sum.alloc(np * 8, st));
   PA_TRY(p_count.alloc(np * 4, st));
   PA_TRY(p_first.alloc(np * 4, st));
-  PA_TRY(p_nids.alloc(sizeof(uint32_t) * grid, st));
-  if (wide) {
-    PA_TRY(p_dsum.alloc(np * 8, st));
-    PA_TRY(p_last.alloc(np * 4, st));
+  PA_TRY(p_last.alloc(np * 4, st));
+  if (kwide) {
     PA_TRY(p_min.alloc(np * 8, st));
     PA_TRY(p_max.alloc(np * 8, st));
+    if (dsum) PA_TRY(p_dsum.alloc(np * 8, st));
   }
-  PA_TRY(inv.alloc(np * 2, st));
-  CUDA_TRY(cudaMemsetAsync(inv.p, 0xFF, np * 2, st));
+  // merged-by-id scratch: sum, dsum, min, max (8 B each) then count, first, last (4 B each)
+  const size_t gp8 = static_cast<size_t>(gp) * 8, gp4 = static_cast<size_t>(gp) * 4;
+  PA_TRY(merged.alloc(gp8 * 4 + gp4 * 3, st));
+  // directory: LcPrep | key_by_id | gt_keys | gt_ids
+  const size_t dir_bytes = sizeof(LcPrep) + static_cast<size_t>(LC_GMAX_MAX) * 8 + static_cast<size_t>(LC_GT_CAP) * 12;
+  PA_TRY(dir.alloc(dir_bytes, st));
+  CUDA_TRY(cudaMemsetAsync(dir.p, 0, sizeof(LcPrep), st));
   CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
-  const int vc = val ? val->vc : VC_I;
-  const int vw = val ? val->width : 8;
   PA_TRY(alloc_result(g, gp, wide, vc != VC_F));
+  if (wide && !kwide) {   // min/max are not computed by this pass: keep the arrays defined
+    CUDA_TRY(cudaMemsetAsync(g->r_min.p, 0xFF, static_cast<size_t>(gp) * 8, st));
+    CUDA_TRY(cudaMemsetAsync(g->r_max.p, 0x00, static_cast<size_t>(gp) * 8, st));
+  }
 
   LcArgs a{};
   a.keys = g->key_data;
   a.kvalid = g->key_valid;
   a.koff = g->key_bit_off;
+  a.kw = g->key_width;
   a.vals = val ? val->data : nullptr;
   a.vvalid = val ? val->valid : nullptr;
   a.voff = val ? val->bit_off : 0;
+  a.vw = val ? val->width : 8;
   a.n = g->n;
-  const bool aligned = (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0) && (!a.vals || reinterpret_cast<uintptr_t>(a.vals) % 16 == 0);
-  a.n_bulk = aligned ? (g->n / LC_CHUNK) * LC_CHUNK : 0;
-  a.agg_mask = mask;
-  a.p_key = p_key.as<uint64_t>();
+  a.force_hash = force_hash ? 1 : 0;
+  char* d = dir.as<char>();
+  a.dir.prep = reinterpret_cast<LcPrep*>(d);
+  a.dir.key_by_id = reinterpret_cast<unsigned long long*>(d + sizeof(LcPrep));
+  a.dir.gt_keys = a.dir.key_by_id + LC_GMAX_MAX;
+  a.dir.gt_ids = reinterpret_cast<unsigned int*>(a.dir.gt_keys + LC_GT_CAP);
   a.p_sum = p_sum.as<uint64_t>();
   a.p_dsum = p_dsum.as<double>();
   a.p_count = p_count.as<uint32_t>();
@@ -323,23 +332,40 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   a.p_last = p_last.as<uint32_t>();
   a.p_min = p_min.as<uint64_t>();
   a.p_max = p_max.as<uint64_t>();
-  a.p_nids = p_nids.as<uint32_t>();
   a.status = g->status.as<uint32_t>();
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0) && (!a.vals || reinterpret_cast<uintptr_t>(a.vals) % 16 == 0);
+  const bool fast = aligned && a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid && !a.vvalid;
   LmArgs m{};
   m.part = a;
   m.grid = grid;
-  m.inv = inv.as<uint16_t>();
+  m.gp = gp;
+  char* mp = merged.as<char>();
+  m.m_sum = reinterpret_cast<uint64_t*>(mp);
+  m.m_dsum = reinterpret_cast<double*>(mp + gp8);
+  m.m_min = reinterpret_cast<uint64_t*>(mp + gp8 * 2);
+  m.m_max = reinterpret_cast<uint64_t*>(mp + gp8 * 3);
+  m.m_count = reinterpret_cast<uint32_t*>(mp + gp8 * 4);
+  m.m_first = m.m_count + gp;
+  m.m_last = m.m_first + gp;
   m.out = g->res;
   m.status = a.status;
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
-  if (wide) PA_TRY(launch_lowcard_w<true>(g, vc, vw, a, m, grid));
-  else PA_TRY(launch_lowcard_w<false>(g, vc, vw, a, m, grid));
+  if (kwide) {
+    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, true>(g, a, m, grid, fast)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, true>(g, a, m, grid, fast)));
+    else PA_TRY((launch_lowcard_t<VC_U, true>(g, a, m, grid, fast)));
+  } else {
+    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, false>(g, a, m, grid, fast)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, false>(g, a, m, grid, fast)));
+    else PA_TRY((launch_lowcard_t<VC_U, false>(g, a, m, grid, fast)));
+  }
   CUDA_TRY(cudaEventRecord(g->ev[3], st));
   uint32_t h_status[ST_WORDS];
   CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  *overflow = h_status[ST_OVERFLOW] != 0;
-  if (!*overflow) g->G = h_status[ST_NGROUPS];
+  if (h_status[ST_OVERFLOW]) *outcome = LC_OVERFLOW;
+  else if (h_status[ST_DENSE_MISS]) *outcome = LC_DENSE_MISS;
+  else { *outcome = LC_DONE; g->G = h_status[ST_NGROUPS]; }
   return PA_OK;
 }
 
@@ -623,15 +649,15 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
     PA_TRY(run_resample(g, val, mask, wide));
     g->last_path = 3;
   } else {
-    const bool lowcard_types = !val || val->width == 4 || val->width == 8;
-    const int gmax = wide ? LC_GMAX_WIDE : LC_GMAX_NARROW;
-    bool try_low = g->opt.path != PA_PATH_GLOBAL && lowcard_types &&
+    const int gmax = lc_gmax(vc, lc_is_wide(mask, vc));
+    bool try_low = g->opt.path != PA_PATH_GLOBAL &&
                    (g->opt.expected_groups == 0 || g->opt.expected_groups <= gmax || g->opt.path == PA_PATH_LOWCARD);
     bool done = false;
     if (try_low) {
-      bool overflow = false;
-      PA_TRY(run_lowcard(g, val, mask, wide, &overflow));
-      if (!overflow) { done = true; g->last_path = PA_PATH_LOWCARD; }
+      LcOutcome oc = LC_DONE;
+      PA_TRY(run_lowcard(g, val, mask, wide, g->opt.lowcard_no_dense != 0, &oc));
+      if (oc == LC_DENSE_MISS) PA_TRY(run_lowcard(g, val, mask, wide, true, &oc));   // a key outside the sampled window
+      if (oc == LC_DONE) { done = true; g->last_path = PA_PATH_LOWCARD; }
       else if (g->opt.path == PA_PATH_LOWCARD) return set_err(PA_ERR_INVALID, "more groups than the shared-memory path holds (%d)", gmax);
     }
     if (!done) {

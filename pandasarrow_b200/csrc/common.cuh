@@ -147,6 +147,20 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
+// 128-bit / 8-bit shared-memory accesses on 32-bit shared addresses (nvcc otherwise splits a uint4
+// store whose components are not already in an aligned register quad into STS.64 + 2 x STS.32).
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // streaming 128-bit global load that does not allocate in L1
 __device__ __forceinline__ ulonglong2 ldg_stream_u64x2(const void* p) {
   ulonglong2 r;

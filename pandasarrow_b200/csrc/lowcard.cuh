@@ -1,25 +1,34 @@
-// Low-cardinality path (stages 1-3 fused): one persistent CTA per SM.
+// Low-cardinality path (stages 1-3 fused): one persistent 8-warp CTA per SM, accumulators privatised
+// per warp in shared memory.
 //
-//  * Every warp streams its own row chunks HBM -> shared memory with 1-D bulk async copies
-//    (cp.async.bulk, the TMA engine) through a private 3-stage mbarrier ring, so the memory
-//    pipeline depth does not depend on occupancy (8 warps / SM).
-//  * Keys are resolved to dense CTA-local group ids through a CTA-shared hash table in shared
-//    memory: 2048 buckets of two 8-byte keys, one LDS.128 per lookup; the steady state is
-//    read-only (plain loads, no atomics), a rare out-of-line slow path inserts new keys with
-//    ATOMS.CAS.64 and handles null keys / the sentinel-valued key / bucket overflow.
-//  * Accumulators are WARP-PRIVATE arrays in shared memory, updated without atomics (sm_100a has
-//    no native 64-bit shared-memory atomics: f64/u64 adds compile to CAS spin loops).  Lanes of a
-//    warp that hit the same group (MATCH.ANY) are first combined with a shuffle-based segmented
-//    reduction in ascending lane (= row) order, then the lowest lane does one read-modify-write.
-//    The order of floating-point additions is therefore a fixed function of (n_rows, grid size):
-//    results are run-to-run deterministic.
-//  * Two 32-row batches are processed interleaved per step so that two independent lookup chains
-//    are in flight per warp.
-//  * At the end each CTA folds its warps in warp order and writes a partial table; a single-CTA
-//    merge kernel joins the partial tables by key, folds them in CTA order, ranks the groups by
+//  * Input: every warp streams "row groups" of 256 rows (8 batches of 32 rows) with coalesced
+//    non-allocating loads (256 contiguous bytes per warp per instruction); the next group is
+//    loaded into a second register buffer before the current one is processed, so ~4 KB per warp /
+//    32 KB per SM are in flight at all times without relying on occupancy.  (The earlier version
+//    staged the rows through shared memory with bulk async copies; ncu showed the kernel bound by
+//    shared-memory wavefronts, so the staging traffic was removed — profiles/r1_lowcard_v3_*.)
+//  * Stage 1-2, key -> dense group id, two modes chosen ON THE DEVICE from a key-range sample taken
+//    by k_lowcard_prep (no host round trip):
+//      dense : all sampled keys lie in a window of <= GMAX values -> id = key - base, no table at all.
+//              A key outside the window aborts the pass (ST_DENSE_MISS) and the host reruns in hash mode.
+//      hash  : CTA-shared open-addressing table in shared memory, 2048 buckets of two 8-byte keys:
+//              one LDS.128 + one LDS.U16 per lookup, read-only in steady state.  New keys take an
+//              out-of-line slow path (ATOMS.CAS.64) that also obtains a GLOBAL id for the key from a
+//              small directory in global memory, so that ids mean the same group in every CTA and
+//              the merge needs no join.  Null keys and the key equal to the table sentinel have
+//              dedicated ids.
+//  * Stage 3: accumulators are WARP-PRIVATE 16-byte slots {sum, count|claim tag, last row} in shared
+//    memory (+ {min, max} and a double sum for the wide aggregates), updated with one LDS.128 +
+//    one STS.128 and no atomics (sm_100a has no native 64-bit shared-memory atomics: f64/u64 adds
+//    compile to ATOMS.CAST.SPIN loops).  Lanes of a warp that hit the same group in a 32-row batch
+//    are found with a claim tag (each lane stores its lane number into the top byte of the slot's
+//    count word and reads the slot back: one lane reads its own number); winners fold the losers'
+//    values in ascending row order with shuffles.  The order of floating-point additions is a fixed
+//    function of (n_rows, grid size): results are run-to-run deterministic.
+//  * At the end each CTA folds its warps in warp order into a partial table; k_lowcard_merge folds
+//    the partial tables (one warp per group id, fixed order), k_lowcard_rank orders the groups by
 //    first row and writes the GroupResult.
-// If a CTA sees more than GMAX distinct keys the pass aborts (status[ST_OVERFLOW]) and the host
-// reruns the global-table path.
+// More than GMAX distinct keys -> ST_OVERFLOW, the host reruns on the global-table path.
 //
 // Replaces Grouper::Consume + MakeGroupings + ApplyGroupings + per-group CallFunction
 // (/root/reference/src/dataframe.cpp:1571-1600, pd_core_macros.h:5-147).
@@ -33,23 +42,61 @@ constexpr int LC_THREADS = LC_WARPS * 32;
 constexpr int LC_NB_LOG2 = 11;
 constexpr int LC_NBUCKET = 1 << LC_NB_LOG2;  // buckets of two keys
 constexpr int LC_TCAP = LC_NBUCKET * 2;      // key slots
-constexpr int LC_STAGES = 3;
-constexpr int LC_CHUNK = 192;                // rows per warp per stage (3 steps of 2 x 32 rows)
-constexpr uint32_t LC_UNSEEN = 0xFFFFFFFFu;  // count sentinel: warp has not met this id yet
+constexpr int LC_STEPS = 4;                  // 64-row steps per row group
+constexpr int LC_GROUP_ROWS = LC_STEPS * 64; // rows per warp per row group
 constexpr uint16_t LC_ID_UNSET = 0xFFFFu;
 constexpr uint16_t LC_ID_OVF = 0xFFFEu;
 constexpr uint32_t LC_NOID = 0xFFFFFFFFu;
+constexpr uint32_t LC_CNT_MASK = 0x00FFFFFFu;   // count field of a slot's count word; byte 3 = claim tag
+                                                // (count == LC_CNT_MASK: the warp has not met this id yet)
+constexpr int LC_GMAX_NARROW = 1024;   // sum / mean(float) / count / first / last : 16 B per id per warp
+constexpr int LC_GMAX_WIDE_F = 640;    // + min / max                              : 32 B
+constexpr int LC_GMAX_WIDE_I = 512;    // + double sum (mean of integers)          : 40 B
+constexpr int LC_GMAX_MAX = LC_GMAX_NARROW;
 
-constexpr int LC_GMAX_NARROW = 1024;   // sum / mean / count / first  (12 B per id per warp)
-constexpr int LC_GMAX_WIDE = 352;      // + min / max / last / dsum    (40 B per id per warp)
+// global key -> id directory (hash mode)
+constexpr int LC_GT_LOG2 = 13;
+constexpr int LC_GT_CAP = 1 << LC_GT_LOG2;
+constexpr uint32_t LC_GID_UNSET = 0xFFFFFFFFu;
+constexpr uint32_t LC_GID_OVF = 0xFFFFFFFEu;
+constexpr int LC_PREP_GRID = 64;       // x 256 threads = 16384 sampled keys
 
-template <bool WIDE>
+template <int VC, bool WIDE>
 struct LcCfg {
-  static constexpr int GMAX = WIDE ? LC_GMAX_WIDE : LC_GMAX_NARROW;
+  static constexpr bool DSUM = WIDE && VC != VC_F;
+  static constexpr int GMAX = WIDE ? (DSUM ? LC_GMAX_WIDE_I : LC_GMAX_WIDE_F) : LC_GMAX_NARROW;
   static constexpr int GP = GMAX + 2;             // + null-key group + (key == kEmptyKey) group
   static constexpr int ID_NULL = GMAX;
   static constexpr int ID_EMPTYKEY = GMAX + 1;
 };
+inline int lc_gmax(int vc, bool wide) { return wide ? (vc != VC_F ? LC_GMAX_WIDE_I : LC_GMAX_WIDE_F) : LC_GMAX_NARROW; }
+
+// Written by k_lowcard_prep (zero-initialised by the host), read by scan / rank.
+struct LcPrep {
+  unsigned long long nmin_ord;   // max over sampled valid keys of ~ord(key)   (ord = key ^ 2^63: signed order)
+  unsigned long long max_ord;    // max over sampled valid keys of  ord(key)
+  unsigned int next_id;          // hash mode: next global id
+  unsigned int pad[3];
+};
+
+struct LcDir {                   // global-memory directory (hash mode ids) + key sample
+  LcPrep* prep;
+  unsigned long long* gt_keys;   // [LC_GT_CAP], kEmptyKey = free
+  unsigned int* gt_ids;          // [LC_GT_CAP]
+  unsigned long long* key_by_id; // [LC_GMAX_MAX]
+};
+
+// dense-mode decision; identical in every kernel that needs it
+__device__ __forceinline__ bool lc_dense_mode(const LcPrep* p, int force_hash, uint32_t gmax, uint64_t* base) {
+  const uint64_t a = p->nmin_ord, b = p->max_ord;
+  *base = 0;
+  if (force_hash || (a == 0 && b == 0)) return false;
+  const uint64_t smin = (~a) ^ 0x8000000000000000ull, smax = b ^ 0x8000000000000000ull;   // two's complement bit patterns
+  const uint64_t span = smax - smin;           // smax >= smin in signed order, so this does not wrap
+  if (span >= gmax) return false;
+  *base = smin - (gmax - (span + 1)) / 2;      // centre the window on the sample (wrapping arithmetic)
+  return true;
+}
 
 struct LcArgs {
   const void* keys;
@@ -58,10 +105,10 @@ struct LcArgs {
   const uint8_t* vvalid;
   int64_t koff, voff;
   int64_t n;
-  int64_t n_bulk;          // rows [0, n_bulk) are streamed with bulk copies (multiple of LC_CHUNK; 0 disables)
-  uint32_t agg_mask;
+  int kw, vw;              // element widths in bytes (generic loader)
+  int force_hash;
+  LcDir dir;
   // per-CTA partial tables, [grid][GP]
-  uint64_t* p_key;
   uint64_t* p_sum;
   double* p_dsum;
   uint32_t* p_count;
@@ -69,50 +116,34 @@ struct LcArgs {
   uint32_t* p_last;
   uint64_t* p_min;
   uint64_t* p_max;
-  uint32_t* p_nids;        // [grid]
   uint32_t* status;
 };
 
-template <bool WIDE>
+template <int VC, bool WIDE>
 struct LcSmem {
-  using Cfg = LcCfg<WIDE>;
-  // byte offsets inside the dynamic shared memory block
-  static constexpr size_t stage_bytes(int kw, int vw) { return static_cast<size_t>(LC_CHUNK) * (kw + vw); }
-  static constexpr size_t OFF_BAR = 0;                                           // LC_WARPS*LC_STAGES u64
-  static constexpr size_t OFF_TKEYS = 256;                                       // LC_TCAP u64
+  using Cfg = LcCfg<VC, WIDE>;
+  static constexpr size_t OFF_MISC = 0;                                          // 4 x u32
+  static constexpr size_t OFF_TKEYS = 16;                                        // LC_TCAP u64
   static constexpr size_t OFF_TIDS = OFF_TKEYS + LC_TCAP * 8;                    // LC_TCAP u16
   static constexpr size_t OFF_FIRST = OFF_TIDS + LC_TCAP * 2;                    // GP u32 (CTA shared)
-  static constexpr size_t OFF_MISC = OFF_FIRST + ((Cfg::GP * 4 + 15) / 16) * 16; // next_id, ovf
-  static constexpr size_t OFF_ACC = OFF_MISC + 16;
-  static constexpr size_t ACC_PER_ID = WIDE ? 40 : 12;
-  static constexpr size_t ACC_PER_WARP = ((Cfg::GP * ACC_PER_ID + 15) / 16) * 16;
-  static constexpr size_t OFF_STAGE = OFF_ACC + ACC_PER_WARP * LC_WARPS;
-  static constexpr size_t total(int kw, int vw) { return OFF_STAGE + stage_bytes(kw, vw) * LC_STAGES * LC_WARPS; }
+  static constexpr size_t OFF_ACC = OFF_FIRST + ((Cfg::GP * 4 + 15) / 16) * 16;
+  static constexpr size_t A_BYTES = static_cast<size_t>(Cfg::GP) * 16;           // {sum, count|tag, last}
+  static constexpr size_t B_BYTES = WIDE ? static_cast<size_t>(Cfg::GP) * 16 : 0;        // {min, max}
+  static constexpr size_t C_BYTES = Cfg::DSUM ? ((static_cast<size_t>(Cfg::GP) * 8 + 15) / 16) * 16 : 0;   // dsum
+  static constexpr size_t ACC_PER_WARP = A_BYTES + B_BYTES + C_BYTES;
+  static constexpr size_t TOTAL = OFF_ACC + ACC_PER_WARP * LC_WARPS;
 };
 
-// Warp-private accumulator views (struct-of-arrays inside the warp's block).
-template <bool WIDE>
-struct LcAcc {
-  using Cfg = LcCfg<WIDE>;
-  uint64_t* sum;   // GP
-  uint32_t* cnt;   // GP
-  uint32_t* last;  // GP (WIDE)
-  uint64_t* mn;    // GP (WIDE)
-  uint64_t* mx;    // GP (WIDE)
-  double* dsum;    // GP (WIDE)
-  __device__ __forceinline__ explicit LcAcc(unsigned char* base) {
-    sum = reinterpret_cast<uint64_t*>(base);
-    if constexpr (WIDE) {
-      mn = sum + Cfg::GP;
-      mx = mn + Cfg::GP;
-      dsum = reinterpret_cast<double*>(mx + Cfg::GP);
-      cnt = reinterpret_cast<uint32_t*>(dsum + Cfg::GP);
-      last = cnt + Cfg::GP;
-    } else {
-      cnt = reinterpret_cast<uint32_t*>(sum + Cfg::GP);
-      last = nullptr; mn = nullptr; mx = nullptr; dsum = nullptr;
-    }
-  }
+// per-thread view of the CTA's shared state
+struct LcCtx {
+  uint32_t accA;                 // this warp's slots (32-bit shared-memory addresses)
+  uint32_t accB;
+  double* accC;
+  unsigned long long* tkeys;
+  uint16_t* tids;
+  uint32_t* cta_first;
+  uint32_t* misc;                // [0] unused, [1] abort seen by this CTA
+  uint64_t base;                 // dense mode
 };
 
 __device__ __forceinline__ uint32_t lc_bucket(uint64_t key) {
@@ -121,8 +152,7 @@ __device__ __forceinline__ uint32_t lc_bucket(uint64_t key) {
 }
 
 // Steady-state lookup of bucket `b`: one LDS.128 (both keys of the bucket) + one LDS.U16.  Returns a
-// value >= LC_ID_OVF when the key is not in this bucket, its id is not published yet, or the row's
-// key equals the empty sentinel.
+// value >= LC_ID_OVF when the key is not in this bucket or its id is not published yet.
 __device__ __forceinline__ uint32_t lc_lookup(uint64_t key, uint32_t b, const unsigned long long* tkeys,
                                               const uint16_t* tids) {
   const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(tkeys + 2 * b);
@@ -132,14 +162,39 @@ __device__ __forceinline__ uint32_t lc_lookup(uint64_t key, uint32_t b, const un
   return hit ? id : static_cast<uint32_t>(LC_ID_UNSET);
 }
 
-// Slow path: null / sentinel-valued keys, insertion on first sight, keys displaced from their home
-// bucket.  Per-lane (divergent) code, kept out of line.  LC_NOID on overflow.
-template <bool WIDE>
-__device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, bool kvalid, unsigned long long* tkeys,
-                                                 volatile uint16_t* tids, uint32_t* misc, uint32_t* status) {
-  using Cfg = LcCfg<WIDE>;
-  if (!kvalid) return Cfg::ID_NULL;
-  if (key == kEmptyKey) return Cfg::ID_EMPTYKEY;
+// Global id of a key that this CTA sees for the first time.  LC_NOID when more than gmax keys exist.
+__device__ __noinline__ uint32_t lc_global_id(uint64_t key, LcDir d, uint32_t gmax) {
+  uint32_t s = static_cast<uint32_t>(hash_key64(key)) & (LC_GT_CAP - 1);
+  for (int probe = 0; probe < LC_GT_CAP; ++probe) {
+    uint64_t k = *reinterpret_cast<volatile unsigned long long*>(d.gt_keys + s);
+    if (k == kEmptyKey) {
+      k = atomicCAS(d.gt_keys + s, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+      if (k == kEmptyKey) {
+        const uint32_t gid = atomicAdd(&d.prep->next_id, 1u);
+        if (gid >= gmax) {
+          *reinterpret_cast<volatile unsigned int*>(d.gt_ids + s) = LC_GID_OVF;
+          return LC_NOID;
+        }
+        d.key_by_id[gid] = key;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(d.gt_ids + s) = gid;
+        return gid;
+      }
+    }
+    if (k == key) {
+      uint32_t v;
+      do { v = *reinterpret_cast<volatile unsigned int*>(d.gt_ids + s); } while (v == LC_GID_UNSET);
+      return v == LC_GID_OVF ? LC_NOID : v;
+    }
+    s = (s + 1) & (LC_GT_CAP - 1);
+  }
+  return LC_NOID;
+}
+
+// Hash-mode slow path: insertion on first sight, keys displaced from their home bucket.  Per-lane
+// (divergent) code, kept out of line.  LC_NOID on overflow.
+__device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
+                                                 uint32_t* misc, LcDir d, uint32_t gmax, uint32_t* status) {
   uint32_t b = lc_bucket(key);
   for (int probe = 0; probe < 4 * LC_NBUCKET; ++probe) {
     const uint64_t k0 = *reinterpret_cast<volatile unsigned long long*>(tkeys + 2 * b);
@@ -151,16 +206,17 @@ __device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, bool kvalid, unsi
       const uint32_t s = (k0 == kEmptyKey) ? 2 * b : 2 * b + 1;   // lowest empty slot of the bucket
       const uint64_t old = atomicCAS(tkeys + s, static_cast<unsigned long long>(kEmptyKey),
                                      static_cast<unsigned long long>(key));
-      if (old == kEmptyKey) {  // this lane inserted the key: hand out the next dense id
-        const uint32_t nid = atomicAdd(misc, 1u);
-        if (nid >= static_cast<uint32_t>(Cfg::GMAX)) {
+      if (old == kEmptyKey) {  // this lane inserted the key into the CTA's table: fetch its global id
+        const uint32_t gid = lc_global_id(key, d, gmax);
+        if (gid == LC_NOID) {
           tids[s] = LC_ID_OVF;
           misc[1] = 1u;
           atomicExch(status + ST_OVERFLOW, 1u);
+          atomicExch(status + ST_ABORT, 1u);
           return LC_NOID;
         }
-        tids[s] = static_cast<uint16_t>(nid);
-        return nid;
+        tids[s] = static_cast<uint16_t>(gid);
+        return gid;
       }
       if (old != key) continue;   // lost the slot to another key: look at the same bucket again
       slot = s;
@@ -174,31 +230,32 @@ __device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, bool kvalid, unsi
   }
   misc[1] = 1u;
   atomicExch(status + ST_OVERFLOW, 1u);
+  atomicExch(status + ST_ABORT, 1u);
   return LC_NOID;
 }
 
-constexpr uint32_t LC_CNT_MASK = 0x00FFFFFFu;   // count field of an accumulator count word; byte 3 = claim tag
-
-// Accumulate one 32-row batch whose ids are known.  Warp-synchronous.
+// Accumulate one 32-row batch whose ids are known.  Warp-synchronous; lane L holds row `row`
+// (= batch row base + L).
 //
 // Duplicate ids inside the batch are found without MATCH.ANY (whose latency grows with the number
 // of distinct values, ~360 cycles at 32): every lane stores its lane number into the top byte of
-// its group's count word, then loads the word back — one lane per group reads its own number (the
+// its slot's count word, then loads the slot back — one lane per group reads its own number (the
 // "winner"), the others learn who won.  Winners then fold the losers' contributions in ascending
 // lane order (their own value at its own lane position, so the result does not depend on which
-// lane the hardware let win), and do one non-atomic read-modify-write.
-template <int VC, bool WIDE>
-__device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row,
-                                              uint32_t* cta_first, const LcAcc<WIDE>& acc) {
+// lane the hardware let win), and do one non-atomic read-modify-write of the 16-byte slot.
+// ALLLIVE: every lane holds a row with a resolved id (no tail, no overflowed lanes).
+template <int VC, bool WIDE, bool ALLLIVE>
+__device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row, const LcCtx& c) {
+  using Cfg = LcCfg<VC, WIDE>;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = lane_id();
-  const bool live = id != LC_NOID;
-  uint32_t* cw = acc.cnt + (live ? id : 0u);
-  if (live) reinterpret_cast<volatile uint8_t*>(cw)[3] = static_cast<uint8_t>(lane);
+  const bool live = ALLLIVE ? true : id != LC_NOID;
+  const uint32_t slot = c.accA + (live ? id : 0u) * 16u;
+  if (live) sts8(slot + 11u, lane);
   __syncwarp();
-  const uint32_t word = live ? *reinterpret_cast<volatile uint32_t*>(cw) : 0u;
-  const uint32_t w = word >> 24;
-  const bool winner = live && (w == lane);
+  const uint4 w = lds128(slot);
+  const uint32_t tag = w.z >> 24;
+  const bool winner = live && (tag == lane);
   const uint32_t losers = __ballot_sync(FULL, live && !winner);
   uint64_t c_sum = 0;           // double bits (VC_F, +0.0) or wrapping integer
   uint32_t c_cnt = 0;
@@ -208,7 +265,7 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
     c_sum = vbits;
     c_cnt = 1;
     if constexpr (WIDE) {
-      if constexpr (VC != VC_F) c_dsum = Wide<VC>::as_double(vbits);
+      if constexpr (Cfg::DSUM) c_dsum = Wide<VC>::as_double(vbits);
       if (!Wide<VC>::is_nan(vbits)) { c_min = Wide<VC>::ord(vbits); c_max = c_min; }
     }
   }
@@ -225,7 +282,7 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
       }
       t_cnt += x_cnt;
       if constexpr (WIDE) {
-        t_dsum += x_dsum;
+        if constexpr (Cfg::DSUM) t_dsum += x_dsum;
         t_min = x_min < t_min ? x_min : t_min;
         t_max = x_max > t_max ? x_max : t_max;
       }
@@ -241,13 +298,13 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
       while (rem) {
         const int L = __ffs(rem) - 1;
         rem &= rem - 1;
-        const uint32_t tw = __shfl_sync(FULL, w, L);
+        const uint32_t tw = __shfl_sync(FULL, tag, L);
         const uint64_t o_sum = __shfl_sync(FULL, c_sum, L);
         const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, L);
         double o_dsum = 0.0;
         uint64_t o_min = kMinInit, o_max = kMaxInit;
         if constexpr (WIDE) {
-          if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, L);
+          if constexpr (Cfg::DSUM) o_dsum = __shfl_sync(FULL, c_dsum, L);
           o_min = __shfl_sync(FULL, c_min, L);
           o_max = __shfl_sync(FULL, c_max, L);
         }
@@ -279,7 +336,7 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
         double o_dsum = 0.0;
         uint64_t o_min = kMinInit, o_max = kMaxInit;
         if constexpr (WIDE) {
-          if constexpr (VC != VC_F) o_dsum = __shfl_sync(FULL, c_dsum, src);
+          if constexpr (Cfg::DSUM) o_dsum = __shfl_sync(FULL, c_dsum, src);
           o_min = __shfl_sync(FULL, c_min, src);
           o_max = __shfl_sync(FULL, c_max, src);
         }
@@ -295,192 +352,248 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
   }
   // one non-atomic read-modify-write per distinct id
   if (doer) {
-    uint32_t old = word & LC_CNT_MASK;
+    uint32_t old = w.z & LC_CNT_MASK;
     if (old == LC_CNT_MASK) {  // first time this warp meets the id: candidate for the CTA's first row
       old = 0;
-      atomicMin(cta_first + id, row - lane + lo_lane);
+      atomicMin(c.cta_first + id, row + lo_lane - lane);
     }
-    *cw = old + c_cnt;   // also clears the claim tag
+    uint64_t s = static_cast<uint64_t>(w.x) | (static_cast<uint64_t>(w.y) << 32);
     if constexpr (VC == VC_F) {
-      double* s = reinterpret_cast<double*>(acc.sum + id);
-      *s = *s + __longlong_as_double(static_cast<long long>(c_sum));
+      s = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(s)) +
+                                                     __longlong_as_double(static_cast<long long>(c_sum))));
     } else {
-      acc.sum[id] += c_sum;
+      s += c_sum;
     }
+    // (the store also clears the claim tag)
+    sts128(slot, static_cast<uint32_t>(s), static_cast<uint32_t>(s >> 32), old + c_cnt, row + hi_lane - lane);
     if constexpr (WIDE) {
-      acc.last[id] = row - lane + hi_lane;
-      if constexpr (VC != VC_F) acc.dsum[id] += c_dsum;
-      if (c_min < acc.mn[id]) acc.mn[id] = c_min;
-      if (c_max > acc.mx[id]) acc.mx[id] = c_max;
+      const uint32_t mslot = c.accB + id * 16u;
+      const uint4 m4 = lds128(mslot);
+      const uint64_t mn = static_cast<uint64_t>(m4.x) | (static_cast<uint64_t>(m4.y) << 32);
+      const uint64_t mx = static_cast<uint64_t>(m4.z) | (static_cast<uint64_t>(m4.w) << 32);
+      if (c_min < mn || c_max > mx) {
+        const uint64_t nn = c_min < mn ? c_min : mn, nx = c_max > mx ? c_max : mx;
+        sts128(mslot, static_cast<uint32_t>(nn), static_cast<uint32_t>(nn >> 32), static_cast<uint32_t>(nx), static_cast<uint32_t>(nx >> 32));
+      }
+      if constexpr (Cfg::DSUM) c.accC[id] += c_dsum;
+    }
+  }
+  __syncwarp();
+}
+
+// One row group in registers: LC_NB = 2 * LC_STEPS batches of 32 rows, entry e = row g0 + 32 e + lane.
+constexpr int LC_NB = 2 * LC_STEPS;
+struct LcBuf {
+  uint64_t key[LC_NB];
+  uint64_t val[LC_NB];
+  uint32_t kv, vv, act;    // bit e: key valid / value valid / row exists
+};
+
+__device__ __forceinline__ uint64_t ldg_stream_u64(const void* p) {
+  uint64_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
+  return r;
+}
+
+// FAST loader: 8-byte keys and values, every row exists, no bitmaps.  Each load instruction reads
+// 256 contiguous bytes per warp.
+__device__ __forceinline__ void lc_load_fast(LcBuf& b, const LcArgs& a, int64_t g0, uint32_t lane, bool have_vals) {
+  const char* kp = static_cast<const char*>(a.keys) + (g0 + lane) * 8;
+  const char* vp = static_cast<const char*>(a.vals) + (g0 + lane) * 8;
+#pragma unroll
+  for (int e = 0; e < LC_NB; ++e) b.key[e] = ldg_stream_u64(kp + e * 256);
+  if (have_vals) {
+#pragma unroll
+    for (int e = 0; e < LC_NB; ++e) b.val[e] = ldg_stream_u64(vp + e * 256);
+  } else {
+#pragma unroll
+    for (int e = 0; e < LC_NB; ++e) b.val[e] = 0;
+  }
+  b.kv = 0xFFFFFFFFu;
+  b.vv = have_vals ? 0xFFFFFFFFu : 0u;
+  b.act = 0xFFFFFFFFu;
+}
+
+template <int VC>
+__device__ __forceinline__ void lc_load_generic(LcBuf& b, const LcArgs& a, int64_t g0, uint32_t lane) {
+  b.kv = 0; b.vv = 0; b.act = 0;
+#pragma unroll
+  for (int e = 0; e < LC_NB; ++e) {
+    const int64_t r = g0 + e * 32 + lane;
+    b.key[e] = 0;
+    b.val[e] = 0;
+    if (r < a.n) {
+      b.act |= 1u << e;
+      b.key[e] = a.kw == 8 ? static_cast<const uint64_t*>(a.keys)[r]
+                           : static_cast<uint64_t>(static_cast<const uint32_t*>(a.keys)[r]);
+      if (!a.kvalid || bit_at(a.kvalid, a.koff + r)) b.kv |= 1u << e;
+      if (a.vals) {
+        switch (a.vw) {
+          case 8: b.val[e] = load_wide<VC, 8>(a.vals, r); break;
+          case 4: b.val[e] = load_wide<VC, 4>(a.vals, r); break;
+          case 2: if constexpr (VC != VC_F) b.val[e] = load_wide<VC, 2>(a.vals, r); break;
+          default: if constexpr (VC != VC_F) b.val[e] = load_wide<VC, 1>(a.vals, r); break;
+        }
+        if (!a.vvalid || bit_at(a.vvalid, a.voff + r)) b.vv |= 1u << e;
+      }
     }
   }
 }
 
-// Two 32-row batches (A: rows rowA + lane, B: rows rowA + 32 + lane), interleaved.
-template <int VC, bool WIDE>
-__device__ __forceinline__ void lc_process_pair(bool actA, bool actB, uint64_t keyA, uint64_t keyB, bool kvA, bool kvB,
-                                                uint64_t vbA, uint64_t vbB, bool vvA, bool vvB, uint32_t rowA,
-                                                unsigned long long* tkeys, uint16_t* tids, uint32_t* cta_first,
-                                                uint32_t* misc, uint32_t* status, const LcAcc<WIDE>& acc) {
+// Process one row group: resolve the ids of all LC_NB batches first (independent lookups in flight,
+// one vote for the rare paths), then accumulate batch by batch.  Returns false on abort.
+// CLEAN: every row exists, no validity bitmaps (value validity = have_vals).
+template <int VC, bool WIDE, bool DENSE, bool CLEAN>
+__device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uint32_t lane, bool have_vals, const LcCtx& c,
+                                                 const LcArgs& a) {
+  using Cfg = LcCfg<VC, WIDE>;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
-  const uint32_t bA = lc_bucket(keyA), bB = lc_bucket(keyB);
-  uint32_t idA = lc_lookup(keyA, bA, tkeys, tids);
-  uint32_t idB = lc_lookup(keyB, bB, tkeys, tids);
-  bool missA = actA && idA >= LC_ID_OVF, missB = actB && idB >= LC_ID_OVF;
-  if (__any_sync(FULL, missA || missB)) {   // keys displaced by one bucket: second inline probe
-    if (missA) idA = lc_lookup(keyA, (bA + 1) & (LC_NBUCKET - 1), tkeys, tids);
-    if (missB) idB = lc_lookup(keyB, (bB + 1) & (LC_NBUCKET - 1), tkeys, tids);
-    missA = actA && idA >= LC_ID_OVF;
-    missB = actB && idB >= LC_ID_OVF;
+  uint32_t id[LC_NB];
+  if constexpr (DENSE) {
+    bool bad = false;
+#pragma unroll
+    for (int e = 0; e < LC_NB; ++e) {
+      const bool act = CLEAN ? true : ((b.act >> e) & 1u) != 0;
+      const bool kvalid = CLEAN ? true : ((b.kv >> e) & 1u) != 0;
+      const uint64_t d = b.key[e] - c.base;
+      id[e] = static_cast<uint32_t>(d);
+      if (!kvalid) id[e] = Cfg::ID_NULL;
+      if (!act) id[e] = LC_NOID;
+      bad |= act && kvalid && d >= static_cast<uint64_t>(Cfg::GMAX);
+    }
+    if (__any_sync(FULL, bad)) {
+      if (lane == 0) {
+        c.misc[1] = 1u;
+        atomicExch(a.status + ST_DENSE_MISS, 1u);
+        atomicExch(a.status + ST_ABORT, 1u);
+      }
+      return false;
+    }
+  } else {
+    uint32_t missmask = 0;
+#pragma unroll
+    for (int e = 0; e < LC_NB; ++e) {
+      const bool act = CLEAN ? true : ((b.act >> e) & 1u) != 0;
+      const bool kvalid = CLEAN ? true : ((b.kv >> e) & 1u) != 0;
+      const bool special = !kvalid || b.key[e] == kEmptyKey;
+      id[e] = lc_lookup(b.key[e], lc_bucket(b.key[e]), c.tkeys, c.tids);
+      if (special) id[e] = kvalid ? Cfg::ID_EMPTYKEY : Cfg::ID_NULL;
+      if (!act) id[e] = LC_NOID;
+      if (act && !special && id[e] >= LC_ID_OVF) missmask |= 1u << e;
+    }
+    if (__any_sync(FULL, missmask != 0)) {   // keys displaced by one bucket: second inline probe, then the slow path
+#pragma unroll
+      for (int e = 0; e < LC_NB; ++e) {
+        if ((missmask >> e) & 1u) {
+          id[e] = lc_lookup(b.key[e], (lc_bucket(b.key[e]) + 1) & (LC_NBUCKET - 1), c.tkeys, c.tids);
+          if (id[e] < LC_ID_OVF) missmask &= ~(1u << e);
+        }
+      }
+      if (__any_sync(FULL, missmask != 0)) {
+#pragma unroll
+        for (int e = 0; e < LC_NB; ++e) {
+          if ((missmask >> e) & 1u) id[e] = lc_slow_resolve(b.key[e], c.tkeys, c.tids, c.misc, a.dir, Cfg::GMAX, a.status);
+          __syncwarp();
+        }
+      }
+    }
   }
-  const bool slowA = missA || (actA && !kvA), slowB = missB || (actB && !kvB);
-  if (__any_sync(FULL, slowA || slowB)) {
-    if (slowA) idA = lc_slow_resolve<WIDE>(keyA, kvA, tkeys, tids, misc, status);
-    __syncwarp();
-    if (slowB) idB = lc_slow_resolve<WIDE>(keyB, kvB, tkeys, tids, misc, status);
-    __syncwarp();
+#pragma unroll
+  for (int e = 0; e < LC_NB; ++e) {
+    const uint32_t row = static_cast<uint32_t>(g0) + e * 32 + lane;
+    const bool vvalid = CLEAN ? have_vals : ((b.vv >> e) & 1u) != 0;
+    constexpr bool ALLLIVE = CLEAN && DENSE;
+    lc_accumulate<VC, WIDE, ALLLIVE>(id[e], b.val[e], vvalid && (ALLLIVE || id[e] != LC_NOID), row, c);
   }
-  if (!actA) idA = LC_NOID;
-  if (!actB) idB = LC_NOID;
-  lc_accumulate<VC, WIDE>(idA, vbA, vvA && actA && idA != LC_NOID, rowA, cta_first, acc);
-  __syncwarp();
-  lc_accumulate<VC, WIDE>(idB, vbB, vvB && actB && idB != LC_NOID, rowA + 32u, cta_first, acc);
-  __syncwarp();
+  return true;
 }
 
-template <int VC, int VW, int KW, bool WIDE, bool NULLS>
-__global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
-  using Cfg = LcCfg<WIDE>;
-  using L = LcSmem<WIDE>;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  unsigned long long* tkeys = reinterpret_cast<unsigned long long*>(smem + L::OFF_TKEYS);
-  uint16_t* tids = reinterpret_cast<uint16_t*>(smem + L::OFF_TIDS);
-  uint32_t* cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
-  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + L::OFF_MISC);   // [0] next id, [1] overflow seen
-  const int warp = threadIdx.x >> 5;
-  const uint32_t lane = lane_id();
-  LcAcc<WIDE> acc(smem + L::OFF_ACC + L::ACC_PER_WARP * warp);
-  constexpr size_t STAGE_BYTES = static_cast<size_t>(LC_CHUNK) * (KW + VW);
-  unsigned char* my_stage = smem + L::OFF_STAGE + STAGE_BYTES * LC_STAGES * warp;
-  uint64_t* my_bar = bars + warp * LC_STAGES;
-
-  // ---- init shared state ----
-  for (int i = threadIdx.x; i < LC_TCAP; i += LC_THREADS) {
-    tkeys[i] = kEmptyKey;
-    tids[i] = LC_ID_UNSET;
-  }
-  for (int i = threadIdx.x; i < Cfg::GP; i += LC_THREADS) cta_first[i] = kNoRow;
-  if (threadIdx.x < 4) misc[threadIdx.x] = 0;
-  for (int i = lane; i < Cfg::GP; i += 32) {
-    acc.sum[i] = 0;
-    acc.cnt[i] = LC_UNSEEN;
-    if constexpr (WIDE) { acc.last[i] = 0; acc.mn[i] = kMinInit; acc.mx[i] = kMaxInit; acc.dsum[i] = 0.0; }
-  }
-  if (lane == 0) {
-    for (int s = 0; s < LC_STAGES; ++s) mbar_init(my_bar + s, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  const bool have_vals = a.vals != nullptr;
-  const bool have_kvalid = NULLS && a.kvalid != nullptr, have_vvalid = NULLS && a.vvalid != nullptr;
+template <int VC, bool WIDE, bool FAST, bool DENSE>
+__device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, int warp, uint32_t lane) {
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * LC_WARPS + warp;
   const int64_t nw = static_cast<int64_t>(gridDim.x) * LC_WARPS;
-  const int64_t nchunks = a.n_bulk / LC_CHUNK;
-  const char* kbase = static_cast<const char*>(a.keys);
-  const char* vbase = static_cast<const char*>(a.vals);
-
-  auto issue = [&](int64_t chunk, int s) {  // lane 0 only
-    unsigned char* dst = my_stage + STAGE_BYTES * s;
-    const uint32_t kbytes = LC_CHUNK * KW, vbytes = have_vals ? LC_CHUNK * VW : 0;
-    mbar_expect_tx(my_bar + s, kbytes + vbytes);
-    bulk_g2s(dst, kbase + chunk * (LC_CHUNK * KW), kbytes, my_bar + s);
-    if (have_vals) bulk_g2s(dst + LC_CHUNK * KW, vbase + chunk * (LC_CHUNK * VW), vbytes, my_bar + s);
-  };
-
-  // ---- streamed part: chunks gw, gw + nw, ... (fixed chunk -> warp map) ----
-  // Every issued bulk copy is waited for before the CTA may exit (also on overflow), so no copy
-  // can land in shared memory that already belongs to another CTA.
-  if (gw < nchunks) {
-    int64_t last_issued = gw;
-    for (int s = 0; s < LC_STAGES; ++s) {
-      const int64_t c = gw + static_cast<int64_t>(s) * nw;
-      if (c < nchunks) {
-        if (lane == 0) issue(c, s);
-        last_issued = c;
-      }
+  const bool have_vals = a.vals != nullptr;
+  const int64_t n_full = a.n / LC_GROUP_ROWS;                        // full row groups
+  const int64_t n_groups = (a.n + LC_GROUP_ROWS - 1) / LC_GROUP_ROWS;
+  volatile uint32_t* abort_local = c.misc + 1;
+  volatile uint32_t* abort_global = a.status + ST_ABORT;
+  if constexpr (FAST) {
+    LcBuf cur, nxt;
+    int64_t g = gw;
+    if (g < n_full) lc_load_fast(cur, a, g * LC_GROUP_ROWS, lane, have_vals);
+    while (g < n_full) {
+      const int64_t gn = g + nw;
+      if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane, have_vals);
+      const uint32_t gabort = *abort_global;
+      if (!lc_process_group<VC, WIDE, DENSE, true>(cur, g * LC_GROUP_ROWS, lane, have_vals, c, a)) return;
+      if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
+      cur = nxt;
+      g = gn;
     }
-    int s = 0;
-    uint32_t phase = 0;
-    for (int64_t c = gw; c <= last_issued; c += nw) {
-      mbar_wait(my_bar + s, phase);
-      // (only the CTA-local flag is polled: a global poll costs one system-scope load per chunk, and
-      //  every CTA meets the same key population, so each one notices an overflow by itself)
-      const bool ovf = __any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(misc + 1) != 0);
-      if (!ovf) {
-        const unsigned char* st = my_stage + STAGE_BYTES * s;
-        const int64_t row0 = c * LC_CHUNK;
-#pragma unroll 1
-        for (int step = 0; step < LC_CHUNK / 64; ++step) {
-          const int rA = step * 64 + lane, rB = rA + 32;
-          uint64_t keyA, keyB;
-          if constexpr (KW == 8) {
-            keyA = reinterpret_cast<const uint64_t*>(st)[rA];
-            keyB = reinterpret_cast<const uint64_t*>(st)[rB];
-          } else {
-            keyA = reinterpret_cast<const uint32_t*>(st)[rA];
-            keyB = reinterpret_cast<const uint32_t*>(st)[rB];
-          }
-          uint64_t vbA = 0, vbB = 0;
-          bool vvA = false, vvB = false, kvA = true, kvB = true;
-          const int64_t rowA = row0 + rA;
-          if (have_vals) {
-            vbA = load_wide<VC, VW>(st + LC_CHUNK * KW, rA);
-            vbB = load_wide<VC, VW>(st + LC_CHUNK * KW, rB);
-            vvA = vvB = true;
-            if (have_vvalid) { vvA = bit_at(a.vvalid, a.voff + rowA); vvB = bit_at(a.vvalid, a.voff + rowA + 32); }
-          }
-          if (have_kvalid) { kvA = bit_at(a.kvalid, a.koff + rowA); kvB = bit_at(a.kvalid, a.koff + rowA + 32); }
-          lc_process_pair<VC, WIDE>(true, true, keyA, keyB, kvA, kvB, vbA, vbB, vvA, vvB, static_cast<uint32_t>(rowA),
-                                    tkeys, tids, cta_first, misc, a.status, acc);
-        }
-      }
-      __syncwarp();
-      const int64_t cn = c + static_cast<int64_t>(LC_STAGES) * nw;
-      if (!ovf && cn < nchunks) {
-        if (lane == 0) {
-          fence_proxy_async();
-          issue(cn, s);
-        }
-        last_issued = cn;
-      }
-      if (++s == LC_STAGES) { s = 0; phase ^= 1; }
+    // the last, partial row group (if any) goes through the generic loader
+    if (n_groups > n_full && gw == (n_full % nw)) {
+      LcBuf t;
+      lc_load_generic<VC>(t, a, n_full * LC_GROUP_ROWS, lane);
+      lc_process_group<VC, WIDE, DENSE, false>(t, n_full * LC_GROUP_ROWS, lane, have_vals, c, a);
+    }
+  } else {
+    LcBuf cur, nxt;
+    int64_t g = gw;
+    if (g < n_groups) lc_load_generic<VC>(cur, a, g * LC_GROUP_ROWS, lane);
+    while (g < n_groups) {
+      const int64_t gn = g + nw;
+      if (gn < n_groups) lc_load_generic<VC>(nxt, a, gn * LC_GROUP_ROWS, lane);
+      const uint32_t gabort = *abort_global;
+      if (!lc_process_group<VC, WIDE, DENSE, false>(cur, g * LC_GROUP_ROWS, lane, have_vals, c, a)) return;
+      if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
+      cur = nxt;
+      g = gn;
     }
   }
+}
 
-  // ---- remainder rows [n_bulk, n): direct loads, warps of the whole grid take 64-row steps ----
-  for (int64_t r0 = a.n_bulk + gw * 64; r0 < a.n; r0 += nw * 64) {
-    if (__any_sync(0xFFFFFFFFu, *reinterpret_cast<volatile uint32_t*>(misc + 1) != 0)) break;
-    const int64_t rowA = r0 + lane, rowB = rowA + 32;
-    const bool actA = rowA < a.n, actB = rowB < a.n;
-    uint64_t keyA = 0, keyB = 0, vbA = 0, vbB = 0;
-    bool kvA = true, kvB = true, vvA = false, vvB = false;
-    if (actA) {
-      keyA = load_key<KW>(a.keys, rowA);
-      if (have_kvalid) kvA = bit_at(a.kvalid, a.koff + rowA);
-      if (have_vals) { vbA = load_wide<VC, VW>(a.vals, rowA); vvA = have_vvalid ? bit_at(a.vvalid, a.voff + rowA) : true; }
+// FAST: int64/uint64 keys and 8-byte values (or none), no validity bitmaps, 16-byte aligned columns.
+template <int VC, bool WIDE, bool FAST>
+__global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
+  using Cfg = LcCfg<VC, WIDE>;
+  using L = LcSmem<VC, WIDE>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  LcCtx c;
+  c.misc = reinterpret_cast<uint32_t*>(smem + L::OFF_MISC);
+  c.tkeys = reinterpret_cast<unsigned long long*>(smem + L::OFF_TKEYS);
+  c.tids = reinterpret_cast<uint16_t*>(smem + L::OFF_TIDS);
+  c.cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
+  unsigned char* my_acc = smem + L::OFF_ACC + L::ACC_PER_WARP * warp;
+  c.accA = smem_u32(my_acc);
+  c.accB = c.accA + static_cast<uint32_t>(L::A_BYTES);
+  c.accC = reinterpret_cast<double*>(my_acc + L::A_BYTES + L::B_BYTES);
+  const bool dense = lc_dense_mode(a.dir.prep, a.force_hash, Cfg::GMAX, &c.base);
+
+  // ---- init shared state ----
+  if (!dense) {
+    for (int i = threadIdx.x; i < LC_TCAP; i += LC_THREADS) {
+      c.tkeys[i] = kEmptyKey;
+      c.tids[i] = LC_ID_UNSET;
     }
-    if (actB) {
-      keyB = load_key<KW>(a.keys, rowB);
-      if (have_kvalid) kvB = bit_at(a.kvalid, a.koff + rowB);
-      if (have_vals) { vbB = load_wide<VC, VW>(a.vals, rowB); vvB = have_vvalid ? bit_at(a.vvalid, a.voff + rowB) : true; }
-    }
-    lc_process_pair<VC, WIDE>(actA, actB, keyA, keyB, kvA, kvB, vbA, vbB, vvA, vvB, static_cast<uint32_t>(rowA), tkeys,
-                              tids, cta_first, misc, a.status, acc);
+  }
+  for (int i = threadIdx.x; i < Cfg::GP; i += LC_THREADS) c.cta_first[i] = kNoRow;
+  if (threadIdx.x < 4) c.misc[threadIdx.x] = 0;
+  for (int i = lane; i < Cfg::GP; i += 32) {
+    reinterpret_cast<uint4*>(my_acc)[i] = make_uint4(0u, 0u, LC_CNT_MASK, 0u);
+    if constexpr (WIDE) reinterpret_cast<ulonglong2*>(my_acc + L::A_BYTES)[i] = make_ulonglong2(kMinInit, kMaxInit);
+    if constexpr (Cfg::DSUM) c.accC[i] = 0.0;
   }
   __syncthreads();
-  if (misc[1]) return;
+
+  if (dense) lc_scan_rows<VC, WIDE, FAST, true>(a, c, warp, lane);
+  else lc_scan_rows<VC, WIDE, FAST, false>(a, c, warp, lane);
+  __syncthreads();
+  if (c.misc[1]) {
+    if (threadIdx.x == 0) atomicExch(a.status + ST_ABORT, 1u);
+    return;
+  }
 
   // ---- fold the warps in warp order and write this CTA's partial table ----
   const size_t pbase = static_cast<size_t>(blockIdx.x) * Cfg::GP;
@@ -490,175 +603,184 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
     uint32_t cnt = 0, last = 0;
     uint64_t mn = kMinInit, mx = kMaxInit;
     for (int w = 0; w < LC_WARPS; ++w) {
-      LcAcc<WIDE> o(smem + L::OFF_ACC + L::ACC_PER_WARP * w);
-      const uint32_t c = o.cnt[id] & LC_CNT_MASK;
-      if (c == LC_CNT_MASK) continue;
-      cnt += c;
-      if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(o.sum[id]));
-      else sum += o.sum[id];
+      const unsigned char* wa = smem + L::OFF_ACC + L::ACC_PER_WARP * w;
+      const uint4 sa = reinterpret_cast<const uint4*>(wa)[id];
+      const uint32_t cw = sa.z & LC_CNT_MASK;
+      if (cw == LC_CNT_MASK) continue;
+      cnt += cw;
+      const uint64_t s = static_cast<uint64_t>(sa.x) | (static_cast<uint64_t>(sa.y) << 32);
+      if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(s));
+      else sum += s;
+      last = sa.w > last ? sa.w : last;
       if constexpr (WIDE) {
-        dsum += o.dsum[id];
-        last = o.last[id] > last ? o.last[id] : last;
-        mn = o.mn[id] < mn ? o.mn[id] : mn;
-        mx = o.mx[id] > mx ? o.mx[id] : mx;
+        const ulonglong2 mm = reinterpret_cast<const ulonglong2*>(wa + L::A_BYTES)[id];
+        mn = mm.x < mn ? mm.x : mn;
+        mx = mm.y > mx ? mm.y : mx;
+        if constexpr (Cfg::DSUM) dsum += reinterpret_cast<const double*>(wa + L::A_BYTES + L::B_BYTES)[id];
       }
     }
     if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(fsum));
     a.p_sum[pbase + id] = sum;
     a.p_count[pbase + id] = cnt;
-    a.p_first[pbase + id] = cta_first[id];
+    a.p_first[pbase + id] = c.cta_first[id];
+    a.p_last[pbase + id] = last;
     if constexpr (WIDE) {
-      a.p_dsum[pbase + id] = dsum;
-      a.p_last[pbase + id] = last;
       a.p_min[pbase + id] = mn;
       a.p_max[pbase + id] = mx;
+      if constexpr (Cfg::DSUM) a.p_dsum[pbase + id] = dsum;
     }
   }
-  for (int slot = threadIdx.x; slot < LC_TCAP; slot += LC_THREADS) {
-    const uint16_t id = tids[slot];
-    if (id < Cfg::GMAX) a.p_key[pbase + id] = tkeys[slot];
-  }
-  if (threadIdx.x == 0) a.p_nids[blockIdx.x] = misc[0] < static_cast<uint32_t>(Cfg::GMAX) ? misc[0] : Cfg::GMAX;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Merge: one CTA.  Joins the per-CTA partial tables by key, folds them in CTA order, ranks the
-// merged groups by first row, writes the GroupResult and status[ST_NGROUPS].
+// Prep: sample the key range (dense-mode decision) and reset the global id directory.
 // ---------------------------------------------------------------------------------------------
-constexpr int LM_THREADS = 1024;
-constexpr int LM_TCAP_LOG2 = 12;
-constexpr int LM_TCAP = 1 << LM_TCAP_LOG2;
+__global__ void __launch_bounds__(256) k_lowcard_prep(LcArgs a) {
+  const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+  const uint32_t nt = gridDim.x * 256u;
+  for (uint32_t i = t; i < LC_GT_CAP; i += nt) {
+    a.dir.gt_keys[i] = kEmptyKey;
+    a.dir.gt_ids[i] = LC_GID_UNSET;
+  }
+  uint64_t nmin = 0, mx = 0;
+  const int64_t r = a.n <= static_cast<int64_t>(nt) ? static_cast<int64_t>(t)
+                                                   : static_cast<int64_t>((static_cast<uint64_t>(t) * static_cast<uint64_t>(a.n)) / nt);
+  if (r < a.n && (!a.kvalid || bit_at(a.kvalid, a.koff + r))) {
+    const uint64_t key = a.kw == 8 ? static_cast<const uint64_t*>(a.keys)[r]
+                                   : static_cast<uint64_t>(static_cast<const uint32_t*>(a.keys)[r]);
+    const uint64_t o = key ^ 0x8000000000000000ull;
+    nmin = ~o;
+    mx = o;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const uint64_t on = __shfl_xor_sync(0xFFFFFFFFu, nmin, d), om = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
+    nmin = on > nmin ? on : nmin;
+    mx = om > mx ? om : mx;
+  }
+  if (lane_id() == 0 && (nmin | mx)) {
+    atomicMax(&a.dir.prep->nmin_ord, static_cast<unsigned long long>(nmin));
+    atomicMax(&a.dir.prep->max_ord, static_cast<unsigned long long>(mx));
+  }
+}
 
+// ---------------------------------------------------------------------------------------------
+// Merge: one warp per group id folds the per-CTA partials (lane-strided, then a fixed shuffle tree).
+// ---------------------------------------------------------------------------------------------
 struct LmArgs {
   LcArgs part;          // partial tables written by the scan
   int grid;             // number of scan CTAs
-  uint16_t* inv;        // [GP][grid] scratch, pre-filled with 0xFFFF: merged id, CTA -> CTA-local id
+  int gp;               // ids per partial table
+  // merged, indexed by id
+  uint64_t* m_sum;
+  double* m_dsum;
+  uint32_t* m_count;
+  uint32_t* m_first;
+  uint32_t* m_last;
+  uint64_t* m_min;
+  uint64_t* m_max;
   GroupResult out;
   uint32_t* status;
 };
 
 template <int VC, bool WIDE>
-__global__ void __launch_bounds__(LM_THREADS, 1) k_lowcard_merge(LmArgs a) {
-  using Cfg = LcCfg<WIDE>;
-  __shared__ unsigned long long mkeys[LM_TCAP];
-  __shared__ uint16_t mids[LM_TCAP];
-  __shared__ uint32_t sfirst[Cfg::GP];
-  __shared__ uint32_t m_next, m_ovf;
-  if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) return;
-  for (int i = threadIdx.x; i < LM_TCAP; i += LM_THREADS) { mkeys[i] = kEmptyKey; mids[i] = LC_ID_UNSET; }
-  for (int i = threadIdx.x; i < Cfg::GP; i += LM_THREADS) sfirst[i] = kNoRow;
-  if (threadIdx.x == 0) { m_next = 0; m_ovf = 0; }
-  __syncthreads();
-  const int grid = a.grid;
-  // phase 1: join by key
-  for (int idx = threadIdx.x; idx < grid * Cfg::GMAX; idx += LM_THREADS) {
-    const int b = idx / Cfg::GMAX, id = idx - b * Cfg::GMAX;
-    if (static_cast<uint32_t>(id) >= a.part.p_nids[b]) continue;
-    const uint64_t key = a.part.p_key[static_cast<size_t>(b) * Cfg::GP + id];
-    uint32_t slot = hash_key(key) >> (32 - LM_TCAP_LOG2);
-    uint32_t mid = LC_NOID;
-    for (int probe = 0; probe < LM_TCAP; ++probe) {
-      const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(mkeys + slot);
-      bool found = (k == key);
-      if (!found && k == kEmptyKey) {
-        const uint64_t old = atomicCAS(mkeys + slot, static_cast<unsigned long long>(kEmptyKey),
-                                       static_cast<unsigned long long>(key));
-        if (old == kEmptyKey) {
-          const uint32_t nid = atomicAdd(&m_next, 1u);
-          if (nid >= static_cast<uint32_t>(Cfg::GMAX)) { m_ovf = 1; *reinterpret_cast<volatile uint16_t*>(mids + slot) = LC_ID_OVF; break; }
-          *reinterpret_cast<volatile uint16_t*>(mids + slot) = static_cast<uint16_t>(nid);
-          mid = nid;
-          break;
-        }
-        found = (old == key);
-      }
-      if (found) {
-        uint16_t v;
-        do { v = *reinterpret_cast<volatile uint16_t*>(mids + slot); } while (v == LC_ID_UNSET);
-        mid = (v == LC_ID_OVF) ? LC_NOID : v;
-        break;
-      }
-      slot = (slot + 1) & (LM_TCAP - 1);
-    }
-    if (mid != LC_NOID) a.inv[static_cast<size_t>(mid) * grid + b] = static_cast<uint16_t>(id);
-  }
-  __syncthreads();
-  if (m_ovf) {
-    if (threadIdx.x == 0) atomicExch(a.status + ST_OVERFLOW, 1u);
-    return;
-  }
-  const int M = m_next;
-  __threadfence_block();
-  __syncthreads();
-  // phase 2: fold partials in CTA order (merged groups M and M+1 are the two special groups);
-  // up to two merged groups per thread (GMAX + 2 may exceed the block size)
-  constexpr int U = (Cfg::GP + LM_THREADS - 1) / LM_THREADS;
-  uint64_t r_sum[U], r_key[U], r_min[U], r_max[U];
-  double r_dsum[U];
-  uint32_t r_cnt[U], r_first[U], r_last[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int m = threadIdx.x + u * LM_THREADS;
-    r_sum[u] = 0; r_key[u] = 0; r_min[u] = kMinInit; r_max[u] = kMaxInit; r_dsum[u] = 0.0;
-    r_cnt[u] = 0; r_first[u] = kNoRow; r_last[u] = 0;
-    if (m >= M + 2) continue;
-    double fsum = 0.0;
-    for (int b = 0; b < grid; ++b) {
-      int id;
-      if (m < M) {
-        const uint16_t v = a.inv[static_cast<size_t>(m) * grid + b];
-        if (v == LC_ID_UNSET) continue;
-        id = v;
-      } else {
-        id = (m == M) ? Cfg::ID_NULL : Cfg::ID_EMPTYKEY;
-      }
-      const size_t p = static_cast<size_t>(b) * Cfg::GP + id;
-      const uint32_t f = a.part.p_first[p];
-      if (f == kNoRow) continue;
-      if (m < M) r_key[u] = a.part.p_key[p];
-      r_first[u] = f < r_first[u] ? f : r_first[u];
-      r_cnt[u] += a.part.p_count[p];
-      if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(a.part.p_sum[p]));
-      else r_sum[u] += a.part.p_sum[p];
-      if constexpr (WIDE) {
-        r_dsum[u] += a.part.p_dsum[p];
-        const uint32_t l = a.part.p_last[p];
-        r_last[u] = l > r_last[u] ? l : r_last[u];
-        const uint64_t mn = a.part.p_min[p], mx = a.part.p_max[p];
-        r_min[u] = mn < r_min[u] ? mn : r_min[u];
-        r_max[u] = mx > r_max[u] ? mx : r_max[u];
-      }
-    }
-    if constexpr (VC == VC_F) r_sum[u] = static_cast<uint64_t>(__double_as_longlong(fsum));
-    if (m == M + 1) r_key[u] = kEmptyKey;
-    sfirst[m] = r_first[u];
-  }
-  __syncthreads();
-  // phase 3: rank by first row (first rows are distinct: a row belongs to exactly one group)
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int m = threadIdx.x + u * LM_THREADS;
-    if (m >= M + 2 || r_first[u] == kNoRow) continue;
-    uint32_t rank = 0;
-    for (int j = 0; j < M + 2; ++j) rank += sfirst[j] < r_first[u];
-    a.out.key[rank] = r_key[u];
-    a.out.key_kind[rank] = (m == M) ? KK_NULL : KK_REGULAR;
-    a.out.sum[rank] = r_sum[u];
-    a.out.count[rank] = r_cnt[u];
-    a.out.first_row[rank] = r_first[u];
+__global__ void __launch_bounds__(256) k_lowcard_merge(LmArgs a) {
+  using Cfg = LcCfg<VC, WIDE>;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const int id = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (id >= Cfg::GP) return;
+  if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_ABORT)) return;
+  const uint32_t lane = lane_id();
+  uint64_t sum = 0, mn = kMinInit, mx = kMaxInit;
+  double fsum = 0.0, dsum = 0.0;
+  uint32_t cnt = 0, first = kNoRow, last = 0;
+  for (int b = lane; b < a.grid; b += 32) {
+    const size_t p = static_cast<size_t>(b) * Cfg::GP + id;
+    const uint32_t f = a.part.p_first[p];
+    if (f == kNoRow) continue;
+    first = f < first ? f : first;
+    cnt += a.part.p_count[p];
+    if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(a.part.p_sum[p]));
+    else sum += a.part.p_sum[p];
+    const uint32_t l = a.part.p_last[p];
+    last = l > last ? l : last;
     if constexpr (WIDE) {
-      a.out.last_row[rank] = r_last[u];
-      a.out.min_ord[rank] = r_min[u];
-      a.out.max_ord[rank] = r_max[u];
-      if (a.out.dsum) a.out.dsum[rank] = r_dsum[u];
+      const uint64_t pmn = a.part.p_min[p], pmx = a.part.p_max[p];
+      mn = pmn < mn ? pmn : mn;
+      mx = pmx > mx ? pmx : mx;
+      if constexpr (Cfg::DSUM) dsum += a.part.p_dsum[p];
     }
   }
-  if (threadIdx.x == 0) {
-    uint32_t G = M;
-    G += sfirst[M] != kNoRow;
-    G += sfirst[M + 1] != kNoRow;
-    a.status[ST_NGROUPS] = G;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const uint32_t of = __shfl_xor_sync(FULL, first, d), ol = __shfl_xor_sync(FULL, last, d);
+    first = of < first ? of : first;
+    last = ol > last ? ol : last;
+    cnt += __shfl_xor_sync(FULL, cnt, d);
+    if constexpr (VC == VC_F) fsum += __shfl_xor_sync(FULL, fsum, d);
+    else sum += __shfl_xor_sync(FULL, sum, d);
+    if constexpr (WIDE) {
+      const uint64_t on = __shfl_xor_sync(FULL, mn, d), ox = __shfl_xor_sync(FULL, mx, d);
+      mn = on < mn ? on : mn;
+      mx = ox > mx ? ox : mx;
+      if constexpr (Cfg::DSUM) dsum += __shfl_xor_sync(FULL, dsum, d);
+    }
   }
+  if (lane == 0) {
+    if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(fsum));
+    a.m_sum[id] = sum;
+    a.m_count[id] = cnt;
+    a.m_first[id] = first;
+    a.m_last[id] = last;
+    if constexpr (WIDE) {
+      a.m_min[id] = mn;
+      a.m_max[id] = mx;
+      if constexpr (Cfg::DSUM) a.m_dsum[id] = dsum;
+    }
+  }
+}
+
+// Rank: one CTA orders the merged groups by first row (first rows are distinct: a row belongs to
+// exactly one group), writes the GroupResult and status[ST_NGROUPS].
+constexpr int LR_THREADS = 1024;
+template <int VC, bool WIDE>
+__global__ void __launch_bounds__(LR_THREADS, 1) k_lowcard_rank(LmArgs a) {
+  using Cfg = LcCfg<VC, WIDE>;
+  __shared__ uint32_t sfirst[Cfg::GP];
+  if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_ABORT)) return;
+  uint64_t base;
+  const bool dense = lc_dense_mode(a.part.dir.prep, a.part.force_hash, Cfg::GMAX, &base);
+  for (int i = threadIdx.x; i < Cfg::GP; i += LR_THREADS) sfirst[i] = a.m_first[i];
+  __syncthreads();
+  int present = 0;
+  for (int id = threadIdx.x; id < Cfg::GP; id += LR_THREADS) {
+    const uint32_t f = sfirst[id];
+    if (f == kNoRow) continue;
+    ++present;
+    uint32_t rank = 0;
+    for (int j = 0; j < Cfg::GP; ++j) rank += sfirst[j] < f;
+    uint64_t key;
+    if (id == Cfg::ID_NULL) key = 0;
+    else if (id == Cfg::ID_EMPTYKEY) key = kEmptyKey;
+    else key = dense ? base + static_cast<uint64_t>(id) : a.part.dir.key_by_id[id];
+    a.out.key[rank] = key;
+    a.out.key_kind[rank] = (id == Cfg::ID_NULL) ? KK_NULL : KK_REGULAR;
+    a.out.sum[rank] = a.m_sum[id];
+    a.out.count[rank] = a.m_count[id];
+    a.out.first_row[rank] = f;
+    a.out.last_row[rank] = a.m_last[id];
+    if constexpr (WIDE) {
+      a.out.min_ord[rank] = a.m_min[id];
+      a.out.max_ord[rank] = a.m_max[id];
+      if constexpr (Cfg::DSUM) { if (a.out.dsum) a.out.dsum[rank] = a.m_dsum[id]; }
+    }
+  }
+  __shared__ uint32_t s_total;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  if (present) atomicAdd(&s_total, static_cast<uint32_t>(present));
+  __syncthreads();
+  if (threadIdx.x == 0) a.status[ST_NGROUPS] = s_total;
 }
 
 }  // namespace pa
