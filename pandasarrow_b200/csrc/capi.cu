@@ -254,8 +254,7 @@ bool is_wide(uint32_t mask, int vc) {
 // ------------------------------ low-cardinality path ------------------------------
 enum LcOutcome { LC_DONE = 0, LC_DENSE_MISS = 1, LC_OVERFLOW = 2 };
 
-// the kernel's WIDE variant: min/max slots (+ a double sum for the mean of integers); `last` is free
-bool lc_is_wide(uint32_t mask, int vc) { return (mask & (AGG_MIN | AGG_MAX)) || ((mask & AGG_MEAN) && vc != VC_F); }
+bool lc_is_wide(uint32_t mask, int vc) { return is_wide(mask, vc); }
 
 template <int VC, bool WIDE>
 int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast) {
@@ -266,7 +265,7 @@ int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, 
   CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL)));
   k_lowcard_prep<<<LC_PREP_GRID, 256, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
-  scan<<<grid, LC_THREADS, L::TOTAL, st>>>(a);
+  scan<<<grid, Cfg::THREADS, L::TOTAL, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(g->ev[2], st));
   k_lowcard_merge<VC, WIDE><<<(Cfg::GP + 7) / 8, 256, 0, st>>>(m);
@@ -289,8 +288,8 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   PA_TRY(p_sum.alloc(np * 8, st));
   PA_TRY(p_count.alloc(np * 4, st));
   PA_TRY(p_first.alloc(np * 4, st));
-  PA_TRY(p_last.alloc(np * 4, st));
   if (kwide) {
+    PA_TRY(p_last.alloc(np * 4, st));
     PA_TRY(p_min.alloc(np * 8, st));
     PA_TRY(p_max.alloc(np * 8, st));
     if (dsum) PA_TRY(p_dsum.alloc(np * 8, st));
@@ -304,10 +303,6 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   CUDA_TRY(cudaMemsetAsync(dir.p, 0, sizeof(LcPrep), st));
   CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
   PA_TRY(alloc_result(g, gp, wide, vc != VC_F));
-  if (wide && !kwide) {   // min/max are not computed by this pass: keep the arrays defined
-    CUDA_TRY(cudaMemsetAsync(g->r_min.p, 0xFF, static_cast<size_t>(gp) * 8, st));
-    CUDA_TRY(cudaMemsetAsync(g->r_max.p, 0x00, static_cast<size_t>(gp) * 8, st));
-  }
 
   LcArgs a{};
   a.keys = g->key_data;
@@ -333,8 +328,8 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   a.p_min = p_min.as<uint64_t>();
   a.p_max = p_max.as<uint64_t>();
   a.status = g->status.as<uint32_t>();
-  const bool aligned = (reinterpret_cast<uintptr_t>(a.keys) % 16 == 0) && (!a.vals || reinterpret_cast<uintptr_t>(a.vals) % 16 == 0);
-  const bool fast = aligned && a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid && !a.vvalid;
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.keys) % 8 == 0) && (reinterpret_cast<uintptr_t>(a.vals) % 8 == 0);
+  const bool fast = a.vals && aligned && a.kw == 8 && a.vw == 8 && !a.kvalid && !a.vvalid;
   LmArgs m{};
   m.part = a;
   m.grid = grid;

@@ -1,12 +1,13 @@
-// Low-cardinality path (stages 1-3 fused): one persistent 8-warp CTA per SM, accumulators privatised
-// per warp in shared memory.
+// Low-cardinality path (stages 1-3 fused): one persistent CTA per SM (12 warps for the narrow
+// aggregates, 8 for the wide ones), accumulators privatised per warp in shared memory.
 //
 //  * Input: every warp streams "row groups" of 256 rows (8 batches of 32 rows) with coalesced
 //    non-allocating loads (256 contiguous bytes per warp per instruction); the next group is
-//    loaded into a second register buffer before the current one is processed, so ~4 KB per warp /
-//    32 KB per SM are in flight at all times without relying on occupancy.  (The earlier version
+//    loaded into a second register buffer before the current one is processed, so 4 KB per warp /
+//    32-48 KB per SM are in flight at all times without relying on occupancy.  (The first version
 //    staged the rows through shared memory with bulk async copies; ncu showed the kernel bound by
-//    shared-memory wavefronts, so the staging traffic was removed — profiles/r1_lowcard_v3_*.)
+//    shared-memory wavefronts and instruction latency, so the staging traffic was removed —
+//    profiles/r1_lowcard_v3_*.)
 //  * Stage 1-2, key -> dense group id, two modes chosen ON THE DEVICE from a key-range sample taken
 //    by k_lowcard_prep (no host round trip):
 //      dense : all sampled keys lie in a window of <= GMAX values -> id = key - base, no table at all.
@@ -17,14 +18,17 @@
 //              small directory in global memory, so that ids mean the same group in every CTA and
 //              the merge needs no join.  Null keys and the key equal to the table sentinel have
 //              dedicated ids.
-//  * Stage 3: accumulators are WARP-PRIVATE 16-byte slots {sum, count|claim tag, last row} in shared
-//    memory (+ {min, max} and a double sum for the wide aggregates), updated with one LDS.128 +
-//    one STS.128 and no atomics (sm_100a has no native 64-bit shared-memory atomics: f64/u64 adds
-//    compile to ATOMS.CAST.SPIN loops).  Lanes of a warp that hit the same group in a 32-row batch
-//    are found with a claim tag (each lane stores its lane number into the top byte of the slot's
-//    count word and reads the slot back: one lane reads its own number); winners fold the losers'
-//    values in ascending row order with shuffles.  The order of floating-point additions is a fixed
-//    function of (n_rows, grid size): results are run-to-run deterministic.
+//  * Stage 3: accumulators are WARP-PRIVATE arrays in shared memory (sum 8 B + count word 4 B per
+//    id; the wide variant adds last row, {min, max} and a double sum), updated with plain loads and
+//    stores — no atomics (sm_100a has no native 64-bit shared-memory atomics: f64/u64 adds compile
+//    to ATOMS.CAST.SPIN loops).  Lanes of a warp that hit the same group in a 32-row batch are
+//    found with a claim tag: each lane stores its lane number into the top byte of the group's
+//    count word and reads the word back; one lane per group reads its own number (the winner).
+//    With one losing lane in the batch (the common case) its group has two members and the winner
+//    adds the loser's value to its own (commutative, so it does not matter which lane won); with
+//    more, an out-of-line routine folds every group in ascending row order.  The order of
+//    floating-point additions is therefore a fixed function of (n_rows, grid size): results are
+//    run-to-run deterministic.
 //  * At the end each CTA folds its warps in warp order into a partial table; k_lowcard_merge folds
 //    the partial tables (one warp per group id, fixed order), k_lowcard_rank orders the groups by
 //    first row and writes the GroupResult.
@@ -37,21 +41,19 @@
 
 namespace pa {
 
-constexpr int LC_WARPS = 8;
-constexpr int LC_THREADS = LC_WARPS * 32;
 constexpr int LC_NB_LOG2 = 11;
 constexpr int LC_NBUCKET = 1 << LC_NB_LOG2;  // buckets of two keys
 constexpr int LC_TCAP = LC_NBUCKET * 2;      // key slots
-constexpr int LC_STEPS = 4;                  // 64-row steps per row group
-constexpr int LC_GROUP_ROWS = LC_STEPS * 64; // rows per warp per row group
+constexpr int LC_NB = 8;                     // 32-row batches per row group
+constexpr int LC_GROUP_ROWS = LC_NB * 32;    // rows per warp per row group
 constexpr uint16_t LC_ID_UNSET = 0xFFFFu;
 constexpr uint16_t LC_ID_OVF = 0xFFFEu;
 constexpr uint32_t LC_NOID = 0xFFFFFFFFu;
-constexpr uint32_t LC_CNT_MASK = 0x00FFFFFFu;   // count field of a slot's count word; byte 3 = claim tag
+constexpr uint32_t LC_CNT_MASK = 0x00FFFFFFu;   // count field of a count word; byte 3 = claim tag
                                                 // (count == LC_CNT_MASK: the warp has not met this id yet)
-constexpr int LC_GMAX_NARROW = 1024;   // sum / mean(float) / count / first / last : 16 B per id per warp
-constexpr int LC_GMAX_WIDE_F = 640;    // + min / max                              : 32 B
-constexpr int LC_GMAX_WIDE_I = 512;    // + double sum (mean of integers)          : 40 B
+constexpr int LC_GMAX_NARROW = 1024;   // sum / mean(float) / count / first    : 12 B per id per warp, 12 warps
+constexpr int LC_GMAX_WIDE_F = 640;    // + min / max / last                   : 32 B per id per warp, 8 warps
+constexpr int LC_GMAX_WIDE_I = 512;    // + double sum (mean of integers)      : 40 B
 constexpr int LC_GMAX_MAX = LC_GMAX_NARROW;
 
 // global key -> id directory (hash mode)
@@ -64,6 +66,8 @@ constexpr int LC_PREP_GRID = 64;       // x 256 threads = 16384 sampled keys
 template <int VC, bool WIDE>
 struct LcCfg {
   static constexpr bool DSUM = WIDE && VC != VC_F;
+  static constexpr int WARPS = WIDE ? 8 : 12;
+  static constexpr int THREADS = WARPS * 32;
   static constexpr int GMAX = WIDE ? (DSUM ? LC_GMAX_WIDE_I : LC_GMAX_WIDE_F) : LC_GMAX_NARROW;
   static constexpr int GP = GMAX + 2;             // + null-key group + (key == kEmptyKey) group
   static constexpr int ID_NULL = GMAX;
@@ -119,31 +123,34 @@ struct LcArgs {
   uint32_t* status;
 };
 
+// Shared-memory layout.  Per warp: [minmax 16 B x GP (wide)] [sum 8 B x GP] [dsum 8 B x GP (ints, wide)]
+// [count word 4 B x GP] [last row 4 B x GP (wide)].
 template <int VC, bool WIDE>
 struct LcSmem {
   using Cfg = LcCfg<VC, WIDE>;
+  static constexpr size_t GP = Cfg::GP;
   static constexpr size_t OFF_MISC = 0;                                          // 4 x u32
   static constexpr size_t OFF_TKEYS = 16;                                        // LC_TCAP u64
   static constexpr size_t OFF_TIDS = OFF_TKEYS + LC_TCAP * 8;                    // LC_TCAP u16
   static constexpr size_t OFF_FIRST = OFF_TIDS + LC_TCAP * 2;                    // GP u32 (CTA shared)
-  static constexpr size_t OFF_ACC = OFF_FIRST + ((Cfg::GP * 4 + 15) / 16) * 16;
-  static constexpr size_t A_BYTES = static_cast<size_t>(Cfg::GP) * 16;           // {sum, count|tag, last}
-  static constexpr size_t B_BYTES = WIDE ? static_cast<size_t>(Cfg::GP) * 16 : 0;        // {min, max}
-  static constexpr size_t C_BYTES = Cfg::DSUM ? ((static_cast<size_t>(Cfg::GP) * 8 + 15) / 16) * 16 : 0;   // dsum
-  static constexpr size_t ACC_PER_WARP = A_BYTES + B_BYTES + C_BYTES;
-  static constexpr size_t TOTAL = OFF_ACC + ACC_PER_WARP * LC_WARPS;
+  static constexpr size_t OFF_ACC = OFF_FIRST + ((GP * 4 + 15) / 16) * 16;
+  static constexpr size_t W_MM = 0;
+  static constexpr size_t W_SUM = W_MM + (WIDE ? GP * 16 : 0);
+  static constexpr size_t W_DSUM = W_SUM + GP * 8;
+  static constexpr size_t W_CW = W_DSUM + (Cfg::DSUM ? GP * 8 : 0);
+  static constexpr size_t W_LAST = W_CW + GP * 4;
+  static constexpr size_t ACC_PER_WARP = ((W_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;
+  static constexpr size_t TOTAL = OFF_ACC + ACC_PER_WARP * Cfg::WARPS;
 };
 
-// per-thread view of the CTA's shared state
+// per-thread view of the CTA's shared state (32-bit shared-memory addresses for the hot arrays)
 struct LcCtx {
-  uint32_t accA;                 // this warp's slots (32-bit shared-memory addresses)
-  uint32_t accB;
-  double* accC;
+  uint32_t sum, cw, last, mm, dsum;   // this warp's accumulator arrays
   unsigned long long* tkeys;
   uint16_t* tids;
   uint32_t* cta_first;
-  uint32_t* misc;                // [0] unused, [1] abort seen by this CTA
-  uint64_t base;                 // dense mode
+  uint32_t* misc;                     // [1] abort seen by this CTA
+  uint64_t base;                      // dense mode
 };
 
 __device__ __forceinline__ uint32_t lc_bucket(uint64_t key) {
@@ -191,9 +198,9 @@ __device__ __noinline__ uint32_t lc_global_id(uint64_t key, LcDir d, uint32_t gm
   return LC_NOID;
 }
 
-// Hash-mode slow path: insertion on first sight, keys displaced from their home bucket.  Per-lane
-// (divergent) code, kept out of line.  LC_NOID on overflow.
-__device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
+// Hash-mode miss path (out of line, per-lane divergent code): probes on from the home bucket,
+// inserts on first sight.  LC_NOID on overflow.
+__device__ __noinline__ uint32_t lc_miss_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
                                                  uint32_t* misc, LcDir d, uint32_t gmax, uint32_t* status) {
   uint32_t b = lc_bucket(key);
   for (int probe = 0; probe < 4 * LC_NBUCKET; ++probe) {
@@ -234,155 +241,194 @@ __device__ __noinline__ uint32_t lc_slow_resolve(uint64_t key, unsigned long lon
   return LC_NOID;
 }
 
+// What one lane (later: one group) adds to the accumulators.
+template <bool WIDE>
+struct LcContrib {
+  uint64_t sum;      // double bits (VC_F) or wrapping integer
+  uint32_t cnt;
+  uint32_t lo, hi;   // lowest / highest lane of the group
+  uint32_t doer;     // this lane performs the read-modify-write
+};
+template <>
+struct LcContrib<true> {
+  uint64_t sum;
+  uint32_t cnt;
+  uint32_t lo, hi;
+  uint32_t doer;
+  double dsum;
+  uint64_t mn, mx;
+};
+
+template <int VC, bool WIDE>
+__device__ __forceinline__ void lc_add(LcContrib<WIDE>& t, const LcContrib<WIDE>& x) {
+  if constexpr (VC == VC_F) {
+    t.sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(t.sum)) +
+                                                       __longlong_as_double(static_cast<long long>(x.sum))));
+  } else {
+    t.sum += x.sum;
+  }
+  t.cnt += x.cnt;
+  if constexpr (WIDE) {
+    if constexpr (VC != VC_F) t.dsum += x.dsum;
+    t.mn = x.mn < t.mn ? x.mn : t.mn;
+    t.mx = x.mx > t.mx ? x.mx : t.mx;
+  }
+}
+
+template <int VC, bool WIDE>
+__device__ __forceinline__ LcContrib<WIDE> lc_shfl(const LcContrib<WIDE>& k, int src) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  LcContrib<WIDE> o = k;
+  o.sum = __shfl_sync(FULL, k.sum, src);
+  o.cnt = __shfl_sync(FULL, k.cnt, src);
+  if constexpr (WIDE) {
+    if constexpr (VC != VC_F) o.dsum = __shfl_sync(FULL, k.dsum, src);
+    o.mn = __shfl_sync(FULL, k.mn, src);
+    o.mx = __shfl_sync(FULL, k.mx, src);
+  }
+  return o;
+}
+
+// Two or more losing lanes in the batch: fold every group in ascending lane (= row) order, so that
+// the result does not depend on which lanes the hardware let win.  Out of line (rare for ~1000
+// groups; for a handful of groups nearly every batch comes here and MATCH.ANY is cheap).
+template <int VC, bool WIDE>
+__device__ __noinline__ LcContrib<WIDE> lc_fold_general(LcContrib<WIDE> k, uint32_t id, uint32_t tag, uint32_t live,
+                                                        uint32_t losers) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = lane_id();
+  const bool winner = live && tag == lane;
+  if (__popc(losers) <= 4) {
+    // few duplicates: one warp-uniform iteration per loser lane, ascending; the winner inserts its
+    // own value at its own lane position
+    LcContrib<WIDE> f = k;
+    f.sum = 0; f.cnt = 0;
+    if constexpr (WIDE) { f.dsum = 0.0; f.mn = kMinInit; f.mx = kMaxInit; }
+    bool own_added = false;
+    uint32_t rem = losers;
+    while (rem) {
+      const int L = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const uint32_t tw = __shfl_sync(FULL, tag, L);
+      const LcContrib<WIDE> o = lc_shfl<VC, WIDE>(k, L);
+      if (winner && tw == lane) {
+        if (!own_added && static_cast<uint32_t>(L) > lane) {
+          lc_add<VC, WIDE>(f, k);
+          own_added = true;
+        }
+        lc_add<VC, WIDE>(f, o);
+        f.lo = static_cast<uint32_t>(L) < f.lo ? static_cast<uint32_t>(L) : f.lo;
+        f.hi = static_cast<uint32_t>(L) > f.hi ? static_cast<uint32_t>(L) : f.hi;
+      }
+    }
+    if (winner) {
+      if (!own_added) lc_add<VC, WIDE>(f, k);
+      k = f;
+    }
+    k.doer = winner;
+  } else {
+    // many duplicates = few distinct ids: the lowest lane of every group pulls its peers in
+    // ascending lane order and does the read-modify-write
+    const uint32_t peers = __match_any_sync(FULL, live ? id : LC_NOID);
+    const uint32_t lanebit = 1u << lane;
+    const bool leader = (peers & (lanebit - 1u)) == 0;
+    uint32_t rem = leader ? (peers & ~lanebit) : 0u;
+    while (__any_sync(FULL, rem != 0)) {
+      const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
+      const LcContrib<WIDE> o = lc_shfl<VC, WIDE>(k, src);
+      if (rem) {
+        lc_add<VC, WIDE>(k, o);
+        rem &= rem - 1;
+      }
+    }
+    k.doer = live && leader;
+    k.lo = lane;
+    k.hi = 31 - __clz(peers);
+  }
+  return k;
+}
+
 // Accumulate one 32-row batch whose ids are known.  Warp-synchronous; lane L holds row `row`
-// (= batch row base + L).
-//
-// Duplicate ids inside the batch are found without MATCH.ANY (whose latency grows with the number
-// of distinct values, ~360 cycles at 32): every lane stores its lane number into the top byte of
-// its slot's count word, then loads the slot back — one lane per group reads its own number (the
-// "winner"), the others learn who won.  Winners then fold the losers' contributions in ascending
-// lane order (their own value at its own lane position, so the result does not depend on which
-// lane the hardware let win), and do one non-atomic read-modify-write of the 16-byte slot.
-// ALLLIVE: every lane holds a row with a resolved id (no tail, no overflowed lanes).
-template <int VC, bool WIDE, bool ALLLIVE>
+// (= batch row base + L).  CLEAN: every lane holds a row with a resolved id and a valid value.
+template <int VC, bool WIDE, bool CLEAN>
 __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row, const LcCtx& c) {
   using Cfg = LcCfg<VC, WIDE>;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = lane_id();
-  const bool live = ALLLIVE ? true : id != LC_NOID;
-  const uint32_t slot = c.accA + (live ? id : 0u) * 16u;
-  if (live) sts8(slot + 11u, lane);
+  const bool live = CLEAN ? true : id != LC_NOID;
+  const uint32_t ida = live ? id : 0u;
+  const uint32_t cw_addr = c.cw + ida * 4u, sum_addr = c.sum + ida * 8u;
+  if (live) sts8(cw_addr + 3u, lane);
   __syncwarp();
-  const uint4 w = lds128(slot);
-  const uint32_t tag = w.z >> 24;
+  const uint32_t cw = lds32(cw_addr);
+  uint64_t s = lds64(sum_addr);
+  const uint32_t tag = cw >> 24;
   const bool winner = live && (tag == lane);
   const uint32_t losers = __ballot_sync(FULL, live && !winner);
-  uint64_t c_sum = 0;           // double bits (VC_F, +0.0) or wrapping integer
-  uint32_t c_cnt = 0;
-  double c_dsum = 0.0;
-  uint64_t c_min = kMinInit, c_max = kMaxInit;
-  if (vvalid) {
-    c_sum = vbits;
-    c_cnt = 1;
-    if constexpr (WIDE) {
-      if constexpr (Cfg::DSUM) c_dsum = Wide<VC>::as_double(vbits);
-      if (!Wide<VC>::is_nan(vbits)) { c_min = Wide<VC>::ord(vbits); c_max = c_min; }
+  LcContrib<WIDE> k;
+  const bool vv = CLEAN ? true : vvalid;
+  k.sum = vv ? vbits : 0ull;
+  k.cnt = vv ? 1u : 0u;
+  k.lo = lane;
+  k.hi = lane;
+  k.doer = winner;
+  if constexpr (WIDE) {
+    k.dsum = 0.0;
+    k.mn = kMinInit;
+    k.mx = kMaxInit;
+    if (vv) {
+      if constexpr (Cfg::DSUM) k.dsum = Wide<VC>::as_double(vbits);
+      if (!Wide<VC>::is_nan(vbits)) { k.mn = Wide<VC>::ord(vbits); k.mx = k.mn; }
     }
   }
-  uint32_t lo_lane = lane, hi_lane = lane;   // lowest / highest lane of my group (meaningful for the doer)
-  bool doer = winner;                        // the lane that performs the read-modify-write
   if (losers) {
-    auto add_to = [&](uint64_t& t_sum, uint32_t& t_cnt, double& t_dsum, uint64_t& t_min, uint64_t& t_max,
-                      uint64_t x_sum, uint32_t x_cnt, double x_dsum, uint64_t x_min, uint64_t x_max) {
-      if constexpr (VC == VC_F) {
-        t_sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(t_sum)) +
-                                                           __longlong_as_double(static_cast<long long>(x_sum))));
-      } else {
-        t_sum += x_sum;
-      }
-      t_cnt += x_cnt;
-      if constexpr (WIDE) {
-        if constexpr (Cfg::DSUM) t_dsum += x_dsum;
-        t_min = x_min < t_min ? x_min : t_min;
-        t_max = x_max > t_max ? x_max : t_max;
-      }
-    };
-    if (__popc(losers) <= 4) {
-      // few duplicates: one warp-uniform iteration per loser lane, ascending
-      uint64_t f_sum = 0;
-      uint32_t f_cnt = 0;
-      double f_dsum = 0.0;
-      uint64_t f_min = kMinInit, f_max = kMaxInit;
-      bool own_added = false;
-      uint32_t rem = losers;
-      while (rem) {
-        const int L = __ffs(rem) - 1;
-        rem &= rem - 1;
-        const uint32_t tw = __shfl_sync(FULL, tag, L);
-        const uint64_t o_sum = __shfl_sync(FULL, c_sum, L);
-        const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, L);
-        double o_dsum = 0.0;
-        uint64_t o_min = kMinInit, o_max = kMaxInit;
-        if constexpr (WIDE) {
-          if constexpr (Cfg::DSUM) o_dsum = __shfl_sync(FULL, c_dsum, L);
-          o_min = __shfl_sync(FULL, c_min, L);
-          o_max = __shfl_sync(FULL, c_max, L);
-        }
-        if (winner && tw == lane) {
-          if (!own_added && static_cast<uint32_t>(L) > lane) {
-            add_to(f_sum, f_cnt, f_dsum, f_min, f_max, c_sum, c_cnt, c_dsum, c_min, c_max);
-            own_added = true;
-          }
-          add_to(f_sum, f_cnt, f_dsum, f_min, f_max, o_sum, o_cnt, o_dsum, o_min, o_max);
-          lo_lane = static_cast<uint32_t>(L) < lo_lane ? static_cast<uint32_t>(L) : lo_lane;
-          hi_lane = static_cast<uint32_t>(L) > hi_lane ? static_cast<uint32_t>(L) : hi_lane;
-        }
-      }
-      if (winner) {
-        if (!own_added) add_to(f_sum, f_cnt, f_dsum, f_min, f_max, c_sum, c_cnt, c_dsum, c_min, c_max);
-        c_sum = f_sum; c_cnt = f_cnt; c_dsum = f_dsum; c_min = f_min; c_max = f_max;
+    if ((losers & (losers - 1u)) == 0u) {
+      // exactly one losing lane: its group has two members, a + b is commutative
+      const int L = __ffs(losers) - 1;
+      const uint32_t tw = __shfl_sync(FULL, tag, L);
+      const LcContrib<WIDE> o = lc_shfl<VC, WIDE>(k, L);
+      if (lane == tw) {
+        lc_add<VC, WIDE>(k, o);
+        k.lo = static_cast<uint32_t>(L) < lane ? static_cast<uint32_t>(L) : lane;
+        k.hi = static_cast<uint32_t>(L) > lane ? static_cast<uint32_t>(L) : lane;
       }
     } else {
-      // many duplicates = few distinct ids, where MATCH.ANY is cheap: the lowest lane of every group
-      // pulls its peers in ascending lane order and does the read-modify-write
-      const uint32_t peers = __match_any_sync(FULL, id);
-      const uint32_t lanebit = 1u << lane;
-      const bool leader = (peers & (lanebit - 1u)) == 0;
-      uint32_t rem = leader ? (peers & ~lanebit) : 0u;
-      while (__any_sync(FULL, rem != 0)) {
-        const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
-        const uint64_t o_sum = __shfl_sync(FULL, c_sum, src);
-        const uint32_t o_cnt = __shfl_sync(FULL, c_cnt, src);
-        double o_dsum = 0.0;
-        uint64_t o_min = kMinInit, o_max = kMaxInit;
-        if constexpr (WIDE) {
-          if constexpr (Cfg::DSUM) o_dsum = __shfl_sync(FULL, c_dsum, src);
-          o_min = __shfl_sync(FULL, c_min, src);
-          o_max = __shfl_sync(FULL, c_max, src);
-        }
-        if (rem) {
-          add_to(c_sum, c_cnt, c_dsum, c_min, c_max, o_sum, o_cnt, o_dsum, o_min, o_max);
-          rem &= rem - 1;
-        }
-      }
-      doer = live && leader;
-      lo_lane = lane;
-      hi_lane = 31 - __clz(peers);
+      k = lc_fold_general<VC, WIDE>(k, id, tag, live, losers);
     }
   }
   // one non-atomic read-modify-write per distinct id
-  if (doer) {
-    uint32_t old = w.z & LC_CNT_MASK;
-    if (old == LC_CNT_MASK) {  // first time this warp meets the id: candidate for the CTA's first row
-      old = 0;
-      atomicMin(c.cta_first + id, row + lo_lane - lane);
-    }
-    uint64_t s = static_cast<uint64_t>(w.x) | (static_cast<uint64_t>(w.y) << 32);
+  if (k.doer) {
+    const uint32_t old = cw & LC_CNT_MASK;
+    const bool first_seen = old == LC_CNT_MASK;   // first time this warp meets the id
     if constexpr (VC == VC_F) {
       s = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(s)) +
-                                                     __longlong_as_double(static_cast<long long>(c_sum))));
+                                                     __longlong_as_double(static_cast<long long>(k.sum))));
     } else {
-      s += c_sum;
+      s += k.sum;
     }
-    // (the store also clears the claim tag)
-    sts128(slot, static_cast<uint32_t>(s), static_cast<uint32_t>(s >> 32), old + c_cnt, row + hi_lane - lane);
+    sts64(sum_addr, s);
+    sts32(cw_addr, (first_seen ? 0u : old) + k.cnt);   // also clears the claim tag
     if constexpr (WIDE) {
-      const uint32_t mslot = c.accB + id * 16u;
+      sts32(c.last + id * 4u, row + k.hi - lane);
+      const uint32_t mslot = c.mm + id * 16u;
       const uint4 m4 = lds128(mslot);
       const uint64_t mn = static_cast<uint64_t>(m4.x) | (static_cast<uint64_t>(m4.y) << 32);
       const uint64_t mx = static_cast<uint64_t>(m4.z) | (static_cast<uint64_t>(m4.w) << 32);
-      if (c_min < mn || c_max > mx) {
-        const uint64_t nn = c_min < mn ? c_min : mn, nx = c_max > mx ? c_max : mx;
+      if (k.mn < mn || k.mx > mx) {
+        const uint64_t nn = k.mn < mn ? k.mn : mn, nx = k.mx > mx ? k.mx : mx;
         sts128(mslot, static_cast<uint32_t>(nn), static_cast<uint32_t>(nn >> 32), static_cast<uint32_t>(nx), static_cast<uint32_t>(nx >> 32));
       }
-      if constexpr (Cfg::DSUM) c.accC[id] += c_dsum;
+      if constexpr (Cfg::DSUM) {
+        const uint32_t da = c.dsum + id * 8u;
+        sts64(da, static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(lds64(da))) + k.dsum)));
+      }
     }
+    if (first_seen) atomicMin(c.cta_first + id, row + k.lo - lane);   // candidate for the CTA's first row
   }
   __syncwarp();
 }
 
-// One row group in registers: LC_NB = 2 * LC_STEPS batches of 32 rows, entry e = row g0 + 32 e + lane.
-constexpr int LC_NB = 2 * LC_STEPS;
+// One row group in registers: LC_NB batches of 32 rows, entry e = row g0 + 32 e + lane.
 struct LcBuf {
   uint64_t key[LC_NB];
   uint64_t val[LC_NB];
@@ -397,20 +443,15 @@ __device__ __forceinline__ uint64_t ldg_stream_u64(const void* p) {
 
 // FAST loader: 8-byte keys and values, every row exists, no bitmaps.  Each load instruction reads
 // 256 contiguous bytes per warp.
-__device__ __forceinline__ void lc_load_fast(LcBuf& b, const LcArgs& a, int64_t g0, uint32_t lane, bool have_vals) {
+__device__ __forceinline__ void lc_load_fast(LcBuf& b, const LcArgs& a, int64_t g0, uint32_t lane) {
   const char* kp = static_cast<const char*>(a.keys) + (g0 + lane) * 8;
   const char* vp = static_cast<const char*>(a.vals) + (g0 + lane) * 8;
 #pragma unroll
   for (int e = 0; e < LC_NB; ++e) b.key[e] = ldg_stream_u64(kp + e * 256);
-  if (have_vals) {
 #pragma unroll
-    for (int e = 0; e < LC_NB; ++e) b.val[e] = ldg_stream_u64(vp + e * 256);
-  } else {
-#pragma unroll
-    for (int e = 0; e < LC_NB; ++e) b.val[e] = 0;
-  }
+  for (int e = 0; e < LC_NB; ++e) b.val[e] = ldg_stream_u64(vp + e * 256);
   b.kv = 0xFFFFFFFFu;
-  b.vv = have_vals ? 0xFFFFFFFFu : 0u;
+  b.vv = 0xFFFFFFFFu;
   b.act = 0xFFFFFFFFu;
 }
 
@@ -442,10 +483,9 @@ __device__ __forceinline__ void lc_load_generic(LcBuf& b, const LcArgs& a, int64
 
 // Process one row group: resolve the ids of all LC_NB batches first (independent lookups in flight,
 // one vote for the rare paths), then accumulate batch by batch.  Returns false on abort.
-// CLEAN: every row exists, no validity bitmaps (value validity = have_vals).
+// CLEAN: every row exists, keys and values are all valid.
 template <int VC, bool WIDE, bool DENSE, bool CLEAN>
-__device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uint32_t lane, bool have_vals, const LcCtx& c,
-                                                 const LcArgs& a) {
+__device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uint32_t lane, const LcCtx& c, const LcArgs& a) {
   using Cfg = LcCfg<VC, WIDE>;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   uint32_t id[LC_NB];
@@ -481,38 +521,29 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
       if (!act) id[e] = LC_NOID;
       if (act && !special && id[e] >= LC_ID_OVF) missmask |= 1u << e;
     }
-    if (__any_sync(FULL, missmask != 0)) {   // keys displaced by one bucket: second inline probe, then the slow path
+    if (__any_sync(FULL, missmask != 0)) {   // displaced or new keys
 #pragma unroll
       for (int e = 0; e < LC_NB; ++e) {
-        if ((missmask >> e) & 1u) {
-          id[e] = lc_lookup(b.key[e], (lc_bucket(b.key[e]) + 1) & (LC_NBUCKET - 1), c.tkeys, c.tids);
-          if (id[e] < LC_ID_OVF) missmask &= ~(1u << e);
-        }
+        if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c.tkeys, c.tids, c.misc, a.dir, Cfg::GMAX, a.status);
       }
-      if (__any_sync(FULL, missmask != 0)) {
-#pragma unroll
-        for (int e = 0; e < LC_NB; ++e) {
-          if ((missmask >> e) & 1u) id[e] = lc_slow_resolve(b.key[e], c.tkeys, c.tids, c.misc, a.dir, Cfg::GMAX, a.status);
-          __syncwarp();
-        }
-      }
+      __syncwarp();
     }
   }
 #pragma unroll
   for (int e = 0; e < LC_NB; ++e) {
     const uint32_t row = static_cast<uint32_t>(g0) + e * 32 + lane;
-    const bool vvalid = CLEAN ? have_vals : ((b.vv >> e) & 1u) != 0;
-    constexpr bool ALLLIVE = CLEAN && DENSE;
-    lc_accumulate<VC, WIDE, ALLLIVE>(id[e], b.val[e], vvalid && (ALLLIVE || id[e] != LC_NOID), row, c);
+    constexpr bool ACLEAN = CLEAN && DENSE;   // (hash mode may leave LC_NOID in a lane after an overflow)
+    const bool vvalid = CLEAN ? true : ((b.vv >> e) & 1u) != 0;
+    lc_accumulate<VC, WIDE, ACLEAN>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, c);
   }
   return true;
 }
 
 template <int VC, bool WIDE, bool FAST, bool DENSE>
 __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, int warp, uint32_t lane) {
-  const int64_t gw = static_cast<int64_t>(blockIdx.x) * LC_WARPS + warp;
-  const int64_t nw = static_cast<int64_t>(gridDim.x) * LC_WARPS;
-  const bool have_vals = a.vals != nullptr;
+  using Cfg = LcCfg<VC, WIDE>;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * Cfg::WARPS + warp;
+  const int64_t nw = static_cast<int64_t>(gridDim.x) * Cfg::WARPS;
   const int64_t n_full = a.n / LC_GROUP_ROWS;                        // full row groups
   const int64_t n_groups = (a.n + LC_GROUP_ROWS - 1) / LC_GROUP_ROWS;
   volatile uint32_t* abort_local = c.misc + 1;
@@ -520,12 +551,12 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
   if constexpr (FAST) {
     LcBuf cur, nxt;
     int64_t g = gw;
-    if (g < n_full) lc_load_fast(cur, a, g * LC_GROUP_ROWS, lane, have_vals);
+    if (g < n_full) lc_load_fast(cur, a, g * LC_GROUP_ROWS, lane);
     while (g < n_full) {
       const int64_t gn = g + nw;
-      if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane, have_vals);
+      if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane);
       const uint32_t gabort = *abort_global;
-      if (!lc_process_group<VC, WIDE, DENSE, true>(cur, g * LC_GROUP_ROWS, lane, have_vals, c, a)) return;
+      if (!lc_process_group<VC, WIDE, DENSE, true>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
       if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
       cur = nxt;
       g = gn;
@@ -534,7 +565,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
     if (n_groups > n_full && gw == (n_full % nw)) {
       LcBuf t;
       lc_load_generic<VC>(t, a, n_full * LC_GROUP_ROWS, lane);
-      lc_process_group<VC, WIDE, DENSE, false>(t, n_full * LC_GROUP_ROWS, lane, have_vals, c, a);
+      lc_process_group<VC, WIDE, DENSE, false>(t, n_full * LC_GROUP_ROWS, lane, c, a);
     }
   } else {
     LcBuf cur, nxt;
@@ -544,7 +575,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
       const int64_t gn = g + nw;
       if (gn < n_groups) lc_load_generic<VC>(nxt, a, gn * LC_GROUP_ROWS, lane);
       const uint32_t gabort = *abort_global;
-      if (!lc_process_group<VC, WIDE, DENSE, false>(cur, g * LC_GROUP_ROWS, lane, have_vals, c, a)) return;
+      if (!lc_process_group<VC, WIDE, DENSE, false>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
       if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
       cur = nxt;
       g = gn;
@@ -552,9 +583,9 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
   }
 }
 
-// FAST: int64/uint64 keys and 8-byte values (or none), no validity bitmaps, 16-byte aligned columns.
+// FAST: int64/uint64 keys and 8-byte values, no validity bitmaps, 8-byte aligned columns.
 template <int VC, bool WIDE, bool FAST>
-__global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
+__global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(LcArgs a) {
   using Cfg = LcCfg<VC, WIDE>;
   using L = LcSmem<VC, WIDE>;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -566,24 +597,31 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
   c.tids = reinterpret_cast<uint16_t*>(smem + L::OFF_TIDS);
   c.cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
   unsigned char* my_acc = smem + L::OFF_ACC + L::ACC_PER_WARP * warp;
-  c.accA = smem_u32(my_acc);
-  c.accB = c.accA + static_cast<uint32_t>(L::A_BYTES);
-  c.accC = reinterpret_cast<double*>(my_acc + L::A_BYTES + L::B_BYTES);
+  const uint32_t acc_s = smem_u32(my_acc);
+  c.mm = acc_s + static_cast<uint32_t>(L::W_MM);
+  c.sum = acc_s + static_cast<uint32_t>(L::W_SUM);
+  c.dsum = acc_s + static_cast<uint32_t>(L::W_DSUM);
+  c.cw = acc_s + static_cast<uint32_t>(L::W_CW);
+  c.last = acc_s + static_cast<uint32_t>(L::W_LAST);
   const bool dense = lc_dense_mode(a.dir.prep, a.force_hash, Cfg::GMAX, &c.base);
 
   // ---- init shared state ----
   if (!dense) {
-    for (int i = threadIdx.x; i < LC_TCAP; i += LC_THREADS) {
+    for (int i = threadIdx.x; i < LC_TCAP; i += Cfg::THREADS) {
       c.tkeys[i] = kEmptyKey;
       c.tids[i] = LC_ID_UNSET;
     }
   }
-  for (int i = threadIdx.x; i < Cfg::GP; i += LC_THREADS) c.cta_first[i] = kNoRow;
+  for (int i = threadIdx.x; i < Cfg::GP; i += Cfg::THREADS) c.cta_first[i] = kNoRow;
   if (threadIdx.x < 4) c.misc[threadIdx.x] = 0;
   for (int i = lane; i < Cfg::GP; i += 32) {
-    reinterpret_cast<uint4*>(my_acc)[i] = make_uint4(0u, 0u, LC_CNT_MASK, 0u);
-    if constexpr (WIDE) reinterpret_cast<ulonglong2*>(my_acc + L::A_BYTES)[i] = make_ulonglong2(kMinInit, kMaxInit);
-    if constexpr (Cfg::DSUM) c.accC[i] = 0.0;
+    reinterpret_cast<uint64_t*>(my_acc + L::W_SUM)[i] = 0ull;
+    reinterpret_cast<uint32_t*>(my_acc + L::W_CW)[i] = LC_CNT_MASK;
+    if constexpr (WIDE) {
+      reinterpret_cast<ulonglong2*>(my_acc + L::W_MM)[i] = make_ulonglong2(kMinInit, kMaxInit);
+      reinterpret_cast<uint32_t*>(my_acc + L::W_LAST)[i] = 0u;
+    }
+    if constexpr (Cfg::DSUM) reinterpret_cast<double*>(my_acc + L::W_DSUM)[i] = 0.0;
   }
   __syncthreads();
 
@@ -597,34 +635,34 @@ __global__ void __launch_bounds__(LC_THREADS, 1) k_lowcard_scan(LcArgs a) {
 
   // ---- fold the warps in warp order and write this CTA's partial table ----
   const size_t pbase = static_cast<size_t>(blockIdx.x) * Cfg::GP;
-  for (int id = threadIdx.x; id < Cfg::GP; id += LC_THREADS) {
+  for (int id = threadIdx.x; id < Cfg::GP; id += Cfg::THREADS) {
     uint64_t sum = 0;
     double fsum = 0.0, dsum = 0.0;
     uint32_t cnt = 0, last = 0;
     uint64_t mn = kMinInit, mx = kMaxInit;
-    for (int w = 0; w < LC_WARPS; ++w) {
+    for (int w = 0; w < Cfg::WARPS; ++w) {
       const unsigned char* wa = smem + L::OFF_ACC + L::ACC_PER_WARP * w;
-      const uint4 sa = reinterpret_cast<const uint4*>(wa)[id];
-      const uint32_t cw = sa.z & LC_CNT_MASK;
+      const uint32_t cw = reinterpret_cast<const uint32_t*>(wa + L::W_CW)[id] & LC_CNT_MASK;
       if (cw == LC_CNT_MASK) continue;
       cnt += cw;
-      const uint64_t s = static_cast<uint64_t>(sa.x) | (static_cast<uint64_t>(sa.y) << 32);
+      const uint64_t s = reinterpret_cast<const uint64_t*>(wa + L::W_SUM)[id];
       if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(s));
       else sum += s;
-      last = sa.w > last ? sa.w : last;
       if constexpr (WIDE) {
-        const ulonglong2 mm = reinterpret_cast<const ulonglong2*>(wa + L::A_BYTES)[id];
+        const uint32_t l = reinterpret_cast<const uint32_t*>(wa + L::W_LAST)[id];
+        last = l > last ? l : last;
+        const ulonglong2 mm = reinterpret_cast<const ulonglong2*>(wa + L::W_MM)[id];
         mn = mm.x < mn ? mm.x : mn;
         mx = mm.y > mx ? mm.y : mx;
-        if constexpr (Cfg::DSUM) dsum += reinterpret_cast<const double*>(wa + L::A_BYTES + L::B_BYTES)[id];
+        if constexpr (Cfg::DSUM) dsum += reinterpret_cast<const double*>(wa + L::W_DSUM)[id];
       }
     }
     if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(fsum));
     a.p_sum[pbase + id] = sum;
     a.p_count[pbase + id] = cnt;
     a.p_first[pbase + id] = c.cta_first[id];
-    a.p_last[pbase + id] = last;
     if constexpr (WIDE) {
+      a.p_last[pbase + id] = last;
       a.p_min[pbase + id] = mn;
       a.p_max[pbase + id] = mx;
       if constexpr (Cfg::DSUM) a.p_dsum[pbase + id] = dsum;
@@ -702,9 +740,9 @@ __global__ void __launch_bounds__(256) k_lowcard_merge(LmArgs a) {
     cnt += a.part.p_count[p];
     if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(a.part.p_sum[p]));
     else sum += a.part.p_sum[p];
-    const uint32_t l = a.part.p_last[p];
-    last = l > last ? l : last;
     if constexpr (WIDE) {
+      const uint32_t l = a.part.p_last[p];
+      last = l > last ? l : last;
       const uint64_t pmn = a.part.p_min[p], pmx = a.part.p_max[p];
       mn = pmn < mn ? pmn : mn;
       mx = pmx > mx ? pmx : mx;
@@ -713,13 +751,14 @@ __global__ void __launch_bounds__(256) k_lowcard_merge(LmArgs a) {
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
-    const uint32_t of = __shfl_xor_sync(FULL, first, d), ol = __shfl_xor_sync(FULL, last, d);
+    const uint32_t of = __shfl_xor_sync(FULL, first, d);
     first = of < first ? of : first;
-    last = ol > last ? ol : last;
     cnt += __shfl_xor_sync(FULL, cnt, d);
     if constexpr (VC == VC_F) fsum += __shfl_xor_sync(FULL, fsum, d);
     else sum += __shfl_xor_sync(FULL, sum, d);
     if constexpr (WIDE) {
+      const uint32_t ol = __shfl_xor_sync(FULL, last, d);
+      last = ol > last ? ol : last;
       const uint64_t on = __shfl_xor_sync(FULL, mn, d), ox = __shfl_xor_sync(FULL, mx, d);
       mn = on < mn ? on : mn;
       mx = ox > mx ? ox : mx;
@@ -731,8 +770,8 @@ __global__ void __launch_bounds__(256) k_lowcard_merge(LmArgs a) {
     a.m_sum[id] = sum;
     a.m_count[id] = cnt;
     a.m_first[id] = first;
-    a.m_last[id] = last;
     if constexpr (WIDE) {
+      a.m_last[id] = last;
       a.m_min[id] = mn;
       a.m_max[id] = mx;
       if constexpr (Cfg::DSUM) a.m_dsum[id] = dsum;
@@ -747,12 +786,14 @@ template <int VC, bool WIDE>
 __global__ void __launch_bounds__(LR_THREADS, 1) k_lowcard_rank(LmArgs a) {
   using Cfg = LcCfg<VC, WIDE>;
   __shared__ uint32_t sfirst[Cfg::GP];
+  __shared__ uint32_t s_total;
   if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_ABORT)) return;
   uint64_t base;
   const bool dense = lc_dense_mode(a.part.dir.prep, a.part.force_hash, Cfg::GMAX, &base);
   for (int i = threadIdx.x; i < Cfg::GP; i += LR_THREADS) sfirst[i] = a.m_first[i];
+  if (threadIdx.x == 0) s_total = 0;
   __syncthreads();
-  int present = 0;
+  uint32_t present = 0;
   for (int id = threadIdx.x; id < Cfg::GP; id += LR_THREADS) {
     const uint32_t f = sfirst[id];
     if (f == kNoRow) continue;
@@ -768,17 +809,14 @@ __global__ void __launch_bounds__(LR_THREADS, 1) k_lowcard_rank(LmArgs a) {
     a.out.sum[rank] = a.m_sum[id];
     a.out.count[rank] = a.m_count[id];
     a.out.first_row[rank] = f;
-    a.out.last_row[rank] = a.m_last[id];
     if constexpr (WIDE) {
+      a.out.last_row[rank] = a.m_last[id];
       a.out.min_ord[rank] = a.m_min[id];
       a.out.max_ord[rank] = a.m_max[id];
       if constexpr (Cfg::DSUM) { if (a.out.dsum) a.out.dsum[rank] = a.m_dsum[id]; }
     }
   }
-  __shared__ uint32_t s_total;
-  if (threadIdx.x == 0) s_total = 0;
-  __syncthreads();
-  if (present) atomicAdd(&s_total, static_cast<uint32_t>(present));
+  if (present) atomicAdd(&s_total, present);
   __syncthreads();
   if (threadIdx.x == 0) a.status[ST_NGROUPS] = s_total;
 }
