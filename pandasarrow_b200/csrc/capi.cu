@@ -396,11 +396,15 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     a.n = g->n;
     a.table = table.p;
     a.cap_mask = cap - 1;
+    a.shift = 64 - __builtin_ctzll(cap);
     a.status = g->status.as<uint32_t>();
     a.agg_mask = mask;
     const int64_t ntiles = (g->n + 1023) / 1024;
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, grid_full)));
-    k_gtable_scan<VC, WIDE><<<grid, 256, 0, st>>>(a);
+    const bool fast = a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid && !a.vvalid &&
+                      reinterpret_cast<uintptr_t>(a.keys) % 16 == 0 && reinterpret_cast<uintptr_t>(a.vals) % 16 == 0;
+    if (fast) k_gtable_scan<VC, WIDE, true><<<grid, 256, 0, st>>>(a);
+    else k_gtable_scan<VC, WIDE, false><<<grid, 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     g->last_launches += 2;
     uint32_t h_status[ST_WORDS];

@@ -44,6 +44,7 @@ struct GScanArgs {
   int kw, vw;
   void* table;             // cap + 2 slots; [cap] = null-key group, [cap+1] = key == kEmptyKey group
   uint64_t cap_mask;       // cap - 1 (cap is a power of two)
+  int shift;               // 64 - log2(cap)
   uint32_t* status;
   uint32_t agg_mask;
 };
@@ -78,34 +79,43 @@ __device__ __forceinline__ uint64_t load_wide_rt(const void* p, int64_t i, int v
   }
 }
 
-// Find-or-insert `key`; returns the slot index or ~0 on overflow (probe budget exhausted).
-template <typename SlotT>
-__device__ __forceinline__ uint64_t gtable_find_or_insert(SlotT* table, uint64_t cap_mask, uint64_t key) {
-  uint64_t s = hash_key64(key) & cap_mask;
+// Slot of a key: Fibonacci hashing (one 64-bit multiply, top bits).
+__device__ __forceinline__ uint64_t gtable_home(uint64_t key, int shift) { return (key * 0x9E3779B97F4A7C15ull) >> shift; }
+
+struct GProbe {
+  uint64_t slot;    // ~0 = overflow
+  uint32_t first;   // first_row / last_row of the slot as seen by the probe (stale reads are safe:
+  uint32_t last;    // first_row only decreases, last_row only increases)
+};
+
+// One probe step: a single 16-byte L2 load returns the slot's key and its {first_row, last_row}.
+__device__ __forceinline__ ulonglong2 gtable_peek(const void* table, uint64_t slot, int slot_log2) {
+  return __ldcg(reinterpret_cast<const ulonglong2*>(static_cast<const char*>(table) + (slot << slot_log2)));
+}
+
+// Continue a probe sequence whose first load `kf` (slot `s`) is already in registers.
+__device__ __forceinline__ GProbe gtable_find_or_insert(void* table, uint64_t cap_mask, int slot_log2, uint64_t key,
+                                                        uint64_t s, ulonglong2 kf) {
   const uint32_t max_probe = cap_mask + 1 < 4096 ? static_cast<uint32_t>(cap_mask + 1) : 4096u;
   for (uint32_t probe = 0; probe < max_probe; ++probe) {
-    unsigned long long* kp = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(table + s));
-    uint64_t k = __ldcg(kp);
-    if (k == key) return s;
-    if (k == kEmptyKey) {
-      uint64_t old = atomicCAS(kp, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
-      if (old == kEmptyKey || old == key) return s;
+    if (kf.x == key) return GProbe{s, static_cast<uint32_t>(kf.y), static_cast<uint32_t>(kf.y >> 32)};
+    if (kf.x == kEmptyKey) {
+      unsigned long long* kp = reinterpret_cast<unsigned long long*>(static_cast<char*>(table) + (s << slot_log2));
+      const uint64_t old = atomicCAS(kp, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+      if (old == kEmptyKey || old == key) return GProbe{s, kNoRow, 0u};
     }
     s = (s + 1) & cap_mask;
+    kf = gtable_peek(table, s, slot_log2);
   }
-  return ~0ull;
+  return GProbe{~0ull, kNoRow, 0u};
 }
 
 template <int VC, bool WIDE>
-__device__ __forceinline__ void gtable_accumulate(typename SlotOf<WIDE>::type* slot, uint32_t row, bool vvalid,
-                                                  uint64_t vbits, uint32_t agg_mask) {
+__device__ __forceinline__ void gtable_accumulate(typename SlotOf<WIDE>::type* slot, const GProbe& pr, uint32_t row,
+                                                  bool vvalid, uint64_t vbits, uint32_t agg_mask) {
   Slot32* b = reinterpret_cast<Slot32*>(slot);
-  // first_row / last_row share one 8-byte word with a cheap pre-check (stale reads are safe:
-  // first_row only decreases, last_row only increases).
-  const uint64_t fl = __ldcg(reinterpret_cast<const unsigned long long*>(&b->first_row));
-  const uint32_t f = static_cast<uint32_t>(fl), l = static_cast<uint32_t>(fl >> 32);
-  if (row < f) atomicMin(&b->first_row, row);
-  if ((agg_mask & AGG_LAST) && row > l) atomicMax(&b->last_row, row);
+  if (row < pr.first) atomicMin(&b->first_row, row);
+  if ((agg_mask & AGG_LAST) && row > pr.last) atomicMax(&b->last_row, row);
   if (!vvalid) return;
   atomicAdd(&b->count, 1u);
   if constexpr (VC == VC_F) {
@@ -127,11 +137,17 @@ __device__ __forceinline__ void gtable_accumulate(typename SlotOf<WIDE>::type* s
   }
 }
 
-// One thread per row, 4 rows per thread per tile so that four independent key/value loads are in
-// flight before the dependent probe chain starts.  Grid: multiple of the SM count (host side).
-template <int VC, bool WIDE>
-__global__ void __launch_bounds__(256) k_gtable_scan(GScanArgs a) {
+// One thread per row, R rows per thread per tile: all key / value loads of the tile are issued
+// first, then the R first-probe loads (one 16-byte L2 transaction each), and only then the
+// dependent work, so R independent L2 round trips are in flight per thread.  Per row in steady
+// state: one L2 load + two L2 reductions (RED.ADD.F64 sum, RED.ADD.U32 count); first/last/min/max
+// are pre-checked against the loaded slot and only rarely issue an atomic.
+// FAST: 8-byte keys and values, no validity bitmaps; thread t of a tile takes the adjacent rows
+// 2t, 2t+1 (128-bit loads) — row order is irrelevant here, first/last rows are atomicMin/Max.
+template <int VC, bool WIDE, bool FAST>
+__global__ void __launch_bounds__(256, 4) k_gtable_scan(GScanArgs a) {
   using SlotT = typename SlotOf<WIDE>::type;
+  constexpr int SLOT_LOG2 = WIDE ? 6 : 5;
   SlotT* table = static_cast<SlotT*>(a.table);
   const uint64_t cap = a.cap_mask + 1;
   constexpr int R = 4;
@@ -139,35 +155,59 @@ __global__ void __launch_bounds__(256) k_gtable_scan(GScanArgs a) {
   const int64_t ntiles = (a.n + tile_rows - 1) / tile_rows;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) return;
-    const int64_t base = t * tile_rows + threadIdx.x;
+    const int64_t tile0 = t * tile_rows;
     uint64_t key[R], vb[R];
+    int64_t row[R];
     bool act[R], kv[R], vv[R];
+    if (FAST && tile0 + tile_rows <= a.n) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int64_t i = base + static_cast<int64_t>(j) * blockDim.x;
-      act[j] = i < a.n;
-      key[j] = 0; vb[j] = 0; kv[j] = true; vv[j] = false;
-      if (act[j]) {
-        key[j] = load_key_rt(a.keys, i, a.kw);
-        if (a.kvalid) kv[j] = bit_at(a.kvalid, a.koff + i);
-        if (a.vals) {
-          vb[j] = load_wide_rt<VC>(a.vals, i, a.vw);
-          vv[j] = a.vvalid ? bit_at(a.vvalid, a.voff + i) : true;
+      for (int h = 0; h < R / 2; ++h) {
+        const int64_t r0 = tile0 + static_cast<int64_t>(h) * blockDim.x * 2 + 2 * threadIdx.x;
+        const ulonglong2 k2 = ldg_stream_u64x2(static_cast<const uint64_t*>(a.keys) + r0);
+        ulonglong2 v2 = make_ulonglong2(0ull, 0ull);
+        if (a.vals) v2 = ldg_stream_u64x2(static_cast<const uint64_t*>(a.vals) + r0);
+        key[2 * h] = k2.x; key[2 * h + 1] = k2.y;
+        vb[2 * h] = v2.x; vb[2 * h + 1] = v2.y;
+        row[2 * h] = r0; row[2 * h + 1] = r0 + 1;
+        act[2 * h] = act[2 * h + 1] = true;
+        kv[2 * h] = kv[2 * h + 1] = true;
+        vv[2 * h] = vv[2 * h + 1] = a.vals != nullptr;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int64_t i = tile0 + threadIdx.x + static_cast<int64_t>(j) * blockDim.x;
+        row[j] = i;
+        act[j] = i < a.n;
+        key[j] = 0; vb[j] = 0; kv[j] = true; vv[j] = false;
+        if (act[j]) {
+          key[j] = load_key_rt(a.keys, i, a.kw);
+          if (a.kvalid) kv[j] = bit_at(a.kvalid, a.koff + i);
+          if (a.vals) {
+            vb[j] = load_wide_rt<VC>(a.vals, i, a.vw);
+            vv[j] = a.vvalid ? bit_at(a.vvalid, a.voff + i) : true;
+          }
         }
       }
+    }
+    uint64_t s[R];
+    ulonglong2 kf[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      s[j] = gtable_home(key[j], a.shift);
+      if (!kv[j]) s[j] = cap;
+      else if (key[j] == kEmptyKey) s[j] = cap + 1;
+      kf[j] = make_ulonglong2(0ull, 0ull);
+      if (act[j]) kf[j] = gtable_peek(table, s[j], SLOT_LOG2);
     }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       if (!act[j]) continue;
-      const int64_t i = base + static_cast<int64_t>(j) * blockDim.x;
-      uint64_t s;
-      if (!kv[j]) s = cap;
-      else if (key[j] == kEmptyKey) s = cap + 1;
-      else {
-        s = gtable_find_or_insert(table, a.cap_mask, key[j]);
-        if (s == ~0ull) { atomicExch(a.status + ST_OVERFLOW, 1u); return; }
-      }
-      gtable_accumulate<VC, WIDE>(table + s, static_cast<uint32_t>(i), vv[j], vb[j], a.agg_mask);
+      GProbe pr;
+      if (s[j] >= cap) pr = GProbe{s[j], static_cast<uint32_t>(kf[j].y), static_cast<uint32_t>(kf[j].y >> 32)};
+      else pr = gtable_find_or_insert(table, a.cap_mask, SLOT_LOG2, key[j], s[j], kf[j]);
+      if (pr.slot == ~0ull) { atomicExch(a.status + ST_OVERFLOW, 1u); return; }
+      gtable_accumulate<VC, WIDE>(table + pr.slot, pr, static_cast<uint32_t>(row[j]), vv[j], vb[j], a.agg_mask);
     }
   }
 }

@@ -521,12 +521,26 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
       if (!act) id[e] = LC_NOID;
       if (act && !special && id[e] >= LC_ID_OVF) missmask |= 1u << e;
     }
-    if (__any_sync(FULL, missmask != 0)) {   // displaced or new keys
+    if (__any_sync(FULL, missmask != 0)) {
+      // keys displaced from a full home bucket (a fixed ~1.5 % of the keys at 1000 groups): one
+      // more inline probe of the neighbouring bucket, per batch and only for the lanes that missed
 #pragma unroll
       for (int e = 0; e < LC_NB; ++e) {
-        if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c.tkeys, c.tids, c.misc, a.dir, Cfg::GMAX, a.status);
+        const bool m = (missmask >> e) & 1u;
+        if (__any_sync(FULL, m)) {
+          if (m) {
+            const uint32_t id2 = lc_lookup(b.key[e], (lc_bucket(b.key[e]) + 1) & (LC_NBUCKET - 1), c.tkeys, c.tids);
+            if (id2 < LC_ID_OVF) { id[e] = id2; missmask &= ~(1u << e); }
+          }
+        }
       }
-      __syncwarp();
+      if (__any_sync(FULL, missmask != 0)) {   // new keys (start of the pass) or longer probe chains
+#pragma unroll
+        for (int e = 0; e < LC_NB; ++e) {
+          if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c.tkeys, c.tids, c.misc, a.dir, Cfg::GMAX, a.status);
+        }
+        __syncwarp();
+      }
     }
   }
 #pragma unroll
