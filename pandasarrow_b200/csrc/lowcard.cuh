@@ -90,15 +90,33 @@ struct LcDir {                   // global-memory directory (hash mode ids) + ke
   unsigned long long* key_by_id; // [LC_GMAX_MAX]
 };
 
-// dense-mode decision; identical in every kernel that needs it
-__device__ __forceinline__ bool lc_dense_mode(const LcPrep* p, int force_hash, uint32_t gmax, uint64_t* base) {
+// Dense-mode decision; identical in every kernel that needs it.  `window` = number of key values
+// the id space covers, `rlog` = log2 of the accumulator replication: when the sampled key range is
+// much smaller than GMAX, every id gets 2^rlog accumulator slots per warp and lane L uses replica
+// L mod 2^rlog, so lanes of a batch collide 2^rlog times less often (with 32 replicas every lane
+// owns its slots and accesses are bank-conflict free).
+__device__ __forceinline__ bool lc_dense_mode(const LcPrep* p, int force_hash, uint32_t gmax, uint64_t* base,
+                                              uint32_t* window, uint32_t* rlog) {
   const uint64_t a = p->nmin_ord, b = p->max_ord;
   *base = 0;
+  *window = gmax;
+  *rlog = 0;
   if (force_hash || (a == 0 && b == 0)) return false;
   const uint64_t smin = (~a) ^ 0x8000000000000000ull, smax = b ^ 0x8000000000000000ull;   // two's complement bit patterns
   const uint64_t span = smax - smin;           // smax >= smin in signed order, so this does not wrap
   if (span >= gmax) return false;
-  *base = smin - (gmax - (span + 1)) / 2;      // centre the window on the sample (wrapping arithmetic)
+  uint32_t gpow = 1;                           // largest power of two <= gmax
+  while (gpow * 2 <= gmax) gpow *= 2;
+  uint32_t w = 1;                              // power of two >= 1.25 x the sampled range
+  while (w < (span + 1) + (span + 1) / 4) w *= 2;
+  if (w * 2 <= gpow) {
+    *window = w;
+    uint32_t r = gpow / w, l = 0;
+    if (r > 32) r = 32;
+    while ((1u << (l + 1)) <= r) ++l;
+    *rlog = l;
+  }
+  *base = smin - (*window - (span + 1)) / 2;   // centre the window on the sample (wrapping arithmetic)
   return true;
 }
 
@@ -150,7 +168,8 @@ struct LcCtx {
   uint16_t* tids;
   uint32_t* cta_first;
   uint32_t* misc;                     // [1] abort seen by this CTA
-  uint64_t base;                      // dense mode
+  uint64_t base;                      // dense mode: id = key - base, must be < window
+  uint32_t window, rlog, rmask;       // dense mode: accumulator replication (slot = id << rlog | lane & rmask)
 };
 
 __device__ __forceinline__ uint32_t lc_bucket(uint64_t key) {
@@ -350,7 +369,7 @@ __device__ __noinline__ LcContrib<WIDE> lc_fold_general(LcContrib<WIDE> k, uint3
 
 // Accumulate one 32-row batch whose ids are known.  Warp-synchronous; lane L holds row `row`
 // (= batch row base + L).  CLEAN: every lane holds a row with a resolved id and a valid value.
-template <int VC, bool WIDE, bool CLEAN>
+template <int VC, bool WIDE, bool CLEAN, bool DENSE>
 __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row, const LcCtx& c) {
   using Cfg = LcCfg<VC, WIDE>;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -423,7 +442,10 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
         sts64(da, static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(lds64(da))) + k.dsum)));
       }
     }
-    if (first_seen) atomicMin(c.cta_first + id, row + k.lo - lane);   // candidate for the CTA's first row
+    if (first_seen) {   // candidate for the CTA's first row (cta_first is indexed by group id, not by slot)
+      const uint32_t gid = (DENSE && id < static_cast<uint32_t>(Cfg::GMAX)) ? (id >> c.rlog) : id;
+      atomicMin(c.cta_first + gid, row + k.lo - lane);
+    }
   }
   __syncwarp();
 }
@@ -496,10 +518,10 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
       const bool act = CLEAN ? true : ((b.act >> e) & 1u) != 0;
       const bool kvalid = CLEAN ? true : ((b.kv >> e) & 1u) != 0;
       const uint64_t d = b.key[e] - c.base;
-      id[e] = static_cast<uint32_t>(d);
+      id[e] = (static_cast<uint32_t>(d) << c.rlog) | (lane & c.rmask);   // this lane's replica of the group's slot
       if (!kvalid) id[e] = Cfg::ID_NULL;
       if (!act) id[e] = LC_NOID;
-      bad |= act && kvalid && d >= static_cast<uint64_t>(Cfg::GMAX);
+      bad |= act && kvalid && d >= static_cast<uint64_t>(c.window);
     }
     if (__any_sync(FULL, bad)) {
       if (lane == 0) {
@@ -548,7 +570,7 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
     const uint32_t row = static_cast<uint32_t>(g0) + e * 32 + lane;
     constexpr bool ACLEAN = CLEAN && DENSE;   // (hash mode may leave LC_NOID in a lane after an overflow)
     const bool vvalid = CLEAN ? true : ((b.vv >> e) & 1u) != 0;
-    lc_accumulate<VC, WIDE, ACLEAN>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, c);
+    lc_accumulate<VC, WIDE, ACLEAN, DENSE>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, c);
   }
   return true;
 }
@@ -617,7 +639,8 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   c.dsum = acc_s + static_cast<uint32_t>(L::W_DSUM);
   c.cw = acc_s + static_cast<uint32_t>(L::W_CW);
   c.last = acc_s + static_cast<uint32_t>(L::W_LAST);
-  const bool dense = lc_dense_mode(a.dir.prep, a.force_hash, Cfg::GMAX, &c.base);
+  const bool dense = lc_dense_mode(a.dir.prep, a.force_hash, Cfg::GMAX, &c.base, &c.window, &c.rlog);
+  c.rmask = (1u << c.rlog) - 1u;
 
   // ---- init shared state ----
   if (!dense) {
@@ -647,28 +670,36 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
     return;
   }
 
-  // ---- fold the warps in warp order and write this CTA's partial table ----
+  // ---- fold the warps (and, in dense mode, the replicas) in a fixed order and write this CTA's partial table ----
   const size_t pbase = static_cast<size_t>(blockIdx.x) * Cfg::GP;
+  const uint32_t nrep = 1u << c.rlog;
   for (int id = threadIdx.x; id < Cfg::GP; id += Cfg::THREADS) {
     uint64_t sum = 0;
     double fsum = 0.0, dsum = 0.0;
     uint32_t cnt = 0, last = 0;
     uint64_t mn = kMinInit, mx = kMaxInit;
-    for (int w = 0; w < Cfg::WARPS; ++w) {
-      const unsigned char* wa = smem + L::OFF_ACC + L::ACC_PER_WARP * w;
-      const uint32_t cw = reinterpret_cast<const uint32_t*>(wa + L::W_CW)[id] & LC_CNT_MASK;
-      if (cw == LC_CNT_MASK) continue;
-      cnt += cw;
-      const uint64_t s = reinterpret_cast<const uint64_t*>(wa + L::W_SUM)[id];
-      if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(s));
-      else sum += s;
-      if constexpr (WIDE) {
-        const uint32_t l = reinterpret_cast<const uint32_t*>(wa + L::W_LAST)[id];
-        last = l > last ? l : last;
-        const ulonglong2 mm = reinterpret_cast<const ulonglong2*>(wa + L::W_MM)[id];
-        mn = mm.x < mn ? mm.x : mn;
-        mx = mm.y > mx ? mm.y : mx;
-        if constexpr (Cfg::DSUM) dsum += reinterpret_cast<const double*>(wa + L::W_DSUM)[id];
+    const bool regular = id < Cfg::GMAX;
+    const uint32_t reps = regular ? nrep : 1u;
+    if (!regular || static_cast<uint32_t>(id) < c.window) {
+      for (int w = 0; w < Cfg::WARPS; ++w) {
+        const unsigned char* wa = smem + L::OFF_ACC + L::ACC_PER_WARP * w;
+        for (uint32_t r = 0; r < reps; ++r) {
+          const uint32_t slot = regular ? ((static_cast<uint32_t>(id) << c.rlog) | r) : static_cast<uint32_t>(id);
+          const uint32_t cw = reinterpret_cast<const uint32_t*>(wa + L::W_CW)[slot] & LC_CNT_MASK;
+          if (cw == LC_CNT_MASK) continue;
+          cnt += cw;
+          const uint64_t s = reinterpret_cast<const uint64_t*>(wa + L::W_SUM)[slot];
+          if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(s));
+          else sum += s;
+          if constexpr (WIDE) {
+            const uint32_t l = reinterpret_cast<const uint32_t*>(wa + L::W_LAST)[slot];
+            last = l > last ? l : last;
+            const ulonglong2 mm = reinterpret_cast<const ulonglong2*>(wa + L::W_MM)[slot];
+            mn = mm.x < mn ? mm.x : mn;
+            mx = mm.y > mx ? mm.y : mx;
+            if constexpr (Cfg::DSUM) dsum += reinterpret_cast<const double*>(wa + L::W_DSUM)[slot];
+          }
+        }
       }
     }
     if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(fsum));
@@ -803,7 +834,8 @@ __global__ void __launch_bounds__(LR_THREADS, 1) k_lowcard_rank(LmArgs a) {
   __shared__ uint32_t s_total;
   if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_ABORT)) return;
   uint64_t base;
-  const bool dense = lc_dense_mode(a.part.dir.prep, a.part.force_hash, Cfg::GMAX, &base);
+  uint32_t window, rlog;
+  const bool dense = lc_dense_mode(a.part.dir.prep, a.part.force_hash, Cfg::GMAX, &base, &window, &rlog);
   for (int i = threadIdx.x; i < Cfg::GP; i += LR_THREADS) sfirst[i] = a.m_first[i];
   if (threadIdx.x == 0) s_total = 0;
   __syncthreads();
