@@ -712,8 +712,10 @@ int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
   a.agg_mask = mask;
   if (nchunks > 0) {
     const int64_t warps_per_block = RS_THREADS / 32;
+    int per_sm = 1;   // one full wave of resident CTAs: the kernel is a grid-stride loop over chunks
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resample_scan<VC, WIDE>, RS_THREADS, 0));
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((nchunks + warps_per_block - 1) / warps_per_block,
-                                                                           static_cast<int64_t>(g->num_sms) * 8)));
+                                                                           static_cast<int64_t>(g->num_sms) * std::max(per_sm, 1))));
     k_resample_scan<VC, WIDE><<<grid, RS_THREADS, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(g->ev[2], st));

@@ -3,10 +3,11 @@
 //
 //   bucket(ts) = floor((ts' - first) / freq),  ts' = ts (closed left) or ts - 1 (closed right)
 //
-// Each warp owns a contiguous chunk of rows and walks it 32 rows at a time.  While all 32 rows
-// fall into the warp's current bucket (the common case: ~1000 ticks per bucket) the batch is
-// reduced with a fixed shuffle tree and folded into register accumulators; the 64-bit division is
-// only executed when a bucket boundary is crossed.  Runs that start and end inside the chunk are
+// Each warp owns a contiguous chunk of rows and walks it 128 rows (4 coalesced loads per column) at
+// a time.  While all rows of a 32-row batch fall into the warp's current bucket (the common case:
+// ~1000 ticks per bucket) every lane folds its own row into lane-private register accumulators — no
+// shuffles; the lanes are combined with a fixed xor-shuffle tree only when a run ends, and the
+// 64-bit division is only executed when a bucket boundary is crossed.  Runs that start and end inside the chunk are
 // complete and are written straight to the bucket table (no atomics); the first and last run of a
 // chunk may continue in the neighbouring chunks, so they go to a boundary list that a second
 // kernel folds in row order.  All floating-point additions therefore happen in a fixed order.
@@ -90,45 +91,70 @@ __device__ __forceinline__ void rs_store_slot(void* table, int64_t b, const Resa
   }
 }
 
-// fixed shuffle tree over the lanes in `mask` (others contribute the identity)
+// Lane-private partial of the open run: every lane folds its own rows (row order), the lanes are
+// combined with a fixed xor-shuffle tree only when the run is closed.
 template <int VC, bool WIDE>
-__device__ __forceinline__ void rs_warp_reduce(uint32_t mask, uint32_t lane, uint64_t vb, bool valid, uint64_t* o_sum,
-                                               double* o_dsum, uint64_t* o_mn, uint64_t* o_mx, uint32_t* o_cnt) {
-  constexpr uint32_t FULL = 0xFFFFFFFFu;
-  const bool in = ((mask >> lane) & 1u) && valid;
-  *o_cnt = __popc(__ballot_sync(FULL, in));
+struct RsLane {
+  uint64_t sum = 0;     // double bits or wrapping int
+  double dsum = 0.0;
   uint64_t mn = kMinInit, mx = kMaxInit;
-  double ds = 0.0;
-  if constexpr (VC == VC_F) {
-    double s = in ? __longlong_as_double(static_cast<long long>(vb)) : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    *o_sum = static_cast<uint64_t>(__double_as_longlong(s));
-  } else {
-    uint64_t s = in ? vb : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    *o_sum = s;
+  uint32_t cnt = 0;
+  __device__ __forceinline__ void reset() { sum = 0; dsum = 0.0; mn = kMinInit; mx = kMaxInit; cnt = 0; }
+  __device__ __forceinline__ void add_row(uint64_t vb, uint32_t agg_mask) {
+    if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(sum)) +
+                                                                             __longlong_as_double(static_cast<long long>(vb))));
+    else sum += vb;
+    ++cnt;
     if constexpr (WIDE) {
-      ds = in ? Wide<VC>::as_double(vb) : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(FULL, ds, o);
+      if constexpr (VC != VC_F) dsum += Wide<VC>::as_double(vb);
+      if ((agg_mask & (AGG_MIN | AGG_MAX)) && !Wide<VC>::is_nan(vb)) {
+        const uint64_t o = Wide<VC>::ord(vb);
+        mn = o < mn ? o : mn;
+        mx = o > mx ? o : mx;
+      }
     }
   }
-  if constexpr (WIDE) {
-    if (in && !Wide<VC>::is_nan(vb)) { mn = Wide<VC>::ord(vb); mx = mn; }
+  // all lanes end up with the warp total
+  __device__ __forceinline__ void warp_total(RsAcc<VC, WIDE>& out) const {
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    uint32_t c = cnt;
+    uint64_t n = mn, x = mx;
+    double ds = dsum;
+    if constexpr (VC == VC_F) {
+      double v = __longlong_as_double(static_cast<long long>(sum));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const uint64_t a = __shfl_xor_sync(FULL, mn, o), b = __shfl_xor_sync(FULL, mx, o);
-      mn = a < mn ? a : mn;
-      mx = b > mx ? b : mx;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      out.sum = static_cast<uint64_t>(__double_as_longlong(v));
+    } else {
+      uint64_t v = sum;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      out.sum = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    out.cnt = c;
+    if constexpr (WIDE) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t a = __shfl_xor_sync(FULL, n, o), b = __shfl_xor_sync(FULL, x, o);
+        n = a < n ? a : n;
+        x = b > x ? b : x;
+        if constexpr (VC != VC_F) ds += __shfl_xor_sync(FULL, ds, o);
+      }
+      out.mn = n;
+      out.mx = x;
+      out.dsum = ds;
     }
   }
-  *o_dsum = ds;
-  *o_mn = mn;
-  *o_mx = mx;
-}
+};
 
+constexpr int RS_U = 4;   // 32-row batches loaded per iteration (loads issued before any dependent work)
+
+// Sortedness: the algorithm needs the BUCKET sequence to be non-decreasing (every bucket is one run
+// of rows); the order of timestamps inside a bucket is irrelevant — as it is for the reference's
+// two-pointer scan (resample.cpp:43-80).  Inside a chunk every new run must open a later bucket
+// than the one before; across chunks the fixup kernel compares the boundary runs.
 template <int VC, bool WIDE>
 __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -136,18 +162,27 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
   const int64_t gw = (static_cast<int64_t>(blockIdx.x) * RS_THREADS + threadIdx.x) >> 5;
   const int64_t nw = (static_cast<int64_t>(gridDim.x) * RS_THREADS) >> 5;
   const ResampleSpec sp = a.spec;
+  const bool fast_vals = a.vals != nullptr && a.vw == 8 && a.vvalid == nullptr;
+  const uint64_t freq = static_cast<uint64_t>(sp.freq);
+  const int64_t shift = sp.closed_right ? 1 : 0;
   for (int64_t c = gw; c < a.nchunks; c += nw) {
     const int64_t row0 = c * RS_CHUNK;
     const int64_t row_end = row0 + RS_CHUNK < a.n ? row0 + RS_CHUNK : a.n;
-    RsAcc<VC, WIDE> acc;
-    int64_t cur_b = -1, cur_lo = 0, cur_hi = 0;   // current bucket and its [lo, hi) range on ts'
+    RsLane<VC, WIDE> part;                         // this lane's share of the open run
+    uint32_t run_first = kNoRow, run_last = 0;     // first / last row of the open run (uniform)
+    int64_t cur_b = -1;                            // bucket of the open run
+    int64_t cur_lo = INT64_MIN;                    // its left edge on ts'; no open run: (ts' - cur_lo) never < freq
+    bool have_run = false;
     bool first_seg = true;                         // the open run started at the chunk's first row
     bool wrote_first = false;
-    int64_t prev_t = row0 > 0 ? a.ts[row0 - 1] : INT64_MIN;   // sortedness across chunk borders
     bool unsorted = false;
     auto flush = [&](bool chunk_end) {
-      // called by all lanes with identical (uniform) state; lane 0 stores
-      if (cur_b < 0) return;
+      // called by all lanes with identical (uniform) run state
+      if (!have_run) return;
+      RsAcc<VC, WIDE> acc;
+      part.warp_total(acc);
+      acc.first_row = run_first;
+      acc.last_row = run_last;
       if (lane == 0) {
         if (first_seg || chunk_end) {
           RsPartial p;
@@ -161,69 +196,83 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
       if (first_seg) wrote_first = true;
       first_seg = false;
     };
-    for (int64_t r0 = row0; r0 < row_end; r0 += 32) {
-      const int64_t row = r0 + lane;
-      const bool active = row < row_end;
-      int64_t t = INT64_MAX;
-      uint64_t vb = 0;
-      bool valid = false;
-      if (active) {
-        t = a.ts[row];
-        if (a.vals) {
-          vb = load_wide_rt<VC>(a.vals, row, a.vw);
-          valid = a.vvalid ? bit_at(a.vvalid, a.voff + row) : true;
+    for (int64_t g0 = row0; g0 < row_end; g0 += 32 * RS_U) {
+      int64_t tt[RS_U];
+      uint64_t vv[RS_U];
+      bool ok[RS_U];
+      const bool full = g0 + 32 * RS_U <= row_end;
+#pragma unroll
+      for (int u = 0; u < RS_U; ++u) {
+        const int64_t row = g0 + u * 32 + lane;
+        tt[u] = INT64_MAX;
+        vv[u] = 0;
+        ok[u] = false;
+        if (full || row < row_end) {
+          tt[u] = a.ts[row];
+          if (fast_vals) {
+            vv[u] = static_cast<const uint64_t*>(a.vals)[row];
+            ok[u] = true;
+          } else if (a.vals) {
+            vv[u] = load_wide_rt<VC>(a.vals, row, a.vw);
+            ok[u] = a.vvalid ? bit_at(a.vvalid, a.voff + row) : true;
+          }
         }
       }
-      // sortedness: every row must be >= its predecessor
-      int64_t before = __shfl_up_sync(FULL, t, 1);
-      if (lane == 0) before = prev_t;
-      if (active && t < before) unsorted = true;
-      const int last_active = __popc(__ballot_sync(FULL, active)) - 1;
-      prev_t = __shfl_sync(FULL, t, last_active);
-      const int64_t tp = sp.closed_right ? t - 1 : t;
-      uint32_t todo = __ballot_sync(FULL, active);
-      while (todo) {
-        const uint32_t in_cur = __ballot_sync(FULL, active && tp >= cur_lo && tp < cur_hi && cur_b >= 0) & todo;
-        if (in_cur) {
-          uint64_t s, mn, mx;
-          double ds;
-          uint32_t cnt;
-          rs_warp_reduce<VC, WIDE>(in_cur, lane, vb, valid, &s, &ds, &mn, &mx, &cnt);
-          acc.add(s, ds, mn, mx, cnt);
-          const uint32_t lo_row = static_cast<uint32_t>(r0) + (__ffs(in_cur) - 1);
-          const uint32_t hi_row = static_cast<uint32_t>(r0) + (31 - __clz(in_cur));
-          if (acc.first_row == kNoRow) acc.first_row = lo_row;
-          acc.last_row = hi_row;
-          todo &= ~in_cur;
+#pragma unroll
+      for (int u = 0; u < RS_U; ++u) {
+        const int64_t r0 = g0 + u * 32;
+        if (!full && r0 >= row_end) break;
+        const int64_t tp = tt[u] - shift;
+        // one unsigned compare: ts' in [cur_lo, cur_lo + freq)
+        const bool in0 = static_cast<uint64_t>(tp - cur_lo) < freq && have_run;
+        if (full && __all_sync(FULL, in0)) {
+          // common case: the whole batch continues the open run; no shuffles, no division
+          if (fast_vals || ok[u]) part.add_row(vv[u], a.agg_mask);
+          run_last = static_cast<uint32_t>(r0) + 31u;
+          continue;
         }
-        if (todo) {
-          // the lowest remaining row opens a new run: close the current one, locate the next bucket
-          flush(false);
-          acc.reset();
-          const int src = __ffs(todo) - 1;
-          const int64_t t0 = __shfl_sync(FULL, tp, src);
-          int64_t b = (t0 - sp.first) / sp.freq;
-          if (t0 < sp.first || b >= sp.nbins) {   // outside the anchored range: input was not sorted
-            unsorted = true;
-            cur_b = -1;
-            todo &= ~(1u << src);
-            continue;
+        const bool active = full || (r0 + lane < row_end);
+        uint32_t todo = __ballot_sync(FULL, active);
+        while (todo) {
+          const uint32_t in_cur = __ballot_sync(FULL, active && have_run && static_cast<uint64_t>(tp - cur_lo) < freq) & todo;
+          if (in_cur) {
+            if (((in_cur >> lane) & 1u) && ok[u]) part.add_row(vv[u], a.agg_mask);
+            if (run_first == kNoRow) run_first = static_cast<uint32_t>(r0) + (__ffs(in_cur) - 1);
+            run_last = static_cast<uint32_t>(r0) + (31 - __clz(in_cur));
+            todo &= ~in_cur;
           }
-          cur_b = b;
-          cur_lo = sp.first + b * sp.freq;
-          cur_hi = cur_lo + sp.freq;
+          if (todo) {
+            // the lowest remaining row opens a new run: close the current one, locate the next bucket
+            flush(false);
+            part.reset();
+            run_first = kNoRow;
+            run_last = 0;
+            const int src = __ffs(todo) - 1;
+            const int64_t t0 = __shfl_sync(FULL, tp, src);
+            const int64_t b = (t0 - sp.first) / sp.freq;
+            if (t0 < sp.first || b >= sp.nbins || b <= cur_b) {
+              // outside the anchored range, or an earlier bucket again: the input was not sorted
+              unsorted = true;
+              have_run = false;
+              todo &= ~(1u << src);
+              continue;
+            }
+            cur_b = b;
+            cur_lo = sp.first + b * sp.freq;
+            have_run = true;
+          }
         }
       }
     }
     // close the last run of the chunk
-    if (cur_b >= 0) flush(true);
+    flush(true);
     if (lane == 0) {
       // mark the slots this chunk did not use as empty
       if (!wrote_first) a.bnd[c * 2].bucket = -1;
       // slot 1 is used only when the chunk's last run is not also its first run
       // (flush(true) with first_seg == true wrote slot 0)
+      if (unsorted) atomicExch(a.status + ST_UNSORTED, 1u);
     }
-    if (__any_sync(FULL, unsorted) && lane == 0) atomicExch(a.status + ST_UNSORTED, 1u);
   }
 }
 
@@ -240,6 +289,7 @@ __global__ void __launch_bounds__(256) k_resample_fixup(RsArgs a) {
   for (int64_t p = e - 1; p >= 0; --p) {
     const int64_t pb = a.bnd[p].bucket;
     if (pb < 0) continue;
+    if (pb > b) atomicExch(a.status + ST_UNSORTED, 1u);   // bucket sequence decreases across a chunk border
     if (pb == b) return;   // not the head of its run
     break;
   }

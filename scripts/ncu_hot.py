@@ -14,4 +14,6 @@ ranked = sorted(range(len(body)), key=lambda i: -int(body[i][ix["# Samples"]]))[
 for i in sorted(ranked):
     r = body[i]
     st = sorted(((int(r[ix[c]]), c[6:]) for c in stall_cols), reverse=True)[:3]
-    print(f"{i:5d} {int(r[ix['# Samples']]):6d} {100*int(r[ix['# Samples']])/tot:5.1f}% ex={r[ix['Instructions Executed']]:>8} wf={r[ix['L1 Wavefronts Shared']]:>9} ideal={r[ix['L1 Wavefronts Shared Ideal']]:>9} {r[ix['Source']].strip()[:60]:60s} {st}")
+    wf = r[ix['L1 Wavefronts Shared']] if 'L1 Wavefronts Shared' in ix else '-'
+    ideal = r[ix['L1 Wavefronts Shared Ideal']] if 'L1 Wavefronts Shared Ideal' in ix else '-'
+    print(f"{i:5d} {int(r[ix['# Samples']]):6d} {100*int(r[ix['# Samples']])/tot:5.1f}% ex={r[ix['Instructions Executed']]:>8} wf={wf:>9} ideal={ideal:>9} {r[ix['Source']].strip()[:60]:60s} {st}")
