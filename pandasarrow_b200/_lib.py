@@ -19,7 +19,8 @@ PA_PARTIAL_WORDS = 11
 EXPORTS = [
     "pa_last_error", "pa_version", "pa_options_init", "pa_device_count", "pa_groupby_create",
     "pa_groupby_num_groups", "pa_groupby_unique", "pa_groupby_aggregate", "pa_groupby_fetch",
-    "pa_groupby_row_ids", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_sync",
+    "pa_groupby_row_ids", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
+    "pa_groupby_sync",
     "pa_groupby_destroy", "pa_resample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
     "pa_merge_create", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
     "pa_synth_validity", "pa_synth_timestamps",
@@ -86,6 +87,7 @@ def load():
     L.pa_groupby_row_ids.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_last_timing.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pa_groupby_last_path.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.pa_groupby_last_detail.argtypes = [P, C.POINTER(C.c_int32)]
     L.pa_groupby_sync.argtypes = [P]
     L.pa_groupby_destroy.argtypes = [P]
     L.pa_groupby_destroy.restype = None

@@ -208,6 +208,7 @@ struct pa_groupby {
   // bookkeeping
   DevBuf status;
   int last_path = 0, last_launches = 0;
+  int last_mode = 0, last_rlog = 0, last_passes = 0;
   float last_total_ms = 0;
   float stage_ms[4] = {0, 0, 0, 0};
   cudaEvent_t ev[6] = {};
@@ -361,6 +362,9 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   if (h_status[ST_OVERFLOW]) *outcome = LC_OVERFLOW;
   else if (h_status[ST_DENSE_MISS]) *outcome = LC_DENSE_MISS;
   else { *outcome = LC_DONE; g->G = h_status[ST_NGROUPS]; }
+  g->last_mode = static_cast<int>(h_status[ST_MODE]);
+  g->last_rlog = static_cast<int>(h_status[ST_RLOG]);
+  g->last_passes += 1;
   return PA_OK;
 }
 
@@ -640,6 +644,7 @@ int setup_keys(pa_groupby* g) {
 int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
   cudaStream_t st = g->stream;
   g->last_launches = 0;
+  g->last_mode = 0; g->last_rlog = 0; g->last_passes = 0;
   const int vc = val ? val->vc : VC_I;
   const bool wide = is_wide(mask, vc);
   CUDA_TRY(cudaEventRecord(g->ev[0], st));
@@ -660,6 +665,7 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
       else if (g->opt.path == PA_PATH_LOWCARD) return set_err(PA_ERR_INVALID, "more groups than the shared-memory path holds (%d)", gmax);
     }
     if (!done) {
+      g->last_mode = 0; g->last_rlog = 0; g->last_passes += 1;
       PA_TRY(run_global(g, val, mask, wide));
       g->last_path = PA_PATH_GLOBAL;
     }
@@ -971,6 +977,12 @@ int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches)
   if (!g) return set_err(PA_ERR_INVALID, "null argument");
   if (path) *path = g->last_path;
   if (kernel_launches) *kernel_launches = g->last_launches;
+  return PA_OK;
+}
+
+int pa_groupby_last_detail(pa_groupby* g, int32_t detail[4]) {
+  if (!g || !detail) return set_err(PA_ERR_INVALID, "null argument");
+  detail[0] = g->last_mode; detail[1] = g->last_rlog; detail[2] = g->last_passes; detail[3] = 0;
   return PA_OK;
 }
 

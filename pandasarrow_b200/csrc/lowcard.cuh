@@ -641,6 +641,10 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   c.last = acc_s + static_cast<uint32_t>(L::W_LAST);
   const bool dense = lc_dense_mode(a.dir.prep, a.force_hash, Cfg::GMAX, &c.base, &c.window, &c.rlog);
   c.rmask = (1u << c.rlog) - 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.status[ST_MODE] = dense ? 1u : 2u;
+    a.status[ST_RLOG] = c.rlog;
+  }
 
   // ---- init shared state ----
   if (!dense) {

@@ -252,3 +252,66 @@ def test_errors(pab):
         g.fetch("max")                                            # not computed
     with pytest.raises(pab.PaError):
         pab.GroupBy("k", pa.record_batch({"k": pa.array([[1], [2]])}))   # unsupported key type
+
+
+# ---------------- the shared-memory path's modes: dense addressing, replication, hash, fallbacks ----------------
+def _rand_vals(rng, n):
+    return pa.array(rng.random(n) * 100.0 - 20.0)
+
+
+@pytest.mark.parametrize("no_dense", [False, True])
+@pytest.mark.parametrize("G,lo", [(16, 0), (16, -7), (200, 10**12), (1000, -500), (1024, 2**40)])
+def test_lowcard_dense_windows_and_hash_mode(pab, orc, no_dense, G, lo):
+    rng = np.random.default_rng(G + (1 if no_dense else 0))
+    n = 400_003
+    frame = {"k": pa.array(rng.integers(lo, lo + G, n), pa.int64()), "v": _rand_vals(rng, n)}
+    gb, ora, rb = _both(pab, orc, frame, "k", no_dense=no_dense)
+    _cmp(gb, ora, rb, "v", ["sum", "mean", "count", "first"], f"G={G} lo={lo} no_dense={no_dense} narrow")
+    t = gb.timing()
+    assert t["path"] == "lowcard" and t["mode"] == ("hash" if no_dense else "dense") and t["passes"] == 1
+    if not no_dense and G == 16:
+        assert t["replication"] == 32          # every lane owns its accumulator slots
+    if G <= 600:
+        _cmp(gb, ora, rb, "v", ALL, f"G={G} lo={lo} no_dense={no_dense} all")
+        assert gb.timing()["path"] == "lowcard"
+
+
+def test_lowcard_scattered_64bit_keys_use_hash_mode(pab, orc):
+    rng = np.random.default_rng(23)
+    n, G = 500_000, 1000
+    pool = rng.integers(np.iinfo(np.int64).min, np.iinfo(np.int64).max, G, dtype=np.int64)
+    frame = {"k": pa.array(pool[rng.integers(0, G, n)]), "v": _rand_vals(rng, n)}
+    gb, ora, rb = _both(pab, orc, frame, "k")
+    _cmp(gb, ora, rb, "v", ["sum", "mean", "count", "first"], "scattered keys")
+    t = gb.timing()
+    assert t["path"] == "lowcard" and t["mode"] == "hash" and t["passes"] == 1
+    a = gb.aggregate(rb.column("v"), ["sum"])["sum"]
+    b = pab.GroupBy("k", rb).aggregate(rb.column("v"), ["sum"])["sum"]
+    assert a.equals(b)                          # hash mode is run-to-run deterministic too
+
+
+def test_lowcard_dense_miss_reruns_in_hash_mode(pab, orc):
+    # keys 0..499 everywhere except one far-away key in a row the 16384-row key sample does not see
+    rng = np.random.default_rng(29)
+    n = 1_000_000
+    k = rng.integers(0, 500, n)
+    k[777_777] = 10**15
+    frame = {"k": pa.array(k, pa.int64()), "v": _rand_vals(rng, n)}
+    gb, ora, rb = _both(pab, orc, frame, "k")
+    _cmp(gb, ora, rb, "v", ALL, "dense miss")
+    t = gb.timing()
+    assert t["path"] == "lowcard" and t["mode"] == "hash" and t["passes"] == 2
+
+
+@pytest.mark.parametrize("G,aggs,path", [(1024, ["sum", "mean", "count"], "lowcard"), (1025, ["sum", "count"], "global"),
+                                         (640, ["sum", "min", "max", "last"], "lowcard"), (641, ["min", "max"], "global"),
+                                         (2000, ["sum", "mean"], "global")])
+def test_lowcard_capacity_boundaries(pab, orc, G, aggs, path):
+    rng = np.random.default_rng(G)
+    n = 300_000
+    k = np.concatenate([np.arange(G), rng.integers(0, G, n - G)])      # every key present
+    frame = {"k": pa.array(k * 3, pa.int64()), "v": _rand_vals(rng, n)}   # stride 3: a window wider than the table
+    gb, ora, rb = _both(pab, orc, frame, "k")
+    _cmp(gb, ora, rb, "v", aggs, f"G={G} {aggs}")
+    assert gb.timing()["path"] == path
+    assert gb.groupSize() == G
