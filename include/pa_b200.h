@@ -208,6 +208,18 @@ int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records
 int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, int32_t n_sources, uint32_t agg_mask,
                     const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out);
 
+/* Low-latency variant for few groups — no host round trip before the collective.  Writes, for every
+ * destination rank, a fixed-size block of (1 + block_records) records into caller-provided DEVICE memory
+ * (n_parts blocks): record 0 is a header (word 0 = number of records that follow, or all-ones when this
+ * handle has more than block_records groups), then the records that rank owns.  The call is stream ordered
+ * (no synchronisation).  All ranks exchange the blocks with an equal-split all-to-all and hand what they
+ * received (n_sources blocks, in source-rank order) to pa_merge_create_padded, which returns
+ * PA_ERR_STATE when any source sent the overflow marker (every rank sees it: fall back to
+ * pa_groupby_partials_count / _export / pa_merge_create). */
+int pa_groupby_partials_export_padded(pa_groupby* g, int32_t n_parts, void* dev_blocks, int64_t block_records);
+int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t block_records, uint32_t agg_mask,
+                           const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out);
+
 /* ---- synthetic workload generator, used by bench.py and the tests so that the
  * same counter-based splitmix64 streams exist on host and device without PCIe staging.
  * All pointers are DEVICE pointers; `first_row` offsets the counter (row-range shards). ---- */

@@ -22,7 +22,7 @@ EXPORTS = [
     "pa_groupby_row_ids", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
     "pa_groupby_sync",
     "pa_groupby_destroy", "pa_resample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
-    "pa_merge_create", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
+    "pa_merge_create", "pa_groupby_partials_export_padded", "pa_merge_create_padded", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
     "pa_synth_validity", "pa_synth_timestamps",
 ]
 
@@ -97,6 +97,9 @@ def load():
     L.pa_groupby_partials_export.argtypes = [P, C.c_int32, P, C.c_int64]
     L.pa_merge_create.argtypes = [P, C.POINTER(C.c_int64), C.c_int32, C.c_uint32, C.c_char_p, C.c_char_p,
                                   C.POINTER(PaOptions), C.POINTER(P)]
+    L.pa_groupby_partials_export_padded.argtypes = [P, C.c_int32, P, C.c_int64]
+    L.pa_merge_create_padded.argtypes = [P, C.c_int32, C.c_int64, C.c_uint32, C.c_char_p, C.c_char_p,
+                                         C.POINTER(PaOptions), C.POINTER(P)]
     L.pa_synth_keys_i64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, P]
     L.pa_synth_vals_f64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, P]
     L.pa_synth_validity.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32, P]

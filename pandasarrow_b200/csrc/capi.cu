@@ -209,6 +209,7 @@ struct pa_groupby {
   DevBuf status;
   int last_path = 0, last_launches = 0;
   int last_mode = 0, last_rlog = 0, last_passes = 0;
+  const uint32_t* emit_G_dev = nullptr;   // run_emit: exact group count lives on the device (g->G is an upper bound)
   float last_total_ms = 0;
   float stage_ms[4] = {0, 0, 0, 0};
   cudaEvent_t ev[6] = {};
@@ -474,6 +475,7 @@ int run_emit(pa_groupby* g, const Column* val, uint32_t mask) {
   EmitArgs e{};
   e.r = g->res;
   e.G = G;
+  e.G_dev = g->emit_G_dev;
   e.vc = val ? val->vc : VC_I;
   e.vw = val ? val->width : 8;
   e.vals = val ? val->data : nullptr;
@@ -846,10 +848,15 @@ static int handle_init(pa_groupby* g, const pa_options* opt) {
   return PA_OK;
 }
 
+struct HandleDeleter {
+  void operator()(pa_groupby* g) const { pa_groupby_destroy(g); }
+};
+using HandlePtr = std::unique_ptr<pa_groupby, HandleDeleter>;
+
 int pa_groupby_create(const struct ArrowDeviceArray* keys, const struct ArrowSchema* key_schemas, int32_t n_keys,
                       const pa_options* opt, pa_groupby** out) {
   if (!keys || !key_schemas || n_keys < 1 || !out) return set_err(PA_ERR_INVALID, "pa_groupby_create: null argument");
-  std::unique_ptr<pa_groupby> g(new pa_groupby());
+  HandlePtr g(new pa_groupby());
   PA_TRY(handle_init(g.get(), opt));
   g->keys.resize(n_keys);
   for (int i = 0; i < n_keys; ++i) {
@@ -1010,7 +1017,7 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
                        int64_t offset_ns, const pa_options* opt, pa_groupby** out) {
   if (!index || !index_schema || !out) return set_err(PA_ERR_INVALID, "pa_resample_create: null argument");
   if (freq_ns <= 0) return set_err(PA_ERR_INVALID, "FREQ must be positive");   // core.cpp:319-322
-  std::unique_ptr<pa_groupby> g(new pa_groupby());
+  HandlePtr g(new pa_groupby());
   PA_TRY(handle_init(g.get(), opt));
   g->keys.resize(1);
   Column& ix = g->keys[0];
@@ -1110,12 +1117,10 @@ int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records
   return PA_OK;
 }
 
-int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, int32_t n_sources, uint32_t agg_mask,
-                    const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out) {
-  if (!counts_by_source || n_sources < 1 || !value_format || !key_format || !out) return set_err(PA_ERR_INVALID, "null argument");
-  if (agg_mask & ~PA_AGG_ALL) return set_err(PA_ERR_INVALID, "bad aggregate mask");
-  std::unique_ptr<pa_groupby> g(new pa_groupby());
-  PA_TRY(handle_init(g.get(), opt));
+// Common part of the two merge entry points.  `d_off` = device array [n_sources + 1], exclusive prefix
+// of the per-source record counts (the exact total is d_off[n_sources]); nrec_max = host-side upper bound.
+static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d_off, int32_t n_sources, uint64_t nrec_max,
+                       uint32_t agg_mask, const char* value_format, const char* key_format) {
   cudaStream_t st = g->stream;
   g->merged = true;
   g->keys.resize(1);
@@ -1128,40 +1133,29 @@ int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, in
   g->index_format = key_format;
   PA_TRY(parse_format(value_format, &g->last_vw, &g->last_vc));
   g->last_vfmt = value_format;
-  std::vector<uint64_t> off(n_sources + 1, 0);
-  for (int i = 0; i < n_sources; ++i) {
-    if (counts_by_source[i] < 0) return set_err(PA_ERR_INVALID, "negative record count");
-    off[i + 1] = off[i] + static_cast<uint64_t>(counts_by_source[i]);
-  }
-  const uint64_t nrec = off[n_sources];
-  if (nrec && !dev_records) return set_err(PA_ERR_INVALID, "null record buffer");
-  if (nrec >= 0xFFFFFFFFull) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-1 partial records per rank");
+  if (nrec_max >= 0xFFFFFFFFull) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-1 partial records per rank");
   uint64_t cap = 1024;
-  while (cap < nrec * 2) cap <<= 1;
+  while (cap < nrec_max * 2) cap <<= 1;
   const uint64_t nslots = cap + 2;
-  DevBuf d_off, tkeys, idx, m_first, m_slot, s_first, s_slot, cub_tmp;
-  PA_TRY(d_off.alloc(sizeof(uint64_t) * (n_sources + 1), st));
-  CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(uint64_t) * (n_sources + 1), cudaMemcpyHostToDevice, st));
+  DevBuf tkeys, idx, m_first, m_slot, s_first, s_slot, cub_tmp;
   PA_TRY(tkeys.alloc(nslots * 8, st));
   PA_TRY(idx.alloc(nslots * n_sources * 4, st));
   const int fgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
   k_fill_u64<<<fgrid, 256, 0, st>>>(tkeys.as<unsigned long long>(), nslots, kEmptyKey);
   CUDA_TRY(cudaMemsetAsync(idx.p, 0xFF, nslots * n_sources * 4, st));
-  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
-  PA_TRY(m_first.alloc(std::max<uint64_t>(nrec, 1) * 8, st));
-  PA_TRY(m_slot.alloc(std::max<uint64_t>(nrec, 1) * 4, st));
+  PA_TRY(m_first.alloc(std::max<uint64_t>(nrec_max, 1) * 8, st));
+  PA_TRY(m_slot.alloc(std::max<uint64_t>(nrec_max, 1) * 4, st));
   MergeArgs a{};
   a.records = static_cast<const uint64_t*>(dev_records);
-  a.src_offset = d_off.as<uint64_t>();
-  a.nsrc = n_sources; a.nrec = nrec;
+  a.src_offset = d_off;
+  a.nsrc = n_sources; a.nrec = nrec_max;
   a.tkeys = tkeys.as<unsigned long long>(); a.cap_mask = cap - 1; a.idx = idx.as<uint32_t>();
   a.status = g->status.as<uint32_t>();
   a.m_first_row = m_first.as<uint64_t>(); a.m_slot = m_slot.as<uint32_t>();
   a.vc = g->last_vc;
-  CUDA_TRY(cudaEventRecord(g->ev[0], st));
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
-  if (nrec) {
-    k_merge_insert<<<static_cast<int>((nrec + 255) / 256), 256, 0, st>>>(a);
+  if (nrec_max) {
+    k_merge_insert<<<static_cast<int>((nrec_max + 255) / 256), 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
   }
   k_merge_compact<<<static_cast<int>((nslots + 255) / 256), 256, 0, st>>>(a);
@@ -1170,12 +1164,13 @@ int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, in
   uint32_t h_status[ST_WORDS];
   CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_status[ST_PEER_OVERFLOW]) return set_err(PA_ERR_STATE, "a source rank had more groups than a padded block holds; use the counted exchange");
   if (h_status[ST_OVERFLOW]) return set_err(PA_ERR_CUDA, "merge table overflow");
   const uint32_t G = h_status[ST_COUNTER];
   g->G = G;
   const bool wide = is_wide(agg_mask, g->last_vc);
   g->last_wide = wide;
-  PA_TRY(alloc_result(g.get(), G, true, true));
+  PA_TRY(alloc_result(g, G, true, true));
   PA_TRY(g->m_count64.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * 8, st));
   g->res.count64 = g->m_count64.as<uint64_t>();
   PA_TRY(g->m_first_val.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * 8, st));
@@ -1203,9 +1198,134 @@ int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, in
   g->have_groups = true;
   g->last_launches = 4;
   g->last_path = 4;
-  PA_TRY(run_emit(g.get(), nullptr, agg_mask));
+  PA_TRY(run_emit(g, nullptr, agg_mask));
   CUDA_TRY(cudaEventRecord(g->ev[4], st));
   CUDA_TRY(cudaStreamSynchronize(st));   // local scratch (table, idx, sort buffers) is released after this point
+  return PA_OK;
+}
+
+int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, int32_t n_sources, uint32_t agg_mask,
+                    const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out) {
+  if (!counts_by_source || n_sources < 1 || !value_format || !key_format || !out) return set_err(PA_ERR_INVALID, "null argument");
+  if (agg_mask & ~PA_AGG_ALL) return set_err(PA_ERR_INVALID, "bad aggregate mask");
+  HandlePtr g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  cudaStream_t st = g->stream;
+  std::vector<uint64_t> off(n_sources + 1, 0);
+  for (int i = 0; i < n_sources; ++i) {
+    if (counts_by_source[i] < 0) return set_err(PA_ERR_INVALID, "negative record count");
+    off[i + 1] = off[i] + static_cast<uint64_t>(counts_by_source[i]);
+  }
+  const uint64_t nrec = off[n_sources];
+  if (nrec && !dev_records) return set_err(PA_ERR_INVALID, "null record buffer");
+  DevBuf d_off;
+  PA_TRY(d_off.alloc(sizeof(uint64_t) * (n_sources + 1), st));
+  CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(uint64_t) * (n_sources + 1), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  CUDA_TRY(cudaEventRecord(g->ev[0], st));
+  PA_TRY(merge_build(g.get(), dev_records, d_off.as<uint64_t>(), n_sources, nrec, agg_mask, value_format, key_format));
+  *out = g.release();
+  return PA_OK;
+}
+
+int pa_groupby_partials_export_padded(pa_groupby* g, int32_t n_parts, void* dev_blocks, int64_t block_records) {
+  if (!g || !dev_blocks || n_parts < 1 || n_parts > 64 || block_records < 1) return set_err(PA_ERR_INVALID, "bad argument (1 <= n_parts <= 64)");
+  if (!g->have_groups || g->merged) return set_err(PA_ERR_STATE, "partials need a finished local aggregate");
+  if (g->keys.size() != 1 && !g->resample) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of composite keys");
+  PA_TRY(ensure_device(g));
+  PartialsArgs a{};
+  a.r = g->res; a.G = g->G; a.nparts = n_parts; a.row_base = g->opt.row_base;
+  a.vw = g->last_vw; a.wide = g->last_wide;
+  for (auto& o : g->outs) {
+    if (o.bit == AGG_FIRST) { a.first_vals = o.values.p; a.first_valid = o.valid.as<uint32_t>(); }
+    if (o.bit == AGG_LAST) { a.last_vals = o.values.p; a.last_valid = o.valid.as<uint32_t>(); }
+  }
+  a.records = static_cast<uint64_t*>(dev_blocks);
+  k_partials_pack_padded<<<1, 1024, 0, g->stream>>>(a, static_cast<uint64_t>(block_records));
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;   // stream ordered: no host synchronisation
+}
+
+int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t block_records, uint32_t agg_mask,
+                           const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out) {
+  if (!dev_blocks || n_sources < 1 || n_sources > 64 || block_records < 1 || !value_format || !key_format || !out)
+    return set_err(PA_ERR_INVALID, "bad argument (1 <= n_sources <= 64)");
+  if (agg_mask & ~PA_AGG_ALL) return set_err(PA_ERR_INVALID, "bad aggregate mask");
+  HandlePtr g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  cudaStream_t st = g->stream;
+  const uint64_t nrec_max = static_cast<uint64_t>(n_sources) * static_cast<uint64_t>(block_records);
+  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  CUDA_TRY(cudaEventRecord(g->ev[0], st));
+  // ---- few records: the whole merge is one single-CTA kernel + emit, one synchronisation ----
+  {
+    pa_groupby* h = g.get();
+    h->merged = true;
+    h->keys.resize(1);
+    int kw = 8, kvc = VC_I;
+    PA_TRY(parse_format(key_format, &kw, &kvc));
+    h->keys[0].format = key_format;
+    h->keys[0].width = kw;
+    h->fields.assign(1, KeyField{});
+    h->fields[0].width = kw;
+    h->index_format = key_format;
+    PA_TRY(parse_format(value_format, &h->last_vw, &h->last_vc));
+    h->last_vfmt = value_format;
+    h->last_wide = is_wide(agg_mask, h->last_vc);
+    const uint32_t cap_out = static_cast<uint32_t>(std::min<uint64_t>(nrec_max, MS_MAX_GROUPS)) + 2;
+    PA_TRY(alloc_result(h, cap_out, true, true));
+    PA_TRY(h->m_count64.alloc(static_cast<size_t>(cap_out) * 8, st));
+    h->res.count64 = h->m_count64.as<uint64_t>();
+    PA_TRY(h->m_first_val.alloc(static_cast<size_t>(cap_out) * 8, st));
+    PA_TRY(h->m_first_row_g.alloc(static_cast<size_t>(cap_out) * 8, st));
+    PA_TRY(h->m_last_val.alloc(static_cast<size_t>(cap_out) * 8, st));
+    PA_TRY(h->m_first_valid.alloc(cap_out, st));
+    PA_TRY(h->m_last_valid.alloc(cap_out, st));
+    MergeSmallArgs m{};
+    m.blocks = static_cast<const uint64_t*>(dev_blocks);
+    m.nsrc = static_cast<uint32_t>(n_sources);
+    m.block_records = static_cast<uint64_t>(block_records);
+    m.vc = h->last_vc;
+    m.out = h->res;
+    m.o_first_val = h->m_first_val.as<uint64_t>(); m.o_last_val = h->m_last_val.as<uint64_t>();
+    m.o_first_valid = h->m_first_valid.as<uint8_t>(); m.o_last_valid = h->m_last_valid.as<uint8_t>();
+    m.o_first_row_g = h->m_first_row_g.as<uint64_t>();
+    m.status = h->status.as<uint32_t>();
+    CUDA_TRY(cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MS_SMEM_BYTES)));
+    CUDA_TRY(cudaEventRecord(h->ev[1], st));
+    k_merge_small<<<1, MS_THREADS, MS_SMEM_BYTES, st>>>(m);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    h->have_groups = true;
+    h->last_launches = 1;
+    h->last_path = 4;
+    h->G = cap_out;                                     // upper bound for the emit grid and the output buffers
+    h->emit_G_dev = h->status.as<uint32_t>() + ST_COUNTER;
+    PA_TRY(run_emit(h, nullptr, agg_mask));
+    h->emit_G_dev = nullptr;
+    CUDA_TRY(cudaEventRecord(h->ev[4], st));
+    uint32_t h_status[ST_WORDS];
+    CUDA_TRY(cudaMemcpyAsync(h_status, h->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_status[ST_PEER_OVERFLOW]) return set_err(PA_ERR_STATE, "a source rank had more groups than a padded block holds; use the counted exchange");
+    if (!h_status[ST_OVERFLOW]) {
+      h->G = h_status[ST_COUNTER];
+      *out = g.release();
+      return PA_OK;
+    }
+    h->outs.clear();                                    // too many records / groups for one CTA: general merge below
+    h->have_groups = false;
+  }
+  DevBuf d_off, records;
+  PA_TRY(d_off.alloc(sizeof(uint64_t) * (n_sources + 1), st));
+  PA_TRY(records.alloc(nrec_max * PA_PARTIAL_WORDS * 8, st));
+  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  k_merge_unpad<<<n_sources, 256, 0, st>>>(static_cast<const uint64_t*>(dev_blocks), static_cast<uint32_t>(n_sources),
+                                           static_cast<uint64_t>(block_records), records.as<uint64_t>(), d_off.as<uint64_t>(),
+                                           g->status.as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  PA_TRY(merge_build(g.get(), records.p, d_off.as<uint64_t>(), n_sources, nrec_max, agg_mask, value_format, key_format));
   *out = g.release();
   return PA_OK;
 }

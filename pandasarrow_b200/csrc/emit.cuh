@@ -14,7 +14,8 @@ __device__ __forceinline__ void store_valid_bit(uint32_t* bitmap, uint32_t g, ui
 
 struct EmitArgs {
   GroupResult r;
-  uint32_t G;
+  uint32_t G;              // number of groups — or an upper bound (grid size) when G_dev is set
+  const uint32_t* G_dev;   // optional: exact number of groups, on the device
   int vc, vw;              // value class / byte width of the input value column
   const void* vals;        // input value column (first / last gather)
   const uint8_t* vvalid;
@@ -74,6 +75,7 @@ __device__ __forceinline__ uint64_t ord_to_wide(uint64_t o, int vc) {
 // grid: ceil(G/256) blocks of 256 (whole warps so that the ballots are full).
 __global__ void __launch_bounds__(256) k_emit(EmitArgs a) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.G_dev) a.G = *a.G_dev;
   const bool in = g < a.G;
   const uint64_t cnt = in ? (a.r.count64 ? a.r.count64[g] : static_cast<uint64_t>(a.r.count[g])) : 0;
   const bool has = cnt > 0;

@@ -56,13 +56,7 @@ __device__ __forceinline__ uint64_t load_raw(const void* p, uint32_t i, int vw) 
   }
 }
 
-__global__ void __launch_bounds__(256) k_partials_scatter(PartialsArgs a) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.G) return;
-  const uint8_t kind = a.r.key_kind[g];
-  const uint32_t o = owner_of(a.r.key[g], kind, a.nparts);
-  const unsigned long long pos = atomicAdd(a.cursor + o, 1ull);
-  uint64_t* rec = a.records + pos * REC_WORDS;
+__device__ __forceinline__ void write_partial_record(const PartialsArgs& a, uint32_t g, uint8_t kind, uint64_t* rec) {
   uint64_t flags = kind == KK_NULL ? RF_KEY_NULL : 0;
   rec[REC_KEY] = a.r.key[g];
   rec[REC_SUM] = a.r.sum[g];
@@ -86,11 +80,74 @@ __global__ void __launch_bounds__(256) k_partials_scatter(PartialsArgs a) {
   rec[REC_FLAGS] = flags;
 }
 
+__global__ void __launch_bounds__(256) k_partials_scatter(PartialsArgs a) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.G) return;
+  const uint8_t kind = a.r.key_kind[g];
+  const uint32_t o = owner_of(a.r.key[g], kind, a.nparts);
+  const unsigned long long pos = atomicAdd(a.cursor + o, 1ull);
+  write_partial_record(a, g, kind, a.records + pos * REC_WORDS);
+}
+
+// Few groups: no host round trip.  One CTA writes, for every destination rank, a fixed-size block
+// of (1 + block_records) records: record 0 is a header (word 0 = number of records that follow, or
+// kBlockOverflow when this rank has more groups than a block holds), then the records that rank
+// owns.  The blocks are exchanged with an equal-split all-to-all.
+constexpr uint64_t kBlockOverflow = ~0ull;
+__global__ void __launch_bounds__(1024, 1) k_partials_pack_padded(PartialsArgs a, uint64_t block_records) {
+  __shared__ unsigned int s_cnt[64];
+  if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t stride = (block_records + 1) * REC_WORDS;
+  const bool overflow = a.G > block_records;
+  if (!overflow) {
+    for (uint32_t g = threadIdx.x; g < a.G; g += blockDim.x) {
+      const uint8_t kind = a.r.key_kind[g];
+      const uint32_t o = owner_of(a.r.key[g], kind, a.nparts);
+      const uint32_t pos = atomicAdd(&s_cnt[o], 1u);
+      write_partial_record(a, g, kind, a.records + o * stride + (1 + pos) * REC_WORDS);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < a.nparts) {
+    uint64_t* hdr = a.records + threadIdx.x * stride;
+    hdr[0] = overflow ? kBlockOverflow : static_cast<uint64_t>(s_cnt[threadIdx.x]);
+    for (int w = 1; w < REC_WORDS; ++w) hdr[w] = 0;
+  }
+}
+
+// Received padded blocks (one per source rank) -> contiguous records + the exclusive prefix of the
+// per-source counts, both on the device.  One CTA per source.
+__global__ void __launch_bounds__(256) k_merge_unpad(const uint64_t* blocks, uint32_t nsrc, uint64_t block_records,
+                                                    uint64_t* records, uint64_t* src_offset, uint32_t* status) {
+  const uint64_t stride = (block_records + 1) * REC_WORDS;
+  const uint32_t s = blockIdx.x;
+  uint64_t off = 0, mine = 0;
+  bool bad = false;
+  for (uint32_t q = 0; q < nsrc; ++q) {
+    const uint64_t c = blocks[q * stride];
+    if (c == kBlockOverflow || c > block_records) { bad = true; continue; }
+    if (q < s) off += c;
+    if (q == s) mine = c;
+  }
+  if (bad) {
+    if (threadIdx.x == 0) atomicExch(status + ST_PEER_OVERFLOW, 1u);
+    mine = 0;
+  }
+  if (threadIdx.x == 0) {
+    src_offset[s] = bad ? 0 : off;
+    if (s == nsrc - 1) src_offset[nsrc] = bad ? 0 : off + mine;
+  }
+  const uint64_t* src = blocks + s * stride + REC_WORDS;
+  uint64_t* dst = records + off * REC_WORDS;
+  for (uint64_t w = threadIdx.x; w < mine * REC_WORDS; w += blockDim.x) dst[w] = src[w];
+}
+
 struct MergeArgs {
   const uint64_t* records;       // all received records, grouped by source rank
   const uint64_t* src_offset;    // [nsrc + 1] exclusive prefix of the per-source record counts (device)
   uint32_t nsrc;
-  uint64_t nrec;
+  uint64_t nrec;                 // upper bound (grid sizing); the exact count is src_offset[nsrc]
   unsigned long long* tkeys;     // cap + 2 keys
   uint64_t cap_mask;
   uint32_t* idx;                 // [(cap + 2) * nsrc] record index per (slot, source) or 0xFFFFFFFF
@@ -109,7 +166,7 @@ struct MergeArgs {
 
 __global__ void __launch_bounds__(256) k_merge_insert(MergeArgs a) {
   const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-  if (i >= a.nrec) return;
+  if (i >= a.src_offset[a.nsrc]) return;   // (device-side count: padded exchanges do not know it on the host)
   // source rank of record i (nsrc is small: linear scan of the prefix array)
   uint32_t s = 0;
   while (s + 1 < a.nsrc && i >= a.src_offset[s + 1]) ++s;
@@ -203,6 +260,176 @@ __global__ void __launch_bounds__(256) k_merge_fold(MergeArgs a) {
   a.o_first_valid[g] = fvalid;
   a.o_last_valid[g] = lvalid;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Few groups (padded exchange): the whole merge in ONE single-CTA kernel — join by key in a
+// shared-memory table, fold every key's records in source-rank order, rank the groups by their
+// global first row, write the final arrays.  Replaces a chain of ~10 latency-bound launches.
+// Limits: <= MS_MAX_REC records in total, <= MS_MAX_GROUPS distinct keys; beyond that the kernel
+// sets ST_OVERFLOW and the host runs the general merge.
+// ---------------------------------------------------------------------------------------------
+constexpr int MS_THREADS = 1024;
+constexpr int MS_MAX_REC = 16384;
+constexpr int MS_TCAP_LOG2 = 13;
+constexpr int MS_TCAP = 1 << MS_TCAP_LOG2;
+constexpr int MS_MAX_GROUPS = 4096;
+constexpr uint32_t MS_NIL = 0xFFFFu;
+
+struct MergeSmallArgs {
+  const uint64_t* blocks;        // received padded blocks, one per source rank
+  uint32_t nsrc;
+  uint64_t block_records;
+  int vc;
+  GroupResult out;               // capacity >= min(nsrc * block_records, MS_MAX_GROUPS) + 2
+  uint64_t* o_first_val; uint64_t* o_last_val; uint8_t* o_first_valid; uint8_t* o_last_valid;
+  uint64_t* o_first_row_g;
+  uint32_t* status;              // ST_COUNTER = number of merged groups
+};
+
+__global__ void __launch_bounds__(MS_THREADS, 1) k_merge_small(MergeSmallArgs a) {
+  extern __shared__ __align__(16) unsigned char ms_smem[];
+  unsigned long long* tkeys = reinterpret_cast<unsigned long long*>(ms_smem);      // MS_TCAP + 2 (null / sentinel key)
+  unsigned long long* gfirst = tkeys + MS_TCAP + 2;                                 // MS_MAX_GROUPS + 2: global first row of group m
+  uint16_t* head = reinterpret_cast<uint16_t*>(gfirst + MS_MAX_GROUPS + 2);         // MS_TCAP + 2: newest record of the slot
+  uint16_t* next = head + MS_TCAP + 2;                                              // MS_MAX_REC: older record of the same slot
+  uint16_t* gslot = next + MS_MAX_REC;                                              // MS_MAX_GROUPS + 2: slot of group m
+  __shared__ uint32_t s_off[65];
+  __shared__ uint32_t s_ngroups, s_bad;
+  const uint64_t stride = (a.block_records + 1) * REC_WORDS;
+  if (threadIdx.x == 0) {
+    uint32_t off = 0;
+    bool bad = false;
+    for (uint32_t s = 0; s < a.nsrc; ++s) {
+      const uint64_t c = a.blocks[s * stride];
+      s_off[s] = off;
+      if (c == kBlockOverflow || c > a.block_records) bad = true;
+      else off += static_cast<uint32_t>(c);
+    }
+    s_off[a.nsrc] = off;
+    s_ngroups = 0;
+    s_bad = bad ? 1u : (off > MS_MAX_REC ? 2u : 0u);
+  }
+  for (int i = threadIdx.x; i < MS_TCAP + 2; i += MS_THREADS) { tkeys[i] = kEmptyKey; head[i] = MS_NIL; }
+  __syncthreads();
+  if (s_bad) {
+    if (threadIdx.x == 0) atomicExch(a.status + (s_bad == 1u ? ST_PEER_OVERFLOW : ST_OVERFLOW), 1u);
+    return;
+  }
+  const uint32_t nrec = s_off[a.nsrc];
+  auto rec_of = [&](uint32_t i, uint32_t* src) -> const uint64_t* {   // i-th record overall (source-major)
+    uint32_t s = 0;
+    while (s + 1 < a.nsrc && i >= s_off[s + 1]) ++s;
+    *src = s;
+    return a.blocks + s * stride + (1 + (i - s_off[s])) * REC_WORDS;
+  };
+  // phase 1: join by key; every slot keeps a list of its records
+  for (uint32_t i = threadIdx.x; i < nrec; i += MS_THREADS) {
+    uint32_t src;
+    const uint64_t* rec = rec_of(i, &src);
+    const uint64_t key = rec[REC_KEY];
+    uint32_t slot;
+    if (rec[REC_FLAGS] & RF_KEY_NULL) slot = MS_TCAP;
+    else if (key == kEmptyKey) slot = MS_TCAP + 1;
+    else {
+      slot = static_cast<uint32_t>(hash_key64(key ^ 0xA5A5A5A5A5A5A5A5ull)) & (MS_TCAP - 1);
+      for (;;) {
+        const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(tkeys + slot);
+        if (k == key) break;
+        if (k == kEmptyKey) {
+          const uint64_t old = atomicCAS(tkeys + slot, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+          if (old == kEmptyKey) {
+            if (atomicAdd(&s_ngroups, 1u) >= MS_MAX_GROUPS) atomicExch(a.status + ST_OVERFLOW, 1u);
+            break;
+          }
+          if (old == key) break;
+        }
+        slot = (slot + 1) & (MS_TCAP - 1);
+      }
+    }
+    // push front (16-bit exchange emulated on the containing 32-bit word)
+    uint32_t* word = reinterpret_cast<uint32_t*>(head) + (slot >> 1);
+    const uint32_t sh = (slot & 1u) * 16u;
+    uint32_t old = *reinterpret_cast<volatile uint32_t*>(word), assumed;
+    do {
+      assumed = old;
+      old = atomicCAS(word, assumed, (assumed & ~(0xFFFFu << sh)) | (i << sh));
+    } while (old != assumed);
+    next[i] = static_cast<uint16_t>((old >> sh) & 0xFFFFu);
+  }
+  __syncthreads();
+  if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) return;
+  // phase 2: enumerate the occupied slots; a group's sort key is its smallest global first row
+  if (threadIdx.x == 0) s_ngroups = 0;
+  __syncthreads();
+  for (int slot = threadIdx.x; slot < MS_TCAP + 2; slot += MS_THREADS) {
+    uint32_t i = head[slot];
+    if (i == MS_NIL) continue;
+    uint64_t first = ~0ull;
+    for (; i != MS_NIL; i = next[i]) {
+      uint32_t src;
+      const uint64_t f = rec_of(i, &src)[REC_FIRST_ROW];
+      first = f < first ? f : first;
+    }
+    const uint32_t m = atomicAdd(&s_ngroups, 1u);
+    gslot[m] = static_cast<uint16_t>(slot);
+    gfirst[m] = first;
+  }
+  __syncthreads();
+  const uint32_t M = s_ngroups;
+  // phase 3: rank by first row (distinct: a row belongs to one group), fold in source-rank order, write
+  for (uint32_t m = threadIdx.x; m < M; m += MS_THREADS) {
+    const uint64_t myf = gfirst[m];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < M; ++j) rank += gfirst[j] < myf;
+    const uint32_t slot = gslot[m];
+    uint64_t key = 0, sum = 0, mn = kMinInit, mx = kMaxInit, cnt = 0, first = ~0ull, last = 0, fv = 0, lv = 0;
+    double fsum = 0.0, dsum = 0.0;
+    bool knull = false, fvalid = false, lvalid = false, any_last = false;
+    // the list holds at most one record per source; visit the sources in ascending order
+    uint32_t done_below = 0;   // sources < done_below are folded
+    for (;;) {
+      uint32_t best = 0xFFFFFFFFu, best_i = MS_NIL;
+      for (uint32_t i = head[slot]; i != MS_NIL; i = next[i]) {
+        uint32_t src;
+        rec_of(i, &src);
+        if (src >= done_below && src < best) { best = src; best_i = i; }
+      }
+      if (best_i == MS_NIL) break;
+      done_below = best + 1;
+      uint32_t src;
+      const uint64_t* rec = rec_of(best_i, &src);
+      key = rec[REC_KEY];
+      const uint64_t flags = rec[REC_FLAGS];
+      knull = flags & RF_KEY_NULL;
+      if (a.vc == VC_F) fsum += __longlong_as_double(static_cast<long long>(rec[REC_SUM]));
+      else sum += rec[REC_SUM];
+      dsum += __longlong_as_double(static_cast<long long>(rec[REC_DSUM]));
+      cnt += rec[REC_COUNT];
+      mn = rec[REC_MIN] < mn ? rec[REC_MIN] : mn;
+      mx = rec[REC_MAX] > mx ? rec[REC_MAX] : mx;
+      if (rec[REC_FIRST_ROW] < first) { first = rec[REC_FIRST_ROW]; fv = rec[REC_FIRST_VAL]; fvalid = flags & RF_FIRST_VALID; }
+      if (!any_last || rec[REC_LAST_ROW] >= last) { last = rec[REC_LAST_ROW]; lv = rec[REC_LAST_VAL]; lvalid = flags & RF_LAST_VALID; any_last = true; }
+    }
+    if (a.vc == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(fsum));
+    const uint32_t g = rank;
+    a.out.key[g] = key;
+    a.out.key_kind[g] = knull ? KK_NULL : KK_REGULAR;
+    a.out.sum[g] = sum;
+    a.out.count[g] = static_cast<uint32_t>(cnt > 0xFFFFFFFFull ? 0xFFFFFFFFull : cnt);
+    if (a.out.count64) a.out.count64[g] = cnt;
+    a.out.first_row[g] = 0;
+    a.out.last_row[g] = 0;
+    if (a.out.min_ord) { a.out.min_ord[g] = mn; a.out.max_ord[g] = mx; }
+    if (a.out.dsum) a.out.dsum[g] = dsum;
+    a.o_first_row_g[g] = first;
+    a.o_first_val[g] = fv;
+    a.o_last_val[g] = lv;
+    a.o_first_valid[g] = fvalid;
+    a.o_last_valid[g] = lvalid;
+  }
+  if (threadIdx.x == 0) a.status[ST_COUNTER] = M;
+}
+constexpr size_t MS_SMEM_BYTES = (MS_TCAP + 2) * 8 + (MS_MAX_GROUPS + 2) * 8 + (MS_TCAP + 2) * 2 + MS_MAX_REC * 2 + (MS_MAX_GROUPS + 2) * 2 + 64;
 
 __global__ void __launch_bounds__(256) k_fill_u64(unsigned long long* p, uint64_t n, unsigned long long v) {
   uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;

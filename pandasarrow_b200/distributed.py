@@ -67,14 +67,49 @@ def exchange_records(send, send_counts: Sequence[int], group=None):
     return recv, recv_counts
 
 
-def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_format: str, group=None, stream=None):
-    """Run the whole multi-GPU step for this rank.  `gb` is this rank's GroupBy over its row shard
-    (created with row_base = first global row of the shard).  Returns the owner-side MergedGroupBy."""
+PADDED_BLOCK_RECORDS = 2048   # padded exchange: up to this many groups per rank (180 KB per peer block)
+
+
+def exchange_padded(send_blocks, group=None):
+    """Equal-split all-to-all of fixed-size blocks: send_blocks[p] goes to rank p, the result's block s came
+    from rank s.  No counts are exchanged and nothing is read back: the whole step stays stream ordered."""
     import torch
     import torch.distributed as dist
-    from .groupby import MergedGroupBy
+    recv = torch.empty_like(send_blocks)
+    dist.all_to_all_single(recv.view(-1), send_blocks.view(-1), group=group)
+    return recv
+
+
+def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_format: str, group=None, stream=None,
+                      padded: Optional[bool] = None):
+    """Run the whole multi-GPU step for this rank.  `gb` is this rank's GroupBy over its row shard
+    (created with row_base = first global row of the shard).  Returns the owner-side MergedGroupBy.
+
+    With few groups (<= PADDED_BLOCK_RECORDS on this rank) the partials travel in fixed-size blocks: one
+    stream-ordered export kernel, one equal-split all-to-all, one merge — no host round trip in between.  A rank
+    with more groups sends an overflow marker to every peer, so all ranks fall back to the counted exchange
+    together.  `stream` must be the current torch stream for the padded path (it is in bench.py)."""
+    import torch
+    import torch.distributed as dist
+    from .groupby import MergedGroupBy, PaError
     world = dist.get_world_size(group)
     gb.aggregate(values, aggs, fetch=False)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if padded is None:
+        padded = stream is not None and stream == torch.cuda.current_stream(dev).cuda_stream
+    if padded:
+        cap = PADDED_BLOCK_RECORDS
+        send = torch.empty((world, cap + 1, PA_PARTIAL_WORDS), dtype=torch.int64, device=dev)
+        gb.partials_export_padded(world, send.data_ptr(), cap)
+        recv = exchange_padded(send, group)
+        try:
+            merged = MergedGroupBy(recv.data_ptr(), [0] * world, aggs, value_format, key_format, device=dev.index,
+                                   stream=stream, padded_block_records=cap)
+            merged._keep = (send, recv)
+            return merged
+        except PaError as e:
+            if "padded block" not in str(e):
+                raise
     counts = gb.partials_count(world)
     dev = torch.device("cuda", torch.cuda.current_device())
     send = torch.empty((max(sum(counts), 1), PA_PARTIAL_WORDS), dtype=torch.int64, device=dev)

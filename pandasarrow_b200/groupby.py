@@ -254,6 +254,9 @@ class GroupBy:
     def partials_export(self, n_parts: int, records_ptr: int, capacity_records: int):
         _check(self._L.pa_groupby_partials_export(self._h, n_parts, records_ptr, capacity_records))
 
+    def partials_export_padded(self, n_parts: int, blocks_ptr: int, block_records: int):
+        _check(self._L.pa_groupby_partials_export_padded(self._h, n_parts, blocks_ptr, block_records))
+
     def timing(self) -> dict:
         total = C.c_double()
         st = (C.c_double * 4)()
@@ -304,15 +307,22 @@ class MergedGroupBy(GroupBy):
     """Owner-side result of the multi-GPU merge: the groups whose hash(key) % world == rank."""
 
     def __init__(self, records_ptr: int, counts_by_source: Sequence[int], aggs: Sequence[str], value_format: str,
-                 key_format: str, device: Optional[int] = None, stream: Optional[int] = None):
+                 key_format: str, device: Optional[int] = None, stream: Optional[int] = None,
+                 padded_block_records: int = 0):
+        """counts_by_source: per-source record counts (counted exchange), or — with padded_block_records > 0 —
+        just the number of sources as a list of that length (padded exchange, counts live in the block headers)."""
         self._L = _lib.load()
         self._h = C.c_void_p()
         self._frame, self._dicts, self.key_names, self._key_args = {}, [None], ["key"], []
         mask = 0
         for a in aggs:
             mask |= PA_AGG[a]
-        counts = (C.c_int64 * len(counts_by_source))(*[int(c) for c in counts_by_source])
         opt = _options(0, "auto", device, stream)
+        if padded_block_records > 0:
+            _check(self._L.pa_merge_create_padded(records_ptr, len(counts_by_source), padded_block_records, mask,
+                                                  value_format.encode(), key_format.encode(), C.byref(opt), C.byref(self._h)))
+            return
+        counts = (C.c_int64 * len(counts_by_source))(*[int(c) for c in counts_by_source])
         _check(self._L.pa_merge_create(records_ptr, counts, len(counts_by_source), mask, value_format.encode(),
                                        key_format.encode(), C.byref(opt), C.byref(self._h)))
 

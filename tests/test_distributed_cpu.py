@@ -58,6 +58,16 @@ def _worker(rank, world, port, q):
     cnts = np.array([recv[recv[:, 0] == k, 4].sum() for k in keys])
     first = np.array([recv[recv[:, 0] == k, 5].min() for k in keys])
     got = D.gather_result({"key": keys, "sum": sums, "count": cnts}, first)
+    # padded exchange: block [p] of my send buffer arrives as block [rank] ... of rank p's receive buffer
+    cap = 8
+    blocks = torch.zeros((world, cap + 1, W), dtype=torch.int64)
+    for p_ in range(world):
+        blocks[p_, 0, 0] = 3                                # header: record count
+        blocks[p_, 1:4, 0] = torch.tensor([rank * 100 + p_ * 10 + j for j in range(3)])
+    got_blocks = D.exchange_padded(blocks)
+    for s in range(world):
+        ok &= int(got_blocks[s, 0, 0]) == 3
+        ok &= got_blocks[s, 1:4, 0].tolist() == [s * 100 + rank * 10 + j for j in range(3)]
     q.put((rank, ok, got["key"].tolist(), got["sum"].tolist(), got["count"].tolist()))
     dist.barrier()
     dist.destroy_process_group()

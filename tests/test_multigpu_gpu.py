@@ -95,3 +95,59 @@ def test_sharded_int_values_and_single_rank():
     assert k1.equals(whole.unique()) and k3.equals(whole.unique())
     for a in ALL:
         assert r1[a].equals(w[a]) and r3[a].equals(w[a]), a     # integer / positional aggregates: bit exact across P
+
+
+def _run_sharded_padded(pab, rb, key, col, aggs, world, cap):
+    """Same as _run_sharded, through the padded (no host round trip) exchange: block [s][o] of rank s's
+    export goes to owner o."""
+    import torch
+    from pandasarrow_b200 import distributed as D
+    from pandasarrow_b200._lib import PA_PARTIAL_WORDS as W
+    n = rb.num_rows
+    sends = []
+    for r in range(world):
+        b, e = D.shard_rows(n, world, r)
+        shard = rb.slice(b, e - b)
+        g = pab.GroupBy(key, shard, row_base=b)
+        g.aggregate(shard.column(col), aggs, fetch=False)
+        buf = torch.empty((world, cap + 1, W), dtype=torch.int64, device="cuda")
+        g.partials_export_padded(world, buf.data_ptr(), cap)
+        sends.append(buf)
+        g.close()
+    torch.cuda.synchronize()
+    out = {a: [] for a in aggs}
+    keys, firsts = [], []
+    for o in range(world):
+        recv = torch.stack([sends[s][o] for s in range(world)]).contiguous()
+        m = pab.MergedGroupBy(recv.data_ptr(), [0] * world, aggs, FMT[rb.column(col).type], FMT.get(rb.column(key).type, "l"),
+                              padded_block_records=cap)
+        for a in aggs:
+            out[a].append(m.fetch(a))
+        keys.append(m.unique()); firsts.append(m.first_rows().to_numpy())
+        m.close()
+    fr = np.concatenate(firsts)
+    order = pa.array(np.argsort(fr, kind="stable"))
+    return pa.concat_arrays(keys).take(order), {a: pa.concat_arrays(out[a]).take(order) for a in aggs}
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_padded_exchange_equals_counted_exchange(world):
+    import pandasarrow_b200 as pab
+    from pandasarrow_b200 import hostgen as hg
+    n, G = 300_007, 500     # <= 640 groups: the wide aggregates stay on the deterministic shared-memory path
+    kmask = hg.valid_mask(n, seed=5, null_every=89)
+    rb = pa.record_batch({"k": pa.array(hg.keys(n, G), mask=~kmask), "v": pa.array(hg.vals(n), mask=~hg.valid_mask(n))})
+    k1, r1, _ = _run_sharded(pab, rb, "k", "v", ALL, world)
+    k2, r2 = _run_sharded_padded(pab, rb, "k", "v", ALL, world, cap=2048)
+    assert k1.equals(k2)
+    for a in ALL:
+        assert r1[a].equals(r2[a]), a          # same records, same source-rank fold order: bit for bit
+
+
+def test_padded_exchange_overflow_marker():
+    import pandasarrow_b200 as pab
+    from pandasarrow_b200 import hostgen as hg
+    n, G = 100_000, 5000
+    rb = pa.record_batch({"k": pa.array(hg.keys(n, G)), "v": pa.array(hg.vals(n))})
+    with pytest.raises(pab.PaError, match="padded block"):
+        _run_sharded_padded(pab, rb, "k", "v", ["sum"], 2, cap=2048)
