@@ -166,8 +166,8 @@ int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]);
 /* Which path the last aggregate took (PA_PATH_LOWCARD / PA_PATH_GLOBAL) and how many of this
  * library's kernels it launched. */
 int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches);
-/* More about the last aggregate call: detail[0] = shared-memory path mode (0 n/a, 1 dense key - base
- * addressing, 2 hash table), detail[1] = log2 of the accumulator replication (dense mode),
+/* More about the last aggregate call: detail[0] = mode (0 n/a; shared-memory path: 1 dense key - base
+ * addressing, 2 hash table; global path: 3 = shared-memory front table with spill), detail[1] = log2 of the accumulator replication (dense mode),
  * detail[2] = scan passes run (2 = a dense pass met a key outside its window and was rerun in hash
  * mode; +1 when the shared-memory tables overflowed and the global-table path ran), detail[3] = 0. */
 int pa_groupby_last_detail(pa_groupby* g, int32_t detail[4]);

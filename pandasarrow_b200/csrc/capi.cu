@@ -380,7 +380,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   const uint64_t cap_limit = [&] { uint64_t c = 1024; while (c < static_cast<uint64_t>(g->n) * 2) c <<= 1; return c; }();
   if (cap > cap_limit) cap = cap_limit;
   DevBuf table;
-  const int grid_full = g->num_sms * 8;
+  const int grid_full = g->num_sms * 6;   // two waves of the 3 resident CTAs per SM
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
   for (;;) {
     const uint64_t nslots = cap + 2;
@@ -408,8 +408,21 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, grid_full)));
     const bool fast = a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid && !a.vvalid &&
                       reinterpret_cast<uintptr_t>(a.keys) % 16 == 0 && reinterpret_cast<uintptr_t>(a.vals) % 16 == 0;
-    if (fast) k_gtable_scan<VC, WIDE, true><<<grid, 256, 0, st>>>(a);
-    else k_gtable_scan<VC, WIDE, false><<<grid, 256, 0, st>>>(a);
+    // Shared-memory front table unless the caller (or an earlier pass on this handle) says there are
+    // far more groups than it holds; it spills to the global table, so it is correct for any input.
+    const uint64_t known = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
+    const bool front = known <= static_cast<uint64_t>(SmTab<VC, WIDE>::MAX_KEYS);
+    if (front) {
+      auto kern = fast ? k_smemtab_scan<VC, WIDE, true> : k_smemtab_scan<VC, WIDE, false>;
+      const size_t smem = SmTab<VC, WIDE>::TOTAL;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      kern<<<g->num_sms, SM_THREADS, smem, st>>>(a);
+    } else if (fast) {
+      k_gtable_scan<VC, WIDE, true><<<grid, 256, 0, st>>>(a);
+    } else {
+      k_gtable_scan<VC, WIDE, false><<<grid, 256, 0, st>>>(a);
+    }
+    g->last_mode = front ? 3 : 0;
     CUDA_TRY(cudaGetLastError());
     g->last_launches += 2;
     uint32_t h_status[ST_WORDS];
@@ -656,8 +669,9 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
     g->last_path = 3;
   } else {
     const int gmax = lc_gmax(vc, lc_is_wide(mask, vc));
-    bool try_low = g->opt.path != PA_PATH_GLOBAL &&
-                   (g->opt.expected_groups == 0 || g->opt.expected_groups <= gmax || g->opt.path == PA_PATH_LOWCARD);
+    // (an earlier pass on this handle may already have told us how many groups there are)
+    const int64_t known_groups = g->opt.expected_groups > 0 ? g->opt.expected_groups : (g->have_groups ? static_cast<int64_t>(g->G) : 0);
+    bool try_low = g->opt.path != PA_PATH_GLOBAL && (known_groups <= gmax + 2 || g->opt.path == PA_PATH_LOWCARD);
     bool done = false;
     if (try_low) {
       LcOutcome oc = LC_DONE;

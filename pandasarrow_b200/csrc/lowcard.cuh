@@ -192,6 +192,7 @@ __device__ __forceinline__ uint32_t lc_lookup(uint64_t key, uint32_t b, const un
 __device__ __noinline__ uint32_t lc_global_id(uint64_t key, LcDir d, uint32_t gmax) {
   uint32_t s = static_cast<uint32_t>(hash_key64(key)) & (LC_GT_CAP - 1);
   for (int probe = 0; probe < LC_GT_CAP; ++probe) {
+    if (*reinterpret_cast<volatile unsigned int*>(&d.prep->next_id) > gmax) return LC_NOID;   // already overflowed: do not crawl a full directory
     uint64_t k = *reinterpret_cast<volatile unsigned long long*>(d.gt_keys + s);
     if (k == kEmptyKey) {
       k = atomicCAS(d.gt_keys + s, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
@@ -221,6 +222,7 @@ __device__ __noinline__ uint32_t lc_global_id(uint64_t key, LcDir d, uint32_t gm
 // inserts on first sight.  LC_NOID on overflow.
 __device__ __noinline__ uint32_t lc_miss_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
                                                  uint32_t* misc, LcDir d, uint32_t gmax, uint32_t* status) {
+  if (*reinterpret_cast<volatile uint32_t*>(misc + 1) || *reinterpret_cast<volatile uint32_t*>(status + ST_ABORT)) return LC_NOID;
   uint32_t b = lc_bucket(key);
   for (int probe = 0; probe < 4 * LC_NBUCKET; ++probe) {
     const uint64_t k0 = *reinterpret_cast<volatile unsigned long long*>(tkeys + 2 * b);

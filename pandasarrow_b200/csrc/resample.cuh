@@ -76,18 +76,16 @@ struct RsAcc {
 template <int VC, bool WIDE>
 __device__ __forceinline__ void rs_store_slot(void* table, int64_t b, const ResampleSpec& sp, const RsAcc<VC, WIDE>& a) {
   using SlotT = typename SlotOf<WIDE>::type;
-  SlotT* s = static_cast<SlotT*>(table) + b;
-  Slot32* q = reinterpret_cast<Slot32*>(s);
+  SlotT* q = static_cast<SlotT*>(table) + b;
   q->key = static_cast<uint64_t>(sp.first + b * sp.freq + sp.label_off);
   q->first_row = a.first_row;
   q->last_row = a.last_row;
   q->sum = a.sum;
   q->count = a.cnt;
   if constexpr (WIDE) {
-    Slot64* w = reinterpret_cast<Slot64*>(s);
-    w->min_ord = a.mn;
-    w->max_ord = a.mx;
-    w->dsum = a.dsum;
+    q->min_ord = a.mn;
+    q->max_ord = a.mx;
+    q->dsum = a.dsum;
   }
 }
 

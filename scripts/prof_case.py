@@ -17,8 +17,10 @@ a = ap.parse_args()
 n = a.rows
 k = torch.empty(n, dtype=torch.int64, device="cuda"); v = torch.empty(n, dtype=torch.float64, device="cuda")
 pab.synth.keys(k, a.groups); pab.synth.vals(v)
-if a.hashed:
-    k.mul_(-7046029254386353131).bitwise_xor_(0x5DEECE66D)
+if a.hashed:   # bijective scramble: multiply, xor with a logical right shift, multiply
+    k.mul_(-3335678366873096957)
+    k.bitwise_xor_((k >> 29) & ((1 << 35) - 1))
+    k.mul_(-4658895280553007687)
 torch.cuda.synchronize()
 dk, dv = pab.DeviceColumn.from_torch(k), pab.DeviceColumn.from_torch(v)
 g = pab.GroupBy("k", {"k": dk, "v": dv}, path=a.path, expected_groups=a.hint)
