@@ -317,6 +317,7 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   a.vw = val ? val->width : 8;
   a.n = g->n;
   a.force_hash = force_hash ? 1 : 0;
+  a.agg_mask = mask;
   char* d = dir.as<char>();
   a.dir.prep = reinterpret_cast<LcPrep*>(d);
   a.dir.key_by_id = reinterpret_cast<unsigned long long*>(d + sizeof(LcPrep));

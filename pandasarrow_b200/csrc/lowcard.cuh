@@ -51,9 +51,9 @@ constexpr uint16_t LC_ID_OVF = 0xFFFEu;
 constexpr uint32_t LC_NOID = 0xFFFFFFFFu;
 constexpr uint32_t LC_CNT_MASK = 0x00FFFFFFu;   // count field of a count word; byte 3 = claim tag
                                                 // (count == LC_CNT_MASK: the warp has not met this id yet)
-constexpr int LC_GMAX_NARROW = 1024;   // sum / mean(float) / count / first    : 12 B per id per warp, 12 warps
-constexpr int LC_GMAX_WIDE_F = 640;    // + min / max / last                   : 32 B per id per warp, 8 warps
-constexpr int LC_GMAX_WIDE_I = 512;    // + double sum (mean of integers)      : 40 B
+constexpr int LC_GMAX_NARROW = 1024;   // sum / mean(float) / count / first : 12 B per id per warp
+constexpr int LC_GMAX_WIDE_F = 1024;   // + min / max / last               : + 20 B per id, CTA shared (order independent)
+constexpr int LC_GMAX_WIDE_I = 640;    // + double sum (mean of integers)  : 20 B per id per warp
 constexpr int LC_GMAX_MAX = LC_GMAX_NARROW;
 
 // global key -> id directory (hash mode)
@@ -66,7 +66,7 @@ constexpr int LC_PREP_GRID = 64;       // x 256 threads = 16384 sampled keys
 template <int VC, bool WIDE>
 struct LcCfg {
   static constexpr bool DSUM = WIDE && VC != VC_F;
-  static constexpr int WARPS = WIDE ? 8 : 12;
+  static constexpr int WARPS = 12;
   static constexpr int THREADS = WARPS * 32;
   static constexpr int GMAX = WIDE ? (DSUM ? LC_GMAX_WIDE_I : LC_GMAX_WIDE_F) : LC_GMAX_NARROW;
   static constexpr int GP = GMAX + 2;             // + null-key group + (key == kEmptyKey) group
@@ -129,6 +129,7 @@ struct LcArgs {
   int64_t n;
   int kw, vw;              // element widths in bytes (generic loader)
   int force_hash;
+  uint32_t agg_mask;
   LcDir dir;
   // per-CTA partial tables, [grid][GP]
   uint64_t* p_sum;
@@ -141,8 +142,9 @@ struct LcArgs {
   uint32_t* status;
 };
 
-// Shared-memory layout.  Per warp: [minmax 16 B x GP (wide)] [sum 8 B x GP] [dsum 8 B x GP (ints, wide)]
-// [count word 4 B x GP] [last row 4 B x GP (wide)].
+// Shared-memory layout.  CTA shared: hash table, first rows, and (wide) {min, max} 16 B + last row 4 B per id,
+// which are order independent and therefore updated by all warps with shared-memory atomics after a plain
+// pre-check.  Per warp: [sum 8 B x GP] [dsum 8 B x GP (mean of integers)] [count word 4 B x GP].
 template <int VC, bool WIDE>
 struct LcSmem {
   using Cfg = LcCfg<VC, WIDE>;
@@ -150,20 +152,23 @@ struct LcSmem {
   static constexpr size_t OFF_MISC = 0;                                          // 4 x u32
   static constexpr size_t OFF_TKEYS = 16;                                        // LC_TCAP u64
   static constexpr size_t OFF_TIDS = OFF_TKEYS + LC_TCAP * 8;                    // LC_TCAP u16
-  static constexpr size_t OFF_FIRST = OFF_TIDS + LC_TCAP * 2;                    // GP u32 (CTA shared)
-  static constexpr size_t OFF_ACC = OFF_FIRST + ((GP * 4 + 15) / 16) * 16;
-  static constexpr size_t W_MM = 0;
-  static constexpr size_t W_SUM = W_MM + (WIDE ? GP * 16 : 0);
+  static constexpr size_t OFF_MM = OFF_TIDS + LC_TCAP * 2;                       // GP x {min, max} (wide)
+  static constexpr size_t OFF_FIRST = OFF_MM + (WIDE ? GP * 16 : 0);             // GP u32
+  static constexpr size_t OFF_LAST = OFF_FIRST + GP * 4;                         // GP u32 (wide)
+  static constexpr size_t OFF_ACC = ((OFF_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;
+  static constexpr size_t W_SUM = 0;
   static constexpr size_t W_DSUM = W_SUM + GP * 8;
   static constexpr size_t W_CW = W_DSUM + (Cfg::DSUM ? GP * 8 : 0);
-  static constexpr size_t W_LAST = W_CW + GP * 4;
-  static constexpr size_t ACC_PER_WARP = ((W_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;
+  static constexpr size_t ACC_PER_WARP = ((W_CW + GP * 4 + 15) / 16) * 16;
   static constexpr size_t TOTAL = OFF_ACC + ACC_PER_WARP * Cfg::WARPS;
 };
 
 // per-thread view of the CTA's shared state (32-bit shared-memory addresses for the hot arrays)
 struct LcCtx {
-  uint32_t sum, cw, last, mm, dsum;   // this warp's accumulator arrays
+  uint32_t sum, cw, dsum;             // this warp's accumulator arrays
+  uint32_t mm;                        // CTA-shared {min, max} array (wide), shared-memory address
+  unsigned long long* mm_p;           // the same, generic pointer (atomics)
+  uint32_t* last_p;                   // CTA-shared last-row array (wide)
   unsigned long long* tkeys;
   uint16_t* tids;
   uint32_t* cta_first;
@@ -262,26 +267,25 @@ __device__ __noinline__ uint32_t lc_miss_resolve(uint64_t key, unsigned long lon
   return LC_NOID;
 }
 
-// What one lane (later: one group) adds to the accumulators.
-template <bool WIDE>
+// What one lane (later: one group) adds to the warp-private accumulators.
+template <bool DSUM>
 struct LcContrib {
   uint64_t sum;      // double bits (VC_F) or wrapping integer
   uint32_t cnt;
-  uint32_t lo, hi;   // lowest / highest lane of the group
+  uint32_t lo;       // lowest lane of the group
   uint32_t doer;     // this lane performs the read-modify-write
 };
 template <>
 struct LcContrib<true> {
   uint64_t sum;
   uint32_t cnt;
-  uint32_t lo, hi;
+  uint32_t lo;
   uint32_t doer;
-  double dsum;
-  uint64_t mn, mx;
+  double dsum;       // sum of the values converted to double (mean of integers)
 };
 
-template <int VC, bool WIDE>
-__device__ __forceinline__ void lc_add(LcContrib<WIDE>& t, const LcContrib<WIDE>& x) {
+template <int VC, bool DSUM>
+__device__ __forceinline__ void lc_add(LcContrib<DSUM>& t, const LcContrib<DSUM>& x) {
   if constexpr (VC == VC_F) {
     t.sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(t.sum)) +
                                                        __longlong_as_double(static_cast<long long>(x.sum))));
@@ -289,32 +293,24 @@ __device__ __forceinline__ void lc_add(LcContrib<WIDE>& t, const LcContrib<WIDE>
     t.sum += x.sum;
   }
   t.cnt += x.cnt;
-  if constexpr (WIDE) {
-    if constexpr (VC != VC_F) t.dsum += x.dsum;
-    t.mn = x.mn < t.mn ? x.mn : t.mn;
-    t.mx = x.mx > t.mx ? x.mx : t.mx;
-  }
+  if constexpr (DSUM) t.dsum += x.dsum;
 }
 
-template <int VC, bool WIDE>
-__device__ __forceinline__ LcContrib<WIDE> lc_shfl(const LcContrib<WIDE>& k, int src) {
+template <int VC, bool DSUM>
+__device__ __forceinline__ LcContrib<DSUM> lc_shfl(const LcContrib<DSUM>& k, int src) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
-  LcContrib<WIDE> o = k;
+  LcContrib<DSUM> o = k;
   o.sum = __shfl_sync(FULL, k.sum, src);
   o.cnt = __shfl_sync(FULL, k.cnt, src);
-  if constexpr (WIDE) {
-    if constexpr (VC != VC_F) o.dsum = __shfl_sync(FULL, k.dsum, src);
-    o.mn = __shfl_sync(FULL, k.mn, src);
-    o.mx = __shfl_sync(FULL, k.mx, src);
-  }
+  if constexpr (DSUM) o.dsum = __shfl_sync(FULL, k.dsum, src);
   return o;
 }
 
 // Two or more losing lanes in the batch: fold every group in ascending lane (= row) order, so that
 // the result does not depend on which lanes the hardware let win.  Out of line (rare for ~1000
 // groups; for a handful of groups nearly every batch comes here and MATCH.ANY is cheap).
-template <int VC, bool WIDE>
-__device__ __noinline__ LcContrib<WIDE> lc_fold_general(LcContrib<WIDE> k, uint32_t id, uint32_t tag, uint32_t live,
+template <int VC, bool DSUM>
+__device__ __noinline__ LcContrib<DSUM> lc_fold_general(LcContrib<DSUM> k, uint32_t id, uint32_t tag, uint32_t live,
                                                         uint32_t losers) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = lane_id();
@@ -322,28 +318,27 @@ __device__ __noinline__ LcContrib<WIDE> lc_fold_general(LcContrib<WIDE> k, uint3
   if (__popc(losers) <= 4) {
     // few duplicates: one warp-uniform iteration per loser lane, ascending; the winner inserts its
     // own value at its own lane position
-    LcContrib<WIDE> f = k;
+    LcContrib<DSUM> f = k;
     f.sum = 0; f.cnt = 0;
-    if constexpr (WIDE) { f.dsum = 0.0; f.mn = kMinInit; f.mx = kMaxInit; }
+    if constexpr (DSUM) f.dsum = 0.0;
     bool own_added = false;
     uint32_t rem = losers;
     while (rem) {
       const int L = __ffs(rem) - 1;
       rem &= rem - 1;
       const uint32_t tw = __shfl_sync(FULL, tag, L);
-      const LcContrib<WIDE> o = lc_shfl<VC, WIDE>(k, L);
+      const LcContrib<DSUM> o = lc_shfl<VC, DSUM>(k, L);
       if (winner && tw == lane) {
         if (!own_added && static_cast<uint32_t>(L) > lane) {
-          lc_add<VC, WIDE>(f, k);
+          lc_add<VC, DSUM>(f, k);
           own_added = true;
         }
-        lc_add<VC, WIDE>(f, o);
+        lc_add<VC, DSUM>(f, o);
         f.lo = static_cast<uint32_t>(L) < f.lo ? static_cast<uint32_t>(L) : f.lo;
-        f.hi = static_cast<uint32_t>(L) > f.hi ? static_cast<uint32_t>(L) : f.hi;
       }
     }
     if (winner) {
-      if (!own_added) lc_add<VC, WIDE>(f, k);
+      if (!own_added) lc_add<VC, DSUM>(f, k);
       k = f;
     }
     k.doer = winner;
@@ -356,23 +351,24 @@ __device__ __noinline__ LcContrib<WIDE> lc_fold_general(LcContrib<WIDE> k, uint3
     uint32_t rem = leader ? (peers & ~lanebit) : 0u;
     while (__any_sync(FULL, rem != 0)) {
       const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
-      const LcContrib<WIDE> o = lc_shfl<VC, WIDE>(k, src);
+      const LcContrib<DSUM> o = lc_shfl<VC, DSUM>(k, src);
       if (rem) {
-        lc_add<VC, WIDE>(k, o);
+        lc_add<VC, DSUM>(k, o);
         rem &= rem - 1;
       }
     }
     k.doer = live && leader;
     k.lo = lane;
-    k.hi = 31 - __clz(peers);
   }
   return k;
 }
 
 // Accumulate one 32-row batch whose ids are known.  Warp-synchronous; lane L holds row `row`
 // (= batch row base + L).  CLEAN: every lane holds a row with a resolved id and a valid value.
+// `id` is the lane's accumulator SLOT (dense mode: group id << rlog | replica), `gid` the group id.
 template <int VC, bool WIDE, bool CLEAN, bool DENSE>
-__device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row, const LcCtx& c) {
+__device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row, uint32_t agg_mask,
+                                              const LcCtx& c) {
   using Cfg = LcCfg<VC, WIDE>;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = lane_id();
@@ -383,44 +379,49 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
   __syncwarp();
   const uint32_t cw = lds32(cw_addr);
   uint64_t s = lds64(sum_addr);
+  const bool vv = CLEAN ? true : vvalid;
+  const uint32_t gid = (DENSE && ida < static_cast<uint32_t>(Cfg::GMAX)) ? (ida >> c.rlog) : ida;
+  if constexpr (WIDE) {
+    // min / max / last row are order independent: CTA-shared arrays, plain pre-check, rare atomic
+    if (live) {
+      if (agg_mask & AGG_LAST) atomicMax(c.last_p + gid, row);
+      if (vv && (agg_mask & (AGG_MIN | AGG_MAX)) && !Wide<VC>::is_nan(vbits)) {
+        const uint64_t o = Wide<VC>::ord(vbits);
+        const uint4 m4 = lds128(c.mm + gid * 16u);
+        const uint64_t mn = static_cast<uint64_t>(m4.x) | (static_cast<uint64_t>(m4.y) << 32);
+        const uint64_t mx = static_cast<uint64_t>(m4.z) | (static_cast<uint64_t>(m4.w) << 32);
+        if (o < mn) atomicMin(c.mm_p + 2 * gid, static_cast<unsigned long long>(o));
+        if (o > mx) atomicMax(c.mm_p + 2 * gid + 1, static_cast<unsigned long long>(o));
+      }
+    }
+  }
   const uint32_t tag = cw >> 24;
   const bool winner = live && (tag == lane);
   const uint32_t losers = __ballot_sync(FULL, live && !winner);
-  LcContrib<WIDE> k;
-  const bool vv = CLEAN ? true : vvalid;
+  LcContrib<Cfg::DSUM> k;
   k.sum = vv ? vbits : 0ull;
   k.cnt = vv ? 1u : 0u;
   k.lo = lane;
-  k.hi = lane;
   k.doer = winner;
-  if constexpr (WIDE) {
-    k.dsum = 0.0;
-    k.mn = kMinInit;
-    k.mx = kMaxInit;
-    if (vv) {
-      if constexpr (Cfg::DSUM) k.dsum = Wide<VC>::as_double(vbits);
-      if (!Wide<VC>::is_nan(vbits)) { k.mn = Wide<VC>::ord(vbits); k.mx = k.mn; }
-    }
-  }
+  if constexpr (Cfg::DSUM) k.dsum = vv ? Wide<VC>::as_double(vbits) : 0.0;
   if (losers) {
     if ((losers & (losers - 1u)) == 0u) {
       // exactly one losing lane: its group has two members, a + b is commutative
       const int L = __ffs(losers) - 1;
       const uint32_t tw = __shfl_sync(FULL, tag, L);
-      const LcContrib<WIDE> o = lc_shfl<VC, WIDE>(k, L);
+      const LcContrib<Cfg::DSUM> o = lc_shfl<VC, Cfg::DSUM>(k, L);
       if (lane == tw) {
-        lc_add<VC, WIDE>(k, o);
+        lc_add<VC, Cfg::DSUM>(k, o);
         k.lo = static_cast<uint32_t>(L) < lane ? static_cast<uint32_t>(L) : lane;
-        k.hi = static_cast<uint32_t>(L) > lane ? static_cast<uint32_t>(L) : lane;
       }
     } else {
-      k = lc_fold_general<VC, WIDE>(k, id, tag, live, losers);
+      k = lc_fold_general<VC, Cfg::DSUM>(k, id, tag, live, losers);
     }
   }
-  // one non-atomic read-modify-write per distinct id
+  // one non-atomic read-modify-write per distinct slot
   if (k.doer) {
     const uint32_t old = cw & LC_CNT_MASK;
-    const bool first_seen = old == LC_CNT_MASK;   // first time this warp meets the id
+    const bool first_seen = old == LC_CNT_MASK;   // first time this warp meets the slot
     if constexpr (VC == VC_F) {
       s = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(s)) +
                                                      __longlong_as_double(static_cast<long long>(k.sum))));
@@ -429,25 +430,11 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
     }
     sts64(sum_addr, s);
     sts32(cw_addr, (first_seen ? 0u : old) + k.cnt);   // also clears the claim tag
-    if constexpr (WIDE) {
-      sts32(c.last + id * 4u, row + k.hi - lane);
-      const uint32_t mslot = c.mm + id * 16u;
-      const uint4 m4 = lds128(mslot);
-      const uint64_t mn = static_cast<uint64_t>(m4.x) | (static_cast<uint64_t>(m4.y) << 32);
-      const uint64_t mx = static_cast<uint64_t>(m4.z) | (static_cast<uint64_t>(m4.w) << 32);
-      if (k.mn < mn || k.mx > mx) {
-        const uint64_t nn = k.mn < mn ? k.mn : mn, nx = k.mx > mx ? k.mx : mx;
-        sts128(mslot, static_cast<uint32_t>(nn), static_cast<uint32_t>(nn >> 32), static_cast<uint32_t>(nx), static_cast<uint32_t>(nx >> 32));
-      }
-      if constexpr (Cfg::DSUM) {
-        const uint32_t da = c.dsum + id * 8u;
-        sts64(da, static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(lds64(da))) + k.dsum)));
-      }
+    if constexpr (Cfg::DSUM) {
+      const uint32_t da = c.dsum + id * 8u;
+      sts64(da, static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(lds64(da))) + k.dsum)));
     }
-    if (first_seen) {   // candidate for the CTA's first row (cta_first is indexed by group id, not by slot)
-      const uint32_t gid = (DENSE && id < static_cast<uint32_t>(Cfg::GMAX)) ? (id >> c.rlog) : id;
-      atomicMin(c.cta_first + gid, row + k.lo - lane);
-    }
+    if (first_seen) atomicMin(c.cta_first + gid, row + k.lo - lane);   // candidate for the CTA's first row
   }
   __syncwarp();
 }
@@ -572,7 +559,7 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
     const uint32_t row = static_cast<uint32_t>(g0) + e * 32 + lane;
     constexpr bool ACLEAN = CLEAN && DENSE;   // (hash mode may leave LC_NOID in a lane after an overflow)
     const bool vvalid = CLEAN ? true : ((b.vv >> e) & 1u) != 0;
-    lc_accumulate<VC, WIDE, ACLEAN, DENSE>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, c);
+    lc_accumulate<VC, WIDE, ACLEAN, DENSE>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, a.agg_mask, c);
   }
   return true;
 }
@@ -636,11 +623,12 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   c.cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
   unsigned char* my_acc = smem + L::OFF_ACC + L::ACC_PER_WARP * warp;
   const uint32_t acc_s = smem_u32(my_acc);
-  c.mm = acc_s + static_cast<uint32_t>(L::W_MM);
   c.sum = acc_s + static_cast<uint32_t>(L::W_SUM);
   c.dsum = acc_s + static_cast<uint32_t>(L::W_DSUM);
   c.cw = acc_s + static_cast<uint32_t>(L::W_CW);
-  c.last = acc_s + static_cast<uint32_t>(L::W_LAST);
+  c.mm_p = reinterpret_cast<unsigned long long*>(smem + L::OFF_MM);
+  c.mm = smem_u32(c.mm_p);
+  c.last_p = reinterpret_cast<uint32_t*>(smem + L::OFF_LAST);
   const bool dense = lc_dense_mode(a.dir.prep, a.force_hash, Cfg::GMAX, &c.base, &c.window, &c.rlog);
   c.rmask = (1u << c.rlog) - 1u;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -655,15 +643,18 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
       c.tids[i] = LC_ID_UNSET;
     }
   }
-  for (int i = threadIdx.x; i < Cfg::GP; i += Cfg::THREADS) c.cta_first[i] = kNoRow;
+  for (int i = threadIdx.x; i < Cfg::GP; i += Cfg::THREADS) {
+    c.cta_first[i] = kNoRow;
+    if constexpr (WIDE) {
+      c.mm_p[2 * i] = kMinInit;
+      c.mm_p[2 * i + 1] = kMaxInit;
+      c.last_p[i] = 0u;
+    }
+  }
   if (threadIdx.x < 4) c.misc[threadIdx.x] = 0;
   for (int i = lane; i < Cfg::GP; i += 32) {
     reinterpret_cast<uint64_t*>(my_acc + L::W_SUM)[i] = 0ull;
     reinterpret_cast<uint32_t*>(my_acc + L::W_CW)[i] = LC_CNT_MASK;
-    if constexpr (WIDE) {
-      reinterpret_cast<ulonglong2*>(my_acc + L::W_MM)[i] = make_ulonglong2(kMinInit, kMaxInit);
-      reinterpret_cast<uint32_t*>(my_acc + L::W_LAST)[i] = 0u;
-    }
     if constexpr (Cfg::DSUM) reinterpret_cast<double*>(my_acc + L::W_DSUM)[i] = 0.0;
   }
   __syncthreads();
@@ -682,8 +673,7 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   for (int id = threadIdx.x; id < Cfg::GP; id += Cfg::THREADS) {
     uint64_t sum = 0;
     double fsum = 0.0, dsum = 0.0;
-    uint32_t cnt = 0, last = 0;
-    uint64_t mn = kMinInit, mx = kMaxInit;
+    uint32_t cnt = 0;
     const bool regular = id < Cfg::GMAX;
     const uint32_t reps = regular ? nrep : 1u;
     if (!regular || static_cast<uint32_t>(id) < c.window) {
@@ -697,14 +687,7 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
           const uint64_t s = reinterpret_cast<const uint64_t*>(wa + L::W_SUM)[slot];
           if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(s));
           else sum += s;
-          if constexpr (WIDE) {
-            const uint32_t l = reinterpret_cast<const uint32_t*>(wa + L::W_LAST)[slot];
-            last = l > last ? l : last;
-            const ulonglong2 mm = reinterpret_cast<const ulonglong2*>(wa + L::W_MM)[slot];
-            mn = mm.x < mn ? mm.x : mn;
-            mx = mm.y > mx ? mm.y : mx;
-            if constexpr (Cfg::DSUM) dsum += reinterpret_cast<const double*>(wa + L::W_DSUM)[slot];
-          }
+          if constexpr (Cfg::DSUM) dsum += reinterpret_cast<const double*>(wa + L::W_DSUM)[slot];
         }
       }
     }
@@ -713,9 +696,9 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
     a.p_count[pbase + id] = cnt;
     a.p_first[pbase + id] = c.cta_first[id];
     if constexpr (WIDE) {
-      a.p_last[pbase + id] = last;
-      a.p_min[pbase + id] = mn;
-      a.p_max[pbase + id] = mx;
+      a.p_last[pbase + id] = c.last_p[id];
+      a.p_min[pbase + id] = c.mm_p[2 * id];
+      a.p_max[pbase + id] = c.mm_p[2 * id + 1];
       if constexpr (Cfg::DSUM) a.p_dsum[pbase + id] = dsum;
     }
   }

@@ -271,9 +271,8 @@ def test_lowcard_dense_windows_and_hash_mode(pab, orc, no_dense, G, lo):
     assert t["path"] == "lowcard" and t["mode"] == ("hash" if no_dense else "dense") and t["passes"] == 1
     if not no_dense and G == 16:
         assert t["replication"] == 32          # every lane owns its accumulator slots
-    if G <= 600:
-        _cmp(gb, ora, rb, "v", ALL, f"G={G} lo={lo} no_dense={no_dense} all")
-        assert gb.timing()["path"] == "lowcard"
+    _cmp(gb, ora, rb, "v", ALL, f"G={G} lo={lo} no_dense={no_dense} all")
+    assert gb.timing()["path"] == "lowcard"
 
 
 def test_lowcard_scattered_64bit_keys_use_hash_mode(pab, orc):
@@ -304,8 +303,8 @@ def test_lowcard_dense_miss_reruns_in_hash_mode(pab, orc):
 
 
 @pytest.mark.parametrize("G,aggs,path", [(1024, ["sum", "mean", "count"], "lowcard"), (1025, ["sum", "count"], "global"),
-                                         (640, ["sum", "min", "max", "last"], "lowcard"), (641, ["min", "max"], "global"),
-                                         (2000, ["sum", "mean"], "global")])
+                                         (1024, ["sum", "min", "max", "last"], "lowcard"), (1025, ["min", "max"], "global"),
+                                         (2000, ["sum", "mean"], "global"), (5000, ALL, "global")])
 def test_lowcard_capacity_boundaries(pab, orc, G, aggs, path):
     rng = np.random.default_rng(G)
     n = 300_000
@@ -315,3 +314,17 @@ def test_lowcard_capacity_boundaries(pab, orc, G, aggs, path):
     _cmp(gb, ora, rb, "v", aggs, f"G={G} {aggs}")
     assert gb.timing()["path"] == path
     assert gb.groupSize() == G
+
+
+def test_int_values_mean_boundary_and_smem_front(pab, orc):
+    # mean of integers needs the per-warp double sum: 640 groups on the shared-memory path, beyond that the
+    # global path with its shared-memory front table (and, past its capacity, spills to the global table)
+    rng = np.random.default_rng(41)
+    n = 400_000
+    for G, path, mode in [(640, "lowcard", "dense"), (700, "global", "smem-front"), (9000, "global", "smem-front")]:
+        k = np.concatenate([np.arange(G), rng.integers(0, G, n - G)])
+        frame = {"k": pa.array(k, pa.int64()), "v": pa.array(rng.integers(-1000, 1000, n), pa.int64(), mask=rng.random(n) < 0.05)}
+        gb, ora, rb = _both(pab, orc, frame, "k")
+        _cmp(gb, ora, rb, "v", ALL, f"int values G={G}")
+        t = gb.timing()
+        assert t["path"] == path and t["mode"] == mode, t
