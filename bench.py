@@ -96,6 +96,16 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(kernel: str, n_rows: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json); scaled linearly when the capture used another row count."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (n_rows / t["rows"])
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(n_rows: int, n_groups: int, n_aggs: int) -> float:
     # SURVEY §8d: 16 B/row in (int64 key + fp64 value) + G x (8 B key + 8 B per aggregate) out
     return 16.0 * n_rows + n_groups * (8.0 + 8.0 * n_aggs)
@@ -248,8 +258,9 @@ def main():
     peak, peak_src = peaks()
     alg = algorithmic_bytes(n, n_groups_found, len(AGGS))
     achieved = alg / (scan * 1e-3) / 1e9
+    kernel = "k_lowcard_scan" if path == "lowcard" else "k_gtable_scan"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_lowcard_scan" if path == "lowcard" else "k_gtable_scan",
+                "traffic": measured_traffic(kernel, n), "kernel": kernel,
                 "kernel_ms": scan, "algorithmic_bytes": alg, "peak_source": peak_src,
                 "frac_of_step": scan / ms_per_step}
 
