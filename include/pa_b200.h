@@ -114,7 +114,8 @@ typedef struct pa_options {
   void* cuda_stream;         /* cudaStream_t to run on; NULL = a stream owned by the handle */
   int64_t row_base;          /* global row number of local row 0 (multi-GPU row-range shards) */
   int64_t lowcard_no_dense;  /* 1 = the shared-memory path never uses dense (key - base) addressing, always hashes */
-  int64_t reserved[3];
+  int64_t no_partition;      /* 1 = never reorder the rows by table region before a global-table scan (>= 2 M groups) */
+  int64_t reserved[2];
 } pa_options;
 
 typedef struct pa_groupby pa_groupby;      /* opaque: key columns + device group table */
@@ -167,7 +168,8 @@ int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]);
  * library's kernels it launched. */
 int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches);
 /* More about the last aggregate call: detail[0] = mode (0 n/a; shared-memory path: 1 dense key - base
- * addressing, 2 hash table; global path: 3 = shared-memory front table with spill), detail[1] = log2 of the accumulator replication (dense mode),
+ * addressing, 2 hash table; global path: 3 = shared-memory front table with spill,
+ * 4 = rows radix-partitioned by table region first, detail[1] = log2(partitions)), detail[1] = log2 of the accumulator replication (dense mode),
  * detail[2] = scan passes run (2 = a dense pass met a key outside its window and was rerun in hash
  * mode; +1 when the shared-memory tables overflowed and the global-table path ran), detail[3] = 0. */
 int pa_groupby_last_detail(pa_groupby* g, int32_t detail[4]);

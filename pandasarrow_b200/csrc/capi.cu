@@ -18,6 +18,7 @@
 #include "gtable.cuh"
 #include "lowcard.cuh"
 #include "merge.cuh"
+#include "partition.cuh"
 #include "resample.cuh"
 
 using namespace pa;
@@ -409,6 +410,41 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, grid_full)));
     const bool fast = a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid && !a.vvalid &&
                       reinterpret_cast<uintptr_t>(a.keys) % 16 == 0 && reinterpret_cast<uintptr_t>(a.vals) % 16 == 0;
+    // Very many groups (table far larger than L2): reorder the rows by table region first (partition.cuh).
+    DevBuf p_keys, p_vals, p_rows, p_counts;
+    const uint64_t known_g = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
+    if (fast && a.vals && known_g >= (2ull << 20) && g->n >= (1ll << 22) && !g->opt.no_partition) {
+      const uint64_t table_bytes = nslots * sizeof(SlotT);
+      int log_parts = 6;
+      while (log_parts < 10 && (table_bytes >> log_parts) > (16ull << 20)) ++log_parts;
+      const int parts = 1 << log_parts;
+      PA_TRY(p_keys.alloc(static_cast<size_t>(g->n) * 8, st));
+      PA_TRY(p_vals.alloc(static_cast<size_t>(g->n) * 8, st));
+      PA_TRY(p_rows.alloc(static_cast<size_t>(g->n) * 4, st));
+      PA_TRY(p_counts.alloc(sizeof(unsigned long long) * parts, st));
+      CUDA_TRY(cudaMemsetAsync(p_counts.p, 0, sizeof(unsigned long long) * parts, st));
+      PartArgs pa_{};
+      pa_.keys = static_cast<const uint64_t*>(a.keys);
+      pa_.vals = static_cast<const uint64_t*>(a.vals);
+      pa_.n = g->n;
+      pa_.log_parts = log_parts;
+      pa_.counts = p_counts.as<unsigned long long>();
+      pa_.out_keys = p_keys.as<uint64_t>();
+      pa_.out_vals = p_vals.as<uint64_t>();
+      pa_.out_rows = p_rows.as<uint32_t>();
+      k_part_hist<<<g->num_sms * 2, PT_THREADS, 0, st>>>(pa_);
+      CUDA_TRY(cudaGetLastError());
+      k_part_offsets<<<1, PT_MAX_PARTS, 0, st>>>(pa_.counts, parts);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(PtSmem::TOTAL)));
+      k_part_scatter<<<g->num_sms, PT_THREADS, PtSmem::TOTAL, st>>>(pa_);
+      CUDA_TRY(cudaGetLastError());
+      g->last_launches += 3;
+      a.keys = p_keys.p;
+      a.vals = p_vals.p;
+      a.rowids = p_rows.as<uint32_t>();
+      g->last_rlog = log_parts;   // reported through pa_groupby_last_detail[1] on this path
+    }
     // Shared-memory front table unless the caller (or an earlier pass on this handle) says there are
     // far more groups than it holds; it spills to the global table, so it is correct for any input.
     const uint64_t known = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
@@ -423,7 +459,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     } else {
       k_gtable_scan<VC, WIDE, false><<<grid, 256, 0, st>>>(a);
     }
-    g->last_mode = front ? 3 : 0;
+    g->last_mode = front ? 3 : (a.rowids ? 4 : 0);
     CUDA_TRY(cudaGetLastError());
     g->last_launches += 2;
     uint32_t h_status[ST_WORDS];

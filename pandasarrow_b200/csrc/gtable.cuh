@@ -46,6 +46,7 @@ struct GScanArgs {
   const void* vals;        // value column (already offset), width vw bytes; may be null (keys only)
   const uint8_t* kvalid;   // key validity bitmap or null
   const uint8_t* vvalid;   // value validity bitmap or null
+  const uint32_t* rowids;  // partitioned input: original row number of every (permuted) row, or null
   int64_t koff, voff;      // bit offsets into the bitmaps
   int64_t n;
   int kw, vw;
@@ -187,6 +188,10 @@ __device__ __forceinline__ void gtile_load(const GScanArgs& a, int64_t tile0, in
       r.key[2 * h] = k2.x; r.key[2 * h + 1] = k2.y;
       r.vb[2 * h] = v2.x; r.vb[2 * h + 1] = v2.y;
       r.row[2 * h] = r0; r.row[2 * h + 1] = r0 + 1;
+      if (a.rowids) {
+        const uint2 ri = *reinterpret_cast<const uint2*>(a.rowids + r0);
+        r.row[2 * h] = ri.x; r.row[2 * h + 1] = ri.y;
+      }
       r.act[2 * h] = r.act[2 * h + 1] = true;
       r.kv[2 * h] = r.kv[2 * h + 1] = true;
       r.vv[2 * h] = r.vv[2 * h + 1] = a.vals != nullptr;
@@ -197,6 +202,7 @@ __device__ __forceinline__ void gtile_load(const GScanArgs& a, int64_t tile0, in
       const int64_t i = tile0 + threadIdx.x + static_cast<int64_t>(j) * blockDim.x;
       r.row[j] = i;
       r.act[j] = i < a.n;
+      if (a.rowids && r.act[j]) r.row[j] = a.rowids[i];
       r.key[j] = 0; r.vb[j] = 0; r.kv[j] = true; r.vv[j] = false;
       if (r.act[j]) {
         r.key[j] = load_key_rt(a.keys, i, a.kw);

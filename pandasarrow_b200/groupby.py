@@ -109,13 +109,15 @@ def _import(out_a, out_s) -> pa.Array:
     return pa.Array._import_from_c(C.addressof(out_a), C.addressof(out_s))
 
 
-def _options(expected_groups=0, path="auto", device=None, stream=None, row_base=0, no_dense=False) -> PaOptions:
+def _options(expected_groups=0, path="auto", device=None, stream=None, row_base=0, no_dense=False,
+             no_partition=False) -> PaOptions:
     o = PaOptions()
     _lib.load().pa_options_init(C.byref(o))
     o.expected_groups = int(expected_groups)
     o.row_base = int(row_base)
     o.path = _PATHS[path]
     o.lowcard_no_dense = 1 if no_dense else 0
+    o.no_partition = 1 if no_partition else 0
     if device is not None:
         o.device = int(device)
     if stream is not None:
@@ -135,7 +137,7 @@ class GroupBy:
 
     def __init__(self, key, frame=None, *, key_arrays: Optional[Sequence[Column]] = None, expected_groups: int = 0,
                  path: str = "auto", device: Optional[int] = None, stream: Optional[int] = None, row_base: int = 0,
-                 no_dense: bool = False, _handle=None):
+                 no_dense: bool = False, no_partition: bool = False, _handle=None):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self._frame = self._as_dict(frame)
@@ -154,7 +156,7 @@ class GroupBy:
         key_arrays = [self._normalise_key(k) for k in key_arrays]
         args, devs, schemas = _pack_args(key_arrays)
         self._key_args = args          # keys are borrowed until destroy
-        opt = _options(expected_groups, path, device, stream, row_base, no_dense)
+        opt = _options(expected_groups, path, device, stream, row_base, no_dense, no_partition)
         try:
             _check(self._L.pa_groupby_create(devs, schemas, len(args), C.byref(opt), C.byref(self._h)))
         except Exception:
@@ -267,7 +269,7 @@ class GroupBy:
         _check(self._L.pa_groupby_last_detail(self._h, det))
         return {"total_ms": total.value, "pack_ms": st[0], "scan_ms": st[1], "merge_ms": st[2], "emit_ms": st[3],
                 "path": {1: "lowcard", 2: "global", 3: "resample"}.get(path.value, "?"), "launches": launches.value,
-                "mode": {0: None, 1: "dense", 2: "hash", 3: "smem-front"}.get(det[0]), "replication": 1 << det[1], "passes": det[2]}
+                "mode": {0: None, 1: "dense", 2: "hash", 3: "smem-front", 4: "partitioned"}.get(det[0]), "replication": 1 << det[1], "passes": det[2]}
 
     # ---- the reference's method surface (group_by.h:85-139): name -> array, [names] -> {name: array} ----
     def _agg(self, agg: str, arg):

@@ -12,6 +12,7 @@ ap.add_argument("--aggs", default="sum,mean,count")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--path", default="auto")
 ap.add_argument("--hint", type=int, default=0)
+ap.add_argument("--no-partition", action="store_true")
 ap.add_argument("--hashed", action="store_true", help="scramble the dense key ids into random-looking 64-bit keys")
 a = ap.parse_args()
 n = a.rows
@@ -23,7 +24,7 @@ if a.hashed:   # bijective scramble: multiply, xor with a logical right shift, m
     k.mul_(-4658895280553007687)
 torch.cuda.synchronize()
 dk, dv = pab.DeviceColumn.from_torch(k), pab.DeviceColumn.from_torch(v)
-g = pab.GroupBy("k", {"k": dk, "v": dv}, path=a.path, expected_groups=a.hint)
+g = pab.GroupBy("k", {"k": dk, "v": dv}, path=a.path, expected_groups=a.hint, no_partition=a.no_partition)
 for i in range(a.iters):
     g.aggregate(dv, a.aggs.split(","), fetch=False)
     t = g.timing()

@@ -328,3 +328,25 @@ def test_int_values_mean_boundary_and_smem_front(pab, orc):
         _cmp(gb, ora, rb, "v", ALL, f"int values G={G}")
         t = gb.timing()
         assert t["path"] == path and t["mode"] == mode, t
+
+
+def test_partitioned_high_cardinality_equals_direct_scan(pab):
+    # >= 2 M expected groups: rows are radix-partitioned by table region first (partition.cuh).  The oracle
+    # needs ~5 us per group and aggregate, so at this size the partitioned pass is checked against the
+    # direct global-table scan (itself oracle-checked above at up to 250 K groups).
+    import torch
+    from util import assert_exact, assert_fp_close
+    n, G = 6_000_001, 2_500_000
+    k = torch.empty(n, dtype=torch.int64, device="cuda"); v = torch.empty(n, dtype=torch.float64, device="cuda")
+    pab.synth.keys(k, G); pab.synth.vals(v)
+    k.mul_(7919).add_(-(10**9))                       # not dense, negative keys too
+    torch.cuda.synchronize()
+    dk, dv = pab.DeviceColumn.from_torch(k), pab.DeviceColumn.from_torch(v)
+    a = pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=G)
+    b = pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=G, no_partition=True)
+    ra, rb_ = a.aggregate(dv, ALL), b.aggregate(dv, ALL)
+    assert a.timing()["mode"] == "partitioned" and b.timing()["mode"] is None
+    assert a.groupSize() == b.groupSize() and a.unique().equals(b.unique())      # same groups, same first-appearance order
+    for name in ALL:
+        (assert_fp_close if name in ("sum", "mean") else assert_exact)(ra[name], rb_[name], name)
+    assert sum(ra["count"].to_pylist()) == n
