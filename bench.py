@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--sweep", action="store_true", help="also run the config-2 cardinality sweep (device resident)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-rows", type=int, default=10_000_000, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=100_000_000, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--extras", action="store_true", help="also time config 3 (multi-key, nullable) and config 4 (resample OHLC)")
     return ap.parse_args()
 
 
@@ -274,7 +275,7 @@ def main():
             pab.synth.keys(keys, g_, first_row)
             torch.cuda.synchronize()
             h = pab.GroupBy("k", {"k": dk, "v": dv}, stream=stream.cuda_stream, device=local, expected_groups=g_)
-            for _ in range(2):
+            for _ in range(3):
                 h.aggregate(dv, SWEEP_AGGS, fetch=False)
             ts = []
             for _ in range(3):
@@ -289,6 +290,57 @@ def main():
             h.close()
         pab.synth.keys(keys, G, first_row)
         torch.cuda.synchronize()
+
+    # ---------------- optional: configs 3 and 4, device resident ----------------
+    extras = None
+    if args.extras and rank == 0:
+        extras = {}
+        try:
+            # config 4: sorted timestamp[ns] index, 1-minute buckets (~1000 ticks each), OHLC + sum
+            ts = torch.empty(n, dtype=torch.int64, device=dev)
+            pab.synth.timestamps(ts)
+            torch.cuda.synchronize()
+            dts = pab.DeviceColumn.from_torch(ts, fmt="tsn:")
+            r = pab.resample({"v": dv}, dts, 60 * 10**9, stream=stream.cuda_stream, device=local)
+            tl = []
+            for _ in range(4):                                     # warm-up: stream-ordered pool growth
+                r.aggregate(dv, ["first", "max", "min", "last", "sum"], fetch=False)
+            for _ in range(5):
+                r.aggregate(dv, ["first", "max", "min", "last", "sum"], fetch=False)
+                tl.append(r.timing())
+            tl.sort(key=lambda t: t["total_ms"])
+            t = tl[len(tl) // 2]
+            extras["resample_ohlc_sum"] = {"rows": n, "buckets": r.groupSize(), "total_ms": t["total_ms"], "scan_ms": t["scan_ms"],
+                                           "rows_per_s": n / (t["total_ms"] * 1e-3), "scan_GBps": 16.0 * n / (t["scan_ms"] * 1e-3) / 1e9,
+                                           "frac": 16.0 * n / (t["scan_ms"] * 1e-3) / 1e9 / peak}
+            r.close(); del ts, dts
+            # config 3: int32 key (1 K values) x int32 dictionary indices (64 symbols) packed into one 64-bit key,
+            # nullable fp64 value (10 % nulls)
+            m = min(n, 500_000_000)
+            k1 = torch.empty(m, dtype=torch.int64, device=dev); pab.synth.keys(k1, 1000, 0)
+            k2 = torch.empty(m, dtype=torch.int64, device=dev); pab.synth.keys(k2, 64, 12345)
+            k1i, k2i = k1.to(torch.int32), k2.to(torch.int32)
+            del k1, k2
+            bits = torch.empty((m + 7) // 8, dtype=torch.uint8, device=dev)
+            pab.synth.validity(bits, m)
+            torch.cuda.synchronize()
+            c1 = pab.DeviceColumn.from_torch(k1i)
+            c2 = pab.DeviceColumn.from_torch(k2i)          # (the int32 indices of a dictionary column are what the kernels see)
+            cv = pab.DeviceColumn.from_torch(vals[:m], valid=bits, null_count=-1)
+            h = pab.GroupBy(["k1", "k2"], {"k1": c1, "k2": c2, "v": cv}, stream=stream.cuda_stream, device=local, expected_groups=64000)
+            tl = []
+            for _ in range(3):
+                h.aggregate(cv, ["sum", "mean", "count", "min", "max"], fetch=False)
+            for _ in range(4):
+                h.aggregate(cv, ["sum", "mean", "count", "min", "max"], fetch=False)
+                tl.append(h.timing())
+            tl.sort(key=lambda t: t["total_ms"])
+            t = tl[len(tl) // 2]
+            extras["multikey_nullable"] = {"rows": m, "groups": h.groupSize(), "path": t["path"], "total_ms": t["total_ms"],
+                                           "pack_ms": t["pack_ms"], "scan_ms": t["scan_ms"], "rows_per_s": m / (t["total_ms"] * 1e-3)}
+            h.close()
+        except Exception as ex:  # noqa: BLE001
+            extras["error"] = repr(ex)[:300]
 
     # ---------------- end to end through the C ABI with HOST buffers (`e2e`) ----------------
     e2e = None
@@ -344,6 +396,8 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         if sweep is not None:
             line["sweep"] = sweep
+        if extras is not None:
+            line["extras"] = extras
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

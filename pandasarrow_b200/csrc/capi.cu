@@ -408,12 +408,12 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     a.agg_mask = mask;
     const int64_t ntiles = (g->n + 1023) / 1024;
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, grid_full)));
-    const bool fast = a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid && !a.vvalid &&
+    const bool fast = a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid &&
                       reinterpret_cast<uintptr_t>(a.keys) % 16 == 0 && reinterpret_cast<uintptr_t>(a.vals) % 16 == 0;
     // Very many groups (table far larger than L2): reorder the rows by table region first (partition.cuh).
     DevBuf p_keys, p_vals, p_rows, p_counts;
     const uint64_t known_g = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
-    if (fast && a.vals && known_g >= (2ull << 20) && g->n >= (1ll << 22) && !g->opt.no_partition) {
+    if (fast && a.vals && !a.vvalid && known_g >= (2ull << 20) && g->n >= (1ll << 22) && !g->opt.no_partition) {
       const uint64_t table_bytes = nslots * sizeof(SlotT);
       int log_parts = 6;
       while (log_parts < 10 && (table_bytes >> log_parts) > (16ull << 20)) ++log_parts;

@@ -166,7 +166,8 @@ __device__ __forceinline__ void gtable_accumulate(typename SlotOf<WIDE>::type* s
 
 constexpr int GT_R = 4;   // rows per thread per tile
 
-// Rows of one tile for this thread.  FAST: 8-byte keys and values, no validity bitmaps: thread t takes
+// Rows of one tile for this thread.  FAST: 8-byte non-null keys and 8-byte values (a value validity bitmap
+// is allowed): thread t takes
 // the adjacent rows 2t, 2t+1 (128-bit non-allocating loads) — row order is irrelevant on this path,
 // first/last rows are atomicMin/Max.
 struct GRows {
@@ -195,6 +196,12 @@ __device__ __forceinline__ void gtile_load(const GScanArgs& a, int64_t tile0, in
       r.act[2 * h] = r.act[2 * h + 1] = true;
       r.kv[2 * h] = r.kv[2 * h + 1] = true;
       r.vv[2 * h] = r.vv[2 * h + 1] = a.vals != nullptr;
+      if (a.vvalid && !a.rowids) {   // value validity: the two adjacent bits of this thread's row pair
+        const int64_t b0 = a.voff + r0;
+        const uint32_t w = static_cast<uint32_t>(a.vvalid[b0 >> 3]) | (static_cast<uint32_t>(a.vvalid[(b0 + 1) >> 3]) << 8);
+        r.vv[2 * h] = (w >> (b0 & 7)) & 1u;
+        r.vv[2 * h + 1] = (w >> (((b0 + 1) & 7) + (((b0 + 1) >> 3) != (b0 >> 3) ? 8 : 0))) & 1u;
+      }
     }
   } else {
 #pragma unroll
