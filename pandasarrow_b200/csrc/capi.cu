@@ -20,6 +20,7 @@
 #include "merge.cuh"
 #include "partition.cuh"
 #include "resample.cuh"
+#include "rowids.cuh"
 
 using namespace pa;
 
@@ -448,8 +449,15 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     // Shared-memory front table unless the caller (or an earlier pass on this handle) says there are
     // far more groups than it holds; it spills to the global table, so it is correct for any input.
     const uint64_t known = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
-    const bool front = known <= static_cast<uint64_t>(SmTab<VC, WIDE>::MAX_KEYS);
+    const bool front = known <= static_cast<uint64_t>(SmTab<VC, WIDE>::CAP);   // (dense keys fill every slot; hashed keys 3/4)
+    DevBuf krange;
     if (front) {
+      PA_TRY(krange.alloc(sizeof(KeyRange), st));
+      CUDA_TRY(cudaMemsetAsync(krange.p, 0, sizeof(KeyRange), st));
+      a.krange = krange.as<KeyRange>();
+      k_key_range<<<SM_SAMPLE_GRID, 256, 0, st>>>(a);
+      CUDA_TRY(cudaGetLastError());
+      g->last_launches += 1;
       auto kern = fast ? k_smemtab_scan<VC, WIDE, true> : k_smemtab_scan<VC, WIDE, false>;
       const size_t smem = SmTab<VC, WIDE>::TOTAL;
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -988,8 +996,49 @@ int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, st
 }
 
 int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema) {
-  (void)g; (void)out; (void)out_schema;
-  return set_err(PA_ERR_NOT_IMPLEMENTED, "pa_groupby_row_ids: group materialisation is a SURVEY §8(f) 'next' row");
+  if (!g || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
+  if (g->merged) return set_err(PA_ERR_STATE, "row ids exist on the rank that holds the rows, not on a merged handle");
+  PA_TRY(ensure_groups(g));
+  PA_TRY(ensure_device(g));
+  cudaStream_t st = g->stream;
+  const uint32_t G = g->G;
+  uint64_t cap = 1024;
+  while (cap < static_cast<uint64_t>(G) * 2) cap <<= 1;
+  DevBuf tkeys, tranks, special, ids;
+  PA_TRY(tkeys.alloc(cap * 8, st));
+  PA_TRY(tranks.alloc(cap * 4, st));
+  PA_TRY(special.alloc(8, st));
+  PA_TRY(ids.alloc(static_cast<size_t>(std::max<int64_t>(g->n, 1)) * 4, st));
+  const int fgrid = static_cast<int>(std::min<uint64_t>((cap + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+  k_fill_u64<<<fgrid, 256, 0, st>>>(tkeys.as<unsigned long long>(), cap, kEmptyKey);
+  CUDA_TRY(cudaMemsetAsync(special.p, 0xFF, 8, st));
+  RowIdArgs a{};
+  a.tkeys = tkeys.as<unsigned long long>();
+  a.tranks = tranks.as<uint32_t>();
+  a.cap_mask = cap - 1;
+  a.shift = 64 - __builtin_ctzll(cap);
+  a.special = special.as<uint32_t>();
+  a.gkey = g->res.key;
+  a.gkind = g->res.key_kind;
+  a.G = G;
+  a.keys = g->key_data;
+  a.kvalid = g->key_valid;
+  a.koff = g->key_bit_off;
+  a.kw = g->key_width;
+  a.n = g->n;
+  a.resample = g->resample ? 1 : 0;
+  a.rs = g->rs;
+  a.out = ids.as<uint32_t>();
+  if (G) {
+    k_rowid_build<<<(G + 255) / 256, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (g->n) {
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+    k_rowid_scan<<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return export_host(st, "I", 4, static_cast<uint32_t>(g->n), ids.p, nullptr, out, out_schema);
 }
 
 int pa_groupby_first_rows(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema) {

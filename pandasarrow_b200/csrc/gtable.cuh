@@ -47,6 +47,7 @@ struct GScanArgs {
   const uint8_t* kvalid;   // key validity bitmap or null
   const uint8_t* vvalid;   // value validity bitmap or null
   const uint32_t* rowids;  // partitioned input: original row number of every (permuted) row, or null
+  KeyRange* krange;        // shared-memory front table: sampled key range (dense-mode decision), or null
   int64_t koff, voff;      // bit offsets into the bitmaps
   int64_t n;
   int kw, vw;
@@ -313,6 +314,11 @@ __global__ void __launch_bounds__(256, 3) k_gtable_scan(GScanArgs a) {
 // for the L2 path.
 // ---------------------------------------------------------------------------------------------
 constexpr int SM_THREADS = 768;
+constexpr int SM_SAMPLE_GRID = 64;   // x 256 threads = 16384 sampled keys
+
+__global__ void __launch_bounds__(256) k_key_range(GScanArgs a) {
+  key_range_sample(a.keys, a.kvalid, a.koff, a.kw, a.n, blockIdx.x * 256u + threadIdx.x, gridDim.x * 256u, a.krange);
+}
 constexpr int SM_MAX_PROBE = 16;
 
 template <int VC, bool WIDE>
@@ -362,6 +368,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_smemtab_scan(GScanArgs a) {
   }
   if (threadIdx.x < 4) s_misc[threadIdx.x] = 0u;
   __syncthreads();
+  // Dense mode (decided on the device from the key sample): the sampled keys span fewer values than the
+  // table has slots -> slot = key - base, no key array, no probing, every slot usable.  A key outside the
+  // window simply spills to the global table.
+  uint64_t base = 0, span = 0;
+  const bool dense = a.krange && key_range_get(a.krange, &base, &span) && span < static_cast<uint64_t>(T::CAP);
+  if (dense) base -= (static_cast<uint64_t>(T::CAP) - (span + 1)) / 2;   // centre the window on the sample
 
   constexpr int R = GT_R;
   const int64_t tile_rows = static_cast<int64_t>(SM_THREADS) * R;
@@ -380,6 +392,11 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_smemtab_scan(GScanArgs a) {
       uint32_t s;
       bool found = false;
       if (!r.kv[j]) { s = T::CAP; found = true; }
+      else if (dense) {
+        const uint64_t d = key - base;
+        s = static_cast<uint32_t>(d);
+        found = d < static_cast<uint64_t>(T::CAP);
+      }
       else if (key == kEmptyKey) { s = T::CAP + 1; found = true; }
       else {
         s = static_cast<uint32_t>(gtable_mix(key) >> (64 - T::CAP_LOG2));
@@ -429,11 +446,13 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_smemtab_scan(GScanArgs a) {
     uint64_t s;
     if (i == T::CAP) s = cap;
     else if (i == T::CAP + 1) s = cap + 1;
-    else s = gtable_home(s_key[i], a.shift);
+    uint64_t fkey = dense ? base + static_cast<uint64_t>(i) : s_key[i];
+    if (i < T::CAP && fkey == kEmptyKey) s = cap + 1;     // (dense window containing the sentinel value)
+    else if (i < T::CAP) s = gtable_home(fkey, a.shift);
     const Sector kf = gtable_peek<WIDE>(table, s, SLOT_LOG2);
     GProbe pr;
     if (s >= cap) pr = GProbe{s, static_cast<uint32_t>(kf.fl), static_cast<uint32_t>(kf.fl >> 32), kf.mn, kf.mx};
-    else pr = gtable_find_or_insert<WIDE>(table, a.cap_mask, SLOT_LOG2, s_key[i], s, kf);
+    else pr = gtable_find_or_insert<WIDE>(table, a.cap_mask, SLOT_LOG2, fkey, s, kf);
     if (pr.slot == ~0ull) { atomicExch(a.status + ST_OVERFLOW, 1u); return; }
     SlotT* g = table + pr.slot;
     if (first < pr.first) atomicMin(&g->first_row, first);

@@ -714,26 +714,7 @@ __global__ void __launch_bounds__(256) k_lowcard_prep(LcArgs a) {
     a.dir.gt_keys[i] = kEmptyKey;
     a.dir.gt_ids[i] = LC_GID_UNSET;
   }
-  uint64_t nmin = 0, mx = 0;
-  const int64_t r = a.n <= static_cast<int64_t>(nt) ? static_cast<int64_t>(t)
-                                                   : static_cast<int64_t>((static_cast<uint64_t>(t) * static_cast<uint64_t>(a.n)) / nt);
-  if (r < a.n && (!a.kvalid || bit_at(a.kvalid, a.koff + r))) {
-    const uint64_t key = a.kw == 8 ? static_cast<const uint64_t*>(a.keys)[r]
-                                   : static_cast<uint64_t>(static_cast<const uint32_t*>(a.keys)[r]);
-    const uint64_t o = key ^ 0x8000000000000000ull;
-    nmin = ~o;
-    mx = o;
-  }
-#pragma unroll
-  for (int d = 16; d; d >>= 1) {
-    const uint64_t on = __shfl_xor_sync(0xFFFFFFFFu, nmin, d), om = __shfl_xor_sync(0xFFFFFFFFu, mx, d);
-    nmin = on > nmin ? on : nmin;
-    mx = om > mx ? om : mx;
-  }
-  if (lane_id() == 0 && (nmin | mx)) {
-    atomicMax(&a.dir.prep->nmin_ord, static_cast<unsigned long long>(nmin));
-    atomicMax(&a.dir.prep->max_ord, static_cast<unsigned long long>(mx));
-  }
+  key_range_sample(a.keys, a.kvalid, a.koff, a.kw, a.n, t, nt, reinterpret_cast<KeyRange*>(a.dir.prep));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -247,6 +247,13 @@ class GroupBy:
     def sync(self):
         _check(self._L.pa_groupby_sync(self._h))
 
+    def row_ids(self) -> pa.Array:
+        """Grouper::Consume equivalent (dataframe.cpp:1584): uint32 group id of every row, ids numbered in
+        first-appearance order (= positions in unique())."""
+        out_a, out_s = ArrowArray(), ArrowSchema()
+        _check(self._L.pa_groupby_row_ids(self._h, C.byref(out_a), C.byref(out_s)))
+        return _import(out_a, out_s)
+
     # ---- multi-GPU: hash-partitioned partial aggregates (include/pa_b200.h, SURVEY §8e) ----
     def partials_count(self, n_parts: int) -> List[int]:
         counts = (C.c_int64 * n_parts)()

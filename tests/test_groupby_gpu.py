@@ -350,3 +350,42 @@ def test_partitioned_high_cardinality_equals_direct_scan(pab):
     for name in ALL:
         (assert_fp_close if name in ("sum", "mean") else assert_exact)(ra[name], rb_[name], name)
     assert sum(ra["count"].to_pylist()) == n
+
+
+# ---------------- Grouper::Consume equivalent: per-row group ids ----------------
+def _expected_ids(key_cols):
+    seen, ids = {}, []
+    for t in zip(*[c.to_pylist() for c in key_cols]):
+        ids.append(seen.setdefault(t, len(seen)))
+    return ids
+
+
+@pytest.mark.parametrize("G,path", [(7, "auto"), (900, "auto"), (5000, "auto"), (70_000, "global")])
+def test_row_ids_match_first_appearance_numbering(pab, G, path):
+    rng = np.random.default_rng(G)
+    n = 120_001
+    k = pa.array(rng.integers(-G // 2, G // 2 + 1, n), pa.int64(), mask=rng.random(n) < 0.01)
+    rb = pa.record_batch({"k": k, "v": pa.array(rng.random(n))})
+    g = pab.GroupBy("k", rb, path=path)
+    ids = g.row_ids()
+    assert ids.type == pa.uint32() and len(ids) == n
+    assert ids.to_pylist() == _expected_ids([k])
+    # ids index unique(): gather the keys back
+    assert g.unique().take(ids).equals(k)
+    g.sum("v")                                           # ids stay valid after an aggregate on the same handle
+    assert g.row_ids().equals(ids)
+
+
+def test_row_ids_composite_int32_and_resample(pab):
+    rng = np.random.default_rng(8)
+    n = 50_000
+    k1 = pa.array(rng.integers(0, 20, n).astype(np.int32), mask=rng.random(n) < 0.02)
+    k2 = pa.array(np.array(["a", "bb", "ccc"])[rng.integers(0, 3, n)]).dictionary_encode()
+    rb = pa.record_batch({"k1": k1, "k2": k2, "v": pa.array(rng.random(n))})
+    g = pab.GroupBy(["k1", "k2"], rb)
+    assert g.row_ids().to_pylist() == _expected_ids([k1, k2.indices])
+    ts = np.sort(rng.integers(0, 3600 * 10**9, n)) + 1_600_000_000 * 10**9
+    r = pab.resample({"v": rb.column("v")}, pa.array(ts, pa.timestamp("ns")), 60 * 10**9)
+    ids = np.asarray(r.row_ids())
+    labels = r.index().cast(pa.int64()).to_numpy()
+    assert (labels[ids] == (ts // (60 * 10**9)) * (60 * 10**9)).all()
