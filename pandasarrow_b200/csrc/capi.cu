@@ -261,15 +261,21 @@ enum LcOutcome { LC_DONE = 0, LC_DENSE_MISS = 1, LC_OVERFLOW = 2 };
 bool lc_is_wide(uint32_t mask, int vc) { return is_wide(mask, vc); }
 
 template <int VC, bool WIDE>
-int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast) {
+int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast, bool hash_kernel) {
   using L = LcSmem<VC, WIDE>;
   using Cfg = LcCfg<VC, WIDE>;
   cudaStream_t st = g->stream;
-  auto scan = fast ? k_lowcard_scan<VC, WIDE, true> : k_lowcard_scan<VC, WIDE, false>;
-  CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL)));
   k_lowcard_prep<<<LC_PREP_GRID, 256, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
-  scan<<<grid, Cfg::THREADS, L::TOTAL, st>>>(a);
+  if (hash_kernel) {
+    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, false> : k_lowcard_scan<VC, WIDE, false, false>;
+    CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL_HASH)));
+    scan<<<grid, Cfg::WARPS_HASH * 32, L::TOTAL_HASH, st>>>(a);
+  } else {
+    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, true> : k_lowcard_scan<VC, WIDE, false, true>;
+    CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL_DENSE)));
+    scan<<<grid, Cfg::WARPS * 32, L::TOTAL_DENSE, st>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(g->ev[2], st));
   k_lowcard_merge<VC, WIDE><<<(Cfg::GP + 7) / 8, 256, 0, st>>>(m);
@@ -351,13 +357,13 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   m.status = a.status;
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
   if (kwide) {
-    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, true>(g, a, m, grid, fast)));
-    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, true>(g, a, m, grid, fast)));
-    else PA_TRY((launch_lowcard_t<VC_U, true>(g, a, m, grid, fast)));
+    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, true>(g, a, m, grid, fast, force_hash)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, true>(g, a, m, grid, fast, force_hash)));
+    else PA_TRY((launch_lowcard_t<VC_U, true>(g, a, m, grid, fast, force_hash)));
   } else {
-    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, false>(g, a, m, grid, fast)));
-    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, false>(g, a, m, grid, fast)));
-    else PA_TRY((launch_lowcard_t<VC_U, false>(g, a, m, grid, fast)));
+    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, false>(g, a, m, grid, fast, force_hash)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, false>(g, a, m, grid, fast, force_hash)));
+    else PA_TRY((launch_lowcard_t<VC_U, false>(g, a, m, grid, fast, force_hash)));
   }
   CUDA_TRY(cudaEventRecord(g->ev[3], st));
   uint32_t h_status[ST_WORDS];
@@ -368,7 +374,7 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   else { *outcome = LC_DONE; g->G = h_status[ST_NGROUPS]; }
   g->last_mode = static_cast<int>(h_status[ST_MODE]);
   g->last_rlog = static_cast<int>(h_status[ST_RLOG]);
-  g->last_passes += 1;
+  if (h_status[ST_DENSE_MISS] != 2u) g->last_passes += 1;   // (2 = the dense kernel declined before scanning a row)
   return PA_OK;
 }
 

@@ -1,5 +1,6 @@
-// Low-cardinality path (stages 1-3 fused): one persistent CTA per SM (12 warps for the narrow
-// aggregates, 8 for the wide ones), accumulators privatised per warp in shared memory.
+// Low-cardinality path (stages 1-3 fused): one persistent CTA per SM, accumulators privatised per
+// warp in shared memory.  Two kernels: the dense-mode kernel (16 warps, no key table) and the
+// hash-mode kernel (12 warps + a 40 KB CTA-shared key table).
 //
 //  * Input: every warp streams "row groups" of 256 rows (8 batches of 32 rows) with coalesced
 //    non-allocating loads (256 contiguous bytes per warp per instruction); the next group is
@@ -8,10 +9,11 @@
 //    staged the rows through shared memory with bulk async copies; ncu showed the kernel bound by
 //    shared-memory wavefronts and instruction latency, so the staging traffic was removed —
 //    profiles/r1_lowcard_v3_*.)
-//  * Stage 1-2, key -> dense group id, two modes chosen ON THE DEVICE from a key-range sample taken
-//    by k_lowcard_prep (no host round trip):
+//  * Stage 1-2, key -> dense group id.  The dense kernel is launched first and decides ON THE DEVICE,
+//    from a key-range sample taken by k_lowcard_prep, whether it applies:
 //      dense : all sampled keys lie in a window of <= GMAX values -> id = key - base, no table at all.
-//              A key outside the window aborts the pass (ST_DENSE_MISS) and the host reruns in hash mode.
+//              Keys not dense (declined before the first row) or a key outside the window met later
+//              (ST_DENSE_MISS): the host launches the hash-mode kernel.
 //      hash  : CTA-shared open-addressing table in shared memory, 2048 buckets of two 8-byte keys:
 //              one LDS.128 + one LDS.U16 per lookup, read-only in steady state.  New keys take an
 //              out-of-line slow path (ATOMS.CAS.64) that also obtains a GLOBAL id for the key from a
@@ -66,8 +68,8 @@ constexpr int LC_PREP_GRID = 64;       // x 256 threads = 16384 sampled keys
 template <int VC, bool WIDE>
 struct LcCfg {
   static constexpr bool DSUM = WIDE && VC != VC_F;
-  static constexpr int WARPS = 12;
-  static constexpr int THREADS = WARPS * 32;
+  static constexpr int WARPS_HASH = 12;           // hash-mode kernel: the CTA-shared key table takes 40 KB
+  static constexpr int WARPS = 16;                // dense-mode kernel: its space holds four more warps' accumulators
   static constexpr int GMAX = WIDE ? (DSUM ? LC_GMAX_WIDE_I : LC_GMAX_WIDE_F) : LC_GMAX_NARROW;
   static constexpr int GP = GMAX + 2;             // + null-key group + (key == kEmptyKey) group
   static constexpr int ID_NULL = GMAX;
@@ -150,17 +152,20 @@ struct LcSmem {
   using Cfg = LcCfg<VC, WIDE>;
   static constexpr size_t GP = Cfg::GP;
   static constexpr size_t OFF_MISC = 0;                                          // 4 x u32
-  static constexpr size_t OFF_TKEYS = 16;                                        // LC_TCAP u64
-  static constexpr size_t OFF_TIDS = OFF_TKEYS + LC_TCAP * 8;                    // LC_TCAP u16
-  static constexpr size_t OFF_MM = OFF_TIDS + LC_TCAP * 2;                       // GP x {min, max} (wide)
+  static constexpr size_t OFF_MM = 16;                                           // GP x {min, max} (wide)
   static constexpr size_t OFF_FIRST = OFF_MM + (WIDE ? GP * 16 : 0);             // GP u32
   static constexpr size_t OFF_LAST = OFF_FIRST + GP * 4;                         // GP u32 (wide)
-  static constexpr size_t OFF_ACC = ((OFF_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;
+  static constexpr size_t OFF_TKEYS = ((OFF_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;   // LC_TCAP u64 (hash mode)
+  static constexpr size_t OFF_TIDS = OFF_TKEYS + LC_TCAP * 8;                    // LC_TCAP u16 (hash mode)
+  static constexpr size_t OFF_ACC_HASH = OFF_TIDS + LC_TCAP * 2;                 // per-warp accumulators, hash mode
+  static constexpr size_t OFF_ACC_DENSE = OFF_TKEYS;                             // dense mode: no table
   static constexpr size_t W_SUM = 0;
   static constexpr size_t W_DSUM = W_SUM + GP * 8;
   static constexpr size_t W_CW = W_DSUM + (Cfg::DSUM ? GP * 8 : 0);
   static constexpr size_t ACC_PER_WARP = ((W_CW + GP * 4 + 15) / 16) * 16;
-  static constexpr size_t TOTAL = OFF_ACC + ACC_PER_WARP * Cfg::WARPS;
+  static constexpr size_t TOTAL_HASH = OFF_ACC_HASH + ACC_PER_WARP * Cfg::WARPS_HASH;
+  static constexpr size_t TOTAL_DENSE = OFF_ACC_DENSE + ACC_PER_WARP * Cfg::WARPS;
+  static constexpr size_t TOTAL = TOTAL_HASH > TOTAL_DENSE ? TOTAL_HASH : TOTAL_DENSE;
 };
 
 // per-thread view of the CTA's shared state (32-bit shared-memory addresses for the hot arrays)
@@ -173,6 +178,7 @@ struct LcCtx {
   uint16_t* tids;
   uint32_t* cta_first;
   uint32_t* misc;                     // [1] abort seen by this CTA
+  int nwarps;                         // warps of the CTA that scan rows
   uint64_t base;                      // dense mode: id = key - base, must be < window
   uint32_t window, rlog, rmask;       // dense mode: accumulator replication (slot = id << rlog | lane & rmask)
 };
@@ -227,7 +233,7 @@ __device__ __noinline__ uint32_t lc_global_id(uint64_t key, LcDir d, uint32_t gm
 // inserts on first sight.  LC_NOID on overflow.
 __device__ __noinline__ uint32_t lc_miss_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
                                                  uint32_t* misc, LcDir d, uint32_t gmax, uint32_t* status) {
-  if (*reinterpret_cast<volatile uint32_t*>(misc + 1) || *reinterpret_cast<volatile uint32_t*>(status + ST_ABORT)) return LC_NOID;
+  if (*reinterpret_cast<volatile uint32_t*>(misc + 1)) return LC_NOID;   // this CTA already gave up
   uint32_t b = lc_bucket(key);
   for (int probe = 0; probe < 4 * LC_NBUCKET; ++probe) {
     const uint64_t k0 = *reinterpret_cast<volatile unsigned long long*>(tkeys + 2 * b);
@@ -539,9 +545,13 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
       for (int e = 0; e < LC_NB; ++e) {
         const bool m = (missmask >> e) & 1u;
         if (__any_sync(FULL, m)) {
-          if (m) {
-            const uint32_t id2 = lc_lookup(b.key[e], (lc_bucket(b.key[e]) + 1) & (LC_NBUCKET - 1), c.tkeys, c.tids);
-            if (id2 < LC_ID_OVF) { id[e] = id2; missmask &= ~(1u << e); }
+          if (m) {   // up to three more buckets inline; longer chains (and new keys) take the slow path
+            const uint32_t hb = lc_bucket(b.key[e]);
+#pragma unroll 1
+            for (uint32_t p = 1; p <= 3; ++p) {
+              const uint32_t id2 = lc_lookup(b.key[e], (hb + p) & (LC_NBUCKET - 1), c.tkeys, c.tids);
+              if (id2 < LC_ID_OVF) { id[e] = id2; missmask &= ~(1u << e); break; }
+            }
           }
         }
       }
@@ -567,8 +577,9 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
 template <int VC, bool WIDE, bool FAST, bool DENSE>
 __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, int warp, uint32_t lane) {
   using Cfg = LcCfg<VC, WIDE>;
-  const int64_t gw = static_cast<int64_t>(blockIdx.x) * Cfg::WARPS + warp;
-  const int64_t nw = static_cast<int64_t>(gridDim.x) * Cfg::WARPS;
+  if (warp >= c.nwarps) return;
+  const int64_t gw = static_cast<int64_t>(blockIdx.x) * c.nwarps + warp;
+  const int64_t nw = static_cast<int64_t>(gridDim.x) * c.nwarps;
   const int64_t n_full = a.n / LC_GROUP_ROWS;                        // full row groups
   const int64_t n_groups = (a.n + LC_GROUP_ROWS - 1) / LC_GROUP_ROWS;
   volatile uint32_t* abort_local = c.misc + 1;
@@ -609,10 +620,13 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
 }
 
 // FAST: int64/uint64 keys and 8-byte values, no validity bitmaps, 8-byte aligned columns.
-template <int VC, bool WIDE, bool FAST>
-__global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(LcArgs a) {
+// DENSEK: the dense-mode kernel (16 warps, no key table; when the key sample says the keys are not dense it
+// returns at once with ST_DENSE_MISS = 2 and the host launches the hash-mode kernel: 12 warps + key table).
+template <int VC, bool WIDE, bool FAST, bool DENSEK>
+__global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, WIDE>::WARPS_HASH) * 32, 1) k_lowcard_scan(LcArgs a) {
   using Cfg = LcCfg<VC, WIDE>;
   using L = LcSmem<VC, WIDE>;
+  constexpr int THREADS = (DENSEK ? Cfg::WARPS : Cfg::WARPS_HASH) * 32;
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -621,7 +635,17 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   c.tkeys = reinterpret_cast<unsigned long long*>(smem + L::OFF_TKEYS);
   c.tids = reinterpret_cast<uint16_t*>(smem + L::OFF_TIDS);
   c.cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
-  unsigned char* my_acc = smem + L::OFF_ACC + L::ACC_PER_WARP * warp;
+  const bool dense = lc_dense_mode(a.dir.prep, DENSEK ? 0 : 1, Cfg::GMAX, &c.base, &c.window, &c.rlog);
+  if (DENSEK && !dense) {   // not a dense key set: hand over to the hash-mode kernel
+    if (threadIdx.x == 0) { atomicExch(a.status + ST_DENSE_MISS, 2u); atomicExch(a.status + ST_ABORT, 1u); }
+    return;
+  }
+  // with many replicas per id (a handful of groups) the accesses are conflict free and 12 warps already
+  // saturate HBM; otherwise all 16 warps scan
+  const int nwarps = DENSEK ? (c.rlog >= 3 ? 12 : Cfg::WARPS) : Cfg::WARPS_HASH;
+  c.nwarps = nwarps;
+  const size_t off_acc = DENSEK ? L::OFF_ACC_DENSE : L::OFF_ACC_HASH;
+  unsigned char* my_acc = smem + off_acc + L::ACC_PER_WARP * (warp < nwarps ? warp : 0);
   const uint32_t acc_s = smem_u32(my_acc);
   c.sum = acc_s + static_cast<uint32_t>(L::W_SUM);
   c.dsum = acc_s + static_cast<uint32_t>(L::W_DSUM);
@@ -629,7 +653,6 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   c.mm_p = reinterpret_cast<unsigned long long*>(smem + L::OFF_MM);
   c.mm = smem_u32(c.mm_p);
   c.last_p = reinterpret_cast<uint32_t*>(smem + L::OFF_LAST);
-  const bool dense = lc_dense_mode(a.dir.prep, a.force_hash, Cfg::GMAX, &c.base, &c.window, &c.rlog);
   c.rmask = (1u << c.rlog) - 1u;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.status[ST_MODE] = dense ? 1u : 2u;
@@ -637,13 +660,13 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   }
 
   // ---- init shared state ----
-  if (!dense) {
-    for (int i = threadIdx.x; i < LC_TCAP; i += Cfg::THREADS) {
+  if constexpr (!DENSEK) {
+    for (int i = threadIdx.x; i < LC_TCAP; i += THREADS) {
       c.tkeys[i] = kEmptyKey;
       c.tids[i] = LC_ID_UNSET;
     }
   }
-  for (int i = threadIdx.x; i < Cfg::GP; i += Cfg::THREADS) {
+  for (int i = threadIdx.x; i < Cfg::GP; i += THREADS) {
     c.cta_first[i] = kNoRow;
     if constexpr (WIDE) {
       c.mm_p[2 * i] = kMinInit;
@@ -652,15 +675,16 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
     }
   }
   if (threadIdx.x < 4) c.misc[threadIdx.x] = 0;
-  for (int i = lane; i < Cfg::GP; i += 32) {
-    reinterpret_cast<uint64_t*>(my_acc + L::W_SUM)[i] = 0ull;
-    reinterpret_cast<uint32_t*>(my_acc + L::W_CW)[i] = LC_CNT_MASK;
-    if constexpr (Cfg::DSUM) reinterpret_cast<double*>(my_acc + L::W_DSUM)[i] = 0.0;
+  if (warp < nwarps) {
+    for (int i = lane; i < Cfg::GP; i += 32) {
+      reinterpret_cast<uint64_t*>(my_acc + L::W_SUM)[i] = 0ull;
+      reinterpret_cast<uint32_t*>(my_acc + L::W_CW)[i] = LC_CNT_MASK;
+      if constexpr (Cfg::DSUM) reinterpret_cast<double*>(my_acc + L::W_DSUM)[i] = 0.0;
+    }
   }
   __syncthreads();
 
-  if (dense) lc_scan_rows<VC, WIDE, FAST, true>(a, c, warp, lane);
-  else lc_scan_rows<VC, WIDE, FAST, false>(a, c, warp, lane);
+  lc_scan_rows<VC, WIDE, FAST, DENSEK>(a, c, warp, lane);
   __syncthreads();
   if (c.misc[1]) {
     if (threadIdx.x == 0) atomicExch(a.status + ST_ABORT, 1u);
@@ -670,15 +694,15 @@ __global__ void __launch_bounds__(LcCfg<VC, WIDE>::THREADS, 1) k_lowcard_scan(Lc
   // ---- fold the warps (and, in dense mode, the replicas) in a fixed order and write this CTA's partial table ----
   const size_t pbase = static_cast<size_t>(blockIdx.x) * Cfg::GP;
   const uint32_t nrep = 1u << c.rlog;
-  for (int id = threadIdx.x; id < Cfg::GP; id += Cfg::THREADS) {
+  for (int id = threadIdx.x; id < Cfg::GP; id += THREADS) {
     uint64_t sum = 0;
     double fsum = 0.0, dsum = 0.0;
     uint32_t cnt = 0;
     const bool regular = id < Cfg::GMAX;
     const uint32_t reps = regular ? nrep : 1u;
     if (!regular || static_cast<uint32_t>(id) < c.window) {
-      for (int w = 0; w < Cfg::WARPS; ++w) {
-        const unsigned char* wa = smem + L::OFF_ACC + L::ACC_PER_WARP * w;
+      for (int w = 0; w < nwarps; ++w) {
+        const unsigned char* wa = smem + off_acc + L::ACC_PER_WARP * w;
         for (uint32_t r = 0; r < reps; ++r) {
           const uint32_t slot = regular ? ((static_cast<uint32_t>(id) << c.rlog) | r) : static_cast<uint32_t>(id);
           const uint32_t cw = reinterpret_cast<const uint32_t*>(wa + L::W_CW)[slot] & LC_CNT_MASK;
