@@ -149,6 +149,15 @@ int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, stru
 int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values,
                          const struct ArrowSchema* value_schema, uint32_t agg_mask);
 
+/* Same, without waiting for the device when every input is device resident (ARROW_DEVICE_CUDA): the pass and
+ * the result formatting are queued on the handle's stream and the call returns; the status words (group count,
+ * overflow / fallback) are read by whichever call needs them next (fetch, num_groups, unique, last_timing,
+ * sync, partials_count, the next aggregate ...), which also redoes the pass on the slower path if the
+ * optimistic one did not apply.  The value buffers must stay alive until then.  Host inputs: identical to
+ * pa_groupby_aggregate. */
+int pa_groupby_aggregate_async(pa_groupby* g, const struct ArrowDeviceArray* values,
+                               const struct ArrowSchema* value_schema, uint32_t agg_mask);
+
 /* Copies one finished aggregate (a single PA_AGG_* bit of the last aggregate call) to a host
  * Arrow array of length num_groups, first-appearance order. */
 int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, struct ArrowSchema* out_schema);

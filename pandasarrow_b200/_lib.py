@@ -18,7 +18,8 @@ PA_PARTIAL_WORDS = 11
 # every symbol include/pa_b200.h declares
 EXPORTS = [
     "pa_last_error", "pa_version", "pa_options_init", "pa_device_count", "pa_groupby_create",
-    "pa_groupby_num_groups", "pa_groupby_unique", "pa_groupby_aggregate", "pa_groupby_fetch",
+    "pa_groupby_num_groups", "pa_groupby_unique", "pa_groupby_aggregate", "pa_groupby_aggregate_async",
+    "pa_groupby_fetch",
     "pa_groupby_row_ids", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
     "pa_groupby_sync",
     "pa_groupby_destroy", "pa_resample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
@@ -82,6 +83,7 @@ def load():
     L.pa_groupby_num_groups.argtypes = [P, C.POINTER(C.c_int64)]
     L.pa_groupby_unique.argtypes = [P, C.c_int32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_aggregate.argtypes = [P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32]
+    L.pa_groupby_aggregate_async.argtypes = [P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32]
     L.pa_groupby_fetch.argtypes = [P, C.c_uint32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_first_rows.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_row_ids.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]

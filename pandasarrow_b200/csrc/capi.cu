@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -72,9 +73,10 @@ struct DevBuf {
     bytes = 0;
   }
   int alloc(size_t n, cudaStream_t stream) {
+    if (n == 0) n = 16;
+    if (p && s == stream && bytes >= n) return PA_OK;   // recycled handle: the old block is big enough
     reset();
     s = stream;
-    if (n == 0) n = 16;
     CUDA_TRY(cudaMallocAsync(&p, n, stream));
     bytes = n;
     return PA_OK;
@@ -212,6 +214,21 @@ struct pa_groupby {
   int last_path = 0, last_launches = 0;
   int last_mode = 0, last_rlog = 0, last_passes = 0;
   const uint32_t* emit_G_dev = nullptr;   // run_emit: exact group count lives on the device (g->G is an upper bound)
+  bool poolable = false;                  // merged handle built by the fused small merge: recycled on destroy
+  // deferred (asynchronous) aggregate: kernels are queued, the status words have not been read yet
+  bool pending = false;
+  Column pending_val;                     // borrowed device pointers of the value column (no ownership)
+  bool pending_has_val = false;
+  uint32_t pending_mask = 0;
+  uint32_t pending_prev_G = 0;
+  bool pending_had_groups = false;
+  // deferred fused merge of padded blocks (multi-GPU): status not read yet; the caller keeps the blocks alive
+  bool pending_merge = false;
+  const void* pm_blocks = nullptr;
+  int32_t pm_nsrc = 0;
+  int64_t pm_block_records = 0;
+  uint32_t pm_mask = 0;
+  std::string pm_vfmt, pm_kfmt;
   float last_total_ms = 0;
   float stage_ms[4] = {0, 0, 0, 0};
   cudaEvent_t ev[6] = {};
@@ -286,7 +303,8 @@ int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, 
   return PA_OK;
 }
 
-int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool force_hash, LcOutcome* outcome) {
+int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool force_hash, LcOutcome* outcome,
+                bool deferred = false) {
   cudaStream_t st = g->stream;
   const int grid = g->num_sms;
   const int vc = val ? val->vc : VC_I;
@@ -366,6 +384,11 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
     else PA_TRY((launch_lowcard_t<VC_U, false>(g, a, m, grid, fast, force_hash)));
   }
   CUDA_TRY(cudaEventRecord(g->ev[3], st));
+  if (deferred) {   // the scratch buffers above are released in stream order; the status is read by finish_pending()
+    g->G = static_cast<uint32_t>(gp);   // upper bound until then
+    *outcome = LC_DONE;
+    return PA_OK;
+  }
   uint32_t h_status[ST_WORDS];
   CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
@@ -707,7 +730,7 @@ int setup_keys(pa_groupby* g) {
   return PA_OK;
 }
 
-int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
+int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask, bool deferred = false, int start_at = 0) {
   cudaStream_t st = g->stream;
   g->last_launches = 0;
   g->last_mode = 0; g->last_rlog = 0; g->last_passes = 0;
@@ -724,9 +747,29 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
     const int64_t known_groups = g->opt.expected_groups > 0 ? g->opt.expected_groups : (g->have_groups ? static_cast<int64_t>(g->G) : 0);
     bool try_low = g->opt.path != PA_PATH_GLOBAL && (known_groups <= gmax + 2 || g->opt.path == PA_PATH_LOWCARD);
     bool done = false;
+    if (start_at == 2) try_low = false;                       // (resuming after a deferred pass overflowed)
+    if (try_low && deferred && start_at == 0 && !g->opt.lowcard_no_dense) {
+      // Deferred: queue the dense-mode pass and the emit without reading the status back.  If the pass turns
+      // out to have declined / aborted / overflowed, finish_pending() resumes synchronously from there.
+      LcOutcome oc = LC_DONE;
+      PA_TRY(run_lowcard(g, val, mask, wide, false, &oc, true));
+      g->last_path = PA_PATH_LOWCARD;
+      g->have_groups = true;
+      g->last_wide = wide;
+      g->last_vc = vc;
+      g->last_vw = val ? val->width : 8;
+      g->last_vfmt = val ? val->format : "l";
+      g->parts_n = 0;
+      g->emit_G_dev = g->status.as<uint32_t>() + ST_NGROUPS;
+      PA_TRY(run_emit(g, val, mask));
+      g->emit_G_dev = nullptr;
+      CUDA_TRY(cudaEventRecord(g->ev[4], st));
+      g->pending = true;
+      return PA_OK;
+    }
     if (try_low) {
       LcOutcome oc = LC_DONE;
-      PA_TRY(run_lowcard(g, val, mask, wide, g->opt.lowcard_no_dense != 0, &oc));
+      PA_TRY(run_lowcard(g, val, mask, wide, g->opt.lowcard_no_dense != 0 || start_at == 1, &oc));
       if (oc == LC_DENSE_MISS) PA_TRY(run_lowcard(g, val, mask, wide, true, &oc));   // a key outside the sampled window
       if (oc == LC_DONE) { done = true; g->last_path = PA_PATH_LOWCARD; }
       else if (g->opt.path == PA_PATH_LOWCARD) return set_err(PA_ERR_INVALID, "more groups than the shared-memory path holds (%d)", gmax);
@@ -746,6 +789,58 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask) {
   PA_TRY(run_emit(g, val, mask));
   CUDA_TRY(cudaEventRecord(g->ev[4], st));
   return PA_OK;
+}
+
+// Completes a deferred aggregate: reads the status words; on success only the group count was missing, otherwise
+// the pass is redone synchronously from the stage that failed.
+int merge_padded_general(pa_groupby* g, const void* dev_blocks, int32_t n_sources, int64_t block_records, uint32_t agg_mask,
+                         const char* value_format, const char* key_format);
+
+int finish_pending(pa_groupby* g) {
+  if (g->pending_merge) {
+    g->pending_merge = false;
+    cudaStream_t st = g->stream;
+    CUDA_TRY(cudaSetDevice(g->device));
+    uint32_t h_status[ST_WORDS];
+    CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_status[ST_PEER_OVERFLOW]) {
+      g->have_groups = false; g->G = 0; g->outs.clear(); g->poolable = false;
+      return set_err(PA_ERR_STATE, "a source rank had more groups than a padded block holds; use the counted exchange");
+    }
+    if (!h_status[ST_OVERFLOW]) {
+      g->G = h_status[ST_COUNTER];
+      return PA_OK;
+    }
+    g->outs.clear();                                    // too many records / groups for one CTA: general merge
+    g->have_groups = false;
+    g->poolable = false;
+    return merge_padded_general(g, g->pm_blocks, g->pm_nsrc, g->pm_block_records, g->pm_mask, g->pm_vfmt.c_str(), g->pm_kfmt.c_str());
+  }
+  if (!g->pending) return PA_OK;
+  g->pending = false;
+  cudaStream_t st = g->stream;
+  CUDA_TRY(cudaSetDevice(g->device));
+  uint32_t h_status[ST_WORDS];
+  CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const Column* val = g->pending_has_val ? &g->pending_val : nullptr;
+  int rc = PA_OK;
+  if (!h_status[ST_OVERFLOW] && !h_status[ST_DENSE_MISS]) {
+    g->G = h_status[ST_NGROUPS];
+    g->last_mode = static_cast<int>(h_status[ST_MODE]);
+    g->last_rlog = static_cast<int>(h_status[ST_RLOG]);
+    g->last_passes = 1;
+  } else {
+    const int passes = h_status[ST_DENSE_MISS] == 2u ? 0 : 1;
+    g->have_groups = g->pending_had_groups;
+    g->G = g->pending_prev_G;
+    rc = aggregate_impl(g, val, g->pending_mask, false, h_status[ST_OVERFLOW] ? 2 : 1);
+    g->last_passes += passes;
+  }
+  if (rc == PA_OK && g->pending_had_groups && g->pending_prev_G != g->G)
+    rc = set_err(PA_ERR_STATE, "group count changed between passes (%u vs %u)", g->pending_prev_G, g->G);
+  return rc;
 }
 
 }  // namespace
@@ -894,6 +989,23 @@ int pa_device_count(int* out) {
   return PA_OK;
 }
 
+// Merged (multi-GPU) handles are created and destroyed once per step; their events, status buffer and
+// result buffers are recycled through a small pool instead of being re-created (≈ 0.2 ms per step).
+static std::mutex g_pool_mutex;
+static std::vector<pa_groupby*> g_merge_pool;
+
+static pa_groupby* pool_take(int device, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  for (size_t i = 0; i < g_merge_pool.size(); ++i) {
+    pa_groupby* h = g_merge_pool[i];
+    if (h->device == device && h->stream == stream) {
+      g_merge_pool.erase(g_merge_pool.begin() + i);
+      return h;
+    }
+  }
+  return nullptr;
+}
+
 static int handle_init(pa_groupby* g, const pa_options* opt) {
   if (opt) g->opt = *opt; else pa_options_init(&g->opt);
   int ndev = 0;
@@ -936,6 +1048,7 @@ int pa_groupby_create(const struct ArrowDeviceArray* keys, const struct ArrowSch
 }
 
 static int ensure_groups(pa_groupby* g) {
+  PA_TRY(finish_pending(g));
   if (g->have_groups) return PA_OK;
   PA_TRY(ensure_device(g));
   return aggregate_impl(g, nullptr, 0);
@@ -973,8 +1086,8 @@ int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, stru
   return export_host(g->stream, g->keys[key_i].format, f.width, G, vals.p, valid.as<uint32_t>(), out, out_schema);
 }
 
-int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
-                         uint32_t agg_mask) {
+static int aggregate_entry(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
+                           uint32_t agg_mask, bool deferred) {
   if (!g || !values || !value_schema) return set_err(PA_ERR_INVALID, "null argument");
   if (agg_mask == 0 || (agg_mask & ~PA_AGG_ALL)) return set_err(PA_ERR_INVALID, "bad aggregate mask 0x%x", agg_mask);
   PA_TRY(ensure_device(g));
@@ -982,18 +1095,54 @@ int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values, c
   PA_TRY(load_column(values, value_schema, g->stream, g->device, &val));
   if (val.n != g->n) return set_err(PA_ERR_INVALID, "value column has %lld rows, keys have %lld", (long long)val.n, (long long)g->n);
   if (value_schema->dictionary) return set_err(PA_ERR_INVALID, "dictionary-encoded value columns are not aggregatable");
-  const uint32_t prev_G = g->G;
-  const bool had = g->have_groups;
-  PA_TRY(aggregate_impl(g, &val, agg_mask));
+  uint32_t prev_G = g->G;
+  bool had = g->have_groups;
+  if (g->pending && deferred && !val.own_data.p && !val.own_valid.p) {
+    // A deferred pass whose results nobody asked for is superseded by this one (its buffers are recycled in
+    // stream order); had it failed, this pass fails the same way and is redone when it is finished.
+    g->pending = false;
+    prev_G = g->pending_prev_G;
+    had = g->pending_had_groups;
+    g->have_groups = had;
+    g->G = prev_G;
+  } else {
+    PA_TRY(finish_pending(g));
+    prev_G = g->G;
+    had = g->have_groups;
+  }
+  // deferred mode needs inputs that outlive the call: device-resident columns only
+  deferred = deferred && !val.own_data.p && !val.own_valid.p && !g->resample && !g->merged;
+  if (deferred) {
+    g->pending_val = Column{};
+    g->pending_val.data = val.data; g->pending_val.valid = val.valid; g->pending_val.bit_off = val.bit_off;
+    g->pending_val.n = val.n; g->pending_val.width = val.width; g->pending_val.vc = val.vc; g->pending_val.format = val.format;
+    g->pending_has_val = true;
+    g->pending_mask = agg_mask;
+    g->pending_prev_G = prev_G;
+    g->pending_had_groups = had;
+  }
+  PA_TRY(aggregate_impl(g, &val, agg_mask, deferred));
+  if (g->pending) return PA_OK;
   if (had && prev_G != g->G) return set_err(PA_ERR_STATE, "group count changed between passes (%u vs %u)", prev_G, g->G);
   // `val` may own device copies of host data: make sure the kernels reading them are done
   if (val.own_data.p) CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PA_OK;
 }
 
+int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
+                         uint32_t agg_mask) {
+  return aggregate_entry(g, values, value_schema, agg_mask, false);
+}
+
+int pa_groupby_aggregate_async(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
+                               uint32_t agg_mask) {
+  return aggregate_entry(g, values, value_schema, agg_mask, true);
+}
+
 int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, struct ArrowSchema* out_schema) {
   if (!g || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
   PA_TRY(ensure_device(g));
+  PA_TRY(finish_pending(g));
   for (auto& o : g->outs) {
     if (o.bit == agg_bit)
       return export_host(g->stream, o.format, o.width, g->G, o.values.p, o.nullable ? o.valid.as<uint32_t>() : nullptr, out, out_schema);
@@ -1071,6 +1220,7 @@ int pa_groupby_first_rows(pa_groupby* g, struct ArrowArray* out, struct ArrowSch
 int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]) {
   if (!g) return set_err(PA_ERR_INVALID, "null argument");
   PA_TRY(ensure_device(g));
+  PA_TRY(finish_pending(g));
   CUDA_TRY(cudaEventSynchronize(g->ev[4]));
   float t = 0;
   CUDA_TRY(cudaEventElapsedTime(&t, g->ev[0], g->ev[4]));
@@ -1088,6 +1238,7 @@ int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]) 
 
 int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches) {
   if (!g) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(finish_pending(g));
   if (path) *path = g->last_path;
   if (kernel_launches) *kernel_launches = g->last_launches;
   return PA_OK;
@@ -1095,6 +1246,7 @@ int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches)
 
 int pa_groupby_last_detail(pa_groupby* g, int32_t detail[4]) {
   if (!g || !detail) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(finish_pending(g));
   detail[0] = g->last_mode; detail[1] = g->last_rlog; detail[2] = g->last_passes; detail[3] = 0;
   return PA_OK;
 }
@@ -1102,12 +1254,25 @@ int pa_groupby_last_detail(pa_groupby* g, int32_t detail[4]) {
 int pa_groupby_sync(pa_groupby* g) {
   if (!g) return set_err(PA_ERR_INVALID, "null argument");
   PA_TRY(ensure_device(g));
+  PA_TRY(finish_pending(g));
   CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PA_OK;
 }
 
 void pa_groupby_destroy(pa_groupby* g) {
   if (!g) return;
+  if (g->merged && !g->own_stream && g->poolable) {
+    // recycle: nothing is freed, so no synchronisation is needed either (stream order protects the buffers)
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_merge_pool.size() < 4) {
+      g->outs.clear();
+      g->have_groups = false;
+      g->pending_merge = false;
+      g->G = 0;
+      g_merge_pool.push_back(g);
+      return;
+    }
+  }
   cudaSetDevice(g->device);
   cudaStreamSynchronize(g->stream);
   g->outs.clear();
@@ -1173,6 +1338,7 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
 // ---- multi-GPU partial export / merge ----
 int pa_groupby_partials_count(pa_groupby* g, int32_t n_parts, int64_t* counts_host) {
   if (!g || !counts_host || n_parts < 1 || n_parts > 64) return set_err(PA_ERR_INVALID, "bad argument (1 <= n_parts <= 64)");
+  PA_TRY(finish_pending(g));
   if (!g->have_groups || g->merged) return set_err(PA_ERR_STATE, "partials need a finished local aggregate");
   if (g->keys.size() != 1 && !g->resample) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of composite keys");
   PA_TRY(ensure_device(g));
@@ -1347,6 +1513,10 @@ int pa_groupby_partials_export_padded(pa_groupby* g, int32_t n_parts, void* dev_
     if (o.bit == AGG_LAST) { a.last_vals = o.values.p; a.last_valid = o.valid.as<uint32_t>(); }
   }
   a.records = static_cast<uint64_t*>(dev_blocks);
+  if (g->pending) {   // deferred local aggregate: group count and failure flag are still on the device
+    a.G_dev = g->status.as<uint32_t>() + ST_NGROUPS;
+    a.abort_dev = g->status.as<uint32_t>() + ST_ABORT;
+  }
   k_partials_pack_padded<<<1, 1024, 0, g->stream>>>(a, static_cast<uint64_t>(block_records));
   CUDA_TRY(cudaGetLastError());
   return PA_OK;   // stream ordered: no host synchronisation
@@ -1357,8 +1527,21 @@ int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t bl
   if (!dev_blocks || n_sources < 1 || n_sources > 64 || block_records < 1 || !value_format || !key_format || !out)
     return set_err(PA_ERR_INVALID, "bad argument (1 <= n_sources <= 64)");
   if (agg_mask & ~PA_AGG_ALL) return set_err(PA_ERR_INVALID, "bad aggregate mask");
-  HandlePtr g(new pa_groupby());
-  PA_TRY(handle_init(g.get(), opt));
+  HandlePtr g;
+  {
+    int dev = opt && opt->device >= 0 ? opt->device : -1;
+    if (dev < 0) CUDA_TRY(cudaGetDevice(&dev));
+    pa_groupby* recycled = (opt && opt->cuda_stream) ? pool_take(dev, static_cast<cudaStream_t>(opt->cuda_stream)) : nullptr;
+    if (recycled) {
+      g.reset(recycled);
+      g->opt = *opt;
+      CUDA_TRY(cudaSetDevice(g->device));
+    } else {
+      g.reset(new pa_groupby());
+      PA_TRY(handle_init(g.get(), opt));
+    }
+  }
+  g->poolable = false;
   cudaStream_t st = g->stream;
   const uint64_t nrec_max = static_cast<uint64_t>(n_sources) * static_cast<uint64_t>(block_records);
   CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
@@ -1397,7 +1580,11 @@ int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t bl
     m.o_first_valid = h->m_first_valid.as<uint8_t>(); m.o_last_valid = h->m_last_valid.as<uint8_t>();
     m.o_first_row_g = h->m_first_row_g.as<uint64_t>();
     m.status = h->status.as<uint32_t>();
-    CUDA_TRY(cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MS_SMEM_BYTES)));
+    static bool attr_set[64] = {};
+    if (!attr_set[h->device & 63]) {
+      CUDA_TRY(cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MS_SMEM_BYTES)));
+      attr_set[h->device & 63] = true;
+    }
     CUDA_TRY(cudaEventRecord(h->ev[1], st));
     k_merge_small<<<1, MS_THREADS, MS_SMEM_BYTES, st>>>(m);
     CUDA_TRY(cudaGetLastError());
@@ -1411,18 +1598,22 @@ int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t bl
     PA_TRY(run_emit(h, nullptr, agg_mask));
     h->emit_G_dev = nullptr;
     CUDA_TRY(cudaEventRecord(h->ev[4], st));
-    uint32_t h_status[ST_WORDS];
-    CUDA_TRY(cudaMemcpyAsync(h_status, h->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    if (h_status[ST_PEER_OVERFLOW]) return set_err(PA_ERR_STATE, "a source rank had more groups than a padded block holds; use the counted exchange");
-    if (!h_status[ST_OVERFLOW]) {
-      h->G = h_status[ST_COUNTER];
-      *out = g.release();
-      return PA_OK;
-    }
-    h->outs.clear();                                    // too many records / groups for one CTA: general merge below
-    h->have_groups = false;
+    // the status words (group count, overflow markers) are read by the first call that needs them
+    h->pending_merge = true;
+    h->poolable = true;
+    h->pm_blocks = dev_blocks; h->pm_nsrc = n_sources; h->pm_block_records = block_records; h->pm_mask = agg_mask;
+    h->pm_vfmt = value_format; h->pm_kfmt = key_format;
+    *out = g.release();
+    return PA_OK;
   }
+}
+
+extern "C++" {
+namespace {
+int merge_padded_general(pa_groupby* g, const void* dev_blocks, int32_t n_sources, int64_t block_records, uint32_t agg_mask,
+                         const char* value_format, const char* key_format) {
+  cudaStream_t st = g->stream;
+  const uint64_t nrec_max = static_cast<uint64_t>(n_sources) * static_cast<uint64_t>(block_records);
   DevBuf d_off, records;
   PA_TRY(d_off.alloc(sizeof(uint64_t) * (n_sources + 1), st));
   PA_TRY(records.alloc(nrec_max * PA_PARTIAL_WORDS * 8, st));
@@ -1431,10 +1622,10 @@ int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t bl
                                            static_cast<uint64_t>(block_records), records.as<uint64_t>(), d_off.as<uint64_t>(),
                                            g->status.as<uint32_t>());
   CUDA_TRY(cudaGetLastError());
-  PA_TRY(merge_build(g.get(), records.p, d_off.as<uint64_t>(), n_sources, nrec_max, agg_mask, value_format, key_format));
-  *out = g.release();
-  return PA_OK;
+  return merge_build(g, records.p, d_off.as<uint64_t>(), n_sources, nrec_max, agg_mask, value_format, key_format);
 }
+}  // namespace
+}  // extern "C++"
 
 // ---- synthetic generator ----
 static int synth_grid(int64_t n) {

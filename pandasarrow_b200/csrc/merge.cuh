@@ -32,6 +32,8 @@ struct PartialsArgs {
   const void* last_vals; const uint32_t* last_valid;
   int vw;
   bool wide;
+  const uint32_t* G_dev;       // optional: group count on the device (deferred local aggregate)
+  const uint32_t* abort_dev;   // optional: non-zero = the local pass failed, send overflow markers
   unsigned long long* counts;  // [nparts] (device)
   unsigned long long* cursor;  // [nparts] running write offsets (device), pre-set to the exclusive prefix of counts
   uint64_t* records;
@@ -99,7 +101,8 @@ __global__ void __launch_bounds__(1024, 1) k_partials_pack_padded(PartialsArgs a
   if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const uint64_t stride = (block_records + 1) * REC_WORDS;
-  const bool overflow = a.G > block_records;
+  if (a.G_dev) a.G = *a.G_dev;
+  const bool overflow = a.G > block_records || (a.abort_dev && *a.abort_dev);
   if (!overflow) {
     for (uint32_t g = threadIdx.x; g < a.G; g += blockDim.x) {
       const uint8_t kind = a.r.key_kind[g];

@@ -81,22 +81,29 @@ def exchange_padded(send_blocks, group=None):
 
 
 def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_format: str, group=None, stream=None,
-                      padded: Optional[bool] = None):
+                      padded: Optional[bool] = None, wait: bool = True):
     """Run the whole multi-GPU step for this rank.  `gb` is this rank's GroupBy over its row shard
     (created with row_base = first global row of the shard).  Returns the owner-side MergedGroupBy.
 
     With few groups (<= PADDED_BLOCK_RECORDS on this rank) the partials travel in fixed-size blocks: one
     stream-ordered export kernel, one equal-split all-to-all, one merge — no host round trip in between.  A rank
     with more groups sends an overflow marker to every peer, so all ranks fall back to the counted exchange
-    together.  `stream` must be the current torch stream for the padded path (it is in bench.py)."""
+    together.  `stream` must be the current torch stream for the padded path (it is in bench.py).
+
+    wait=False (padded path only): nothing is read back at all — local pass, export, exchange and merge are just
+    queued, so consecutive steps pipeline; the first call on the returned handle that needs a result completes
+    it (and raises PaError if a rank had overflowed: rerun that step with wait=True)."""
     import torch
     import torch.distributed as dist
     from .groupby import MergedGroupBy, PaError
     world = dist.get_world_size(group)
-    gb.aggregate(values, aggs, fetch=False)
     dev = torch.device("cuda", torch.cuda.current_device())
     if padded is None:
         padded = stream is not None and stream == torch.cuda.current_stream(dev).cuda_stream
+    # padded path: the local pass is only queued (no status read-back); export, exchange and merge are queued
+    # behind it, so the host never waits before the merge's own result read.  A local pass that did not fit
+    # the optimistic path makes the export send overflow markers, and everything is redone synchronously below.
+    gb.aggregate(values, aggs, fetch=False, wait=not padded)
     if padded:
         cap = PADDED_BLOCK_RECORDS
         send = torch.empty((world, cap + 1, PA_PARTIAL_WORDS), dtype=torch.int64, device=dev)
@@ -106,6 +113,8 @@ def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_fo
             merged = MergedGroupBy(recv.data_ptr(), [0] * world, aggs, value_format, key_format, device=dev.index,
                                    stream=stream, padded_block_records=cap)
             merged._keep = (send, recv)
+            if wait:
+                merged.groupSize()          # completes the merge; raises if any rank sent the overflow marker
             return merged
         except PaError as e:
             if "padded block" not in str(e):

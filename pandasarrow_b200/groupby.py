@@ -226,13 +226,16 @@ class GroupBy:
         return _import(a, s)
 
     # ---- aggregation core ----
-    def aggregate(self, values: Column, aggs: Sequence[str], fetch: bool = True) -> Dict[str, pa.Array]:
+    def aggregate(self, values: Column, aggs: Sequence[str], fetch: bool = True, wait: bool = True) -> Dict[str, pa.Array]:
+        """One fused pass computing `aggs` of `values` per group.  wait=False (device-resident inputs): queue the
+        pass and return; the next call that needs the result (fetch, groupSize, timing, ...) completes it."""
         mask = 0
         for a in aggs:
             mask |= PA_AGG[a]
         arg = _CArg(values)
+        fn = self._L.pa_groupby_aggregate if (wait or fetch) else self._L.pa_groupby_aggregate_async
         try:
-            _check(self._L.pa_groupby_aggregate(self._h, C.byref(arg.dev), C.byref(arg.schema), mask))
+            _check(fn(self._h, C.byref(arg.dev), C.byref(arg.schema), mask))
         finally:
             arg.close()
         if not fetch:

@@ -389,3 +389,33 @@ def test_row_ids_composite_int32_and_resample(pab):
     ids = np.asarray(r.row_ids())
     labels = r.index().cast(pa.int64()).to_numpy()
     assert (labels[ids] == (ts // (60 * 10**9)) * (60 * 10**9)).all()
+
+
+# ---------------- deferred (asynchronous) aggregate ----------------
+@pytest.mark.parametrize("G,expect", [(1000, ("lowcard", "dense", 1)), (5000, ("global", "smem-front", 2)),
+                                      (300_000, ("global", "smem-front", 2))])
+def test_async_aggregate_equals_sync(pab, G, expect):
+    import torch
+    from util import assert_exact, assert_fp_close
+    n = 2_000_000
+    k = torch.empty(n, dtype=torch.int64, device="cuda"); v = torch.empty(n, dtype=torch.float64, device="cuda")
+    pab.synth.keys(k, G); pab.synth.vals(v)
+    torch.cuda.synchronize()
+    dk, dv = pab.DeviceColumn.from_torch(k), pab.DeviceColumn.from_torch(v)
+    a = pab.GroupBy("k", {"k": dk, "v": dv}); b = pab.GroupBy("k", {"k": dk, "v": dv})
+    assert a.aggregate(dv, ALL, fetch=False, wait=False) == {}
+    t = a.timing()                                        # completes the pass (falls back synchronously if needed)
+    assert (t["path"], t["mode"], t["passes"]) == expect
+    rb_ = b.aggregate(dv, ALL)
+    assert a.unique().equals(b.unique())
+    for name in ALL:
+        (assert_fp_close if name in ("sum", "mean") else assert_exact)(a.fetch(name), rb_[name], name)
+    # scattered keys: the dense kernel declines, the deferred pass is redone in hash mode
+    k.mul_(-3335678366873096957)
+    torch.cuda.synchronize()
+    c = pab.GroupBy("k", {"k": dk, "v": dv})
+    c.aggregate(dv, ["sum", "count"], fetch=False, wait=False)
+    assert c.groupSize() == a.groupSize()
+    if G == 1000:
+        assert c.timing()["mode"] == "hash"
+        assert c.fetch("count").equals(a.fetch("count"))
