@@ -4,9 +4,12 @@
 
 #include <arrow/c/bridge.h>
 #include <arrow/compute/api.h>
+#include <arrow/compute/row/grouper.h>
 
 #include <algorithm>
 #include <cctype>
+#include <iostream>
+#include <limits>
 #include <stdexcept>
 
 #include "../../../include/pa_b200.h"
@@ -212,6 +215,126 @@ ArrayPtr GroupBy::unique() const {
   }
   uniqueKeys = arr;
   return uniqueKeys;
+}
+
+// ------------------------------ materialised groups ------------------------------
+// The reference materialises every group of every column in its constructor (dataframe.cpp:1571-1600);
+// here it happens on first use only.  Group ids come from the GPU, the regrouping is Arrow's.
+void GroupBy::materialize() const {
+  if (materialized) return;
+  if (!handle) throw std::runtime_error("GroupBy is empty");
+  ArrowArray a;
+  ArrowSchema sc;
+  if (pa_groupby_row_ids(handle, &a, &sc) != PA_OK) throw_pa("pa_groupby_row_ids");
+  auto ids = ReturnOrThrowOnFailure(arrow::ImportArray(&a, &sc));
+  const int64_t G = static_cast<int64_t>(groupSize());
+  if (G > std::numeric_limits<int32_t>::max()) throw std::runtime_error("too many groups to materialise");
+  auto groupings = ReturnOrThrowOnFailure(arrow::compute::Grouper::MakeGroupings(
+      static_cast<const arrow::UInt32Array&>(*ids), static_cast<uint32_t>(G)));
+  auto regroup = [&](const ArrayPtr& col, std::vector<ArrayPtr>* out) {
+    auto lists = ReturnOrThrowOnFailure(arrow::compute::Grouper::ApplyGroupings(*groupings, *col));
+    out->resize(G);
+    for (int64_t g = 0; g < G; ++g) (*out)[g] = lists->value_slice(g);
+  };
+  regroup(df.indexArray(), &indexGroups);
+  groups.assign(G, arrow::ArrayVector{});
+  for (int c = 0; c < df.m_array->num_columns(); ++c) {
+    std::vector<ArrayPtr> per_group;
+    regroup(df.m_array->column(c), &per_group);
+    for (int64_t g = 0; g < G; ++g) groups[g].push_back(per_group[g]);
+  }
+  materialized = true;
+}
+
+int64_t GroupBy::indexOfKey(ScalarPtr const& key) const {
+  auto keys = unique();
+  ScalarPtr k = key;
+  if (!k->type->Equals(keys->type())) k = ReturnOrThrowOnFailure(k->CastTo(keys->type()));   // HashScalar: Equals(CastTo(a.type))
+  for (int64_t g = 0; g < keys->length(); ++g) {
+    auto s = ReturnOrThrowOnFailure(keys->GetScalar(g));
+    if (s->Equals(*k)) return g;
+  }
+  return -1;
+}
+
+arrow::ArrayVector GroupBy::group(ScalarPtr const& key) const {
+  materialize();
+  const int64_t g = indexOfKey(key);
+  if (g < 0) {
+    std::cout << key->ToString() << " is an invalid key\n";     // group_by.h:45-48
+    throw std::out_of_range("invalid group key");
+  }
+  return groups[g];
+}
+
+DataFrame GroupBy::MakeSubDataFrame(int64_t groupIndex, std::shared_ptr<arrow::Schema> const& schema) const {
+  materialize();
+  if (groupIndex < 0 || groupIndex >= static_cast<int64_t>(groups.size())) throw std::out_of_range("group index");
+  return DataFrame(schema, indexGroups[groupIndex]->length(), groups[groupIndex], indexGroups[groupIndex]);
+}
+
+DataFrame GroupBy::MakeSubDataFrame(ScalarPtr const& key, std::shared_ptr<arrow::Schema> const& schema) const {
+  materialize();
+  const int64_t g = indexOfKey(key);
+  if (g < 0) throw std::out_of_range("invalid group key");
+  return MakeSubDataFrame(g, schema);
+}
+
+static arrow::Result<ArrayPtr> build_array(arrow::ScalarVector const& scalars) {   // group_by.h:191-217
+  if (scalars.empty()) return arrow::Status::Invalid("no groups");
+  ARROW_ASSIGN_OR_RAISE(auto builder, arrow::MakeBuilder(scalars.back()->type));
+  ARROW_RETURN_NOT_OK(builder->AppendScalars(scalars));
+  return builder->Finish();
+}
+
+arrow::Result<Series> GroupBy::apply(std::function<ScalarPtr(DataFrame const&)> fn) {
+  const int64_t G = static_cast<int64_t>(groupSize());
+  auto schema = df.m_array->schema();
+  arrow::ScalarVector result(G);
+  for (int64_t g = 0; g < G; ++g) result[g] = fn(MakeSubDataFrame(g, schema));
+  ARROW_ASSIGN_OR_RAISE(auto arr, build_array(result));
+  return Series(arr, unique());
+}
+
+arrow::Result<Series> GroupBy::apply(std::function<ArrayPtr(DataFrame const&)> fn) {
+  const int64_t G = static_cast<int64_t>(groupSize());
+  auto schema = df.m_array->schema();
+  arrow::ArrayVector result(G);
+  for (int64_t g = 0; g < G; ++g) {
+    auto sub = MakeSubDataFrame(g, schema);
+    result[g] = fn(sub);
+    if (result[g]->length() != sub.num_rows())
+      throw std::runtime_error("Failed to Merge Apply::Functor due to inconsistent Row Length\n" + std::to_string(result[g]->length()) +
+                               " != " + std::to_string(sub.num_rows()));
+  }
+  ARROW_ASSIGN_OR_RAISE(auto arr, arrow::Concatenate(result));
+  return Series(arr, df.indexArray());
+}
+
+arrow::Result<DataFrame> GroupBy::apply(std::function<ScalarPtr(Series const&)> fn) {
+  materialize();
+  const int64_t G = static_cast<int64_t>(groupSize());
+  auto schema = df.m_array->schema();
+  auto names = schema->field_names();
+  arrow::ArrayVector columns;
+  arrow::FieldVector fields;
+  for (int c = 0; c < schema->num_fields(); ++c) {
+    arrow::ScalarVector result(G);
+    for (int64_t g = 0; g < G; ++g) result[g] = fn(Series(groups[g][c], indexGroups[g], names[c]));
+    ARROW_ASSIGN_OR_RAISE(auto arr, build_array(result));
+    fields.push_back(arrow::field(names[c], arr->type()));
+    columns.push_back(arr);
+  }
+  return DataFrame(arrow::schema(fields), G, columns);
+}
+
+Scalar Series::sum() const {
+  return Scalar(ReturnOrThrowOnFailure(arrow::compute::CallFunction("sum", {m_array})).scalar());
+}
+
+Scalar DataFrame::sum() const {
+  auto chunked = std::make_shared<arrow::ChunkedArray>(m_array->columns());
+  return Scalar(ReturnOrThrowOnFailure(arrow::compute::CallFunction("sum", {chunked})).scalar());
 }
 
 arrow::Result<arrow::ArrayVector> GroupBy::aggregate(std::string const& column, uint32_t mask, bool drop_validity) {

@@ -12,9 +12,12 @@
 // pd::Series here are only the thin containers the path needs (a RecordBatch / Array plus an
 // index), not the reference's ~300-method wrappers (out of scope).
 //
-// Not carried over (SURVEY.md §8f "next"): group materialisation (group(), MakeSubDataFrame,
-// apply*, orderedGroups) and the aggregates outside sum/mean/count/min/max/first/last/min_max;
-// those methods exist and return arrow::Status::NotImplemented.
+// Group materialisation (group(), MakeSubDataFrame, apply*, orderedGroups; group_by.h:38-83,141-162,
+// dataframe.cpp:1354-1510) is built lazily from the per-row group ids the GPU returns
+// (pa_groupby_row_ids = what Grouper::Consume returned) with Arrow's MakeGroupings / ApplyGroupings,
+// exactly the calls the reference makes after Consume (dataframe.cpp:1539-1569,1586-1597).
+// Not carried over (SURVEY.md §8f "next"): the aggregates outside sum/mean/count/min/max/first/
+// last/min_max; those methods exist and return arrow::Status::NotImplemented.
 #pragma once
 #include <arrow/api.h>
 
@@ -89,6 +92,7 @@ class Series {
   Scalar operator[](int64_t i) const { return Scalar(ReturnOrThrowOnFailure(m_array->GetScalar(i))); }
   template <class T>
   std::vector<T> values() const;
+  Scalar sum() const;   // ndframe.cpp:220 (whole-column sum; used by the reference's apply tests)
   // series.cpp:351-359
   Resampler resample(std::string const& rule, bool closed_right = false, bool label_right = false,
                      TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0),
@@ -131,6 +135,7 @@ class DataFrame {
   Series operator[](std::string const& name) const;
   Scalar at(int64_t row, int64_t col) const { return Scalar(ReturnOrThrowOnFailure(m_array->column(static_cast<int>(col))->GetScalar(row))); }
   DataFrame setIndex(ArrayPtr const& index) const { return DataFrame(m_array, index); }
+  Scalar sum() const;   // ndframe.cpp:220 over all columns concatenated (ndframe.h:329-335)
 
   // dataframe.cpp:1227-1235
   GroupBy group_by(const std::string& key) const;
@@ -189,7 +194,29 @@ class GroupBy {
   PD_NOT_ON_GPU(all) PD_NOT_ON_GPU(any) PD_NOT_ON_GPU(approximate_median) PD_NOT_ON_GPU(count_distinct)
   PD_NOT_ON_GPU(product) PD_NOT_ON_GPU(mode) PD_NOT_ON_GPU(stddev) PD_NOT_ON_GPU(variance) PD_NOT_ON_GPU(tdigest)
 #undef PD_NOT_ON_GPU
-  arrow::Result<Series> apply(std::function<ScalarPtr(DataFrame const&)>) { return arrow::Status::NotImplemented("apply needs group materialisation (SURVEY 8f-2)"); }
+  // ---- materialised groups (group_by.h:38-83, 141-162; dataframe.cpp:1430-1510) ----
+  arrow::ArrayVector group(ScalarPtr const& key) const;                       // every column's rows of one group
+  template <class T, class = std::enable_if_t<!std::is_same_v<std::decay_t<T>, ScalarPtr>>>
+  arrow::ArrayVector group(T&& value) const {
+    ScalarPtr key = arrow::MakeScalar(std::forward<T>(value));
+    return group(key);
+  }
+  DataFrame MakeSubDataFrame(int64_t groupIndex, std::shared_ptr<arrow::Schema> const& schema) const;
+  DataFrame MakeSubDataFrame(ScalarPtr const& key, std::shared_ptr<arrow::Schema> const& schema) const;
+  arrow::Result<Series> apply(std::function<ScalarPtr(DataFrame const&)> fn);
+  arrow::Result<Series> apply(std::function<ArrayPtr(DataFrame const&)> fn);
+  arrow::Result<DataFrame> apply(std::function<ScalarPtr(Series const&)> fn);
+  arrow::Result<Series> apply_async(std::function<ScalarPtr(DataFrame const&)> fn) { return apply(std::move(fn)); }
+  arrow::Result<DataFrame> apply_async(std::function<ScalarPtr(Series const&)> fn) { return apply(std::move(fn)); }
+  template <class IndexType>
+  std::vector<std::pair<IndexType, DataFrame>> orderedGroups() const {
+    const int64_t n = static_cast<int64_t>(groupSize());
+    auto schema = df.m_array->schema();
+    std::vector<std::pair<IndexType, DataFrame>> result;
+    result.reserve(n);
+    for (int64_t g = 0; g < n; ++g) result.emplace_back(Scalar(GetKeyByIndex(g)).template as<IndexType>(), MakeSubDataFrame(g, schema));
+    return result;
+  }
 
  protected:
   GroupBy() = default;
@@ -204,6 +231,12 @@ class GroupBy {
   ArrayPtr key_array;                          // kept alive: the C ABI borrows the key buffers
   std::shared_ptr<arrow::Array> key_dictionary;  // for dictionary / utf8 keys
   mutable ArrayPtr uniqueKeys;
+  // lazily materialised groups, by group index (first-appearance order)
+  void materialize() const;
+  int64_t indexOfKey(ScalarPtr const& key) const;
+  mutable bool materialized = false;
+  mutable std::vector<arrow::ArrayVector> groups;     // groups[g][column]
+  mutable arrow::ArrayVector indexGroups;             // indexGroups[g]
   friend class Resampler;
 };
 

@@ -7,6 +7,8 @@
 #include <iostream>
 #include <string>
 
+#include <arrow/compute/api.h>
+
 #include "../../pandasarrow_b200/csrc/host/pd_groupby.h"
 
 using namespace std::string_literals;
@@ -139,6 +141,46 @@ static void test_apply_sums() {
   REQUIRE(pd::ReturnOrThrowOnFailure(g3.sum("b")).values<int64_t>() == (std::vector<int64_t>{37, 12, 3, 3}));
 }
 
+// dataframe_iterator_test.cpp:11-76 — apply callbacks over materialised groups (+ group(), MakeSubDataFrame,
+// orderedGroups from cudf_examples/dataframe_resample_test.cpp:8-69)
+static void test_apply_callbacks_and_groups() {
+  auto df = pd::DataFrame(std::map<std::string, std::vector<int32_t>>{{"a", {1, 1, 3, 1, 1, 1, 3, 8, 2, 2}}, {"b", {10, 9, 8, 7, 6, 5, 4, 3, 2, 1}}});
+  auto groupby = df.group_by("a"s);
+  REQUIRE(groupby.groupSize() == 4);
+  auto col_sum = [](pd::Series const& s) -> std::shared_ptr<arrow::Scalar> { return s.sum().scalar; };
+  auto result = pd::ReturnOrThrowOnFailure(groupby.apply(col_sum));
+  REQUIRE(result.num_rows() == 4);
+  REQUIRE(result.num_columns() == 2);
+  REQUIRE(result["a"].values<int64_t>() == (std::vector<int64_t>{5, 6, 8, 4}));
+  REQUIRE(result["b"].values<int64_t>() == (std::vector<int64_t>{37, 12, 3, 3}));
+  auto frame_sum = [](pd::DataFrame const& s) -> std::shared_ptr<arrow::Scalar> { return s.sum().scalar; };
+  auto rows = pd::ReturnOrThrowOnFailure(groupby.apply(frame_sum));
+  REQUIRE(rows.size() == 4);
+  REQUIRE(rows.values<int64_t>() == (std::vector<int64_t>{42, 18, 11, 7}));
+  REQUIRE(pd::ReturnOrThrowOnFailure(groupby.apply_async(frame_sum)).values<int64_t>() == (std::vector<int64_t>{42, 18, 11, 7}));
+  // per-group row order is the original row order (dataframe_resample_test.cpp:49-52)
+  auto g1 = groupby.group(1);
+  REQUIRE(g1.size() == 2);
+  REQUIRE(g1[1]->length() == 5);
+  REQUIRE(pd::Series(g1[1], nullptr).values<int64_t>() == (std::vector<int64_t>{10, 9, 7, 6, 5}));
+  auto sub = groupby.MakeSubDataFrame(1, df.array()->schema());      // second group: key 3
+  REQUIRE(sub.num_rows() == 2);
+  REQUIRE(sub["b"].values<int64_t>() == (std::vector<int64_t>{8, 4}));
+  REQUIRE(pd::Series(sub.indexArray(), nullptr).values<int64_t>() == (std::vector<int64_t>{2, 6}));
+  REQUIRE_THROWS(groupby.group(77));
+  auto ordered = groupby.orderedGroups<int64_t>();
+  REQUIRE(ordered.size() == 4);
+  REQUIRE(ordered[2].first == 8);
+  REQUIRE(ordered[2].second.num_rows() == 1);
+  // apply with an array-valued functor: rows come back group by group, indexed by the frame's index
+  auto twice = [](pd::DataFrame const& s) -> pd::ArrayPtr {
+    return arrow::compute::CallFunction("multiply", {s["b"].array(), arrow::MakeScalar(int32_t(2))}).ValueOrDie().make_array();
+  };
+  auto doubled = pd::ReturnOrThrowOnFailure(groupby.apply(twice));
+  REQUIRE(doubled.size() == 10);
+  REQUIRE(doubled.values<int64_t>() == (std::vector<int64_t>{20, 18, 14, 12, 10, 16, 8, 6, 4, 2}));
+}
+
 // series_resample_test.cpp:12-70
 static void test_resample_series() {
   auto index = pd::date_range(pd::ns_from_ymd(2000, 1, 1), 9);
@@ -211,6 +253,7 @@ int main() {
     test_make_groups_and_aggregates();
     test_bardata();
     test_apply_sums();
+    test_apply_callbacks_and_groups();
     test_resample_series();
     test_downsample();
   } catch (std::exception const& e) {
