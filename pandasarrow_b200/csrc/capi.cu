@@ -297,7 +297,7 @@ int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, 
   CUDA_TRY(cudaEventRecord(g->ev[2], st));
   k_lowcard_merge<VC, WIDE><<<(Cfg::GP + 7) / 8, 256, 0, st>>>(m);
   CUDA_TRY(cudaGetLastError());
-  k_lowcard_rank<VC, WIDE><<<1, LR_THREADS, 0, st>>>(m);
+  k_lowcard_rank<VC, WIDE><<<(Cfg::GP + LR_THREADS / 32 - 1) / (LR_THREADS / 32), LR_THREADS, 0, st>>>(m);
   CUDA_TRY(cudaGetLastError());
   g->last_launches += 4;
   return PA_OK;
@@ -439,7 +439,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     const int64_t ntiles = (g->n + 1023) / 1024;
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, grid_full)));
     const bool fast = a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid &&
-                      reinterpret_cast<uintptr_t>(a.keys) % 16 == 0 && reinterpret_cast<uintptr_t>(a.vals) % 16 == 0;
+                      reinterpret_cast<uintptr_t>(a.keys) % 32 == 0 && reinterpret_cast<uintptr_t>(a.vals) % 32 == 0;
     // Very many groups (table far larger than L2): reorder the rows by table region first (partition.cuh).
     DevBuf p_keys, p_vals, p_rows, p_counts;
     const uint64_t known_g = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);

@@ -184,4 +184,14 @@ __device__ __forceinline__ ulonglong2 ldg_stream_u64x2(const void* p) {
   return r;
 }
 
+// streaming 256-bit global load, no L1 allocation, evict-first in L2 (LDG.E.NA.EFL2.256): input rows are
+// read exactly once and must not push the group table out of L2.  32-byte aligned address.
+struct u64x4 { unsigned long long a, b, c, d; };
+__device__ __forceinline__ u64x4 ldg_stream_u64x4(const void* p) {
+  u64x4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(r.a), "=l"(r.b), "=l"(r.c), "=l"(r.d) : "l"(p));
+  return r;
+}
+
 }  // namespace pa

@@ -169,7 +169,7 @@ constexpr int GT_R = 4;   // rows per thread per tile
 
 // Rows of one tile for this thread.  FAST: 8-byte non-null keys and 8-byte values (a value validity bitmap
 // is allowed): thread t takes
-// the adjacent rows 2t, 2t+1 (128-bit non-allocating loads) — row order is irrelevant on this path,
+// the adjacent rows 4t .. 4t+3 (256-bit non-allocating, L2 evict-first loads) — row order is irrelevant on this path,
 // first/last rows are atomicMin/Max.
 struct GRows {
   uint64_t key[GT_R], vb[GT_R];
@@ -181,28 +181,31 @@ template <int VC, bool FAST>
 __device__ __forceinline__ void gtile_load(const GScanArgs& a, int64_t tile0, int64_t tile_rows, GRows& r) {
   constexpr int R = GT_R;
   if (FAST && tile0 + tile_rows <= a.n) {
+    static_assert(GT_R == 4, "one 256-bit load = 4 rows");
+    const int64_t r0 = tile0 + 4 * static_cast<int64_t>(threadIdx.x);
+    const u64x4 k4 = ldg_stream_u64x4(static_cast<const uint64_t*>(a.keys) + r0);
+    u64x4 v4{0ull, 0ull, 0ull, 0ull};
+    if (a.vals) v4 = ldg_stream_u64x4(static_cast<const uint64_t*>(a.vals) + r0);
+    r.key[0] = k4.a; r.key[1] = k4.b; r.key[2] = k4.c; r.key[3] = k4.d;
+    r.vb[0] = v4.a; r.vb[1] = v4.b; r.vb[2] = v4.c; r.vb[3] = v4.d;
 #pragma unroll
-    for (int h = 0; h < R / 2; ++h) {
-      const int64_t r0 = tile0 + static_cast<int64_t>(h) * blockDim.x * 2 + 2 * threadIdx.x;
-      const ulonglong2 k2 = ldg_stream_u64x2(static_cast<const uint64_t*>(a.keys) + r0);
-      ulonglong2 v2 = make_ulonglong2(0ull, 0ull);
-      if (a.vals) v2 = ldg_stream_u64x2(static_cast<const uint64_t*>(a.vals) + r0);
-      r.key[2 * h] = k2.x; r.key[2 * h + 1] = k2.y;
-      r.vb[2 * h] = v2.x; r.vb[2 * h + 1] = v2.y;
-      r.row[2 * h] = r0; r.row[2 * h + 1] = r0 + 1;
-      if (a.rowids) {
-        const uint2 ri = *reinterpret_cast<const uint2*>(a.rowids + r0);
-        r.row[2 * h] = ri.x; r.row[2 * h + 1] = ri.y;
-      }
-      r.act[2 * h] = r.act[2 * h + 1] = true;
-      r.kv[2 * h] = r.kv[2 * h + 1] = true;
-      r.vv[2 * h] = r.vv[2 * h + 1] = a.vals != nullptr;
-      if (a.vvalid && !a.rowids) {   // value validity: the two adjacent bits of this thread's row pair
-        const int64_t b0 = a.voff + r0;
-        const uint32_t w = static_cast<uint32_t>(a.vvalid[b0 >> 3]) | (static_cast<uint32_t>(a.vvalid[(b0 + 1) >> 3]) << 8);
-        r.vv[2 * h] = (w >> (b0 & 7)) & 1u;
-        r.vv[2 * h + 1] = (w >> (((b0 + 1) & 7) + (((b0 + 1) >> 3) != (b0 >> 3) ? 8 : 0))) & 1u;
-      }
+    for (int j = 0; j < R; ++j) {
+      r.row[j] = r0 + j;
+      r.act[j] = true;
+      r.kv[j] = true;
+      r.vv[j] = a.vals != nullptr;
+    }
+    if (a.rowids) {
+      const uint4 ri = *reinterpret_cast<const uint4*>(a.rowids + r0);
+      r.row[0] = ri.x; r.row[1] = ri.y; r.row[2] = ri.z; r.row[3] = ri.w;
+    }
+    if (a.vvalid && !a.rowids) {   // value validity: the four adjacent bits of this thread's rows
+      const int64_t b0 = a.voff + r0;
+      const uint32_t w = static_cast<uint32_t>(a.vvalid[b0 >> 3]) | (static_cast<uint32_t>(a.vvalid[(b0 + 3) >> 3]) << 8);
+      const uint32_t sh = static_cast<uint32_t>(b0 & 7);
+      const uint32_t bits = (((b0 + 3) >> 3) != (b0 >> 3)) ? (w >> sh) : (static_cast<uint32_t>(a.vvalid[b0 >> 3]) >> sh);
+#pragma unroll
+      for (int j = 0; j < R; ++j) r.vv[j] = (bits >> j) & 1u;
     }
   } else {
 #pragma unroll

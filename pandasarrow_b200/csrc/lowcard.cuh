@@ -818,47 +818,47 @@ __global__ void __launch_bounds__(256) k_lowcard_merge(LmArgs a) {
   }
 }
 
-// Rank: one CTA orders the merged groups by first row (first rows are distinct: a row belongs to
-// exactly one group), writes the GroupResult and status[ST_NGROUPS].
-constexpr int LR_THREADS = 1024;
+// Rank: orders the merged groups by first row (first rows are distinct: a row belongs to exactly one
+// group), writes the GroupResult and status[ST_NGROUPS] (zeroed by the host before the pass).  One warp
+// per group id: the lanes split the comparisons against all first rows (staged in shared memory).
+constexpr int LR_THREADS = 256;
 template <int VC, bool WIDE>
-__global__ void __launch_bounds__(LR_THREADS, 1) k_lowcard_rank(LmArgs a) {
+__global__ void __launch_bounds__(LR_THREADS) k_lowcard_rank(LmArgs a) {
   using Cfg = LcCfg<VC, WIDE>;
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
   __shared__ uint32_t sfirst[Cfg::GP];
-  __shared__ uint32_t s_total;
   if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_ABORT)) return;
+  for (int i = threadIdx.x; i < Cfg::GP; i += LR_THREADS) sfirst[i] = a.m_first[i];
+  __syncthreads();
+  const int id = blockIdx.x * (LR_THREADS / 32) + (threadIdx.x >> 5);
+  if (id >= Cfg::GP) return;
+  const uint32_t f = sfirst[id];
+  if (f == kNoRow) return;
+  const uint32_t lane = lane_id();
+  uint32_t rank = 0;
+  for (int j = lane; j < Cfg::GP; j += 32) rank += sfirst[j] < f;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) rank += __shfl_xor_sync(FULL, rank, d);
+  if (lane != 0) return;
   uint64_t base;
   uint32_t window, rlog;
   const bool dense = lc_dense_mode(a.part.dir.prep, a.part.force_hash, Cfg::GMAX, &base, &window, &rlog);
-  for (int i = threadIdx.x; i < Cfg::GP; i += LR_THREADS) sfirst[i] = a.m_first[i];
-  if (threadIdx.x == 0) s_total = 0;
-  __syncthreads();
-  uint32_t present = 0;
-  for (int id = threadIdx.x; id < Cfg::GP; id += LR_THREADS) {
-    const uint32_t f = sfirst[id];
-    if (f == kNoRow) continue;
-    ++present;
-    uint32_t rank = 0;
-    for (int j = 0; j < Cfg::GP; ++j) rank += sfirst[j] < f;
-    uint64_t key;
-    if (id == Cfg::ID_NULL) key = 0;
-    else if (id == Cfg::ID_EMPTYKEY) key = kEmptyKey;
-    else key = dense ? base + static_cast<uint64_t>(id) : a.part.dir.key_by_id[id];
-    a.out.key[rank] = key;
-    a.out.key_kind[rank] = (id == Cfg::ID_NULL) ? KK_NULL : KK_REGULAR;
-    a.out.sum[rank] = a.m_sum[id];
-    a.out.count[rank] = a.m_count[id];
-    a.out.first_row[rank] = f;
-    if constexpr (WIDE) {
-      a.out.last_row[rank] = a.m_last[id];
-      a.out.min_ord[rank] = a.m_min[id];
-      a.out.max_ord[rank] = a.m_max[id];
-      if constexpr (Cfg::DSUM) { if (a.out.dsum) a.out.dsum[rank] = a.m_dsum[id]; }
-    }
+  uint64_t key;
+  if (id == Cfg::ID_NULL) key = 0;
+  else if (id == Cfg::ID_EMPTYKEY) key = kEmptyKey;
+  else key = dense ? base + static_cast<uint64_t>(id) : a.part.dir.key_by_id[id];
+  a.out.key[rank] = key;
+  a.out.key_kind[rank] = (id == Cfg::ID_NULL) ? KK_NULL : KK_REGULAR;
+  a.out.sum[rank] = a.m_sum[id];
+  a.out.count[rank] = a.m_count[id];
+  a.out.first_row[rank] = f;
+  if constexpr (WIDE) {
+    a.out.last_row[rank] = a.m_last[id];
+    a.out.min_ord[rank] = a.m_min[id];
+    a.out.max_ord[rank] = a.m_max[id];
+    if constexpr (Cfg::DSUM) { if (a.out.dsum) a.out.dsum[rank] = a.m_dsum[id]; }
   }
-  if (present) atomicAdd(&s_total, present);
-  __syncthreads();
-  if (threadIdx.x == 0) a.status[ST_NGROUPS] = s_total;
+  atomicAdd(a.status + ST_NGROUPS, 1u);
 }
 
 }  // namespace pa

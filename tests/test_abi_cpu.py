@@ -65,3 +65,19 @@ def test_host_generator_matches_survey_definition():
     assert (np.diff(ts) > 0).all() and ts[0] >= hg.T0_NS
     # shards concatenate to the whole (row-range sharding)
     assert np.array_equal(np.concatenate([hg.keys(400, 77, 0), hg.keys(600, 77, 400)]), hg.keys(1000, 77))
+
+
+def test_bench_reference_arm_prints_contract_json():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port) runs without a GPU and prints one
+    JSON line with the contract's keys (tiny sample here; the default sample is 100 M rows)."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-rows", "200000", "--groups", "100"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "groupby_agg_rows_per_s" and line["unit"] == "rows/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
