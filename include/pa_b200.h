@@ -92,6 +92,11 @@ struct ArrowDeviceArray {
  *   COUNT  int64 number of non-null values
  *   MIN/MAX input dtype; NaN skipped unless the group is all-NaN; null for an all-null group
  *   FIRST/LAST value at the first/last row of the group, nulls NOT skipped (positional)
+ * Second-stage aggregates (GROUPBY_AGG(product), GROUPBY_NUMERIC_AGG(variance|stddev), dataframe.cpp:1516-1536):
+ * a second pass over keys + values after the fused one, single-GPU handles only.
+ *   PRODUCT  int*->int64 (wraps), uint*->uint64, float/double->double; null for an all-null group
+ *   VARIANCE/STDDEV  double, ddof 0, two-pass (mean, then squared deviations) as arrow::compute's
+ *            scalar kernel; null for an all-null group (the reference's wrapper drops that validity)
  */
 #define PA_AGG_SUM 1u
 #define PA_AGG_MEAN 2u
@@ -100,7 +105,11 @@ struct ArrowDeviceArray {
 #define PA_AGG_MAX 16u
 #define PA_AGG_FIRST 32u
 #define PA_AGG_LAST 64u
-#define PA_AGG_ALL 127u
+#define PA_AGG_ALL 127u          /* everything the fused pass computes */
+#define PA_AGG_PRODUCT 128u
+#define PA_AGG_VARIANCE 256u
+#define PA_AGG_STDDEV 512u
+#define PA_AGG_STAGE2 896u       /* PRODUCT | VARIANCE | STDDEV */
 
 /* ---- kernel path selection (pa_options.path); AUTO is what a caller wants ---- */
 #define PA_PATH_AUTO 0

@@ -281,7 +281,7 @@ Result<std::shared_ptr<Array>> agg_numeric(Groups& g, const std::string& func,
                                            std::shared_ptr<Array>* valid_out) {
   ARROW_ASSIGN_OR_RAISE(int c, g.column_index(column));
   ARROW_RETURN_NOT_OK(g.ensure_gathered(c));
-  if (func == "mean")  // dataframe.cpp:1512
+  if (func == "mean" || func == "variance" || func == "stddev")  // dataframe.cpp:1512,1516,1520
     return agg_numeric_typed<double, arrow::DoubleScalar, arrow::DoubleBuilder>(g, func, c,
                                                                                 nthreads, valid_out);
   if (func == "count")  // dataframe.cpp:1526
@@ -530,7 +530,7 @@ int orc_groupby_row_ids(void* h, ArrowArray* out, ArrowSchema* out_schema) {
 }
 
 // func: "sum" "min" "max" "product"  -> GROUPBY_AGG semantics (nulls kept)
-//       "mean" "count"               -> GROUPBY_NUMERIC_AGG semantics (validity dropped);
+//       "mean" "count" "variance" "stddev" -> GROUPBY_NUMERIC_AGG semantics (validity dropped);
 //                                       out_valid (optional) receives the scalar validity
 //       "first" "last"               -> positional
 // out_valid/out_valid_schema may be NULL.
@@ -542,7 +542,7 @@ int orc_groupby_agg(void* h, const char* func, const char* column, int nthreads,
   Result<std::shared_ptr<Array>> r = Status::NotImplemented("aggregate ", f);
   std::shared_ptr<Array> valid;
   if (f == "sum" || f == "min" || f == "max" || f == "product") r = agg_boxed(*g, f, column, nthreads);
-  else if (f == "mean" || f == "count") r = agg_numeric(*g, f, column, nthreads, out_valid ? &valid : nullptr);
+  else if (f == "mean" || f == "count" || f == "variance" || f == "stddev") r = agg_numeric(*g, f, column, nthreads, out_valid ? &valid : nullptr);
   else if (f == "first") r = agg_position(*g, false, column);
   else if (f == "last") r = agg_position(*g, true, column);
   if (!r.ok()) return fail(r.status());

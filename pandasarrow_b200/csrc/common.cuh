@@ -7,7 +7,8 @@ namespace pa {
 
 // ---- aggregate mask bits (mirror include/pa_b200.h) ----
 constexpr uint32_t AGG_SUM = 1u, AGG_MEAN = 2u, AGG_COUNT = 4u, AGG_MIN = 8u, AGG_MAX = 16u,
-                   AGG_FIRST = 32u, AGG_LAST = 64u;
+                   AGG_FIRST = 32u, AGG_LAST = 64u,
+                   AGG_PRODUCT = 128u, AGG_VARIANCE = 256u, AGG_STDDEV = 512u;   // second-stage aggregates (stage2.cuh)
 
 // Value classes: how a value column is widened for accumulation.
 //   VC_F: float/double -> double sum, min/max on double

@@ -56,6 +56,7 @@ struct GScanArgs {
   int shift;               // 64 - log2(cap)
   uint32_t* status;
   uint32_t agg_mask;
+  uint32_t sm_max_keys;    // shared-memory front table, hash mode: keys admitted before the rest spills
 };
 
 template <bool WIDE>
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) k_smemtab_scan(GScanArgs a) {
           const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(s_key + s);
           if (k == key) { found = true; break; }
           if (k == kEmptyKey) {
-            if (*reinterpret_cast<volatile uint32_t*>(s_misc) >= static_cast<uint32_t>(T::MAX_KEYS)) break;   // table is full enough: spill
+            if (*reinterpret_cast<volatile uint32_t*>(s_misc) >= a.sm_max_keys) break;   // table is full enough: spill
             const uint64_t old = atomicCAS(s_key + s, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
             if (old == kEmptyKey) { atomicAdd(s_misc, 1u); found = true; break; }
             if (old == key) { found = true; break; }

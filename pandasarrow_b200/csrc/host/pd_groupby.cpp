@@ -344,7 +344,7 @@ arrow::Result<arrow::ArrayVector> GroupBy::aggregate(std::string const& column, 
   Exported v(*col);
   if (pa_groupby_aggregate(handle, &v.dev, &v.schema, mask) != PA_OK) return pa_status("aggregate");
   arrow::ArrayVector out;
-  for (uint32_t bit = 1; bit <= PA_AGG_LAST; bit <<= 1) {
+  for (uint32_t bit = 1; bit <= PA_AGG_STDDEV; bit <<= 1) {
     if (!(mask & bit)) continue;
     ArrowArray a;
     ArrowSchema s;
@@ -385,6 +385,13 @@ arrow::Result<DataFrame> GroupBy::min(std::vector<std::string> const& args) { re
 arrow::Result<Series> GroupBy::min(std::string const& arg) { return seriesOf(arg, kMin, false, true); }
 arrow::Result<DataFrame> GroupBy::sum(std::vector<std::string> const& args) { return frameOf(args, kSum, false, true); }
 arrow::Result<Series> GroupBy::sum(std::string const& arg) { return seriesOf(arg, kSum, false, true); }
+// GROUPBY_AGG(product) dataframe.cpp:1536; GROUPBY_NUMERIC_AGG(stddev|variance, double) :1516,1520 (validity dropped)
+arrow::Result<DataFrame> GroupBy::product(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_PRODUCT, false, true); }
+arrow::Result<Series> GroupBy::product(std::string const& arg) { return seriesOf(arg, PA_AGG_PRODUCT, false, true); }
+arrow::Result<DataFrame> GroupBy::variance(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_VARIANCE, true, true); }
+arrow::Result<Series> GroupBy::variance(std::string const& arg) { return seriesOf(arg, PA_AGG_VARIANCE, true, true); }
+arrow::Result<DataFrame> GroupBy::stddev(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_STDDEV, true, true); }
+arrow::Result<Series> GroupBy::stddev(std::string const& arg) { return seriesOf(arg, PA_AGG_STDDEV, true, true); }
 // dataframe.cpp:1698-1806: first(vector) is indexed by the keys, first(string) is not (:1748),
 // last(vector) is not (:1781), last(string) is (:1805)
 arrow::Result<DataFrame> GroupBy::first(std::vector<std::string> const& args) { return frameOf(args, kFirst, false, true); }
@@ -438,6 +445,9 @@ arrow::Result<DataFrame> Resampler::frameOfAll(std::string const& name) {
   else if (name == "sum") r = GroupBy::sum(cols);
   else if (name == "first") r = GroupBy::first(cols);
   else if (name == "last") r = GroupBy::last(cols);
+  else if (name == "product") r = GroupBy::product(cols);
+  else if (name == "variance") r = GroupBy::variance(cols);
+  else if (name == "stddev") r = GroupBy::stddev(cols);
   ARROW_RETURN_NOT_OK(r.status());
   return r->setIndex(unique());
 }

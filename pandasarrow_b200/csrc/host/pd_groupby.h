@@ -16,8 +16,9 @@
 // dataframe.cpp:1354-1510) is built lazily from the per-row group ids the GPU returns
 // (pa_groupby_row_ids = what Grouper::Consume returned) with Arrow's MakeGroupings / ApplyGroupings,
 // exactly the calls the reference makes after Consume (dataframe.cpp:1539-1569,1586-1597).
-// Not carried over (SURVEY.md §8f "next"): the aggregates outside sum/mean/count/min/max/first/
-// last/min_max; those methods exist and return arrow::Status::NotImplemented.
+// product / variance / stddev run a second device pass (stage2.cuh).  Not carried over (SURVEY.md §8f
+// "next"): all/any/approximate_median/count_distinct/mode/tdigest; those methods exist and return
+// arrow::Status::NotImplemented.
 #pragma once
 #include <arrow/api.h>
 
@@ -186,13 +187,19 @@ class GroupBy {
   arrow::Result<DataFrame> min_max(std::string const& arg);
   arrow::Result<DataFrame> sum(std::vector<std::string> const& args);
   arrow::Result<Series> sum(std::string const& arg);
+  arrow::Result<DataFrame> product(std::vector<std::string> const& args);
+  arrow::Result<Series> product(std::string const& arg);
+  arrow::Result<DataFrame> variance(std::vector<std::string> const& args);
+  arrow::Result<Series> variance(std::string const& arg);
+  arrow::Result<DataFrame> stddev(std::vector<std::string> const& args);
+  arrow::Result<Series> stddev(std::string const& arg);
 
   // declared by the reference, outside this path's CUDA scope
 #define PD_NOT_ON_GPU(name)                                                                                   \
   arrow::Result<DataFrame> name(std::vector<std::string> const&) { return arrow::Status::NotImplemented(#name " is not part of the B200 group-by path"); } \
   arrow::Result<Series> name(std::string const&) { return arrow::Status::NotImplemented(#name " is not part of the B200 group-by path"); }
   PD_NOT_ON_GPU(all) PD_NOT_ON_GPU(any) PD_NOT_ON_GPU(approximate_median) PD_NOT_ON_GPU(count_distinct)
-  PD_NOT_ON_GPU(product) PD_NOT_ON_GPU(mode) PD_NOT_ON_GPU(stddev) PD_NOT_ON_GPU(variance) PD_NOT_ON_GPU(tdigest)
+  PD_NOT_ON_GPU(mode) PD_NOT_ON_GPU(tdigest)
 #undef PD_NOT_ON_GPU
   // ---- materialised groups (group_by.h:38-83, 141-162; dataframe.cpp:1430-1510) ----
   arrow::ArrayVector group(ScalarPtr const& key) const;                       // every column's rows of one group
@@ -252,7 +259,7 @@ class Resampler : protected GroupBy {
 #define PD_RESAMPLE_FN(name) \
   arrow::Result<DataFrame> name() { return frameOfAll(#name); }
   PD_RESAMPLE_FN(mean) PD_RESAMPLE_FN(count) PD_RESAMPLE_FN(max) PD_RESAMPLE_FN(min) PD_RESAMPLE_FN(sum)
-  PD_RESAMPLE_FN(first) PD_RESAMPLE_FN(last)
+  PD_RESAMPLE_FN(first) PD_RESAMPLE_FN(last) PD_RESAMPLE_FN(product) PD_RESAMPLE_FN(variance) PD_RESAMPLE_FN(stddev)
 #undef PD_RESAMPLE_FN
   arrow::Result<DataFrame> min_max() { return GroupBy::min_max(getDF().columnNames()); }
   using GroupBy::apply;

@@ -6,7 +6,7 @@
 // scan kernel afterwards walks the table region by region and its working set stays L2 resident:
 //   k_part_hist     rows per partition (shared-memory histogram per CTA, one global add per bin)
 //   k_part_offsets  exclusive prefix -> start offset (write cursor) of every partition
-//   k_part_scatter  per tile of 8192 rows: shared-memory histogram gives every row its rank inside the
+//   k_part_scatter  per tile of 4096 rows: shared-memory histogram gives every row its rank inside the
 //                   tile's run for its partition; the tile is regrouped in shared memory and written
 //                   out as contiguous runs (one global cursor add per partition and tile) together
 //                   with the original row numbers, which first/last need
@@ -18,9 +18,10 @@
 
 namespace pa {
 
-constexpr int PT_THREADS = 1024;
+constexpr int PH_THREADS = 1024;                      // histogram kernel
+constexpr int PT_THREADS = 512;
 constexpr int PT_ROWS = 8;                            // rows per thread
-constexpr int PT_TILE = PT_THREADS * PT_ROWS;         // 8192 rows per CTA tile
+constexpr int PT_TILE = PT_THREADS * PT_ROWS;         // 4096 rows per CTA tile
 constexpr int PT_MAX_PARTS = 1024;
 
 struct PartArgs {
@@ -38,20 +39,20 @@ __device__ __forceinline__ uint32_t part_of(uint64_t key, int log_parts) {
   return static_cast<uint32_t>(gtable_mix(key) >> (64 - log_parts));
 }
 
-__global__ void __launch_bounds__(PT_THREADS) k_part_hist(PartArgs a) {
+__global__ void __launch_bounds__(PH_THREADS) k_part_hist(PartArgs a) {
   __shared__ unsigned int s_hist[PT_MAX_PARTS];
   const int parts = 1 << a.log_parts;
-  for (int i = threadIdx.x; i < parts; i += PT_THREADS) s_hist[i] = 0;
+  for (int i = threadIdx.x; i < parts; i += PH_THREADS) s_hist[i] = 0;
   __syncthreads();
   const int64_t n2 = a.n / 2;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(PT_THREADS) + threadIdx.x; i < n2; i += static_cast<int64_t>(gridDim.x) * PT_THREADS) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(PH_THREADS) + threadIdx.x; i < n2; i += static_cast<int64_t>(gridDim.x) * PH_THREADS) {
     const ulonglong2 k = ldg_stream_u64x2(a.keys + 2 * i);
     atomicAdd(&s_hist[part_of(k.x, a.log_parts)], 1u);
     atomicAdd(&s_hist[part_of(k.y, a.log_parts)], 1u);
   }
   if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&s_hist[part_of(a.keys[a.n - 1], a.log_parts)], 1u);
   __syncthreads();
-  for (int i = threadIdx.x; i < parts; i += PT_THREADS)
+  for (int i = threadIdx.x; i < parts; i += PH_THREADS)
     if (s_hist[i]) atomicAdd(a.counts + i, static_cast<unsigned long long>(s_hist[i]));
 }
 
@@ -73,23 +74,28 @@ __global__ void __launch_bounds__(PT_MAX_PARTS) k_part_offsets(unsigned long lon
 struct PtSmem {
   static constexpr size_t OFF_KEY = 0;
   static constexpr size_t OFF_VAL = OFF_KEY + sizeof(uint64_t) * PT_TILE;
-  static constexpr size_t OFF_ROW = OFF_VAL + sizeof(uint64_t) * PT_TILE;
-  static constexpr size_t OFF_DEST = OFF_ROW + sizeof(uint32_t) * PT_TILE;
-  static constexpr size_t OFF_HIST = OFF_DEST + sizeof(uint32_t) * PT_TILE;
+  static constexpr size_t OFF_DELTA = OFF_VAL + sizeof(uint64_t) * PT_TILE;
+  static constexpr size_t OFF_ROW = OFF_DELTA + sizeof(unsigned long long) * PT_MAX_PARTS;
+  static constexpr size_t OFF_HIST = OFF_ROW + sizeof(uint32_t) * PT_TILE;
   static constexpr size_t OFF_OFF = OFF_HIST + sizeof(uint32_t) * PT_MAX_PARTS;
-  static constexpr size_t OFF_BASE = OFF_OFF + sizeof(uint32_t) * PT_MAX_PARTS;
-  static constexpr size_t TOTAL = OFF_BASE + sizeof(unsigned long long) * PT_MAX_PARTS;
+  static constexpr size_t TOTAL = OFF_OFF + sizeof(uint32_t) * PT_MAX_PARTS;
 };
+static_assert(2 * (PtSmem::TOTAL + 1024) <= 228 * 1024, "two scatter CTAs per SM");
 
-__global__ void __launch_bounds__(PT_THREADS, 1) k_part_scatter(PartArgs a) {
+// Two CTAs per SM: the phases of a tile are separated by barriers (load -> rank -> claim -> regroup -> write),
+// so a second resident CTA keeps the memory system busy while the first one regroups.
+__global__ void __launch_bounds__(PT_THREADS, 2) k_part_scatter(PartArgs a) {
   extern __shared__ __align__(16) unsigned char pt_smem[];
   uint64_t* st_key = reinterpret_cast<uint64_t*>(pt_smem + PtSmem::OFF_KEY);
   uint64_t* st_val = reinterpret_cast<uint64_t*>(pt_smem + PtSmem::OFF_VAL);
   uint32_t* st_row = reinterpret_cast<uint32_t*>(pt_smem + PtSmem::OFF_ROW);
-  uint32_t* st_dest = reinterpret_cast<uint32_t*>(pt_smem + PtSmem::OFF_DEST);
   unsigned int* s_hist = reinterpret_cast<unsigned int*>(pt_smem + PtSmem::OFF_HIST);
   unsigned int* s_off = reinterpret_cast<unsigned int*>(pt_smem + PtSmem::OFF_OFF);
-  unsigned long long* s_base = reinterpret_cast<unsigned long long*>(pt_smem + PtSmem::OFF_BASE);
+  // s_delta[p] = (start of this tile's run for p in the output) - (start of the run in the regrouped tile):
+  // regrouped position i of partition p goes to output position s_delta[p] + i
+  unsigned long long* s_delta = reinterpret_cast<unsigned long long*>(pt_smem + PtSmem::OFF_DELTA);
+  __shared__ unsigned int s_wsum[PT_THREADS / 32];
+  constexpr int BINS = PT_MAX_PARTS / PT_THREADS;    // histogram bins per thread in the scan
   const int parts = 1 << a.log_parts;
   const int64_t ntiles = (a.n + PT_TILE - 1) / PT_TILE;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -122,33 +128,44 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part_scatter(PartArgs a) {
       }
     }
     __syncthreads();
-    // exclusive scan of the tile histogram (1024 bins, one per thread) + claim the output ranges
+    // exclusive scan of the tile histogram (BINS adjacent bins per thread) + claim the output ranges
     {
-      const unsigned int mine = threadIdx.x < parts ? s_hist[threadIdx.x] : 0u;
-      unsigned int incl = mine;
+      unsigned int mine[BINS], tot = 0;
+#pragma unroll
+      for (int b = 0; b < BINS; ++b) {
+        const int bin = threadIdx.x * BINS + b;
+        mine[b] = bin < parts ? s_hist[bin] : 0u;
+        tot += mine[b];
+      }
+      unsigned int incl = tot;
       const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if (lane >= static_cast<uint32_t>(d)) incl += v;
       }
-      __shared__ unsigned int s_wsum[32];
       if (lane == 31) s_wsum[w] = incl;
       __syncthreads();
       if (w == 0) {
-        unsigned int x = s_wsum[lane];
+        unsigned int x = lane < PT_THREADS / 32 ? s_wsum[lane] : 0u;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, x, d);
           if (lane >= static_cast<uint32_t>(d)) x += v;
         }
-        s_wsum[lane] = x;
+        if (lane < PT_THREADS / 32) s_wsum[lane] = x;
       }
       __syncthreads();
-      const unsigned int excl = incl - mine + (w ? s_wsum[w - 1] : 0u);
-      if (threadIdx.x < parts) {
-        s_off[threadIdx.x] = excl;
-        s_base[threadIdx.x] = mine ? atomicAdd(a.counts + threadIdx.x, static_cast<unsigned long long>(mine)) : 0ull;
+      unsigned int excl = incl - tot + (w ? s_wsum[w - 1] : 0u);
+#pragma unroll
+      for (int b = 0; b < BINS; ++b) {
+        const int bin = threadIdx.x * BINS + b;
+        if (bin < parts) {
+          s_off[bin] = excl;
+          const unsigned long long base = mine[b] ? atomicAdd(a.counts + bin, static_cast<unsigned long long>(mine[b])) : 0ull;
+          s_delta[bin] = base - excl;
+        }
+        excl += mine[b];
       }
     }
     __syncthreads();
@@ -156,19 +173,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_part_scatter(PartArgs a) {
 #pragma unroll
     for (int j = 0; j < PT_ROWS; ++j) {
       if (pr[j] == 0xFFFFFFFFu) continue;
-      const uint32_t p = pr[j] >> 13, rank = pr[j] & 0x1FFFu;
-      const uint32_t pos = s_off[p] + rank;
+      const uint32_t pos = s_off[pr[j] >> 13] + (pr[j] & 0x1FFFu);
       const int r = 2 * (threadIdx.x + (j >> 1) * PT_THREADS) + (j & 1);
       st_key[pos] = key[j];
       st_val[pos] = val[j];
       st_row[pos] = static_cast<uint32_t>(tile0 + r);
-      st_dest[pos] = static_cast<uint32_t>(s_base[p] + rank);
     }
     __syncthreads();
-    // contiguous runs out
+    // contiguous runs out (the partition of a regrouped row is recomputed from its key)
     for (int i = threadIdx.x; i < cnt; i += PT_THREADS) {
-      const uint32_t d = st_dest[i];
-      a.out_keys[d] = st_key[i];
+      const uint64_t k = st_key[i];
+      const unsigned long long d = s_delta[part_of(k, a.log_parts)] + static_cast<unsigned long long>(i);
+      a.out_keys[d] = k;
       a.out_vals[d] = st_val[i];
       a.out_rows[d] = st_row[i];
     }

@@ -43,34 +43,29 @@ __global__ void __launch_bounds__(256) k_rowid_build(RowIdArgs a) {
   }
 }
 
+// Group id of row i (0xFFFFFFFF if its key was never aggregated — cannot happen for a finished handle).
+__device__ __forceinline__ uint32_t rowid_lookup(const RowIdArgs& a, int64_t i) {
+  uint64_t key = load_key_rt(a.keys, i, a.kw);
+  if (a.kvalid && !bit_at(a.kvalid, a.koff + i)) return a.special[0];
+  if (a.resample) {
+    const int64_t tp = static_cast<int64_t>(key) - (a.rs.closed_right ? 1 : 0);
+    const int64_t b = (tp - a.rs.first) / a.rs.freq;
+    key = static_cast<uint64_t>(a.rs.first + b * a.rs.freq + a.rs.label_off);
+  }
+  if (key == kEmptyKey) return a.special[1];
+  uint64_t s = gtable_home(key, a.shift);
+  for (;;) {
+    const uint64_t k = __ldg(a.tkeys + s);
+    if (k == key) return __ldg(a.tranks + s);
+    if (k == kEmptyKey) return 0xFFFFFFFFu;
+    s = (s + 1) & a.cap_mask;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_rowid_scan(RowIdArgs a) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (; i < a.n; i += stride) {
-    uint64_t key = load_key_rt(a.keys, i, a.kw);
-    uint32_t id = 0xFFFFFFFFu;
-    if (a.kvalid && !bit_at(a.kvalid, a.koff + i)) {
-      id = a.special[0];
-    } else {
-      if (a.resample) {
-        const int64_t tp = static_cast<int64_t>(key) - (a.rs.closed_right ? 1 : 0);
-        const int64_t b = (tp - a.rs.first) / a.rs.freq;
-        key = static_cast<uint64_t>(a.rs.first + b * a.rs.freq + a.rs.label_off);
-      }
-      if (key == kEmptyKey) {
-        id = a.special[1];
-      } else {
-        uint64_t s = gtable_home(key, a.shift);
-        for (;;) {
-          const uint64_t k = __ldg(a.tkeys + s);
-          if (k == key) { id = __ldg(a.tranks + s); break; }
-          if (k == kEmptyKey) break;   // cannot happen for a key that was aggregated
-          s = (s + 1) & a.cap_mask;
-        }
-      }
-    }
-    a.out[i] = id;
-  }
+  for (; i < a.n; i += stride) a.out[i] = rowid_lookup(a, i);
 }
 
 }  // namespace pa

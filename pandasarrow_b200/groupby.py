@@ -302,6 +302,10 @@ class GroupBy:
     def max(self, arg): return self._agg("max", arg)
     def first(self, arg): return self._agg("first", arg)
     def last(self, arg): return self._agg("last", arg)
+    # second-stage aggregates (group_by.h:88-136 / dataframe.cpp:1516-1536): one extra pass over keys + values
+    def product(self, arg): return self._agg("product", arg)
+    def variance(self, arg): return self._agg("variance", arg)
+    def stddev(self, arg): return self._agg("stddev", arg)
 
     def min_max(self, arg):
         """GroupBy::min_max (dataframe.cpp:1602-1696): one pass, two columns."""
@@ -359,6 +363,9 @@ class Resampler(GroupBy):
     def max(self, arg=None): return self._all("max") if arg is None else super().max(arg)
     def first(self, arg=None): return self._all("first") if arg is None else super().first(arg)
     def last(self, arg=None): return self._all("last") if arg is None else super().last(arg)
+    def product(self, arg=None): return self._all("product") if arg is None else super().product(arg)
+    def variance(self, arg=None): return self._all("variance") if arg is None else super().variance(arg)
+    def stddev(self, arg=None): return self._all("stddev") if arg is None else super().stddev(arg)
 
 
 def resample(frame, index: Column, freq_ns: int, closed_right: bool = False, label_right: bool = False,

@@ -96,7 +96,7 @@ static void test_make_groups_and_aggregates() {
 
   REQUIRE_THROWS(pd::GroupBy("nope", df));                                 // group_by.h:27-30
   REQUIRE(!groupby.sum("nope").ok());
-  REQUIRE(groupby.stddev("age").status().IsNotImplemented());
+  REQUIRE(groupby.count_distinct("age").status().IsNotImplemented());
 }
 
 // dataframe_resample_test.cpp:252-305 — OHLC bars through group_by
@@ -181,6 +181,32 @@ static void test_apply_callbacks_and_groups() {
   REQUIRE(doubled.values<int64_t>() == (std::vector<int64_t>{20, 18, 14, 12, 10, 16, 8, 6, 4, 2}));
 }
 
+// GROUPBY_AGG(product) / GROUPBY_NUMERIC_AGG(variance|stddev) (dataframe.cpp:1516-1536): expected values from the
+// same arrow::compute scalar kernels the reference calls per group
+static pd::ArrayPtr int32_array(std::vector<int32_t> const& v) {
+  arrow::Int32Builder b;
+  pd::ThrowOnFailure(b.AppendValues(v));
+  return pd::ReturnOrThrowOnFailure(b.Finish());
+}
+
+static void test_second_stage_aggregates() {
+  auto df = people();
+  pd::GroupBy groupby("gender", df);
+  auto male = pd::ReturnOrThrowOnFailure(arrow::compute::CallFunction("variance", {int32_array({16, 10, 20, 40, 15, 35, 45})}));
+  auto female = pd::ReturnOrThrowOnFailure(arrow::compute::CallFunction("variance", {int32_array({10, 30, 25})}));
+  const double vm = male.scalar_as<arrow::DoubleScalar>().value, vf = female.scalar_as<arrow::DoubleScalar>().value;
+  auto var = pd::ReturnOrThrowOnFailure(groupby.variance("age"));
+  REQUIRE(std::fabs(var[0].as<double>() - vm) <= 1e-12 * vm);
+  REQUIRE(std::fabs(var[1].as<double>() - vf) <= 1e-12 * vf);
+  auto sd = pd::ReturnOrThrowOnFailure(groupby.stddev({"age"s, "height"s}));
+  REQUIRE(std::fabs(sd["age"][0].as<double>() - std::sqrt(vm)) <= 1e-12 * std::sqrt(vm));
+  REQUIRE(sd["height"].size() == 2);
+  auto prod = pd::ReturnOrThrowOnFailure(groupby.product("age"));
+  REQUIRE(prod[0].as<int64_t>() == int64_t(16) * 10 * 20 * 40 * 15 * 35 * 45);
+  REQUIRE(prod[1].as<int64_t>() == int64_t(10) * 30 * 25);
+  REQUIRE(!groupby.tdigest("age").ok());                      // still outside the path: NotImplemented, not a crash
+}
+
 // series_resample_test.cpp:12-70
 static void test_resample_series() {
   auto index = pd::date_range(pd::ns_from_ymd(2000, 1, 1), 9);
@@ -254,6 +280,7 @@ int main() {
     test_bardata();
     test_apply_sums();
     test_apply_callbacks_and_groups();
+    test_second_stage_aggregates();
     test_resample_series();
     test_downsample();
   } catch (std::exception const& e) {
