@@ -706,12 +706,15 @@ int run_stage2(pa_groupby* g, const Column* val, uint32_t ext) {
   a.mean = mean.as<double>();
   a.m2 = m2.as<double>();
   a.prod = prod.as<unsigned long long>();
-  a.use_smem = G <= S2_SMEM_G ? 1u : 0u;
-  a.combine = G <= S2_COMBINE_G ? 1u : 0u;
+  a.use_smem = G <= S2_SMEM_SLOTS ? 1u : 0u;
+  a.rlog = 0;
+  // (replicas only while they stay small: the key -> id lookups want the L1 that shared memory takes away —
+  //  1000 groups measured 5.7 ms per 1 B rows unreplicated against 7.3 ms with 4 replicas)
+  while (a.use_smem && a.rlog < 5 && (static_cast<uint64_t>(G) << (a.rlog + 1)) <= S2_REPL_SLOTS) ++a.rlog;
   if (g->n > 0) {
-    const size_t smem = a.use_smem ? static_cast<size_t>(G) * 16 : 0;
+    const size_t smem = a.use_smem ? (static_cast<size_t>(G) << a.rlog) * 16 : 0;
     auto kern = vc == VC_F ? k_stage2<VC_F> : (vc == VC_I ? k_stage2<VC_I> : k_stage2<VC_U>);
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S2_SMEM_G * 16)));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S2_SMEM_SLOTS * 16)));
     int per_sm = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, S2_THREADS, smem));
     const int64_t want = (g->n + S2_THREADS - 1) / S2_THREADS;

@@ -10,10 +10,11 @@
 // whichever path fits the key cardinality); this file is the second pass.  It looks every row's key up
 // in a read-only key -> group table built from the finished GroupResult (rowids.cuh), subtracts the
 // group mean and accumulates (x - mean)^2 — and the running product — per group:
-//   few groups (<= S2_COMBINE_G)   equal ids are first combined inside the warp (butterfly per distinct id),
-//                                  one shared-memory update per distinct id and warp
-//   G <= S2_SMEM_G                 CTA-shared accumulators (shared-memory atomics; the product is a CAS loop),
-//                                  flushed with one global update per group and CTA
+//   G <= S2_SMEM_SLOTS             CTA-shared accumulators (shared-memory atomics; the product is a CAS loop),
+//                                  replicated R = 2^rlog times (slot = id * R + lane % R, R <= 32 and
+//                                  G * R <= S2_REPL_SLOTS) so that the lanes of a warp hitting one
+//                                  group do not serialise on one address; the replicas are folded in slot
+//                                  order and flushed with one global update per group and CTA
 //   more                           L2 atomics straight into the per-group arrays
 // m2 is a sum of non-negative terms (condition number 1), so its value is insensitive to the order of
 // summation to ~n eps; the product of floats is order dependent in the last bits like every
@@ -24,8 +25,8 @@
 namespace pa {
 
 constexpr int S2_THREADS = 512;
-constexpr uint32_t S2_SMEM_G = 4096;     // x 16 bytes of shared memory
-constexpr uint32_t S2_COMBINE_G = 64;
+constexpr uint32_t S2_SMEM_SLOTS = 4096;     // x 16 bytes of shared memory
+constexpr uint32_t S2_REPL_SLOTS = 1024;     // replicate the accumulators only up to this many slots
 
 struct Stage2Args {
   RowIdArgs ids;              // lookup table + key column (`out` unused)
@@ -36,7 +37,8 @@ struct Stage2Args {
   const double* mean;         // [G]
   double* m2;                 // [G] zero-initialised, or null
   unsigned long long* prod;   // [G] initialised to one, or null
-  uint32_t use_smem, combine;
+  uint32_t use_smem;
+  int rlog;                   // shared-memory accumulators: log2 of the replication
 };
 
 template <int VC>
@@ -77,65 +79,42 @@ template <int VC>
 __global__ void __launch_bounds__(S2_THREADS) k_stage2(Stage2Args a) {
   extern __shared__ __align__(16) unsigned char s2_smem[];
   const uint32_t G = a.ids.G;
+  const uint32_t nslots = G << a.rlog;
   double* s_m2 = reinterpret_cast<double*>(s2_smem);
-  unsigned long long* s_prod = reinterpret_cast<unsigned long long*>(s2_smem + sizeof(double) * G);
+  unsigned long long* s_prod = reinterpret_cast<unsigned long long*>(s2_smem + sizeof(double) * nslots);
   const unsigned long long one = s2_one<VC>();
   if (a.use_smem) {
-    for (uint32_t i = threadIdx.x; i < G; i += S2_THREADS) { s_m2[i] = 0.0; s_prod[i] = one; }
+    for (uint32_t i = threadIdx.x; i < nslots; i += S2_THREADS) { s_m2[i] = 0.0; s_prod[i] = one; }
     __syncthreads();
   }
-  auto accumulate = [&](uint32_t id, double d2, unsigned long long p) {
-    if (a.use_smem) {
-      if (a.m2) atomicAdd(s_m2 + id, d2);
-      if (a.prod) s2_atomic_mul<VC>(s_prod + id, p);
-    } else {
-      if (a.m2) atomicAdd(a.m2 + id, d2);
-      if (a.prod) s2_atomic_mul<VC>(a.prod + id, p);
-    }
-  };
+  const uint32_t rep = lane_id() & ((1u << a.rlog) - 1u);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * S2_THREADS;
-  const int64_t n_round = (a.ids.n + 31) / 32 * 32;    // whole warps stay in the loop together (shuffles below)
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(S2_THREADS) + threadIdx.x; i < n_round; i += stride) {
-    bool act = i < a.ids.n;
-    uint32_t id = 0xFFFFFFFFu;
-    double d2 = 0.0;
-    unsigned long long p = one;
-    if (act) {
-      id = rowid_lookup(a.ids, i);
-      act = id != 0xFFFFFFFFu && (!a.vvalid || bit_at(a.vvalid, a.voff + i));
-    }
-    if (act) {
-      const uint64_t bits = load_wide_rt<VC>(a.vals, i, a.vw);
-      const double d = Wide<VC>::as_double(bits) - __ldg(a.mean + id);
-      d2 = d * d;
-      p = bits;
-    }
-    if (a.combine) {
-      uint32_t todo = __ballot_sync(0xFFFFFFFFu, act);
-      while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const uint32_t cur = __shfl_sync(0xFFFFFFFFu, id, leader);
-        const bool mine = act && id == cur;
-        const uint32_t peers = __ballot_sync(0xFFFFFFFFu, mine);
-        double r2 = mine ? d2 : 0.0;
-        unsigned long long rp = mine ? p : one;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          r2 += __shfl_xor_sync(0xFFFFFFFFu, r2, o);
-          rp = s2_mul<VC>(rp, __shfl_xor_sync(0xFFFFFFFFu, rp, o));
-        }
-        if (static_cast<int>(lane_id()) == leader) accumulate(cur, r2, rp);
-        todo &= ~peers;
-      }
-    } else if (act) {
-      accumulate(id, d2, p);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(S2_THREADS) + threadIdx.x; i < a.ids.n; i += stride) {
+    const uint32_t id = rowid_lookup(a.ids, i);
+    if (id == 0xFFFFFFFFu || (a.vvalid && !bit_at(a.vvalid, a.voff + i))) continue;
+    const uint64_t bits = load_wide_rt<VC>(a.vals, i, a.vw);
+    const double d = Wide<VC>::as_double(bits) - __ldg(a.mean + id);
+    if (a.use_smem) {
+      const uint32_t s = (id << a.rlog) | rep;
+      if (a.m2) atomicAdd(s_m2 + s, d * d);
+      if (a.prod) s2_atomic_mul<VC>(s_prod + s, bits);
+    } else {
+      if (a.m2) atomicAdd(a.m2 + id, d * d);
+      if (a.prod) s2_atomic_mul<VC>(a.prod + id, bits);
     }
   }
   if (a.use_smem) {
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < G; i += S2_THREADS) {
-      if (a.m2 && s_m2[i] != 0.0) atomicAdd(a.m2 + i, s_m2[i]);
-      if (a.prod && s_prod[i] != one) s2_atomic_mul<VC>(a.prod + i, s_prod[i]);
+    const uint32_t R = 1u << a.rlog;
+    for (uint32_t g = threadIdx.x; g < G; g += S2_THREADS) {
+      double m = 0.0;
+      unsigned long long p = one;
+      for (uint32_t r = 0; r < R; ++r) {
+        m += s_m2[(g << a.rlog) | r];
+        p = s2_mul<VC>(p, s_prod[(g << a.rlog) | r]);
+      }
+      if (a.m2 && m != 0.0) atomicAdd(a.m2 + g, m);
+      if (a.prod && p != one) s2_atomic_mul<VC>(a.prod + g, p);
     }
   }
 }
