@@ -175,6 +175,22 @@ int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, st
  * first-appearance order.  Host array of length n_rows. */
 int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema);
 
+/* Grouper::MakeGroupings equivalent (dataframe.cpp:1586-1588): the row numbers of every group, group-contiguous
+ * in result (first-appearance) order and ascending inside a group — the values (`rows`, int32[n_rows]) and the
+ * offsets (int32[num_groups + 1]) of the ListArray<int32> the reference builds.  `rows` may be NULL (offsets only).
+ * Built on the device on first use (row ids -> stable radix sort) and kept on the handle. */
+int pa_groupby_groupings(pa_groupby* g, struct ArrowArray* offsets, struct ArrowSchema* offsets_schema,
+                         struct ArrowArray* rows, struct ArrowSchema* rows_schema);
+
+/* Grouper::ApplyGroupings equivalent for one column (dataframe.cpp:1546,1562): the column gathered on the device
+ * into the order of pa_groupby_groupings — group j is the slice [offsets[j], offsets[j+1]).  Fixed-width columns
+ * (1/2/4/8-byte elements), validity carried along.  Host array of the column's own type, n_rows long. */
+int pa_groupby_take_grouped(pa_groupby* g, const struct ArrowDeviceArray* column, const struct ArrowSchema* schema,
+                            struct ArrowArray* out, struct ArrowSchema* out_schema);
+
+/* Device time (ms) of building the groupings, and of the last pa_groupby_take_grouped gather kernel. */
+int pa_groupby_groupings_timing(pa_groupby* g, double* build_ms, double* take_ms);
+
 /* Global row number (pa_options.row_base + local row) of the first row of every group, uint64, in
  * result order.  For merged handles: the minimum over all ranks. */
 int pa_groupby_first_rows(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema);

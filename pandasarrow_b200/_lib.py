@@ -21,7 +21,7 @@ EXPORTS = [
     "pa_last_error", "pa_version", "pa_options_init", "pa_device_count", "pa_groupby_create",
     "pa_groupby_num_groups", "pa_groupby_unique", "pa_groupby_aggregate", "pa_groupby_aggregate_async",
     "pa_groupby_fetch",
-    "pa_groupby_row_ids", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
+    "pa_groupby_row_ids", "pa_groupby_groupings", "pa_groupby_take_grouped", "pa_groupby_groupings_timing", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
     "pa_groupby_sync",
     "pa_groupby_destroy", "pa_resample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
     "pa_merge_create", "pa_groupby_partials_export_padded", "pa_merge_create_padded", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
@@ -88,6 +88,9 @@ def load():
     L.pa_groupby_fetch.argtypes = [P, C.c_uint32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_first_rows.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_row_ids.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
+    L.pa_groupby_groupings.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema), C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
+    L.pa_groupby_take_grouped.argtypes = [P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
+    L.pa_groupby_groupings_timing.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pa_groupby_last_timing.argtypes = [P, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.pa_groupby_last_path.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.pa_groupby_last_detail.argtypes = [P, C.POINTER(C.c_int32)]

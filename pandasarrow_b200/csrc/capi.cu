@@ -23,6 +23,7 @@
 #include "resample.cuh"
 #include "rowids.cuh"
 #include "stage2.cuh"
+#include "groupings.cuh"
 
 using namespace pa;
 
@@ -232,7 +233,10 @@ struct pa_groupby {
   std::string pm_vfmt, pm_kfmt;
   float last_total_ms = 0;
   float stage_ms[4] = {0, 0, 0, 0};
-  cudaEvent_t ev[6] = {};
+  cudaEvent_t ev[10] = {};                // [6..7]: groupings build, [8..9]: last grouped take
+  // group materialisation (groupings.cuh), built on first use; keys are immutable so it never goes stale
+  DevBuf grp_order, grp_offsets;
+  bool have_groupings = false;
 };
 
 namespace {
@@ -1298,6 +1302,110 @@ int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema
     CUDA_TRY(cudaGetLastError());
   }
   return export_host(st, "I", 4, static_cast<uint32_t>(g->n), ids.p, nullptr, out, out_schema);
+}
+
+namespace {
+// ids -> stable sort by id -> (order, offsets), cached on the handle
+int ensure_groupings(pa_groupby* g) {
+  if (g->have_groupings) return PA_OK;
+  if (g->merged) return set_err(PA_ERR_STATE, "groupings exist on the rank that holds the rows, not on a merged handle");
+  if (g->n >= (1ll << 31)) return set_err(PA_ERR_INVALID, "groupings use int32 offsets like the reference's ListArray<int32>: at most 2^31 - 1 rows");
+  cudaStream_t st = g->stream;
+  const uint32_t G = g->G;
+  const int64_t n = g->n;
+  CUDA_TRY(cudaEventRecord(g->ev[6], st));
+  RowLookup lk;
+  PA_TRY(build_row_lookup(g, &lk));
+  DevBuf ids, sorted_ids, iota, tmp;
+  const size_t nb = static_cast<size_t>(std::max<int64_t>(n, 1)) * 4;
+  PA_TRY(ids.alloc(nb, st));
+  PA_TRY(sorted_ids.alloc(nb, st));
+  PA_TRY(iota.alloc(nb, st));
+  PA_TRY(g->grp_order.alloc(nb, st));
+  PA_TRY(g->grp_offsets.alloc((static_cast<size_t>(G) + 1) * 4, st));
+  if (n > 0) {
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+    lk.a.out = ids.as<uint32_t>();
+    k_rowid_scan<<<grid, 256, 0, st>>>(lk.a);
+    CUDA_TRY(cudaGetLastError());
+    k_iota_u32<<<grid, 256, 0, st>>>(iota.as<uint32_t>(), n);
+    CUDA_TRY(cudaGetLastError());
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < static_cast<uint64_t>(G)) ++bits;
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ids.as<uint32_t>(), sorted_ids.as<uint32_t>(), iota.as<uint32_t>(),
+                                             g->grp_order.as<uint32_t>(), static_cast<int>(n), 0, bits, st));
+    PA_TRY(tmp.alloc(tmp_bytes, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ids.as<uint32_t>(), sorted_ids.as<uint32_t>(), iota.as<uint32_t>(),
+                                             g->grp_order.as<uint32_t>(), static_cast<int>(n), 0, bits, st));
+    k_group_offsets<<<grid, 256, 0, st>>>(sorted_ids.as<uint32_t>(), n, G, g->grp_offsets.as<int32_t>());
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    CUDA_TRY(cudaMemsetAsync(g->grp_offsets.p, 0, (static_cast<size_t>(G) + 1) * 4, st));
+  }
+  CUDA_TRY(cudaEventRecord(g->ev[7], st));
+  CUDA_TRY(cudaEventRecord(g->ev[8], st));
+  CUDA_TRY(cudaEventRecord(g->ev[9], st));
+  g->have_groupings = true;
+  return PA_OK;
+}
+}  // namespace
+
+int pa_groupby_groupings(pa_groupby* g, struct ArrowArray* offsets, struct ArrowSchema* offsets_schema,
+                         struct ArrowArray* rows, struct ArrowSchema* rows_schema) {
+  if (!g || !offsets || !offsets_schema) return set_err(PA_ERR_INVALID, "null argument");
+  if ((rows == nullptr) != (rows_schema == nullptr)) return set_err(PA_ERR_INVALID, "rows and rows_schema go together");
+  PA_TRY(ensure_groups(g));
+  PA_TRY(ensure_device(g));
+  PA_TRY(ensure_groupings(g));
+  PA_TRY(export_host(g->stream, "i", 4, g->G + 1, g->grp_offsets.p, nullptr, offsets, offsets_schema));
+  if (rows) PA_TRY(export_host(g->stream, "i", 4, static_cast<uint32_t>(g->n), g->grp_order.p, nullptr, rows, rows_schema));
+  return PA_OK;
+}
+
+int pa_groupby_take_grouped(pa_groupby* g, const struct ArrowDeviceArray* column, const struct ArrowSchema* schema,
+                            struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  if (!g || !column || !schema || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
+  PA_TRY(ensure_groups(g));
+  PA_TRY(ensure_device(g));
+  PA_TRY(ensure_groupings(g));
+  cudaStream_t st = g->stream;
+  Column col;
+  PA_TRY(load_column(column, schema, st, g->device, &col));
+  if (col.n != g->n) return set_err(PA_ERR_INVALID, "column has %lld rows, keys have %lld", (long long)col.n, (long long)g->n);
+  if (schema->dictionary) return set_err(PA_ERR_INVALID, "dictionary-encoded columns: gather the indices, keep the dictionary");
+  DevBuf vals, valid;
+  const int64_t n = g->n;
+  PA_TRY(vals.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)) * col.width, st));
+  if (col.valid) PA_TRY(valid.alloc((static_cast<size_t>(n) + 31) / 32 * 4 + 4, st));
+  if (n > 0) {
+    TakeArgs a{};
+    a.col = col.data;
+    a.valid = col.valid;
+    a.bit_off = col.bit_off;
+    a.width = col.width;
+    a.order = g->grp_order.as<uint32_t>();
+    a.n = n;
+    a.out = vals.p;
+    a.out_valid = col.valid ? valid.as<uint32_t>() : nullptr;
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+    CUDA_TRY(cudaEventRecord(g->ev[8], st));
+    k_take_grouped<<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(g->ev[9], st));
+  }
+  return export_host(st, col.format, col.width, static_cast<uint32_t>(n), vals.p, col.valid ? valid.as<uint32_t>() : nullptr, out, out_schema);
+}
+
+int pa_groupby_groupings_timing(pa_groupby* g, double* build_ms, double* take_ms) {
+  if (!g) return set_err(PA_ERR_INVALID, "null argument");
+  if (!g->have_groupings) return set_err(PA_ERR_STATE, "no groupings were built on this handle");
+  PA_TRY(ensure_device(g));
+  CUDA_TRY(cudaEventSynchronize(g->ev[9]));
+  float t = 0;
+  if (build_ms) { CUDA_TRY(cudaEventElapsedTime(&t, g->ev[6], g->ev[7])); *build_ms = t; }
+  if (take_ms) { CUDA_TRY(cudaEventElapsedTime(&t, g->ev[8], g->ev[9])); *take_ms = t; }
+  return PA_OK;
 }
 
 int pa_groupby_first_rows(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema) {

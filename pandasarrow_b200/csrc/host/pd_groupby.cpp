@@ -220,21 +220,46 @@ ArrayPtr GroupBy::unique() const {
 // ------------------------------ materialised groups ------------------------------
 // The reference materialises every group of every column in its constructor (dataframe.cpp:1571-1600);
 // here it happens on first use only.  Group ids come from the GPU, the regrouping is Arrow's.
+// Fixed-width numeric / temporal columns are gathered on the device (pa_groupby_take_grouped); anything else
+// (strings, booleans, dictionaries) with arrow's Take on the row order the device produced.
+static bool device_takeable(const arrow::DataType& t) {
+  switch (t.id()) {
+    case arrow::Type::INT8: case arrow::Type::INT16: case arrow::Type::INT32: case arrow::Type::INT64:
+    case arrow::Type::UINT8: case arrow::Type::UINT16: case arrow::Type::UINT32: case arrow::Type::UINT64:
+    case arrow::Type::FLOAT: case arrow::Type::DOUBLE: case arrow::Type::TIMESTAMP: case arrow::Type::DATE32:
+    case arrow::Type::DATE64: case arrow::Type::TIME32: case arrow::Type::TIME64: case arrow::Type::DURATION:
+      return true;
+    default:
+      return false;
+  }
+}
+
+// The reference's makeGroups tail (dataframe.cpp:1586-1597): MakeGroupings + ApplyGroupings of the index and of
+// every column, here as pa_groupby_groupings (device: row ids -> stable sort) + pa_groupby_take_grouped.
 void GroupBy::materialize() const {
   if (materialized) return;
   if (!handle) throw std::runtime_error("GroupBy is empty");
-  ArrowArray a;
-  ArrowSchema sc;
-  if (pa_groupby_row_ids(handle, &a, &sc) != PA_OK) throw_pa("pa_groupby_row_ids");
-  auto ids = ReturnOrThrowOnFailure(arrow::ImportArray(&a, &sc));
   const int64_t G = static_cast<int64_t>(groupSize());
   if (G > std::numeric_limits<int32_t>::max()) throw std::runtime_error("too many groups to materialise");
-  auto groupings = ReturnOrThrowOnFailure(arrow::compute::Grouper::MakeGroupings(
-      static_cast<const arrow::UInt32Array&>(*ids), static_cast<uint32_t>(G)));
+  ArrowArray oa, ra;
+  ArrowSchema os, rs;
+  if (pa_groupby_groupings(handle, &oa, &os, &ra, &rs) != PA_OK) throw_pa("pa_groupby_groupings");
+  auto offsets = std::static_pointer_cast<arrow::Int32Array>(ReturnOrThrowOnFailure(arrow::ImportArray(&oa, &os)));
+  auto rows = ReturnOrThrowOnFailure(arrow::ImportArray(&ra, &rs));
   auto regroup = [&](const ArrayPtr& col, std::vector<ArrayPtr>* out) {
-    auto lists = ReturnOrThrowOnFailure(arrow::compute::Grouper::ApplyGroupings(*groupings, *col));
+    ArrayPtr gathered;
+    if (device_takeable(*col->type())) {
+      Exported v(*col);
+      ArrowArray a;
+      ArrowSchema sc;
+      if (pa_groupby_take_grouped(handle, &v.dev, &v.schema, &a, &sc) != PA_OK) throw_pa("pa_groupby_take_grouped");
+      gathered = ReturnOrThrowOnFailure(import_result(&a, &sc));
+      if (!gathered->type()->Equals(col->type())) gathered = ReturnOrThrowOnFailure(gathered->View(col->type()));
+    } else {
+      gathered = ReturnOrThrowOnFailure(arrow::compute::Take(*col, *rows));
+    }
     out->resize(G);
-    for (int64_t g = 0; g < G; ++g) (*out)[g] = lists->value_slice(g);
+    for (int64_t g = 0; g < G; ++g) (*out)[g] = gathered->Slice(offsets->Value(g), offsets->Value(g + 1) - offsets->Value(g));
   };
   regroup(df.indexArray(), &indexGroups);
   groups.assign(G, arrow::ArrayVector{});

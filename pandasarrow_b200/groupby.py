@@ -257,6 +257,32 @@ class GroupBy:
         _check(self._L.pa_groupby_row_ids(self._h, C.byref(out_a), C.byref(out_s)))
         return _import(out_a, out_s)
 
+    def groupings(self, rows: bool = True):
+        """Grouper::MakeGroupings equivalent (dataframe.cpp:1586-1588): (offsets int32[G+1], rows int32[n]) — group j
+        owns rows[offsets[j]:offsets[j+1]], ascending.  rows=False: offsets only."""
+        oa, os_, ra, rs = ArrowArray(), ArrowSchema(), ArrowArray(), ArrowSchema()
+        if rows:
+            _check(self._L.pa_groupby_groupings(self._h, C.byref(oa), C.byref(os_), C.byref(ra), C.byref(rs)))
+            return _import(oa, os_), _import(ra, rs)
+        _check(self._L.pa_groupby_groupings(self._h, C.byref(oa), C.byref(os_), None, None))
+        return _import(oa, os_), None
+
+    def take_grouped(self, column: Column) -> pa.Array:
+        """Grouper::ApplyGroupings equivalent for one column (dataframe.cpp:1546,1562): the column gathered on the
+        device into group-contiguous order (see groupings())."""
+        arg = _CArg(column)
+        a, s = ArrowArray(), ArrowSchema()
+        try:
+            _check(self._L.pa_groupby_take_grouped(self._h, C.byref(arg.dev), C.byref(arg.schema), C.byref(a), C.byref(s)))
+        finally:
+            arg.close()
+        return _import(a, s)
+
+    def groupings_timing(self) -> dict:
+        b, t = C.c_double(), C.c_double()
+        _check(self._L.pa_groupby_groupings_timing(self._h, C.byref(b), C.byref(t)))
+        return {"build_ms": b.value, "take_ms": t.value}
+
     # ---- multi-GPU: hash-partitioned partial aggregates (include/pa_b200.h, SURVEY §8e) ----
     def partials_count(self, n_parts: int) -> List[int]:
         counts = (C.c_int64 * n_parts)()
