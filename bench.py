@@ -369,6 +369,21 @@ def main():
             extras["variance_stddev_product"] = {"rows": n, "groups": h.groupSize(), "total_ms": t["total_ms"], "first_pass_ms": t["scan_ms"],
                                                  "second_pass_ms": t["emit_ms"], "rows_per_s": n / (t["total_ms"] * 1e-3)}
             h.close()
+            # group materialisation: MakeGroupings + ApplyGroupings of one fp64 column on the device
+            # (int32 offsets like the reference: < 2^31 rows); device times only, the host copies are not in them
+            m = min(n, 200_000_000)
+            ck, cv2 = pab.DeviceColumn.from_torch(keys[:m]), pab.DeviceColumn.from_torch(vals[:m])
+            for _ in range(2):                                       # first round: stream-ordered pool growth
+                h = pab.GroupBy("k", {"k": ck, "v": cv2}, stream=stream.cuda_stream, device=local)
+                h.groupSize()
+                h.groupings(rows=False)
+                h.take_grouped(cv2)
+                t = h.groupings_timing()
+                if _ == 0:
+                    h.close()
+            extras["materialise_groups"] = {"rows": m, "groups": h.groupSize(), "groupings_build_ms": t["build_ms"], "take_column_ms": t["take_ms"],
+                                            "rows_per_s_build": m / (t["build_ms"] * 1e-3), "rows_per_s_take": m / (t["take_ms"] * 1e-3)}
+            h.close()
         except Exception as ex:  # noqa: BLE001
             extras["error"] = repr(ex)[:300]
 
