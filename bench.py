@@ -224,7 +224,9 @@ def main():
             gb.aggregate(dv, AGGS, fetch=False, wait=False)
         else:
             with torch.cuda.stream(stream):
-                m = D.sharded_aggregate(gb, dv, AGGS, "g", "l", stream=stream.cuda_stream, wait=False)
+                # (more groups than a padded block holds: counted exchange, which reads the counts back)
+                big = args.groups > D.PADDED_BLOCK_RECORDS
+                m = D.sharded_aggregate(gb, dv, AGGS, "g", "l", stream=stream.cuda_stream, wait=big, padded=False if big else None)
             handles.append(m)
             if len(handles) > 2:
                 handles.pop(0).close()      # (recycled by the library without synchronising)

@@ -28,23 +28,24 @@ for it in range(6):
     recv, rc = D.exchange_records(send[:sum(counts)], counts); t4 = T()
     m = MergedGroupBy(recv.data_ptr(), rc, aggs, "g", "l", device=local); t5 = T()
     m.close(); t6 = T()
-    # padded path, phase by phase
-    cap = D.PADDED_BLOCK_RECORDS
-    sendb = torch.empty((world, cap + 1, PA_PARTIAL_WORDS), dtype=torch.int64, device="cuda"); p0 = T()
-    gb.partials_export_padded(world, sendb.data_ptr(), cap); p1 = T()
-    recvb = D.exchange_padded(sendb); p2 = T()
-    m2 = MergedGroupBy(recvb.data_ptr(), [0] * world, aggs, "g", "l", device=local, padded_block_records=cap); p3 = T()
-    gs = m2.groupSize(); tm = gb.timing(); p4 = T()
-    m2.close(); p5 = T()
-    # the same without intermediate synchronisation
-    q0 = T()
-    sendb = torch.empty((world, cap + 1, PA_PARTIAL_WORDS), dtype=torch.int64, device="cuda")
-    gb.partials_export_padded(world, sendb.data_ptr(), cap)
-    recvb = D.exchange_padded(sendb)
-    m2 = MergedGroupBy(recvb.data_ptr(), [0] * world, aggs, "g", "l", device=local, padded_block_records=cap)
-    m2.close(); q1 = T()
-    if rank == 0:
-        print(f"it{it} padded: alloc {1e3*(p0-t6):.3f} export {1e3*(p1-p0):.3f} exchange {1e3*(p2-p1):.3f} merge {1e3*(p3-p2):.3f} query {1e3*(p4-p3):.3f} close {1e3*(p5-p4):.3f}; unsynced total {1e3*(q1-q0):.3f} ms; groups {gs}")
+    if G <= D.PADDED_BLOCK_RECORDS:
+        # padded path, phase by phase
+        cap = D.PADDED_BLOCK_RECORDS
+        sendb = torch.empty((world, cap + 1, PA_PARTIAL_WORDS), dtype=torch.int64, device="cuda"); p0 = T()
+        gb.partials_export_padded(world, sendb.data_ptr(), cap); p1 = T()
+        recvb = D.exchange_padded(sendb); p2 = T()
+        m2 = MergedGroupBy(recvb.data_ptr(), [0] * world, aggs, "g", "l", device=local, padded_block_records=cap); p3 = T()
+        gs = m2.groupSize(); tm = gb.timing(); p4 = T()
+        m2.close(); p5 = T()
+        # the same without intermediate synchronisation
+        q0 = T()
+        sendb = torch.empty((world, cap + 1, PA_PARTIAL_WORDS), dtype=torch.int64, device="cuda")
+        gb.partials_export_padded(world, sendb.data_ptr(), cap)
+        recvb = D.exchange_padded(sendb)
+        m2 = MergedGroupBy(recvb.data_ptr(), [0] * world, aggs, "g", "l", device=local, padded_block_records=cap)
+        m2.close(); q1 = T()
+        if rank == 0:
+            print(f"it{it} padded: alloc {1e3*(p0-t6):.3f} export {1e3*(p1-p0):.3f} exchange {1e3*(p2-p1):.3f} merge {1e3*(p3-p2):.3f} query {1e3*(p4-p3):.3f} close {1e3*(p5-p4):.3f}; unsynced total {1e3*(q1-q0):.3f} ms; groups {gs}")
     if rank == 0:
         print(f"it{it}: local {1e3*(t1-t0):.3f}  count {1e3*(t2-t1):.3f}  export {1e3*(t3-t2):.3f}  exchange {1e3*(t4-t3):.3f}  merge {1e3*(t5-t4):.3f}  close {1e3*(t6-t5):.3f} ms; groups {m.groupSize() if False else sum(rc)}")
 dist.destroy_process_group()
