@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,7 +80,13 @@ struct DevBuf {
     if (p && s == stream && bytes >= n) return PA_OK;   // recycled handle: the old block is big enough
     reset();
     s = stream;
+    static const bool dbg = getenv("PA_DEBUG_ALLOC") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     CUDA_TRY(cudaMallocAsync(&p, n, stream));
+    if (dbg) {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > 2.0) fprintf(stderr, "[pa alloc] %.1f MB took %.1f ms\n", n / 1048576.0, ms);
+    }
     bytes = n;
     return PA_OK;
   }
@@ -237,6 +244,10 @@ struct pa_groupby {
   // group materialisation (groupings.cuh), built on first use; keys are immutable so it never goes stale
   DevBuf grp_order, grp_offsets;
   bool have_groupings = false;
+  // Scratch of the global-table / resample passes, kept between calls on the handle: returning multi-GB blocks to
+  // the stream-ordered pool and asking for them again fragments it (cudaMallocAsync then takes 50-1700 ms per call
+  // at 100 M groups); a repeated aggregate on the same handle reuses these without touching the allocator.
+  struct Scratch { DevBuf table, p_keys, p_vals, p_rows, p_counts, krange, c_first, c_slot, s_first, s_slot, cub_tmp, bnd; } scr;
 };
 
 namespace {
@@ -422,7 +433,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   while (cap < want * 2 || cap < cap_floor) cap <<= 1;
   const uint64_t cap_limit = [&] { uint64_t c = 1024; while (c < static_cast<uint64_t>(g->n) * 2) c <<= 1; return c; }();
   if (cap > cap_limit) cap = cap_limit;
-  DevBuf table;
+  DevBuf& table = g->scr.table;
   const int grid_full = g->num_sms * 6;   // two waves of the 3 resident CTAs per SM
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
   for (;;) {
@@ -452,7 +463,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     const bool fast = a.kw == 8 && (!a.vals || a.vw == 8) && !a.kvalid &&
                       reinterpret_cast<uintptr_t>(a.keys) % 32 == 0 && reinterpret_cast<uintptr_t>(a.vals) % 32 == 0;
     // Very many groups (table far larger than L2): reorder the rows by table region first (partition.cuh).
-    DevBuf p_keys, p_vals, p_rows, p_counts;
+    DevBuf &p_keys = g->scr.p_keys, &p_vals = g->scr.p_vals, &p_rows = g->scr.p_rows, &p_counts = g->scr.p_counts;
     const uint64_t known_g = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
     if (fast && a.vals && !a.vvalid && known_g >= (2ull << 20) && g->n >= (1ll << 22) && !g->opt.no_partition) {
       const uint64_t table_bytes = nslots * sizeof(SlotT);
@@ -491,7 +502,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     const uint64_t known = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
     const bool front = known <= static_cast<uint64_t>(SmTab<VC, WIDE>::CAP);   // (dense keys fill every slot; hashed keys 3/4)
     a.sm_max_keys = static_cast<uint32_t>(SmTab<VC, WIDE>::MAX_KEYS);
-    DevBuf krange;
+    DevBuf& krange = g->scr.krange;
     if (front) {
       PA_TRY(krange.alloc(sizeof(KeyRange), st));
       CUDA_TRY(cudaMemsetAsync(krange.p, 0, sizeof(KeyRange), st));
@@ -522,7 +533,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   // compact occupied slots, order them by first row, gather
   const uint64_t nslots = cap + 2;
   const uint64_t max_groups = std::min<uint64_t>(nslots, static_cast<uint64_t>(g->n) + 2);
-  DevBuf c_first, c_slot, s_first, s_slot, cub_tmp;
+  DevBuf &c_first = g->scr.c_first, &c_slot = g->scr.c_slot, &s_first = g->scr.s_first, &s_slot = g->scr.s_slot, &cub_tmp = g->scr.cub_tmp;
   PA_TRY(c_first.alloc(max_groups * 4, st));
   PA_TRY(c_slot.alloc(max_groups * 4, st));
   const int cgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
@@ -982,7 +993,7 @@ int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
   cudaStream_t st = g->stream;
   const int64_t nbins = g->rs.nbins;
   const uint64_t nslots = static_cast<uint64_t>(nbins) + 2;
-  DevBuf table, bnd;
+  DevBuf &table = g->scr.table, &bnd = g->scr.bnd;
   PA_TRY(table.alloc(nslots * sizeof(SlotT), st));
   CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
   const int init_grid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
@@ -1024,7 +1035,7 @@ int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
   }
   // occupied buckets -> first-appearance (= time) order -> GroupResult
   const uint64_t max_groups = std::min<uint64_t>(nslots, static_cast<uint64_t>(g->n) + 2);
-  DevBuf c_first, c_slot, s_first, s_slot, cub_tmp;
+  DevBuf &c_first = g->scr.c_first, &c_slot = g->scr.c_slot, &s_first = g->scr.s_first, &s_slot = g->scr.s_slot, &cub_tmp = g->scr.cub_tmp;
   PA_TRY(c_first.alloc(max_groups * 4, st));
   PA_TRY(c_slot.alloc(max_groups * 4, st));
   const int cgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
