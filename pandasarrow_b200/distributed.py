@@ -130,6 +130,24 @@ def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_fo
     return merged
 
 
+def resample_anchor(first_ts_local: Optional[int], ticks_per_day: int = 86_400 * 10**9, group=None) -> int:
+    """Common bucket anchor for a row-range sharded resample (last row): the reference anchors the
+    bucket grid at the start of the day of the FIRST timestamp (TimeGrouperOrigin::StartDay, resample.cpp:85-178);
+    every rank must use the global first timestamp, not its shard's.  Returns start_day(min over ranks) to pass as
+    `origin="custom", origin_custom_ns=...`.  first_ts_local: this shard's first timestamp (None = empty shard)."""
+    import torch
+    import torch.distributed as dist
+    big = (1 << 63) - 1
+    t = torch.tensor([big if first_ts_local is None else int(first_ts_local)], dtype=torch.int64)
+    if dist.get_backend(group) == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    first = int(t.item())
+    if first == big:
+        return 0
+    return first - first % ticks_per_day          # (Python's % is a floor modulus: correct before the epoch too)
+
+
 def gather_result(local: Dict[str, "np.ndarray"], first_rows: "np.ndarray", group=None) -> Dict[str, "np.ndarray"]:
     """All-gather the owners' result columns and restore global first-appearance order
     (stable sort by global first row).  Host-side convenience for tests / small results."""

@@ -396,12 +396,14 @@ class Resampler(GroupBy):
 
 def resample(frame, index: Column, freq_ns: int, closed_right: bool = False, label_right: bool = False,
              origin: str = "start_day", origin_custom_ns: int = 0, offset_ns: int = 0, *, device=None,
-             stream=None) -> Resampler:
-    """pd::resample(df, time_duration rule, ...) (resample.h:91-122) on a sorted timestamp index."""
+             stream=None, row_base: int = 0) -> Resampler:
+    """pd::resample(df, time_duration rule, ...) (resample.h:91-122) on a sorted timestamp index.
+    row_base: global row number of local row 0 (multi-GPU row-range shards; use a common `origin="custom"` anchor on
+    every rank — distributed.resample_anchor — so that all shards cut the same bucket grid)."""
     L = _lib.load()
     arg = _CArg(index)
     h = C.c_void_p()
-    opt = _options(0, "auto", device, stream)
+    opt = _options(0, "auto", device, stream, row_base=row_base)
     try:
         _check(L.pa_resample_create(C.byref(arg.dev), C.byref(arg.schema), int(freq_ns), int(closed_right),
                                     int(label_right), ORIGIN[origin], int(origin_custom_ns), int(offset_ns),

@@ -81,3 +81,15 @@ def test_bench_reference_arm_prints_contract_json():
     assert line["value"] > 0 and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_header_is_plain_c_and_cxx():
+    """The drop-in boundary is a C ABI: include/pa_b200.h must compile as C99 and as C++ on its own."""
+    import subprocess, tempfile
+    hdr = os.path.join(ROOT, "include", "pa_b200.h")
+    for lang, std, comp in (("c", "-std=c99", "gcc"), ("c++", "-std=c++17", "g++")):
+        with tempfile.NamedTemporaryFile("w", suffix=".c" if lang == "c" else ".cpp", delete=False) as f:
+            f.write(f'#include "{hdr}"\nint main(void) {{ pa_options o; pa_options_init(&o); return (int)sizeof(struct ArrowDeviceArray) == 0; }}\n')
+        r = subprocess.run([comp, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", lang, f.name], capture_output=True, text=True)
+        os.unlink(f.name)
+        assert r.returncode == 0, r.stderr

@@ -68,6 +68,12 @@ def _worker(rank, world, port, q):
     for s in range(world):
         ok &= int(got_blocks[s, 0, 0]) == 3
         ok &= got_blocks[s, 1:4, 0].tolist() == [s * 100 + rank * 10 + j for j in range(3)]
+    # resample anchor: start of the day of the GLOBAL first tick, also when a rank's shard is empty / before the epoch
+    day = 86_400 * 10**9
+    ok &= D.resample_anchor(5 * day + 123 + rank * day) == 5 * day
+    ok &= D.resample_anchor(None if rank == 0 else 7 * day + 5) == 7 * day
+    ok &= D.resample_anchor(-3 if rank == 1 else 10) == -day
+    ok &= D.resample_anchor(None) == 0
     q.put((rank, ok, got["key"].tolist(), got["sum"].tolist(), got["count"].tolist()))
     dist.barrier()
     dist.destroy_process_group()

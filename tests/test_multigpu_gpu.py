@@ -151,3 +151,53 @@ def test_padded_exchange_overflow_marker():
     rb = pa.record_batch({"k": pa.array(hg.keys(n, G)), "v": pa.array(hg.vals(n))})
     with pytest.raises(pab.PaError, match="padded block"):
         _run_sharded_padded(pab, rb, "k", "v", ["sum"], 2, cap=2048)
+
+
+@pytest.mark.parametrize("world", [2, 5])
+@pytest.mark.parametrize("closed_right,label_right", [(False, False), (True, True)])
+def test_sharded_resample_equals_single_gpu(world, closed_right, label_right):
+    """SURVEY §8e last row: a sorted index sharded by row range; every shard cuts the same bucket grid (common
+    custom anchor = start of the day of the GLOBAL first tick), partial buckets meet in the ordinary merge."""
+    import torch
+    import pandasarrow_b200 as pab
+    from pandasarrow_b200 import distributed as D
+    from pandasarrow_b200._lib import PA_PARTIAL_WORDS as W
+    from util import assert_exact, assert_fp_close
+    rng = np.random.default_rng(11)
+    n, freq = 300_000, 7 * 60 * 10**9            # 7 minutes does not divide a day: the grid depends on the anchor
+    ts = np.cumsum(rng.integers(1, 3_000_000_000, n)).astype(np.int64) + 1_577_836_800_000_000_000 + 5 * 3600 * 10**9
+    idx = pa.array(ts, pa.timestamp("ns"))
+    v = pa.array(rng.normal(size=n), mask=rng.random(n) < 0.1)
+    single = pab.resample({"v": v}, idx, freq, closed_right=closed_right, label_right=label_right)
+    want = single.aggregate(v, ALL)
+    anchor = int(ts[0] - ts[0] % (86_400 * 10**9))
+    sends, counts = [], []
+    for r in range(world):
+        b, e = D.shard_rows(n, world, r)
+        sv = v.slice(b, e - b)
+        g = pab.resample({"v": sv}, idx.slice(b, e - b), freq, closed_right=closed_right, label_right=label_right,
+                         origin="custom", origin_custom_ns=anchor, row_base=b)
+        g.aggregate(sv, ALL, fetch=False)
+        c = g.partials_count(world)
+        buf = torch.empty((max(sum(c), 1), W), dtype=torch.int64, device="cuda")
+        g.partials_export(world, buf.data_ptr(), buf.shape[0])
+        sends.append(buf[:sum(c)]); counts.append(c)
+        g.close()
+    keys, firsts, out = [], [], {a: [] for a in ALL}
+    for o in range(world):
+        segs, rc = [], []
+        for s_ in range(world):
+            off = sum(counts[s_][:o])
+            segs.append(sends[s_][off:off + counts[s_][o]]); rc.append(counts[s_][o])
+        recv = torch.cat(segs).contiguous() if sum(rc) else torch.empty((1, W), dtype=torch.int64, device="cuda")
+        m = pab.MergedGroupBy(recv.data_ptr(), rc, ALL, "g", "tsn:")
+        for a in ALL:
+            out[a].append(m.fetch(a))
+        keys.append(m.unique()); firsts.append(m.first_rows().to_numpy())
+        m.close()
+    order = pa.array(np.argsort(np.concatenate(firsts), kind="stable"))
+    labels = pa.concat_arrays(keys).take(order)
+    assert labels.cast(pa.int64()).equals(single.index().cast(pa.int64()))          # same buckets, time order
+    for a in ALL:
+        got = pa.concat_arrays(out[a]).take(order)
+        (assert_fp_close if a in ("sum", "mean") else assert_exact)(got, want[a], f"{a} P={world}")
