@@ -110,6 +110,8 @@ struct ArrowDeviceArray {
 #define PA_AGG_VARIANCE 256u
 #define PA_AGG_STDDEV 512u
 #define PA_AGG_STAGE2 896u       /* PRODUCT | VARIANCE | STDDEV */
+#define PA_AGG_BOOL_ALL 1024u     /* GroupBy::all: boolean ('b') value columns only; bool result, null for an all-null group */
+#define PA_AGG_BOOL_ANY 2048u     /* GroupBy::any */
 
 /* ---- kernel path selection (pa_options.path); AUTO is what a caller wants ---- */
 #define PA_PATH_AUTO 0
@@ -153,8 +155,8 @@ int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, stru
 
 /* Stage 3, fused with stages 1-2: one pass over keys + values computing every aggregate in
  * agg_mask (GroupBy::sum/mean/count/min/max/first/last, pd_core_macros.h:5-147,
- * dataframe.cpp:1698-1806).  Value formats: g f l L i I s S c C (double, float, (u)int64/32/16/8)
- * and 64-bit temporal types.  Results stay on the device until fetched. */
+ * dataframe.cpp:1698-1806).  Value formats: g f l L i I s S c C (double, float, (u)int64/32/16/8),
+ * 64-bit temporal types, and b (boolean: count / all / any only).  Results stay on the device until fetched. */
 int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values,
                          const struct ArrowSchema* value_schema, uint32_t agg_mask);
 

@@ -287,6 +287,8 @@ Result<std::shared_ptr<Array>> agg_numeric(Groups& g, const std::string& func,
   if (func == "count")  // dataframe.cpp:1526
     return agg_numeric_typed<int64_t, arrow::Int64Scalar, arrow::Int64Builder>(g, func, c,
                                                                                nthreads, valid_out);
+  if (func == "all" || func == "any")  // dataframe.cpp:1522,1524 (std::vector<bool> there; bytes here, same values)
+    return agg_numeric_typed<uint8_t, arrow::BooleanScalar, arrow::BooleanBuilder>(g, func, c, nthreads, valid_out);
   return Status::NotImplemented("numeric aggregate ", func);
 }
 
@@ -530,7 +532,7 @@ int orc_groupby_row_ids(void* h, ArrowArray* out, ArrowSchema* out_schema) {
 }
 
 // func: "sum" "min" "max" "product"  -> GROUPBY_AGG semantics (nulls kept)
-//       "mean" "count" "variance" "stddev" -> GROUPBY_NUMERIC_AGG semantics (validity dropped);
+//       "mean" "count" "variance" "stddev" "all" "any" -> GROUPBY_NUMERIC_AGG semantics (validity dropped);
 //                                       out_valid (optional) receives the scalar validity
 //       "first" "last"               -> positional
 // out_valid/out_valid_schema may be NULL.
@@ -542,7 +544,7 @@ int orc_groupby_agg(void* h, const char* func, const char* column, int nthreads,
   Result<std::shared_ptr<Array>> r = Status::NotImplemented("aggregate ", f);
   std::shared_ptr<Array> valid;
   if (f == "sum" || f == "min" || f == "max" || f == "product") r = agg_boxed(*g, f, column, nthreads);
-  else if (f == "mean" || f == "count" || f == "variance" || f == "stddev") r = agg_numeric(*g, f, column, nthreads, out_valid ? &valid : nullptr);
+  else if (f == "mean" || f == "count" || f == "variance" || f == "stddev" || f == "all" || f == "any") r = agg_numeric(*g, f, column, nthreads, out_valid ? &valid : nullptr);
   else if (f == "first") r = agg_position(*g, false, column);
   else if (f == "last") r = agg_position(*g, true, column);
   if (!r.ok()) return fail(r.status());

@@ -103,8 +103,10 @@ struct Column {
   int vc = VC_I;                    // value class (value columns)
   std::string format;               // Arrow format string of the (index) type
   bool is_dict = false;
+  bool is_bool = false;             // Arrow boolean (bit-packed) unpacked to one byte per value in own_data
   int64_t dict_len = 0;
-  DevBuf own_data, own_valid;       // set when the input lived on the host
+  DevBuf own_data, own_valid;       // set when the input lived on the host (or was unpacked)
+  DevBuf own_bits;                  // boolean host input: the packed bits on the device
 };
 
 int parse_format(const char* f, int* width, int* vc) {
@@ -120,6 +122,7 @@ int parse_format(const char* f, int* width, int* vc) {
     case 'S': *width = 2; *vc = VC_U; return PA_OK;
     case 'c': *width = 1; *vc = VC_I; return PA_OK;
     case 'C': *width = 1; *vc = VC_U; return PA_OK;
+    case 'b': *width = 1; *vc = VC_U; return PA_OK;   // boolean: unpacked to bytes by load_column
     case 't':
       // tss/tsm/tsu/tsn timestamps, tD* durations, ttu/ttn time64, tdm date64: 64-bit; tdD date32, tts/ttm: 32-bit
       if (f[1] == 's' || f[1] == 'D') { *width = 8; *vc = VC_I; return PA_OK; }
@@ -142,6 +145,43 @@ int load_column(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t 
   out->n = a.length;
   const bool has_nulls = a.null_count != 0 && a.buffers[0] != nullptr;
   const char* values = static_cast<const char*>(a.buffers[1]);
+  out->is_bool = sc->format[0] == 'b';
+  if (out->is_bool) {
+    // Bit-packed values -> one byte per value on the device (the kernels then see a uint8 column of 0 / 1).
+    if (da->device_type == ARROW_DEVICE_CUDA && da->device_id != device)
+      return set_err(PA_ERR_INVALID, "array lives on device %lld, handle on %d", (long long)da->device_id, device);
+    const bool on_dev = da->device_type == ARROW_DEVICE_CUDA;
+    if (!on_dev && da->device_type != ARROW_DEVICE_CPU && da->device_type != ARROW_DEVICE_CUDA_HOST)
+      return set_err(PA_ERR_INVALID, "unsupported device_type %d", (int)da->device_type);
+    if (on_dev && da->sync_event) CUDA_TRY(cudaStreamWaitEvent(st, *static_cast<cudaEvent_t*>(da->sync_event), 0));
+    const int64_t first_byte = a.offset / 8;
+    const size_t nbytes = static_cast<size_t>((a.offset + a.length + 7) / 8 - first_byte);
+    const uint8_t* bits = reinterpret_cast<const uint8_t*>(values) + first_byte;
+    if (!on_dev) {
+      PA_TRY(out->own_bits.alloc(std::max<size_t>(nbytes, 1), st));
+      if (nbytes) CUDA_TRY(cudaMemcpyAsync(out->own_bits.p, bits, nbytes, cudaMemcpyHostToDevice, st));
+      bits = out->own_bits.as<uint8_t>();
+    }
+    PA_TRY(out->own_data.alloc(static_cast<size_t>(std::max<int64_t>(a.length, 1)), st));
+    if (a.length > 0) {
+      const int grid = static_cast<int>(std::min<int64_t>((a.length + 255) / 256, 148 * 16));
+      k_unpack_bool<<<grid, 256, 0, st>>>(bits, a.offset % 8, a.length, out->own_data.as<uint8_t>());
+      CUDA_TRY(cudaGetLastError());
+    }
+    out->data = out->own_data.p;
+    if (has_nulls) {
+      if (on_dev) {
+        out->valid = static_cast<const uint8_t*>(a.buffers[0]);
+        out->bit_off = a.offset;
+      } else {
+        PA_TRY(out->own_valid.alloc(nbytes, st));
+        CUDA_TRY(cudaMemcpyAsync(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, cudaMemcpyHostToDevice, st));
+        out->valid = out->own_valid.as<uint8_t>();
+        out->bit_off = a.offset % 8;
+      }
+    }
+    return PA_OK;
+  }
   if (da->device_type == ARROW_DEVICE_CUDA) {
     if (da->device_id != device) return set_err(PA_ERR_INVALID, "array lives on device %lld, handle on %d", (long long)da->device_id, device);
     out->data = values ? values + a.offset * out->width : nullptr;
@@ -747,6 +787,38 @@ int run_stage2(pa_groupby* g, const Column* val, uint32_t ext) {
   return PA_OK;
 }
 
+// all / any of a boolean column (GROUPBY_NUMERIC_AGG(all|any, bool), dataframe.cpp:1522-1524): bit-packed Arrow
+// booleans from the min / max of the unpacked 0 / 1 bytes.  Appends to g->outs.
+int run_bool_emit(pa_groupby* g, uint32_t extb) {
+  cudaStream_t st = g->stream;
+  const uint32_t G = g->G;
+  const size_t words = (static_cast<size_t>(G) + 31) / 32 + 1;
+  uint32_t* ptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int k = 0;
+  for (uint32_t bit : {PA_AGG_BOOL_ALL, PA_AGG_BOOL_ANY}) {
+    if (extb & bit) {
+      g->outs.emplace_back();
+      AggOut& o = g->outs.back();
+      o.bit = bit;
+      o.format = "b";
+      o.width = 1;
+      o.nullable = true;
+      PA_TRY(o.values.alloc(words * 4, st));
+      PA_TRY(o.valid.alloc(words * 4, st));
+      ptr[k][0] = o.values.as<uint32_t>();
+      ptr[k][1] = o.valid.as<uint32_t>();
+    }
+    ++k;
+  }
+  if (G > 0) {
+    k_emit_bool<<<(G + 255) / 256, 256, 0, st>>>(g->res, G, ptr[0][0], ptr[0][1], ptr[1][0], ptr[1][1]);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 1;
+    CUDA_TRY(cudaEventRecord(g->ev[4], st));
+  }
+  return PA_OK;
+}
+
 // ------------------------------ Arrow export ------------------------------
 struct ExportPriv {
   void* bufs[2] = {nullptr, nullptr};
@@ -771,7 +843,7 @@ void release_schema(ArrowSchema* s) {
 int export_host(cudaStream_t st, const std::string& format, int width, uint32_t G, const void* d_values,
                 const uint32_t* d_valid, ArrowArray* out, ArrowSchema* out_schema) {
   auto* priv = new ExportPriv();
-  const size_t vbytes = static_cast<size_t>(G) * width;
+  const size_t vbytes = format == "b" ? (static_cast<size_t>(G) + 31) / 32 * 4 : static_cast<size_t>(G) * width;   // booleans are bit-packed
   priv->bufs[1] = malloc(std::max<size_t>(vbytes, 64));
   const size_t words = (static_cast<size_t>(G) + 31) / 32;
   int64_t null_count = 0;
@@ -1229,19 +1301,27 @@ int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, stru
 static int aggregate_entry(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
                            uint32_t agg_mask, bool deferred) {
   if (!g || !values || !value_schema) return set_err(PA_ERR_INVALID, "null argument");
-  if (agg_mask == 0 || (agg_mask & ~(PA_AGG_ALL | PA_AGG_STAGE2))) return set_err(PA_ERR_INVALID, "bad aggregate mask 0x%x", agg_mask);
+  if (agg_mask == 0 || (agg_mask & ~(PA_AGG_ALL | PA_AGG_STAGE2 | PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY))) return set_err(PA_ERR_INVALID, "bad aggregate mask 0x%x", agg_mask);
+  const uint32_t requested = agg_mask;
+  const uint32_t extb = agg_mask & (PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY);
   // product / variance / stddev: a second pass after the ordinary one, which then has to deliver count (and the mean)
   const uint32_t ext = agg_mask & PA_AGG_STAGE2;
   if (ext && g->merged) return set_err(PA_ERR_NOT_IMPLEMENTED, "product / variance / stddev are not available on merged (multi-GPU) handles");
-  if (ext) {
+  if (extb && g->merged) return set_err(PA_ERR_NOT_IMPLEMENTED, "all / any are not available on merged (multi-GPU) handles");
+  if (ext || extb) {
     deferred = false;
-    agg_mask = (agg_mask & PA_AGG_ALL) | PA_AGG_COUNT | ((ext & (PA_AGG_VARIANCE | PA_AGG_STDDEV)) ? PA_AGG_MEAN : 0u);
+    // all = (min over the 0 / 1 bytes) != 0, any = (max) != 0: the ordinary pass delivers both
+    agg_mask = (agg_mask & PA_AGG_ALL) | PA_AGG_COUNT | ((ext & (PA_AGG_VARIANCE | PA_AGG_STDDEV)) ? PA_AGG_MEAN : 0u) |
+               ((extb & PA_AGG_BOOL_ALL) ? PA_AGG_MIN : 0u) | ((extb & PA_AGG_BOOL_ANY) ? PA_AGG_MAX : 0u);
   }
   PA_TRY(ensure_device(g));
   Column val;
   PA_TRY(load_column(values, value_schema, g->stream, g->device, &val));
   if (val.n != g->n) return set_err(PA_ERR_INVALID, "value column has %lld rows, keys have %lld", (long long)val.n, (long long)g->n);
   if (value_schema->dictionary) return set_err(PA_ERR_INVALID, "dictionary-encoded value columns are not aggregatable");
+  if (val.is_bool && (requested & ~(PA_AGG_COUNT | PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY)))
+    return set_err(PA_ERR_INVALID, "boolean columns aggregate with count / all / any only");
+  if (extb && !val.is_bool) return set_err(PA_ERR_INVALID, "all / any need a boolean column (arrow::compute has no kernel for other types)");
   uint32_t prev_G = g->G;
   bool had = g->have_groups;
   if (g->pending && deferred && !val.own_data.p && !val.own_valid.p) {
@@ -1272,6 +1352,11 @@ static int aggregate_entry(pa_groupby* g, const struct ArrowDeviceArray* values,
   if (g->pending) return PA_OK;
   if (had && prev_G != g->G) return set_err(PA_ERR_STATE, "group count changed between passes (%u vs %u)", prev_G, g->G);
   if (ext) PA_TRY(run_stage2(g, &val, ext));
+  if (val.is_bool) {
+    // the helper min / max columns are bytes, not Arrow booleans: only what was asked for stays fetchable
+    g->outs.erase(std::remove_if(g->outs.begin(), g->outs.end(), [&](const AggOut& o) { return (o.bit & requested) == 0; }), g->outs.end());
+    if (extb) PA_TRY(run_bool_emit(g, extb));
+  }
   // `val` may own device copies of host data: make sure the kernels reading them are done
   if (val.own_data.p) CUDA_TRY(cudaStreamSynchronize(g->stream));
   return PA_OK;

@@ -137,6 +137,29 @@ __global__ void __launch_bounds__(256) k_emit(EmitArgs a) {
   }
 }
 
+// Arrow boolean values (bit-packed, `bit_off` < 8 bits into the first byte) -> one byte per value.
+__global__ void __launch_bounds__(256) k_unpack_bool(const uint8_t* bits, int64_t bit_off, int64_t n, uint8_t* out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) out[i] = bit_at(bits, bit_off + i) ? 1 : 0;
+}
+
+// all / any per group from the min / max of the unpacked bytes; bit-packed values + validity (whole warps).
+__global__ void __launch_bounds__(256) k_emit_bool(GroupResult r, uint32_t G, uint32_t* o_all, uint32_t* o_all_valid,
+                                                   uint32_t* o_any, uint32_t* o_any_valid) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = g < G;
+  const uint64_t cnt = in ? (r.count64 ? r.count64[g] : static_cast<uint64_t>(r.count[g])) : 0;
+  const bool has = cnt > 0;
+  const uint32_t mv = __ballot_sync(0xFFFFFFFFu, has);
+  const uint32_t ma = __ballot_sync(0xFFFFFFFFu, has && o_all && r.min_ord[g] != 0);
+  const uint32_t my = __ballot_sync(0xFFFFFFFFu, has && o_any && r.max_ord[g] != 0);
+  if (lane_id() == 0 && (g & ~31u) < G) {
+    if (o_all) { o_all[g >> 5] = ma; o_all_valid[g >> 5] = mv; }
+    if (o_any) { o_any[g >> 5] = my; o_any_valid[g >> 5] = mv; }
+  }
+}
+
 // ---- composite keys: field j occupies bits [shift_j, shift_j + bits_j) of the packed key; a
 // nullable field has one extra top bit that is set (value bits zero) for null. ----
 constexpr int kMaxKeyCols = 4;

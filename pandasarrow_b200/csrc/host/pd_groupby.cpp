@@ -369,7 +369,7 @@ arrow::Result<arrow::ArrayVector> GroupBy::aggregate(std::string const& column, 
   Exported v(*col);
   if (pa_groupby_aggregate(handle, &v.dev, &v.schema, mask) != PA_OK) return pa_status("aggregate");
   arrow::ArrayVector out;
-  for (uint32_t bit = 1; bit <= PA_AGG_STDDEV; bit <<= 1) {
+  for (uint32_t bit = 1; bit <= PA_AGG_BOOL_ANY; bit <<= 1) {
     if (!(mask & bit)) continue;
     ArrowArray a;
     ArrowSchema s;
@@ -417,6 +417,11 @@ arrow::Result<DataFrame> GroupBy::variance(std::vector<std::string> const& args)
 arrow::Result<Series> GroupBy::variance(std::string const& arg) { return seriesOf(arg, PA_AGG_VARIANCE, true, true); }
 arrow::Result<DataFrame> GroupBy::stddev(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_STDDEV, true, true); }
 arrow::Result<Series> GroupBy::stddev(std::string const& arg) { return seriesOf(arg, PA_AGG_STDDEV, true, true); }
+// GROUPBY_NUMERIC_AGG(all|any, bool) dataframe.cpp:1522,1524
+arrow::Result<DataFrame> GroupBy::all(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_BOOL_ALL, true, true); }
+arrow::Result<Series> GroupBy::all(std::string const& arg) { return seriesOf(arg, PA_AGG_BOOL_ALL, true, true); }
+arrow::Result<DataFrame> GroupBy::any(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_BOOL_ANY, true, true); }
+arrow::Result<Series> GroupBy::any(std::string const& arg) { return seriesOf(arg, PA_AGG_BOOL_ANY, true, true); }
 // dataframe.cpp:1698-1806: first(vector) is indexed by the keys, first(string) is not (:1748),
 // last(vector) is not (:1781), last(string) is (:1805)
 arrow::Result<DataFrame> GroupBy::first(std::vector<std::string> const& args) { return frameOf(args, kFirst, false, true); }

@@ -332,6 +332,9 @@ class GroupBy:
     def product(self, arg): return self._agg("product", arg)
     def variance(self, arg): return self._agg("variance", arg)
     def stddev(self, arg): return self._agg("stddev", arg)
+    # boolean columns (GROUPBY_NUMERIC_AGG(all|any, bool), dataframe.cpp:1522-1524)
+    def all(self, arg): return self._agg("all", arg)
+    def any(self, arg): return self._agg("any", arg)
 
     def min_max(self, arg):
         """GroupBy::min_max (dataframe.cpp:1602-1696): one pass, two columns."""

@@ -205,6 +205,14 @@ static void test_second_stage_aggregates() {
   REQUIRE(prod[0].as<int64_t>() == int64_t(16) * 10 * 20 * 40 * 15 * 35 * 45);
   REQUIRE(prod[1].as<int64_t>() == int64_t(10) * 30 * 25);
   REQUIRE(!groupby.tdigest("age").ok());                      // still outside the path: NotImplemented, not a crash
+  // GROUPBY_NUMERIC_AGG(all|any, bool): a boolean column
+  pd::DataFrame flags{pd::range(0L, 6L), std::pair{"k"s, std::vector{1, 1, 2, 2, 3, 3}},
+                      std::pair{"b"s, std::vector<bool>{true, true, true, false, false, false}}};
+  pd::GroupBy by_k("k", flags);
+  auto all = pd::ReturnOrThrowOnFailure(by_k.all("b"));
+  auto any = pd::ReturnOrThrowOnFailure(by_k.any("b"));
+  REQUIRE(all[0].as<bool>() && !all[1].as<bool>() && !all[2].as<bool>());
+  REQUIRE(any[0].as<bool>() && any[1].as<bool>() && !any[2].as<bool>());
 }
 
 // series_resample_test.cpp:12-70

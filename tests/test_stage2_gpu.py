@@ -175,3 +175,43 @@ def test_stage2_refused_on_merged_handles(pab):
     m = pab.MergedGroupBy(buf.data_ptr(), c, ["sum", "count"], "g", "l")
     with pytest.raises(pab.PaError, match="merged"):
         m.aggregate(rb.column("v"), ["variance"])
+
+
+# ---------------- all / any on boolean columns (GROUPBY_NUMERIC_AGG(all|any, bool), dataframe.cpp:1522-1524) ----------------
+@pytest.mark.parametrize("n,G,kw", [(50_000, 7, {}), (200_000, 900, {}), (200_000, 5000, {}), (300_000, 100_000, {"path": "global"})])
+def test_bool_all_any_match_oracle(pab, orc, n, G, kw):
+    from util import align_to
+    rng = np.random.default_rng(n + G)
+    k = rng.integers(0, G, n)
+    b = rng.random(n) < 0.97                       # mostly true, so that `all` is true for some groups
+    b[k % 5 == 0] = True
+    b[k % 7 == 1] = False                          # groups that are all false: `any` false
+    vm = rng.random(n) < 0.1
+    vm[k % 11 == 3] = True                         # all-null groups
+    rb = pa.record_batch({"k": pa.array(k, pa.int64(), mask=rng.random(n) < 0.01), "b": pa.array(b, pa.bool_(), mask=vm)})
+    gb, ora = pab.GroupBy("k", rb, **kw), orc.OracleGroupBy(rb, "k")
+    perm = pa.array(align_to([(x,) for x in gb.unique().to_pylist()], [(x,) for x in ora.unique().to_pylist()]))
+    r = gb.aggregate(rb.column("b"), ["all", "any", "count"])
+    for a in ("all", "any"):
+        want, valid = ora.agg(a, "b", nthreads=8, with_validity=True)
+        got = r[a].take(perm)
+        assert got.type == pa.bool_()
+        assert got.is_valid().to_pylist() == valid.to_pylist(), a            # null for an all-null group ...
+        assert got.fill_null(False).to_pylist() == want.to_pylist(), a       # ... which the reference's wrapper turns into false
+    assert r["count"].take(perm).equals(ora.agg("count", "b", nthreads=8))
+    assert len(set(r["all"].to_pylist())) == 3 and len(set(r["any"].to_pylist())) >= 2     # true, false and null all occur
+    # a sliced boolean column (bit offset not a multiple of 8) gives the same answer
+    padded = pa.concat_arrays([pa.array([True, None, False], pa.bool_()), rb.column("b")]).slice(3)
+    assert gb.aggregate(padded, ["all"])["all"].equals(r["all"])
+
+
+def test_bool_columns_reject_other_aggregates(pab):
+    rb = pa.record_batch({"k": pa.array([1, 2, 1], pa.int64()), "b": pa.array([True, False, True]), "v": pa.array([1.0, 2.0, 3.0])})
+    g = pab.GroupBy("k", rb)
+    with pytest.raises(pab.PaError, match="boolean columns"):
+        g.aggregate(rb.column("b"), ["sum"])
+    with pytest.raises(pab.PaError, match="boolean column"):
+        g.aggregate(rb.column("v"), ["all"])
+    assert g.all("b").to_pylist() == [True, False] and g.any("b").to_pylist() == [True, False]
+    with pytest.raises(pab.PaError, match="not part of the last"):
+        g.fetch("min")                               # the helper min / max columns are not exposed
