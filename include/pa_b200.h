@@ -112,6 +112,8 @@ struct ArrowDeviceArray {
 #define PA_AGG_STAGE2 896u       /* PRODUCT | VARIANCE | STDDEV */
 #define PA_AGG_BOOL_ALL 1024u     /* GroupBy::all: boolean ('b') value columns only; bool result, null for an all-null group */
 #define PA_AGG_BOOL_ANY 2048u     /* GroupBy::any */
+#define PA_AGG_COUNT_DISTINCT 4096u /* GroupBy::count_distinct: int64 number of distinct non-null values (by bit pattern, as
+                                      arrow's memo table: -0.0 and +0.0 are two values); single-GPU handles, < 2^31 rows */
 
 /* ---- kernel path selection (pa_options.path); AUTO is what a caller wants ---- */
 #define PA_PATH_AUTO 0

@@ -284,7 +284,7 @@ Result<std::shared_ptr<Array>> agg_numeric(Groups& g, const std::string& func,
   if (func == "mean" || func == "variance" || func == "stddev")  // dataframe.cpp:1512,1516,1520
     return agg_numeric_typed<double, arrow::DoubleScalar, arrow::DoubleBuilder>(g, func, c,
                                                                                 nthreads, valid_out);
-  if (func == "count")  // dataframe.cpp:1526
+  if (func == "count" || func == "count_distinct")  // dataframe.cpp:1526,1528
     return agg_numeric_typed<int64_t, arrow::Int64Scalar, arrow::Int64Builder>(g, func, c,
                                                                                nthreads, valid_out);
   if (func == "all" || func == "any")  // dataframe.cpp:1522,1524 (std::vector<bool> there; bytes here, same values)
@@ -544,7 +544,7 @@ int orc_groupby_agg(void* h, const char* func, const char* column, int nthreads,
   Result<std::shared_ptr<Array>> r = Status::NotImplemented("aggregate ", f);
   std::shared_ptr<Array> valid;
   if (f == "sum" || f == "min" || f == "max" || f == "product") r = agg_boxed(*g, f, column, nthreads);
-  else if (f == "mean" || f == "count" || f == "variance" || f == "stddev" || f == "all" || f == "any") r = agg_numeric(*g, f, column, nthreads, out_valid ? &valid : nullptr);
+  else if (f == "mean" || f == "count" || f == "variance" || f == "stddev" || f == "all" || f == "any" || f == "count_distinct") r = agg_numeric(*g, f, column, nthreads, out_valid ? &valid : nullptr);
   else if (f == "first") r = agg_position(*g, false, column);
   else if (f == "last") r = agg_position(*g, true, column);
   if (!r.ok()) return fail(r.status());

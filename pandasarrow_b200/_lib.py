@@ -12,7 +12,7 @@ ARROW_DEVICE_CPU = 1
 ARROW_DEVICE_CUDA = 2
 
 PA_AGG = {"sum": 1, "mean": 2, "count": 4, "min": 8, "max": 16, "first": 32, "last": 64,
-          "product": 128, "variance": 256, "stddev": 512, "all": 1024, "any": 2048}
+          "product": 128, "variance": 256, "stddev": 512, "all": 1024, "any": 2048, "count_distinct": 4096}
 PA_PATH_AUTO, PA_PATH_LOWCARD, PA_PATH_GLOBAL = 0, 1, 2
 PA_PARTIAL_WORDS = 11
 

@@ -25,6 +25,7 @@
 #include "rowids.cuh"
 #include "stage2.cuh"
 #include "groupings.cuh"
+#include "distinct.cuh"
 
 using namespace pa;
 
@@ -819,6 +820,67 @@ int run_bool_emit(pa_groupby* g, uint32_t extb) {
   return PA_OK;
 }
 
+// count_distinct (distinct.cuh): ids + value bits -> two stable radix sorts -> boundary count.  Appends to g->outs.
+int run_count_distinct(pa_groupby* g, const Column* val) {
+  cudaStream_t st = g->stream;
+  const uint32_t G = g->G;
+  const int64_t n = g->n;
+  if (n >= (1ll << 31)) return set_err(PA_ERR_INVALID, "count_distinct sorts with 32-bit positions: at most 2^31 - 1 rows");
+  g->outs.emplace_back();
+  AggOut& o = g->outs.back();
+  o.bit = PA_AGG_COUNT_DISTINCT;
+  o.format = "l";
+  o.width = 8;
+  o.nullable = false;
+  PA_TRY(o.values.alloc(static_cast<size_t>(std::max<uint32_t>(G, 1)) * 8, st));
+  if (G == 0) return PA_OK;
+  DevBuf distinct, id_a, id_b, bits_a, bits_b, tmp;
+  PA_TRY(distinct.alloc(static_cast<size_t>(G) * 8, st));
+  CUDA_TRY(cudaMemsetAsync(distinct.p, 0, static_cast<size_t>(G) * 8, st));
+  if (n > 0) {
+    RowLookup lk;
+    PA_TRY(build_row_lookup(g, &lk));
+    const size_t nn = static_cast<size_t>(n);
+    PA_TRY(id_a.alloc(nn * 4, st));
+    PA_TRY(id_b.alloc(nn * 4, st));
+    PA_TRY(bits_a.alloc(nn * 8, st));
+    PA_TRY(bits_b.alloc(nn * 8, st));
+    DistinctFillArgs a{};
+    a.ids = lk.a;
+    a.vals = val->data;
+    a.vvalid = val->valid;
+    a.voff = val->bit_off;
+    a.vw = val->width;
+    a.out_bits = bits_a.as<uint64_t>();
+    a.out_id = id_a.as<uint32_t>();
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+    if (val->vc == VC_F) k_distinct_fill<VC_F><<<grid, 256, 0, st>>>(a);
+    else if (val->vc == VC_I) k_distinct_fill<VC_I><<<grid, 256, 0, st>>>(a);
+    else k_distinct_fill<VC_U><<<grid, 256, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    // by value (64 bits; narrower columns need fewer), then stably by id (32 bits: kNoGroup must sort last)
+    const int vbits = val->vc == VC_F ? 64 : (val->vc == VC_I ? 64 : std::min(64, val->width * 8));
+    size_t t1 = 0, t2 = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, bits_a.as<uint64_t>(), bits_b.as<uint64_t>(), id_a.as<uint32_t>(), id_b.as<uint32_t>(),
+                                             static_cast<int>(n), 0, vbits, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t2, id_b.as<uint32_t>(), id_a.as<uint32_t>(), bits_b.as<uint64_t>(), bits_a.as<uint64_t>(),
+                                             static_cast<int>(n), 0, 32, st));
+    PA_TRY(tmp.alloc(std::max(t1, t2), st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, t1, bits_a.as<uint64_t>(), bits_b.as<uint64_t>(), id_a.as<uint32_t>(), id_b.as<uint32_t>(),
+                                             static_cast<int>(n), 0, vbits, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, t2, id_b.as<uint32_t>(), id_a.as<uint32_t>(), bits_b.as<uint64_t>(), bits_a.as<uint64_t>(),
+                                             static_cast<int>(n), 0, 32, st));
+    const int64_t threads = (n + CD_PER_THREAD - 1) / CD_PER_THREAD;
+    k_distinct_count<<<static_cast<int>((threads + 255) / 256), 256, 0, st>>>(id_a.as<uint32_t>(), bits_a.as<uint64_t>(), n, distinct.as<unsigned long long>());
+    CUDA_TRY(cudaGetLastError());
+  }
+  k_distinct_emit<<<(G + 255) / 256, 256, 0, st>>>(distinct.as<unsigned long long>(), G, o.values.as<int64_t>());
+  CUDA_TRY(cudaGetLastError());
+  g->last_launches += 5;
+  CUDA_TRY(cudaEventRecord(g->ev[4], st));
+  return PA_OK;
+}
+
 // ------------------------------ Arrow export ------------------------------
 struct ExportPriv {
   void* bufs[2] = {nullptr, nullptr};
@@ -1301,14 +1363,16 @@ int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, stru
 static int aggregate_entry(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
                            uint32_t agg_mask, bool deferred) {
   if (!g || !values || !value_schema) return set_err(PA_ERR_INVALID, "null argument");
-  if (agg_mask == 0 || (agg_mask & ~(PA_AGG_ALL | PA_AGG_STAGE2 | PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY))) return set_err(PA_ERR_INVALID, "bad aggregate mask 0x%x", agg_mask);
+  if (agg_mask == 0 || (agg_mask & ~(PA_AGG_ALL | PA_AGG_STAGE2 | PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY | PA_AGG_COUNT_DISTINCT))) return set_err(PA_ERR_INVALID, "bad aggregate mask 0x%x", agg_mask);
   const uint32_t requested = agg_mask;
   const uint32_t extb = agg_mask & (PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY);
+  const bool want_distinct = (agg_mask & PA_AGG_COUNT_DISTINCT) != 0;
+  if (want_distinct && g->merged) return set_err(PA_ERR_NOT_IMPLEMENTED, "count_distinct is not available on merged (multi-GPU) handles");
   // product / variance / stddev: a second pass after the ordinary one, which then has to deliver count (and the mean)
   const uint32_t ext = agg_mask & PA_AGG_STAGE2;
   if (ext && g->merged) return set_err(PA_ERR_NOT_IMPLEMENTED, "product / variance / stddev are not available on merged (multi-GPU) handles");
   if (extb && g->merged) return set_err(PA_ERR_NOT_IMPLEMENTED, "all / any are not available on merged (multi-GPU) handles");
-  if (ext || extb) {
+  if (ext || extb || want_distinct) {
     deferred = false;
     // all = (min over the 0 / 1 bytes) != 0, any = (max) != 0: the ordinary pass delivers both
     agg_mask = (agg_mask & PA_AGG_ALL) | PA_AGG_COUNT | ((ext & (PA_AGG_VARIANCE | PA_AGG_STDDEV)) ? PA_AGG_MEAN : 0u) |
@@ -1319,7 +1383,7 @@ static int aggregate_entry(pa_groupby* g, const struct ArrowDeviceArray* values,
   PA_TRY(load_column(values, value_schema, g->stream, g->device, &val));
   if (val.n != g->n) return set_err(PA_ERR_INVALID, "value column has %lld rows, keys have %lld", (long long)val.n, (long long)g->n);
   if (value_schema->dictionary) return set_err(PA_ERR_INVALID, "dictionary-encoded value columns are not aggregatable");
-  if (val.is_bool && (requested & ~(PA_AGG_COUNT | PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY)))
+  if (val.is_bool && (requested & ~(PA_AGG_COUNT | PA_AGG_BOOL_ALL | PA_AGG_BOOL_ANY | PA_AGG_COUNT_DISTINCT)))
     return set_err(PA_ERR_INVALID, "boolean columns aggregate with count / all / any only");
   if (extb && !val.is_bool) return set_err(PA_ERR_INVALID, "all / any need a boolean column (arrow::compute has no kernel for other types)");
   uint32_t prev_G = g->G;
@@ -1352,6 +1416,7 @@ static int aggregate_entry(pa_groupby* g, const struct ArrowDeviceArray* values,
   if (g->pending) return PA_OK;
   if (had && prev_G != g->G) return set_err(PA_ERR_STATE, "group count changed between passes (%u vs %u)", prev_G, g->G);
   if (ext) PA_TRY(run_stage2(g, &val, ext));
+  if (want_distinct) PA_TRY(run_count_distinct(g, &val));
   if (val.is_bool) {
     // the helper min / max columns are bytes, not Arrow booleans: only what was asked for stays fetchable
     g->outs.erase(std::remove_if(g->outs.begin(), g->outs.end(), [&](const AggOut& o) { return (o.bit & requested) == 0; }), g->outs.end());

@@ -369,7 +369,7 @@ arrow::Result<arrow::ArrayVector> GroupBy::aggregate(std::string const& column, 
   Exported v(*col);
   if (pa_groupby_aggregate(handle, &v.dev, &v.schema, mask) != PA_OK) return pa_status("aggregate");
   arrow::ArrayVector out;
-  for (uint32_t bit = 1; bit <= PA_AGG_BOOL_ANY; bit <<= 1) {
+  for (uint32_t bit = 1; bit <= PA_AGG_COUNT_DISTINCT; bit <<= 1) {
     if (!(mask & bit)) continue;
     ArrowArray a;
     ArrowSchema s;
@@ -422,6 +422,9 @@ arrow::Result<DataFrame> GroupBy::all(std::vector<std::string> const& args) { re
 arrow::Result<Series> GroupBy::all(std::string const& arg) { return seriesOf(arg, PA_AGG_BOOL_ALL, true, true); }
 arrow::Result<DataFrame> GroupBy::any(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_BOOL_ANY, true, true); }
 arrow::Result<Series> GroupBy::any(std::string const& arg) { return seriesOf(arg, PA_AGG_BOOL_ANY, true, true); }
+// GROUPBY_NUMERIC_AGG(count_distinct, int64_t) dataframe.cpp:1528
+arrow::Result<DataFrame> GroupBy::count_distinct(std::vector<std::string> const& args) { return frameOf(args, PA_AGG_COUNT_DISTINCT, true, true); }
+arrow::Result<Series> GroupBy::count_distinct(std::string const& arg) { return seriesOf(arg, PA_AGG_COUNT_DISTINCT, true, true); }
 // dataframe.cpp:1698-1806: first(vector) is indexed by the keys, first(string) is not (:1748),
 // last(vector) is not (:1781), last(string) is (:1805)
 arrow::Result<DataFrame> GroupBy::first(std::vector<std::string> const& args) { return frameOf(args, kFirst, false, true); }

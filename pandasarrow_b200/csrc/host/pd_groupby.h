@@ -17,7 +17,7 @@
 // (pa_groupby_row_ids = what Grouper::Consume returned) with Arrow's MakeGroupings / ApplyGroupings,
 // exactly the calls the reference makes after Consume (dataframe.cpp:1539-1569,1586-1597).
 // product / variance / stddev run a second device pass (stage2.cuh).  Not carried over (SURVEY.md §8f
-// "next"): approximate_median/count_distinct/mode/tdigest; those methods exist and return
+// "next"): approximate_median/mode/tdigest; those methods exist and return
 // arrow::Status::NotImplemented.
 #pragma once
 #include <arrow/api.h>
@@ -197,12 +197,14 @@ class GroupBy {
   arrow::Result<Series> all(std::string const& arg);
   arrow::Result<DataFrame> any(std::vector<std::string> const& args);
   arrow::Result<Series> any(std::string const& arg);
+  arrow::Result<DataFrame> count_distinct(std::vector<std::string> const& args);
+  arrow::Result<Series> count_distinct(std::string const& arg);
 
   // declared by the reference, outside this path's CUDA scope
 #define PD_NOT_ON_GPU(name)                                                                                   \
   arrow::Result<DataFrame> name(std::vector<std::string> const&) { return arrow::Status::NotImplemented(#name " is not part of the B200 group-by path"); } \
   arrow::Result<Series> name(std::string const&) { return arrow::Status::NotImplemented(#name " is not part of the B200 group-by path"); }
-  PD_NOT_ON_GPU(approximate_median) PD_NOT_ON_GPU(count_distinct)
+  PD_NOT_ON_GPU(approximate_median)
   PD_NOT_ON_GPU(mode) PD_NOT_ON_GPU(tdigest)
 #undef PD_NOT_ON_GPU
   // ---- materialised groups (group_by.h:38-83, 141-162; dataframe.cpp:1430-1510) ----

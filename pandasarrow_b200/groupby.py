@@ -335,6 +335,7 @@ class GroupBy:
     # boolean columns (GROUPBY_NUMERIC_AGG(all|any, bool), dataframe.cpp:1522-1524)
     def all(self, arg): return self._agg("all", arg)
     def any(self, arg): return self._agg("any", arg)
+    def count_distinct(self, arg): return self._agg("count_distinct", arg)     # dataframe.cpp:1528; sort based
 
     def min_max(self, arg):
         """GroupBy::min_max (dataframe.cpp:1602-1696): one pass, two columns."""

@@ -96,7 +96,7 @@ static void test_make_groups_and_aggregates() {
 
   REQUIRE_THROWS(pd::GroupBy("nope", df));                                 // group_by.h:27-30
   REQUIRE(!groupby.sum("nope").ok());
-  REQUIRE(groupby.count_distinct("age").status().IsNotImplemented());
+  REQUIRE(groupby.approximate_median("age").status().IsNotImplemented());
 }
 
 // dataframe_resample_test.cpp:252-305 — OHLC bars through group_by
@@ -213,6 +213,10 @@ static void test_second_stage_aggregates() {
   auto any = pd::ReturnOrThrowOnFailure(by_k.any("b"));
   REQUIRE(all[0].as<bool>() && !all[1].as<bool>() && !all[2].as<bool>());
   REQUIRE(any[0].as<bool>() && any[1].as<bool>() && !any[2].as<bool>());
+  auto nd = pd::ReturnOrThrowOnFailure(groupby.count_distinct("age"));     // male: 16 10 20 40 15 35 45, female: 10 30 25
+  REQUIRE(nd[0].as<int64_t>() == 7 && nd[1].as<int64_t>() == 3);
+  auto nh = pd::ReturnOrThrowOnFailure(groupby.count_distinct("height"));  // male: 9 9 9 8 8 8 8, female: 9 9 8
+  REQUIRE(nh[0].as<int64_t>() == 2 && nh[1].as<int64_t>() == 2);
 }
 
 // series_resample_test.cpp:12-70

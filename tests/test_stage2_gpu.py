@@ -215,3 +215,43 @@ def test_bool_columns_reject_other_aggregates(pab):
     assert g.all("b").to_pylist() == [True, False] and g.any("b").to_pylist() == [True, False]
     with pytest.raises(pab.PaError, match="not part of the last"):
         g.fetch("min")                               # the helper min / max columns are not exposed
+
+
+# ---------------- count_distinct (GROUPBY_NUMERIC_AGG(count_distinct, int64_t), dataframe.cpp:1528) ----------------
+@pytest.mark.parametrize("n,G,kw", [(40_000, 3, {}), (200_000, 700, {}), (200_000, 6000, {}), (300_000, 120_000, {"path": "global"})])
+def test_count_distinct_matches_oracle(pab, orc, n, G, kw):
+    from util import align_to
+    rng = np.random.default_rng(7 * n + G)
+    vm = rng.random(n) < 0.1
+    k = rng.integers(0, G, n)
+    vm[k % 13 == 5] = True                                                  # all-null groups: 0
+    f = rng.integers(0, 50, n).astype(np.float64) / 4
+    f[rng.random(n) < 0.01] = -0.0
+    f[rng.random(n) < 0.01] = np.nan
+    rb = pa.record_batch({
+        "k": pa.array(k * 17 - 40, pa.int64(), mask=rng.random(n) < 0.01),
+        "f": pa.array(f, pa.float64(), mask=vm),                            # few distinct values, -0.0 / 0.0 / NaN among them
+        "r": pa.array(rng.normal(size=n), pa.float64(), mask=vm),           # (almost) all distinct
+        "i": pa.array(rng.integers(-20, 20, n), pa.int64(), mask=vm),
+        "u8": pa.array(rng.integers(0, 9, n).astype(np.uint8), pa.uint8(), mask=vm),
+        "f32": pa.array((rng.integers(0, 30, n) / 8).astype(np.float32), pa.float32(), mask=vm),
+        "b": pa.array(rng.random(n) < 0.5, pa.bool_(), mask=vm)})
+    gb, ora = pab.GroupBy("k", rb, **kw), orc.OracleGroupBy(rb, "k")
+    perm = pa.array(align_to([(x,) for x in gb.unique().to_pylist()], [(x,) for x in ora.unique().to_pylist()]))
+    for c in ("f", "r", "i", "u8", "f32", "b"):
+        got = gb.count_distinct(c).take(perm)
+        want = ora.agg("count_distinct", c, nthreads=8)
+        assert got.type == pa.int64() and got.null_count == 0
+        assert got.equals(want), c
+    both = gb.aggregate(rb.column("i"), ["count_distinct", "count", "sum"])
+    assert (both["count_distinct"].to_numpy() <= both["count"].to_numpy()).all()
+
+
+def test_count_distinct_bit_pattern_semantics(pab, orc):
+    # arrow's memo table hashes the bits: -0.0 and +0.0 are two values, one NaN payload is one value
+    rb = pa.record_batch({"k": pa.array([1, 1, 1, 1, 2, 2, 2, 3], pa.int64()),
+                          "v": pa.array([0.0, -0.0, float("nan"), float("nan"), 1.0, 1.0, None, None])})
+    g, ora = pab.GroupBy("k", rb), orc.OracleGroupBy(rb, "k")
+    assert g.count_distinct("v").to_pylist() == ora.agg("count_distinct", "v").to_pylist() == [3, 1, 0]
+    e = pa.record_batch({"k": pa.array([], pa.int64()), "v": pa.array([], pa.float64())})
+    assert len(pab.GroupBy("k", e).count_distinct("v")) == 0
