@@ -1537,6 +1537,7 @@ int pa_groupby_take_grouped(pa_groupby* g, const struct ArrowDeviceArray* column
   PA_TRY(load_column(column, schema, st, g->device, &col));
   if (col.n != g->n) return set_err(PA_ERR_INVALID, "column has %lld rows, keys have %lld", (long long)col.n, (long long)g->n);
   if (schema->dictionary) return set_err(PA_ERR_INVALID, "dictionary-encoded columns: gather the indices, keep the dictionary");
+  if (col.is_bool) return set_err(PA_ERR_INVALID, "boolean columns are not gathered on the device (bit-packed); use the row order of pa_groupby_groupings");
   DevBuf vals, valid;
   const int64_t n = g->n;
   PA_TRY(vals.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)) * col.width, st));

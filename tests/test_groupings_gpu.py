@@ -101,3 +101,5 @@ def test_groupings_empty_and_errors(pab):
     with pytest.raises(pab.PaError, match="rows"):
         g.take_grouped(pa.array([1.0, 2.0]))
     assert g.take_grouped(rb.column("v")).to_pylist() == [1.0, 3.0, 2.0]
+    with pytest.raises(pab.PaError, match="boolean"):
+        g.take_grouped(pa.array([True, False, True]))
