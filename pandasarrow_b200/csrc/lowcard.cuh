@@ -671,9 +671,10 @@ __global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, W
     if (threadIdx.x == 0) { atomicExch(a.status + ST_DENSE_MISS, 2u); atomicExch(a.status + ST_ABORT, 1u); }
     return;
   }
-  // with many replicas per id (a handful of groups) the accesses are conflict free and 12 warps already
-  // saturate HBM; otherwise all 16 warps scan
-  const int nwarps = DENSEK ? (c.rlog >= 3 ? 12 : Cfg::WARPS) : Cfg::WARPS_HASH;
+  // lane-private replicas (32 per id) of the narrow layout are conflict free and 12 warps already saturate HBM
+  // (2.99 against 3.05 ms at 16 groups); everything else wants all 16 warps (wide set: 3.6 against 4.2 ms at 16
+  // groups, 4.4 against 5.3 ms at 64; narrow 64 groups: 3.3 against 3.7 ms)
+  const int nwarps = DENSEK ? ((!WIDE && c.rlog >= 5) ? 12 : Cfg::WARPS) : Cfg::WARPS_HASH;
   c.nwarps = nwarps;
   const size_t off_acc = DENSEK ? L::OFF_ACC_DENSE : L::OFF_ACC_HASH;
   unsigned char* my_acc = smem + off_acc + L::ACC_PER_WARP * (warp < nwarps ? warp : 0);
