@@ -288,9 +288,7 @@ __device__ __forceinline__ bool gtable_probe_accumulate(typename SlotOf<WIDE>::t
 template <int VC, bool WIDE, bool FAST>
 __global__ void __launch_bounds__(256, 3) k_gtable_scan(GScanArgs a) {
   using SlotT = typename SlotOf<WIDE>::type;
-  constexpr int SLOT_LOG2 = WIDE ? 6 : 5;
   SlotT* table = static_cast<SlotT*>(a.table);
-  const uint64_t cap = a.cap_mask + 1;
   constexpr int R = GT_R;
   const int64_t tile_rows = static_cast<int64_t>(blockDim.x) * R;
   const int64_t ntiles = (a.n + tile_rows - 1) / tile_rows;

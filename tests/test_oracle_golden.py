@@ -229,3 +229,48 @@ def test_multi_key_engine():
     assert g.unique(0).to_pylist() == [1, 2, 1, None]
     assert g.unique(1).to_pylist() == ["x", "x", "y", "x"]
     assert g.agg("sum", "v").to_pylist() == [6.0, 6.0, 3.0, 6.0]
+
+
+def test_second_stage_aggregates_pinned_to_arrow_scalar_kernels():
+    # GROUPBY_AGG(product), GROUPBY_NUMERIC_AGG(variance|stddev|all|any|count_distinct) (dataframe.cpp:1516-1536):
+    # the oracle must equal one arrow::compute call per group slice with default options — checked here through
+    # pyarrow's bindings of the same kernels (same libarrow), so the GPU parity tests rest on a pinned oracle.
+    import pyarrow.compute as pc
+    rng = np.random.default_rng(0)
+    n = 5000
+    k = rng.integers(0, 9, n)
+    vm = rng.random(n) < 0.2
+    vm[k == 4] = True                                         # an all-null group
+    rb = pa.record_batch({
+        "k": pa.array(k, pa.int64()),
+        "f": pa.array(rng.normal(2.0, 3.0, n), pa.float64(), mask=vm),
+        "i": pa.array(rng.integers(-4, 5, n), pa.int32(), mask=vm),
+        "p": pa.array(np.exp(rng.uniform(-0.01, 0.01, n)), pa.float64(), mask=vm),
+        "b": pa.array(rng.random(n) < 0.9, pa.bool_(), mask=vm),
+        "z": pa.array(rng.choice([0.0, -0.0, 1.5, float("nan")], n), pa.float64(), mask=vm)})
+    g = orc.OracleGroupBy(rb, "k")
+    keys = g.unique().to_pylist()
+    assert keys == list(dict.fromkeys(k.tolist()))            # 9 keys in 5000 rows: first-appearance order
+    tbl = pa.table(rb)
+    for j, key in enumerate(keys):
+        sl = tbl.filter(pc.equal(tbl["k"], key))
+        for func, col in (("variance", "f"), ("stddev", "f"), ("variance", "i"), ("stddev", "i")):
+            want = getattr(pc, func)(sl[col])
+            got, valid = g.agg(func, col, with_validity=True)
+            assert valid[j].as_py() == want.is_valid
+            if want.is_valid:
+                assert got[j].as_py() == want.as_py(), (func, col, key)          # bit for bit: same kernel, same slice
+            else:
+                assert got[j].as_py() == 0.0                                       # `.value` of a null scalar
+        for col in ("p", "i"):
+            want = pc.product(sl[col])
+            got = g.agg("product", col)[j]
+            assert got.is_valid == want.is_valid and (not want.is_valid or got.as_py() == want.as_py()), ("product", col, key)
+        for func in ("all", "any"):
+            want = getattr(pc, func)(sl["b"])
+            got, valid = g.agg(func, "b", with_validity=True)
+            assert valid[j].as_py() == want.is_valid and got[j].as_py() == (want.as_py() if want.is_valid else False)
+        for col in ("z", "i", "b"):
+            assert g.agg("count_distinct", col)[j].as_py() == pc.count_distinct(sl[col]).as_py(), ("count_distinct", col, key)
+    # -0.0 / +0.0 / NaN are three distinct values for arrow's memo table
+    assert max(g.agg("count_distinct", "z").to_pylist()) == 4
