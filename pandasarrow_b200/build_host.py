@@ -14,6 +14,8 @@ TEST_BIN = os.path.join(ROOT, "tests", "cpp", "_build", "facade_tests")
 SRC = os.path.join(HERE, "csrc", "host", "pd_groupby.cpp")
 HDR = os.path.join(HERE, "csrc", "host", "pd_groupby.h")
 TEST_SRC = os.path.join(ROOT, "tests", "cpp", "facade_tests.cpp")
+SCALAR_TEST_BIN = os.path.join(ROOT, "tests", "cpp", "_build", "scalar_agg_tests")
+SCALAR_TEST_SRC = os.path.join(ROOT, "tests", "cpp", "scalar_agg_tests.cpp")
 
 
 def _arrow():
@@ -48,5 +50,17 @@ def build(force: bool = False, verbose: bool = False):
     return FACADE, TEST_BIN
 
 
+def build_scalar_tests(force: bool = False):
+    """tests/cpp/scalar_agg_tests (whole-column aggregates); kept apart from build() so that it cannot affect it."""
+    inc, libdir, libs = _arrow()
+    build(force)
+    if force or _stale(SCALAR_TEST_BIN, [SCALAR_TEST_SRC, HDR, FACADE]):
+        cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-Wall", "-Wno-deprecated-declarations", "-I", inc, SCALAR_TEST_SRC, "-o", SCALAR_TEST_BIN,
+               "-L", LIB_DIR, "-lpd_b200", "-lpa_b200", "-L", libdir, f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{LIB_DIR}"] + libs
+        subprocess.run(cmd, check=True)
+    return SCALAR_TEST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_scalar_tests(force="--force" in sys.argv))

@@ -357,6 +357,63 @@ Scalar Series::sum() const {
   return Scalar(ReturnOrThrowOnFailure(arrow::compute::CallFunction("sum", {m_array})).scalar());
 }
 
+namespace {
+// One group over the whole column: constant int64 key -> pa_groupby_create -> one fused pass -> G = 1 results.
+arrow::Result<arrow::ArrayVector> column_aggregate(const ArrayPtr& col, uint32_t mask) {
+  if (!col) return arrow::Status::Invalid("empty series");
+  ARROW_ASSIGN_OR_RAISE(auto zeros, arrow::MakeArrayFromScalar(arrow::Int64Scalar(0), col->length()));
+  Exported k(*zeros);
+  pa_options opt;
+  pa_options_init(&opt);
+  pa_groupby* h = nullptr;
+  if (pa_groupby_create(&k.dev, &k.schema, 1, &opt, &h) != PA_OK) return pa_status("pa_groupby_create");
+  std::unique_ptr<pa_groupby, void (*)(pa_groupby*)> guard(h, pa_groupby_destroy);
+  Exported v(*col);
+  if (pa_groupby_aggregate(h, &v.dev, &v.schema, mask) != PA_OK) return pa_status("aggregate");
+  arrow::ArrayVector out;
+  for (uint32_t bit = 1; bit <= PA_AGG_LAST; bit <<= 1) {
+    if (!(mask & bit)) continue;
+    ArrowArray a;
+    ArrowSchema s;
+    if (pa_groupby_fetch(h, bit, &a, &s) != PA_OK) return pa_status("fetch");
+    ARROW_ASSIGN_OR_RAISE(auto arr, import_result(&a, &s));
+    out.push_back(arr);
+  }
+  return out;
+}
+
+// first (only) group of a G <= 1 result; an empty column has no group: null, as arrow's min_count = 1 gives
+ScalarPtr only_value(const ArrayPtr& arr) {
+  if (arr->length() == 0) return arrow::MakeNullScalar(arr->type());
+  return ReturnOrThrowOnFailure(arr->GetScalar(0));
+}
+
+Scalar column_scalar(const ArrayPtr& col, uint32_t bit, bool skip_null) {
+  auto r = ReturnOrThrowOnFailure(column_aggregate(col, bit));
+  ScalarPtr s = only_value(r[0]);
+  if (!skip_null && col->null_count() > 0) s = arrow::MakeNullScalar(s->type);
+  return Scalar(s);
+}
+}  // namespace
+
+Scalar Series::mean(bool skip_null) const { return column_scalar(m_array, PA_AGG_MEAN, skip_null); }
+Scalar Series::min(bool skip_null) const { return column_scalar(m_array, PA_AGG_MIN, skip_null); }
+Scalar Series::max(bool skip_null) const { return column_scalar(m_array, PA_AGG_MAX, skip_null); }
+Scalar Series::sum_on_device(bool skip_null) const { return column_scalar(m_array, PA_AGG_SUM, skip_null); }
+
+std::pair<Scalar, Scalar> Series::min_max(bool skip_null) const {
+  auto r = ReturnOrThrowOnFailure(column_aggregate(m_array, PA_AGG_MIN | PA_AGG_MAX));
+  ScalarPtr mn = only_value(r[0]), mx = only_value(r[1]);
+  if (!skip_null && m_array->null_count() > 0) { mn = arrow::MakeNullScalar(mn->type); mx = arrow::MakeNullScalar(mx->type); }
+  return {Scalar(mn), Scalar(mx)};
+}
+
+int64_t Series::count() const {
+  auto r = ReturnOrThrowOnFailure(column_aggregate(m_array, PA_AGG_COUNT));
+  if (r[0]->length() == 0) return 0;
+  return std::static_pointer_cast<arrow::Int64Array>(r[0])->Value(0);
+}
+
 Scalar DataFrame::sum() const {
   auto chunked = std::make_shared<arrow::ChunkedArray>(m_array->columns());
   return Scalar(ReturnOrThrowOnFailure(arrow::compute::CallFunction("sum", {chunked})).scalar());

@@ -93,7 +93,16 @@ class Series {
   Scalar operator[](int64_t i) const { return Scalar(ReturnOrThrowOnFailure(m_array->GetScalar(i))); }
   template <class T>
   std::vector<T> values() const;
-  Scalar sum() const;   // ndframe.cpp:220 (whole-column sum; used by the reference's apply tests)
+  Scalar sum() const;   // ndframe.cpp:220 (whole-column sum; used by the reference's apply tests) — host Arrow call, see DESIGN §1
+  // NDFrame::mean/min/max/count/min_max (ndframe.cpp:119,160-175) on the GPU: the column is
+  // aggregated as ONE group through the same C ABI (constant key).  skip_null = false: null as soon as the column
+  // holds a null, as ScalarAggregateOptions{skip_nulls = false} makes arrow answer.
+  Scalar mean(bool skip_null = true) const;
+  Scalar min(bool skip_null = true) const;
+  Scalar max(bool skip_null = true) const;
+  std::pair<Scalar, Scalar> min_max(bool skip_null = true) const;
+  int64_t count() const;
+  Scalar sum_on_device(bool skip_null = true) const;   // what sum() becomes once verified on the GPU box
   // series.cpp:351-359
   Resampler resample(std::string const& rule, bool closed_right = false, bool label_right = false,
                      TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0),
