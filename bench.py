@@ -112,6 +112,16 @@ def algorithmic_bytes(n_rows: int, n_groups: int, n_aggs: int) -> float:
     return 16.0 * n_rows + n_groups * (8.0 + 8.0 * n_aggs)
 
 
+def _hostgen():
+    """hostgen.py (numpy data generator) loaded by path: importing the package would load libpa_b200.so,
+    which must not appear in the reference arm's process."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pa_hostgen", os.path.join(ROOT, "pandasarrow_b200", "hostgen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def cpu_reference(rows: int, groups: int, repeats: int = 1) -> dict:
     """The reference's CPU path (oracle port of its Arrow call sequence) on this box's host cores:
     GroupBy ctor (hash + groupings + gathers of index and every column + per-group map inserts:
@@ -119,7 +129,7 @@ def cpu_reference(rows: int, groups: int, repeats: int = 1) -> dict:
     cores (OpenMP standing in for TBB)."""
     import pyarrow as pa
     from oracle import oracle as orc
-    from pandasarrow_b200 import hostgen as hg
+    hg = _hostgen()
     threads = os.cpu_count() or 1
     rb = pa.record_batch({"k": pa.array(hg.keys(rows, groups)), "v": pa.array(hg.vals(rows))})
     index = pa.array(range(rows), pa.int64())

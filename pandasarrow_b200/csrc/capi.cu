@@ -1675,13 +1675,22 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
     return set_err(PA_ERR_INVALID, "axis must be a TimestampArray but got array of type '%s'", f ? f : "?");  // resample.cpp:213-216
   if (ix.valid) return set_err(PA_ERR_NOT_IMPLEMENTED, "resample: null timestamps are not supported");
   int64_t ticks_per_day = 86400LL * 1000000000LL;
+  int64_t ns_per_tick = 1;
   if (is_ts) {
     switch (f[2]) {
-      case 's': ticks_per_day = 86400LL; break;
-      case 'm': ticks_per_day = 86400LL * 1000; break;
-      case 'u': ticks_per_day = 86400LL * 1000000; break;
+      case 's': ticks_per_day = 86400LL; ns_per_tick = 1000000000LL; break;
+      case 'm': ticks_per_day = 86400LL * 1000; ns_per_tick = 1000000LL; break;
+      case 'u': ticks_per_day = 86400LL * 1000000; ns_per_tick = 1000LL; break;
       default: break;
     }
+  }
+  // freq / offset / custom origin arrive in nanoseconds; the bucket arithmetic runs in index ticks
+  if (ns_per_tick != 1) {
+    if (freq_ns % ns_per_tick || offset_ns % ns_per_tick || (origin == 5 && origin_custom_ns % ns_per_tick))
+      return set_err(PA_ERR_INVALID, "resample: freq / offset / origin are not whole multiples of the index unit ('%s')", f);
+    freq_ns /= ns_per_tick;
+    offset_ns /= ns_per_tick;
+    origin_custom_ns /= ns_per_tick;
   }
   g->n = ix.n;
   if (g->n >= 0xFFFFFFFELL) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-2 rows per call; shard by row range");

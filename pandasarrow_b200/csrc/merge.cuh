@@ -348,18 +348,27 @@ __global__ void __launch_bounds__(MS_THREADS, 1) k_merge_small(MergeSmallArgs a)
     else if (key == kEmptyKey) slot = MS_TCAP + 1;
     else {
       slot = static_cast<uint32_t>(hash_key64(key ^ 0xA5A5A5A5A5A5A5A5ull)) & (MS_TCAP - 1);
-      for (;;) {
+      // Bounded probe: more than MS_MAX_GROUPS distinct keys (skewed ownership) must end in ST_OVERFLOW and the
+      // general merge on the host side, never in a full table that threads circle forever.
+      bool placed = false;
+      for (int probe = 0; probe < MS_TCAP; ++probe) {
+        if (*reinterpret_cast<volatile uint32_t*>(&s_ngroups) > MS_MAX_GROUPS) break;
         const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(tkeys + slot);
-        if (k == key) break;
+        if (k == key) { placed = true; break; }
         if (k == kEmptyKey) {
           const uint64_t old = atomicCAS(tkeys + slot, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
           if (old == kEmptyKey) {
             if (atomicAdd(&s_ngroups, 1u) >= MS_MAX_GROUPS) atomicExch(a.status + ST_OVERFLOW, 1u);
+            placed = true;
             break;
           }
-          if (old == key) break;
+          if (old == key) { placed = true; break; }
         }
         slot = (slot + 1) & (MS_TCAP - 1);
+      }
+      if (!placed) {   // table (nearly) full: give up on this record, the host reruns the general merge
+        atomicExch(a.status + ST_OVERFLOW, 1u);
+        continue;
       }
     }
     // push front (16-bit exchange emulated on the containing 32-bit word)

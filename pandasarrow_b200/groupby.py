@@ -233,11 +233,18 @@ class GroupBy:
         for a in aggs:
             mask |= PA_AGG[a]
         arg = _CArg(values)
-        fn = self._L.pa_groupby_aggregate if (wait or fetch) else self._L.pa_groupby_aggregate_async
+        deferred = not (wait or fetch)
+        fn = self._L.pa_groupby_aggregate_async if deferred else self._L.pa_groupby_aggregate
         try:
             _check(fn(self._h, C.byref(arg.dev), C.byref(arg.schema), mask))
         finally:
-            arg.close()
+            if deferred:
+                # the handle keeps borrowed pointers of the value column until the pass is finished (a declined
+                # dense pass is redone from them): keep the column alive until the next call replaces it
+                self._pending_arg = arg
+            else:
+                arg.close()
+                self._pending_arg = None
         if not fetch:
             return {}
         return {a: self.fetch(a) for a in aggs}
