@@ -37,11 +37,14 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
     ap.add_argument("--groups", type=int, default=1000)
-    ap.add_argument("--sweep", action="store_true", help="also run the config-2 cardinality sweep (device resident)")
+    ap.add_argument("--sweep", action="store_true", help="(default at N=1) config-2 cardinality sweep, device resident")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--config5-groups", type=int, default=100_000_000, help="N>1: groups of the config-5 extra (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=100_000_000, help="rows of the bounded CPU-baseline sample")
-    ap.add_argument("--extras", action="store_true", help="also time config 3 (multi-key, nullable) and config 4 (resample OHLC)")
+    ap.add_argument("--extras", action="store_true", help="(default at N=1) config 3 (multi-key, nullable), config 4 (resample OHLC), scattered keys, ...")
     return ap.parse_args()
 
 
@@ -97,11 +100,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _source_sha(rel: str) -> str:
+    import hashlib
+    return hashlib.sha256(open(os.path.join(ROOT, rel), "rb").read()).hexdigest()[:16]
+
+
 def measured_traffic(kernel: str, n_rows: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
-    `ncu --set full` capture (profiles/r1_traffic.json); scaled linearly when the capture used another row count."""
+    `ncu --set full` capture (profiles/r2_traffic.json); scaled linearly when the capture used another row count.
+    The capture is stamped with the hash of the kernel's source file: a stale capture reads as null."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[kernel]
+        if t.get("source_sha") != _source_sha(t["source"]):
+            return None
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (n_rows / t["rows"])
     except Exception:
         return None
@@ -295,7 +306,9 @@ def main():
 
     # ---------------- optional cardinality sweep (config 2), device resident ----------------
     sweep = None
-    if args.sweep and rank == 0:
+    do_sweep = (args.sweep or world == 1) and not args.no_sweep and world == 1
+    do_extras = (args.extras or world == 1) and not args.no_extras and world == 1
+    if do_sweep and rank == 0:
         sweep = []
         for g_ in SWEEP_G:
             if g_ > n:
@@ -321,9 +334,31 @@ def main():
 
     # ---------------- optional: configs 3 and 4, device resident ----------------
     extras = None
-    if args.extras and rank == 0:
+    if do_extras and rank == 0:
         extras = {}
         try:
+            # the headline workload with SCATTERED 64-bit keys (an odd multiplier + offset over the same group
+            # ids: the key set is no dense window, so the shared-memory kernel runs in hash mode)
+            for g_, tag in ((G, "scattered_keys"), (4096, "scattered_keys_4096")):
+                pab.synth.keys(keys, g_, first_row)
+                keys.mul_(0x2545F4914F6CDD1D).add_(0x1234567)
+                torch.cuda.synchronize()
+                h = pab.GroupBy("k", {"k": dk, "v": dv}, stream=stream.cuda_stream, device=local)
+                tl = []
+                for _ in range(3):
+                    h.aggregate(dv, AGGS, fetch=False)
+                for _ in range(5):
+                    h.aggregate(dv, AGGS, fetch=False)
+                    tl.append(h.timing())
+                tl.sort(key=lambda t: t["total_ms"])
+                t = tl[len(tl) // 2]
+                ab = algorithmic_bytes(n, h.groupSize(), len(AGGS))
+                extras[tag] = {"rows": n, "groups": h.groupSize(), "path": t["path"], "mode": t["mode"], "total_ms": t["total_ms"],
+                               "scan_ms": t["scan_ms"], "rows_per_s": n / (t["total_ms"] * 1e-3),
+                               "scan_GBps": ab / (t["scan_ms"] * 1e-3) / 1e9, "frac": ab / (t["scan_ms"] * 1e-3) / 1e9 / peak}
+                h.close()
+            pab.synth.keys(keys, G, first_row)
+            torch.cuda.synchronize()
             # config 4: sorted timestamp[ns] index, 1-minute buckets (~1000 ticks each), OHLC + sum
             ts = torch.empty(n, dtype=torch.int64, device=dev)
             pab.synth.timestamps(ts)
@@ -398,6 +433,48 @@ def main():
             h.close()
         except Exception as ex:  # noqa: BLE001
             extras["error"] = repr(ex)[:300]
+
+    # ---------------- N > 1: config 5 (BASELINE configs[4]): 1 B rows per GPU, 100 M groups, counted exchange ----------------
+    if world > 1 and args.config5_groups > 0 and not args.no_extras:
+        extras = extras or {}
+        try:
+            g5 = args.config5_groups
+            pab.synth.keys(keys, g5, first_row)
+            torch.cuda.synchronize()
+            h5 = pab.GroupBy("k", {"k": dk, "v": dv}, stream=stream.cuda_stream, device=local, row_base=first_row, expected_groups=g5)
+            local_ms = []
+            for _ in range(3):                                   # local pass alone (what one GPU does for its shard)
+                h5.aggregate(dv, AGGS, fetch=False)
+                local_ms.append(h5.timing()["total_ms"])
+            def step5():
+                with torch.cuda.stream(stream):
+                    return D.sharded_aggregate(h5, dv, AGGS, "g", "l", stream=stream.cuda_stream, wait=True, padded=False)
+            m5 = step5()                                         # warm-up (allocations, NCCL channels)
+            m5.close()
+            barrier()
+            k5 = 3
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record(stream)
+            found = 0
+            for _ in range(k5):
+                m5 = step5()
+                found = m5.groupSize()
+                m5.close()
+            t1.record(stream)
+            barrier()
+            t5 = torch.tensor([t0.elapsed_time(t1) / k5, min(local_ms)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            tg5 = torch.tensor([found], device=dev, dtype=torch.int64)
+            dist.all_reduce(tg5)
+            extras["config5"] = {"rows_per_gpu": n, "groups": g5, "groups_found_global": int(tg5.item()), "aggs": AGGS,
+                                 "exchange": "counted", "steps": k5, "ms_per_step": t5[0].item(),
+                                 "local_pass_ms": t5[1].item(), "rows_per_s": world * n / (t5[0].item() * 1e-3),
+                                 "efficiency_vs_local_pass": t5[1].item() / t5[0].item()}
+            h5.close()
+        except Exception as ex:  # noqa: BLE001
+            extras["config5"] = {"error": repr(ex)[:300]}
+        pab.synth.keys(keys, G, first_row)
+        torch.cuda.synchronize()
 
     # ---------------- end to end through the C ABI with HOST buffers (`e2e`) ----------------
     e2e = None

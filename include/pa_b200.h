@@ -128,7 +128,9 @@ typedef struct pa_options {
   int64_t row_base;          /* global row number of local row 0 (multi-GPU row-range shards) */
   int64_t lowcard_no_dense;  /* 1 = the shared-memory path never uses dense (key - base) addressing, always hashes */
   int64_t no_partition;      /* 1 = never reorder the rows by table region before a global-table scan (>= 2 M groups) */
-  int64_t reserved[2];
+  int64_t lowcard_detect;    /* shared-memory path, lanes of a 32-row batch that hit one group: 0 = default (MATCH.ANY),
+                                1 = claim tags in the count words (the round-1 scheme; kept for A/B measurements) */
+  int64_t reserved[1];
 } pa_options;
 
 typedef struct pa_groupby pa_groupby;      /* opaque: key columns + device group table */
@@ -170,6 +172,16 @@ int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values,
  * pa_groupby_aggregate. */
 int pa_groupby_aggregate_async(pa_groupby* g, const struct ArrowDeviceArray* values,
                                const struct ArrowSchema* value_schema, uint32_t agg_mask);
+
+/* NDFrame<T>::sum / mean / min / max / count / first / last / min_max / agg
+ * (/root/reference/src/ndframe.cpp:119,129,160-175,220,237-241): the whole column aggregated as ONE group by the
+ * same fused pass (no key column is passed; a constant key is generated on the device).  Returns a handle with
+ * num_groups <= 1 (0 for an empty column) whose results are read with pa_groupby_fetch.  skip_nulls != 0:
+ * FIRST / LAST are the first / last VALID value, as arrow's scalar `first` / `last` kernels (GroupBy::first/last
+ * stay positional); skip_nulls == 0: positional.  The caller applies arrow's "any null -> null" rule for
+ * skip_nulls == 0 on sum / mean / min / max from the column's null_count. */
+int pa_column_aggregate(const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
+                        uint32_t agg_mask, int32_t skip_nulls, const pa_options* opt, pa_groupby** out);
 
 /* Copies one finished aggregate (a single PA_AGG_* bit of the last aggregate call) to a host
  * Arrow array of length num_groups, first-appearance order. */

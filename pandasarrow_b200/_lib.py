@@ -20,7 +20,7 @@ PA_PARTIAL_WORDS = 11
 EXPORTS = [
     "pa_last_error", "pa_version", "pa_options_init", "pa_device_count", "pa_groupby_create",
     "pa_groupby_num_groups", "pa_groupby_unique", "pa_groupby_aggregate", "pa_groupby_aggregate_async",
-    "pa_groupby_fetch",
+    "pa_groupby_fetch", "pa_column_aggregate",
     "pa_groupby_row_ids", "pa_groupby_groupings", "pa_groupby_take_grouped", "pa_groupby_groupings_timing", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
     "pa_groupby_sync",
     "pa_groupby_destroy", "pa_resample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
@@ -57,7 +57,7 @@ class ArrowDeviceArray(C.Structure):
 class PaOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("path", C.c_int32), ("expected_groups", C.c_int64),
                 ("cuda_stream", C.c_void_p), ("row_base", C.c_int64), ("lowcard_no_dense", C.c_int64),
-                ("no_partition", C.c_int64), ("reserved", C.c_int64 * 2)]
+                ("no_partition", C.c_int64), ("lowcard_detect", C.c_int64), ("reserved", C.c_int64 * 1)]
 
 
 _lib = None
@@ -85,6 +85,8 @@ def load():
     L.pa_groupby_unique.argtypes = [P, C.c_int32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_aggregate.argtypes = [P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32]
     L.pa_groupby_aggregate_async.argtypes = [P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32]
+    L.pa_column_aggregate.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32, C.c_int32,
+                                      C.POINTER(PaOptions), C.POINTER(P)]
     L.pa_groupby_fetch.argtypes = [P, C.c_uint32, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_first_rows.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_groupby_row_ids.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]

@@ -334,21 +334,22 @@ enum LcOutcome { LC_DONE = 0, LC_DENSE_MISS = 1, LC_OVERFLOW = 2 };
 
 bool lc_is_wide(uint32_t mask, int vc) { return is_wide(mask, vc); }
 
-template <int VC, bool WIDE>
+template <int VC, bool WIDE, int DET>
 int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast, bool hash_kernel) {
-  using L = LcSmem<VC, WIDE>;
   using Cfg = LcCfg<VC, WIDE>;
   cudaStream_t st = g->stream;
   k_lowcard_prep<<<LC_PREP_GRID, 256, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   if (hash_kernel) {
-    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, false> : k_lowcard_scan<VC, WIDE, false, false>;
-    CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL_HASH)));
-    scan<<<grid, Cfg::WARPS_HASH * 32, L::TOTAL_HASH, st>>>(a);
+    using L = LcSmem<VC, WIDE, true>;
+    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, false, DET> : k_lowcard_scan<VC, WIDE, false, false, DET>;
+    CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL)));
+    scan<<<grid, L::WARPS * 32, L::TOTAL, st>>>(a);
   } else {
-    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, true> : k_lowcard_scan<VC, WIDE, false, true>;
-    CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL_DENSE)));
-    scan<<<grid, Cfg::WARPS * 32, L::TOTAL_DENSE, st>>>(a);
+    using L = LcSmem<VC, WIDE, false>;
+    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, true, DET> : k_lowcard_scan<VC, WIDE, false, true, DET>;
+    CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL)));
+    scan<<<grid, L::WARPS * 32, L::TOTAL, st>>>(a);
   }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(g->ev[2], st));
@@ -358,6 +359,13 @@ int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, 
   CUDA_TRY(cudaGetLastError());
   g->last_launches += 4;
   return PA_OK;
+}
+
+template <int VC, bool WIDE>
+int launch_lowcard_d(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast, bool hash_kernel) {
+  // duplicate detection inside a 32-row batch: MATCH.ANY (default) or the round-1 claim tags (pa_options.lowcard_detect = 1)
+  if (g->opt.lowcard_detect == 1) return launch_lowcard_t<VC, WIDE, 0>(g, a, m, grid, fast, hash_kernel);
+  return launch_lowcard_t<VC, WIDE, 1>(g, a, m, grid, fast, hash_kernel);
 }
 
 int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool force_hash, LcOutcome* outcome,
@@ -432,13 +440,13 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   m.status = a.status;
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
   if (kwide) {
-    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, true>(g, a, m, grid, fast, force_hash)));
-    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, true>(g, a, m, grid, fast, force_hash)));
-    else PA_TRY((launch_lowcard_t<VC_U, true>(g, a, m, grid, fast, force_hash)));
+    if (vc == VC_F) PA_TRY((launch_lowcard_d<VC_F, true>(g, a, m, grid, fast, force_hash)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_d<VC_I, true>(g, a, m, grid, fast, force_hash)));
+    else PA_TRY((launch_lowcard_d<VC_U, true>(g, a, m, grid, fast, force_hash)));
   } else {
-    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, false>(g, a, m, grid, fast, force_hash)));
-    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, false>(g, a, m, grid, fast, force_hash)));
-    else PA_TRY((launch_lowcard_t<VC_U, false>(g, a, m, grid, fast, force_hash)));
+    if (vc == VC_F) PA_TRY((launch_lowcard_d<VC_F, false>(g, a, m, grid, fast, force_hash)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_d<VC_I, false>(g, a, m, grid, fast, force_hash)));
+    else PA_TRY((launch_lowcard_d<VC_U, false>(g, a, m, grid, fast, force_hash)));
   }
   CUDA_TRY(cudaEventRecord(g->ev[3], st));
   if (deferred) {   // the scratch buffers above are released in stream order; the status is read by finish_pending()
@@ -1435,6 +1443,54 @@ int pa_groupby_aggregate(pa_groupby* g, const struct ArrowDeviceArray* values, c
 int pa_groupby_aggregate_async(pa_groupby* g, const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
                                uint32_t agg_mask) {
   return aggregate_entry(g, values, value_schema, agg_mask, true);
+}
+
+// NDFrame<T>::sum/mean/min/max/count/first/last/min_max/agg (/root/reference/src/ndframe.cpp:119-241): the whole
+// column as ONE group (constant key generated on the device), through the same fused pass.
+int pa_column_aggregate(const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema, uint32_t agg_mask,
+                        int32_t skip_nulls, const pa_options* opt, pa_groupby** out) {
+  if (!values || !value_schema || !out) return set_err(PA_ERR_INVALID, "pa_column_aggregate: null argument");
+  if (agg_mask == 0 || (agg_mask & ~(PA_AGG_ALL | PA_AGG_STAGE2))) return set_err(PA_ERR_INVALID, "bad aggregate mask 0x%x", agg_mask);
+  HandlePtr g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  cudaStream_t st = g->stream;
+  const int64_t n = values->array.length;
+  if (n >= 0xFFFFFFFEll) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-2 rows per call; shard by row range");
+  g->keys.resize(1);
+  Column& k = g->keys[0];
+  k.format = "l"; k.width = 8; k.vc = VC_I; k.n = n;
+  PA_TRY(k.own_data.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)) * 8, st));
+  CUDA_TRY(cudaMemsetAsync(k.own_data.p, 0, static_cast<size_t>(std::max<int64_t>(n, 1)) * 8, st));
+  k.data = k.own_data.p;
+  g->n = n;
+  PA_TRY(setup_keys(g.get()));
+  const uint32_t positional = agg_mask & (PA_AGG_FIRST | PA_AGG_LAST);
+  const bool patch = skip_nulls && positional && values->array.null_count != 0 && values->array.buffers[0] != nullptr && n > 0;
+  if (!patch) {
+    PA_TRY(aggregate_entry(g.get(), values, value_schema, agg_mask, false));
+  } else {
+    // first / last skip nulls here (arrow's scalar kernels), unlike GroupBy::first/last which are positional
+    Column val;
+    PA_TRY(load_column(values, value_schema, st, g->device, &val));
+    if (val.is_bool) return set_err(PA_ERR_INVALID, "boolean columns aggregate with count / all / any only");
+    PA_TRY(aggregate_impl(g.get(), &val, (agg_mask & PA_AGG_ALL) | PA_AGG_FIRST | PA_AGG_LAST));
+    DevBuf range;
+    PA_TRY(range.alloc(8, st));
+    const uint32_t init[2] = {kNoRow, 0u};
+    CUDA_TRY(cudaMemcpyAsync(range.p, init, 8, cudaMemcpyHostToDevice, st));
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 8)));
+    k_valid_row_range<<<grid, 256, 0, st>>>(val.valid, val.bit_off, n, range.as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+    if (g->G > 0) {
+      k_apply_row_range<<<1, 1, 0, st>>>(range.as<uint32_t>(), g->res.first_row, g->res.last_row);
+      CUDA_TRY(cudaGetLastError());
+    }
+    PA_TRY(run_emit(g.get(), &val, (agg_mask & PA_AGG_ALL) | PA_AGG_FIRST | PA_AGG_LAST));
+    if (agg_mask & PA_AGG_STAGE2) PA_TRY(run_stage2(g.get(), &val, agg_mask & PA_AGG_STAGE2));
+    CUDA_TRY(cudaStreamSynchronize(st));   // `val` / `range` may own device copies
+  }
+  *out = g.release();
+  return PA_OK;
 }
 
 int pa_groupby_fetch(pa_groupby* g, uint32_t agg_bit, struct ArrowArray* out, struct ArrowSchema* out_schema) {

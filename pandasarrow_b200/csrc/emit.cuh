@@ -137,6 +137,36 @@ __global__ void __launch_bounds__(256) k_emit(EmitArgs a) {
   }
 }
 
+// Whole-column first / last with skip_nulls (arrow's scalar `first` / `last`, NDFrame::first/last, ndframe.cpp:129,160):
+// lowest / highest VALID row.  range[0] = min valid row (init kNoRow), range[1] = max valid row + 1 (init 0).
+__global__ void __launch_bounds__(256) k_valid_row_range(const uint8_t* valid, int64_t bit_off, int64_t n, uint32_t* range) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  uint32_t lo = kNoRow, hi = 0;
+  for (; i < n; i += stride) {
+    if (bit_at(valid, bit_off + i)) {
+      const uint32_t r = static_cast<uint32_t>(i);
+      lo = r < lo ? r : lo;
+      hi = r + 1 > hi ? r + 1 : hi;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const uint32_t ol = __shfl_xor_sync(0xFFFFFFFFu, lo, d), oh = __shfl_xor_sync(0xFFFFFFFFu, hi, d);
+    lo = ol < lo ? ol : lo;
+    hi = oh > hi ? oh : hi;
+  }
+  if (lane_id() == 0) {
+    if (lo != kNoRow) atomicMin(range, lo);
+    if (hi) atomicMax(range + 1, hi);
+  }
+}
+// Points the single group's first / last row at the valid range (no valid row: keeps the positional rows, whose
+// values are null anyway).
+__global__ void k_apply_row_range(const uint32_t* range, uint32_t* first_row, uint32_t* last_row) {
+  if (range[0] != kNoRow) { first_row[0] = range[0]; last_row[0] = range[1] - 1u; }
+}
+
 // Arrow boolean values (bit-packed, `bit_off` < 8 bits into the first byte) -> one byte per value.
 __global__ void __launch_bounds__(256) k_unpack_bool(const uint8_t* bits, int64_t bit_off, int64_t n, uint8_t* out) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;

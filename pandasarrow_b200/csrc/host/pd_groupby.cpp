@@ -353,25 +353,18 @@ arrow::Result<DataFrame> GroupBy::apply(std::function<ScalarPtr(Series const&)> 
   return DataFrame(arrow::schema(fields), G, columns);
 }
 
-Scalar Series::sum() const {
-  return Scalar(ReturnOrThrowOnFailure(arrow::compute::CallFunction("sum", {m_array})).scalar());
-}
-
 namespace {
-// One group over the whole column: constant int64 key -> pa_groupby_create -> one fused pass -> G = 1 results.
-arrow::Result<arrow::ArrayVector> column_aggregate(const ArrayPtr& col, uint32_t mask) {
+// NDFrame aggregates (ndframe.cpp:119-241): the whole column as ONE group, pa_column_aggregate -> G <= 1 results.
+arrow::Result<arrow::ArrayVector> column_aggregate(const ArrayPtr& col, uint32_t mask, bool skip_null = true) {
   if (!col) return arrow::Status::Invalid("empty series");
-  ARROW_ASSIGN_OR_RAISE(auto zeros, arrow::MakeArrayFromScalar(arrow::Int64Scalar(0), col->length()));
-  Exported k(*zeros);
   pa_options opt;
   pa_options_init(&opt);
   pa_groupby* h = nullptr;
-  if (pa_groupby_create(&k.dev, &k.schema, 1, &opt, &h) != PA_OK) return pa_status("pa_groupby_create");
-  std::unique_ptr<pa_groupby, void (*)(pa_groupby*)> guard(h, pa_groupby_destroy);
   Exported v(*col);
-  if (pa_groupby_aggregate(h, &v.dev, &v.schema, mask) != PA_OK) return pa_status("aggregate");
+  if (pa_column_aggregate(&v.dev, &v.schema, mask, skip_null ? 1 : 0, &opt, &h) != PA_OK) return pa_status("pa_column_aggregate");
+  std::unique_ptr<pa_groupby, void (*)(pa_groupby*)> guard(h, pa_groupby_destroy);
   arrow::ArrayVector out;
-  for (uint32_t bit = 1; bit <= PA_AGG_LAST; bit <<= 1) {
+  for (uint32_t bit = 1; bit <= PA_AGG_STDDEV; bit <<= 1) {
     if (!(mask & bit)) continue;
     ArrowArray a;
     ArrowSchema s;
@@ -389,17 +382,42 @@ ScalarPtr only_value(const ArrayPtr& arr) {
 }
 
 Scalar column_scalar(const ArrayPtr& col, uint32_t bit, bool skip_null) {
-  auto r = ReturnOrThrowOnFailure(column_aggregate(col, bit));
+  auto r = ReturnOrThrowOnFailure(column_aggregate(col, bit, skip_null));
   ScalarPtr s = only_value(r[0]);
-  if (!skip_null && col->null_count() > 0) s = arrow::MakeNullScalar(s->type);
+  // ScalarAggregateOptions{skip_nulls = false}: any null in the column makes the aggregate null (first / last are
+  // positional in that mode and carry their own validity)
+  if (!skip_null && col->null_count() > 0 && !(bit & (PA_AGG_FIRST | PA_AGG_LAST))) s = arrow::MakeNullScalar(s->type);
   return Scalar(s);
+}
+
+uint32_t agg_bit_of(std::string const& name) {
+  if (name == "sum") return PA_AGG_SUM;
+  if (name == "mean") return PA_AGG_MEAN;
+  if (name == "min") return PA_AGG_MIN;
+  if (name == "max") return PA_AGG_MAX;
+  if (name == "first") return PA_AGG_FIRST;
+  if (name == "last") return PA_AGG_LAST;
+  if (name == "product") return PA_AGG_PRODUCT;
+  return 0;
 }
 }  // namespace
 
+Scalar Series::sum(bool skip_null) const { return column_scalar(m_array, PA_AGG_SUM, skip_null); }
 Scalar Series::mean(bool skip_null) const { return column_scalar(m_array, PA_AGG_MEAN, skip_null); }
 Scalar Series::min(bool skip_null) const { return column_scalar(m_array, PA_AGG_MIN, skip_null); }
 Scalar Series::max(bool skip_null) const { return column_scalar(m_array, PA_AGG_MAX, skip_null); }
-Scalar Series::sum_on_device(bool skip_null) const { return column_scalar(m_array, PA_AGG_SUM, skip_null); }
+Scalar Series::first(bool skip_null) const { return column_scalar(m_array, PA_AGG_FIRST, skip_null); }
+Scalar Series::last(bool skip_null) const { return column_scalar(m_array, PA_AGG_LAST, skip_null); }
+Scalar Series::product(bool skip_null) const { return column_scalar(m_array, PA_AGG_PRODUCT, skip_null); }
+Scalar Series::sum_on_device(bool skip_null) const { return sum(skip_null); }
+
+// NDFrame::agg(name, skip_null) (ndframe.cpp:237-241): the aggregates of this path by name
+Scalar Series::agg(std::string const& name, bool skip_null) const {
+  if (name == "count") return Scalar(arrow::MakeScalar(count()));
+  const uint32_t bit = agg_bit_of(name);
+  if (!bit) throw std::runtime_error("NotImplemented: Series::agg(\"" + name + "\") is outside the B200 group-by path");
+  return column_scalar(m_array, bit, skip_null);
+}
 
 std::pair<Scalar, Scalar> Series::min_max(bool skip_null) const {
   auto r = ReturnOrThrowOnFailure(column_aggregate(m_array, PA_AGG_MIN | PA_AGG_MAX));
@@ -414,9 +432,34 @@ int64_t Series::count() const {
   return std::static_pointer_cast<arrow::Int64Array>(r[0])->Value(0);
 }
 
+// ndframe.cpp:220 over all columns (ndframe.h:329-335 concatenates them into one chunked array, which requires
+// one common dtype): the device sum of every column, folded in column order like arrow folds the chunks.
 Scalar DataFrame::sum() const {
-  auto chunked = std::make_shared<arrow::ChunkedArray>(m_array->columns());
-  return Scalar(ReturnOrThrowOnFailure(arrow::compute::CallFunction("sum", {chunked})).scalar());
+  ScalarPtr total;
+  for (int c = 0; c < m_array->num_columns(); ++c) {
+    auto r = ReturnOrThrowOnFailure(column_aggregate(m_array->column(c), PA_AGG_SUM));
+    ScalarPtr s = only_value(r[0]);
+    if (!s->is_valid) continue;
+    if (!total) { total = s; continue; }
+    if (!total->type->Equals(s->type)) throw std::runtime_error("DataFrame::sum: columns of different types");
+    switch (s->type->id()) {
+      case arrow::Type::DOUBLE:
+        total = arrow::MakeScalar(static_cast<const arrow::DoubleScalar&>(*total).value + static_cast<const arrow::DoubleScalar&>(*s).value);
+        break;
+      case arrow::Type::INT64:
+        total = arrow::MakeScalar(static_cast<int64_t>(static_cast<uint64_t>(static_cast<const arrow::Int64Scalar&>(*total).value) +
+                                                       static_cast<uint64_t>(static_cast<const arrow::Int64Scalar&>(*s).value)));
+        break;
+      default:
+        total = arrow::MakeScalar(static_cast<const arrow::UInt64Scalar&>(*total).value + static_cast<const arrow::UInt64Scalar&>(*s).value);
+    }
+  }
+  if (!total) {
+    if (m_array->num_columns() == 0) return Scalar(arrow::MakeNullScalar(arrow::float64()));
+    auto r = ReturnOrThrowOnFailure(column_aggregate(m_array->column(0), PA_AGG_SUM));
+    return Scalar(arrow::MakeNullScalar(r[0]->type()));
+  }
+  return Scalar(total);
 }
 
 arrow::Result<arrow::ArrayVector> GroupBy::aggregate(std::string const& column, uint32_t mask, bool drop_validity) {

@@ -13,9 +13,9 @@
 // index), not the reference's ~300-method wrappers (out of scope).
 //
 // Group materialisation (group(), MakeSubDataFrame, apply*, orderedGroups; group_by.h:38-83,141-162,
-// dataframe.cpp:1354-1510) is built lazily from the per-row group ids the GPU returns
-// (pa_groupby_row_ids = what Grouper::Consume returned) with Arrow's MakeGroupings / ApplyGroupings,
-// exactly the calls the reference makes after Consume (dataframe.cpp:1539-1569,1586-1597).
+// dataframe.cpp:1354-1510) is built lazily ON THE DEVICE: pa_groupby_groupings (= Grouper::MakeGroupings) and
+// pa_groupby_take_grouped (= Grouper::ApplyGroupings), the calls the reference makes after Consume
+// (dataframe.cpp:1539-1569,1586-1597); the façade only slices the gathered columns.
 // product / variance / stddev run a second device pass (stage2.cuh).  Not carried over (SURVEY.md §8f
 // "next"): approximate_median/mode/tdigest; those methods exist and return
 // arrow::Status::NotImplemented.
@@ -93,16 +93,21 @@ class Series {
   Scalar operator[](int64_t i) const { return Scalar(ReturnOrThrowOnFailure(m_array->GetScalar(i))); }
   template <class T>
   std::vector<T> values() const;
-  Scalar sum() const;   // ndframe.cpp:220 (whole-column sum; used by the reference's apply tests) — host Arrow call, see DESIGN §1
-  // NDFrame::mean/min/max/count/min_max (ndframe.cpp:119,160-175) on the GPU: the column is
-  // aggregated as ONE group through the same C ABI (constant key).  skip_null = false: null as soon as the column
-  // holds a null, as ScalarAggregateOptions{skip_nulls = false} makes arrow answer.
+  // NDFrame::sum/mean/min/max/count/first/last/min_max/agg (ndframe.cpp:119,129,160-175,220,237-241; SURVEY §8 row
+  // a17) on the GPU: the column is aggregated as ONE group by the fused pass (pa_column_aggregate).  skip_null =
+  // false: null as soon as the column holds a null, as ScalarAggregateOptions{skip_nulls = false} makes arrow answer.
+  // first / last follow arrow's scalar kernels here (skip_null: first / last VALID value), unlike GroupBy::first.
+  Scalar sum(bool skip_null = true) const;
   Scalar mean(bool skip_null = true) const;
   Scalar min(bool skip_null = true) const;
   Scalar max(bool skip_null = true) const;
+  Scalar first(bool skip_null = true) const;
+  Scalar last(bool skip_null = true) const;
+  Scalar product(bool skip_null = true) const;
+  Scalar agg(std::string const& name, bool skip_null = true) const;
   std::pair<Scalar, Scalar> min_max(bool skip_null = true) const;
   int64_t count() const;
-  Scalar sum_on_device(bool skip_null = true) const;   // what sum() becomes once verified on the GPU box
+  Scalar sum_on_device(bool skip_null = true) const;   // (kept for callers of round 1: same as sum())
   // series.cpp:351-359
   Resampler resample(std::string const& rule, bool closed_right = false, bool label_right = false,
                      TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0),

@@ -14,12 +14,17 @@
 //      dense : all sampled keys lie in a window of <= GMAX values -> id = key - base, no table at all.
 //              Keys not dense (declined before the first row) or a key outside the window met later
 //              (ST_DENSE_MISS): the host launches the hash-mode kernel.
-//      hash  : CTA-shared open-addressing table in shared memory, 2048 buckets of two 8-byte keys:
-//              one LDS.128 + one LDS.U16 per lookup, read-only in steady state.  New keys take an
-//              out-of-line slow path (ATOMS.CAS.64) that also obtains a GLOBAL id for the key from a
-//              small directory in global memory, so that ids mean the same group in every CTA and
-//              the merge needs no join.  Null keys and the key equal to the table sentinel have
-//              dedicated ids.
+//      hash  : CTA-shared open-addressing table in shared memory, 4096 PACKED 8-byte entries
+//              {52 key bits | 2-bit displacement | 10-bit id}: the key is first mixed by a BIJECTION of
+//              64 bits whose top 12 bits are the home slot, so home slot + displacement + the other 52
+//              bits identify the key exactly and ONE LDS.64 per probe answers "which id" (round 1: LDS.128
+//              of a two-key bucket + LDS.U16 of the id = 14 wavefronts per 32 rows against 6 now; the
+//              shared-memory pipe is what bounds this kernel).  Read-only in steady state; 12 % of the
+//              keys sit one slot past home (second probe, those lanes only), keys displaced by more than
+//              three slots (~2 in 1000) live in a 16-entry overflow list.  New keys take an out-of-line
+//              slow path (ATOMS.CAS.64) that also obtains a GLOBAL id for the key from a small directory
+//              in global memory, so that ids mean the same group in every CTA and the merge needs no
+//              join.  Null keys and the key equal to the directory sentinel have dedicated ids.
 //  * Stage 3: accumulators are WARP-PRIVATE arrays in shared memory (sum 8 B + count word 4 B per
 //    id; the wide variant adds last row, {min, max} and a double sum), updated with plain loads and
 //    stores — no atomics (sm_100a has no native 64-bit shared-memory atomics: f64/u64 adds compile
@@ -43,13 +48,17 @@
 
 namespace pa {
 
-constexpr int LC_NB_LOG2 = 11;
-constexpr int LC_NBUCKET = 1 << LC_NB_LOG2;  // buckets of two keys
-constexpr int LC_TCAP = LC_NBUCKET * 2;      // key slots
+constexpr int LC_HT_LOG2 = 12;
+constexpr int LC_HT = 1 << LC_HT_LOG2;       // packed entries of the hash-mode table
+constexpr int LC_HT_MAXD = 3;                // largest displacement an entry can record (2 bits)
+constexpr int LC_OVF = 16;                   // overflow list: keys displaced further than that
+constexpr uint64_t LC_HE_EMPTY = ~0ull;      // (id field 0x3FF is never assigned)
+constexpr uint32_t LC_HE_PENDING = 0x3FEu;   // id field while the inserting lane fetches the global id
+constexpr uint32_t LC_HE_OVF = 0x3FDu;       // id field of a key that did not get an id (more than GMAX keys)
 constexpr int LC_NB = 8;                     // 32-row batches per row group
 constexpr int LC_GROUP_ROWS = LC_NB * 32;    // rows per warp per row group
-constexpr uint16_t LC_ID_UNSET = 0xFFFFu;
-constexpr uint16_t LC_ID_OVF = 0xFFFEu;
+constexpr uint32_t LC_ID_UNSET = 0xFFFFu;
+constexpr uint32_t LC_ID_OVF = 0xFFFEu;
 constexpr uint32_t LC_NOID = 0xFFFFFFFFu;
 constexpr uint32_t LC_CNT_MASK = 0x00FFFFFFu;   // count field of a count word; byte 3 = claim tag
                                                 // (count == LC_CNT_MASK: the warp has not met this id yet)
@@ -57,6 +66,7 @@ constexpr int LC_GMAX_NARROW = 1024;   // sum / mean(float) / count / first : 12
 constexpr int LC_GMAX_WIDE_F = 1024;   // + min / max / last               : + 20 B per id, CTA shared (order independent)
 constexpr int LC_GMAX_WIDE_I = 640;    // + double sum (mean of integers)  : 20 B per id per warp
 constexpr int LC_GMAX_MAX = LC_GMAX_NARROW;
+constexpr int LC_GMAX_HASH = 1000;     // hash-mode kernel: ids fit 10 bits (< LC_HE_OVF) and 16 warps' accumulators fit next to the table
 
 // global key -> id directory (hash mode)
 constexpr int LC_GT_LOG2 = 13;
@@ -68,14 +78,17 @@ constexpr int LC_PREP_GRID = 64;       // x 256 threads = 16384 sampled keys
 template <int VC, bool WIDE>
 struct LcCfg {
   static constexpr bool DSUM = WIDE && VC != VC_F;
-  static constexpr int WARPS_HASH = 12;           // hash-mode kernel: the CTA-shared key table takes 40 KB
-  static constexpr int WARPS = 16;                // dense-mode kernel: its space holds four more warps' accumulators
+  static constexpr int WARPS = 16;                // dense-mode kernel (no key table)
   static constexpr int GMAX = WIDE ? (DSUM ? LC_GMAX_WIDE_I : LC_GMAX_WIDE_F) : LC_GMAX_NARROW;
   static constexpr int GP = GMAX + 2;             // + null-key group + (key == kEmptyKey) group
   static constexpr int ID_NULL = GMAX;
   static constexpr int ID_EMPTYKEY = GMAX + 1;
+  // hash-mode kernel: its own (smaller) id space so that the table and 16 warps' accumulators share 227 KB
+  static constexpr int GMAX_H = GMAX < LC_GMAX_HASH ? GMAX : LC_GMAX_HASH;
+  static constexpr int GP_H = GMAX_H + 2;
 };
 inline int lc_gmax(int vc, bool wide) { return wide ? (vc != VC_F ? LC_GMAX_WIDE_I : LC_GMAX_WIDE_F) : LC_GMAX_NARROW; }
+inline int lc_gmax_hash(int vc, bool wide) { const int g = lc_gmax(vc, wide); return g < LC_GMAX_HASH ? g : LC_GMAX_HASH; }
 
 // Written by k_lowcard_prep (zero-initialised by the host), read by scan / rank.
 struct LcPrep {
@@ -144,28 +157,32 @@ struct LcArgs {
   uint32_t* status;
 };
 
-// Shared-memory layout.  CTA shared: hash table, first rows, and (wide) {min, max} 16 B + last row 4 B per id,
-// which are order independent and therefore updated by all warps with shared-memory atomics after a plain
-// pre-check.  Per warp: [sum 8 B x GP] [dsum 8 B x GP (mean of integers)] [count word 4 B x GP].
-template <int VC, bool WIDE>
+// Shared-memory layout.  CTA shared: first rows, (wide) {min, max} 16 B + last row 4 B per id — order
+// independent, updated by all warps with shared-memory atomics after a plain pre-check — and, in the hash-mode
+// kernel (HASHK), the packed key table + overflow list.  Per warp: [sum 8 B x GP] [dsum 8 B x GP (mean of
+// integers)] [count word 4 B x GP].  The hash-mode kernel uses its own, slightly smaller id space (GP_H).
+template <int VC, bool WIDE, bool HASHK>
 struct LcSmem {
   using Cfg = LcCfg<VC, WIDE>;
-  static constexpr size_t GP = Cfg::GP;
+  static constexpr size_t GP = HASHK ? Cfg::GP_H : Cfg::GP;
   static constexpr size_t OFF_MISC = 0;                                          // 4 x u32
   static constexpr size_t OFF_MM = 16;                                           // GP x {min, max} (wide)
   static constexpr size_t OFF_FIRST = OFF_MM + (WIDE ? GP * 16 : 0);             // GP u32
   static constexpr size_t OFF_LAST = OFF_FIRST + GP * 4;                         // GP u32 (wide)
-  static constexpr size_t OFF_TKEYS = ((OFF_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;   // LC_TCAP u64 (hash mode)
-  static constexpr size_t OFF_TIDS = OFF_TKEYS + LC_TCAP * 8;                    // LC_TCAP u16 (hash mode)
-  static constexpr size_t OFF_ACC_HASH = OFF_TIDS + LC_TCAP * 2;                 // per-warp accumulators, hash mode
-  static constexpr size_t OFF_ACC_DENSE = OFF_TKEYS;                             // dense mode: no table
+  static constexpr size_t OFF_TAB = ((OFF_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;   // LC_HT packed entries (hash)
+  static constexpr size_t OFF_OVFK = OFF_TAB + (HASHK ? LC_HT * 8 : 0);          // LC_OVF keys (hash)
+  static constexpr size_t OFF_OVFI = OFF_OVFK + (HASHK ? LC_OVF * 8 : 0);        // LC_OVF ids (hash)
+  static constexpr size_t OFF_ACC = ((OFF_OVFI + (HASHK ? LC_OVF * 4 : 0) + 15) / 16) * 16;
   static constexpr size_t W_SUM = 0;
   static constexpr size_t W_DSUM = W_SUM + GP * 8;
   static constexpr size_t W_CW = W_DSUM + (Cfg::DSUM ? GP * 8 : 0);
   static constexpr size_t ACC_PER_WARP = ((W_CW + GP * 4 + 15) / 16) * 16;
-  static constexpr size_t TOTAL_HASH = OFF_ACC_HASH + ACC_PER_WARP * Cfg::WARPS_HASH;
-  static constexpr size_t TOTAL_DENSE = OFF_ACC_DENSE + ACC_PER_WARP * Cfg::WARPS;
-  static constexpr size_t TOTAL = TOTAL_HASH > TOTAL_DENSE ? TOTAL_HASH : TOTAL_DENSE;
+  static constexpr size_t BUDGET = 227 * 1024;
+  static constexpr int WARPS_FIT = static_cast<int>((BUDGET - OFF_ACC) / ACC_PER_WARP);
+  static constexpr int WARPS = HASHK ? (WARPS_FIT < 16 ? WARPS_FIT : 16) : Cfg::WARPS;
+  static constexpr size_t TOTAL = OFF_ACC + ACC_PER_WARP * WARPS;
+  static_assert(TOTAL <= BUDGET, "shared-memory layout exceeds 227 KB");
+  static_assert(WARPS >= 8, "too few warps to keep HBM busy");
 };
 
 // per-thread view of the CTA's shared state (32-bit shared-memory addresses for the hot arrays)
@@ -174,29 +191,27 @@ struct LcCtx {
   uint32_t mm;                        // CTA-shared {min, max} array (wide), shared-memory address
   unsigned long long* mm_p;           // the same, generic pointer (atomics)
   uint32_t* last_p;                   // CTA-shared last-row array (wide)
-  unsigned long long* tkeys;
-  uint16_t* tids;
+  uint32_t tab;                       // hash mode: packed table, shared-memory address
+  unsigned long long* tab_p;          // the same, generic pointer (atomics)
+  unsigned long long* ovf_keys;       // hash mode: overflow list
+  uint32_t* ovf_ids;
   uint32_t* cta_first;
-  uint32_t* misc;                     // [1] abort seen by this CTA
+  uint32_t* misc;                     // [1] abort seen by this CTA, [2] entries of the overflow list
   int nwarps;                         // warps of the CTA that scan rows
   uint64_t base;                      // dense mode: id = key - base, must be < window
   uint32_t window, rlog, rmask;       // dense mode: accumulator replication (slot = id << rlog | lane & rmask)
 };
 
-__device__ __forceinline__ uint32_t lc_bucket(uint64_t key) {
-  const uint32_t lo = static_cast<uint32_t>(key), hi = static_cast<uint32_t>(key >> 32);
-  return ((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u) ^ (lo >> 15)) * 0x2C1B3C6Du >> (32 - LC_NB_LOG2);
-}
+// Hash mode: bijective mix of the key; the top LC_HT_LOG2 bits are the home slot, the rest is what an entry stores.
+__device__ __forceinline__ uint64_t lc_mix(uint64_t key) { return (key ^ (key >> 32)) * 0x9E3779B97F4A7C15ull; }
 
-// Steady-state lookup of bucket `b`: one LDS.128 (both keys of the bucket) + one LDS.U16.  Returns a
-// value >= LC_ID_OVF when the key is not in this bucket or its id is not published yet.
-__device__ __forceinline__ uint32_t lc_lookup(uint64_t key, uint32_t b, const unsigned long long* tkeys,
-                                              const uint16_t* tids) {
-  const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(tkeys + 2 * b);
-  const bool h1 = kk.y == key;
-  const bool hit = (kk.x == key) | h1;
-  const uint32_t id = tids[2 * b + (h1 ? 1u : 0u)];
-  return hit ? id : static_cast<uint32_t>(LC_ID_UNSET);
+// One probe of the packed table at displacement `d`: LDS.64.  Returns the id, or a value >= LC_HE_OVF when this
+// slot does not hold the key (or its id is not published yet).
+__device__ __forceinline__ uint32_t lc_probe(uint64_t m, uint32_t d, uint32_t tab) {
+  const uint32_t slot = (static_cast<uint32_t>(m >> (64 - LC_HT_LOG2)) + d) & (LC_HT - 1);
+  const uint64_t en = lds64(tab + slot * 8u);
+  const uint64_t want = (m << LC_HT_LOG2) | (static_cast<uint64_t>(d) << 10);
+  return ((en ^ want) >> 10) == 0 ? (static_cast<uint32_t>(en) & 0x3FFu) : static_cast<uint32_t>(LC_ID_UNSET);
 }
 
 // Global id of a key that this CTA sees for the first time.  LC_NOID when more than gmax keys exist.
@@ -229,47 +244,59 @@ __device__ __noinline__ uint32_t lc_global_id(uint64_t key, LcDir d, uint32_t gm
   return LC_NOID;
 }
 
-// Hash-mode miss path (out of line, per-lane divergent code): probes on from the home bucket,
-// inserts on first sight.  LC_NOID on overflow.
-__device__ __noinline__ uint32_t lc_miss_resolve(uint64_t key, unsigned long long* tkeys, volatile uint16_t* tids,
-                                                 uint32_t* misc, LcDir d, uint32_t gmax, uint32_t* status) {
-  if (*reinterpret_cast<volatile uint32_t*>(misc + 1)) return LC_NOID;   // this CTA already gave up
-  uint32_t b = lc_bucket(key);
-  for (int probe = 0; probe < 4 * LC_NBUCKET; ++probe) {
-    const uint64_t k0 = *reinterpret_cast<volatile unsigned long long*>(tkeys + 2 * b);
-    const uint64_t k1 = *reinterpret_cast<volatile unsigned long long*>(tkeys + 2 * b + 1);
-    uint32_t slot;
-    if (k0 == key) slot = 2 * b;
-    else if (k1 == key) slot = 2 * b + 1;
-    else if (k0 == kEmptyKey || k1 == kEmptyKey) {
-      const uint32_t s = (k0 == kEmptyKey) ? 2 * b : 2 * b + 1;   // lowest empty slot of the bucket
-      const uint64_t old = atomicCAS(tkeys + s, static_cast<unsigned long long>(kEmptyKey),
-                                     static_cast<unsigned long long>(key));
-      if (old == kEmptyKey) {  // this lane inserted the key into the CTA's table: fetch its global id
-        const uint32_t gid = lc_global_id(key, d, gmax);
-        if (gid == LC_NOID) {
-          tids[s] = LC_ID_OVF;
-          misc[1] = 1u;
-          atomicExch(status + ST_OVERFLOW, 1u);
-          atomicExch(status + ST_ABORT, 1u);
-          return LC_NOID;
-        }
-        tids[s] = static_cast<uint16_t>(gid);
-        return gid;
-      }
-      if (old != key) continue;   // lost the slot to another key: look at the same bucket again
-      slot = s;
-    } else {
-      b = (b + 1) & (LC_NBUCKET - 1);
-      continue;
-    }
-    uint16_t id;
-    do { id = tids[slot]; } while (id == LC_ID_UNSET);   // inserter publishes the id right after its CAS
-    return id == LC_ID_OVF ? LC_NOID : id;
-  }
+__device__ __forceinline__ void lc_give_up(uint32_t* misc, uint32_t* status) {
   misc[1] = 1u;
   atomicExch(status + ST_OVERFLOW, 1u);
   atomicExch(status + ST_ABORT, 1u);
+}
+
+// Hash-mode miss path (out of line, per-lane divergent code): walks the key's probe sequence, inserts on first
+// sight (entry first, then the global id), falls back to the overflow list past LC_HT_MAXD.  LC_NOID on overflow.
+__device__ __noinline__ uint32_t lc_miss_resolve(uint64_t key, const LcCtx& c, LcDir dir, uint32_t gmax, uint32_t* status) {
+  if (*reinterpret_cast<volatile uint32_t*>(c.misc + 1)) return LC_NOID;   // this CTA already gave up
+  const uint64_t m = lc_mix(key);
+  const uint32_t home = static_cast<uint32_t>(m >> (64 - LC_HT_LOG2));
+  for (uint32_t d = 0; d <= LC_HT_MAXD; ++d) {
+    volatile unsigned long long* slot = c.tab_p + ((home + d) & (LC_HT - 1));
+    const uint64_t mine = (m << LC_HT_LOG2) | (static_cast<uint64_t>(d) << 10);
+    uint64_t en = *slot;
+    if (en == LC_HE_EMPTY) {
+      en = atomicCAS(const_cast<unsigned long long*>(slot), static_cast<unsigned long long>(LC_HE_EMPTY),
+                     static_cast<unsigned long long>(mine | LC_HE_PENDING));
+      if (en == LC_HE_EMPTY) {   // this lane inserted the key into the CTA's table: fetch its global id
+        const uint32_t gid = lc_global_id(key, dir, gmax);
+        *slot = mine | (gid == LC_NOID ? LC_HE_OVF : gid);
+        if (gid == LC_NOID) lc_give_up(c.misc, status);
+        return gid;
+      }
+    }
+    if (((en ^ mine) >> 10) == 0) {   // the key's own entry (possibly still pending)
+      uint32_t id = static_cast<uint32_t>(en) & 0x3FFu;
+      while (id == LC_HE_PENDING) id = static_cast<uint32_t>(*slot) & 0x3FFu;
+      return id == LC_HE_OVF ? LC_NOID : id;
+    }
+  }
+  // every slot of the probe window holds another key: overflow list (full keys, linear)
+  for (int i = 0; i < LC_OVF; ++i) {
+    volatile unsigned long long* ok = c.ovf_keys + i;
+    uint64_t k = *ok;
+    if (k == kEmptyKey) {
+      k = atomicCAS(const_cast<unsigned long long*>(ok), static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+      if (k == kEmptyKey) {
+        const uint32_t gid = lc_global_id(key, dir, gmax);
+        *reinterpret_cast<volatile uint32_t*>(c.ovf_ids + i) = gid == LC_NOID ? LC_ID_OVF : gid;
+        atomicMax(c.misc + 2, static_cast<uint32_t>(i + 1));
+        if (gid == LC_NOID) lc_give_up(c.misc, status);
+        return gid;
+      }
+    }
+    if (k == key) {
+      uint32_t id;
+      do { id = *reinterpret_cast<volatile uint32_t*>(c.ovf_ids + i); } while (id == LC_ID_UNSET);
+      return id == LC_ID_OVF ? LC_NOID : id;
+    }
+  }
+  lc_give_up(c.misc, status);   // pathological key set (everything hashes together): the global-table path takes over
   return LC_NOID;
 }
 
@@ -369,10 +396,29 @@ __device__ __noinline__ LcContrib<DSUM> lc_fold_general(LcContrib<DSUM> k, uint3
   return k;
 }
 
+// min / max / last row are order independent: CTA-shared arrays, plain pre-check, rare atomic
+template <int VC>
+__device__ __forceinline__ void lc_wide_update(uint32_t gid, uint64_t vbits, bool vv, uint32_t row, uint32_t agg_mask, const LcCtx& c) {
+  if (agg_mask & AGG_LAST) atomicMax(c.last_p + gid, row);
+  if (vv && (agg_mask & (AGG_MIN | AGG_MAX)) && !Wide<VC>::is_nan(vbits)) {
+    const uint64_t o = Wide<VC>::ord(vbits);
+    const uint4 m4 = lds128(c.mm + gid * 16u);
+    const uint64_t mn = static_cast<uint64_t>(m4.x) | (static_cast<uint64_t>(m4.y) << 32);
+    const uint64_t mx = static_cast<uint64_t>(m4.z) | (static_cast<uint64_t>(m4.w) << 32);
+    if (o < mn) atomicMin(c.mm_p + 2 * gid, static_cast<unsigned long long>(o));
+    if (o > mx) atomicMax(c.mm_p + 2 * gid + 1, static_cast<unsigned long long>(o));
+  }
+}
+
 // Accumulate one 32-row batch whose ids are known.  Warp-synchronous; lane L holds row `row`
 // (= batch row base + L).  CLEAN: every lane holds a row with a resolved id and a valid value.
 // `id` is the lane's accumulator SLOT (dense mode: group id << rlog | replica), `gid` the group id.
-template <int VC, bool WIDE, bool CLEAN, bool DENSE>
+// DET selects how lanes that hit the same slot in one batch find each other:
+//   0  claim tag: every lane stores its lane number into byte 3 of the slot's count word (STS.8) and reads the word
+//      back; one lane per slot reads its own number.  Counts are 24 bits per warp and slot.
+//   1  MATCH.ANY on the slot number: no shared-memory traffic for the detection, the lowest lane of every group
+//      folds its peers in ascending lane (= row) order.  Counts are 32 bits.
+template <int VC, bool WIDE, bool CLEAN, bool DENSE, int DET>
 __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row, uint32_t agg_mask,
                                               const LcCtx& c) {
   using Cfg = LcCfg<VC, WIDE>;
@@ -381,35 +427,64 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
   const bool live = CLEAN ? true : id != LC_NOID;
   const uint32_t ida = live ? id : 0u;
   const uint32_t cw_addr = c.cw + ida * 4u, sum_addr = c.sum + ida * 8u;
-  if (live) sts8(cw_addr + 3u, lane);
-  __syncwarp();
-  const uint32_t cw = lds32(cw_addr);
-  uint64_t s = lds64(sum_addr);
   const bool vv = CLEAN ? true : vvalid;
   const uint32_t gid = (DENSE && ida < static_cast<uint32_t>(Cfg::GMAX)) ? (ida >> c.rlog) : ida;
-  if constexpr (WIDE) {
-    // min / max / last row are order independent: CTA-shared arrays, plain pre-check, rare atomic
-    if (live) {
-      if (agg_mask & AGG_LAST) atomicMax(c.last_p + gid, row);
-      if (vv && (agg_mask & (AGG_MIN | AGG_MAX)) && !Wide<VC>::is_nan(vbits)) {
-        const uint64_t o = Wide<VC>::ord(vbits);
-        const uint4 m4 = lds128(c.mm + gid * 16u);
-        const uint64_t mn = static_cast<uint64_t>(m4.x) | (static_cast<uint64_t>(m4.y) << 32);
-        const uint64_t mx = static_cast<uint64_t>(m4.z) | (static_cast<uint64_t>(m4.w) << 32);
-        if (o < mn) atomicMin(c.mm_p + 2 * gid, static_cast<unsigned long long>(o));
-        if (o > mx) atomicMax(c.mm_p + 2 * gid + 1, static_cast<unsigned long long>(o));
-      }
-    }
-  }
-  const uint32_t tag = cw >> 24;
-  const bool winner = live && (tag == lane);
-  const uint32_t losers = __ballot_sync(FULL, live && !winner);
   LcContrib<Cfg::DSUM> k;
   k.sum = vv ? vbits : 0ull;
   k.cnt = vv ? 1u : 0u;
   k.lo = lane;
-  k.doer = winner;
   if constexpr (Cfg::DSUM) k.dsum = vv ? Wide<VC>::as_double(vbits) : 0.0;
+  if constexpr (DET == 1) {
+    // loads first (lanes of one group read the same words: a broadcast, no extra wavefronts), detection meanwhile
+    const uint32_t cw = lds32(cw_addr);
+    uint64_t s = lds64(sum_addr);
+    const uint32_t peers = __match_any_sync(FULL, live ? id : (0x80000000u | lane));
+    const uint32_t lanebit = 1u << lane;
+    const bool leader = (peers & (lanebit - 1u)) == 0;
+    if constexpr (WIDE) {
+      if (live) lc_wide_update<VC>(gid, vbits, vv, row, agg_mask, c);
+    }
+    if (__any_sync(FULL, !leader)) {
+      uint32_t rem = leader ? (peers & ~lanebit) : 0u;
+      while (__any_sync(FULL, rem != 0)) {
+        const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
+        const LcContrib<Cfg::DSUM> o = lc_shfl<VC, Cfg::DSUM>(k, src);
+        if (rem) {
+          lc_add<VC, Cfg::DSUM>(k, o);
+          rem &= rem - 1;
+        }
+      }
+    }
+    if (leader && live) {
+      const bool first_seen = cw == 0xFFFFFFFFu;   // first time this warp meets the slot
+      if constexpr (VC == VC_F) {
+        s = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(s)) +
+                                                       __longlong_as_double(static_cast<long long>(k.sum))));
+      } else {
+        s += k.sum;
+      }
+      sts64(sum_addr, s);
+      sts32(cw_addr, (first_seen ? 0u : cw) + k.cnt);
+      if constexpr (Cfg::DSUM) {
+        const uint32_t da = c.dsum + id * 8u;
+        sts64(da, static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(lds64(da))) + k.dsum)));
+      }
+      if (first_seen) atomicMin(c.cta_first + gid, row);   // the leader holds the group's lowest row of this batch
+    }
+    __syncwarp();
+    return;
+  } else {
+  if (live) sts8(cw_addr + 3u, lane);
+  __syncwarp();
+  const uint32_t cw = lds32(cw_addr);
+  uint64_t s = lds64(sum_addr);
+  if constexpr (WIDE) {
+    if (live) lc_wide_update<VC>(gid, vbits, vv, row, agg_mask, c);
+  }
+  const uint32_t tag = cw >> 24;
+  const bool winner = live && (tag == lane);
+  const uint32_t losers = __ballot_sync(FULL, live && !winner);
+  k.doer = winner;
   if (losers) {
     if ((losers & (losers - 1u)) == 0u) {
       // exactly one losing lane: its group has two members, a + b is commutative
@@ -474,6 +549,7 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
     if (first_seen) atomicMin(c.cta_first + gid, row + k.lo - lane);   // candidate for the CTA's first row
   }
   __syncwarp();
+  }
 }
 
 // One row group in registers: LC_NB batches of 32 rows, entry e = row g0 + 32 e + lane.
@@ -529,14 +605,12 @@ __device__ __forceinline__ void lc_load_generic(LcBuf& b, const LcArgs& a, int64
   }
 }
 
-// Process one row group: resolve the ids of all LC_NB batches first (independent lookups in flight,
-// one vote for the rare paths), then accumulate batch by batch.  Returns false on abort.
-// CLEAN: every row exists, keys and values are all valid.
+// One row group: resolve the ids of all LC_NB batches first (independent lookups in flight, one vote for the rare
+// paths; returns false on abort), then accumulate batch by batch.  CLEAN: every row exists, keys and values are valid.
 template <int VC, bool WIDE, bool DENSE, bool CLEAN>
-__device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uint32_t lane, const LcCtx& c, const LcArgs& a) {
+__device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[LC_NB], uint32_t lane, const LcCtx& c, const LcArgs& a) {
   using Cfg = LcCfg<VC, WIDE>;
   constexpr uint32_t FULL = 0xFFFFFFFFu;
-  uint32_t id[LC_NB];
   if constexpr (DENSE) {
     bool bad = false;
 #pragma unroll
@@ -558,56 +632,81 @@ __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uin
       return false;
     }
   } else {
+    // probe 0 of every batch (8 independent LDS.64 in flight), then the displaced keys: 12 % of the keys of a
+    // 1000-key set sit one slot further, 2.7 % two or three; new keys and the overflow list are out of line
     uint32_t missmask = 0;
 #pragma unroll
     for (int e = 0; e < LC_NB; ++e) {
       const bool act = CLEAN ? true : ((b.act >> e) & 1u) != 0;
       const bool kvalid = CLEAN ? true : ((b.kv >> e) & 1u) != 0;
       const bool special = !kvalid || b.key[e] == kEmptyKey;
-      id[e] = lc_lookup(b.key[e], lc_bucket(b.key[e]), c.tkeys, c.tids);
-      if (special) id[e] = kvalid ? Cfg::ID_EMPTYKEY : Cfg::ID_NULL;
+      id[e] = lc_probe(lc_mix(b.key[e]), 0u, c.tab);
+      if (special) id[e] = kvalid ? Cfg::GMAX_H + 1 : Cfg::GMAX_H;
       if (!act) id[e] = LC_NOID;
-      if (act && !special && id[e] >= LC_ID_OVF) missmask |= 1u << e;
+      if (act && !special && id[e] >= LC_HE_OVF) missmask |= 1u << e;
     }
     if (__any_sync(FULL, missmask != 0)) {
-      // keys displaced from a full home bucket (a fixed ~1.5 % of the keys at 1000 groups): one
-      // more inline probe of the neighbouring bucket, per batch and only for the lanes that missed
 #pragma unroll
       for (int e = 0; e < LC_NB; ++e) {
-        const bool m = (missmask >> e) & 1u;
-        if (__any_sync(FULL, m)) {
-          if (m) {   // up to three more buckets inline; longer chains (and new keys) take the slow path
-            const uint32_t hb = lc_bucket(b.key[e]);
-#pragma unroll 1
-            for (uint32_t p = 1; p <= 3; ++p) {
-              const uint32_t id2 = lc_lookup(b.key[e], (hb + p) & (LC_NBUCKET - 1), c.tkeys, c.tids);
-              if (id2 < LC_ID_OVF) { id[e] = id2; missmask &= ~(1u << e); break; }
-            }
-          }
+        if ((missmask >> e) & 1u) {
+          const uint32_t id2 = lc_probe(lc_mix(b.key[e]), 1u, c.tab);
+          if (id2 < LC_HE_OVF) { id[e] = id2; missmask &= ~(1u << e); }
         }
       }
-      if (__any_sync(FULL, missmask != 0)) {   // new keys (start of the pass) or longer probe chains
+      if (__any_sync(FULL, missmask != 0)) {
 #pragma unroll
         for (int e = 0; e < LC_NB; ++e) {
-          if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c.tkeys, c.tids, c.misc, a.dir, Cfg::GMAX, a.status);
+          const bool m = (missmask >> e) & 1u;
+          if (__any_sync(FULL, m)) {
+            if (m) {
+#pragma unroll 1
+              for (uint32_t d = 2; d <= LC_HT_MAXD; ++d) {
+                const uint32_t id2 = lc_probe(lc_mix(b.key[e]), d, c.tab);
+                if (id2 < LC_HE_OVF) { id[e] = id2; missmask &= ~(1u << e); break; }
+              }
+              if ((missmask >> e) & 1u) {   // overflow list (published entries only), else the slow path
+                const uint32_t novf = *reinterpret_cast<volatile uint32_t*>(c.misc + 2);
+                for (uint32_t i = 0; i < novf; ++i) {
+                  if (*reinterpret_cast<volatile unsigned long long*>(c.ovf_keys + i) == b.key[e]) {
+                    const uint32_t oid = *reinterpret_cast<volatile uint32_t*>(c.ovf_ids + i);
+                    if (oid < LC_ID_OVF) { id[e] = oid; missmask &= ~(1u << e); }
+                    break;
+                  }
+                }
+              }
+              if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c, a.dir, Cfg::GMAX_H, a.status);
+            }
+          }
         }
         __syncwarp();
       }
     }
   }
+  return true;
+}
+
+template <int VC, bool WIDE, bool DENSE, bool CLEAN, int DET>
+__device__ __forceinline__ void lc_accumulate_group(const LcBuf& b, const uint32_t (&id)[LC_NB], int64_t g0, uint32_t lane,
+                                                    const LcCtx& c, const LcArgs& a) {
 #pragma unroll
   for (int e = 0; e < LC_NB; ++e) {
     const uint32_t row = static_cast<uint32_t>(g0) + e * 32 + lane;
     constexpr bool ACLEAN = CLEAN && DENSE;   // (hash mode may leave LC_NOID in a lane after an overflow)
     const bool vvalid = CLEAN ? true : ((b.vv >> e) & 1u) != 0;
-    lc_accumulate<VC, WIDE, ACLEAN, DENSE>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, a.agg_mask, c);
+    lc_accumulate<VC, WIDE, ACLEAN, DENSE, DET>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, a.agg_mask, c);
   }
+}
+
+template <int VC, bool WIDE, bool DENSE, bool CLEAN, int DET>
+__device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uint32_t lane, const LcCtx& c, const LcArgs& a) {
+  uint32_t id[LC_NB];
+  if (!lc_resolve_group<VC, WIDE, DENSE, CLEAN>(b, id, lane, c, a)) return false;
+  lc_accumulate_group<VC, WIDE, DENSE, CLEAN, DET>(b, id, g0, lane, c, a);
   return true;
 }
 
-template <int VC, bool WIDE, bool FAST, bool DENSE>
+template <int VC, bool WIDE, bool FAST, bool DENSE, int DET>
 __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, int warp, uint32_t lane) {
-  using Cfg = LcCfg<VC, WIDE>;
   if (warp >= c.nwarps) return;
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * c.nwarps + warp;
   const int64_t nw = static_cast<int64_t>(gridDim.x) * c.nwarps;
@@ -621,9 +720,19 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
     if (g < n_full) lc_load_fast(cur, a, g * LC_GROUP_ROWS, lane);
     while (g < n_full) {
       const int64_t gn = g + nw;
-      if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane);
       const uint32_t gabort = *abort_global;
-      if (!lc_process_group<VC, WIDE, DENSE, true>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
+      if constexpr (DENSE) {
+        if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane);
+        if (!lc_process_group<VC, WIDE, DENSE, true, DET>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
+      } else {
+        // hash mode: the keys stay live through the probe rounds, so the next row group is requested after them
+        // (its 4 KB per warp then travel during the 8 accumulate batches) — at 128 registers per thread the
+        // prefetch buffer would otherwise spill to local memory, which shares the LSU with shared memory
+        uint32_t id[LC_NB];
+        if (!lc_resolve_group<VC, WIDE, DENSE, true>(cur, id, lane, c, a)) return;
+        if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane);
+        lc_accumulate_group<VC, WIDE, DENSE, true, DET>(cur, id, g * LC_GROUP_ROWS, lane, c, a);
+      }
       if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
       cur = nxt;
       g = gn;
@@ -632,7 +741,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
     if (n_groups > n_full && gw == (n_full % nw)) {
       LcBuf t;
       lc_load_generic<VC>(t, a, n_full * LC_GROUP_ROWS, lane);
-      lc_process_group<VC, WIDE, DENSE, false>(t, n_full * LC_GROUP_ROWS, lane, c, a);
+      lc_process_group<VC, WIDE, DENSE, false, DET>(t, n_full * LC_GROUP_ROWS, lane, c, a);
     }
   } else {
     LcBuf cur, nxt;
@@ -642,7 +751,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
       const int64_t gn = g + nw;
       if (gn < n_groups) lc_load_generic<VC>(nxt, a, gn * LC_GROUP_ROWS, lane);
       const uint32_t gabort = *abort_global;
-      if (!lc_process_group<VC, WIDE, DENSE, false>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
+      if (!lc_process_group<VC, WIDE, DENSE, false, DET>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
       if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
       cur = nxt;
       g = gn;
@@ -652,19 +761,25 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
 
 // FAST: int64/uint64 keys and 8-byte values, no validity bitmaps, 8-byte aligned columns.
 // DENSEK: the dense-mode kernel (16 warps, no key table; when the key sample says the keys are not dense it
-// returns at once with ST_DENSE_MISS = 2 and the host launches the hash-mode kernel: 12 warps + key table).
-template <int VC, bool WIDE, bool FAST, bool DENSEK>
-__global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, WIDE>::WARPS_HASH) * 32, 1) k_lowcard_scan(LcArgs a) {
+// returns at once with ST_DENSE_MISS = 2 and the host launches the hash-mode kernel: packed key table + as many
+// warps as fit beside it, 16 for the narrow aggregate set).  DET: duplicate detection (lc_accumulate).
+template <int VC, bool WIDE, bool FAST, bool DENSEK, int DET>
+__global__ void __launch_bounds__(LcSmem<VC, WIDE, !DENSEK>::WARPS * 32, 1) k_lowcard_scan(LcArgs a) {
   using Cfg = LcCfg<VC, WIDE>;
-  using L = LcSmem<VC, WIDE>;
-  constexpr int THREADS = (DENSEK ? Cfg::WARPS : Cfg::WARPS_HASH) * 32;
+  using L = LcSmem<VC, WIDE, !DENSEK>;
+  constexpr int THREADS = L::WARPS * 32;
+  constexpr int GPK = static_cast<int>(L::GP);          // ids of this kernel's accumulator arrays
+  constexpr int GMAXK = GPK - 2;
+  constexpr uint32_t CNT_UNSEEN = DET == 1 ? 0xFFFFFFFFu : LC_CNT_MASK;
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
   LcCtx c;
   c.misc = reinterpret_cast<uint32_t*>(smem + L::OFF_MISC);
-  c.tkeys = reinterpret_cast<unsigned long long*>(smem + L::OFF_TKEYS);
-  c.tids = reinterpret_cast<uint16_t*>(smem + L::OFF_TIDS);
+  c.tab_p = reinterpret_cast<unsigned long long*>(smem + L::OFF_TAB);
+  c.tab = smem_u32(c.tab_p);
+  c.ovf_keys = reinterpret_cast<unsigned long long*>(smem + L::OFF_OVFK);
+  c.ovf_ids = reinterpret_cast<uint32_t*>(smem + L::OFF_OVFI);
   c.cta_first = reinterpret_cast<uint32_t*>(smem + L::OFF_FIRST);
   const bool dense = lc_dense_mode(a.dir.prep, DENSEK ? 0 : 1, Cfg::GMAX, &c.base, &c.window, &c.rlog);
   if (DENSEK && !dense) {   // not a dense key set: hand over to the hash-mode kernel
@@ -674,10 +789,9 @@ __global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, W
   // lane-private replicas (32 per id) of the narrow layout are conflict free and 12 warps already saturate HBM
   // (2.99 against 3.05 ms at 16 groups); everything else wants all 16 warps (wide set: 3.6 against 4.2 ms at 16
   // groups, 4.4 against 5.3 ms at 64; narrow 64 groups: 3.3 against 3.7 ms)
-  const int nwarps = DENSEK ? ((!WIDE && c.rlog >= 5) ? 12 : Cfg::WARPS) : Cfg::WARPS_HASH;
+  const int nwarps = DENSEK ? ((!WIDE && c.rlog >= 5) ? 12 : L::WARPS) : L::WARPS;
   c.nwarps = nwarps;
-  const size_t off_acc = DENSEK ? L::OFF_ACC_DENSE : L::OFF_ACC_HASH;
-  unsigned char* my_acc = smem + off_acc + L::ACC_PER_WARP * (warp < nwarps ? warp : 0);
+  unsigned char* my_acc = smem + L::OFF_ACC + L::ACC_PER_WARP * (warp < nwarps ? warp : 0);
   const uint32_t acc_s = smem_u32(my_acc);
   c.sum = acc_s + static_cast<uint32_t>(L::W_SUM);
   c.dsum = acc_s + static_cast<uint32_t>(L::W_DSUM);
@@ -693,12 +807,10 @@ __global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, W
 
   // ---- init shared state ----
   if constexpr (!DENSEK) {
-    for (int i = threadIdx.x; i < LC_TCAP; i += THREADS) {
-      c.tkeys[i] = kEmptyKey;
-      c.tids[i] = LC_ID_UNSET;
-    }
+    for (int i = threadIdx.x; i < LC_HT; i += THREADS) c.tab_p[i] = LC_HE_EMPTY;
+    if (threadIdx.x < LC_OVF) { c.ovf_keys[threadIdx.x] = kEmptyKey; c.ovf_ids[threadIdx.x] = LC_ID_UNSET; }
   }
-  for (int i = threadIdx.x; i < Cfg::GP; i += THREADS) {
+  for (int i = threadIdx.x; i < GPK; i += THREADS) {
     c.cta_first[i] = kNoRow;
     if constexpr (WIDE) {
       c.mm_p[2 * i] = kMinInit;
@@ -708,15 +820,15 @@ __global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, W
   }
   if (threadIdx.x < 4) c.misc[threadIdx.x] = 0;
   if (warp < nwarps) {
-    for (int i = lane; i < Cfg::GP; i += 32) {
+    for (int i = lane; i < GPK; i += 32) {
       reinterpret_cast<uint64_t*>(my_acc + L::W_SUM)[i] = 0ull;
-      reinterpret_cast<uint32_t*>(my_acc + L::W_CW)[i] = LC_CNT_MASK;
+      reinterpret_cast<uint32_t*>(my_acc + L::W_CW)[i] = CNT_UNSEEN;
       if constexpr (Cfg::DSUM) reinterpret_cast<double*>(my_acc + L::W_DSUM)[i] = 0.0;
     }
   }
   __syncthreads();
 
-  lc_scan_rows<VC, WIDE, FAST, DENSEK>(a, c, warp, lane);
+  lc_scan_rows<VC, WIDE, FAST, DENSEK, DET>(a, c, warp, lane);
   __syncthreads();
   if (c.misc[1]) {
     if (threadIdx.x == 0) atomicExch(a.status + ST_ABORT, 1u);
@@ -724,21 +836,25 @@ __global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, W
   }
 
   // ---- fold the warps (and, in dense mode, the replicas) in a fixed order and write this CTA's partial table ----
+  // (partial tables are always Cfg::GP ids wide; the hash-mode kernel's two special ids move to the end)
   const size_t pbase = static_cast<size_t>(blockIdx.x) * Cfg::GP;
   const uint32_t nrep = 1u << c.rlog;
   for (int id = threadIdx.x; id < Cfg::GP; id += THREADS) {
+    const bool regular = id < Cfg::GMAX;
+    const int kid = regular ? id : id - Cfg::GMAX + GMAXK;      // this kernel's slot number of partial-table id `id`
+    const bool present = regular ? id < GMAXK : true;
     uint64_t sum = 0;
     double fsum = 0.0, dsum = 0.0;
     uint32_t cnt = 0;
-    const bool regular = id < Cfg::GMAX;
     const uint32_t reps = regular ? nrep : 1u;
-    if (!regular || static_cast<uint32_t>(id) < c.window) {
+    if (present && (!regular || static_cast<uint32_t>(id) < c.window)) {
       for (int w = 0; w < nwarps; ++w) {
-        const unsigned char* wa = smem + off_acc + L::ACC_PER_WARP * w;
+        const unsigned char* wa = smem + L::OFF_ACC + L::ACC_PER_WARP * w;
         for (uint32_t r = 0; r < reps; ++r) {
-          const uint32_t slot = regular ? ((static_cast<uint32_t>(id) << c.rlog) | r) : static_cast<uint32_t>(id);
-          const uint32_t cw = reinterpret_cast<const uint32_t*>(wa + L::W_CW)[slot] & LC_CNT_MASK;
-          if (cw == LC_CNT_MASK) continue;
+          const uint32_t slot = regular ? ((static_cast<uint32_t>(kid) << c.rlog) | r) : static_cast<uint32_t>(kid);
+          uint32_t cw = reinterpret_cast<const uint32_t*>(wa + L::W_CW)[slot];
+          if constexpr (DET != 1) cw &= LC_CNT_MASK;
+          if (cw == CNT_UNSEEN) continue;
           cnt += cw;
           const uint64_t s = reinterpret_cast<const uint64_t*>(wa + L::W_SUM)[slot];
           if constexpr (VC == VC_F) fsum += __longlong_as_double(static_cast<long long>(s));
@@ -750,11 +866,11 @@ __global__ void __launch_bounds__((DENSEK ? LcCfg<VC, WIDE>::WARPS : LcCfg<VC, W
     if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(fsum));
     a.p_sum[pbase + id] = sum;
     a.p_count[pbase + id] = cnt;
-    a.p_first[pbase + id] = c.cta_first[id];
+    a.p_first[pbase + id] = present ? c.cta_first[kid] : kNoRow;
     if constexpr (WIDE) {
-      a.p_last[pbase + id] = c.last_p[id];
-      a.p_min[pbase + id] = c.mm_p[2 * id];
-      a.p_max[pbase + id] = c.mm_p[2 * id + 1];
+      a.p_last[pbase + id] = present ? c.last_p[kid] : 0u;
+      a.p_min[pbase + id] = present ? c.mm_p[2 * kid] : kMinInit;
+      a.p_max[pbase + id] = present ? c.mm_p[2 * kid + 1] : kMaxInit;
       if constexpr (Cfg::DSUM) a.p_dsum[pbase + id] = dsum;
     }
   }

@@ -53,7 +53,20 @@ static void check_column(const pd::ArrayPtr& a, bool floating) {
     auto mm = s.min_max(skip);
     REQUIRE(same(mm.first, host("min", a, skip)) && same(mm.second, host("max", a, skip)));
     REQUIRE(same(s.mean(skip), host("mean", a, skip), 1e-12));
-    REQUIRE(same(s.sum_on_device(skip), host("sum", a, skip), floating ? 1e-12 : 0.0));
+    REQUIRE(same(s.sum(skip), host("sum", a, skip), floating ? 1e-12 : 0.0));
+    REQUIRE(same(s.agg("sum", skip), host("sum", a, skip), floating ? 1e-12 : 0.0));
+    // NDFrame::first / last (ndframe.cpp:129,160): arrow's scalar kernels, which skip nulls unless told not to
+    REQUIRE(same(s.first(skip), host("first", a, skip)));
+    REQUIRE(same(s.last(skip), host("last", a, skip)));
+    REQUIRE(same(s.agg("max", skip), host("max", a, skip)));
+  }
+  {
+    // DataFrame::sum (ndframe.cpp:220 over the concatenated columns): two copies of the column
+    auto rb = arrow::RecordBatch::Make(arrow::schema({arrow::field("a", a->type()), arrow::field("b", a->type())}), a->length(), {a, a});
+    pd::DataFrame df(rb);
+    auto chunked = std::make_shared<arrow::ChunkedArray>(arrow::ArrayVector{a, a});
+    auto want = pd::ReturnOrThrowOnFailure(ac::CallFunction("sum", {chunked})).scalar();
+    REQUIRE(same(df.sum(), want, floating ? 1e-12 : 0.0));
   }
   REQUIRE(s.count() == std::static_pointer_cast<arrow::Int64Scalar>(pd::ReturnOrThrowOnFailure(ac::CallFunction("count", {a})).scalar())->value);
 }
@@ -74,6 +87,12 @@ int main() {
     check_column(make<arrow::Int64Builder>(std::vector<int64_t>{}), false);                      // empty: null / 0
     check_column(make<arrow::DoubleBuilder>(std::vector<double>{1.0, 2.0}, {false, false}), true); // all null
     check_column(make<arrow::DoubleBuilder>(std::vector<double>{3.5}), true);
+    {   // nulls at both ends: first / last must skip them (skip_null) or return them (positional)
+      std::vector<bool> ends(10007, true);
+      for (int i = 0; i < 40; ++i) { ends[i] = false; ends[10006 - i] = false; }
+      check_column(make<arrow::DoubleBuilder>(dv, ends), true);
+      check_column(make<arrow::Int32Builder>(iv, ends), false);
+    }
   } catch (std::exception const& e) {
     std::printf("EXCEPTION: %s\n", e.what());
     return 2;
