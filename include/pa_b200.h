@@ -128,9 +128,7 @@ typedef struct pa_options {
   int64_t row_base;          /* global row number of local row 0 (multi-GPU row-range shards) */
   int64_t lowcard_no_dense;  /* 1 = the shared-memory path never uses dense (key - base) addressing, always hashes */
   int64_t no_partition;      /* 1 = never reorder the rows by table region before a global-table scan (>= 2 M groups) */
-  int64_t lowcard_detect;    /* shared-memory path, lanes of a 32-row batch that hit one group: 0 = default (MATCH.ANY),
-                                1 = claim tags in the count words (the round-1 scheme; kept for A/B measurements) */
-  int64_t reserved[1];
+  int64_t reserved[2];
 } pa_options;
 
 typedef struct pa_groupby pa_groupby;      /* opaque: key columns + device group table */
@@ -240,6 +238,17 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
                        int64_t freq_ns, int32_t closed_right, int32_t label_right, int32_t origin,
                        int64_t origin_custom_ns, int64_t offset_ns, const pa_options* opt,
                        pa_groupby** out);
+
+/* DataFrame::downsample (dataframe.cpp:1265-1290): groups on the per-row label
+ * arrow::compute::FloorTemporal / CeilTemporal(index, RoundTemporalOptions(multiple, unit, week_starts_monday,
+ * ceil_is_strictly_greater = false, calendar_based_origin)) — computed on the device, bit-identical to arrow's
+ * kernels without a time zone — minus one day for W / M / Q / Y, exactly as the reference does.  `unit` is the
+ * reference's rule letter: N U L S T H D W M Q Y.  `index` is a timestamp column (any resolution for the fixed
+ * units, [ns] for W / M / Q / Y; may be unsorted; null timestamps form the null-key group).  The returned handle is
+ * an ordinary pa_groupby whose unique key is the label column. */
+int pa_downsample_create(const struct ArrowDeviceArray* index, const struct ArrowSchema* index_schema, int32_t multiple,
+                         char unit, int32_t closed_label_right, int32_t week_starts_monday, int32_t calendar_based_origin,
+                         const pa_options* opt, pa_groupby** out);
 
 /* ---- multi-GPU: row-range shards, hash-partitioned partial aggregates, merge ----
  * The reference has no multi-device path.  Each rank aggregates its shard (pa_options.row_base =

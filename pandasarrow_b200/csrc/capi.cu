@@ -26,6 +26,9 @@
 #include "stage2.cuh"
 #include "groupings.cuh"
 #include "distinct.cuh"
+#include "temporal.cuh"
+#include "order.cuh"
+#include "csort.cuh"
 
 using namespace pa;
 
@@ -283,12 +286,12 @@ struct pa_groupby {
   float stage_ms[4] = {0, 0, 0, 0};
   cudaEvent_t ev[10] = {};                // [6..7]: groupings build, [8..9]: last grouped take
   // group materialisation (groupings.cuh), built on first use; keys are immutable so it never goes stale
-  DevBuf grp_order, grp_offsets;
+  DevBuf grp_order, grp_offsets, grp_dest;
   bool have_groupings = false;
   // Scratch of the global-table / resample passes, kept between calls on the handle: returning multi-GB blocks to
   // the stream-ordered pool and asking for them again fragments it (cudaMallocAsync then takes 50-1700 ms per call
   // at 100 M groups); a repeated aggregate on the same handle reuses these without touching the allocator.
-  struct Scratch { DevBuf table, p_keys, p_vals, p_rows, p_counts, krange, c_first, c_slot, s_first, s_slot, cub_tmp, bnd; } scr;
+  struct Scratch { DevBuf table, p_keys, p_vals, p_rows, p_counts, krange, c_first, c_slot, s_first, s_slot, cub_tmp, bnd, bitmap, prefix8, tile_sums; } scr;
 };
 
 namespace {
@@ -334,7 +337,7 @@ enum LcOutcome { LC_DONE = 0, LC_DENSE_MISS = 1, LC_OVERFLOW = 2 };
 
 bool lc_is_wide(uint32_t mask, int vc) { return is_wide(mask, vc); }
 
-template <int VC, bool WIDE, int DET>
+template <int VC, bool WIDE>
 int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast, bool hash_kernel) {
   using Cfg = LcCfg<VC, WIDE>;
   cudaStream_t st = g->stream;
@@ -342,12 +345,12 @@ int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, 
   CUDA_TRY(cudaGetLastError());
   if (hash_kernel) {
     using L = LcSmem<VC, WIDE, true>;
-    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, false, DET> : k_lowcard_scan<VC, WIDE, false, false, DET>;
+    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, false> : k_lowcard_scan<VC, WIDE, false, false>;
     CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL)));
     scan<<<grid, L::WARPS * 32, L::TOTAL, st>>>(a);
   } else {
     using L = LcSmem<VC, WIDE, false>;
-    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, true, DET> : k_lowcard_scan<VC, WIDE, false, true, DET>;
+    auto scan = fast ? k_lowcard_scan<VC, WIDE, true, true> : k_lowcard_scan<VC, WIDE, false, true>;
     CUDA_TRY(cudaFuncSetAttribute(scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::TOTAL)));
     scan<<<grid, L::WARPS * 32, L::TOTAL, st>>>(a);
   }
@@ -359,13 +362,6 @@ int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, 
   CUDA_TRY(cudaGetLastError());
   g->last_launches += 4;
   return PA_OK;
-}
-
-template <int VC, bool WIDE>
-int launch_lowcard_d(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, bool fast, bool hash_kernel) {
-  // duplicate detection inside a 32-row batch: MATCH.ANY (default) or the round-1 claim tags (pa_options.lowcard_detect = 1)
-  if (g->opt.lowcard_detect == 1) return launch_lowcard_t<VC, WIDE, 0>(g, a, m, grid, fast, hash_kernel);
-  return launch_lowcard_t<VC, WIDE, 1>(g, a, m, grid, fast, hash_kernel);
 }
 
 int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool force_hash, LcOutcome* outcome,
@@ -440,13 +436,13 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   m.status = a.status;
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
   if (kwide) {
-    if (vc == VC_F) PA_TRY((launch_lowcard_d<VC_F, true>(g, a, m, grid, fast, force_hash)));
-    else if (vc == VC_I) PA_TRY((launch_lowcard_d<VC_I, true>(g, a, m, grid, fast, force_hash)));
-    else PA_TRY((launch_lowcard_d<VC_U, true>(g, a, m, grid, fast, force_hash)));
+    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, true>(g, a, m, grid, fast, force_hash)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, true>(g, a, m, grid, fast, force_hash)));
+    else PA_TRY((launch_lowcard_t<VC_U, true>(g, a, m, grid, fast, force_hash)));
   } else {
-    if (vc == VC_F) PA_TRY((launch_lowcard_d<VC_F, false>(g, a, m, grid, fast, force_hash)));
-    else if (vc == VC_I) PA_TRY((launch_lowcard_d<VC_I, false>(g, a, m, grid, fast, force_hash)));
-    else PA_TRY((launch_lowcard_d<VC_U, false>(g, a, m, grid, fast, force_hash)));
+    if (vc == VC_F) PA_TRY((launch_lowcard_t<VC_F, false>(g, a, m, grid, fast, force_hash)));
+    else if (vc == VC_I) PA_TRY((launch_lowcard_t<VC_I, false>(g, a, m, grid, fast, force_hash)));
+    else PA_TRY((launch_lowcard_t<VC_U, false>(g, a, m, grid, fast, force_hash)));
   }
   CUDA_TRY(cudaEventRecord(g->ev[3], st));
   if (deferred) {   // the scratch buffers above are released in stream order; the status is read by finish_pending()
@@ -463,6 +459,39 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   g->last_mode = static_cast<int>(h_status[ST_MODE]);
   g->last_rlog = static_cast<int>(h_status[ST_RLOG]);
   if (h_status[ST_DENSE_MISS] != 2u) g->last_passes += 1;   // (2 = the dense kernel declined before scanning a row)
+  return PA_OK;
+}
+
+// Orders G compacted (first_row, slot) pairs by first row WITHOUT a sort (order.cuh): rank query on a bitmap of the
+// first rows.  Writes the slots in first-appearance order to `s_slot`.
+int order_by_first_row(pa_groupby* g, const uint32_t* c_first, const uint32_t* c_slot, uint32_t G, uint32_t* s_slot) {
+  if (G == 0) return PA_OK;
+  cudaStream_t st = g->stream;
+  const uint64_t n_rows = static_cast<uint64_t>(std::max<int64_t>(g->n, 1));
+  const uint64_t nblocks = (n_rows + 32ull * BM_BLOCK_WORDS - 1) / (32ull * BM_BLOCK_WORDS);
+  const uint64_t nwords = nblocks * BM_BLOCK_WORDS;
+  const uint32_t ntiles = static_cast<uint32_t>((nblocks + SC_TILE - 1) / SC_TILE);
+  PA_TRY(g->scr.bitmap.alloc(nwords * 4, st));
+  PA_TRY(g->scr.prefix8.alloc(nblocks * 4, st));
+  PA_TRY(g->scr.tile_sums.alloc(static_cast<size_t>(ntiles) * 4, st));
+  uint32_t* bitmap = g->scr.bitmap.as<uint32_t>();
+  uint32_t* prefix8 = g->scr.prefix8.as<uint32_t>();
+  uint32_t* tile_sums = g->scr.tile_sums.as<uint32_t>();
+  CUDA_TRY(cudaMemsetAsync(bitmap, 0, nwords * 4, st));
+  k_bm_set<<<(G + 255) / 256, 256, 0, st>>>(c_first, G, bitmap);
+  CUDA_TRY(cudaGetLastError());
+  const int cgrid = static_cast<int>(std::min<uint64_t>((nblocks + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+  k_bm_count8<<<cgrid, 256, 0, st>>>(bitmap, nblocks, prefix8);
+  CUDA_TRY(cudaGetLastError());
+  k_scan_tiles<<<ntiles, 256, 0, st>>>(prefix8, nblocks, tile_sums);
+  CUDA_TRY(cudaGetLastError());
+  k_scan_sums<<<1, 256, 0, st>>>(tile_sums, ntiles);
+  CUDA_TRY(cudaGetLastError());
+  k_scan_apply<<<ntiles, 256, 0, st>>>(prefix8, nblocks, tile_sums);
+  CUDA_TRY(cudaGetLastError());
+  k_bm_rank<<<(G + 255) / 256, 256, 0, st>>>(c_first, c_slot, G, bitmap, prefix8, s_slot);
+  CUDA_TRY(cudaGetLastError());
+  g->last_launches += 6;
   return PA_OK;
 }
 
@@ -582,7 +611,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   // compact occupied slots, order them by first row, gather
   const uint64_t nslots = cap + 2;
   const uint64_t max_groups = std::min<uint64_t>(nslots, static_cast<uint64_t>(g->n) + 2);
-  DevBuf &c_first = g->scr.c_first, &c_slot = g->scr.c_slot, &s_first = g->scr.s_first, &s_slot = g->scr.s_slot, &cub_tmp = g->scr.cub_tmp;
+  DevBuf &c_first = g->scr.c_first, &c_slot = g->scr.c_slot, &s_slot = g->scr.s_slot;
   PA_TRY(c_first.alloc(max_groups * 4, st));
   PA_TRY(c_slot.alloc(max_groups * 4, st));
   const int cgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
@@ -595,14 +624,8 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   g->G = G;
   PA_TRY(alloc_result(g, G, WIDE, VC != VC_F));
   if (G > 0) {
-    PA_TRY(s_first.alloc(static_cast<size_t>(G) * 4, st));
     PA_TRY(s_slot.alloc(static_cast<size_t>(G) * 4, st));
-    size_t tmp_bytes = 0;
-    // ordering G (first_row, slot) pairs is bookkeeping, not one of the three hot stages: CUB's
-    // radix sort (library code) is used for it and counted as such in DESIGN.md.
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
-    PA_TRY(cub_tmp.alloc(tmp_bytes, st));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
+    PA_TRY(order_by_first_row(g, c_first.as<uint32_t>(), c_slot.as<uint32_t>(), G, s_slot.as<uint32_t>()));
     k_gtable_gather<WIDE><<<(G + 255) / 256, 256, 0, st>>>(table.as<SlotT>(), cap, s_slot.as<uint32_t>(), G, g->res);
     CUDA_TRY(cudaGetLastError());
     g->last_launches += 1;
@@ -1028,6 +1051,9 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask, bool deferre
     // (an earlier pass on this handle may already have told us how many groups there are)
     const int64_t known_groups = g->opt.expected_groups > 0 ? g->opt.expected_groups : (g->have_groups ? static_cast<int64_t>(g->G) : 0);
     bool try_low = g->opt.path != PA_PATH_GLOBAL && (known_groups <= gmax + 2 || g->opt.path == PA_PATH_LOWCARD);
+    // the per-warp count words of the shared-memory path hold 24 bits next to the claim tag (lowcard.cuh): with
+    // 148 SMs x >= 12 warps a warp sees at most 2^32 / 1776 = 2.4 M rows; a small MIG slice must not overflow them
+    if (g->n / (static_cast<int64_t>(g->num_sms) * 12) >= (1ll << 24) - 1) try_low = false;
     bool done = false;
     if (start_at == 2) try_low = false;                       // (resuming after a deferred pass overflowed)
     if (try_low && deferred && start_at == 0 && !g->opt.lowcard_no_dense) {
@@ -1177,7 +1203,7 @@ int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
   }
   // occupied buckets -> first-appearance (= time) order -> GroupResult
   const uint64_t max_groups = std::min<uint64_t>(nslots, static_cast<uint64_t>(g->n) + 2);
-  DevBuf &c_first = g->scr.c_first, &c_slot = g->scr.c_slot, &s_first = g->scr.s_first, &s_slot = g->scr.s_slot, &cub_tmp = g->scr.cub_tmp;
+  DevBuf &c_first = g->scr.c_first, &c_slot = g->scr.c_slot, &s_slot = g->scr.s_slot;
   PA_TRY(c_first.alloc(max_groups * 4, st));
   PA_TRY(c_slot.alloc(max_groups * 4, st));
   const int cgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
@@ -1192,12 +1218,8 @@ int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
   g->G = G;
   PA_TRY(alloc_result(g, G, WIDE, VC != VC_F));
   if (G > 0) {
-    PA_TRY(s_first.alloc(static_cast<size_t>(G) * 4, st));
     PA_TRY(s_slot.alloc(static_cast<size_t>(G) * 4, st));
-    size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
-    PA_TRY(cub_tmp.alloc(tmp_bytes, st));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, c_first.as<uint32_t>(), s_first.as<uint32_t>(), c_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 32, st));
+    PA_TRY(order_by_first_row(g, c_first.as<uint32_t>(), c_slot.as<uint32_t>(), G, s_slot.as<uint32_t>()));
     k_gtable_gather<WIDE><<<(G + 255) / 256, 256, 0, st>>>(table.as<SlotT>(), static_cast<uint64_t>(nbins), s_slot.as<uint32_t>(), G, g->res);
     CUDA_TRY(cudaGetLastError());
     g->last_launches += 1;
@@ -1524,7 +1546,22 @@ int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema
 }
 
 namespace {
-// ids -> stable sort by id -> (order, offsets), cached on the handle
+// device-wide exclusive scan of a uint32 array in place (order.cuh)
+int scan_u32(pa_groupby* g, uint32_t* data, uint64_t n, DevBuf* tile_sums) {
+  cudaStream_t st = g->stream;
+  const uint32_t ntiles = static_cast<uint32_t>((n + SC_TILE - 1) / SC_TILE);
+  PA_TRY(tile_sums->alloc(static_cast<size_t>(std::max<uint32_t>(ntiles, 1)) * 4, st));
+  if (n == 0) return PA_OK;
+  k_scan_tiles<<<ntiles, 256, 0, st>>>(data, n, tile_sums->as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  k_scan_sums<<<1, 256, 0, st>>>(tile_sums->as<uint32_t>(), ntiles);
+  CUDA_TRY(cudaGetLastError());
+  k_scan_apply<<<ntiles, 256, 0, st>>>(data, n, tile_sums->as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;
+}
+
+// ids -> stable counting sort by id (csort.cuh) -> (order, dest, offsets), cached on the handle
 int ensure_groupings(pa_groupby* g) {
   if (g->have_groupings) return PA_OK;
   if (g->merged) return set_err(PA_ERR_STATE, "groupings exist on the rank that holds the rows, not on a merged handle");
@@ -1535,36 +1572,70 @@ int ensure_groupings(pa_groupby* g) {
   CUDA_TRY(cudaEventRecord(g->ev[6], st));
   RowLookup lk;
   PA_TRY(build_row_lookup(g, &lk));
-  DevBuf ids, sorted_ids, iota, tmp;
-  const size_t nb = static_cast<size_t>(std::max<int64_t>(n, 1)) * 4;
-  PA_TRY(ids.alloc(nb, st));
-  PA_TRY(sorted_ids.alloc(nb, st));
-  PA_TRY(iota.alloc(nb, st));
-  PA_TRY(g->grp_order.alloc(nb, st));
+  DevBuf ids, keys_a, keys_b, pay_a, pay_b, counts, tile_sums;
+  const size_t nb4 = static_cast<size_t>(std::max<int64_t>(n, 1)) * 4;
+  PA_TRY(ids.alloc(nb4, st));
+  PA_TRY(g->grp_order.alloc(nb4, st));
+  PA_TRY(g->grp_dest.alloc(nb4, st));
   PA_TRY(g->grp_offsets.alloc((static_cast<size_t>(G) + 1) * 4, st));
   if (n > 0) {
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
     lk.a.out = ids.as<uint32_t>();
     k_rowid_scan<<<grid, 256, 0, st>>>(lk.a);
     CUDA_TRY(cudaGetLastError());
-    k_iota_u32<<<grid, 256, 0, st>>>(iota.as<uint32_t>(), n);
-    CUDA_TRY(cudaGetLastError());
     int bits = 1;
     while (bits < 32 && (1ull << bits) < static_cast<uint64_t>(G)) ++bits;
-    size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ids.as<uint32_t>(), sorted_ids.as<uint32_t>(), iota.as<uint32_t>(),
-                                             g->grp_order.as<uint32_t>(), static_cast<int>(n), 0, bits, st));
-    PA_TRY(tmp.alloc(tmp_bytes, st));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, ids.as<uint32_t>(), sorted_ids.as<uint32_t>(), iota.as<uint32_t>(),
-                                             g->grp_order.as<uint32_t>(), static_cast<int>(n), 0, bits, st));
-    k_group_offsets<<<grid, 256, 0, st>>>(sorted_ids.as<uint32_t>(), n, G, g->grp_offsets.as<int32_t>());
-    CUDA_TRY(cudaGetLastError());
+    const int passes = (bits + CS_BITS - 1) / CS_BITS;
+    const int64_t ntiles = (n + CS_TILE - 1) / CS_TILE;
+    const int nb = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, static_cast<int64_t>(g->num_sms) * 4)));
+    const int64_t chunk = ((ntiles + nb - 1) / nb) * CS_TILE;
+    PA_TRY(counts.alloc(sizeof(uint32_t) * CS_R * static_cast<size_t>(nb), st));
+    if (passes > 1) {   // ping-pong buffers; the last pass writes its payload to grp_order and the sorted ids to keys_a / keys_b
+      PA_TRY(keys_a.alloc(nb4, st));
+      PA_TRY(pay_a.alloc(nb4, st));
+      PA_TRY(keys_b.alloc(nb4, st));
+      if (passes > 2) PA_TRY(pay_b.alloc(nb4, st));
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      CUDA_TRY(cudaFuncSetAttribute(k_cs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CS_SMEM)));
+      attr_set = true;
+    }
+    const uint32_t* in_keys = ids.as<uint32_t>();
+    const uint32_t* in_pay = nullptr;
+    for (int p = 0; p < passes; ++p) {
+      const bool last = p == passes - 1;
+      CsArgs a{};
+      a.keys = in_keys; a.payload = in_pay; a.n = n; a.shift = p * CS_BITS; a.nb = nb; a.chunk = chunk;
+      a.counts = counts.as<uint32_t>();
+      DevBuf& ok = (p % 2 == 0) ? keys_a : keys_b;
+      DevBuf& op = (p % 2 == 0) ? pay_a : pay_b;
+      a.out_keys = last ? (passes > 1 ? ok.as<uint32_t>() : nullptr) : ok.as<uint32_t>();
+      a.out_payload = last ? g->grp_order.as<uint32_t>() : op.as<uint32_t>();
+      a.out_dest = last ? g->grp_dest.as<uint32_t>() : nullptr;
+      k_cs_hist<<<nb, CS_THREADS, 0, st>>>(a);
+      CUDA_TRY(cudaGetLastError());
+      PA_TRY(scan_u32(g, counts.as<uint32_t>(), static_cast<uint64_t>(CS_R) * nb, &tile_sums));
+      k_cs_scatter<<<nb, CS_THREADS, CS_SMEM, st>>>(a);
+      CUDA_TRY(cudaGetLastError());
+      if (last) {
+        if (passes == 1) {
+          k_cs_offsets<<<(G + 1 + 255) / 256, 256, 0, st>>>(counts.as<uint32_t>(), nb, G, n, g->grp_offsets.as<int32_t>());
+        } else {
+          k_group_offsets<<<grid, 256, 0, st>>>(a.out_keys, n, G, g->grp_offsets.as<int32_t>());
+        }
+        CUDA_TRY(cudaGetLastError());
+      }
+      in_keys = a.out_keys;
+      in_pay = a.out_payload;
+    }
   } else {
     CUDA_TRY(cudaMemsetAsync(g->grp_offsets.p, 0, (static_cast<size_t>(G) + 1) * 4, st));
   }
   CUDA_TRY(cudaEventRecord(g->ev[7], st));
   CUDA_TRY(cudaEventRecord(g->ev[8], st));
   CUDA_TRY(cudaEventRecord(g->ev[9], st));
+  CUDA_TRY(cudaStreamSynchronize(st));   // the sort buffers above are released here
   g->have_groupings = true;
   return PA_OK;
 }
@@ -1593,24 +1664,47 @@ int pa_groupby_take_grouped(pa_groupby* g, const struct ArrowDeviceArray* column
   PA_TRY(load_column(column, schema, st, g->device, &col));
   if (col.n != g->n) return set_err(PA_ERR_INVALID, "column has %lld rows, keys have %lld", (long long)col.n, (long long)g->n);
   if (schema->dictionary) return set_err(PA_ERR_INVALID, "dictionary-encoded columns: gather the indices, keep the dictionary");
-  if (col.is_bool) return set_err(PA_ERR_INVALID, "boolean columns are not gathered on the device (bit-packed); use the row order of pa_groupby_groupings");
-  DevBuf vals, valid;
   const int64_t n = g->n;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+  const size_t words = (static_cast<size_t>(n) + 31) / 32 + 1;
+  DevBuf vals, valid;
+  if (col.is_bool) {
+    // bit-packed values: gathered bit by bit from the packed input (load_column keeps it in own_bits for host
+    // inputs; device inputs are read in place)
+    const ArrowArray& arr = column->array;
+    const uint8_t* bits = col.own_bits.p ? col.own_bits.as<uint8_t>() : static_cast<const uint8_t*>(arr.buffers[1]);
+    const int64_t boff = col.own_bits.p ? arr.offset % 8 : arr.offset;
+    PA_TRY(vals.alloc(words * 4, st));
+    if (col.valid) PA_TRY(valid.alloc(words * 4, st));
+    if (n > 0) {
+      CUDA_TRY(cudaEventRecord(g->ev[8], st));
+      k_take_bits<<<grid, 256, 0, st>>>(bits, boff, g->grp_order.as<uint32_t>(), n, vals.as<uint32_t>());
+      CUDA_TRY(cudaGetLastError());
+      if (col.valid) {
+        k_take_bits<<<grid, 256, 0, st>>>(col.valid, col.bit_off, g->grp_order.as<uint32_t>(), n, valid.as<uint32_t>());
+        CUDA_TRY(cudaGetLastError());
+      }
+      CUDA_TRY(cudaEventRecord(g->ev[9], st));
+    }
+    return export_host(st, "b", 1, static_cast<uint32_t>(n), vals.p, col.valid ? valid.as<uint32_t>() : nullptr, out, out_schema);
+  }
   PA_TRY(vals.alloc(static_cast<size_t>(std::max<int64_t>(n, 1)) * col.width, st));
-  if (col.valid) PA_TRY(valid.alloc((static_cast<size_t>(n) + 31) / 32 * 4 + 4, st));
+  if (col.valid) {
+    PA_TRY(valid.alloc(words * 4, st));
+    CUDA_TRY(cudaMemsetAsync(valid.p, 0, words * 4, st));
+  }
   if (n > 0) {
-    TakeArgs a{};
+    TakeScatterArgs a{};
     a.col = col.data;
     a.valid = col.valid;
     a.bit_off = col.bit_off;
     a.width = col.width;
-    a.order = g->grp_order.as<uint32_t>();
+    a.dest = g->grp_dest.as<uint32_t>();
     a.n = n;
     a.out = vals.p;
     a.out_valid = col.valid ? valid.as<uint32_t>() : nullptr;
-    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
     CUDA_TRY(cudaEventRecord(g->ev[8], st));
-    k_take_grouped<<<grid, 256, 0, st>>>(a);
+    k_take_scatter<<<grid, 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(g->ev[9], st));
   }
@@ -1772,6 +1866,65 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
     g->rs.nbins = (last - first) / freq_ns;
     if (g->n < g->rs.nbins) return set_err(PA_ERR_NOT_IMPLEMENTED, "upSampling is not implemented.");  // resample.h:102-105
   }
+  *out = g.release();
+  return PA_OK;
+}
+
+// DataFrame::downsample (/root/reference/src/dataframe.cpp:1265-1290): per-row label = Floor/CeilTemporal(index)
+// computed on the device (temporal.cuh), then the ordinary hash group-by on the labels.
+int pa_downsample_create(const struct ArrowDeviceArray* index, const struct ArrowSchema* index_schema, int32_t multiple,
+                         char unit, int32_t closed_label_right, int32_t week_starts_monday, int32_t calendar_based_origin,
+                         const pa_options* opt, pa_groupby** out) {
+  if (!index || !index_schema || !out) return set_err(PA_ERR_INVALID, "pa_downsample_create: null argument");
+  if (multiple < 1) return set_err(PA_ERR_INVALID, "Invalid time offset: multiple must be >= 1");
+  const char* units = "NULSTHDWMQY";
+  if (!unit || !strchr(units, unit)) return set_err(PA_ERR_INVALID, "Invalid time offset unit '%c'", unit ? unit : '?');
+  const char* f = index_schema->format;
+  if (!f || f[0] != 't' || f[1] != 's') return set_err(PA_ERR_INVALID, "axis must be a TimestampArray but got array of type '%s'", f ? f : "?");
+  HandlePtr g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  cudaStream_t st = g->stream;
+  Column ix;
+  PA_TRY(load_column(index, index_schema, st, g->device, &ix));
+  int64_t tps = 1000000000LL;
+  switch (f[2]) {
+    case 's': tps = 1; break;
+    case 'm': tps = 1000; break;
+    case 'u': tps = 1000000; break;
+    default: break;
+  }
+  const bool calendar = unit == 'W' || unit == 'M' || unit == 'Q' || unit == 'Y';
+  // the reference's W / M / Q / Y branch subtracts one day and re-types the labels as timestamp[ns]
+  // (dataframe.cpp:1279-1287); other resolutions would change meaning there
+  if (calendar && tps != 1000000000LL) return set_err(PA_ERR_NOT_IMPLEMENTED, "downsample by W / M / Q / Y needs a timestamp[ns] index");
+  TemporalSpec spec{};
+  spec.multiple = multiple;
+  spec.unit = unit;
+  spec.ceil = closed_label_right ? 1 : 0;
+  spec.week_starts_monday = week_starts_monday ? 1 : 0;
+  spec.calendar_origin = calendar_based_origin ? 1 : 0;
+  spec.ticks_per_sec = tps;
+  spec.post_shift = calendar ? -86400LL * tps : 0;
+  g->keys.resize(1);
+  Column& k = g->keys[0];
+  k.format = calendar ? "tsn:" : f;
+  k.width = 8; k.vc = VC_I; k.n = ix.n;
+  PA_TRY(k.own_data.alloc(static_cast<size_t>(std::max<int64_t>(ix.n, 1)) * 8, st));
+  if (ix.n > 0) {
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((ix.n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+    k_temporal_labels<<<grid, 256, 0, st>>>(static_cast<const int64_t*>(ix.data), ix.valid, ix.bit_off, ix.n, spec, k.own_data.as<int64_t>());
+    CUDA_TRY(cudaGetLastError());
+  }
+  k.data = k.own_data.p;
+  if (ix.valid) {   // null timestamps stay null labels: their own group, like any null key
+    if (ix.own_valid.p) k.own_valid = std::move(ix.own_valid);
+    k.valid = ix.valid;
+    k.bit_off = ix.bit_off;
+  }
+  g->n = ix.n;
+  if (g->n >= 0xFFFFFFFEll) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-2 rows per call; shard by row range");
+  PA_TRY(setup_keys(g.get()));
+  CUDA_TRY(cudaStreamSynchronize(st));   // `ix` may own the device copy of a host index
   *out = g.release();
   return PA_OK;
 }

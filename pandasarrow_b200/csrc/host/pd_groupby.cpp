@@ -122,37 +122,13 @@ Resampler Series::resample(std::string const& rule, bool closed_right, bool labe
 }
 
 Resampler DataFrame::downsample(std::string const& rule, bool closed_label_right, bool weekStartsMonday, bool startEpoch) const {
-  // dataframe.cpp:1265-1290: per-row label = Floor/CeilTemporal(index) — the same Arrow call as the
-  // reference (a host-side element-wise relabel; moving it onto the GPU is SURVEY §8f-3) — then the
-  // GPU hash group-by on the labels.
-  namespace ac = arrow::compute;
-  static const bool init = [] { return ac::Initialize().ok(); }();
-  (void)init;
+  // dataframe.cpp:1265-1290: per-row label = Floor/CeilTemporal(index, RoundTemporalOptions(value, unit,
+  // weekStartsMonday, false, startEpoch)), minus one day for W / M / Q / Y — computed on the device
+  // (pa_downsample_create, csrc/temporal.cuh), then the GPU hash group-by on the labels.
   const auto [unit, value] = splitTimeSpan(rule);
-  ac::CalendarUnit cu;
-  switch (unit.empty() ? ' ' : unit[0]) {
-    case 'N': cu = ac::CalendarUnit::NANOSECOND; break;
-    case 'U': cu = ac::CalendarUnit::MICROSECOND; break;
-    case 'L': cu = ac::CalendarUnit::MILLISECOND; break;
-    case 'S': cu = ac::CalendarUnit::SECOND; break;
-    case 'T': cu = ac::CalendarUnit::MINUTE; break;
-    case 'H': cu = ac::CalendarUnit::HOUR; break;
-    case 'D': cu = ac::CalendarUnit::DAY; break;
-    case 'W': cu = ac::CalendarUnit::WEEK; break;
-    case 'M': cu = ac::CalendarUnit::MONTH; break;
-    case 'Q': cu = ac::CalendarUnit::QUARTER; break;
-    case 'Y': cu = ac::CalendarUnit::YEAR; break;
-    default: throw std::runtime_error("Invalid time offset " + rule);
-  }
-  ac::RoundTemporalOptions opt(value, cu, weekStartsMonday, false, startEpoch);
-  auto binned = ReturnOrThrowOnFailure(closed_label_right ? ac::CeilTemporal(m_index, opt) : ac::FloorTemporal(m_index, opt)).make_array();
-  if ((!unit.empty() && unit.back() == 'E') || unit == "M" || unit == "W" || unit == "Y" || unit == "Q") {
-    auto one_day = arrow::MakeScalar(arrow::date32(), 1L).MoveValueUnsafe();
-    auto d = ReturnOrThrowOnFailure(ac::Subtract(binned, one_day));
-    d = ReturnOrThrowOnFailure(ac::Cast(d, arrow::int64()));
-    binned = ReturnOrThrowOnFailure(ac::Cast(d, arrow::timestamp(arrow::TimeUnit::NANO))).make_array();
-  }
-  return Resampler(DataFrame(m_array, binned));
+  const char u = unit.empty() ? ' ' : unit[0];
+  if (std::string("NULSTHDWMQY").find(u) == std::string::npos) throw std::runtime_error("Invalid time offset " + rule);
+  return Resampler(*this, Resampler::DownsampleRule{value, u, closed_label_right, weekStartsMonday, startEpoch});
 }
 
 // ------------------------------ GroupBy ------------------------------
@@ -565,6 +541,18 @@ Resampler::Resampler(DataFrame const& _df, int64_t freq_ns, bool closed_right, b
   if (pa_resample_create(&k.dev, &k.schema, freq_ns, closed_right, label_right, origin_code(origin.type), origin.custom_ns,
                          offset_ns, &opt, &handle) != PA_OK)
     throw_pa("resample");
+}
+
+Resampler::Resampler(DataFrame const& _df, DownsampleRule const& rule) {
+  df = _df;
+  key_array = df.indexArray();
+  if (!key_array) throw std::runtime_error("frame has no index");
+  Exported k(*key_array);
+  pa_options opt;
+  pa_options_init(&opt);
+  if (pa_downsample_create(&k.dev, &k.schema, rule.multiple, rule.unit, rule.closed_label_right, rule.week_starts_monday,
+                           rule.calendar_based_origin, &opt, &handle) != PA_OK)
+    throw_pa("downsample");
 }
 
 arrow::Result<DataFrame> Resampler::frameOfAll(std::string const& name) {

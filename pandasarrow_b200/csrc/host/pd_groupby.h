@@ -159,7 +159,7 @@ class DataFrame {
   Resampler resample(std::string const& rule, bool closed_right = false, bool label_right = false,
                      TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0),
                      std::string const& tz = "") const;
-  // dataframe.cpp:1265-1290 (fixed-width units N U L S T H D; calendar units are a "next" row)
+  // dataframe.cpp:1265-1290: every unit of the reference (N U L S T H D W M Q Y), labels computed on the device
   Resampler downsample(std::string const& rule, bool closed_label_right = true, bool weekStartsMonday = true,
                        bool startEpoch = true) const;
 
@@ -274,6 +274,9 @@ class Resampler : protected GroupBy {
   // time-bucket specialisation: sorted index + fixed width (pd::resample)
   Resampler(DataFrame const& _df, int64_t freq_ns, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
             int64_t offset_ns);
+  // DataFrame::downsample (dataframe.cpp:1265-1290): groups on Floor/CeilTemporal(index) labels made on the device
+  struct DownsampleRule { int multiple; char unit; bool closed_label_right, week_starts_monday, calendar_based_origin; };
+  Resampler(DataFrame const& _df, DownsampleRule const& rule);
   ArrayPtr index() const { return this->unique(); }
   const DataFrame& data() const { return this->getDF(); }
 #define PD_RESAMPLE_FN(name) \

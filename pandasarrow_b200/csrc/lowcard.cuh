@@ -413,12 +413,11 @@ __device__ __forceinline__ void lc_wide_update(uint32_t gid, uint64_t vbits, boo
 // Accumulate one 32-row batch whose ids are known.  Warp-synchronous; lane L holds row `row`
 // (= batch row base + L).  CLEAN: every lane holds a row with a resolved id and a valid value.
 // `id` is the lane's accumulator SLOT (dense mode: group id << rlog | replica), `gid` the group id.
-// DET selects how lanes that hit the same slot in one batch find each other:
-//   0  claim tag: every lane stores its lane number into byte 3 of the slot's count word (STS.8) and reads the word
-//      back; one lane per slot reads its own number.  Counts are 24 bits per warp and slot.
-//   1  MATCH.ANY on the slot number: no shared-memory traffic for the detection, the lowest lane of every group
-//      folds its peers in ascending lane (= row) order.  Counts are 32 bits.
-template <int VC, bool WIDE, bool CLEAN, bool DENSE, int DET>
+// Lanes that hit the same slot in one batch find each other through a claim tag: every lane stores its lane number
+// into byte 3 of the slot's count word (STS.8) and reads the word back; one lane per slot reads its own number.
+// (Measured alternative, scripts/ubench/lc_variants.cu: MATCH.ANY on the slot number needs no shared-memory traffic
+// but issues at ~1 per 40 cycles per SM on sm_100a — 3.64 ms against 1.70 ms per 512 M rows — so the tags stay.)
+template <int VC, bool WIDE, bool CLEAN, bool DENSE>
 __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool vvalid, uint32_t row, uint32_t agg_mask,
                                               const LcCtx& c) {
   using Cfg = LcCfg<VC, WIDE>;
@@ -434,46 +433,6 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
   k.cnt = vv ? 1u : 0u;
   k.lo = lane;
   if constexpr (Cfg::DSUM) k.dsum = vv ? Wide<VC>::as_double(vbits) : 0.0;
-  if constexpr (DET == 1) {
-    // loads first (lanes of one group read the same words: a broadcast, no extra wavefronts), detection meanwhile
-    const uint32_t cw = lds32(cw_addr);
-    uint64_t s = lds64(sum_addr);
-    const uint32_t peers = __match_any_sync(FULL, live ? id : (0x80000000u | lane));
-    const uint32_t lanebit = 1u << lane;
-    const bool leader = (peers & (lanebit - 1u)) == 0;
-    if constexpr (WIDE) {
-      if (live) lc_wide_update<VC>(gid, vbits, vv, row, agg_mask, c);
-    }
-    if (__any_sync(FULL, !leader)) {
-      uint32_t rem = leader ? (peers & ~lanebit) : 0u;
-      while (__any_sync(FULL, rem != 0)) {
-        const int src = rem ? (__ffs(rem) - 1) : static_cast<int>(lane);
-        const LcContrib<Cfg::DSUM> o = lc_shfl<VC, Cfg::DSUM>(k, src);
-        if (rem) {
-          lc_add<VC, Cfg::DSUM>(k, o);
-          rem &= rem - 1;
-        }
-      }
-    }
-    if (leader && live) {
-      const bool first_seen = cw == 0xFFFFFFFFu;   // first time this warp meets the slot
-      if constexpr (VC == VC_F) {
-        s = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(s)) +
-                                                       __longlong_as_double(static_cast<long long>(k.sum))));
-      } else {
-        s += k.sum;
-      }
-      sts64(sum_addr, s);
-      sts32(cw_addr, (first_seen ? 0u : cw) + k.cnt);
-      if constexpr (Cfg::DSUM) {
-        const uint32_t da = c.dsum + id * 8u;
-        sts64(da, static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(lds64(da))) + k.dsum)));
-      }
-      if (first_seen) atomicMin(c.cta_first + gid, row);   // the leader holds the group's lowest row of this batch
-    }
-    __syncwarp();
-    return;
-  } else {
   if (live) sts8(cw_addr + 3u, lane);
   __syncwarp();
   const uint32_t cw = lds32(cw_addr);
@@ -549,7 +508,6 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
     if (first_seen) atomicMin(c.cta_first + gid, row + k.lo - lane);   // candidate for the CTA's first row
   }
   __syncwarp();
-  }
 }
 
 // One row group in registers: LC_NB batches of 32 rows, entry e = row g0 + 32 e + lane.
@@ -632,51 +590,53 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
       return false;
     }
   } else {
-    // probe 0 of every batch (8 independent LDS.64 in flight), then the displaced keys: 12 % of the keys of a
-    // 1000-key set sit one slot further, 2.7 % two or three; new keys and the overflow list are out of line
+    // probe 0 of every batch (8 independent LDS.64 in flight), then — lanes that missed only — the displaced keys:
+    // of a 1000-key set 9.4 % sit one slot past home, 2.0 % two, 0.5 % three, 0.2 % in the overflow list.  All four
+    // rounds are straight-line predicated code (nearly every 256-row group has a lane in every round; a loop with
+    // votes per batch measured 8.8 ms per 1 B rows against 6.4 ms for round 1's bucket table); only keys that
+    // are not in the table yet leave it for the out-of-line insert.
+    uint64_t mix[LC_NB];
     uint32_t missmask = 0;
 #pragma unroll
     for (int e = 0; e < LC_NB; ++e) {
       const bool act = CLEAN ? true : ((b.act >> e) & 1u) != 0;
       const bool kvalid = CLEAN ? true : ((b.kv >> e) & 1u) != 0;
       const bool special = !kvalid || b.key[e] == kEmptyKey;
-      id[e] = lc_probe(lc_mix(b.key[e]), 0u, c.tab);
+      mix[e] = lc_mix(b.key[e]);
+      id[e] = lc_probe(mix[e], 0u, c.tab);
       if (special) id[e] = kvalid ? Cfg::GMAX_H + 1 : Cfg::GMAX_H;
       if (!act) id[e] = LC_NOID;
       if (act && !special && id[e] >= LC_HE_OVF) missmask |= 1u << e;
     }
-    if (__any_sync(FULL, missmask != 0)) {
+#pragma unroll
+    for (uint32_t d = 1; d <= LC_HT_MAXD; ++d) {
 #pragma unroll
       for (int e = 0; e < LC_NB; ++e) {
         if ((missmask >> e) & 1u) {
-          const uint32_t id2 = lc_probe(lc_mix(b.key[e]), 1u, c.tab);
+          const uint32_t id2 = lc_probe(mix[e], d, c.tab);
           if (id2 < LC_HE_OVF) { id[e] = id2; missmask &= ~(1u << e); }
+        }
+      }
+    }
+    if (__any_sync(FULL, missmask != 0)) {
+      // overflow list (published entries), then the insert path
+      const uint32_t novf = *reinterpret_cast<volatile uint32_t*>(c.misc + 2);
+#pragma unroll
+      for (int e = 0; e < LC_NB; ++e) {
+        if ((missmask >> e) & 1u) {
+          for (uint32_t i = 0; i < novf; ++i) {
+            if (lds64(smem_u32(c.ovf_keys + i)) == b.key[e]) {
+              const uint32_t oid = *reinterpret_cast<volatile uint32_t*>(c.ovf_ids + i);
+              if (oid < LC_ID_OVF) { id[e] = oid; missmask &= ~(1u << e); }
+              break;
+            }
+          }
         }
       }
       if (__any_sync(FULL, missmask != 0)) {
 #pragma unroll
         for (int e = 0; e < LC_NB; ++e) {
-          const bool m = (missmask >> e) & 1u;
-          if (__any_sync(FULL, m)) {
-            if (m) {
-#pragma unroll 1
-              for (uint32_t d = 2; d <= LC_HT_MAXD; ++d) {
-                const uint32_t id2 = lc_probe(lc_mix(b.key[e]), d, c.tab);
-                if (id2 < LC_HE_OVF) { id[e] = id2; missmask &= ~(1u << e); break; }
-              }
-              if ((missmask >> e) & 1u) {   // overflow list (published entries only), else the slow path
-                const uint32_t novf = *reinterpret_cast<volatile uint32_t*>(c.misc + 2);
-                for (uint32_t i = 0; i < novf; ++i) {
-                  if (*reinterpret_cast<volatile unsigned long long*>(c.ovf_keys + i) == b.key[e]) {
-                    const uint32_t oid = *reinterpret_cast<volatile uint32_t*>(c.ovf_ids + i);
-                    if (oid < LC_ID_OVF) { id[e] = oid; missmask &= ~(1u << e); }
-                    break;
-                  }
-                }
-              }
-              if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c, a.dir, Cfg::GMAX_H, a.status);
-            }
-          }
+          if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c, a.dir, Cfg::GMAX_H, a.status);
         }
         __syncwarp();
       }
@@ -685,7 +645,7 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
   return true;
 }
 
-template <int VC, bool WIDE, bool DENSE, bool CLEAN, int DET>
+template <int VC, bool WIDE, bool DENSE, bool CLEAN>
 __device__ __forceinline__ void lc_accumulate_group(const LcBuf& b, const uint32_t (&id)[LC_NB], int64_t g0, uint32_t lane,
                                                     const LcCtx& c, const LcArgs& a) {
 #pragma unroll
@@ -693,19 +653,19 @@ __device__ __forceinline__ void lc_accumulate_group(const LcBuf& b, const uint32
     const uint32_t row = static_cast<uint32_t>(g0) + e * 32 + lane;
     constexpr bool ACLEAN = CLEAN && DENSE;   // (hash mode may leave LC_NOID in a lane after an overflow)
     const bool vvalid = CLEAN ? true : ((b.vv >> e) & 1u) != 0;
-    lc_accumulate<VC, WIDE, ACLEAN, DENSE, DET>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, a.agg_mask, c);
+    lc_accumulate<VC, WIDE, ACLEAN, DENSE>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, a.agg_mask, c);
   }
 }
 
-template <int VC, bool WIDE, bool DENSE, bool CLEAN, int DET>
+template <int VC, bool WIDE, bool DENSE, bool CLEAN>
 __device__ __forceinline__ bool lc_process_group(const LcBuf& b, int64_t g0, uint32_t lane, const LcCtx& c, const LcArgs& a) {
   uint32_t id[LC_NB];
   if (!lc_resolve_group<VC, WIDE, DENSE, CLEAN>(b, id, lane, c, a)) return false;
-  lc_accumulate_group<VC, WIDE, DENSE, CLEAN, DET>(b, id, g0, lane, c, a);
+  lc_accumulate_group<VC, WIDE, DENSE, CLEAN>(b, id, g0, lane, c, a);
   return true;
 }
 
-template <int VC, bool WIDE, bool FAST, bool DENSE, int DET>
+template <int VC, bool WIDE, bool FAST, bool DENSE>
 __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, int warp, uint32_t lane) {
   if (warp >= c.nwarps) return;
   const int64_t gw = static_cast<int64_t>(blockIdx.x) * c.nwarps + warp;
@@ -723,7 +683,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
       const uint32_t gabort = *abort_global;
       if constexpr (DENSE) {
         if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane);
-        if (!lc_process_group<VC, WIDE, DENSE, true, DET>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
+        if (!lc_process_group<VC, WIDE, DENSE, true>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
       } else {
         // hash mode: the keys stay live through the probe rounds, so the next row group is requested after them
         // (its 4 KB per warp then travel during the 8 accumulate batches) — at 128 registers per thread the
@@ -731,7 +691,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
         uint32_t id[LC_NB];
         if (!lc_resolve_group<VC, WIDE, DENSE, true>(cur, id, lane, c, a)) return;
         if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane);
-        lc_accumulate_group<VC, WIDE, DENSE, true, DET>(cur, id, g * LC_GROUP_ROWS, lane, c, a);
+        lc_accumulate_group<VC, WIDE, DENSE, true>(cur, id, g * LC_GROUP_ROWS, lane, c, a);
       }
       if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
       cur = nxt;
@@ -741,7 +701,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
     if (n_groups > n_full && gw == (n_full % nw)) {
       LcBuf t;
       lc_load_generic<VC>(t, a, n_full * LC_GROUP_ROWS, lane);
-      lc_process_group<VC, WIDE, DENSE, false, DET>(t, n_full * LC_GROUP_ROWS, lane, c, a);
+      lc_process_group<VC, WIDE, DENSE, false>(t, n_full * LC_GROUP_ROWS, lane, c, a);
     }
   } else {
     LcBuf cur, nxt;
@@ -751,7 +711,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
       const int64_t gn = g + nw;
       if (gn < n_groups) lc_load_generic<VC>(nxt, a, gn * LC_GROUP_ROWS, lane);
       const uint32_t gabort = *abort_global;
-      if (!lc_process_group<VC, WIDE, DENSE, false, DET>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
+      if (!lc_process_group<VC, WIDE, DENSE, false>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
       if (__any_sync(0xFFFFFFFFu, (*abort_local | gabort) != 0)) return;
       cur = nxt;
       g = gn;
@@ -762,15 +722,15 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
 // FAST: int64/uint64 keys and 8-byte values, no validity bitmaps, 8-byte aligned columns.
 // DENSEK: the dense-mode kernel (16 warps, no key table; when the key sample says the keys are not dense it
 // returns at once with ST_DENSE_MISS = 2 and the host launches the hash-mode kernel: packed key table + as many
-// warps as fit beside it, 16 for the narrow aggregate set).  DET: duplicate detection (lc_accumulate).
-template <int VC, bool WIDE, bool FAST, bool DENSEK, int DET>
+// warps as fit beside it, 16 for the narrow aggregate set).
+template <int VC, bool WIDE, bool FAST, bool DENSEK>
 __global__ void __launch_bounds__(LcSmem<VC, WIDE, !DENSEK>::WARPS * 32, 1) k_lowcard_scan(LcArgs a) {
   using Cfg = LcCfg<VC, WIDE>;
   using L = LcSmem<VC, WIDE, !DENSEK>;
   constexpr int THREADS = L::WARPS * 32;
   constexpr int GPK = static_cast<int>(L::GP);          // ids of this kernel's accumulator arrays
   constexpr int GMAXK = GPK - 2;
-  constexpr uint32_t CNT_UNSEEN = DET == 1 ? 0xFFFFFFFFu : LC_CNT_MASK;
+  constexpr uint32_t CNT_UNSEEN = LC_CNT_MASK;
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -828,7 +788,7 @@ __global__ void __launch_bounds__(LcSmem<VC, WIDE, !DENSEK>::WARPS * 32, 1) k_lo
   }
   __syncthreads();
 
-  lc_scan_rows<VC, WIDE, FAST, DENSEK, DET>(a, c, warp, lane);
+  lc_scan_rows<VC, WIDE, FAST, DENSEK>(a, c, warp, lane);
   __syncthreads();
   if (c.misc[1]) {
     if (threadIdx.x == 0) atomicExch(a.status + ST_ABORT, 1u);
@@ -853,7 +813,7 @@ __global__ void __launch_bounds__(LcSmem<VC, WIDE, !DENSEK>::WARPS * 32, 1) k_lo
         for (uint32_t r = 0; r < reps; ++r) {
           const uint32_t slot = regular ? ((static_cast<uint32_t>(kid) << c.rlog) | r) : static_cast<uint32_t>(kid);
           uint32_t cw = reinterpret_cast<const uint32_t*>(wa + L::W_CW)[slot];
-          if constexpr (DET != 1) cw &= LC_CNT_MASK;
+          cw &= LC_CNT_MASK;
           if (cw == CNT_UNSEEN) continue;
           cnt += cw;
           const uint64_t s = reinterpret_cast<const uint64_t*>(wa + L::W_SUM)[slot];

@@ -110,7 +110,7 @@ def _import(out_a, out_s) -> pa.Array:
 
 
 def _options(expected_groups=0, path="auto", device=None, stream=None, row_base=0, no_dense=False,
-             no_partition=False, detect=0) -> PaOptions:
+             no_partition=False) -> PaOptions:
     o = PaOptions()
     _lib.load().pa_options_init(C.byref(o))
     o.expected_groups = int(expected_groups)
@@ -118,7 +118,6 @@ def _options(expected_groups=0, path="auto", device=None, stream=None, row_base=
     o.path = _PATHS[path]
     o.lowcard_no_dense = 1 if no_dense else 0
     o.no_partition = 1 if no_partition else 0
-    o.lowcard_detect = int(detect)
     if device is not None:
         o.device = int(device)
     if stream is not None:
@@ -138,7 +137,7 @@ class GroupBy:
 
     def __init__(self, key, frame=None, *, key_arrays: Optional[Sequence[Column]] = None, expected_groups: int = 0,
                  path: str = "auto", device: Optional[int] = None, stream: Optional[int] = None, row_base: int = 0,
-                 no_dense: bool = False, no_partition: bool = False, detect: int = 0, _handle=None):
+                 no_dense: bool = False, no_partition: bool = False, _handle=None):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self._frame = self._as_dict(frame)
@@ -157,7 +156,7 @@ class GroupBy:
         key_arrays = [self._normalise_key(k) for k in key_arrays]
         args, devs, schemas = _pack_args(key_arrays)
         self._key_args = args          # keys are borrowed until destroy
-        opt = _options(expected_groups, path, device, stream, row_base, no_dense, no_partition, detect)
+        opt = _options(expected_groups, path, device, stream, row_base, no_dense, no_partition)
         try:
             _check(self._L.pa_groupby_create(devs, schemas, len(args), C.byref(opt), C.byref(self._h)))
         except Exception:
@@ -420,6 +419,30 @@ def resample(frame, index: Column, freq_ns: int, closed_right: bool = False, lab
         _check(L.pa_resample_create(C.byref(arg.dev), C.byref(arg.schema), int(freq_ns), int(closed_right),
                                     int(label_right), ORIGIN[origin], int(origin_custom_ns), int(offset_ns),
                                     C.byref(opt), C.byref(h)))
+    except Exception:
+        arg.close()
+        raise
+    r = Resampler(None, frame, _handle=h)
+    r._key_args = [arg]
+    return r
+
+
+def downsample(frame, index: Column, rule: str, closed_label_right: bool = True, week_starts_monday: bool = True,
+               start_epoch: bool = True, *, device=None, stream=None) -> Resampler:
+    """DataFrame::downsample (dataframe.cpp:1265-1290): rule = "<multiple><unit>" with unit in N U L S T H D W M Q Y;
+    labels = Floor/CeilTemporal(index) computed on the device (minus one day for W / M / Q / Y, as the reference)."""
+    import re
+    m = re.fullmatch(r"(\d*)([A-Za-z]+)", rule)
+    if not m:
+        raise RuntimeError(f"Invalid time offset {rule}")
+    mult = int(m.group(1)) if m.group(1) else 1
+    L = _lib.load()
+    arg = _CArg(index)
+    h = C.c_void_p()
+    opt = _options(0, "auto", device, stream)
+    try:
+        _check(L.pa_downsample_create(C.byref(arg.dev), C.byref(arg.schema), mult, m.group(2)[0].encode(), int(closed_label_right),
+                                      int(week_starts_monday), int(start_epoch), C.byref(opt), C.byref(h)))
     except Exception:
         arg.close()
         raise

@@ -260,7 +260,7 @@ def _rand_vals(rng, n):
 
 
 @pytest.mark.parametrize("no_dense", [False, True])
-@pytest.mark.parametrize("G,lo", [(16, 0), (16, -7), (200, 10**12), (1000, -500), (1024, 2**40)])
+@pytest.mark.parametrize("G,lo", [(16, 0), (16, -7), (200, 10**12), (1000, -500), (1000, 2**40)])
 def test_lowcard_dense_windows_and_hash_mode(pab, orc, no_dense, G, lo):
     rng = np.random.default_rng(G + (1 if no_dense else 0))
     n = 400_003
@@ -289,6 +289,36 @@ def test_lowcard_scattered_64bit_keys_use_hash_mode(pab, orc):
     assert a.equals(b)                          # hash mode is run-to-run deterministic too
 
 
+def _keys_with_home(home, count, seed):
+    """int64 keys whose hash-mode home slot (top 12 bits of lc_mix(key), lowcard.cuh) is `home`."""
+    C = 0x9E3779B97F4A7C15
+    cinv = pow(C, -1, 1 << 64)
+    rng = np.random.default_rng(seed)
+    out = []
+    for low in rng.integers(0, 1 << 52, count, dtype=np.uint64).tolist():
+        m = (home << 52) | low
+        y = (m * cinv) & ((1 << 64) - 1)            # m = y * C  (mod 2^64)
+        key = y ^ (y >> 32)                         # y = key ^ (key >> 32) is an involution
+        assert (((key ^ (key >> 32)) * C) & ((1 << 64) - 1)) >> 52 == home
+        out.append(key - (1 << 64) if key >= (1 << 63) else key)
+    return np.array(out, dtype=np.int64)
+
+
+@pytest.mark.parametrize("clash,path", [(4, "lowcard"), (14, "lowcard"), (40, "global")])
+def test_lowcard_hash_mode_displaced_keys_and_overflow_list(pab, orc, clash, path):
+    # `clash` keys share one home slot of the packed table: 4 fill the probe window (displacements 0..3), the next
+    # 16 go to the overflow list, more than that and the kernel gives up in favour of the global-table path
+    rng = np.random.default_rng(clash)
+    n = 300_000
+    pool = np.concatenate([_keys_with_home(1234, clash, clash), rng.integers(-2**62, 2**62, 300, dtype=np.int64)])
+    frame = {"k": pa.array(pool[rng.integers(0, len(pool), n)]), "v": _rand_vals(rng, n)}
+    gb, ora, rb = _both(pab, orc, frame, "k")
+    _cmp(gb, ora, rb, "v", ["sum", "mean", "count", "first"], f"clash={clash} narrow")
+    assert gb.timing()["path"] == path
+    _cmp(gb, ora, rb, "v", ALL, f"clash={clash} all")
+    assert gb.timing()["path"] == path
+
+
 def test_lowcard_dense_miss_reruns_in_hash_mode(pab, orc):
     # keys 0..499 everywhere except one far-away key in a row the 16384-row key sample does not see
     rng = np.random.default_rng(29)
@@ -302,18 +332,30 @@ def test_lowcard_dense_miss_reruns_in_hash_mode(pab, orc):
     assert t["path"] == "lowcard" and t["mode"] == "hash" and t["passes"] == 2
 
 
-@pytest.mark.parametrize("G,aggs,path", [(1024, ["sum", "mean", "count"], "lowcard"), (1025, ["sum", "count"], "global"),
-                                         (1024, ["sum", "min", "max", "last"], "lowcard"), (1025, ["min", "max"], "global"),
+@pytest.mark.parametrize("G,aggs,path", [(1000, ["sum", "mean", "count"], "lowcard"), (1001, ["sum", "count"], "global"),
+                                         (1000, ["sum", "min", "max", "last"], "lowcard"), (1001, ["min", "max"], "global"),
                                          (2000, ["sum", "mean"], "global"), (5000, ALL, "global")])
 def test_lowcard_capacity_boundaries(pab, orc, G, aggs, path):
     rng = np.random.default_rng(G)
     n = 300_000
     k = np.concatenate([np.arange(G), rng.integers(0, G, n - G)])      # every key present
-    frame = {"k": pa.array(k * 3, pa.int64()), "v": _rand_vals(rng, n)}   # stride 3: a window wider than the table
+    frame = {"k": pa.array(k * 3, pa.int64()), "v": _rand_vals(rng, n)}   # stride 3: a window wider than the table -> hash mode (1000 ids)
     gb, ora, rb = _both(pab, orc, frame, "k")
     _cmp(gb, ora, rb, "v", aggs, f"G={G} {aggs}")
     assert gb.timing()["path"] == path
     assert gb.groupSize() == G
+
+
+@pytest.mark.parametrize("G,path", [(1024, "lowcard"), (1025, "global")])
+def test_lowcard_dense_capacity_boundary(pab, orc, G, path):
+    # dense (key - base) addressing holds 1024 ids; the hash-mode kernel 1000 (its packed table shares the 227 KB)
+    rng = np.random.default_rng(G + 5)
+    n = 300_000
+    k = np.concatenate([np.arange(G), rng.integers(0, G, n - G)]) + 10**9
+    frame = {"k": pa.array(k, pa.int64()), "v": _rand_vals(rng, n)}
+    gb, ora, rb = _both(pab, orc, frame, "k")
+    _cmp(gb, ora, rb, "v", ["sum", "mean", "count", "first"], f"dense G={G}")
+    assert gb.timing()["path"] == path and gb.groupSize() == G
 
 
 def test_int_values_mean_boundary_and_smem_front(pab, orc):

@@ -143,3 +143,69 @@ def test_resample_errors(pab):
         r.sum()
     empty = pab.resample({"v": pa.array([], pa.float64())}, pa.array([], pa.timestamp("ns")), MIN)
     assert empty.groupSize() == 0 and len(empty.sum()["v"]) == 0
+
+
+# ---------------- DataFrame::downsample: labels computed on the device (csrc/temporal.cuh) ----------------
+@pytest.mark.parametrize("rule,closed_label_right,wsm,start_epoch", [
+    ("3T", True, True, True), ("3T", False, True, True), ("7T", True, True, False), ("7T", False, True, True),
+    ("1H", True, True, True), ("5H", False, True, True), ("1D", True, True, True), ("3D", False, True, True), ("3D", True, True, False),
+    ("250L", False, True, True), ("15S", True, True, True),
+    ("1W", True, True, True), ("1W", False, False, True), ("2W", True, True, False), ("2W", False, True, True),
+    ("1M", True, True, True), ("1M", False, True, True), ("5M", True, True, False), ("2Q", False, True, True), ("1Q", True, True, True),
+    ("1Y", True, True, True), ("3Y", False, True, True)])
+def test_downsample_labels_on_device_vs_arrow(pab, orc, rule, closed_label_right, wsm, start_epoch):
+    """Per-row labels are arrow's Floor/CeilTemporal (minus one day for W / M / Q / Y), as the reference computes them on
+    the host; group set, labels and aggregates must match the oracle's group-by on those labels.  Unsorted index."""
+    import re
+    from util import assert_exact, assert_fp_close
+    rng = np.random.default_rng(len(rule) * 7 + closed_label_right)
+    n = 150_000
+    span = {"L": 4 * 10**9, "S": 3600 * 10**9, "T": 86400 * 10**9, "H": 40 * 86400 * 10**9, "D": 400 * 86400 * 10**9}.get(rule[-1], 9000 * 86400 * 10**9)
+    ts = 1_500_000_000 * 10**9 + rng.integers(-span, span, n)
+    ts[:50] = (ts[:50] // (86400 * 10**9)) * 86400 * 10**9                 # some rows exactly on day boundaries
+    idx = pa.array(ts, pa.timestamp("ns"), mask=rng.random(n) < 0.002)      # a few null timestamps: their own (null-label) group
+    frame = {"px": pa.array(rng.random(n) * 100), "qty": pa.array(rng.integers(0, 1000, n), pa.int64(), mask=rng.random(n) < 0.05)}
+    mult, unit = re.fullmatch(r"(\d+)([A-Z])", rule).groups()
+    labels = orc.downsample_labels(idx, int(mult), unit, closed_label_right, wsm, start_epoch)
+    ora = orc.OracleGroupBy(pa.record_batch(frame), "__resampler_idx__", index=labels)
+    r = pab.downsample(frame, idx, rule, closed_label_right, wsm, start_epoch)
+    assert r.groupSize() == ora.num_groups
+    ours, theirs = r.index(), ora.unique()
+    assert ours.type == theirs.type
+    so = np.argsort(ours.cast(pa.int64()).fill_null(-2**63).to_numpy(), kind="stable")
+    st = np.argsort(theirs.cast(pa.int64()).fill_null(-2**63).to_numpy(), kind="stable")
+    assert ours.take(pa.array(so)).equals(theirs.take(pa.array(st))), "labels differ"
+    for name in frame:
+        res = r.aggregate(frame[name], ALL)
+        for a in ALL:
+            got = res[a].take(pa.array(so))
+            want = ora.agg(a, name, nthreads=8).take(pa.array(st))
+            if a == "mean":
+                m, valid = ora.agg("mean", name, nthreads=8, with_validity=True)
+                want = pa.array(m.to_numpy(zero_copy_only=False), pa.float64(), mask=~np.asarray(valid.to_numpy(zero_copy_only=False), dtype=bool)).take(pa.array(st))
+            if a in ("sum", "mean") and pa.types.is_floating(got.type):
+                assert_fp_close(got, want, f"{rule} {name} {a}")
+            else:
+                assert_exact(got, want, f"{rule} {name} {a}")
+
+
+@pytest.mark.parametrize("unit,per", [("us", 10**3), ("ms", 10**6), ("s", 10**9)])
+def test_resample_non_nanosecond_index(pab, orc, unit, per):
+    """freq / offset arrive in nanoseconds, the index may tick in s / ms / us: buckets must be the same as for the
+    nanosecond twin of the index (the reference itself only handles [ns]; a width that is no whole number of ticks is refused)."""
+    from util import assert_exact
+    rng = np.random.default_rng(per % 97)
+    n = 50_000
+    ts_ns = (1_600_000_000 * 10**9 + np.cumsum(rng.integers(1, 40, n)) * 10**9)       # whole seconds: exact in every unit
+    frame = {"v": pa.array(rng.integers(0, 100, n), pa.int64())}
+    want = pab.resample(frame, pa.array(ts_ns, pa.timestamp("ns")), 5 * MIN, offset_ns=30 * 10**9)
+    got = pab.resample(frame, pa.array(ts_ns // per, pa.timestamp(unit)), 5 * MIN, offset_ns=30 * 10**9)
+    assert got.groupSize() == want.groupSize()
+    assert np.array_equal(got.index().cast(pa.int64()).to_numpy() * per, want.index().cast(pa.int64()).to_numpy())
+    assert got.index().type == pa.timestamp(unit)
+    assert_exact(got.sum()["v"], want.sum()["v"], unit)
+    ora = orc.resample(pa.record_batch(frame), pa.array(ts_ns, pa.timestamp("ns")), 5 * MIN, offset_ns=30 * 10**9)
+    assert np.array_equal(np.sort(ora.unique().cast(pa.int64()).to_numpy()), want.index().cast(pa.int64()).to_numpy())
+    if per > 1:
+        with pytest.raises(pab.PaError, match="whole multiples"):
+            pab.resample(frame, pa.array(ts_ns // per, pa.timestamp(unit)), 1500 if unit != "us" else 1500 + 1)
