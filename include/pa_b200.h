@@ -281,6 +281,26 @@ int pa_groupby_partials_export_padded(pa_groupby* g, int32_t n_parts, void* dev_
 int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t block_records, uint32_t agg_mask,
                            const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out);
 
+/* ---- the same exchange driven from C: communicator handle + one call per step.
+ * pa_comm wraps an NCCL communicator over the GPUs of one node (NVLink / NVSwitch).  Rank 0 obtains an id with
+ * pa_comm_unique_id (PA_COMM_ID_BYTES bytes), every rank receives it by any out-of-band channel (MPI, a file,
+ * torch.distributed ...) and calls pa_comm_create; or an existing ncclComm_t is adopted (not destroyed by
+ * pa_comm_destroy).  pa_groupby_sharded_aggregate then runs, on the handle's stream: the local fused pass over this
+ * rank's row shard (pa_options.row_base = its first global row), the owner bucketing, the exchange of counts
+ * (ncclAllGather) and records (grouped ncclSend / ncclRecv), and the owner-side merge; `merged_out` answers
+ * num_groups / unique / fetch / first_rows for the groups with hash(key) % world == rank.  Send / receive / merge
+ * scratch stays on the communicator between steps.  Aggregates: PA_AGG_ALL bits. */
+#define PA_COMM_ID_BYTES 128
+typedef struct pa_comm pa_comm;
+int pa_comm_unique_id(void* out_id, int64_t capacity_bytes);
+int pa_comm_create(const void* id, int32_t world, int32_t rank, int32_t device, pa_comm** out);
+int pa_comm_adopt(void* nccl_comm, int32_t world, int32_t rank, int32_t device, pa_comm** out);
+void pa_comm_destroy(pa_comm* c);
+int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDeviceArray* values,
+                                 const struct ArrowSchema* value_schema, uint32_t agg_mask, pa_groupby** merged_out);
+/* Device time (ms) of the last step's phases: [0] local pass, [1] count + export, [2] exchange, [3] merge, [4] total. */
+int pa_comm_last_phases(pa_comm* c, double phase_ms[5]);
+
 /* ---- synthetic workload generator, used by bench.py and the tests so that the
  * same counter-based splitmix64 streams exist on host and device without PCIe staging.
  * All pointers are DEVICE pointers; `first_row` offsets the counter (row-range shards). ---- */

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpa_b200.so")
+LIB_PATH = os.environ.get("PA_B200_LIB") or os.path.join(HERE, "lib", "libpa_b200.so")   # (override: kernel A/B experiments)
 
 ARROW_DEVICE_CPU = 1
 ARROW_DEVICE_CUDA = 2
@@ -26,6 +26,7 @@ EXPORTS = [
     "pa_groupby_destroy", "pa_resample_create", "pa_downsample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
     "pa_merge_create", "pa_groupby_partials_export_padded", "pa_merge_create_padded", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
     "pa_synth_validity", "pa_synth_timestamps",
+    "pa_comm_unique_id", "pa_comm_create", "pa_comm_adopt", "pa_comm_destroy", "pa_groupby_sharded_aggregate", "pa_comm_last_phases",
 ]
 
 
@@ -63,6 +64,22 @@ class PaOptions(C.Structure):
 _lib = None
 
 
+def _preload_nccl():
+    """libpa_b200.so needs libnccl.so.2 (pa_comm_*).  A process that also imports torch must end up with ONE copy, and
+    torch wants the one bundled in its wheel set (newer than the system's): load that first, by path, when it exists,
+    so that both resolve the soname to it whatever the import order."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            return
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -71,6 +88,7 @@ def load():
         raise ImportError(
             f"pandasarrow_b200: CUDA library {LIB_PATH} is missing. Build it with "
             "`python -m pandasarrow_b200.build` (nvcc, sm_100a). There is no CPU fallback.")
+    _preload_nccl()
     L = C.CDLL(LIB_PATH)
     for name in EXPORTS:
         if not hasattr(L, name):
@@ -110,6 +128,13 @@ def load():
     L.pa_groupby_partials_export_padded.argtypes = [P, C.c_int32, P, C.c_int64]
     L.pa_merge_create_padded.argtypes = [P, C.c_int32, C.c_int64, C.c_uint32, C.c_char_p, C.c_char_p,
                                          C.POINTER(PaOptions), C.POINTER(P)]
+    L.pa_comm_unique_id.argtypes = [P, C.c_int64]
+    L.pa_comm_create.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(P)]
+    L.pa_comm_adopt.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(P)]
+    L.pa_comm_destroy.argtypes = [P]
+    L.pa_comm_destroy.restype = None
+    L.pa_groupby_sharded_aggregate.argtypes = [P, P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32, C.POINTER(P)]
+    L.pa_comm_last_phases.argtypes = [P, C.POINTER(C.c_double)]
     L.pa_synth_keys_i64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, P]
     L.pa_synth_vals_f64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, P]
     L.pa_synth_validity.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32, P]

@@ -32,7 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "capi.cu"), "-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "capi.cu"), "-o", LIB, "-lnccl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

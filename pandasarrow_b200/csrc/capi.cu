@@ -3,6 +3,7 @@
 // No computation happens on the host and there is no CPU fallback.
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -29,6 +30,7 @@
 #include "temporal.cuh"
 #include "order.cuh"
 #include "csort.cuh"
+#include "strkeys.cuh"
 
 using namespace pa;
 
@@ -111,6 +113,11 @@ struct Column {
   int64_t dict_len = 0;
   DevBuf own_data, own_valid;       // set when the input lived on the host (or was unpacked)
   DevBuf own_bits;                  // boolean host input: the packed bits on the device
+  // utf8 / large_utf8 KEY columns (strkeys.cuh): `data` is the per-row 64-bit hash, the strings stay reachable here
+  bool is_str = false;
+  StrCol str{};
+  DevBuf own_offsets, own_bytes;
+  uint64_t str_seed = 0;
 };
 
 int parse_format(const char* f, int* width, int* vc) {
@@ -210,6 +217,68 @@ int load_column(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t 
     return set_err(PA_ERR_INVALID, "unsupported device_type %d", (int)da->device_type);
   }
   return PA_OK;
+}
+
+// utf8 / large_utf8 key column: offsets + bytes onto the device (or borrowed), then one 64-bit hash per row.
+int hash_string_key(Column* out, cudaStream_t st, int num_sms) {
+  PA_TRY(out->own_data.alloc(static_cast<size_t>(std::max<int64_t>(out->n, 1)) * 8, st));
+  if (out->n > 0) {
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((out->n + 255) / 256, static_cast<int64_t>(num_sms) * 16)));
+    k_str_hash<<<grid, 256, 0, st>>>(out->str, out->valid, out->bit_off, out->n, 0x5851F42D4C957F2Dull + out->str_seed * 0x9E3779B97F4A7C15ull,
+                                     out->own_data.as<uint64_t>());
+    CUDA_TRY(cudaGetLastError());
+  }
+  out->data = out->own_data.p;
+  return PA_OK;
+}
+
+int load_string_key(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t st, int device, int num_sms, Column* out) {
+  const ArrowArray& a = da->array;
+  if (a.n_buffers < 3) return set_err(PA_ERR_INVALID, "utf8 array needs 3 buffers (validity, offsets, data), got %lld", (long long)a.n_buffers);
+  const bool wide = sc->format[0] == 'U';
+  const int ow = wide ? 8 : 4;
+  out->format = sc->format;
+  out->is_str = true;
+  out->width = 8;
+  out->vc = VC_U;
+  out->n = a.length;
+  const bool has_nulls = a.null_count != 0 && a.buffers[0] != nullptr;
+  const char* offs = static_cast<const char*>(a.buffers[1]) + a.offset * ow;
+  const uint8_t* bytes = static_cast<const uint8_t*>(a.buffers[2]);
+  if (da->device_type == ARROW_DEVICE_CUDA) {
+    if (da->device_id != device) return set_err(PA_ERR_INVALID, "array lives on device %lld, handle on %d", (long long)da->device_id, device);
+    if (da->sync_event) CUDA_TRY(cudaStreamWaitEvent(st, *static_cast<cudaEvent_t*>(da->sync_event), 0));
+    out->str.offsets = offs;
+    out->str.bytes = bytes;
+    out->valid = has_nulls ? static_cast<const uint8_t*>(a.buffers[0]) : nullptr;
+    out->bit_off = a.offset;
+  } else if (da->device_type == ARROW_DEVICE_CPU || da->device_type == ARROW_DEVICE_CUDA_HOST) {
+    const int64_t n = a.length;
+    int64_t first = 0, last = 0;
+    if (a.buffers[1]) {
+      first = wide ? reinterpret_cast<const int64_t*>(offs)[0] : reinterpret_cast<const int32_t*>(offs)[0];
+      last = wide ? reinterpret_cast<const int64_t*>(offs)[n] : reinterpret_cast<const int32_t*>(offs)[n];
+    }
+    PA_TRY(out->own_offsets.alloc(static_cast<size_t>(n + 1) * ow, st));
+    if (a.buffers[1]) CUDA_TRY(cudaMemcpyAsync(out->own_offsets.p, offs, static_cast<size_t>(n + 1) * ow, cudaMemcpyHostToDevice, st));
+    else CUDA_TRY(cudaMemsetAsync(out->own_offsets.p, 0, static_cast<size_t>(n + 1) * ow, st));
+    PA_TRY(out->own_bytes.alloc(static_cast<size_t>(std::max<int64_t>(last - first, 1)), st));
+    if (last > first) CUDA_TRY(cudaMemcpyAsync(out->own_bytes.p, bytes + first, static_cast<size_t>(last - first), cudaMemcpyHostToDevice, st));
+    out->str.offsets = out->own_offsets.p;
+    out->str.bytes = out->own_bytes.as<uint8_t>() - first;       // offsets stay absolute
+    if (has_nulls) {
+      const int64_t first_byte = a.offset / 8;
+      const size_t nbytes = static_cast<size_t>((a.offset + a.length + 7) / 8 - first_byte);
+      PA_TRY(out->own_valid.alloc(nbytes, st));
+      CUDA_TRY(cudaMemcpyAsync(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, cudaMemcpyHostToDevice, st));
+      out->valid = out->own_valid.as<uint8_t>();
+      out->bit_off = a.offset % 8;
+    }
+  } else {
+    return set_err(PA_ERR_INVALID, "unsupported device_type %d", (int)da->device_type);
+  }
+  out->str.wide = wide ? 1 : 0;
+  return hash_string_key(out, st, num_sms);
 }
 
 struct KeyField {
@@ -1341,7 +1410,13 @@ int pa_groupby_create(const struct ArrowDeviceArray* keys, const struct ArrowSch
   PA_TRY(handle_init(g.get(), opt));
   g->keys.resize(n_keys);
   for (int i = 0; i < n_keys; ++i) {
-    PA_TRY(load_column(&keys[i], &key_schemas[i], g->stream, g->device, &g->keys[i]));
+    const char* kf = key_schemas[i].format;
+    if (kf && (kf[0] == 'u' || kf[0] == 'U') && kf[1] == 0) {
+      if (n_keys != 1) return set_err(PA_ERR_NOT_IMPLEMENTED, "utf8 keys inside a composite key: dictionary-encode that column");
+      PA_TRY(load_string_key(&keys[i], &key_schemas[i], g->stream, g->device, g->num_sms, &g->keys[i]));
+    } else {
+      PA_TRY(load_column(&keys[i], &key_schemas[i], g->stream, g->device, &g->keys[i]));
+    }
     if (g->keys[i].n != g->keys[0].n) return set_err(PA_ERR_INVALID, "key columns differ in length");
   }
   g->n = g->keys[0].n;
@@ -1985,8 +2060,12 @@ int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records
 
 // Common part of the two merge entry points.  `d_off` = device array [n_sources + 1], exclusive prefix
 // of the per-source record counts (the exact total is d_off[n_sources]); nrec_max = host-side upper bound.
+// Scratch of one merge (key table, per-source index, compaction / sort buffers).  A communicator keeps one between
+// steps (pa_groupby_sharded_aggregate) so that a step allocates nothing but its result.
+struct MergeScratch { DevBuf tkeys, idx, m_first, m_slot, s_first, s_slot, cub_tmp; };
+
 static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d_off, int32_t n_sources, uint64_t nrec_max,
-                       uint32_t agg_mask, const char* value_format, const char* key_format) {
+                       uint32_t agg_mask, const char* value_format, const char* key_format, MergeScratch* keep = nullptr) {
   cudaStream_t st = g->stream;
   g->merged = true;
   g->keys.resize(1);
@@ -2003,7 +2082,9 @@ static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d
   uint64_t cap = 1024;
   while (cap < nrec_max * 2) cap <<= 1;
   const uint64_t nslots = cap + 2;
-  DevBuf tkeys, idx, m_first, m_slot, s_first, s_slot, cub_tmp;
+  MergeScratch local_scratch;
+  MergeScratch& ms = keep ? *keep : local_scratch;
+  DevBuf &tkeys = ms.tkeys, &idx = ms.idx, &m_first = ms.m_first, &m_slot = ms.m_slot, &s_first = ms.s_first, &s_slot = ms.s_slot, &cub_tmp = ms.cub_tmp;
   PA_TRY(tkeys.alloc(nslots * 8, st));
   PA_TRY(idx.alloc(nslots * n_sources * 4, st));
   const int fgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
@@ -2220,6 +2301,161 @@ int merge_padded_general(pa_groupby* g, const void* dev_blocks, int32_t n_source
 }
 }  // namespace
 }  // extern "C++"
+
+// ---- multi-GPU through the C ABI: communicator + the whole sharded step (SURVEY.md §8b "multi-GPU variants taking a
+// communicator handle", §8e) ----
+struct pa_comm {
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0, device = 0;
+  bool own = false;
+  DevBuf send, recv, d_counts, d_all;     // kept between steps (grow only)
+  MergeScratch merge;
+  double phase_ms[5] = {0, 0, 0, 0, 0};   // last step: local pass, count + export, exchange, merge, total
+  cudaEvent_t ev[6] = {};
+};
+
+#define NCCL_TRY(expr)                                                                                          \
+  do {                                                                                                          \
+    ncclResult_t r__ = (expr);                                                                                  \
+    if (r__ != ncclSuccess) return set_err(PA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, ncclGetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
+
+int pa_comm_unique_id(void* out_id, int64_t capacity_bytes) {
+  if (!out_id || capacity_bytes < static_cast<int64_t>(sizeof(ncclUniqueId))) return set_err(PA_ERR_INVALID, "id buffer must hold %zu bytes", sizeof(ncclUniqueId));
+  ncclUniqueId id;
+  NCCL_TRY(ncclGetUniqueId(&id));
+  memcpy(out_id, &id, sizeof id);
+  return PA_OK;
+}
+
+static int comm_finish(pa_comm* c) {
+  for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+  return PA_OK;
+}
+
+int pa_comm_create(const void* id, int32_t world, int32_t rank, int32_t device, pa_comm** out) {
+  if (!id || !out || world < 1 || world > 64 || rank < 0 || rank >= world) return set_err(PA_ERR_INVALID, "pa_comm_create: bad argument (1 <= world <= 64)");
+  std::unique_ptr<pa_comm> c(new pa_comm());
+  c->world = world; c->rank = rank; c->device = device; c->own = true;
+  CUDA_TRY(cudaSetDevice(device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof uid);
+  NCCL_TRY(ncclCommInitRank(&c->comm, world, uid, rank));
+  PA_TRY(comm_finish(c.get()));
+  *out = c.release();
+  return PA_OK;
+}
+
+int pa_comm_adopt(void* nccl_comm, int32_t world, int32_t rank, int32_t device, pa_comm** out) {
+  if (!nccl_comm || !out || world < 1 || world > 64 || rank < 0 || rank >= world) return set_err(PA_ERR_INVALID, "pa_comm_adopt: bad argument");
+  std::unique_ptr<pa_comm> c(new pa_comm());
+  c->comm = static_cast<ncclComm_t>(nccl_comm);
+  c->world = world; c->rank = rank; c->device = device; c->own = false;
+  CUDA_TRY(cudaSetDevice(device));
+  PA_TRY(comm_finish(c.get()));
+  *out = c.release();
+  return PA_OK;
+}
+
+void pa_comm_destroy(pa_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->own && c->comm) ncclCommDestroy(c->comm);
+  delete c;
+}
+
+int pa_comm_last_phases(pa_comm* c, double phase_ms[5]) {
+  if (!c || !phase_ms) return set_err(PA_ERR_INVALID, "null argument");
+  for (int i = 0; i < 5; ++i) phase_ms[i] = c->phase_ms[i];
+  return PA_OK;
+}
+
+// One multi-GPU step for this rank: local stages 1-3 on its row shard -> partial records bucketed by owner =
+// hash(key) % world -> counts (ncclAllGather) and records (grouped ncclSend / ncclRecv: NCCL 2.27 has no all-to-all
+// primitive) over NVLink -> owner-side merge in source-rank order.  Everything runs on the handle's stream.
+int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDeviceArray* values,
+                                 const struct ArrowSchema* value_schema, uint32_t agg_mask, pa_groupby** merged_out) {
+  if (!g || !c || !values || !value_schema || !merged_out) return set_err(PA_ERR_INVALID, "null argument");
+  if (agg_mask == 0 || (agg_mask & ~PA_AGG_ALL)) return set_err(PA_ERR_NOT_IMPLEMENTED, "sharded aggregates: sum / mean / count / min / max / first / last");
+  if (g->device != c->device) return set_err(PA_ERR_INVALID, "handle lives on device %d, communicator on %d", g->device, c->device);
+  PA_TRY(ensure_device(g));
+  cudaStream_t st = g->stream;
+  const int W = c->world;
+  CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  // 1. local pass
+  PA_TRY(aggregate_entry(g, values, value_schema, agg_mask, false));
+  CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  // 2. counts per owner, all ranks' counts to everybody
+  PA_TRY(c->d_counts.alloc(sizeof(uint64_t) * W, st));
+  PA_TRY(c->d_all.alloc(sizeof(uint64_t) * W * W, st));
+  CUDA_TRY(cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint64_t) * W, st));
+  {
+    PartialsArgs a{};
+    a.r = g->res; a.G = g->G; a.nparts = W; a.counts = c->d_counts.as<unsigned long long>();
+    if (g->G) {
+      k_partials_count<<<(g->G + 255) / 256, 256, 0, st>>>(a);
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+  NCCL_TRY(ncclAllGather(c->d_counts.p, c->d_all.p, W, ncclUint64, c->comm, st));
+  std::vector<uint64_t> all(static_cast<size_t>(W) * W);
+  CUDA_TRY(cudaMemcpyAsync(all.data(), c->d_all.p, sizeof(uint64_t) * W * W, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  std::vector<int64_t> send_cnt(W), recv_cnt(W);
+  uint64_t send_total = 0, recv_total = 0;
+  for (int p = 0; p < W; ++p) {
+    send_cnt[p] = static_cast<int64_t>(all[static_cast<size_t>(c->rank) * W + p]);
+    recv_cnt[p] = static_cast<int64_t>(all[static_cast<size_t>(p) * W + c->rank]);
+    send_total += send_cnt[p];
+    recv_total += recv_cnt[p];
+  }
+  // 3. export the records grouped by owner
+  PA_TRY(c->send.alloc(std::max<uint64_t>(send_total, 1) * PA_PARTIAL_WORDS * 8, st));
+  PA_TRY(c->recv.alloc(std::max<uint64_t>(recv_total, 1) * PA_PARTIAL_WORDS * 8, st));
+  g->parts_n = W;
+  g->parts_counts.assign(send_cnt.begin(), send_cnt.end());
+  PA_TRY(pa_groupby_partials_export(g, W, c->send.p, static_cast<int64_t>(std::max<uint64_t>(send_total, g->G))));
+  CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  // 4. all-to-all of the records
+  NCCL_TRY(ncclGroupStart());
+  {
+    uint64_t so = 0, ro = 0;
+    for (int p = 0; p < W; ++p) {
+      if (send_cnt[p]) NCCL_TRY(ncclSend(c->send.as<uint64_t>() + so * PA_PARTIAL_WORDS, static_cast<size_t>(send_cnt[p]) * PA_PARTIAL_WORDS, ncclUint64, p, c->comm, st));
+      if (recv_cnt[p]) NCCL_TRY(ncclRecv(c->recv.as<uint64_t>() + ro * PA_PARTIAL_WORDS, static_cast<size_t>(recv_cnt[p]) * PA_PARTIAL_WORDS, ncclUint64, p, c->comm, st));
+      so += send_cnt[p];
+      ro += recv_cnt[p];
+    }
+  }
+  NCCL_TRY(ncclGroupEnd());
+  CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  // 5. owner-side merge
+  const std::string kfmt = g->resample ? g->index_format : g->keys[0].format;
+  HandlePtr m(new pa_groupby());
+  pa_options mo;
+  pa_options_init(&mo);
+  mo.device = g->device;
+  mo.cuda_stream = st;
+  PA_TRY(handle_init(m.get(), &mo));
+  std::vector<uint64_t> off(W + 1, 0);
+  for (int i = 0; i < W; ++i) off[i + 1] = off[i] + static_cast<uint64_t>(recv_cnt[i]);
+  DevBuf d_off;
+  PA_TRY(d_off.alloc(sizeof(uint64_t) * (W + 1), st));
+  CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(uint64_t) * (W + 1), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(m->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  CUDA_TRY(cudaEventRecord(m->ev[0], st));
+  PA_TRY(merge_build(m.get(), c->recv.p, d_off.as<uint64_t>(), W, recv_total, agg_mask, value_schema->format, kfmt.c_str(), &c->merge));
+  CUDA_TRY(cudaEventRecord(c->ev[4], st));
+  CUDA_TRY(cudaEventSynchronize(c->ev[4]));
+  float t = 0;
+  for (int i = 0; i < 4; ++i) { CUDA_TRY(cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1])); c->phase_ms[i] = t; }
+  CUDA_TRY(cudaEventElapsedTime(&t, c->ev[0], c->ev[4]));
+  c->phase_ms[4] = t;
+  *merged_out = m.release();
+  return PA_OK;
+}
 
 // ---- synthetic generator ----
 static int synth_grid(int64_t n) {

@@ -196,14 +196,15 @@ ArrayPtr GroupBy::unique() const {
 // ------------------------------ materialised groups ------------------------------
 // The reference materialises every group of every column in its constructor (dataframe.cpp:1571-1600);
 // here it happens on first use only.  Group ids come from the GPU, the regrouping is Arrow's.
-// Fixed-width numeric / temporal columns are gathered on the device (pa_groupby_take_grouped); anything else
-// (strings, booleans, dictionaries) with arrow's Take on the row order the device produced.
+// Fixed-width numeric / temporal and boolean columns are regrouped on the device (pa_groupby_take_grouped); strings
+// and dictionaries with arrow's Take on the row order the device produced.
 static bool device_takeable(const arrow::DataType& t) {
   switch (t.id()) {
     case arrow::Type::INT8: case arrow::Type::INT16: case arrow::Type::INT32: case arrow::Type::INT64:
     case arrow::Type::UINT8: case arrow::Type::UINT16: case arrow::Type::UINT32: case arrow::Type::UINT64:
     case arrow::Type::FLOAT: case arrow::Type::DOUBLE: case arrow::Type::TIMESTAMP: case arrow::Type::DATE32:
     case arrow::Type::DATE64: case arrow::Type::TIME32: case arrow::Type::TIME64: case arrow::Type::DURATION:
+    case arrow::Type::BOOL:
       return true;
     default:
       return false;

@@ -179,7 +179,13 @@ struct LcSmem {
   static constexpr size_t ACC_PER_WARP = ((W_CW + GP * 4 + 15) / 16) * 16;
   static constexpr size_t BUDGET = 227 * 1024;
   static constexpr int WARPS_FIT = static_cast<int>((BUDGET - OFF_ACC) / ACC_PER_WARP);
-  static constexpr int WARPS = HASHK ? (WARPS_FIT < 16 ? WARPS_FIT : 16) : Cfg::WARPS;
+#ifndef LC_HASH_WARPS_MAX
+#define LC_HASH_WARPS_MAX 16
+#endif
+#ifndef LC_HASH_EARLY_LOADS
+#define LC_HASH_EARLY_LOADS 0
+#endif
+  static constexpr int WARPS = HASHK ? (WARPS_FIT < LC_HASH_WARPS_MAX ? WARPS_FIT : LC_HASH_WARPS_MAX) : Cfg::WARPS;
   static constexpr size_t TOTAL = OFF_ACC + ACC_PER_WARP * WARPS;
   static_assert(TOTAL <= BUDGET, "shared-memory layout exceeds 227 KB");
   static_assert(WARPS >= 8, "too few warps to keep HBM busy");
@@ -681,7 +687,7 @@ __device__ __forceinline__ void lc_scan_rows(const LcArgs& a, const LcCtx& c, in
     while (g < n_full) {
       const int64_t gn = g + nw;
       const uint32_t gabort = *abort_global;
-      if constexpr (DENSE) {
+      if constexpr (DENSE || LC_HASH_EARLY_LOADS) {
         if (gn < n_full) lc_load_fast(nxt, a, gn * LC_GROUP_ROWS, lane);
         if (!lc_process_group<VC, WIDE, DENSE, true>(cur, g * LC_GROUP_ROWS, lane, c, a)) return;
       } else {

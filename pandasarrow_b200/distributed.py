@@ -67,6 +67,69 @@ def exchange_records(send, send_counts: Sequence[int], group=None):
     return recv, recv_counts
 
 
+class Comm:
+    """pa_comm (include/pa_b200.h): an NCCL communicator owned by libpa_b200.so.  The unique id travels over the
+    already initialised torch.distributed group (any backend); after that the whole sharded step — local pass, owner
+    bucketing, count / record exchange, merge — is ONE C call (pa_groupby_sharded_aggregate), and this module is
+    just its caller."""
+
+    def __init__(self, group=None, device: Optional[int] = None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .groupby import _check
+        L = _lib.load()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.cuda.current_device() if device is None else device
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _check(L.pa_comm_unique_id(buf, 128))
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        self._h = C.c_void_p()
+        self.world, self.rank, self.device = world, rank, dev
+        _check(L.pa_comm_create(raw, world, rank, dev, C.byref(self._h)))
+        self._L = L
+
+    def sharded_aggregate(self, gb, values, aggs: Sequence[str]):
+        """One multi-GPU step; returns the owner-side MergedGroupBy."""
+        import ctypes as C
+        from ._lib import PA_AGG
+        from .groupby import MergedGroupBy, _CArg, _check
+        mask = 0
+        for a in aggs:
+            mask |= PA_AGG[a]
+        arg = _CArg(values)
+        h = C.c_void_p()
+        try:
+            _check(self._L.pa_groupby_sharded_aggregate(gb._h, self._h, C.byref(arg.dev), C.byref(arg.schema), mask, C.byref(h)))
+        finally:
+            arg.close()
+        return MergedGroupBy._from_handle(h)
+
+    def phases(self) -> Dict[str, float]:
+        import ctypes as C
+        from .groupby import _check
+        p = (C.c_double * 5)()
+        _check(self._L.pa_comm_last_phases(self._h, p))
+        return {"local_ms": p[0], "export_ms": p[1], "exchange_ms": p[2], "merge_ms": p[3], "total_ms": p[4]}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.pa_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 PADDED_BLOCK_RECORDS = 2048   # padded exchange: up to this many groups per rank (180 KB per peer block)
 
 

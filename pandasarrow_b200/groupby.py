@@ -380,6 +380,17 @@ class MergedGroupBy(GroupBy):
                                        key_format.encode(), C.byref(opt), C.byref(self._h)))
 
 
+def _merged_from_handle(h) -> "MergedGroupBy":
+    m = MergedGroupBy.__new__(MergedGroupBy)
+    m._L = _lib.load()
+    m._h = h
+    m._frame, m._dicts, m.key_names, m._key_args = {}, [None], ["key"], []
+    return m
+
+
+MergedGroupBy._from_handle = staticmethod(_merged_from_handle)
+
+
 class Resampler(GroupBy):
     """pd::Resampler (group_by.h:255-299): every aggregate runs over all columns of the frame and
     the result is indexed by the bucket labels (`index()`)."""

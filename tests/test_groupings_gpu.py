@@ -101,5 +101,25 @@ def test_groupings_empty_and_errors(pab):
     with pytest.raises(pab.PaError, match="rows"):
         g.take_grouped(pa.array([1.0, 2.0]))
     assert g.take_grouped(rb.column("v")).to_pylist() == [1.0, 3.0, 2.0]
-    with pytest.raises(pab.PaError, match="boolean"):
-        g.take_grouped(pa.array([True, False, True]))
+    assert g.take_grouped(pa.array([True, False, True])).to_pylist() == [True, True, False]   # bit-packed booleans: bit gather
+
+
+@pytest.mark.parametrize("G", [3, 1000, 1500, 70_000, 1_200_000])
+def test_counting_sort_passes_and_scatter_take(pab, G):
+    """MakeGroupings = own stable counting sort (csort.cuh): one pass up to 1024 groups, two up to 2^20, three beyond;
+    ApplyGroupings = scatter through dest[row].  Checked against a stable numpy argsort of the row ids."""
+    rng = np.random.default_rng(G)
+    n = 2_000_003
+    k = rng.integers(0, G, n)
+    k[:min(G, n)] = np.arange(min(G, n))
+    rb = pa.record_batch({"k": pa.array(k, pa.int64())})
+    gb = pab.GroupBy("k", rb, expected_groups=G)
+    offsets, rows = gb.groupings()
+    ids = gb.row_ids().to_numpy()
+    want_off, want_rows = _expected(ids, gb.groupSize())
+    assert np.array_equal(offsets.to_numpy(), want_off)
+    assert np.array_equal(rows.to_numpy(), want_rows)
+    for col in (pa.array(rng.normal(size=n), mask=rng.random(n) < 0.1), pa.array(rng.integers(-100, 100, n).astype(np.int16)),
+                pa.array(rng.integers(0, 255, n).astype(np.uint8), mask=rng.random(n) < 0.5), pa.array(rng.random(n) < 0.3, mask=rng.random(n) < 0.05),
+                pa.array(rng.normal(size=n + 5).astype(np.float32)).slice(5)):
+        assert gb.take_grouped(col).equals(col.take(pa.array(want_rows))), col.type
