@@ -446,9 +446,10 @@ def main():
             for _ in range(3):                                   # local pass alone (what one GPU does for its shard)
                 h5.aggregate(dv, AGGS, fetch=False)
                 local_ms.append(h5.timing()["total_ms"])
+            # the whole sharded step is ONE C call on the library's own NCCL communicator (pa_groupby_sharded_aggregate)
+            comm = D.Comm(device=local)
             def step5():
-                with torch.cuda.stream(stream):
-                    return D.sharded_aggregate(h5, dv, AGGS, "g", "l", stream=stream.cuda_stream, wait=True, padded=False)
+                return comm.sharded_aggregate(h5, dv, AGGS)
             m5 = step5()                                         # warm-up (allocations, NCCL channels)
             m5.close()
             barrier()
@@ -456,8 +457,10 @@ def main():
             t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
             t0.record(stream)
             found = 0
+            phases = []
             for _ in range(k5):
                 m5 = step5()
+                phases.append(comm.phases())
                 found = m5.groupSize()
                 m5.close()
             t1.record(stream)
@@ -466,10 +469,13 @@ def main():
             dist.all_reduce(t5, op=dist.ReduceOp.MAX)
             tg5 = torch.tensor([found], device=dev, dtype=torch.int64)
             dist.all_reduce(tg5)
+            ph = {k: sorted(p_[k] for p_ in phases)[len(phases) // 2] for k in phases[0]}
             extras["config5"] = {"rows_per_gpu": n, "groups": g5, "groups_found_global": int(tg5.item()), "aggs": AGGS,
-                                 "exchange": "counted", "steps": k5, "ms_per_step": t5[0].item(),
+                                 "exchange": "pa_comm (C ABI): ncclAllGather of counts + grouped ncclSend/ncclRecv of records",
+                                 "steps": k5, "ms_per_step": t5[0].item(),
                                  "local_pass_ms": t5[1].item(), "rows_per_s": world * n / (t5[0].item() * 1e-3),
-                                 "efficiency_vs_local_pass": t5[1].item() / t5[0].item()}
+                                 "efficiency_vs_local_pass": t5[1].item() / t5[0].item(), "phases_rank0_ms": ph}
+            comm.close()
             h5.close()
         except Exception as ex:  # noqa: BLE001
             extras["config5"] = {"error": repr(ex)[:300]}

@@ -306,6 +306,7 @@ struct pa_groupby {
   std::vector<Column> keys;
   std::vector<KeyField> fields;
   bool packed = false;
+  bool str_verified = false;        // utf8 key: the hash grouping has been checked byte for byte (strkeys.cuh)
   DevBuf packed_keys;
   const void* key_data = nullptr;   // what the scan kernels read
   const uint8_t* key_valid = nullptr;
@@ -813,6 +814,26 @@ int build_row_lookup(pa_groupby* g, RowLookup* lk) {
   return PA_OK;
 }
 
+int verify_string_keys(pa_groupby* g, bool* collided) {
+  cudaStream_t st = g->stream;
+  *collided = false;
+  if (g->n == 0 || g->G == 0) return PA_OK;
+  RowLookup lk;
+  PA_TRY(build_row_lookup(g, &lk));
+  DevBuf flag;
+  PA_TRY(flag.alloc(4, st));
+  CUDA_TRY(cudaMemsetAsync(flag.p, 0, 4, st));
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+  k_str_verify<<<grid, 256, 0, st>>>(g->keys[0].str, lk.a, g->res.first_row, flag.as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  uint32_t h = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h, flag.p, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h == 2u) return set_err(PA_ERR_STATE, "utf8 keys: a row's hash is missing from the group table");
+  *collided = h != 0;
+  return PA_OK;
+}
+
 // product / variance / stddev (stage2.cuh): the second pass over keys + values, after the ordinary pass has
 // produced sum (or the double sum) and count per group.  Appends its outputs to g->outs.
 int run_stage2(pa_groupby* g, const Column* val, uint32_t ext) {
@@ -983,8 +1004,8 @@ int run_count_distinct(pa_groupby* g, const Column* val) {
 
 // ------------------------------ Arrow export ------------------------------
 struct ExportPriv {
-  void* bufs[2] = {nullptr, nullptr};
-  const void* ptrs[2] = {nullptr, nullptr};
+  void* bufs[3] = {nullptr, nullptr, nullptr};
+  const void* ptrs[3] = {nullptr, nullptr, nullptr};
   std::string format;
 };
 
@@ -993,6 +1014,7 @@ void release_array(ArrowArray* a) {
   if (p) {
     free(p->bufs[0]);
     free(p->bufs[1]);
+    free(p->bufs[2]);
     delete p;
   }
   a->release = nullptr;
@@ -1104,7 +1126,32 @@ int setup_keys(pa_groupby* g) {
   return PA_OK;
 }
 
+int verify_string_keys(pa_groupby* g, bool* collided);
+
+int aggregate_impl_raw(pa_groupby* g, const Column* val, uint32_t mask, bool deferred, int start_at);
+
+// utf8 keys are grouped by a seeded 64-bit hash of their bytes; the first pass on a handle checks the grouping byte
+// for byte against each group's representative and, should two different strings ever share a hash, re-hashes the
+// column with another seed and repeats (strkeys.cuh).
 int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask, bool deferred = false, int start_at = 0) {
+  const bool str = !g->resample && !g->merged && g->keys.size() == 1 && g->keys[0].is_str;
+  if (!str || g->str_verified) return aggregate_impl_raw(g, val, mask, deferred, start_at);
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    PA_TRY(aggregate_impl_raw(g, val, mask, false, attempt == 0 ? start_at : 0));
+    bool collided = false;
+    PA_TRY(verify_string_keys(g, &collided));
+    if (!collided) { g->str_verified = true; return PA_OK; }
+    g->keys[0].str_seed += 1;
+    PA_TRY(hash_string_key(&g->keys[0], g->stream, g->num_sms));
+    g->key_data = g->keys[0].data;
+    g->have_groups = false;
+    g->G = 0;
+    g->outs.clear();
+  }
+  return set_err(PA_ERR_STATE, "utf8 keys: four differently seeded 64-bit hashes all collided");
+}
+
+int aggregate_impl_raw(pa_groupby* g, const Column* val, uint32_t mask, bool deferred, int start_at) {
   cudaStream_t st = g->stream;
   g->last_launches = 0;
   g->last_mode = 0; g->last_rlog = 0; g->last_passes = 0;
@@ -1440,10 +1487,16 @@ int pa_groupby_num_groups(pa_groupby* g, int64_t* out) {
   return PA_OK;
 }
 
+static int unique_strings(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema);
+
 int pa_groupby_unique(pa_groupby* g, int32_t key_i, struct ArrowArray* out, struct ArrowSchema* out_schema) {
   if (!g || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
   PA_TRY(ensure_groups(g));
   PA_TRY(ensure_device(g));
+  if (!g->resample && !g->merged && g->keys.size() == 1 && g->keys[0].is_str) {
+    if (key_i != 0) return set_err(PA_ERR_INVALID, "key index %d out of range", key_i);
+    return unique_strings(g, out, out_schema);
+  }
   if (g->resample) {
     if (key_i != 0) return set_err(PA_ERR_INVALID, "key index %d out of range", key_i);
     return export_host(g->stream, g->index_format, 8, g->G, g->res.key, nullptr, out, out_schema);
@@ -1715,6 +1768,71 @@ int ensure_groupings(pa_groupby* g) {
   return PA_OK;
 }
 }  // namespace
+
+// unique() of a utf8 / large_utf8 key: the bytes of every group's first row, in group order (int32 offsets; a result
+// of more than 2 GiB of distinct strings is refused).
+static int unique_strings(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  cudaStream_t st = g->stream;
+  const uint32_t G = g->G;
+  const Column& k = g->keys[0];
+  DevBuf offs, tile_sums, bytes, valid;
+  PA_TRY(offs.alloc(static_cast<size_t>(G + 1) * 4, st));
+  k_str_lengths<<<(G + 1 + 255) / 256, 256, 0, st>>>(k.str, g->res.first_row, g->res.key_kind, G, offs.as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  uint64_t total64 = 0;
+  {
+    DevBuf tot;
+    PA_TRY(tot.alloc(8, st));
+    CUDA_TRY(cudaMemsetAsync(tot.p, 0, 8, st));
+    if (G) k_sum_u32<<<std::min<uint32_t>((G + 255) / 256, 1024u), 256, 0, st>>>(offs.as<uint32_t>(), G, tot.as<unsigned long long>());
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(&total64, tot.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  if (total64 > 0x7FFFFFFFull) return set_err(PA_ERR_NOT_IMPLEMENTED, "distinct utf8 keys total %llu bytes; int32 offsets hold 2 GiB", (unsigned long long)total64);
+  PA_TRY(scan_u32(g, offs.as<uint32_t>(), static_cast<uint64_t>(G) + 1, &tile_sums));
+  PA_TRY(bytes.alloc(std::max<uint64_t>(total64, 1), st));
+  PA_TRY(valid.alloc(((static_cast<size_t>(G) + 31) / 32 + 1) * 4, st));
+  if (G) {
+    k_str_gather<<<(static_cast<uint64_t>(G) * 32 + 255) / 256, 256, 0, st>>>(k.str, g->res.first_row, g->res.key_kind, G, offs.as<uint32_t>(), bytes.as<uint8_t>());
+    CUDA_TRY(cudaGetLastError());
+    k_kind_validity<<<(G + 31) / 32 * 32 / 256 + 1, 256, 0, st>>>(g->res.key_kind, G, valid.as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+  }
+  auto* priv = new ExportPriv();
+  const size_t words = (static_cast<size_t>(G) + 31) / 32;
+  priv->bufs[0] = malloc(std::max<size_t>(words * 4, 64));
+  priv->bufs[1] = malloc(std::max<size_t>((static_cast<size_t>(G) + 1) * 4, 64));
+  priv->bufs[2] = malloc(std::max<size_t>(total64, 64));
+  cudaError_t e = cudaMemcpyAsync(priv->bufs[1], offs.p, (static_cast<size_t>(G) + 1) * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && G) e = cudaMemcpyAsync(priv->bufs[0], valid.p, words * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && total64) e = cudaMemcpyAsync(priv->bufs[2], bytes.p, total64, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    free(priv->bufs[0]); free(priv->bufs[1]); free(priv->bufs[2]); delete priv;
+    return set_err(PA_ERR_CUDA, "result copy failed: %s", cudaGetErrorString(e));
+  }
+  int64_t set = 0;
+  for (size_t i = 0; i < words; ++i) set += __builtin_popcount(static_cast<const uint32_t*>(priv->bufs[0])[i]);
+  const int64_t null_count = static_cast<int64_t>(G) - set;
+  if (null_count == 0) { free(priv->bufs[0]); priv->bufs[0] = nullptr; }
+  for (int i = 0; i < 3; ++i) priv->ptrs[i] = priv->bufs[i];
+  memset(out, 0, sizeof *out);
+  out->length = G;
+  out->null_count = null_count;
+  out->n_buffers = 3;
+  out->buffers = priv->ptrs;
+  out->release = release_array;
+  out->private_data = priv;
+  memset(out_schema, 0, sizeof *out_schema);
+  auto* f = new std::string("u");
+  out_schema->format = f->c_str();
+  out_schema->name = "";
+  out_schema->flags = ARROW_FLAG_NULLABLE;
+  out_schema->release = release_schema;
+  out_schema->private_data = f;
+  return PA_OK;
+}
 
 int pa_groupby_groupings(pa_groupby* g, struct ArrowArray* offsets, struct ArrowSchema* offsets_schema,
                          struct ArrowArray* rows, struct ArrowSchema* rows_schema) {
@@ -2010,6 +2128,7 @@ int pa_groupby_partials_count(pa_groupby* g, int32_t n_parts, int64_t* counts_ho
   PA_TRY(finish_pending(g));
   if (!g->have_groups || g->merged) return set_err(PA_ERR_STATE, "partials need a finished local aggregate");
   if (g->keys.size() != 1 && !g->resample) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of composite keys");
+  if (!g->resample && g->keys[0].is_str) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of utf8 keys: dictionary-encode the column against a shared dictionary");
   PA_TRY(ensure_device(g));
   cudaStream_t st = g->stream;
   DevBuf counts;
@@ -2179,6 +2298,7 @@ int pa_groupby_partials_export_padded(pa_groupby* g, int32_t n_parts, void* dev_
   if (!g || !dev_blocks || n_parts < 1 || n_parts > 64 || block_records < 1) return set_err(PA_ERR_INVALID, "bad argument (1 <= n_parts <= 64)");
   if (!g->have_groups || g->merged) return set_err(PA_ERR_STATE, "partials need a finished local aggregate");
   if (g->keys.size() != 1 && !g->resample) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of composite keys");
+  if (!g->resample && g->keys[0].is_str) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of utf8 keys: dictionary-encode the column against a shared dictionary");
   PA_TRY(ensure_device(g));
   PartialsArgs a{};
   a.r = g->res; a.G = g->G; a.nparts = n_parts; a.row_base = g->opt.row_base;
@@ -2380,6 +2500,8 @@ int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDe
   if (!g || !c || !values || !value_schema || !merged_out) return set_err(PA_ERR_INVALID, "null argument");
   if (agg_mask == 0 || (agg_mask & ~PA_AGG_ALL)) return set_err(PA_ERR_NOT_IMPLEMENTED, "sharded aggregates: sum / mean / count / min / max / first / last");
   if (g->device != c->device) return set_err(PA_ERR_INVALID, "handle lives on device %d, communicator on %d", g->device, c->device);
+  if (g->keys.size() != 1 && !g->resample) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of composite keys");
+  if (!g->resample && g->keys[0].is_str) return set_err(PA_ERR_NOT_IMPLEMENTED, "multi-GPU merge of utf8 keys: dictionary-encode the column against a shared dictionary");
   PA_TRY(ensure_device(g));
   cudaStream_t st = g->stream;
   const int W = c->world;

@@ -138,14 +138,8 @@ GroupBy::GroupBy(const std::string& key, DataFrame frame) : df(std::move(frame))
   else key_array = df[key].array();   // throws std::runtime_error for an unknown column
   if (!key_array) throw std::runtime_error("frame has no index");
   ArrayPtr to_export = key_array;
-  if (key_array->type_id() == arrow::Type::STRING || key_array->type_id() == arrow::Type::LARGE_STRING) {
-    // utf8 keys: dictionary-encode (first-appearance ordered) and group on the indices; hashing raw
-    // strings on the GPU is SURVEY §8f.
-    static const bool init = [] { return arrow::compute::Initialize().ok(); }();
-    (void)init;
-    auto enc = ReturnOrThrowOnFailure(arrow::compute::DictionaryEncode(key_array)).make_array();
-    to_export = enc;
-  }
+  // utf8 / large_utf8 keys go to the device as they are (format "u" / "U": offsets + bytes, hashed and verified there,
+  // csrc/strkeys.cuh); unique() comes back as strings.
   if (to_export->type_id() == arrow::Type::DICTIONARY) {
     auto d = std::static_pointer_cast<arrow::DictionaryArray>(to_export);
     key_dictionary = d->dictionary();

@@ -8,7 +8,7 @@
 //                 column with another seed (probability ~ n_groups^2 / 2^65 per attempt)
 //   k_str_lengths / k_str_gather   unique(): lengths of the representatives -> offsets (scan) -> bytes
 #pragma once
-#include "common.cuh"
+#include "rowids.cuh"
 
 namespace pa {
 
@@ -51,19 +51,21 @@ __global__ void __launch_bounds__(256) k_str_hash(StrCol c, const uint8_t* valid
   }
 }
 
-// ids[i] = group of row i (rowids.cuh); first_row[g] = representative row of group g
-__global__ void __launch_bounds__(256) k_str_verify(StrCol c, const uint8_t* valid, int64_t bit_off, int64_t n, const uint32_t* ids,
-                                                    const uint32_t* first_row, uint32_t* collision) {
+// Every row against the representative (first row) of the group its HASH belongs to; `a` is the read-only
+// hash -> group lookup of rowids.cuh built over the hash column.
+__global__ void __launch_bounds__(256) k_str_verify(StrCol c, RowIdArgs a, const uint32_t* first_row, uint32_t* collision) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (; i < n; i += stride) {
-    if (valid && !bit_at(valid, bit_off + i)) continue;
-    const int64_t r = first_row[ids[i]];
+  for (; i < a.n; i += stride) {
+    if (a.kvalid && !bit_at(a.kvalid, a.koff + i)) continue;
+    const uint32_t g = rowid_lookup(a, i);
+    if (g >= a.G) { atomicExch(collision, 2u); continue; }
+    const int64_t r = first_row[g];
     if (r == i) continue;
-    const int64_t a = str_off(c, i), la = str_off(c, i + 1) - a;
-    const int64_t b = str_off(c, r), lb = str_off(c, r + 1) - b;
-    bool same = la == lb && !(valid && !bit_at(valid, bit_off + r));
-    for (int64_t j = 0; same && j < la; ++j) same = c.bytes[a + j] == c.bytes[b + j];
+    const int64_t x = str_off(c, i), lx = str_off(c, i + 1) - x;
+    const int64_t y = str_off(c, r), ly = str_off(c, r + 1) - y;
+    bool same = lx == ly;
+    for (int64_t j = 0; same && j < lx; ++j) same = c.bytes[x + j] == c.bytes[y + j];
     if (!same) atomicExch(collision, 1u);
   }
 }
@@ -75,6 +77,22 @@ __global__ void __launch_bounds__(256) k_str_lengths(StrCol c, const uint32_t* f
     len_out[g] = key_kind[g] == 1 /* KK_NULL */ ? 0u : static_cast<uint32_t>(str_off(c, r + 1) - str_off(c, r));
   }
   if (g == G) len_out[G] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_sum_u32(const uint32_t* v, uint32_t n, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) acc += v[i];
+#pragma unroll
+  for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+  if (lane_id() == 0 && acc) atomicAdd(out, acc);
+}
+
+// validity words of unique(): bit g = group g's key is not null (whole words, zero padded)
+__global__ void __launch_bounds__(256) k_kind_validity(const uint8_t* key_kind, uint32_t G, uint32_t* out) {
+  const uint32_t g = blockIdx.x * 256u + threadIdx.x;
+  const bool ok = g < G && key_kind[g] != 1;
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
+  if (lane_id() == 0 && g < (G + 31) / 32 * 32) out[g >> 5] = m;
 }
 
 // out_offsets = exclusive scan of the lengths (G + 1 entries); one warp per group copies the bytes

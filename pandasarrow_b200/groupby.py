@@ -167,9 +167,10 @@ class GroupBy:
     def _normalise_key(self, k):
         if isinstance(k, pa.ChunkedArray):
             k = k.combine_chunks()
-        if isinstance(k, pa.Array) and (pa.types.is_string(k.type) or pa.types.is_large_string(k.type)):
-            # utf8 keys are dictionary-encoded first (a data-format conversion, first-appearance ordered);
-            # hashing raw strings on the GPU is a SURVEY §8(f) "next" row.
+        if (isinstance(k, pa.Array) and (pa.types.is_string(k.type) or pa.types.is_large_string(k.type))
+                and len(self.key_names) > 1):
+            # a utf8 column inside a COMPOSITE key is dictionary-encoded (its codes pack into the 64-bit key); a single
+            # utf8 key goes to the device as strings (format "u": offsets + bytes, csrc/strkeys.cuh)
             k = k.dictionary_encode()
         self._dicts.append(k.dictionary if isinstance(k, pa.DictionaryArray) else None)
         return k
