@@ -325,7 +325,7 @@ def main():
             ts.sort(key=lambda t: t["total_ms"])
             t = ts[len(ts) // 2]
             ab = algorithmic_bytes(n, h.groupSize(), len(SWEEP_AGGS))
-            sweep.append({"groups": g_, "found": h.groupSize(), "path": t["path"], "total_ms": t["total_ms"],
+            sweep.append({"groups": g_, "found": h.groupSize(), "path": t["path"], "mode": t["mode"], "total_ms": t["total_ms"],
                           "scan_ms": t["scan_ms"], "rows_per_s": n / (t["total_ms"] * 1e-3),
                           "scan_GBps": ab / (t["scan_ms"] * 1e-3) / 1e9, "frac": ab / (t["scan_ms"] * 1e-3) / 1e9 / peak})
             h.close()

@@ -217,7 +217,8 @@ int pa_groupby_last_timing(pa_groupby* g, double* total_ms, double stage_ms[4]);
 int pa_groupby_last_path(pa_groupby* g, int32_t* path, int32_t* kernel_launches);
 /* More about the last aggregate call: detail[0] = mode (0 n/a; shared-memory path: 1 dense key - base
  * addressing, 2 hash table; global path: 3 = shared-memory front table with spill,
- * 4 = rows radix-partitioned by table region first, detail[1] = log2(partitions)), detail[1] = log2 of the accumulator replication (dense mode),
+ * 4 = rows radix-partitioned by table region first, detail[1] = log2(partitions); 5 = rows radix-partitioned into buckets that
+ * are aggregated in shared memory, detail[1] = log2(buckets)), detail[1] = log2 of the accumulator replication (dense mode),
  * detail[2] = scan passes run (2 = a dense pass met a key outside its window and was rerun in hash
  * mode; +1 when the shared-memory tables overflowed and the global-table path ran), detail[3] = 0. */
 int pa_groupby_last_detail(pa_groupby* g, int32_t detail[4]);

@@ -1,0 +1,529 @@
+// Medium / high cardinality (more groups than one shared-memory table holds): radix-partition the rows into
+// buckets whose distinct keys fit a CTA's shared-memory table, then aggregate bucket by bucket in shared memory.
+// No global-memory atomics per row, no global hash table: every key lives in exactly one bucket, so a bucket's
+// groups are final when its rows are done and are appended to the output as they are.
+//
+//   m = rp_mix(key)                 bijective 64-bit mix; its TOP bits pick the bucket, the next bits the table slot
+//   k_rp_hist1      level 1: rows per bucket (1024 buckets = top 10 bits) + a HyperLogLog sketch of the keys
+//                   (4096 registers, fed by the 1/8 of the key space whose mix ends in 000) -> estimated group count,
+//                   from which the host picks the total number of bucket bits B (buckets of ~CAP/4 keys)
+//   k_rp_offsets1   exclusive prefix of the 1024 counts -> write cursors
+//   k_rp_scatter    per tile of 4096 rows: shared-memory histogram gives every row its rank inside the tile's run for
+//                   its bucket, the tile is regrouped in shared memory and written out as contiguous runs (one global
+//                   cursor add per bucket and tile) together with the ORIGINAL ROW NUMBERS (first / last need them)
+//   B > 10 (more than ~2 M groups): level 2 inside every level-1 bucket on the next B - 10 bits —
+//   k_rp_tiles      tiles per level-1 bucket (tiles never straddle a bucket) -> prefix
+//   k_rp_hist2      rows per (level-1 bucket, sub-bucket): shared-memory histogram of the current parent, flushed
+//                   when a CTA's contiguous tile range moves on to the next parent
+//   (device-wide exclusive scan, order.cuh) and k_rp_scatter again, reading the level-1 output
+//   k_bucket_agg    one CTA per bucket at a time (buckets handed out by an atomic counter): CTA-shared open-addressing
+//                   table in shared memory (8192 slots narrow / 4096 wide), ATOMS.CAS.64 to claim a key, shared-memory
+//                   atomics for sum / count / first / last / min / max exactly like k_smemtab_scan; when the bucket's
+//                   rows are done its groups are appended to the unordered result (one global counter add per
+//                   bucket) and the slots are reset in the same sweep
+//   k_bm_rank_scatter  first-appearance order by bitmap rank (order.cuh), writing the GroupResult directly
+//
+// DRAM traffic per row (8-byte key + 8-byte value): hist 8 B, scatter 16 + 20 B, aggregate 20 B = 64 B for one level
+// (+ 8 + 20 + 20 B for the second level) against 16 B algorithmic: the floor of this design is 0.25 (0.14) of the
+// 16 B/row roofline.  Only for 8-byte keys and values without validity bitmaps; anything else, and any bucket that
+// turns out to hold more keys than its table (ST_OVERFLOW), goes to the global-table path (gtable.cuh).
+// Replaces Grouper::Consume + per-group CallFunction (/root/reference/src/dataframe.cpp:1582-1584,
+// pd_core_macros.h:114-147) for the cardinalities where the reference's per-group loop takes seconds.
+#pragma once
+#include "gtable.cuh"
+#include "order.cuh"
+
+namespace pa {
+
+constexpr int RP_THREADS = 512;
+constexpr int RP_ROWS = 8;                            // rows per thread
+constexpr int RP_TILE = RP_THREADS * RP_ROWS;         // 4096 rows per tile
+constexpr int RP_MAX_FAN = 1024;
+constexpr int RP_L1_LOG = 10;                         // level 1 always splits 1024 ways
+constexpr int RP_MAX_BITS = 20;                       // at most 2^20 buckets
+constexpr int RH_THREADS = 1024;
+constexpr int HLL_LOG2 = 12;
+constexpr int HLL_M = 1 << HLL_LOG2;
+constexpr int HLL_SAMPLE_LOG2 = 3;                    // one key value in 8 feeds the sketch
+constexpr int BK_THREADS = 768;
+constexpr int BK_MAX_PROBE = 64;
+
+__device__ __forceinline__ uint64_t rp_mix(uint64_t key) { return (key ^ (key >> 32)) * 0x9E3779B97F4A7C15ull; }
+
+__device__ __forceinline__ uint64_t ldg_stream_u64_na(const void* p) {
+  uint64_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32_na(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// level 1 histogram + HyperLogLog
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rp_hist1_one(uint64_t key, unsigned int* s_hist, unsigned int* s_hll) {
+  const uint64_t m = rp_mix(key);
+  atomicAdd(&s_hist[m >> (64 - RP_L1_LOG)], 1u);
+  uint64_t h = (m ^ (m >> 29)) * 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  if ((h & ((1u << HLL_SAMPLE_LOG2) - 1u)) == 0) {
+    const uint32_t idx = static_cast<uint32_t>(h >> HLL_SAMPLE_LOG2) & (HLL_M - 1);
+    const uint64_t rest = h >> (HLL_SAMPLE_LOG2 + HLL_LOG2);                 // 49 bits
+    const uint32_t rank = rest ? static_cast<uint32_t>(__clzll(static_cast<long long>(rest << (HLL_SAMPLE_LOG2 + HLL_LOG2)))) + 1u : 50u;
+    atomicMax(&s_hll[idx], rank);
+  }
+}
+
+__global__ void __launch_bounds__(RH_THREADS) k_rp_hist1(const uint64_t* keys, int64_t n, unsigned int* counts, unsigned int* hll) {
+  __shared__ unsigned int s_hist[1 << RP_L1_LOG];
+  __shared__ unsigned int s_hll[HLL_M];
+  for (int i = threadIdx.x; i < (1 << RP_L1_LOG); i += RH_THREADS) s_hist[i] = 0;
+  for (int i = threadIdx.x; i < HLL_M; i += RH_THREADS) s_hll[i] = 0;
+  __syncthreads();
+  const int64_t n2 = n / 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(RH_THREADS) + threadIdx.x; i < n2; i += static_cast<int64_t>(gridDim.x) * RH_THREADS) {
+    const ulonglong2 k = ldg_stream_u64x2(keys + 2 * i);
+    rp_hist1_one(k.x, s_hist, s_hll);
+    rp_hist1_one(k.y, s_hist, s_hll);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) rp_hist1_one(keys[n - 1], s_hist, s_hll);
+  __syncthreads();
+  for (int i = threadIdx.x; i < (1 << RP_L1_LOG); i += RH_THREADS)
+    if (s_hist[i]) atomicAdd(counts + i, s_hist[i]);
+  for (int i = threadIdx.x; i < HLL_M; i += RH_THREADS)
+    if (s_hll[i]) atomicMax(hll + i, s_hll[i]);
+}
+
+// one CTA of 1024 threads: counts -> exclusive prefix (in place)
+__global__ void __launch_bounds__(1024) k_rp_offsets1(unsigned int* counts) {
+  __shared__ unsigned int s[1024];
+  const int t = threadIdx.x;
+  const unsigned int own = counts[t];
+  s[t] = own;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const unsigned int v = t >= d ? s[t - d] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  counts[t] = s[t] - own;
+}
+
+// after the level-1 scatter `ends[p]` is the end of bucket p: tiles per bucket -> exclusive prefix [1025]
+__global__ void __launch_bounds__(1024) k_rp_tiles(const unsigned int* ends, unsigned int* tile_prefix) {
+  __shared__ unsigned int s[1024];
+  const int t = threadIdx.x;
+  const unsigned int start = t ? ends[t - 1] : 0u;
+  const unsigned int own = (ends[t] - start + RP_TILE - 1) / RP_TILE;
+  s[t] = own;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const unsigned int v = t >= d ? s[t - d] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  tile_prefix[t] = s[t] - own;
+  if (t == 1023) tile_prefix[1024] = s[t];
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiles
+// ---------------------------------------------------------------------------------------------
+struct RpArgs {
+  const uint64_t* keys;
+  const uint64_t* vals;          // may be null (keys-only pass)
+  const uint32_t* rows;          // original row numbers of the source rows; null = the source IS the original order
+  int64_t n;
+  int shift;                     // bucket inside the parent = (rp_mix(key) >> shift) & (fan - 1)
+  int log_fan;
+  int n_parents;                 // 1 (level 1) or 1024 (level 2)
+  const unsigned int* parent_end;    // [n_parents] end of every parent in the source order; null for level 1
+  const unsigned int* tile_prefix;   // [n_parents + 1]; null for level 1
+  unsigned int* cursors;         // [n_parents << log_fan] write cursors (level-2 histogram: counts)
+  uint64_t* out_keys;
+  uint64_t* out_vals;
+  uint32_t* out_rows;
+};
+
+struct RpTile { uint32_t parent; int64_t row0; int cnt; };
+
+__device__ __forceinline__ uint32_t rp_num_tiles(const RpArgs& a) {
+  return a.parent_end ? a.tile_prefix[a.n_parents] : static_cast<uint32_t>((a.n + RP_TILE - 1) / RP_TILE);
+}
+
+__device__ __forceinline__ RpTile rp_tile(const RpArgs& a, uint32_t t) {
+  RpTile r;
+  if (!a.parent_end) {
+    r.parent = 0;
+    r.row0 = static_cast<int64_t>(t) * RP_TILE;
+    const int64_t left = a.n - r.row0;
+    r.cnt = left < RP_TILE ? static_cast<int>(left) : RP_TILE;
+    return r;
+  }
+  uint32_t lo = 0, hi = static_cast<uint32_t>(a.n_parents);      // largest p with tile_prefix[p] <= t
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(a.tile_prefix + mid) <= t) lo = mid; else hi = mid;
+  }
+  const uint32_t start = lo ? __ldg(a.parent_end + lo - 1) : 0u, end = __ldg(a.parent_end + lo);
+  r.parent = lo;
+  r.row0 = static_cast<int64_t>(start) + static_cast<int64_t>(t - __ldg(a.tile_prefix + lo)) * RP_TILE;
+  const int64_t left = static_cast<int64_t>(end) - r.row0;
+  r.cnt = left < RP_TILE ? static_cast<int>(left) : RP_TILE;
+  return r;
+}
+
+// level 2 histogram: every CTA takes a contiguous range of tiles; the shared-memory histogram covers the sub-buckets
+// of the current parent and is flushed when the range moves on to the next one
+__global__ void __launch_bounds__(RP_THREADS) k_rp_hist2(RpArgs a) {
+  __shared__ unsigned int s_hist[RP_MAX_FAN];
+  const uint32_t ntiles = rp_num_tiles(a);
+  const uint32_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t t0 = blockIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+  const int fan = 1 << a.log_fan;
+  uint32_t cur = 0xFFFFFFFFu;
+  for (uint32_t t = t0; t < t1; ++t) {
+    const RpTile tl = rp_tile(a, t);
+    if (tl.parent != cur) {
+      __syncthreads();
+      if (cur != 0xFFFFFFFFu) {
+        for (int i = threadIdx.x; i < fan; i += RP_THREADS)
+          if (s_hist[i]) atomicAdd(a.cursors + (static_cast<size_t>(cur) << a.log_fan) + i, s_hist[i]);
+        __syncthreads();
+      }
+      for (int i = threadIdx.x; i < fan; i += RP_THREADS) s_hist[i] = 0;
+      __syncthreads();
+      cur = tl.parent;
+    }
+    for (int r = threadIdx.x; r < tl.cnt; r += RP_THREADS) {
+      const uint64_t m = rp_mix(ldg_stream_u64_na(a.keys + tl.row0 + r));
+      atomicAdd(&s_hist[static_cast<uint32_t>(m >> a.shift) & (fan - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  if (cur != 0xFFFFFFFFu) {
+    for (int i = threadIdx.x; i < fan; i += RP_THREADS)
+      if (s_hist[i]) atomicAdd(a.cursors + (static_cast<size_t>(cur) << a.log_fan) + i, s_hist[i]);
+  }
+}
+
+struct RpSmem {
+  static constexpr size_t OFF_KEY = 0;
+  static constexpr size_t OFF_VAL = OFF_KEY + sizeof(uint64_t) * RP_TILE;
+  static constexpr size_t OFF_ROW = OFF_VAL + sizeof(uint64_t) * RP_TILE;
+  static constexpr size_t OFF_HIST = OFF_ROW + sizeof(uint32_t) * RP_TILE;
+  static constexpr size_t OFF_OFF = OFF_HIST + sizeof(uint32_t) * RP_MAX_FAN;
+  static constexpr size_t OFF_DELTA = OFF_OFF + sizeof(uint32_t) * RP_MAX_FAN;
+  static constexpr size_t TOTAL = OFF_DELTA + sizeof(uint32_t) * RP_MAX_FAN;
+};
+static_assert(2 * (RpSmem::TOTAL + 1024) <= 228 * 1024, "two scatter CTAs per SM");
+
+// Two CTAs per SM: the phases of a tile are separated by barriers (load -> rank -> claim -> regroup -> write), so a
+// second resident CTA keeps the memory system busy while the first one regroups.
+__global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(RpArgs a) {
+  extern __shared__ __align__(16) unsigned char rp_smem[];
+  uint64_t* st_key = reinterpret_cast<uint64_t*>(rp_smem + RpSmem::OFF_KEY);
+  uint64_t* st_val = reinterpret_cast<uint64_t*>(rp_smem + RpSmem::OFF_VAL);
+  uint32_t* st_row = reinterpret_cast<uint32_t*>(rp_smem + RpSmem::OFF_ROW);
+  unsigned int* s_hist = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_HIST);
+  unsigned int* s_off = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_OFF);
+  // s_delta[b] = (start of this tile's run for b in the output) - (start of the run in the regrouped tile)
+  unsigned int* s_delta = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_DELTA);
+  __shared__ unsigned int s_wsum[RP_THREADS / 32];
+  constexpr int BINS = RP_MAX_FAN / RP_THREADS;      // histogram bins per thread in the scan
+  const int fan = 1 << a.log_fan;
+  const uint32_t ntiles = rp_num_tiles(a);
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const RpTile tl = rp_tile(a, t);
+    unsigned int* cursors = a.cursors + (static_cast<size_t>(tl.parent) << a.log_fan);
+    for (int i = threadIdx.x; i < fan; i += RP_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    uint64_t key[RP_ROWS], val[RP_ROWS];
+    uint32_t pr[RP_ROWS];    // bucket << 13 | rank inside the tile's run for that bucket
+#pragma unroll
+    for (int j = 0; j < RP_ROWS; ++j) {
+      const int r = threadIdx.x + j * RP_THREADS;
+      key[j] = 0; val[j] = 0;
+      if (r < tl.cnt) {
+        key[j] = ldg_stream_u64_na(a.keys + tl.row0 + r);
+        if (a.vals) val[j] = ldg_stream_u64_na(a.vals + tl.row0 + r);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RP_ROWS; ++j) {
+      const int r = threadIdx.x + j * RP_THREADS;
+      pr[j] = 0xFFFFFFFFu;
+      if (r < tl.cnt) {
+        const uint32_t b = static_cast<uint32_t>(rp_mix(key[j]) >> a.shift) & (fan - 1);
+        pr[j] = (b << 13) | atomicAdd(&s_hist[b], 1u);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the tile histogram (BINS adjacent bins per thread) + claim the output ranges
+    {
+      unsigned int mine[BINS], tot = 0;
+#pragma unroll
+      for (int b = 0; b < BINS; ++b) {
+        const int bin = threadIdx.x * BINS + b;
+        mine[b] = bin < fan ? s_hist[bin] : 0u;
+        tot += mine[b];
+      }
+      unsigned int incl = tot;
+      const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= static_cast<uint32_t>(d)) incl += v;
+      }
+      if (lane == 31) s_wsum[w] = incl;
+      __syncthreads();
+      if (w == 0) {
+        unsigned int x = lane < RP_THREADS / 32 ? s_wsum[lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, x, d);
+          if (lane >= static_cast<uint32_t>(d)) x += v;
+        }
+        if (lane < RP_THREADS / 32) s_wsum[lane] = x;
+      }
+      __syncthreads();
+      unsigned int excl = incl - tot + (w ? s_wsum[w - 1] : 0u);
+#pragma unroll
+      for (int b = 0; b < BINS; ++b) {
+        const int bin = threadIdx.x * BINS + b;
+        if (bin < fan) {
+          s_off[bin] = excl;
+          const unsigned int base = mine[b] ? atomicAdd(cursors + bin, mine[b]) : 0u;
+          s_delta[bin] = base - excl;
+        }
+        excl += mine[b];
+      }
+    }
+    __syncthreads();
+    // regroup the tile in shared memory (the original row numbers are fetched only now: 64 registers per thread)
+    uint32_t row[RP_ROWS];
+#pragma unroll
+    for (int j = 0; j < RP_ROWS; ++j) {
+      const int r = threadIdx.x + j * RP_THREADS;
+      row[j] = static_cast<uint32_t>(tl.row0 + r);
+      if (a.rows && pr[j] != 0xFFFFFFFFu) row[j] = ldg_stream_u32_na(a.rows + tl.row0 + r);
+    }
+#pragma unroll
+    for (int j = 0; j < RP_ROWS; ++j) {
+      if (pr[j] == 0xFFFFFFFFu) continue;
+      const uint32_t pos = s_off[pr[j] >> 13] + (pr[j] & 0x1FFFu);
+      st_key[pos] = key[j];
+      st_val[pos] = val[j];
+      st_row[pos] = row[j];
+    }
+    __syncthreads();
+    // contiguous runs out (the bucket of a regrouped row is recomputed from its key)
+    for (int i = threadIdx.x; i < tl.cnt; i += RP_THREADS) {
+      const uint64_t k = st_key[i];
+      const unsigned int d = s_delta[static_cast<uint32_t>(rp_mix(k) >> a.shift) & (fan - 1)] + static_cast<unsigned int>(i);
+      a.out_keys[d] = k;
+      if (a.vals) a.out_vals[d] = st_val[i];
+      a.out_rows[d] = st_row[i];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bucket aggregation
+// ---------------------------------------------------------------------------------------------
+struct BkArgs {
+  const uint64_t* keys;          // partitioned rows (arrays padded by 4 elements: 256-bit loads may read past a bucket)
+  const uint64_t* vals;          // may be null
+  const uint32_t* rows;
+  const unsigned int* bucket_end;   // [n_buckets]
+  uint32_t n_buckets;
+  int part_bits;                 // bits of rp_mix consumed by the partitioning
+  unsigned int* next_bucket;     // work counter
+  uint32_t agg_mask;
+  uint32_t max_keys;             // keys a bucket's table admits
+  // unordered groups
+  uint64_t* u_key;
+  uint64_t* u_sum;
+  uint32_t* u_count;
+  uint32_t* u_first;
+  uint32_t* u_last;
+  uint64_t* u_min;
+  uint64_t* u_max;
+  double* u_dsum;
+  uint32_t u_cap;
+  uint32_t* status;              // ST_OVERFLOW, ST_COUNTER (groups appended)
+};
+
+template <int VC, bool WIDE>
+__global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
+  using T = SmTab<VC, WIDE>;
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(st_smem + T::OFF_KEY);
+  unsigned long long* s_sum = reinterpret_cast<unsigned long long*>(st_smem + T::OFF_SUM);
+  unsigned long long* s_mn = reinterpret_cast<unsigned long long*>(st_smem + T::OFF_MN);
+  unsigned long long* s_mx = reinterpret_cast<unsigned long long*>(st_smem + T::OFF_MX);
+  double* s_dsum = reinterpret_cast<double*>(st_smem + T::OFF_DSUM);
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(st_smem + T::OFF_CNT);
+  uint32_t* s_first = reinterpret_cast<uint32_t*>(st_smem + T::OFF_FIRST);
+  uint32_t* s_last = reinterpret_cast<uint32_t*>(st_smem + T::OFF_LAST);
+  uint32_t* s_misc = reinterpret_cast<uint32_t*>(st_smem + T::OFF_MISC);   // [0] keys in the table, [1] bucket, [2] output base, [3] emit cursor
+  for (int i = threadIdx.x; i < T::NSLOT; i += BK_THREADS) {
+    s_key[i] = kEmptyKey;
+    s_sum[i] = 0ull;
+    s_cnt[i] = 0u;
+    s_first[i] = kNoRow;
+    if constexpr (WIDE) { s_mn[i] = kMinInit; s_mx[i] = kMaxInit; s_last[i] = 0u; }
+    if constexpr (T::DSUM) s_dsum[i] = 0.0;
+  }
+  if (threadIdx.x < 4) s_misc[threadIdx.x] = 0u;
+  __syncthreads();
+  for (;;) {
+    if (threadIdx.x == 0) {
+      s_misc[1] = atomicAdd(a.next_bucket, 1u);
+      s_misc[3] = 0u;
+    }
+    __syncthreads();
+    const uint32_t b = s_misc[1];
+    if (b >= a.n_buckets) break;
+    if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) break;
+    const uint32_t start = b ? a.bucket_end[b - 1] : 0u, end = a.bucket_end[b];
+    bool failed = false;
+    for (uint64_t base = (start & ~3u) + 4u * threadIdx.x; base < end; base += 4u * BK_THREADS) {
+      const u64x4 k4 = ldg_stream_u64x4(a.keys + base);
+      u64x4 v4{0ull, 0ull, 0ull, 0ull};
+      if (a.vals) v4 = ldg_stream_u64x4(a.vals + base);
+      const uint4 r4 = *reinterpret_cast<const uint4*>(a.rows + base);
+      const uint64_t keyv[4] = {k4.a, k4.b, k4.c, k4.d};
+      const uint64_t valv[4] = {v4.a, v4.b, v4.c, v4.d};
+      const uint32_t rowv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t idx = base + j;
+        if (idx < start || idx >= end) continue;
+        const uint64_t key = keyv[j];
+        const uint32_t row = rowv[j];
+        uint32_t s;
+        bool found = false;
+        if (key == kEmptyKey) { s = T::CAP + 1; found = true; }
+        else {
+          s = static_cast<uint32_t>((rp_mix(key) << a.part_bits) >> (64 - T::CAP_LOG2));
+          for (int probe = 0; probe < BK_MAX_PROBE; ++probe) {
+            const uint64_t k = *reinterpret_cast<volatile unsigned long long*>(s_key + s);
+            if (k == key) { found = true; break; }
+            if (k == kEmptyKey) {
+              if (*reinterpret_cast<volatile uint32_t*>(s_misc) >= a.max_keys) break;
+              const uint64_t old = atomicCAS(s_key + s, static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+              if (old == kEmptyKey) { atomicAdd(s_misc, 1u); found = true; break; }
+              if (old == key) { found = true; break; }
+            }
+            s = (s + 1) & (T::CAP - 1);
+          }
+        }
+        if (!found) { failed = true; continue; }
+        if (row < *reinterpret_cast<volatile uint32_t*>(s_first + s)) atomicMin(s_first + s, row);
+        if constexpr (WIDE) {
+          if ((a.agg_mask & AGG_LAST) && row > *reinterpret_cast<volatile uint32_t*>(s_last + s)) atomicMax(s_last + s, row);
+        }
+        if (!a.vals) continue;
+        atomicAdd(s_cnt + s, 1u);
+        if constexpr (VC == VC_F) atomicAdd(reinterpret_cast<double*>(s_sum + s), __longlong_as_double(static_cast<long long>(valv[j])));
+        else atomicAdd(s_sum + s, static_cast<unsigned long long>(valv[j]));
+        if constexpr (WIDE) {
+          if constexpr (T::DSUM) {
+            if (a.agg_mask & AGG_MEAN) atomicAdd(s_dsum + s, Wide<VC>::as_double(valv[j]));
+          }
+          if ((a.agg_mask & (AGG_MIN | AGG_MAX)) && !Wide<VC>::is_nan(valv[j])) {
+            const uint64_t o = Wide<VC>::ord(valv[j]);
+            if (o < *reinterpret_cast<volatile unsigned long long*>(s_mn + s)) atomicMin(s_mn + s, static_cast<unsigned long long>(o));
+            if (o > *reinterpret_cast<volatile unsigned long long*>(s_mx + s)) atomicMax(s_mx + s, static_cast<unsigned long long>(o));
+          }
+        }
+      }
+    }
+    if (failed) atomicExch(a.status + ST_OVERFLOW, 1u);
+    __syncthreads();
+    if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) break;
+    // ---- append this bucket's groups, resetting the slots in the same sweep ----
+    if (threadIdx.x == 0) {
+      const uint32_t total = s_misc[0] + (s_first[T::CAP + 1] != kNoRow ? 1u : 0u);
+      const uint32_t gbase = atomicAdd(a.status + ST_COUNTER, total);
+      s_misc[2] = gbase;
+      if (static_cast<uint64_t>(gbase) + total > a.u_cap) atomicExch(a.status + ST_OVERFLOW, 2u);
+    }
+    __syncthreads();
+    const uint32_t gbase = s_misc[2];
+    const bool fits = static_cast<uint64_t>(gbase) + s_misc[0] + 1u <= a.u_cap;
+    for (int i0 = 0; i0 < T::NSLOT; i0 += BK_THREADS) {
+      const int i = i0 + threadIdx.x;
+      const uint32_t first = i < T::NSLOT ? s_first[i] : kNoRow;
+      const bool occ = first != kNoRow;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, occ);
+      if (m == 0) continue;
+      uint32_t wbase = 0;
+      if (lane_id() == 0) wbase = atomicAdd(s_misc + 3, __popc(m));
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+      if (occ) {
+        const uint32_t pos = gbase + wbase + __popc(m & ((1u << lane_id()) - 1u));
+        if (fits) {
+          a.u_key[pos] = i == T::CAP + 1 ? kEmptyKey : s_key[i];
+          a.u_sum[pos] = s_sum[i];
+          a.u_count[pos] = s_cnt[i];
+          a.u_first[pos] = first;
+          if constexpr (WIDE) {
+            a.u_last[pos] = s_last[i];
+            a.u_min[pos] = s_mn[i];
+            a.u_max[pos] = s_mx[i];
+            if constexpr (T::DSUM) { if (a.u_dsum) a.u_dsum[pos] = s_dsum[i]; }
+          }
+        }
+        s_key[i] = kEmptyKey;
+        s_sum[i] = 0ull;
+        s_cnt[i] = 0u;
+        s_first[i] = kNoRow;
+        if constexpr (WIDE) { s_mn[i] = kMinInit; s_mx[i] = kMaxInit; s_last[i] = 0u; }
+        if constexpr (T::DSUM) s_dsum[i] = 0.0;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_misc[0] = 0u;
+    __syncthreads();
+  }
+}
+
+// GroupResult[rank of first_row[i]] = unordered group i (bitmap + block prefix of order.cuh)
+struct BkOrderArgs {
+  const uint64_t* u_key; const uint64_t* u_sum; const uint32_t* u_count; const uint32_t* u_first; const uint32_t* u_last;
+  const uint64_t* u_min; const uint64_t* u_max; const double* u_dsum;
+  uint32_t G;
+  const uint32_t* bitmap; const uint32_t* prefix8;
+  GroupResult out;
+  int wide;
+};
+__global__ void __launch_bounds__(256) k_bm_rank_scatter(BkOrderArgs a) {
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= a.G) return;
+  const uint32_t r = a.u_first[i];
+  const uint32_t word = r >> 5, blk = word / BM_BLOCK_WORDS;
+  uint32_t rank = a.prefix8[blk];
+  for (uint32_t w = blk * BM_BLOCK_WORDS; w < word; ++w) rank += __popc(a.bitmap[w]);
+  rank += __popc(a.bitmap[word] & ((1u << (r & 31u)) - 1u));
+  a.out.key[rank] = a.u_key[i];
+  a.out.key_kind[rank] = KK_REGULAR;
+  a.out.sum[rank] = a.u_sum[i];
+  a.out.count[rank] = a.u_count[i];
+  a.out.first_row[rank] = r;
+  a.out.last_row[rank] = a.wide ? a.u_last[i] : 0u;
+  if (a.wide) {
+    a.out.min_ord[rank] = a.u_min[i];
+    a.out.max_ord[rank] = a.u_max[i];
+    if (a.out.dsum && a.u_dsum) a.out.dsum[rank] = a.u_dsum[i];
+  }
+}
+
+}  // namespace pa

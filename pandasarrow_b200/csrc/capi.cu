@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +23,7 @@
 #include "lowcard.cuh"
 #include "merge.cuh"
 #include "partition.cuh"
+#include "bucketed.cuh"
 #include "resample.cuh"
 #include "rowids.cuh"
 #include "stage2.cuh"
@@ -67,22 +69,30 @@ struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   cudaStream_t s = nullptr;
+  bool plain = false;     // cudaMalloc / cudaFree instead of the stream-ordered pool: for buffers that outlive the streams they are used on
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
   DevBuf& operator=(DevBuf&& o) noexcept {
-    if (this != &o) { reset(); p = o.p; bytes = o.bytes; s = o.s; o.p = nullptr; o.bytes = 0; }
+    if (this != &o) { reset(); p = o.p; bytes = o.bytes; s = o.s; plain = o.plain; o.p = nullptr; o.bytes = 0; }
     return *this;
   }
   ~DevBuf() { reset(); }
   void reset() {
-    if (p) cudaFreeAsync(p, s);
+    if (p) { if (plain) cudaFree(p); else cudaFreeAsync(p, s); }
     p = nullptr;
     bytes = 0;
   }
   int alloc(size_t n, cudaStream_t stream) {
     if (n == 0) n = 16;
+    if (plain) {
+      if (p && bytes >= n) return PA_OK;
+      reset();
+      CUDA_TRY(cudaMalloc(&p, n));
+      bytes = n;
+      return PA_OK;
+    }
     if (p && s == stream && bytes >= n) return PA_OK;   // recycled handle: the old block is big enough
     reset();
     s = stream;
@@ -361,7 +371,12 @@ struct pa_groupby {
   // Scratch of the global-table / resample passes, kept between calls on the handle: returning multi-GB blocks to
   // the stream-ordered pool and asking for them again fragments it (cudaMallocAsync then takes 50-1700 ms per call
   // at 100 M groups); a repeated aggregate on the same handle reuses these without touching the allocator.
-  struct Scratch { DevBuf table, p_keys, p_vals, p_rows, p_counts, krange, c_first, c_slot, s_first, s_slot, cub_tmp, bnd, bitmap, prefix8, tile_sums; } scr;
+  struct Scratch {
+    DevBuf table, p_keys, p_vals, p_rows, p_counts, krange, c_first, c_slot, s_first, s_slot, cub_tmp, bnd, bitmap, prefix8, tile_sums;
+    // bucketed path (bucketed.cuh): second-level rows, histograms / cursors, sketch, unordered groups
+    DevBuf q_keys, q_vals, q_rows, rp_counts1, rp_counts2, rp_tiles, rp_hll, rp_next, u_key, u_sum, u_count, u_first, u_last, u_min, u_max, u_dsum;
+  } scr;
+  double est_groups = 0;                  // bucketed path: HyperLogLog estimate of the last pass (diagnostics)
 };
 
 namespace {
@@ -566,6 +581,184 @@ int order_by_first_row(pa_groupby* g, const uint32_t* c_first, const uint32_t* c
 }
 
 // ------------------------------ global-table path ------------------------------
+
+// device-wide exclusive scan of a uint32 array in place (order.cuh)
+int scan_u32_on(pa_groupby* g, uint32_t* data, uint64_t n, DevBuf* tile_sums) {
+  cudaStream_t st = g->stream;
+  const uint32_t ntiles = static_cast<uint32_t>((n + SC_TILE - 1) / SC_TILE);
+  PA_TRY(tile_sums->alloc(static_cast<size_t>(std::max<uint32_t>(ntiles, 1)) * 4, st));
+  if (n == 0) return PA_OK;
+  k_scan_tiles<<<ntiles, 256, 0, st>>>(data, n, tile_sums->as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  k_scan_sums<<<1, 256, 0, st>>>(tile_sums->as<uint32_t>(), ntiles);
+  CUDA_TRY(cudaGetLastError());
+  k_scan_apply<<<ntiles, 256, 0, st>>>(data, n, tile_sums->as<uint32_t>());
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;
+}
+
+// HyperLogLog estimate from the registers k_rp_hist1 filled (one key value in 2^HLL_SAMPLE_LOG2 feeds the sketch).
+double hll_estimate(const uint32_t* reg) {
+  const double m = HLL_M;
+  double sum = 0;
+  int zeros = 0;
+  for (int i = 0; i < HLL_M; ++i) { sum += std::ldexp(1.0, -static_cast<int>(reg[i])); zeros += reg[i] == 0; }
+  double e = (0.7213 / (1.0 + 1.079 / m)) * m * m / sum;
+  if (e <= 2.5 * m && zeros > 0) e = m * std::log(m / zeros);      // small-range correction (linear counting)
+  return e * static_cast<double>(1u << HLL_SAMPLE_LOG2);
+}
+
+// The bucketed path (bucketed.cuh).  *declined = true: the estimate says a single shared-memory table holds the
+// groups, or a bucket overflowed its table — the caller continues on the global-table path.
+template <int VC, bool WIDE>
+int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, bool* declined) {
+  using T = SmTab<VC, WIDE>;
+  cudaStream_t st = g->stream;
+  *declined = false;
+  auto& sc = g->scr;
+  const int64_t n = g->n;
+  const uint64_t* keys = static_cast<const uint64_t*>(g->key_data);
+  const uint64_t* vals = val ? static_cast<const uint64_t*>(val->data) : nullptr;
+  CUDA_TRY(cudaEventRecord(g->ev[1], st));
+  // ---- level 1 histogram + sketch ----
+  PA_TRY(sc.rp_counts1.alloc(sizeof(uint32_t) * 1024, st));
+  PA_TRY(sc.rp_hll.alloc(sizeof(uint32_t) * HLL_M, st));
+  CUDA_TRY(cudaMemsetAsync(sc.rp_counts1.p, 0, sizeof(uint32_t) * 1024, st));
+  CUDA_TRY(cudaMemsetAsync(sc.rp_hll.p, 0, sizeof(uint32_t) * HLL_M, st));
+  CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
+  k_rp_hist1<<<g->num_sms * 2, RH_THREADS, 0, st>>>(keys, n, sc.rp_counts1.as<unsigned int>(), sc.rp_hll.as<unsigned int>());
+  CUDA_TRY(cudaGetLastError());
+  std::vector<uint32_t> reg(HLL_M);
+  CUDA_TRY(cudaMemcpyAsync(reg.data(), sc.rp_hll.p, sizeof(uint32_t) * HLL_M, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const double est = hll_estimate(reg.data());
+  g->est_groups = est;
+  const uint64_t hint = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
+  // plan for the larger of hint and estimate (the sketch is good to a few per cent; a wrong hint must not overflow the tables)
+  const uint64_t plan = std::max<uint64_t>(hint, static_cast<uint64_t>(est * 1.05) + 64);
+  g->last_launches += 1;
+  if (!hint && plan <= static_cast<uint64_t>(T::CAP)) { *declined = true; return PA_OK; }   // the front table (gtable.cuh) holds them
+  const uint64_t per_bucket = T::CAP / 4;
+  int bits = RP_L1_LOG;
+  while (bits < RP_MAX_BITS && (plan >> bits) > per_bucket) ++bits;
+  const uint32_t nb = 1u << bits;
+  // ---- level 1 scatter ----
+  const size_t pad = 4;
+  PA_TRY(sc.p_keys.alloc((static_cast<size_t>(n) + pad) * 8, st));
+  if (vals) PA_TRY(sc.p_vals.alloc((static_cast<size_t>(n) + pad) * 8, st));
+  PA_TRY(sc.p_rows.alloc((static_cast<size_t>(n) + pad) * 4, st));
+  k_rp_offsets1<<<1, 1024, 0, st>>>(sc.rp_counts1.as<unsigned int>());
+  CUDA_TRY(cudaGetLastError());
+  RpArgs a1{};
+  a1.keys = keys; a1.vals = vals; a1.rows = nullptr; a1.n = n;
+  a1.shift = 64 - RP_L1_LOG; a1.log_fan = RP_L1_LOG; a1.n_parents = 1;
+  a1.cursors = sc.rp_counts1.as<unsigned int>();
+  a1.out_keys = sc.p_keys.as<uint64_t>(); a1.out_vals = vals ? sc.p_vals.as<uint64_t>() : nullptr; a1.out_rows = sc.p_rows.as<uint32_t>();
+  CUDA_TRY(cudaFuncSetAttribute(k_rp_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RpSmem::TOTAL)));
+  k_rp_scatter<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a1);
+  CUDA_TRY(cudaGetLastError());
+  g->last_launches += 2;
+  BkArgs b{};
+  b.keys = sc.p_keys.as<uint64_t>(); b.vals = vals ? sc.p_vals.as<uint64_t>() : nullptr; b.rows = sc.p_rows.as<uint32_t>();
+  b.bucket_end = sc.rp_counts1.as<unsigned int>();
+  if (bits > RP_L1_LOG) {
+    // ---- level 2 inside every level-1 bucket ----
+    const int log_fan2 = bits - RP_L1_LOG;
+    PA_TRY(sc.rp_tiles.alloc(sizeof(uint32_t) * 1025, st));
+    PA_TRY(sc.rp_counts2.alloc(sizeof(uint32_t) * nb, st));
+    CUDA_TRY(cudaMemsetAsync(sc.rp_counts2.p, 0, sizeof(uint32_t) * nb, st));
+    k_rp_tiles<<<1, 1024, 0, st>>>(sc.rp_counts1.as<unsigned int>(), sc.rp_tiles.as<unsigned int>());
+    CUDA_TRY(cudaGetLastError());
+    RpArgs a2{};
+    a2.keys = sc.p_keys.as<uint64_t>(); a2.vals = b.vals; a2.rows = sc.p_rows.as<uint32_t>(); a2.n = n;
+    a2.shift = 64 - bits; a2.log_fan = log_fan2; a2.n_parents = 1024;
+    a2.parent_end = sc.rp_counts1.as<unsigned int>(); a2.tile_prefix = sc.rp_tiles.as<unsigned int>();
+    a2.cursors = sc.rp_counts2.as<unsigned int>();
+    k_rp_hist2<<<g->num_sms * 4, RP_THREADS, 0, st>>>(a2);
+    CUDA_TRY(cudaGetLastError());
+    PA_TRY(scan_u32_on(g, sc.rp_counts2.as<uint32_t>(), nb, &sc.tile_sums));
+    PA_TRY(sc.q_keys.alloc((static_cast<size_t>(n) + pad) * 8, st));
+    if (vals) PA_TRY(sc.q_vals.alloc((static_cast<size_t>(n) + pad) * 8, st));
+    PA_TRY(sc.q_rows.alloc((static_cast<size_t>(n) + pad) * 4, st));
+    a2.out_keys = sc.q_keys.as<uint64_t>(); a2.out_vals = vals ? sc.q_vals.as<uint64_t>() : nullptr; a2.out_rows = sc.q_rows.as<uint32_t>();
+    k_rp_scatter<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a2);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 6;
+    b.keys = sc.q_keys.as<uint64_t>(); b.vals = vals ? sc.q_vals.as<uint64_t>() : nullptr; b.rows = sc.q_rows.as<uint32_t>();
+    b.bucket_end = sc.rp_counts2.as<unsigned int>();
+  }
+  // ---- bucket aggregation ----
+  uint64_t u_cap64 = std::min<uint64_t>(static_cast<uint64_t>(n) + 1, plan + plan / 4 + 65536);
+  u_cap64 = std::min<uint64_t>(u_cap64, static_cast<uint64_t>(nb) * (T::MAX_KEYS + 1));
+  const uint32_t u_cap = static_cast<uint32_t>(std::min<uint64_t>(u_cap64, 0xFFFFFFF0ull));
+  PA_TRY(sc.u_key.alloc(static_cast<size_t>(u_cap) * 8, st));
+  PA_TRY(sc.u_sum.alloc(static_cast<size_t>(u_cap) * 8, st));
+  PA_TRY(sc.u_count.alloc(static_cast<size_t>(u_cap) * 4, st));
+  PA_TRY(sc.u_first.alloc(static_cast<size_t>(u_cap) * 4, st));
+  if (WIDE) {
+    PA_TRY(sc.u_last.alloc(static_cast<size_t>(u_cap) * 4, st));
+    PA_TRY(sc.u_min.alloc(static_cast<size_t>(u_cap) * 8, st));
+    PA_TRY(sc.u_max.alloc(static_cast<size_t>(u_cap) * 8, st));
+    if (VC != VC_F) PA_TRY(sc.u_dsum.alloc(static_cast<size_t>(u_cap) * 8, st));
+  }
+  PA_TRY(sc.rp_next.alloc(4, st));
+  CUDA_TRY(cudaMemsetAsync(sc.rp_next.p, 0, 4, st));
+  b.n_buckets = nb; b.part_bits = bits; b.next_bucket = sc.rp_next.as<unsigned int>();
+  b.agg_mask = mask; b.max_keys = T::MAX_KEYS;
+  b.u_key = sc.u_key.as<uint64_t>(); b.u_sum = sc.u_sum.as<uint64_t>(); b.u_count = sc.u_count.as<uint32_t>(); b.u_first = sc.u_first.as<uint32_t>();
+  b.u_last = WIDE ? sc.u_last.as<uint32_t>() : nullptr; b.u_min = WIDE ? sc.u_min.as<uint64_t>() : nullptr; b.u_max = WIDE ? sc.u_max.as<uint64_t>() : nullptr;
+  b.u_dsum = (WIDE && VC != VC_F) ? sc.u_dsum.as<double>() : nullptr;
+  b.u_cap = u_cap; b.status = g->status.as<uint32_t>();
+  {
+    auto kern = k_bucket_agg<VC, WIDE>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::TOTAL)));
+    kern<<<g->num_sms, BK_THREADS, T::TOTAL, st>>>(b);
+    CUDA_TRY(cudaGetLastError());
+  }
+  g->last_launches += 1;
+  CUDA_TRY(cudaEventRecord(g->ev[2], st));
+  uint32_t h_status[ST_WORDS];
+  CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_status[ST_OVERFLOW]) { *declined = true; return PA_OK; }
+  const uint32_t G = h_status[ST_COUNTER];
+  g->G = G;
+  PA_TRY(alloc_result(g, G, WIDE, VC != VC_F));
+  if (G > 0) {
+    // ---- first-appearance order by bitmap rank, written straight into the GroupResult ----
+    const uint64_t n_rows = static_cast<uint64_t>(std::max<int64_t>(n, 1));
+    const uint64_t nblocks = (n_rows + 32ull * BM_BLOCK_WORDS - 1) / (32ull * BM_BLOCK_WORDS);
+    const uint64_t nwords = nblocks * BM_BLOCK_WORDS;
+    const uint32_t ntiles = static_cast<uint32_t>((nblocks + SC_TILE - 1) / SC_TILE);
+    PA_TRY(sc.bitmap.alloc(nwords * 4, st));
+    PA_TRY(sc.prefix8.alloc(nblocks * 4, st));
+    PA_TRY(sc.tile_sums.alloc(static_cast<size_t>(std::max<uint32_t>(ntiles, 1)) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(sc.bitmap.p, 0, nwords * 4, st));
+    k_bm_set<<<(G + 255) / 256, 256, 0, st>>>(b.u_first, G, sc.bitmap.as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+    const int cgrid = static_cast<int>(std::min<uint64_t>((nblocks + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+    k_bm_count8<<<cgrid, 256, 0, st>>>(sc.bitmap.as<uint32_t>(), nblocks, sc.prefix8.as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+    k_scan_tiles<<<ntiles, 256, 0, st>>>(sc.prefix8.as<uint32_t>(), nblocks, sc.tile_sums.as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+    k_scan_sums<<<1, 256, 0, st>>>(sc.tile_sums.as<uint32_t>(), ntiles);
+    CUDA_TRY(cudaGetLastError());
+    k_scan_apply<<<ntiles, 256, 0, st>>>(sc.prefix8.as<uint32_t>(), nblocks, sc.tile_sums.as<uint32_t>());
+    CUDA_TRY(cudaGetLastError());
+    BkOrderArgs o{};
+    o.u_key = b.u_key; o.u_sum = b.u_sum; o.u_count = b.u_count; o.u_first = b.u_first; o.u_last = b.u_last;
+    o.u_min = b.u_min; o.u_max = b.u_max; o.u_dsum = b.u_dsum; o.G = G;
+    o.bitmap = sc.bitmap.as<uint32_t>(); o.prefix8 = sc.prefix8.as<uint32_t>(); o.out = g->res; o.wide = WIDE ? 1 : 0;
+    k_bm_rank_scatter<<<(G + 255) / 256, 256, 0, st>>>(o);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 6;
+  }
+  g->last_mode = 5;
+  g->last_rlog = bits;
+  CUDA_TRY(cudaEventRecord(g->ev[3], st));
+  return PA_OK;
+}
+
 template <int VC, bool WIDE>
 int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   using SlotT = typename SlotOf<WIDE>::type;
@@ -583,6 +776,19 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   if (cap > cap_limit) cap = cap_limit;
   DevBuf& table = g->scr.table;
   const int grid_full = g->num_sms * 6;   // two waves of the 3 resident CTAs per SM
+  {
+    // More groups than one shared-memory table holds (or nobody knows how many): partition into buckets and
+    // aggregate those in shared memory (bucketed.cuh); it declines when its own estimate says the front table is enough
+    const uint64_t known0 = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
+    const bool plain = g->key_width == 8 && (!val || val->width == 8) && !g->key_valid && (!val || !val->valid) &&
+                       reinterpret_cast<uintptr_t>(g->key_data) % 32 == 0 && (!val || reinterpret_cast<uintptr_t>(val->data) % 32 == 0);
+    if (plain && !g->opt.no_partition && g->n >= (1ll << 22) && (known0 == 0 || known0 > static_cast<uint64_t>(SmTab<VC, WIDE>::CAP))) {
+      bool declined = false;
+      PA_TRY((run_bucketed_t<VC, WIDE>(g, val, mask, &declined)));
+      if (!declined) return PA_OK;
+      g->last_mode = 0; g->last_rlog = 0;
+    }
+  }
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
   for (;;) {
     const uint64_t nslots = cap + 2;
@@ -1675,19 +1881,7 @@ int pa_groupby_row_ids(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema
 
 namespace {
 // device-wide exclusive scan of a uint32 array in place (order.cuh)
-int scan_u32(pa_groupby* g, uint32_t* data, uint64_t n, DevBuf* tile_sums) {
-  cudaStream_t st = g->stream;
-  const uint32_t ntiles = static_cast<uint32_t>((n + SC_TILE - 1) / SC_TILE);
-  PA_TRY(tile_sums->alloc(static_cast<size_t>(std::max<uint32_t>(ntiles, 1)) * 4, st));
-  if (n == 0) return PA_OK;
-  k_scan_tiles<<<ntiles, 256, 0, st>>>(data, n, tile_sums->as<uint32_t>());
-  CUDA_TRY(cudaGetLastError());
-  k_scan_sums<<<1, 256, 0, st>>>(tile_sums->as<uint32_t>(), ntiles);
-  CUDA_TRY(cudaGetLastError());
-  k_scan_apply<<<ntiles, 256, 0, st>>>(data, n, tile_sums->as<uint32_t>());
-  CUDA_TRY(cudaGetLastError());
-  return PA_OK;
-}
+int scan_u32(pa_groupby* g, uint32_t* data, uint64_t n, DevBuf* tile_sums) { return scan_u32_on(g, data, n, tile_sums); }
 
 // ids -> stable counting sort by id (csort.cuh) -> (order, dest, offsets), cached on the handle
 int ensure_groupings(pa_groupby* g) {
@@ -1816,6 +2010,13 @@ static int unique_strings(pa_groupby* g, struct ArrowArray* out, struct ArrowSch
   for (size_t i = 0; i < words; ++i) set += __builtin_popcount(static_cast<const uint32_t*>(priv->bufs[0])[i]);
   const int64_t null_count = static_cast<int64_t>(G) - set;
   if (null_count == 0) { free(priv->bufs[0]); priv->bufs[0] = nullptr; }
+  const bool large = k.str.wide != 0;      // large_utf8 in, large_utf8 out (int64 offsets, widened on the host: G + 1 numbers)
+  if (large) {
+    int64_t* wide = static_cast<int64_t*>(malloc(std::max<size_t>((static_cast<size_t>(G) + 1) * 8, 64)));
+    for (size_t i = 0; i <= G; ++i) wide[i] = static_cast<const uint32_t*>(priv->bufs[1])[i];
+    free(priv->bufs[1]);
+    priv->bufs[1] = wide;
+  }
   for (int i = 0; i < 3; ++i) priv->ptrs[i] = priv->bufs[i];
   memset(out, 0, sizeof *out);
   out->length = G;
@@ -1825,7 +2026,7 @@ static int unique_strings(pa_groupby* g, struct ArrowArray* out, struct ArrowSch
   out->release = release_array;
   out->private_data = priv;
   memset(out_schema, 0, sizeof *out_schema);
-  auto* f = new std::string("u");
+  auto* f = new std::string(large ? "U" : "u");
   out_schema->format = f->c_str();
   out_schema->name = "";
   out_schema->flags = ARROW_FLAG_NULLABLE;
@@ -2449,6 +2650,11 @@ int pa_comm_unique_id(void* out_id, int64_t capacity_bytes) {
 }
 
 static int comm_finish(pa_comm* c) {
+  // The communicator outlives the handles (and their streams) it is used with: its scratch does not belong to any
+  // stream's allocation order.
+  for (DevBuf* b : {&c->send, &c->recv, &c->d_counts, &c->d_all, &c->merge.tkeys, &c->merge.idx, &c->merge.m_first, &c->merge.m_slot,
+                    &c->merge.s_first, &c->merge.s_slot, &c->merge.cub_tmp})
+    b->plain = true;
   for (auto& e : c->ev) CUDA_TRY(cudaEventCreate(&e));
   return PA_OK;
 }

@@ -18,6 +18,10 @@ namespace pd {
 
 namespace {
 
+// arrow::compute's function registry (Take for dictionary keys / string group slices, and whatever a caller's apply
+// functors use — "add", "multiply" ...) has to be initialised once per process in Arrow >= 21.
+const bool g_compute_initialised = [] { return arrow::compute::Initialize().ok(); }();
+
 [[noreturn]] void throw_pa(const char* what) { throw std::runtime_error(std::string(what) + ": " + pa_last_error()); }
 
 arrow::Status pa_status(const char* what) { return arrow::Status::Invalid(what, ": ", pa_last_error()); }

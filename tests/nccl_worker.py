@@ -16,6 +16,8 @@ ALL = ["sum", "mean", "count", "min", "max", "first", "last"]
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()
     import torch
     import torch.distributed as dist
     import pandasarrow_b200 as pab

@@ -136,9 +136,56 @@ def test_config2_16m_groups_partition_path_vs_oracle(env):
         res = gb.aggregate(dv, aggs)
         ours = _np(gb.unique())
         t = gb.timing()
-    assert t["mode"] == "partitioned", t
+    assert t["mode"] == "bucketed", t
     assert np.array_equal(ours, _first_appearance(kh))
-    _cmp_vec(ours, res, ora, "v", aggs, "config 2 G=16M partitioned")
+    _cmp_vec(ours, res, ora, "v", aggs, "config 2 G=16M bucketed")
+    ora.close()
+
+
+@pytest.mark.parametrize("n,G,scattered,hint,ints,aggs", [
+    (6_000_000, 50_000, True, False, False, ["sum", "mean", "count"]),                                  # unknown G: sketch decides, one level
+    (6_000_000, 50_000, False, True, False, ["sum", "mean", "count", "min", "max", "first", "last"]),   # wide table
+    (8_000_000, 3_000_000, True, True, False, ["sum", "min", "max", "count"]),                          # two levels
+    (8_000_000, 3_000_000, False, False, True, ["sum", "mean", "count", "min", "max", "first", "last"]),   # two levels, integer values (double sum)
+    (5_000_000, 5_000_000, True, False, False, ["sum", "count", "first"]),                              # every key once
+])
+def test_bucketed_path_vs_oracle(env, n, G, scattered, hint, ints, aggs):
+    """bucketed.cuh (radix partition into buckets + shared-memory aggregation per bucket) against the oracle: one and
+    two partition levels, narrow and wide tables, hinted and sketch-estimated group counts, the sentinel key value."""
+    pab, orc, torch = env
+    k, v = _gen(pab, torch, n, G, scattered)
+    k[12345] = -7046029254386353131            # == kEmptyKey (0x9E3779B97F4A7C15): the table sentinel is a legal key
+    k[n - 1] = -7046029254386353131
+    if ints:
+        v = ((v * 2001.0).to(torch.int64) - 1000)
+    torch.cuda.synchronize()
+    kh, vh = k.cpu().numpy(), v.cpu().numpy()
+    rb = pa.record_batch({"k": pa.array(kh), "v": pa.array(vh)})
+    ora = orc.OracleGroupBy(rb, "k")
+    dk, dv = pab.DeviceColumn.from_torch(k), pab.DeviceColumn.from_torch(v)
+    with pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=G if hint else 0) as gb:
+        res = gb.aggregate(dv, aggs)
+        ours = _np(gb.unique())
+        t = gb.timing()
+        assert t["mode"] == "bucketed", t
+        ids = _np(gb.row_ids())
+        assert np.array_equal(ours[ids[:100000]], kh[:100000])
+    assert np.array_equal(ours, _first_appearance(kh)), "not in strict first-appearance order"
+    if ints:
+        for a in aggs:   # integer sums wrap exactly, means accumulate in double (1e-9 covers mixed signs, as in config 3)
+            want = ora.agg(a, "v", nthreads=THREADS)
+            so, st = np.argsort(ours, kind="stable"), np.argsort(_np(ora.unique()), kind="stable")
+            g_, w_ = _np(res[a])[so], _np(want)[st]
+            if a == "mean":
+                assert (np.abs(g_ - w_) <= 1e-9 * np.maximum(np.abs(w_), 1.0)).all()
+            else:
+                assert np.array_equal(g_, w_), a
+    else:
+        _cmp_vec(ours, res, ora, "v", aggs, f"bucketed n={n} G={G} scattered={scattered} hint={hint} bits={t['replication']}")
+    # a keys-only pass (group discovery without a value column) takes the same path
+    with pab.GroupBy("k", {"k": dk}, expected_groups=G if hint else 0) as gb2:
+        assert gb2.groupSize() == len(ours)
+        assert np.array_equal(_np(gb2.unique()), ours)
     ora.close()
 
 
