@@ -127,8 +127,9 @@ typedef struct pa_options {
   void* cuda_stream;         /* cudaStream_t to run on; NULL = a stream owned by the handle */
   int64_t row_base;          /* global row number of local row 0 (multi-GPU row-range shards) */
   int64_t lowcard_no_dense;  /* 1 = the shared-memory path never uses dense (key - base) addressing, always hashes */
-  int64_t no_partition;      /* 1 = never reorder the rows by table region before a global-table scan (>= 2 M groups) */
-  int64_t reserved[2];
+  int64_t no_partition;      /* 1 = never radix-partition the rows (bucketed path / table regions): plain global-table scan */
+  int64_t bucket_bits;       /* tuning / tests: 0 = automatic; else level-1 bits | level-2 bits << 8 of the bucketed path */
+  int64_t reserved[1];
 } pa_options;
 
 typedef struct pa_groupby pa_groupby;      /* opaque: key columns + device group table */

@@ -38,9 +38,13 @@ namespace pa {
 constexpr int RP_THREADS = 512;
 constexpr int RP_ROWS = 8;                            // rows per thread
 constexpr int RP_TILE = RP_THREADS * RP_ROWS;         // 4096 rows per tile
+constexpr int RP_CHUNK_TILES = 16;
+constexpr int RP_CHUNK_ROWS = RP_TILE * RP_CHUNK_TILES;   // rows per chunk (the unit of the offset bookkeeping)
 constexpr int RP_MAX_FAN = 1024;
 constexpr int RP_L1_LOG = 10;                         // level 1 always splits 1024 ways
 constexpr int RP_MAX_BITS = 20;                       // at most 2^20 buckets
+constexpr int RP_SINGLE_MAX_LOG = 7;                  // one level up to 128 buckets: the scatter slows down with its fan-out (runs of
+                                                      // 4096 / fan rows: 7.7 / 8.4 / 10.5 / 15 / 25 / 43 ms per 1 B rows at 32 ... 1024)
 constexpr int RH_THREADS = 1024;
 constexpr int HLL_LOG2 = 12;
 constexpr int HLL_M = 1 << HLL_LOG2;
@@ -62,11 +66,65 @@ __device__ __forceinline__ uint32_t ldg_stream_u32_na(const void* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// level 1 histogram + HyperLogLog
+// partition: chunks, histograms, offsets, scatter — no global atomics, stable, deterministic
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rp_hist1_one(uint64_t key, unsigned int* s_hist, unsigned int* s_hll) {
-  const uint64_t m = rp_mix(key);
-  atomicAdd(&s_hist[m >> (64 - RP_L1_LOG)], 1u);
+// A level splits every PARENT range of rows (level 1: the whole input; level 2: every level-1 bucket) `fan` ways.
+// Parents are cut into CHUNKS of RP_CHUNK_ROWS consecutive rows (the last one of a parent ragged).  The histogram
+// kernel counts rows per (chunk, bucket); the counts are laid out "flat" as
+//     flat[cbase_p * fan + bucket * chunks_p + chunk_in_parent]        (cbase_p = chunks of the parents before p)
+// so that ONE exclusive scan of the flat array yields, for every chunk, the absolute output position of its first row
+// of every bucket: buckets of a parent follow each other, chunks inside a bucket follow each other in row order.
+// The scatter kernel loads a chunk's `fan` cursors into shared memory and advances them privately tile by tile.
+struct RpArgs {
+  const uint64_t* keys;
+  const uint64_t* vals;          // may be null (keys-only pass)
+  const uint32_t* rows;          // original row numbers of the source rows; null = the source IS the original order
+  int64_t n;
+  int shift;                     // bucket inside the parent = (rp_mix(key) >> shift) & (fan - 1)
+  int log_fan;
+  int n_parents;                 // 1 (level 1) or the number of level-1 buckets
+  const unsigned int* parent_end;   // [n_parents] end of every parent in the source order; null for level 1
+  const unsigned int* cprefix;      // [n_parents + 1] chunks before parent p; null for level 1
+  unsigned int n_chunks1;        // level 1: number of chunks
+  unsigned int* counts;          // histogram out — level 1: fine counts [chunk][1024]; level 2: the flat layout
+  const unsigned int* offsets;   // scatter in: the scanned flat layout
+  unsigned int* hll;             // level 1 histogram: sketch registers
+  uint64_t* out_keys;
+  uint64_t* out_vals;
+  uint32_t* out_rows;
+};
+
+struct RpChunk { uint32_t cl, chunks_p, cbase; int64_t row0; int cnt; };
+
+__device__ __forceinline__ uint32_t rp_num_chunks(const RpArgs& a) {
+  return a.cprefix ? a.cprefix[a.n_parents] : a.n_chunks1;
+}
+
+__device__ __forceinline__ RpChunk rp_chunk(const RpArgs& a, uint32_t c) {
+  RpChunk r;
+  if (!a.cprefix) {
+    r.cl = c; r.chunks_p = a.n_chunks1; r.cbase = 0;
+    r.row0 = static_cast<int64_t>(c) * RP_CHUNK_ROWS;
+    const int64_t left = a.n - r.row0;
+    r.cnt = left < RP_CHUNK_ROWS ? static_cast<int>(left) : RP_CHUNK_ROWS;
+    return r;
+  }
+  uint32_t lo = 0, hi = static_cast<uint32_t>(a.n_parents);      // largest p with cprefix[p] <= c
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(a.cprefix + mid) <= c) lo = mid; else hi = mid;
+  }
+  const uint32_t start = lo ? __ldg(a.parent_end + lo - 1) : 0u, end = __ldg(a.parent_end + lo);
+  r.cbase = __ldg(a.cprefix + lo);
+  r.chunks_p = __ldg(a.cprefix + lo + 1) - r.cbase;
+  r.cl = c - r.cbase;
+  r.row0 = static_cast<int64_t>(start) + static_cast<int64_t>(r.cl) * RP_CHUNK_ROWS;
+  const int64_t left = static_cast<int64_t>(end) - r.row0;
+  r.cnt = left < RP_CHUNK_ROWS ? static_cast<int>(left) : RP_CHUNK_ROWS;
+  return r;
+}
+
+__device__ __forceinline__ void rp_hll_add(uint64_t m, unsigned int* s_hll) {
   uint64_t h = (m ^ (m >> 29)) * 0xBF58476D1CE4E5B9ull;
   h ^= h >> 32;
   if ((h & ((1u << HLL_SAMPLE_LOG2) - 1u)) == 0) {
@@ -77,139 +135,89 @@ __device__ __forceinline__ void rp_hist1_one(uint64_t key, unsigned int* s_hist,
   }
 }
 
-__global__ void __launch_bounds__(RH_THREADS) k_rp_hist1(const uint64_t* keys, int64_t n, unsigned int* counts, unsigned int* hll) {
-  __shared__ unsigned int s_hist[1 << RP_L1_LOG];
-  __shared__ unsigned int s_hll[HLL_M];
-  for (int i = threadIdx.x; i < (1 << RP_L1_LOG); i += RH_THREADS) s_hist[i] = 0;
-  for (int i = threadIdx.x; i < HLL_M; i += RH_THREADS) s_hll[i] = 0;
-  __syncthreads();
-  const int64_t n2 = n / 2;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(RH_THREADS) + threadIdx.x; i < n2; i += static_cast<int64_t>(gridDim.x) * RH_THREADS) {
-    const ulonglong2 k = ldg_stream_u64x2(keys + 2 * i);
-    rp_hist1_one(k.x, s_hist, s_hll);
-    rp_hist1_one(k.y, s_hist, s_hll);
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) rp_hist1_one(keys[n - 1], s_hist, s_hll);
-  __syncthreads();
-  for (int i = threadIdx.x; i < (1 << RP_L1_LOG); i += RH_THREADS)
-    if (s_hist[i]) atomicAdd(counts + i, s_hist[i]);
-  for (int i = threadIdx.x; i < HLL_M; i += RH_THREADS)
-    if (s_hll[i]) atomicMax(hll + i, s_hll[i]);
-}
-
-// one CTA of 1024 threads: counts -> exclusive prefix (in place)
-__global__ void __launch_bounds__(1024) k_rp_offsets1(unsigned int* counts) {
-  __shared__ unsigned int s[1024];
-  const int t = threadIdx.x;
-  const unsigned int own = counts[t];
-  s[t] = own;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    const unsigned int v = t >= d ? s[t - d] : 0u;
-    __syncthreads();
-    s[t] += v;
-    __syncthreads();
-  }
-  counts[t] = s[t] - own;
-}
-
-// after the level-1 scatter `ends[p]` is the end of bucket p: tiles per bucket -> exclusive prefix [1025]
-__global__ void __launch_bounds__(1024) k_rp_tiles(const unsigned int* ends, unsigned int* tile_prefix) {
-  __shared__ unsigned int s[1024];
-  const int t = threadIdx.x;
-  const unsigned int start = t ? ends[t - 1] : 0u;
-  const unsigned int own = (ends[t] - start + RP_TILE - 1) / RP_TILE;
-  s[t] = own;
-  __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {
-    const unsigned int v = t >= d ? s[t - d] : 0u;
-    __syncthreads();
-    s[t] += v;
-    __syncthreads();
-  }
-  tile_prefix[t] = s[t] - own;
-  if (t == 1023) tile_prefix[1024] = s[t];
-}
-
-// ---------------------------------------------------------------------------------------------
-// tiles
-// ---------------------------------------------------------------------------------------------
-struct RpArgs {
-  const uint64_t* keys;
-  const uint64_t* vals;          // may be null (keys-only pass)
-  const uint32_t* rows;          // original row numbers of the source rows; null = the source IS the original order
-  int64_t n;
-  int shift;                     // bucket inside the parent = (rp_mix(key) >> shift) & (fan - 1)
-  int log_fan;
-  int n_parents;                 // 1 (level 1) or 1024 (level 2)
-  const unsigned int* parent_end;    // [n_parents] end of every parent in the source order; null for level 1
-  const unsigned int* tile_prefix;   // [n_parents + 1]; null for level 1
-  unsigned int* cursors;         // [n_parents << log_fan] write cursors (level-2 histogram: counts)
-  uint64_t* out_keys;
-  uint64_t* out_vals;
-  uint32_t* out_rows;
-};
-
-struct RpTile { uint32_t parent; int64_t row0; int cnt; };
-
-__device__ __forceinline__ uint32_t rp_num_tiles(const RpArgs& a) {
-  return a.parent_end ? a.tile_prefix[a.n_parents] : static_cast<uint32_t>((a.n + RP_TILE - 1) / RP_TILE);
-}
-
-__device__ __forceinline__ RpTile rp_tile(const RpArgs& a, uint32_t t) {
-  RpTile r;
-  if (!a.parent_end) {
-    r.parent = 0;
-    r.row0 = static_cast<int64_t>(t) * RP_TILE;
-    const int64_t left = a.n - r.row0;
-    r.cnt = left < RP_TILE ? static_cast<int>(left) : RP_TILE;
-    return r;
-  }
-  uint32_t lo = 0, hi = static_cast<uint32_t>(a.n_parents);      // largest p with tile_prefix[p] <= t
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(a.tile_prefix + mid) <= t) lo = mid; else hi = mid;
-  }
-  const uint32_t start = lo ? __ldg(a.parent_end + lo - 1) : 0u, end = __ldg(a.parent_end + lo);
-  r.parent = lo;
-  r.row0 = static_cast<int64_t>(start) + static_cast<int64_t>(t - __ldg(a.tile_prefix + lo)) * RP_TILE;
-  const int64_t left = static_cast<int64_t>(end) - r.row0;
-  r.cnt = left < RP_TILE ? static_cast<int>(left) : RP_TILE;
-  return r;
-}
-
-// level 2 histogram: every CTA takes a contiguous range of tiles; the shared-memory histogram covers the sub-buckets
-// of the current parent and is flushed when the range moves on to the next one
-__global__ void __launch_bounds__(RP_THREADS) k_rp_hist2(RpArgs a) {
+// Rows per (chunk, bucket).  L1: 1024 fine buckets (the top 10 bits of the mix; the host folds them to the fan-out it
+// picks once the sketch has told it how many groups there are) + the HyperLogLog sketch.
+template <bool L1>
+__global__ void __launch_bounds__(RH_THREADS) k_rp_hist(RpArgs a) {
   __shared__ unsigned int s_hist[RP_MAX_FAN];
-  const uint32_t ntiles = rp_num_tiles(a);
-  const uint32_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-  const uint32_t t0 = blockIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
-  const int fan = 1 << a.log_fan;
-  uint32_t cur = 0xFFFFFFFFu;
-  for (uint32_t t = t0; t < t1; ++t) {
-    const RpTile tl = rp_tile(a, t);
-    if (tl.parent != cur) {
-      __syncthreads();
-      if (cur != 0xFFFFFFFFu) {
-        for (int i = threadIdx.x; i < fan; i += RP_THREADS)
-          if (s_hist[i]) atomicAdd(a.cursors + (static_cast<size_t>(cur) << a.log_fan) + i, s_hist[i]);
-        __syncthreads();
+  __shared__ unsigned int s_hll[L1 ? HLL_M : 1];
+  const int fan = L1 ? RP_MAX_FAN : (1 << a.log_fan);
+  const uint32_t nchunks = rp_num_chunks(a);
+  if constexpr (L1) {
+    for (int i = threadIdx.x; i < HLL_M; i += RH_THREADS) s_hll[i] = 0;
+  }
+  for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    for (int i = threadIdx.x; i < fan; i += RH_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const RpChunk ch = rp_chunk(a, c);
+    const uint64_t* kp = a.keys + ch.row0;
+#pragma unroll 4
+    for (int r = threadIdx.x; r < ch.cnt; r += RH_THREADS) {
+      const uint64_t m = rp_mix(ldg_stream_u64_na(kp + r));
+      if constexpr (L1) {
+        atomicAdd(&s_hist[m >> (64 - RP_L1_LOG)], 1u);
+        rp_hll_add(m, s_hll);
+      } else {
+        atomicAdd(&s_hist[static_cast<uint32_t>(m >> a.shift) & (fan - 1)], 1u);
       }
-      for (int i = threadIdx.x; i < fan; i += RP_THREADS) s_hist[i] = 0;
-      __syncthreads();
-      cur = tl.parent;
     }
-    for (int r = threadIdx.x; r < tl.cnt; r += RP_THREADS) {
-      const uint64_t m = rp_mix(ldg_stream_u64_na(a.keys + tl.row0 + r));
-      atomicAdd(&s_hist[static_cast<uint32_t>(m >> a.shift) & (fan - 1)], 1u);
+    __syncthreads();
+    if constexpr (L1) {
+      for (int i = threadIdx.x; i < fan; i += RH_THREADS) a.counts[static_cast<size_t>(c) * RP_MAX_FAN + i] = s_hist[i];
+    } else {
+      unsigned int* dst = a.counts + static_cast<size_t>(ch.cbase) * fan + ch.cl;
+      for (int i = threadIdx.x; i < fan; i += RH_THREADS) dst[static_cast<size_t>(i) * ch.chunks_p] = s_hist[i];
     }
+    __syncthreads();
   }
+  if constexpr (L1) {
+    for (int i = threadIdx.x; i < HLL_M; i += RH_THREADS)
+      if (s_hll[i]) atomicMax(a.hll + i, s_hll[i]);
+  }
+}
+
+// level 1: fine counts [chunk][1024] -> flat[bucket * n_chunks + chunk] with 2^b1 buckets (bucket = fine >> (10 - b1))
+__global__ void __launch_bounds__(256) k_rp_fold(const unsigned int* fine, uint32_t n_chunks, int b1, unsigned int* flat) {
+  const uint64_t i = blockIdx.x * 256ull + threadIdx.x;
+  const uint32_t c = static_cast<uint32_t>(i >> b1), B = static_cast<uint32_t>(i) & ((1u << b1) - 1u);
+  if (c >= n_chunks) return;
+  const int s = RP_L1_LOG - b1;
+  const unsigned int* src = fine + static_cast<size_t>(c) * RP_MAX_FAN + (static_cast<size_t>(B) << s);
+  unsigned int sum = 0;
+  for (int j = 0; j < (1 << s); ++j) sum += src[j];
+  flat[static_cast<size_t>(B) * n_chunks + c] = sum;
+}
+
+// ends[parent << log_fan | bucket] = end of that bucket in the output order, read off the scanned flat layout (which
+// carries one extra entry holding n)
+__global__ void __launch_bounds__(256) k_rp_ends(RpArgs a, unsigned int* ends) {
+  const uint32_t e = blockIdx.x * 256u + threadIdx.x;
+  if (e >= (static_cast<uint32_t>(a.n_parents) << a.log_fan)) return;
+  const uint32_t p = e >> a.log_fan, sb = e & ((1u << a.log_fan) - 1u);
+  const uint32_t cbase = a.cprefix ? a.cprefix[p] : 0u;
+  const uint32_t chunks_p = a.cprefix ? a.cprefix[p + 1] - cbase : a.n_chunks1;
+  ends[e] = a.offsets[(static_cast<size_t>(cbase) << a.log_fan) + static_cast<size_t>(sb + 1) * chunks_p];
+}
+
+// chunks per parent -> exclusive prefix [n_parents + 1] (n_parents <= 1024)
+__global__ void __launch_bounds__(1024) k_rp_cprefix(const unsigned int* ends, int n_parents, unsigned int* cprefix) {
+  __shared__ unsigned int s[1024];
+  const int t = threadIdx.x;
+  unsigned int own = 0;
+  if (t < n_parents) {
+    const unsigned int start = t ? ends[t - 1] : 0u;
+    own = (ends[t] - start + RP_CHUNK_ROWS - 1) / RP_CHUNK_ROWS;
+  }
+  s[t] = own;
   __syncthreads();
-  if (cur != 0xFFFFFFFFu) {
-    for (int i = threadIdx.x; i < fan; i += RP_THREADS)
-      if (s_hist[i]) atomicAdd(a.cursors + (static_cast<size_t>(cur) << a.log_fan) + i, s_hist[i]);
+  for (int d = 1; d < 1024; d <<= 1) {
+    const unsigned int v = t >= d ? s[t - d] : 0u;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
   }
+  if (t < n_parents) cprefix[t] = s[t] - own;
+  if (t == n_parents - 1) cprefix[n_parents] = s[t];
 }
 
 struct RpSmem {
@@ -219,11 +227,12 @@ struct RpSmem {
   static constexpr size_t OFF_HIST = OFF_ROW + sizeof(uint32_t) * RP_TILE;
   static constexpr size_t OFF_OFF = OFF_HIST + sizeof(uint32_t) * RP_MAX_FAN;
   static constexpr size_t OFF_DELTA = OFF_OFF + sizeof(uint32_t) * RP_MAX_FAN;
-  static constexpr size_t TOTAL = OFF_DELTA + sizeof(uint32_t) * RP_MAX_FAN;
+  static constexpr size_t OFF_CUR = OFF_DELTA + sizeof(uint32_t) * RP_MAX_FAN;
+  static constexpr size_t TOTAL = OFF_CUR + sizeof(uint32_t) * RP_MAX_FAN;
 };
-static_assert(2 * (RpSmem::TOTAL + 1024) <= 228 * 1024, "two scatter CTAs per SM");
+static_assert(2 * (RpSmem::TOTAL + 1024) <= 227 * 1024, "two scatter CTAs per SM");
 
-// Two CTAs per SM: the phases of a tile are separated by barriers (load -> rank -> claim -> regroup -> write), so a
+// Two CTAs per SM: the phases of a tile are separated by barriers (load -> rank -> offsets -> regroup -> write), so a
 // second resident CTA keeps the memory system busy while the first one regroups.
 __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(RpArgs a) {
   extern __shared__ __align__(16) unsigned char rp_smem[];
@@ -234,103 +243,113 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(RpArgs a) {
   unsigned int* s_off = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_OFF);
   // s_delta[b] = (start of this tile's run for b in the output) - (start of the run in the regrouped tile)
   unsigned int* s_delta = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_DELTA);
+  unsigned int* s_cur = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_CUR);   // this chunk's write cursors
   __shared__ unsigned int s_wsum[RP_THREADS / 32];
   constexpr int BINS = RP_MAX_FAN / RP_THREADS;      // histogram bins per thread in the scan
   const int fan = 1 << a.log_fan;
-  const uint32_t ntiles = rp_num_tiles(a);
-  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const RpTile tl = rp_tile(a, t);
-    unsigned int* cursors = a.cursors + (static_cast<size_t>(tl.parent) << a.log_fan);
-    for (int i = threadIdx.x; i < fan; i += RP_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    uint64_t key[RP_ROWS], val[RP_ROWS];
-    uint32_t pr[RP_ROWS];    // bucket << 13 | rank inside the tile's run for that bucket
-#pragma unroll
-    for (int j = 0; j < RP_ROWS; ++j) {
-      const int r = threadIdx.x + j * RP_THREADS;
-      key[j] = 0; val[j] = 0;
-      if (r < tl.cnt) {
-        key[j] = ldg_stream_u64_na(a.keys + tl.row0 + r);
-        if (a.vals) val[j] = ldg_stream_u64_na(a.vals + tl.row0 + r);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < RP_ROWS; ++j) {
-      const int r = threadIdx.x + j * RP_THREADS;
-      pr[j] = 0xFFFFFFFFu;
-      if (r < tl.cnt) {
-        const uint32_t b = static_cast<uint32_t>(rp_mix(key[j]) >> a.shift) & (fan - 1);
-        pr[j] = (b << 13) | atomicAdd(&s_hist[b], 1u);
-      }
-    }
-    __syncthreads();
-    // exclusive scan of the tile histogram (BINS adjacent bins per thread) + claim the output ranges
+  const uint32_t nchunks = rp_num_chunks(a);
+  for (uint32_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const RpChunk ch = rp_chunk(a, c);
     {
-      unsigned int mine[BINS], tot = 0;
-#pragma unroll
-      for (int b = 0; b < BINS; ++b) {
-        const int bin = threadIdx.x * BINS + b;
-        mine[b] = bin < fan ? s_hist[bin] : 0u;
-        tot += mine[b];
-      }
-      unsigned int incl = tot;
-      const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= static_cast<uint32_t>(d)) incl += v;
-      }
-      if (lane == 31) s_wsum[w] = incl;
+      const unsigned int* src = a.offsets + (static_cast<size_t>(ch.cbase) << a.log_fan) + ch.cl;
+      for (int i = threadIdx.x; i < fan; i += RP_THREADS) s_cur[i] = src[static_cast<size_t>(i) * ch.chunks_p];
+    }
+    for (int t0 = 0; t0 < ch.cnt; t0 += RP_TILE) {
+      const int64_t row0 = ch.row0 + t0;
+      const int cnt = ch.cnt - t0 < RP_TILE ? ch.cnt - t0 : RP_TILE;
+      for (int i = threadIdx.x; i < fan; i += RP_THREADS) s_hist[i] = 0;
       __syncthreads();
-      if (w == 0) {
-        unsigned int x = lane < RP_THREADS / 32 ? s_wsum[lane] : 0u;
+      uint64_t key[RP_ROWS], val[RP_ROWS];
+      uint32_t pr[RP_ROWS];    // bucket << 13 | rank inside the tile's run for that bucket
+#pragma unroll
+      for (int j = 0; j < RP_ROWS; ++j) {
+        const int r = threadIdx.x + j * RP_THREADS;
+        key[j] = 0; val[j] = 0;
+        if (r < cnt) {
+          key[j] = ldg_stream_u64_na(a.keys + row0 + r);
+          if (a.vals) val[j] = ldg_stream_u64_na(a.vals + row0 + r);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RP_ROWS; ++j) {
+        const int r = threadIdx.x + j * RP_THREADS;
+        pr[j] = 0xFFFFFFFFu;
+        if (r < cnt) {
+          const uint32_t b = static_cast<uint32_t>(rp_mix(key[j]) >> a.shift) & (fan - 1);
+          pr[j] = (b << 13) | atomicAdd(&s_hist[b], 1u);
+        }
+      }
+      __syncthreads();
+      // exclusive scan of the tile histogram (BINS adjacent bins per thread); the output ranges come from the chunk's
+      // private cursors (every bin is owned by one thread)
+      {
+        unsigned int mine[BINS], tot = 0;
+#pragma unroll
+        for (int b = 0; b < BINS; ++b) {
+          const int bin = threadIdx.x * BINS + b;
+          mine[b] = bin < fan ? s_hist[bin] : 0u;
+          tot += mine[b];
+        }
+        unsigned int incl = tot;
+        const uint32_t lane = lane_id(), w = threadIdx.x >> 5;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, x, d);
-          if (lane >= static_cast<uint32_t>(d)) x += v;
+          const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+          if (lane >= static_cast<uint32_t>(d)) incl += v;
         }
-        if (lane < RP_THREADS / 32) s_wsum[lane] = x;
+        if (lane == 31) s_wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+          unsigned int x = lane < RP_THREADS / 32 ? s_wsum[lane] : 0u;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= static_cast<uint32_t>(d)) x += v;
+          }
+          if (lane < RP_THREADS / 32) s_wsum[lane] = x;
+        }
+        __syncthreads();
+        unsigned int excl = incl - tot + (w ? s_wsum[w - 1] : 0u);
+#pragma unroll
+        for (int b = 0; b < BINS; ++b) {
+          const int bin = threadIdx.x * BINS + b;
+          if (bin < fan) {
+            s_off[bin] = excl;
+            const unsigned int base = s_cur[bin];
+            s_delta[bin] = base - excl;
+            s_cur[bin] = base + mine[b];
+          }
+          excl += mine[b];
+        }
       }
       __syncthreads();
-      unsigned int excl = incl - tot + (w ? s_wsum[w - 1] : 0u);
+      // regroup the tile in shared memory (the original row numbers are fetched only now: 64 registers per thread)
+      uint32_t row[RP_ROWS];
 #pragma unroll
-      for (int b = 0; b < BINS; ++b) {
-        const int bin = threadIdx.x * BINS + b;
-        if (bin < fan) {
-          s_off[bin] = excl;
-          const unsigned int base = mine[b] ? atomicAdd(cursors + bin, mine[b]) : 0u;
-          s_delta[bin] = base - excl;
-        }
-        excl += mine[b];
+      for (int j = 0; j < RP_ROWS; ++j) {
+        const int r = threadIdx.x + j * RP_THREADS;
+        row[j] = static_cast<uint32_t>(row0 + r);
+        if (a.rows && pr[j] != 0xFFFFFFFFu) row[j] = ldg_stream_u32_na(a.rows + row0 + r);
       }
-    }
-    __syncthreads();
-    // regroup the tile in shared memory (the original row numbers are fetched only now: 64 registers per thread)
-    uint32_t row[RP_ROWS];
 #pragma unroll
-    for (int j = 0; j < RP_ROWS; ++j) {
-      const int r = threadIdx.x + j * RP_THREADS;
-      row[j] = static_cast<uint32_t>(tl.row0 + r);
-      if (a.rows && pr[j] != 0xFFFFFFFFu) row[j] = ldg_stream_u32_na(a.rows + tl.row0 + r);
+      for (int j = 0; j < RP_ROWS; ++j) {
+        if (pr[j] == 0xFFFFFFFFu) continue;
+        const uint32_t pos = s_off[pr[j] >> 13] + (pr[j] & 0x1FFFu);
+        st_key[pos] = key[j];
+        st_val[pos] = val[j];
+        st_row[pos] = row[j];
+      }
+      __syncthreads();
+      // contiguous runs out (the bucket of a regrouped row is recomputed from its key)
+      for (int i = threadIdx.x; i < cnt; i += RP_THREADS) {
+        const uint64_t k = st_key[i];
+        const unsigned int d = s_delta[static_cast<uint32_t>(rp_mix(k) >> a.shift) & (fan - 1)] + static_cast<unsigned int>(i);
+        a.out_keys[d] = k;
+        if (a.vals) a.out_vals[d] = st_val[i];
+        a.out_rows[d] = st_row[i];
+      }
+      __syncthreads();
     }
-#pragma unroll
-    for (int j = 0; j < RP_ROWS; ++j) {
-      if (pr[j] == 0xFFFFFFFFu) continue;
-      const uint32_t pos = s_off[pr[j] >> 13] + (pr[j] & 0x1FFFu);
-      st_key[pos] = key[j];
-      st_val[pos] = val[j];
-      st_row[pos] = row[j];
-    }
-    __syncthreads();
-    // contiguous runs out (the bucket of a regrouped row is recomputed from its key)
-    for (int i = threadIdx.x; i < tl.cnt; i += RP_THREADS) {
-      const uint64_t k = st_key[i];
-      const unsigned int d = s_delta[static_cast<uint32_t>(rp_mix(k) >> a.shift) & (fan - 1)] + static_cast<unsigned int>(i);
-      a.out_keys[d] = k;
-      if (a.vals) a.out_vals[d] = st_val[i];
-      a.out_rows[d] = st_row[i];
-    }
-    __syncthreads();
   }
 }
 
@@ -358,6 +377,14 @@ struct BkArgs {
   double* u_dsum;
   uint32_t u_cap;
   uint32_t* status;              // ST_OVERFLOW, ST_COUNTER (groups appended)
+  // ranged mode (fewer buckets than would keep every SM busy): every CTA takes an equal, contiguous share of the
+  // partitioned rows and flushes its table into the global table (gtable.cuh) whenever its rows move on to the next
+  // bucket; a bucket shared by several CTAs is merged there by the L2 atomics (a few per group and CTA, not per row)
+  int ranged;
+  int64_t n;
+  void* table;
+  uint64_t cap_mask;
+  int shift;
 };
 
 template <int VC, bool WIDE>
@@ -383,16 +410,44 @@ __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
   }
   if (threadIdx.x < 4) s_misc[threadIdx.x] = 0u;
   __syncthreads();
-  for (;;) {
-    if (threadIdx.x == 0) {
-      s_misc[1] = atomicAdd(a.next_bucket, 1u);
-      s_misc[3] = 0u;
+  using SlotT = typename SlotOf<WIDE>::type;
+  constexpr int SLOT_LOG2 = WIDE ? 6 : 5;
+  int64_t lo_c = 0, hi_c = 0;
+  uint32_t bcur = 0;
+  if (a.ranged) {
+    const int64_t per = ((a.n + gridDim.x - 1) / gridDim.x + 3) & ~3ll;
+    lo_c = static_cast<int64_t>(blockIdx.x) * per;
+    hi_c = lo_c + per < a.n ? lo_c + per : a.n;
+    uint32_t l = 0, h = a.n_buckets;                       // first bucket that ends after lo_c
+    while (l < h) {
+      const uint32_t mid = (l + h) >> 1;
+      if (static_cast<int64_t>(a.bucket_end[mid]) > lo_c) h = mid; else l = mid + 1;
     }
-    __syncthreads();
-    const uint32_t b = s_misc[1];
-    if (b >= a.n_buckets) break;
-    if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) break;
-    const uint32_t start = b ? a.bucket_end[b - 1] : 0u, end = a.bucket_end[b];
+    bcur = l;
+  }
+  for (;;) {
+    uint32_t b, start, end;
+    if (!a.ranged) {
+      if (threadIdx.x == 0) {
+        s_misc[1] = atomicAdd(a.next_bucket, 1u);
+        s_misc[3] = 0u;
+      }
+      __syncthreads();
+      b = s_misc[1];
+      if (b >= a.n_buckets) break;
+      if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) break;
+      start = b ? a.bucket_end[b - 1] : 0u;
+      end = a.bucket_end[b];
+    } else {
+      b = bcur++;
+      if (b >= a.n_buckets || lo_c >= hi_c) break;
+      if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) break;
+      const int64_t be = a.bucket_end[b];
+      start = static_cast<uint32_t>(lo_c);
+      end = static_cast<uint32_t>(be < hi_c ? be : hi_c);
+      lo_c = end;
+      if (start >= end) continue;
+    }
     bool failed = false;
     for (uint64_t base = (start & ~3u) + 4u * threadIdx.x; base < end; base += 4u * BK_THREADS) {
       const u64x4 k4 = ldg_stream_u64x4(a.keys + base);
@@ -449,6 +504,46 @@ __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
     if (failed) atomicExch(a.status + ST_OVERFLOW, 1u);
     __syncthreads();
     if (*reinterpret_cast<volatile uint32_t*>(a.status + ST_OVERFLOW)) break;
+    if (a.ranged) {
+      // ---- flush into the global table, resetting the slots in the same sweep ----
+      SlotT* table = static_cast<SlotT*>(a.table);
+      const uint64_t cap = a.cap_mask + 1;
+      for (int i = threadIdx.x; i < T::NSLOT; i += BK_THREADS) {
+        const uint32_t first = s_first[i];
+        if (first == kNoRow) continue;
+        const uint64_t fkey = s_key[i];
+        uint64_t sl = i == T::CAP + 1 ? cap + 1 : gtable_home(fkey, a.shift);
+        const Sector kf = gtable_peek<WIDE>(table, sl, SLOT_LOG2);
+        GProbe pr;
+        if (sl >= cap) pr = GProbe{sl, static_cast<uint32_t>(kf.fl), static_cast<uint32_t>(kf.fl >> 32), kf.mn, kf.mx};
+        else pr = gtable_find_or_insert<WIDE>(table, a.cap_mask, SLOT_LOG2, fkey, sl, kf);
+        if (pr.slot == ~0ull) { atomicExch(a.status + ST_OVERFLOW, 1u); break; }
+        SlotT* g = table + pr.slot;
+        if (first < pr.first) atomicMin(&g->first_row, first);
+        const uint32_t c = s_cnt[i];
+        if (c) {
+          atomicAdd(&g->count, c);
+          if constexpr (VC == VC_F) atomicAdd(reinterpret_cast<double*>(&g->sum), __longlong_as_double(static_cast<long long>(s_sum[i])));
+          else atomicAdd(reinterpret_cast<unsigned long long*>(&g->sum), s_sum[i]);
+        }
+        if constexpr (WIDE) {
+          if ((a.agg_mask & AGG_LAST) && s_last[i] > pr.last) atomicMax(&g->last_row, s_last[i]);
+          if (s_mn[i] < pr.mn) atomicMin(reinterpret_cast<unsigned long long*>(&g->min_ord), s_mn[i]);
+          if (s_mx[i] > pr.mx) atomicMax(reinterpret_cast<unsigned long long*>(&g->max_ord), s_mx[i]);
+          if constexpr (T::DSUM) { if (c) atomicAdd(&g->dsum, s_dsum[i]); }
+        }
+        s_key[i] = kEmptyKey;
+        s_sum[i] = 0ull;
+        s_cnt[i] = 0u;
+        s_first[i] = kNoRow;
+        if constexpr (WIDE) { s_mn[i] = kMinInit; s_mx[i] = kMaxInit; s_last[i] = 0u; }
+        if constexpr (T::DSUM) s_dsum[i] = 0.0;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_misc[0] = 0u;
+      __syncthreads();
+      continue;
+    }
     // ---- append this bucket's groups, resetting the slots in the same sweep ----
     if (threadIdx.x == 0) {
       const uint32_t total = s_misc[0] + (s_first[T::CAP + 1] != kNoRow ? 1u : 0u);

@@ -374,9 +374,11 @@ struct pa_groupby {
   struct Scratch {
     DevBuf table, p_keys, p_vals, p_rows, p_counts, krange, c_first, c_slot, s_first, s_slot, cub_tmp, bnd, bitmap, prefix8, tile_sums;
     // bucketed path (bucketed.cuh): second-level rows, histograms / cursors, sketch, unordered groups
-    DevBuf q_keys, q_vals, q_rows, rp_counts1, rp_counts2, rp_tiles, rp_hll, rp_next, u_key, u_sum, u_count, u_first, u_last, u_min, u_max, u_dsum;
+    DevBuf q_keys, q_vals, q_rows, rp_fine, rp_counts1, rp_counts2, rp_ends1, rp_ends2, rp_tiles, rp_hll, rp_next, u_key, u_sum, u_count, u_first, u_last, u_min, u_max, u_dsum;
   } scr;
-  double est_groups = 0;                  // bucketed path: HyperLogLog estimate of the last pass (diagnostics)
+  double est_groups = 0;                  // bucketed path: HyperLogLog estimate of the group count
+  bool bk_have_hist = false;              // bucketed path: level-1 fine histogram + sketch of this handle's keys exist
+  int bk_bits = -1, bk_b1 = -1;           // bucketed path: plan whose offsets / bucket ends are cached in scr.rp_*
 };
 
 namespace {
@@ -611,8 +613,10 @@ double hll_estimate(const uint32_t* reg) {
 // The bucketed path (bucketed.cuh).  *declined = true: the estimate says a single shared-memory table holds the
 // groups, or a bucket overflowed its table — the caller continues on the global-table path.
 template <int VC, bool WIDE>
-int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, bool* declined) {
+int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* cap_io, bool* declined, bool* table_filled) {
   using T = SmTab<VC, WIDE>;
+  using SlotT = typename SlotOf<WIDE>::type;
+  *table_filled = false;
   cudaStream_t st = g->stream;
   *declined = false;
   auto& sc = g->scr;
@@ -620,74 +624,151 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, bool* declin
   const uint64_t* keys = static_cast<const uint64_t*>(g->key_data);
   const uint64_t* vals = val ? static_cast<const uint64_t*>(val->data) : nullptr;
   CUDA_TRY(cudaEventRecord(g->ev[1], st));
-  // ---- level 1 histogram + sketch ----
-  PA_TRY(sc.rp_counts1.alloc(sizeof(uint32_t) * 1024, st));
-  PA_TRY(sc.rp_hll.alloc(sizeof(uint32_t) * HLL_M, st));
-  CUDA_TRY(cudaMemsetAsync(sc.rp_counts1.p, 0, sizeof(uint32_t) * 1024, st));
-  CUDA_TRY(cudaMemsetAsync(sc.rp_hll.p, 0, sizeof(uint32_t) * HLL_M, st));
+  // ---- level 1 histogram (1024 fine buckets per chunk) + sketch ----
+  // Everything up to the scatter depends on the KEYS only (the scatter keeps its cursors private), and a handle's keys
+  // never change: histograms, offsets and bucket ends are computed by the first pass and reused by every later one.
+  const uint32_t nchunks1 = static_cast<uint32_t>((n + RP_CHUNK_ROWS - 1) / RP_CHUNK_ROWS);
   CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
-  k_rp_hist1<<<g->num_sms * 2, RH_THREADS, 0, st>>>(keys, n, sc.rp_counts1.as<unsigned int>(), sc.rp_hll.as<unsigned int>());
-  CUDA_TRY(cudaGetLastError());
-  std::vector<uint32_t> reg(HLL_M);
-  CUDA_TRY(cudaMemcpyAsync(reg.data(), sc.rp_hll.p, sizeof(uint32_t) * HLL_M, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  const double est = hll_estimate(reg.data());
-  g->est_groups = est;
+  RpArgs a1{};
+  a1.keys = keys; a1.vals = vals; a1.rows = nullptr; a1.n = n;
+  a1.n_parents = 1; a1.n_chunks1 = nchunks1;
+  if (!g->bk_have_hist) {
+    PA_TRY(sc.rp_fine.alloc(sizeof(uint32_t) * RP_MAX_FAN * static_cast<size_t>(nchunks1), st));
+    PA_TRY(sc.rp_hll.alloc(sizeof(uint32_t) * HLL_M, st));
+    CUDA_TRY(cudaMemsetAsync(sc.rp_hll.p, 0, sizeof(uint32_t) * HLL_M, st));
+    a1.counts = sc.rp_fine.as<unsigned int>(); a1.hll = sc.rp_hll.as<unsigned int>();
+    k_rp_hist<true><<<g->num_sms * 2, RH_THREADS, 0, st>>>(a1);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> reg(HLL_M);
+    CUDA_TRY(cudaMemcpyAsync(reg.data(), sc.rp_hll.p, sizeof(uint32_t) * HLL_M, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    g->est_groups = hll_estimate(reg.data());
+    g->bk_have_hist = true;
+    g->bk_bits = g->bk_b1 = -1;
+    g->last_launches += 1;
+  }
+  const double est = g->est_groups;
   const uint64_t hint = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
   // plan for the larger of hint and estimate (the sketch is good to a few per cent; a wrong hint must not overflow the tables)
   const uint64_t plan = std::max<uint64_t>(hint, static_cast<uint64_t>(est * 1.05) + 64);
-  g->last_launches += 1;
   if (!hint && plan <= static_cast<uint64_t>(T::CAP)) { *declined = true; return PA_OK; }   // the front table (gtable.cuh) holds them
-  const uint64_t per_bucket = T::CAP / 4;
-  int bits = RP_L1_LOG;
+  // Buckets of ~CAP/2 keys on average (the table admits 3/4 CAP; bucket sizes are Poisson around the mean).  Up to
+  // 1024 buckets in one level; more = two levels with the bits split evenly (long runs in both scatters).
+  const uint64_t per_bucket = T::CAP / 2;
+  int bits = 1;
   while (bits < RP_MAX_BITS && (plan >> bits) > per_bucket) ++bits;
+  int b1 = bits <= RP_SINGLE_MAX_LOG ? bits : (bits + 1) / 2;
+  if (g->opt.bucket_bits > 0) {                         // tuning / test override: level-1 bits | level-2 bits << 8
+    b1 = static_cast<int>(g->opt.bucket_bits & 0xFF);
+    const int b2o = static_cast<int>((g->opt.bucket_bits >> 8) & 0xFF);
+    if (b1 < 1 || b1 > RP_L1_LOG || b2o > RP_L1_LOG) return set_err(PA_ERR_INVALID, "bucket bits override out of range");
+    bits = b1 + b2o;
+  }
+  const int b2 = bits - b1;
   const uint32_t nb = 1u << bits;
-  // ---- level 1 scatter ----
   const size_t pad = 4;
+  const bool replan = g->bk_bits != bits || g->bk_b1 != b1;    // (first pass, or the group-count hint moved the plan)
+  // ---- level 1: fold the fine counts to 2^b1 buckets, scan, bucket ends, scatter ----
+  const size_t flat1 = (static_cast<size_t>(nchunks1) << b1) + 1;
+  if (replan) {
+    PA_TRY(sc.rp_counts1.alloc(sizeof(uint32_t) * flat1, st));
+    PA_TRY(sc.rp_ends1.alloc(sizeof(uint32_t) * (1u << b1), st));
+    CUDA_TRY(cudaMemsetAsync(sc.rp_counts1.as<uint32_t>() + (flat1 - 1), 0, sizeof(uint32_t), st));
+    k_rp_fold<<<static_cast<unsigned>((flat1 - 1 + 255) / 256), 256, 0, st>>>(sc.rp_fine.as<unsigned int>(), nchunks1, b1, sc.rp_counts1.as<unsigned int>());
+    CUDA_TRY(cudaGetLastError());
+    PA_TRY(scan_u32_on(g, sc.rp_counts1.as<uint32_t>(), flat1, &sc.tile_sums));
+    g->last_launches += 4;
+  }
   PA_TRY(sc.p_keys.alloc((static_cast<size_t>(n) + pad) * 8, st));
   if (vals) PA_TRY(sc.p_vals.alloc((static_cast<size_t>(n) + pad) * 8, st));
   PA_TRY(sc.p_rows.alloc((static_cast<size_t>(n) + pad) * 4, st));
-  k_rp_offsets1<<<1, 1024, 0, st>>>(sc.rp_counts1.as<unsigned int>());
-  CUDA_TRY(cudaGetLastError());
-  RpArgs a1{};
-  a1.keys = keys; a1.vals = vals; a1.rows = nullptr; a1.n = n;
-  a1.shift = 64 - RP_L1_LOG; a1.log_fan = RP_L1_LOG; a1.n_parents = 1;
-  a1.cursors = sc.rp_counts1.as<unsigned int>();
+  a1.shift = 64 - b1; a1.log_fan = b1;
+  a1.offsets = sc.rp_counts1.as<unsigned int>();
   a1.out_keys = sc.p_keys.as<uint64_t>(); a1.out_vals = vals ? sc.p_vals.as<uint64_t>() : nullptr; a1.out_rows = sc.p_rows.as<uint32_t>();
+  if (replan) {
+    k_rp_ends<<<((1u << b1) + 255) / 256, 256, 0, st>>>(a1, sc.rp_ends1.as<unsigned int>());
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 1;
+  }
   CUDA_TRY(cudaFuncSetAttribute(k_rp_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RpSmem::TOTAL)));
   k_rp_scatter<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a1);
   CUDA_TRY(cudaGetLastError());
-  g->last_launches += 2;
+  g->last_launches += 1;
   BkArgs b{};
   b.keys = sc.p_keys.as<uint64_t>(); b.vals = vals ? sc.p_vals.as<uint64_t>() : nullptr; b.rows = sc.p_rows.as<uint32_t>();
-  b.bucket_end = sc.rp_counts1.as<unsigned int>();
-  if (bits > RP_L1_LOG) {
+  b.bucket_end = sc.rp_ends1.as<unsigned int>();
+  if (b2 > 0) {
     // ---- level 2 inside every level-1 bucket ----
-    const int log_fan2 = bits - RP_L1_LOG;
-    PA_TRY(sc.rp_tiles.alloc(sizeof(uint32_t) * 1025, st));
-    PA_TRY(sc.rp_counts2.alloc(sizeof(uint32_t) * nb, st));
-    CUDA_TRY(cudaMemsetAsync(sc.rp_counts2.p, 0, sizeof(uint32_t) * nb, st));
-    k_rp_tiles<<<1, 1024, 0, st>>>(sc.rp_counts1.as<unsigned int>(), sc.rp_tiles.as<unsigned int>());
-    CUDA_TRY(cudaGetLastError());
+    const int np = 1 << b1;
+    const size_t chunks2_max = static_cast<size_t>(n) / RP_CHUNK_ROWS + np + 1;
+    const size_t flat2 = (chunks2_max << b2) + 1;
+    // (Only level 1 is cached: inside a tile's run the level-1 scatter orders rows by atomic arrival, so the rows on
+    // either side of a level-2 chunk boundary differ from pass to pass and the level-2 counts have to be retaken.)
+    PA_TRY(sc.rp_tiles.alloc(sizeof(uint32_t) * (np + 1), st));
+    PA_TRY(sc.rp_counts2.alloc(sizeof(uint32_t) * flat2, st));
+    PA_TRY(sc.rp_ends2.alloc(sizeof(uint32_t) * nb, st));
+    CUDA_TRY(cudaMemsetAsync(sc.rp_counts2.p, 0, sizeof(uint32_t) * flat2, st));
+    if (replan) {
+      k_rp_cprefix<<<1, 1024, 0, st>>>(sc.rp_ends1.as<unsigned int>(), np, sc.rp_tiles.as<unsigned int>());
+      CUDA_TRY(cudaGetLastError());
+    }
     RpArgs a2{};
     a2.keys = sc.p_keys.as<uint64_t>(); a2.vals = b.vals; a2.rows = sc.p_rows.as<uint32_t>(); a2.n = n;
-    a2.shift = 64 - bits; a2.log_fan = log_fan2; a2.n_parents = 1024;
-    a2.parent_end = sc.rp_counts1.as<unsigned int>(); a2.tile_prefix = sc.rp_tiles.as<unsigned int>();
-    a2.cursors = sc.rp_counts2.as<unsigned int>();
-    k_rp_hist2<<<g->num_sms * 4, RP_THREADS, 0, st>>>(a2);
+    a2.shift = 64 - bits; a2.log_fan = b2; a2.n_parents = np;
+    a2.parent_end = sc.rp_ends1.as<unsigned int>(); a2.cprefix = sc.rp_tiles.as<unsigned int>();
+    a2.counts = sc.rp_counts2.as<unsigned int>();
+    k_rp_hist<false><<<g->num_sms * 2, RH_THREADS, 0, st>>>(a2);
     CUDA_TRY(cudaGetLastError());
-    PA_TRY(scan_u32_on(g, sc.rp_counts2.as<uint32_t>(), nb, &sc.tile_sums));
+    PA_TRY(scan_u32_on(g, sc.rp_counts2.as<uint32_t>(), flat2, &sc.tile_sums));
+    g->last_launches += 5;
     PA_TRY(sc.q_keys.alloc((static_cast<size_t>(n) + pad) * 8, st));
     if (vals) PA_TRY(sc.q_vals.alloc((static_cast<size_t>(n) + pad) * 8, st));
     PA_TRY(sc.q_rows.alloc((static_cast<size_t>(n) + pad) * 4, st));
+    a2.offsets = sc.rp_counts2.as<unsigned int>();
     a2.out_keys = sc.q_keys.as<uint64_t>(); a2.out_vals = vals ? sc.q_vals.as<uint64_t>() : nullptr; a2.out_rows = sc.q_rows.as<uint32_t>();
+    k_rp_ends<<<(nb + 255) / 256, 256, 0, st>>>(a2, sc.rp_ends2.as<unsigned int>());
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 1;
     k_rp_scatter<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a2);
     CUDA_TRY(cudaGetLastError());
-    g->last_launches += 6;
+    g->last_launches += 1;
     b.keys = sc.q_keys.as<uint64_t>(); b.vals = vals ? sc.q_vals.as<uint64_t>() : nullptr; b.rows = sc.q_rows.as<uint32_t>();
-    b.bucket_end = sc.rp_counts2.as<unsigned int>();
+    b.bucket_end = sc.rp_ends2.as<unsigned int>();
   }
+  g->bk_bits = bits; g->bk_b1 = b1;
   // ---- bucket aggregation ----
+  // Few buckets (they would leave SMs idle, and a bucket is as long as its keys are frequent): ranged mode — equal
+  // row shares per CTA, tables flushed into the global table, which the caller then compacts and orders as usual.
+  const bool ranged = nb < static_cast<uint32_t>(4 * g->num_sms);
+  BkArgs& bref = b;
+  bref.ranged = ranged ? 1 : 0;
+  bref.n = n;
+  if (ranged) {
+    uint64_t cap = *cap_io;
+    while (cap < plan * 2) cap <<= 1;
+    *cap_io = cap;
+    const uint64_t nslots = cap + 2;
+    PA_TRY(sc.table.alloc(nslots * sizeof(SlotT), st));
+    const int init_grid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+    k_gtable_init<WIDE><<<init_grid, 256, 0, st>>>(sc.table.as<SlotT>(), nslots);
+    CUDA_TRY(cudaGetLastError());
+    bref.table = sc.table.p; bref.cap_mask = cap - 1; bref.shift = 64 - __builtin_ctzll(cap);
+    bref.n_buckets = nb; bref.part_bits = bits; bref.agg_mask = mask; bref.max_keys = T::MAX_KEYS;
+    bref.status = g->status.as<uint32_t>();
+    auto kern = k_bucket_agg<VC, WIDE>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::TOTAL)));
+    kern<<<g->num_sms, BK_THREADS, T::TOTAL, st>>>(bref);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 2;
+    uint32_t h_status[ST_WORDS];
+    CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_status[ST_OVERFLOW]) { *declined = true; return PA_OK; }
+    g->last_mode = 5;
+    g->last_rlog = bits;
+    *table_filled = true;
+    return PA_OK;
+  }
   uint64_t u_cap64 = std::min<uint64_t>(static_cast<uint64_t>(n) + 1, plan + plan / 4 + 65536);
   u_cap64 = std::min<uint64_t>(u_cap64, static_cast<uint64_t>(nb) * (T::MAX_KEYS + 1));
   const uint32_t u_cap = static_cast<uint32_t>(std::min<uint64_t>(u_cap64, 0xFFFFFFF0ull));
@@ -776,6 +857,7 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
   if (cap > cap_limit) cap = cap_limit;
   DevBuf& table = g->scr.table;
   const int grid_full = g->num_sms * 6;   // two waves of the 3 resident CTAs per SM
+  bool table_filled = false;              // the bucketed path (ranged mode) already left the groups in `table`
   {
     // More groups than one shared-memory table holds (or nobody knows how many): partition into buckets and
     // aggregate those in shared memory (bucketed.cuh); it declines when its own estimate says the front table is enough
@@ -784,13 +866,13 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
                        reinterpret_cast<uintptr_t>(g->key_data) % 32 == 0 && (!val || reinterpret_cast<uintptr_t>(val->data) % 32 == 0);
     if (plain && !g->opt.no_partition && g->n >= (1ll << 22) && (known0 == 0 || known0 > static_cast<uint64_t>(SmTab<VC, WIDE>::CAP))) {
       bool declined = false;
-      PA_TRY((run_bucketed_t<VC, WIDE>(g, val, mask, &declined)));
-      if (!declined) return PA_OK;
-      g->last_mode = 0; g->last_rlog = 0;
+      PA_TRY((run_bucketed_t<VC, WIDE>(g, val, mask, &cap, &declined, &table_filled)));
+      if (!declined && !table_filled) return PA_OK;
+      if (declined) { g->last_mode = 0; g->last_rlog = 0; }
     }
   }
-  CUDA_TRY(cudaEventRecord(g->ev[1], st));
-  for (;;) {
+  if (!table_filled) CUDA_TRY(cudaEventRecord(g->ev[1], st));
+  while (!table_filled) {
     const uint64_t nslots = cap + 2;
     PA_TRY(table.alloc(nslots * sizeof(SlotT), st));
     CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
@@ -1351,6 +1433,7 @@ int aggregate_impl(pa_groupby* g, const Column* val, uint32_t mask, bool deferre
     PA_TRY(hash_string_key(&g->keys[0], g->stream, g->num_sms));
     g->key_data = g->keys[0].data;
     g->have_groups = false;
+    g->bk_have_hist = false;
     g->G = 0;
     g->outs.clear();
   }

@@ -13,6 +13,7 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--scattered", action="store_true")
 ap.add_argument("--no-hint", action="store_true")
 ap.add_argument("--no-partition", action="store_true")
+ap.add_argument("--bits", type=lambda x: int(x, 0), default=0)
 a = ap.parse_args()
 n = a.rows
 k = torch.empty(n, dtype=torch.int64, device="cuda"); v = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -21,7 +22,7 @@ if a.scattered:
     k.mul_(0x2545F4914F6CDD1D).add_(0x1234567)
 torch.cuda.synchronize()
 dk, dv = pab.DeviceColumn.from_torch(k), pab.DeviceColumn.from_torch(v)
-g = pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=0 if a.no_hint else a.groups, no_partition=a.no_partition)
+g = pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=0 if a.no_hint else a.groups, no_partition=a.no_partition, bucket_bits=a.bits)
 for i in range(a.iters):
     g.aggregate(dv, a.aggs.split(","), fetch=False)
     t = g.timing()

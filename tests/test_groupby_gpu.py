@@ -373,9 +373,10 @@ def test_int_values_mean_boundary_and_smem_front(pab, orc):
 
 
 def test_partitioned_high_cardinality_equals_direct_scan(pab):
-    # >= 2 M expected groups: rows are radix-partitioned by table region first (partition.cuh).  The oracle
-    # needs ~5 us per group and aggregate, so at this size the partitioned pass is checked against the
-    # direct global-table scan (itself oracle-checked above at up to 250 K groups).
+    # More groups than one shared-memory table holds: rows are radix-partitioned into buckets first (bucketed.cuh).
+    # The oracle needs ~5 us per group and aggregate, so at this size the partitioned pass is checked against the
+    # direct global-table scan (itself oracle-checked above at up to 250 K groups); tests/test_parity_large_gpu.py
+    # holds the bucketed path to the oracle.
     import torch
     from util import assert_exact, assert_fp_close
     n, G = 6_000_001, 2_500_000
@@ -387,7 +388,7 @@ def test_partitioned_high_cardinality_equals_direct_scan(pab):
     a = pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=G)
     b = pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=G, no_partition=True)
     ra, rb_ = a.aggregate(dv, ALL), b.aggregate(dv, ALL)
-    assert a.timing()["mode"] == "partitioned" and b.timing()["mode"] is None
+    assert a.timing()["mode"] == "bucketed" and b.timing()["mode"] is None
     assert a.groupSize() == b.groupSize() and a.unique().equals(b.unique())      # same groups, same first-appearance order
     for name in ALL:
         (assert_fp_close if name in ("sum", "mean") else assert_exact)(ra[name], rb_[name], name)
