@@ -241,6 +241,27 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
                        int64_t origin_custom_ns, int64_t offset_ns, const pa_options* opt,
                        pa_groupby** out);
 
+/* pd::resample with a DateOffset rule (resample.cpp:248-267 makeGroupInfo's DateOffset branch, core.cpp:12-60
+ * DateOffset::add, core.cpp:175-265 date_range, resample.cpp:180-200 adjustBinEdges).  offset_type is the reference's
+ * DateOffset::Type (core.h:122-134); Day "D", WeekStart "WS", MonthStart "MS", QuarterStart "QS", YearStart "YS" are the
+ * ones the reference's date_range accepts, the others return PA_ERR_NOT_IMPLEMENTED with the reference's message, as
+ * does closed_right = 0 ("closed_left is not currently supported by DateOffset").  binner = date_range(first - freq,
+ * last + freq, freq) at midnight; bucket i = (edge[i], edge[i+1]] with edge = binner + 1 day - 1 ns (edge = binner for
+ * a plain "1D" rule), labelled binner[i] (label_right: binner[i+1]).  The index must be a sorted, null-free
+ * timestamp[ns] column.  Same handle semantics as pa_resample_create. */
+#define PA_OFFSET_DAY 0
+#define PA_OFFSET_MONTH_END 1
+#define PA_OFFSET_QUARTER_START 2
+#define PA_OFFSET_QUARTER_END 3
+#define PA_OFFSET_WEEK_START 4
+#define PA_OFFSET_WEEK_END 5
+#define PA_OFFSET_MONTH_START 6
+#define PA_OFFSET_YEAR_END 7
+#define PA_OFFSET_YEAR_START 8
+int pa_resample_create_calendar(const struct ArrowDeviceArray* index, const struct ArrowSchema* index_schema,
+                                int32_t offset_type, int32_t multiplier, int32_t closed_right, int32_t label_right,
+                                const pa_options* opt, pa_groupby** out);
+
 /* DataFrame::downsample (dataframe.cpp:1265-1290): groups on the per-row label
  * arrow::compute::FloorTemporal / CeilTemporal(index, RoundTemporalOptions(multiple, unit, week_starts_monday,
  * ceil_is_strictly_greater = false, calendar_based_origin)) — computed on the device, bit-identical to arrow's

@@ -56,6 +56,7 @@ def lib():
         L.orc_groupby_group_slice.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_resample_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                           C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_resample_labels_calendar.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_downsample_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char, C.c_int, C.c_int,
                                             C.c_int, C.c_void_p, C.c_void_p]
         L.orc_scalar_agg.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -163,6 +164,23 @@ def resample_labels(index: pa.Array, freq_ns: int, closed_right=False, label_rig
                                      int(label_right), ORIGIN[origin], origin_custom_ns, offset_ns,
                                      C.addressof(a), C.addressof(s)))
     return _import_array(a, s)
+
+
+OFFSET_TYPES = {"D": 0, "M": 1, "QS": 2, "Q": 3, "WS": 4, "W": 5, "MS": 6, "Y": 7, "YS": 8}   # DateOffset::Type, core.h:122-134
+
+
+def resample_labels_calendar(index: pa.Array, code: str, multiplier: int = 1, closed_right=True, label_right=False) -> pa.Array:
+    """Per-row labels of pd::resample with a DateOffset rule (resample.cpp:248-267 + resample.h:19-43)."""
+    ia, isch = _export(index)
+    a, s = _ArrowArray(), _ArrowSchema()
+    _check(lib().orc_resample_labels_calendar(C.addressof(ia), C.addressof(isch), OFFSET_TYPES[code], multiplier,
+                                              int(closed_right), int(label_right), C.addressof(a), C.addressof(s)))
+    return _import_array(a, s)
+
+
+def resample_calendar(frame: pa.RecordBatch, index: pa.Array, code: str, multiplier: int = 1, **kw) -> "OracleGroupBy":
+    labels = resample_labels_calendar(index, code, multiplier, **kw)
+    return OracleGroupBy(frame, "__resampler_idx__", index=labels)
 
 
 def downsample_labels(index: pa.Array, multiple: int, unit: str, closed_label_right=False,

@@ -339,8 +339,8 @@ Status agg_min_max(Groups& g, const std::string& column, int nthreads,
 
 // ---------------------------------------------------------------------------------------
 // Resample (resample.cpp / resample.h).  Boost ptime/time_duration are replaced by int64
-// nanoseconds since the Unix epoch; only fixed-width rules (time_duration) are restated —
-// DateOffset rules are a "next" row.
+// nanoseconds since the Unix epoch; fixed-width rules (time_duration) first, the DateOffset branch
+//  further down on std::chrono's civil calendar.
 // ---------------------------------------------------------------------------------------
 constexpr int64_t kNsPerDay = 86400LL * 1000000000LL;
 
@@ -433,6 +433,100 @@ Result<std::shared_ptr<Array>> resample_labels(const std::shared_ptr<Array>& ax,
     return Status::NotImplemented("upSampling is not implemented.");
   if (bins.size() != n_labels)
     return Status::Invalid("Processing Group Info requires bins.size() == labels->length()");
+  std::vector<int64_t> labels(bins.back());
+  int64_t prev = 0;
+  for (size_t b = 0; b < bins.size(); ++b) {
+    for (int64_t i = prev; i < bins[b]; ++i) labels[i] = binner[label_begin + b];
+    prev = bins[b];
+  }
+  ARROW_RETURN_NOT_OK(out.AppendValues(labels));
+  return out.Finish();
+}
+
+// makeGroupInfo's DateOffset branch (resample.cpp:248-267) + GroupInfo::downsample.  Boost.date_time is replaced by
+// std::chrono's civil calendar (sys_days / year_month_day): DateOffset::add (core.cpp:12-60), the day / week / month /
+// year iterators of date_range (core.cpp:175-265) and adjustBinEdges (resample.cpp:180-200) are restated on it.
+// Offset types are the reference's DateOffset::Type enumerators (core.h:122-134).
+enum OffsetType { kDay = 0, kMonthEnd = 1, kQuarterStart = 2, kQuarterEnd = 3, kWeekStart = 4, kWeekEnd = 5,
+                  kMonthStart = 6, kYearEnd = 7, kYearStart = 8 };
+
+namespace cal = std::chrono;
+
+// core.cpp:12-60 for the types date_range accepts.  `currentDate += months(k)` only contributes its year / month:
+// every one of these branches then rebuilds the date on day 1.
+cal::sys_days offset_add(cal::sys_days d, int type, int k) {
+  const cal::year_month_day ymd{d};
+  switch (type) {
+    case kMonthStart: {
+      const cal::year_month ym = cal::year_month{ymd.year(), ymd.month()} + cal::months{k};
+      return cal::sys_days{ym / cal::day{1}};
+    }
+    case kQuarterStart: {
+      const cal::year_month ym = cal::year_month{ymd.year(), ymd.month()} + cal::months{3 * k};
+      const unsigned m = (static_cast<unsigned>(ym.month()) - 1) / 3 * 3 + 1;
+      return cal::sys_days{ym.year() / cal::month{m} / cal::day{1}};
+    }
+    case kYearStart:
+      return cal::sys_days{(ymd.year() + cal::years{k}) / cal::January / cal::day{1}};
+    case kWeekStart:
+      return d + cal::days{7 * k};
+    default:
+      return d + cal::days{k};
+  }
+}
+
+Result<std::shared_ptr<Array>> resample_labels_calendar(const std::shared_ptr<Array>& ax, int type, int multiplier,
+                                                        bool closed_right, bool label_right) {
+  auto ts = std::dynamic_pointer_cast<arrow::TimestampArray>(ax);
+  if (!ts) return Status::Invalid("axis must be a TimestampArray but got array of type ", ax->type()->ToString());
+  if (ts->null_count() > 0) return Status::NotImplemented("oracle: null timestamps");
+  arrow::TimestampBuilder out(ts->type(), arrow::default_memory_pool());
+  if (ts->length() == 0) return out.Finish();
+  ARROW_ASSIGN_OR_RAISE(Datum mm, ac::MinMax(ts));
+  const auto& st = mm.scalar_as<arrow::StructScalar>();
+  const int64_t mn = static_cast<const arrow::TimestampScalar&>(*st.value[0]).value;
+  const int64_t mx = static_cast<const arrow::TimestampScalar&>(*st.value[1]).value;
+  if (!closed_right) return Status::NotImplemented("closed_left is not currently supported by DateOffset");
+  if (multiplier < 1) return Status::Invalid("FREQ must be >= 1");
+  switch (type) {   // switchFunction, core.cpp:235-265
+    case kMonthEnd: return Status::NotImplemented("MonthEnd not supported use arrow month().groupby()");
+    case kQuarterEnd: return Status::NotImplemented("QuarterEnd not supported use arrow quarter().groupby()");
+    case kWeekEnd: return Status::NotImplemented("WeekEnd not supported use arrow weeks().groupby()");
+    case kYearEnd: return Status::NotImplemented("YearEnd not supported use arrow year().groupby()");
+    default: break;
+  }
+  const cal::sys_days first{cal::days{floor_to_day(mn) / kNsPerDay}}, last{cal::days{floor_to_day(mx) / kNsPerDay}};
+  const cal::sys_days start = offset_add(first, type, -multiplier), stop = offset_add(last, type, multiplier);
+  if (start >= stop) return Status::Invalid("start date has to be less than end date");
+  if (type == kQuarterStart && static_cast<unsigned>(cal::year_month_day{start}.month()) / 3 != 0)
+    return Status::Invalid("A quarter freq requires month is on a quarter, +/- with DateOffset");
+  std::vector<int64_t> binner;
+  {
+    cal::sys_days it = start;
+    cal::year_month ym{cal::year_month_day{start}.year(), cal::year_month_day{start}.month()};
+    while (it <= stop) {
+      binner.push_back(static_cast<int64_t>(it.time_since_epoch().count()) * kNsPerDay);
+      switch (type) {   // day_iterator / week_iterator / month_iterator (x3 for quarters) / year_iterator
+        case kDay: it += cal::days{multiplier}; break;
+        case kWeekStart: it += cal::days{7 * multiplier}; break;
+        case kMonthStart: ym += cal::months{multiplier}; it = cal::sys_days{ym / cal::day{1}}; break;
+        case kQuarterStart: ym += cal::months{3 * multiplier}; it = cal::sys_days{ym / cal::day{1}}; break;
+        default: ym += cal::years{multiplier}; it = cal::sys_days{ym / cal::day{1}}; break;
+      }
+    }
+  }
+  std::vector<int64_t> edges = binner;
+  if (!(type == kDay && multiplier == 1)) {   // adjustBinEdges: + 1 day - 1 ns; drop the last edge when the one before covers max
+    for (auto& e : edges) e += kNsPerDay - 1;
+    if (edges[edges.size() - 2] > mx) { edges.pop_back(); binner.pop_back(); }
+  }
+  std::vector<int64_t> bins;
+  ARROW_RETURN_NOT_OK(generate_bins(ts->raw_values(), ts->length(), edges, true, &bins));
+  size_t label_begin = label_right ? 1 : 0;
+  size_t n_labels = binner.size() - label_begin;
+  if (bins.size() < n_labels) n_labels = bins.size();
+  if (bins.back() < static_cast<int64_t>(n_labels)) return Status::NotImplemented("upSampling is not implemented.");
+  if (bins.size() != n_labels) return Status::Invalid("Processing Group Info requires bins.size() == labels->length()");
   std::vector<int64_t> labels(bins.back());
   int64_t prev = 0;
   for (size_t b = 0; b < bins.size(); ++b) {
@@ -592,6 +686,17 @@ int orc_resample_labels(ArrowArray* index, ArrowSchema* index_schema, int64_t fr
   if (!ix.ok()) return fail(ix.status());
   auto r = resample_labels(*ix, freq_ns, closed_right != 0, label_right != 0, origin,
                            origin_custom_ns, offset_ns);
+  if (!r.ok()) return fail(r.status());
+  auto st = export_array(*r, out, out_schema);
+  return st.ok() ? 0 : fail(st);
+}
+
+int orc_resample_labels_calendar(ArrowArray* index, ArrowSchema* index_schema, int offset_type, int multiplier,
+                                 int closed_right, int label_right, ArrowArray* out, ArrowSchema* out_schema) {
+  ensure_compute_initialized();
+  auto ix = arrow::ImportArray(index, index_schema);
+  if (!ix.ok()) return fail(ix.status());
+  auto r = resample_labels_calendar(*ix, offset_type, multiplier, closed_right != 0, label_right != 0);
   if (!r.ok()) return fail(r.status());
   auto st = export_array(*r, out, out_schema);
   return st.ok() ? 0 : fail(st);

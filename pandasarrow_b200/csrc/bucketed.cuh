@@ -356,6 +356,12 @@ __global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(RpArgs a) {
 // ---------------------------------------------------------------------------------------------
 // bucket aggregation
 // ---------------------------------------------------------------------------------------------
+struct __align__(32) BkRec32 { uint64_t key, sum; uint32_t count, first; uint64_t pad; };
+struct __align__(64) BkRec64 { uint64_t key, sum; uint32_t count, first, last, pad; uint64_t mn, mx; double dsum; uint64_t pad2; };
+static_assert(sizeof(BkRec32) == 32 && sizeof(BkRec64) == 64, "group records are whole sectors");
+template <bool WIDE> struct BkRecOf { using type = BkRec32; };
+template <> struct BkRecOf<true> { using type = BkRec64; };
+
 struct BkArgs {
   const uint64_t* keys;          // partitioned rows (arrays padded by 4 elements: 256-bit loads may read past a bucket)
   const uint64_t* vals;          // may be null
@@ -366,15 +372,10 @@ struct BkArgs {
   unsigned int* next_bucket;     // work counter
   uint32_t agg_mask;
   uint32_t max_keys;             // keys a bucket's table admits
-  // unordered groups
-  uint64_t* u_key;
-  uint64_t* u_sum;
-  uint32_t* u_count;
+  // unordered groups: one record per group (BkRec: whole sectors, so the ordering pass reads a group with one or two
+  // adjacent sector fetches) + their first rows as a plain array (bitmap / rank passes)
+  void* u_rec;
   uint32_t* u_first;
-  uint32_t* u_last;
-  uint64_t* u_min;
-  uint64_t* u_max;
-  double* u_dsum;
   uint32_t u_cap;
   uint32_t* status;              // ST_OVERFLOW, ST_COUNTER (groups appended)
   // ranged mode (fewer buckets than would keep every SM busy): every CTA takes an equal, contiguous share of the
@@ -566,16 +567,23 @@ __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
       if (occ) {
         const uint32_t pos = gbase + wbase + __popc(m & ((1u << lane_id()) - 1u));
         if (fits) {
-          a.u_key[pos] = i == T::CAP + 1 ? kEmptyKey : s_key[i];
-          a.u_sum[pos] = s_sum[i];
-          a.u_count[pos] = s_cnt[i];
-          a.u_first[pos] = first;
+          using Rec = typename BkRecOf<WIDE>::type;
+          Rec r{};
+          r.key = i == T::CAP + 1 ? kEmptyKey : s_key[i];
+          r.sum = s_sum[i];
+          r.count = s_cnt[i];
+          r.first = first;
           if constexpr (WIDE) {
-            a.u_last[pos] = s_last[i];
-            a.u_min[pos] = s_mn[i];
-            a.u_max[pos] = s_mx[i];
-            if constexpr (T::DSUM) { if (a.u_dsum) a.u_dsum[pos] = s_dsum[i]; }
+            r.last = s_last[i];
+            r.mn = s_mn[i];
+            r.mx = s_mx[i];
+            if constexpr (T::DSUM) r.dsum = s_dsum[i];
           }
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<Rec*>(a.u_rec) + pos);
+          const uint4* src = reinterpret_cast<const uint4*>(&r);
+#pragma unroll
+          for (int q = 0; q < static_cast<int>(sizeof(Rec) / 16); ++q) dst[q] = src[q];
+          a.u_first[pos] = first;
         }
         s_key[i] = kEmptyKey;
         s_sum[i] = 0ull;
@@ -591,33 +599,30 @@ __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
   }
 }
 
-// GroupResult[rank of first_row[i]] = unordered group i (bitmap + block prefix of order.cuh)
-struct BkOrderArgs {
-  const uint64_t* u_key; const uint64_t* u_sum; const uint32_t* u_count; const uint32_t* u_first; const uint32_t* u_last;
-  const uint64_t* u_min; const uint64_t* u_max; const double* u_dsum;
-  uint32_t G;
-  const uint32_t* bitmap; const uint32_t* prefix8;
-  GroupResult out;
-  int wide;
-};
-__global__ void __launch_bounds__(256) k_bm_rank_scatter(BkOrderArgs a) {
-  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-  if (i >= a.G) return;
-  const uint32_t r = a.u_first[i];
-  const uint32_t word = r >> 5, blk = word / BM_BLOCK_WORDS;
-  uint32_t rank = a.prefix8[blk];
-  for (uint32_t w = blk * BM_BLOCK_WORDS; w < word; ++w) rank += __popc(a.bitmap[w]);
-  rank += __popc(a.bitmap[word] & ((1u << (r & 31u)) - 1u));
-  a.out.key[rank] = a.u_key[i];
-  a.out.key_kind[rank] = KK_REGULAR;
-  a.out.sum[rank] = a.u_sum[i];
-  a.out.count[rank] = a.u_count[i];
-  a.out.first_row[rank] = r;
-  a.out.last_row[rank] = a.wide ? a.u_last[i] : 0u;
-  if (a.wide) {
-    a.out.min_ord[rank] = a.u_min[i];
-    a.out.max_ord[rank] = a.u_max[i];
-    if (a.out.dsum && a.u_dsum) a.out.dsum[rank] = a.u_dsum[i];
+// GroupResult[r] = unordered group perm[r] (perm = k_bm_rank of the first rows, order.cuh): one random record fetch
+// per group, everything else streams
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_bk_gather(const void* recs, const uint32_t* perm, uint32_t G, GroupResult out) {
+  using Rec = typename BkRecOf<WIDE>::type;
+  const uint32_t r = blockIdx.x * 256u + threadIdx.x;
+  if (r >= G) return;
+  const uint4* src = reinterpret_cast<const uint4*>(static_cast<const Rec*>(recs) + perm[r]);
+  Rec rec;
+  uint4* dst = reinterpret_cast<uint4*>(&rec);
+#pragma unroll
+  for (int q = 0; q < static_cast<int>(sizeof(Rec) / 16); ++q) dst[q] = __ldg(src + q);
+  out.key[r] = rec.key;
+  out.key_kind[r] = KK_REGULAR;
+  out.sum[r] = rec.sum;
+  out.count[r] = rec.count;
+  out.first_row[r] = rec.first;
+  if constexpr (WIDE) {
+    out.last_row[r] = rec.last;
+    out.min_ord[r] = rec.mn;
+    out.max_ord[r] = rec.mx;
+    if (out.dsum) out.dsum[r] = rec.dsum;
+  } else {
+    out.last_row[r] = 0u;
   }
 }
 

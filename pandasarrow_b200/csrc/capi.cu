@@ -326,6 +326,7 @@ struct pa_groupby {
   bool resample = false;
   std::string index_format;
   ResampleSpec rs{};
+  DevBuf rs_edges, rs_labels;             // calendar rules: bucket edges / labels on the device (rs.edges / rs.labels)
   // group table in first-appearance order
   bool have_groups = false;
   uint32_t G = 0;
@@ -374,7 +375,7 @@ struct pa_groupby {
   struct Scratch {
     DevBuf table, p_keys, p_vals, p_rows, p_counts, krange, c_first, c_slot, s_first, s_slot, cub_tmp, bnd, bitmap, prefix8, tile_sums;
     // bucketed path (bucketed.cuh): second-level rows, histograms / cursors, sketch, unordered groups
-    DevBuf q_keys, q_vals, q_rows, rp_fine, rp_counts1, rp_counts2, rp_ends1, rp_ends2, rp_tiles, rp_hll, rp_next, u_key, u_sum, u_count, u_first, u_last, u_min, u_max, u_dsum;
+    DevBuf q_keys, q_vals, q_rows, rp_fine, rp_counts1, rp_counts2, rp_ends1, rp_ends2, rp_tiles, rp_hll, rp_next, u_rec, u_first;
   } scr;
   double est_groups = 0;                  // bucketed path: HyperLogLog estimate of the group count
   bool bk_have_hist = false;              // bucketed path: level-1 fine histogram + sketch of this handle's keys exist
@@ -772,23 +773,14 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
   uint64_t u_cap64 = std::min<uint64_t>(static_cast<uint64_t>(n) + 1, plan + plan / 4 + 65536);
   u_cap64 = std::min<uint64_t>(u_cap64, static_cast<uint64_t>(nb) * (T::MAX_KEYS + 1));
   const uint32_t u_cap = static_cast<uint32_t>(std::min<uint64_t>(u_cap64, 0xFFFFFFF0ull));
-  PA_TRY(sc.u_key.alloc(static_cast<size_t>(u_cap) * 8, st));
-  PA_TRY(sc.u_sum.alloc(static_cast<size_t>(u_cap) * 8, st));
-  PA_TRY(sc.u_count.alloc(static_cast<size_t>(u_cap) * 4, st));
+  using Rec = typename BkRecOf<WIDE>::type;
+  PA_TRY(sc.u_rec.alloc(static_cast<size_t>(u_cap) * sizeof(Rec), st));
   PA_TRY(sc.u_first.alloc(static_cast<size_t>(u_cap) * 4, st));
-  if (WIDE) {
-    PA_TRY(sc.u_last.alloc(static_cast<size_t>(u_cap) * 4, st));
-    PA_TRY(sc.u_min.alloc(static_cast<size_t>(u_cap) * 8, st));
-    PA_TRY(sc.u_max.alloc(static_cast<size_t>(u_cap) * 8, st));
-    if (VC != VC_F) PA_TRY(sc.u_dsum.alloc(static_cast<size_t>(u_cap) * 8, st));
-  }
   PA_TRY(sc.rp_next.alloc(4, st));
   CUDA_TRY(cudaMemsetAsync(sc.rp_next.p, 0, 4, st));
   b.n_buckets = nb; b.part_bits = bits; b.next_bucket = sc.rp_next.as<unsigned int>();
   b.agg_mask = mask; b.max_keys = T::MAX_KEYS;
-  b.u_key = sc.u_key.as<uint64_t>(); b.u_sum = sc.u_sum.as<uint64_t>(); b.u_count = sc.u_count.as<uint32_t>(); b.u_first = sc.u_first.as<uint32_t>();
-  b.u_last = WIDE ? sc.u_last.as<uint32_t>() : nullptr; b.u_min = WIDE ? sc.u_min.as<uint64_t>() : nullptr; b.u_max = WIDE ? sc.u_max.as<uint64_t>() : nullptr;
-  b.u_dsum = (WIDE && VC != VC_F) ? sc.u_dsum.as<double>() : nullptr;
+  b.u_rec = sc.u_rec.p; b.u_first = sc.u_first.as<uint32_t>();
   b.u_cap = u_cap; b.status = g->status.as<uint32_t>();
   {
     auto kern = k_bucket_agg<VC, WIDE>;
@@ -826,12 +818,12 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
     CUDA_TRY(cudaGetLastError());
     k_scan_apply<<<ntiles, 256, 0, st>>>(sc.prefix8.as<uint32_t>(), nblocks, sc.tile_sums.as<uint32_t>());
     CUDA_TRY(cudaGetLastError());
-    BkOrderArgs o{};
-    o.u_key = b.u_key; o.u_sum = b.u_sum; o.u_count = b.u_count; o.u_first = b.u_first; o.u_last = b.u_last;
-    o.u_min = b.u_min; o.u_max = b.u_max; o.u_dsum = b.u_dsum; o.G = G;
-    o.bitmap = sc.bitmap.as<uint32_t>(); o.prefix8 = sc.prefix8.as<uint32_t>(); o.out = g->res; o.wide = WIDE ? 1 : 0;
-    k_bm_rank_scatter<<<(G + 255) / 256, 256, 0, st>>>(o);
+    PA_TRY(sc.s_slot.alloc(static_cast<size_t>(G) * 4, st));
+    k_bm_rank<<<(G + 255) / 256, 256, 0, st>>>(b.u_first, nullptr, G, sc.bitmap.as<uint32_t>(), sc.prefix8.as<uint32_t>(), sc.s_slot.as<uint32_t>());
     CUDA_TRY(cudaGetLastError());
+    k_bk_gather<WIDE><<<(G + 255) / 256, 256, 0, st>>>(sc.u_rec.p, sc.s_slot.as<uint32_t>(), G, g->res);
+    CUDA_TRY(cudaGetLastError());
+    g->last_launches += 1;
     g->last_launches += 6;
   }
   g->last_mode = 5;
@@ -2342,6 +2334,135 @@ int pa_resample_create(const struct ArrowDeviceArray* index, const struct ArrowS
     g->rs.first = first;
     g->rs.nbins = (last - first) / freq_ns;
     if (g->n < g->rs.nbins) return set_err(PA_ERR_NOT_IMPLEMENTED, "upSampling is not implemented.");  // resample.h:102-105
+  }
+  *out = g.release();
+  return PA_OK;
+}
+
+// pd::resample with a DateOffset rule (makeGroupInfo's DateOffset branch, /root/reference/src/resample.cpp:248-267;
+// DateOffset::add, core.cpp:12-60; date_range + switchFunction, core.cpp:175-265; adjustBinEdges, resample.cpp:180-200).
+// The host computes the O(#buckets) binner / edge / label arrays; the rows are reduced by the same sorted-run kernel
+// as the fixed-width rules, which looks a bucket up in the edge array only where a new run of rows begins.
+namespace {
+int64_t days_from_civil(int64_t y, int m, int d) {       // proleptic Gregorian, days since 1970-01-01
+  y -= m <= 2;
+  const int64_t era = (y >= 0 ? y : y - 399) / 400;
+  const int64_t yoe = y - era * 400;
+  const int64_t doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+  const int64_t doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+  return era * 146097 + doe - 719468;
+}
+void civil_from_days(int64_t z, int64_t* y, int* m, int* d) {
+  z += 719468;
+  const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+  const int64_t doe = z - era * 146097;
+  const int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  const int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+  const int64_t mp = (5 * doy + 2) / 153;
+  *d = static_cast<int>(doy - (153 * mp + 2) / 5 + 1);
+  *m = static_cast<int>(mp < 10 ? mp + 3 : mp - 9);
+  *y = yoe + era * 400 + (*m <= 2);
+}
+// DateOffset::add for the rule types date_range accepts; the day of the month only survives for Day / WeekStart,
+// the others snap to the first day of a month, so boost's end-of-month rules never come into play.
+int64_t offset_add(int64_t day, int type, int64_t k) {
+  if (type == PA_OFFSET_DAY) return day + k;
+  if (type == PA_OFFSET_WEEK_START) return day + 7 * k;
+  int64_t y; int m, d;
+  civil_from_days(day, &y, &m, &d);
+  int64_t ym = y * 12 + (m - 1);
+  if (type == PA_OFFSET_MONTH_START) ym += k;
+  else if (type == PA_OFFSET_QUARTER_START) { ym += 3 * k; ym = floor_div(ym, 3) * 3; }
+  else /* YEAR_START */ { ym += 12 * k; ym = floor_div(ym, 12) * 12; }
+  return days_from_civil(floor_div(ym, 12), static_cast<int>(ym - floor_div(ym, 12) * 12) + 1, 1);
+}
+}  // namespace
+
+int pa_resample_create_calendar(const struct ArrowDeviceArray* index, const struct ArrowSchema* index_schema, int32_t offset_type,
+                                int32_t multiplier, int32_t closed_right, int32_t label_right, const pa_options* opt,
+                                pa_groupby** out) {
+  if (!index || !index_schema || !out) return set_err(PA_ERR_INVALID, "pa_resample_create_calendar: null argument");
+  if (multiplier < 1) return set_err(PA_ERR_INVALID, "FREQ must be >= 1");                                   // core.cpp:186-189
+  switch (offset_type) {
+    case PA_OFFSET_DAY: case PA_OFFSET_WEEK_START: case PA_OFFSET_MONTH_START: case PA_OFFSET_QUARTER_START: case PA_OFFSET_YEAR_START: break;
+    case PA_OFFSET_MONTH_END: return set_err(PA_ERR_NOT_IMPLEMENTED, "MonthEnd not supported use arrow month().groupby()");       // core.cpp:243-260
+    case PA_OFFSET_QUARTER_END: return set_err(PA_ERR_NOT_IMPLEMENTED, "QuarterEnd not supported use arrow quarter().groupby()");
+    case PA_OFFSET_WEEK_END: return set_err(PA_ERR_NOT_IMPLEMENTED, "WeekEnd not supported use arrow weeks().groupby()");
+    case PA_OFFSET_YEAR_END: return set_err(PA_ERR_NOT_IMPLEMENTED, "YearEnd not supported use arrow year().groupby()");
+    default: return set_err(PA_ERR_INVALID, "unknown DateOffset type %d", offset_type);
+  }
+  if (!closed_right) return set_err(PA_ERR_NOT_IMPLEMENTED, "closed_left is not currently supported by DateOffset");   // resample.cpp:256-258
+  HandlePtr g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  g->keys.resize(1);
+  Column& ix = g->keys[0];
+  PA_TRY(load_column(index, index_schema, g->stream, g->device, &ix));
+  const char* f = index_schema->format;
+  if (!(f && f[0] == 't' && f[1] == 's') || ix.width != 8)
+    return set_err(PA_ERR_INVALID, "axis must be a TimestampArray but got array of type '%s'", f ? f : "?");   // resample.cpp:213-216
+  if (f[2] != 'n') return set_err(PA_ERR_NOT_IMPLEMENTED, "resample by a DateOffset rule needs a timestamp[ns] index (the reference's bins and labels are nanoseconds)");
+  if (ix.valid) return set_err(PA_ERR_NOT_IMPLEMENTED, "resample: null timestamps are not supported");
+  g->n = ix.n;
+  if (g->n >= 0xFFFFFFFELL) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-2 rows per call; shard by row range");
+  g->resample = true;
+  g->index_format = f;
+  g->fields.assign(1, KeyField{});
+  g->key_data = ix.data;
+  g->key_width = 8;
+  g->rs = ResampleSpec{};
+  g->rs.closed_right = 1;
+  if (g->n > 0) {
+    constexpr int64_t kDay = 86400LL * 1000000000LL;
+    int64_t ends[2];
+    CUDA_TRY(cudaMemcpyAsync(&ends[0], ix.data, 8, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(&ends[1], static_cast<const int64_t*>(ix.data) + (g->n - 1), 8, cudaMemcpyDeviceToHost, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    if (ends[1] < ends[0]) return set_err(PA_ERR_INVALID, "resample: the index must be sorted ascending");
+    const int64_t first_day = floor_div(ends[0], kDay), last_day = floor_div(ends[1], kDay);
+    const int64_t start = offset_add(first_day, offset_type, -static_cast<int64_t>(multiplier));
+    const int64_t stop = offset_add(last_day, offset_type, multiplier);
+    if (start >= stop) return set_err(PA_ERR_INVALID, "start date has to be less than end date");              // core.cpp:181-184
+    if (offset_type == PA_OFFSET_QUARTER_START) {
+      int64_t y; int m, d;
+      civil_from_days(start, &y, &m, &d);
+      if (m / 3 != 0) return set_err(PA_ERR_INVALID, "A quarter freq requires month is on a quarter, +/- with DateOffset");   // core.cpp:247-250
+    }
+    // date_range(first - freq, last + freq, freq): the iterator steps `multiplier` units from `start` while <= stop
+    std::vector<int64_t> binner;
+    for (int64_t i = 0;; ++i) {
+      int64_t day;
+      if (offset_type == PA_OFFSET_DAY) day = start + i * multiplier;
+      else if (offset_type == PA_OFFSET_WEEK_START) day = start + 7 * i * multiplier;
+      else day = offset_add(start, offset_type, i * multiplier);
+      if (day > stop) break;
+      binner.push_back(day * kDay);
+      if (binner.size() > (1u << 28)) return set_err(PA_ERR_INVALID, "resample: too many buckets");
+    }
+    std::vector<int64_t> edges(binner);
+    if (!(offset_type == PA_OFFSET_DAY && multiplier == 1)) {                                                 // adjustBinEdges
+      for (auto& e : edges) e += kDay - 1;
+      if (edges.size() >= 2 && edges[edges.size() - 2] > ends[1]) { edges.pop_back(); binner.pop_back(); }
+    }
+    if (edges.size() < 2) return set_err(PA_ERR_INVALID, "Invalid length for values or for binner");
+    if (ends[0] < edges.front()) return set_err(PA_ERR_INVALID, "Values falls before first bin");             // resample.cpp:33-41
+    if (ends[1] > edges.back()) return set_err(PA_ERR_INVALID, "Values falls after last bin");
+    const int64_t nbins = static_cast<int64_t>(edges.size()) - 1;
+    if (g->n < nbins) return set_err(PA_ERR_NOT_IMPLEMENTED, "upSampling is not implemented.");               // resample.h:102-105
+    std::vector<int64_t> labels(static_cast<size_t>(nbins));
+    for (int64_t i = 0; i < nbins; ++i) labels[i] = binner[static_cast<size_t>(i) + (label_right ? 1 : 0)];
+    // bin i = (edges[i], edges[i+1]] on ts = [edges[i], edges[i+1]) on ts' = ts - 1; a value equal to edges[0] passes
+    // the reference's range check and lands in bin 0
+    edges[0] -= 1;
+    PA_TRY(g->rs_edges.alloc(edges.size() * 8, g->stream));
+    PA_TRY(g->rs_labels.alloc(labels.size() * 8, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->rs_edges.p, edges.data(), edges.size() * 8, cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaMemcpyAsync(g->rs_labels.p, labels.data(), labels.size() * 8, cudaMemcpyHostToDevice, g->stream));
+    CUDA_TRY(cudaStreamSynchronize(g->stream));
+    g->rs.first = edges[0];
+    g->rs.freq = kDay;
+    g->rs.nbins = nbins;
+    g->rs.edges = g->rs_edges.as<int64_t>();
+    g->rs.labels = g->rs_labels.as<int64_t>();
   }
   *out = g.release();
   return PA_OK;

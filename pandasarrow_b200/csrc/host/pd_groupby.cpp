@@ -572,15 +572,50 @@ arrow::Result<DataFrame> Resampler::frameOfAll(std::string const& name) {
   return r->setIndex(unique());
 }
 
+std::optional<DateOffset> DateOffset::FromString(std::string const& code) {
+  const auto [unit, mul] = splitTimeSpan(code);
+  DateOffset o;
+  o.multiplier = mul;
+  if (unit == "D") o.type = Day;
+  else if (unit == "WS") o.type = WeekStart;
+  else if (unit == "W") o.type = WeekEnd;
+  else if (unit == "MS") o.type = MonthStart;
+  else if (unit == "M") o.type = MonthEnd;
+  else if (unit == "Y") o.type = YearEnd;
+  else if (unit == "YS") o.type = YearStart;
+  else if (unit == "Q") o.type = QuarterEnd;
+  else if (unit == "QS") o.type = QuarterStart;
+  else return std::nullopt;
+  return o;
+}
+
+Resampler::Resampler(DataFrame const& _df, DateOffset const& rule, bool closed_right, bool label_right) {
+  df = _df;
+  key_array = df.indexArray();
+  if (!key_array) throw std::runtime_error("frame has no index");
+  Exported k(*key_array);
+  pa_options opt;
+  pa_options_init(&opt);
+  if (pa_resample_create_calendar(&k.dev, &k.schema, static_cast<int32_t>(rule.type), rule.multiplier, closed_right, label_right,
+                                  &opt, &handle) != PA_OK)
+    throw_pa("resample");
+}
+
 namespace {
-time_duration rule_to_duration(std::string const& rule) {
-  auto [unit, value] = splitTimeSpan(rule);   // resample.h:61-86
+// resample.h:61-86: minute / second / ... units are fixed-width rules, everything else goes to DateOffset::FromString
+std::optional<time_duration> rule_to_duration(std::string const& rule) {
+  auto [unit, value] = splitTimeSpan(rule);
   if (unit == "T" || unit == "min") return minutes(value);
   if (unit == "S") return seconds(value);
   if (unit == "L" || unit == "ms") return milliseconds(value);
   if (unit == "U" || unit == "us") return microseconds(value);
   if (unit == "N" || unit == "ns") return nanoseconds(value);
-  throw std::runtime_error("DateOffset rules (" + rule + ") are not part of the B200 resample path yet (SURVEY 8f-3)");
+  return std::nullopt;
+}
+DateOffset rule_to_offset(std::string const& rule) {
+  auto o = DateOffset::FromString(rule);
+  if (!o) throw std::runtime_error("Invalid time offset " + rule);   // (the reference dereferences an empty optional here)
+  return *o;
 }
 }  // namespace
 
@@ -589,9 +624,16 @@ Resampler resample(DataFrame const& df, time_duration const& rule, bool closed_r
   if (!tz.empty()) throw std::runtime_error("resample: tz is not supported");
   return Resampler(df, rule.count(), closed_right, label_right, origin, offset.count());
 }
+Resampler resample(DataFrame const& df, DateOffset const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const&,
+                   time_duration const&, std::string const& tz) {
+  // (origin and offset only enter adjustDatesAnchored, which the DateOffset branch never calls: resample.cpp:248-267)
+  if (!tz.empty()) throw std::runtime_error("resample: tz is not supported");
+  return Resampler(df, rule, closed_right, label_right);
+}
 Resampler resample(DataFrame const& df, std::string const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
                    time_duration const& offset, std::string const& tz) {
-  return resample(df, rule_to_duration(rule), closed_right, label_right, origin, offset, tz);
+  if (auto d = rule_to_duration(rule)) return resample(df, *d, closed_right, label_right, origin, offset, tz);
+  return resample(df, rule_to_offset(rule), closed_right, label_right, origin, offset, tz);
 }
 Resampler resample(Series const& s, time_duration const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
                    time_duration const& offset, std::string const& tz) {
@@ -599,9 +641,15 @@ Resampler resample(Series const& s, time_duration const& rule, bool closed_right
   DataFrame df(arrow::schema({arrow::field(s.name(), s.dtype())}), s.size(), {s.array()}, s.indexArray());
   return resample(df, rule, closed_right, label_right, origin, offset, tz);
 }
+Resampler resample(Series const& s, DateOffset const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
+                   time_duration const& offset, std::string const& tz) {
+  DataFrame df(arrow::schema({arrow::field(s.name(), s.dtype())}), s.size(), {s.array()}, s.indexArray());
+  return resample(df, rule, closed_right, label_right, origin, offset, tz);
+}
 Resampler resample(Series const& s, std::string const& rule, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
                    time_duration const& offset, std::string const& tz) {
-  return resample(s, rule_to_duration(rule), closed_right, label_right, origin, offset, tz);
+  if (auto d = rule_to_duration(rule)) return resample(s, *d, closed_right, label_right, origin, offset, tz);
+  return resample(s, rule_to_offset(rule), closed_right, label_right, origin, offset, tz);
 }
 
 // ------------------------------ helpers ------------------------------

@@ -26,6 +26,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <optional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -48,6 +49,14 @@ inline time_duration nanoseconds(int64_t n) { return std::chrono::nanoseconds(n)
 struct TimeGrouperOrigin {
   enum Type { Epoch, Start, StartDay, End, EndDay, Custom } type{StartDay};
   int64_t custom_ns{0};
+};
+
+// core.h:122-159: calendar rule of pd::resample ("2D", "WS", "MS", "QS", "YS"; the END types exist in the reference but
+// its date_range rejects them, core.cpp:243-260)
+struct DateOffset {
+  enum Type { Day, MonthEnd, QuarterStart, QuarterEnd, WeekStart, WeekEnd, MonthStart, YearEnd, YearStart } type{Day};
+  int multiplier{1};
+  static std::optional<DateOffset> FromString(std::string const& code);   // core.cpp:62-108
 };
 
 // core.h:181-194
@@ -274,6 +283,9 @@ class Resampler : protected GroupBy {
   // time-bucket specialisation: sorted index + fixed width (pd::resample)
   Resampler(DataFrame const& _df, int64_t freq_ns, bool closed_right, bool label_right, TimeGrouperOrigin const& origin,
             int64_t offset_ns);
+  // calendar rule (makeGroupInfo's DateOffset branch, resample.cpp:248-267): edges / labels made by the host side of the
+  // C ABI, rows reduced by the same sorted-run kernel
+  Resampler(DataFrame const& _df, DateOffset const& rule, bool closed_right, bool label_right);
   // DataFrame::downsample (dataframe.cpp:1265-1290): groups on Floor/CeilTemporal(index) labels made on the device
   struct DownsampleRule { int multiple; char unit; bool closed_label_right, week_starts_monday, calendar_based_origin; };
   Resampler(DataFrame const& _df, DownsampleRule const& rule);
@@ -295,6 +307,10 @@ class Resampler : protected GroupBy {
 // resample.h:51-122
 Resampler resample(DataFrame const& df, std::string const& rule, bool closed_right = false, bool label_right = false,
                    TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0), std::string const& tz = "");
+Resampler resample(DataFrame const& df, DateOffset const& rule, bool closed_right = false, bool label_right = false,
+                   TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(), std::string const& tz = "");
+Resampler resample(Series const& s, DateOffset const& rule, bool closed_right = false, bool label_right = false,
+                   TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(), std::string const& tz = "");
 Resampler resample(DataFrame const& df, time_duration const& rule, bool closed_right = false, bool label_right = false,
                    TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0), std::string const& tz = "");
 Resampler resample(Series const& s, std::string const& rule, bool closed_right = false, bool label_right = false,

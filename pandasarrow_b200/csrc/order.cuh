@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t* data, uint64_t n, 
   for (int j = 0; j < 8; ++j) if (base + j < n) data[base + j] += add;
 }
 
-// sorted_slot[rank of first_row[i]] = slot[i]
+// sorted_slot[rank of first_row[i]] = slot[i]   (slot == null: i itself)
 __global__ void __launch_bounds__(256) k_bm_rank(const uint32_t* first_row, const uint32_t* slot, uint32_t G, const uint32_t* bitmap,
                                                  const uint32_t* prefix8, uint32_t* sorted_slot) {
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_bm_rank(const uint32_t* first_row, cons
   uint32_t rank = prefix8[blk];
   for (uint32_t w = blk * BM_BLOCK_WORDS; w < word; ++w) rank += __popc(bitmap[w]);
   rank += __popc(bitmap[word] & ((1u << (r & 31u)) - 1u));
-  sorted_slot[rank] = slot[i];
+  sorted_slot[rank] = slot ? slot[i] : i;
 }
 
 }  // namespace pa

@@ -28,7 +28,37 @@ struct ResampleSpec {
   int64_t nbins;
   int64_t label_off;    // 0 or freq (label_right)
   int closed_right;
+  // calendar (DateOffset) rules: bucket b = [edges[b], edges[b + 1]) on ts' with the label labels[b]; both arrays are
+  // computed on the host (O(#buckets), makeGroupInfo's DateOffset branch) and live on the device.  null = fixed width.
+  const int64_t* edges;   // [nbins + 1], ascending
+  const int64_t* labels;  // [nbins]
 };
+
+// Bucket of ts' (= ts, or ts - 1 when the buckets are closed on the right); -1 = outside the anchored range.
+// Only evaluated where a new run of rows begins, never per row.
+__device__ __forceinline__ int64_t rs_locate(const ResampleSpec& sp, int64_t tp, int64_t* lo, uint64_t* width) {
+  if (!sp.edges) {
+    if (tp < sp.first) return -1;
+    const int64_t b = (tp - sp.first) / sp.freq;
+    if (b >= sp.nbins) return -1;
+    *lo = sp.first + b * sp.freq;
+    *width = static_cast<uint64_t>(sp.freq);
+    return b;
+  }
+  if (tp < __ldg(sp.edges) || tp >= __ldg(sp.edges + sp.nbins)) return -1;
+  int64_t l = 0, h = sp.nbins;                    // largest b with edges[b] <= tp
+  while (h - l > 1) {
+    const int64_t mid = (l + h) >> 1;
+    if (__ldg(sp.edges + mid) <= tp) l = mid; else h = mid;
+  }
+  const int64_t e0 = __ldg(sp.edges + l);
+  *lo = e0;
+  *width = static_cast<uint64_t>(__ldg(sp.edges + l + 1) - e0);
+  return l;
+}
+__device__ __forceinline__ int64_t rs_label(const ResampleSpec& sp, int64_t b) {
+  return sp.labels ? __ldg(sp.labels + b) : sp.first + b * sp.freq + sp.label_off;
+}
 
 struct __align__(16) RsPartial {
   int64_t bucket;       // -1: empty
@@ -77,7 +107,7 @@ template <int VC, bool WIDE>
 __device__ __forceinline__ void rs_store_slot(void* table, int64_t b, const ResampleSpec& sp, const RsAcc<VC, WIDE>& a) {
   using SlotT = typename SlotOf<WIDE>::type;
   SlotT* q = static_cast<SlotT*>(table) + b;
-  q->key = static_cast<uint64_t>(sp.first + b * sp.freq + sp.label_off);
+  q->key = static_cast<uint64_t>(rs_label(sp, b));
   q->first_row = a.first_row;
   q->last_row = a.last_row;
   q->sum = a.sum;
@@ -161,7 +191,6 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
   const int64_t nw = (static_cast<int64_t>(gridDim.x) * RS_THREADS) >> 5;
   const ResampleSpec sp = a.spec;
   const bool fast_vals = a.vals != nullptr && a.vw == 8 && a.vvalid == nullptr;
-  const uint64_t freq = static_cast<uint64_t>(sp.freq);
   const int64_t shift = sp.closed_right ? 1 : 0;
   for (int64_t c = gw; c < a.nchunks; c += nw) {
     const int64_t row0 = c * RS_CHUNK;
@@ -169,7 +198,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
     RsLane<VC, WIDE> part;                         // this lane's share of the open run
     uint32_t run_first = kNoRow, run_last = 0;     // first / last row of the open run (uniform)
     int64_t cur_b = -1;                            // bucket of the open run
-    int64_t cur_lo = INT64_MIN;                    // its left edge on ts'; no open run: (ts' - cur_lo) never < freq
+    int64_t cur_lo = INT64_MIN;                    // its left edge on ts'
+    uint64_t freq = 0;                             // its width (fixed rules: the same for every bucket)
     bool have_run = false;
     bool first_seg = true;                         // the open run started at the chunk's first row
     bool wrote_first = false;
@@ -247,8 +277,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
             run_last = 0;
             const int src = __ffs(todo) - 1;
             const int64_t t0 = __shfl_sync(FULL, tp, src);
-            const int64_t b = (t0 - sp.first) / sp.freq;
-            if (t0 < sp.first || b >= sp.nbins || b <= cur_b) {
+            int64_t lo_b = 0;
+            uint64_t w_b = 0;
+            const int64_t b = rs_locate(sp, t0, &lo_b, &w_b);
+            if (b < 0 || b <= cur_b) {
               // outside the anchored range, or an earlier bucket again: the input was not sorted
               unsorted = true;
               have_run = false;
@@ -256,7 +288,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
               continue;
             }
             cur_b = b;
-            cur_lo = sp.first + b * sp.freq;
+            cur_lo = lo_b;
+            freq = w_b;
             have_run = true;
           }
         }

@@ -49,8 +49,11 @@ __device__ __forceinline__ uint32_t rowid_lookup(const RowIdArgs& a, int64_t i) 
   if (a.kvalid && !bit_at(a.kvalid, a.koff + i)) return a.special[0];
   if (a.resample) {
     const int64_t tp = static_cast<int64_t>(key) - (a.rs.closed_right ? 1 : 0);
-    const int64_t b = (tp - a.rs.first) / a.rs.freq;
-    key = static_cast<uint64_t>(a.rs.first + b * a.rs.freq + a.rs.label_off);
+    int64_t lo = 0;
+    uint64_t w = 0;
+    const int64_t b = rs_locate(a.rs, tp, &lo, &w);
+    if (b < 0) return 0xFFFFFFFFu;
+    key = static_cast<uint64_t>(rs_label(a.rs, b));
   }
   if (key == kEmptyKey) return a.special[1];
   uint64_t s = gtable_home(key, a.shift);

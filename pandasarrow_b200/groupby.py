@@ -440,6 +440,34 @@ def resample(frame, index: Column, freq_ns: int, closed_right: bool = False, lab
     return r
 
 
+# DateOffset::Type (core.h:122-134) by rule code (DateOffset::FromString, core.cpp:62-108)
+OFFSET_TYPES = {"D": 0, "M": 1, "QS": 2, "Q": 3, "WS": 4, "W": 5, "MS": 6, "Y": 7, "YS": 8}
+
+
+def resample_calendar(frame, index: Column, rule: str, closed_right: bool = False, label_right: bool = False, *,
+                      device=None, stream=None) -> Resampler:
+    """pd::resample(df, "<k><code>", ...) with a DateOffset rule (resample.h:62-88 -> resample.cpp:248-267): D, WS, MS,
+    QS, YS; the month / quarter / week / year END codes and closed_right=False fail like the reference."""
+    import re
+    m = re.fullmatch(r"(\d*)([A-Za-z]+)", rule)
+    if not m or m.group(2) not in OFFSET_TYPES:
+        raise RuntimeError(f"Invalid time offset {rule}")
+    mult = int(m.group(1)) if m.group(1) else 1
+    L = _lib.load()
+    arg = _CArg(index)
+    h = C.c_void_p()
+    opt = _options(0, "auto", device, stream)
+    try:
+        _check(L.pa_resample_create_calendar(C.byref(arg.dev), C.byref(arg.schema), OFFSET_TYPES[m.group(2)], mult,
+                                             int(closed_right), int(label_right), C.byref(opt), C.byref(h)))
+    except Exception:
+        arg.close()
+        raise
+    r = Resampler(None, frame, _handle=h)
+    r._key_args = [arg]
+    return r
+
+
 def downsample(frame, index: Column, rule: str, closed_label_right: bool = True, week_starts_monday: bool = True,
                start_epoch: bool = True, *, device=None, stream=None) -> Resampler:
     """DataFrame::downsample (dataframe.cpp:1265-1290): rule = "<multiple><unit>" with unit in N U L S T H D W M Q Y;

@@ -262,6 +262,44 @@ static void test_resample_series() {
 }
 
 // series_resample_test.cpp:87-130 — DataFrame::downsample
+// pd::resample with DateOffset rules (resample.h:62-88 string rule -> makeGroupInfo's DateOffset branch,
+// resample.cpp:248-267).  Expected values worked out by hand from the reference code; the same case is held to the
+// oracle in tests/test_calendar_cpu.py::test_oracle_calendar_known_answer.
+static void test_resample_calendar_rules() {
+  // hourly ticks 2020-01-31 22:00 .. 2020-02-02 03:00 (30 of them), values 0..29
+  auto index = pd::date_range(pd::ns_from_ymd(2020, 1, 31) + 22LL * 3600 * 1000000000LL, 30, pd::minutes(60));
+  auto series = pd::Series(pd::range(0L, 30L), index, "v");
+  {
+    // "MS": binner 2019-12-01, 2020-01-01, 2020-02-01, 2020-03-01; bucket = (binner + 1 day - 1 ns]: the 26 ticks up to
+    // 2020-02-01 23:00 carry the label 2020-01-01, the last 4 carry 2020-02-01; the empty first bucket does not appear
+    auto resampler = pd::resample(series, "MS", true);
+    auto gi = resampler.index();
+    REQUIRE(gi->length() == 2);
+    REQUIRE(str_at(gi, 0) == "2020-01-01 00:00:00.000000000");
+    REQUIRE(str_at(gi, 1) == "2020-02-01 00:00:00.000000000");
+    auto sum = pd::ReturnOrThrowOnFailure(resampler.sum());
+    REQUIRE(sum.at(0, 0) == int64_t(25 * 26 / 2));
+    REQUIRE(sum.at(1, 0) == int64_t(26 + 27 + 28 + 29));
+    auto cnt = pd::ReturnOrThrowOnFailure(resampler.count());
+    REQUIRE(cnt.at(0, 0) == int64_t(26));
+  }
+  {
+    // "1D", label right: edges are the midnights themselves; a tick AT midnight closes the bucket that ends there
+    auto resampler = pd::resample(series, pd::DateOffset{pd::DateOffset::Day, 1}, true, true);
+    auto gi = resampler.index();
+    REQUIRE(gi->length() == 3);
+    REQUIRE(str_at(gi, 0) == "2020-02-01 00:00:00.000000000");      // ticks 22:00, 23:00, 00:00
+    REQUIRE(str_at(gi, 2) == "2020-02-03 00:00:00.000000000");
+    auto cnt = pd::ReturnOrThrowOnFailure(resampler.count());
+    REQUIRE(cnt.at(0, 0) == int64_t(3));
+    REQUIRE(cnt.at(1, 0) == int64_t(24));
+    REQUIRE(cnt.at(2, 0) == int64_t(3));
+  }
+  REQUIRE_THROWS(pd::resample(series, "MS"));             // closed_left is not currently supported by DateOffset
+  REQUIRE_THROWS(pd::resample(series, "M", true));        // MonthEnd not supported use arrow month().groupby()
+  REQUIRE_THROWS(pd::resample(series, "bogus", true));
+}
+
 static void test_downsample() {
   auto index = pd::date_range(pd::ns_from_ymd(2000, 1, 1), 9);
   pd::DataFrame df(arrow::schema({arrow::field("i", arrow::int64())}), 9, {pd::range(0L, 9L)}, index);
@@ -294,6 +332,7 @@ int main() {
     test_apply_callbacks_and_groups();
     test_second_stage_aggregates();
     test_resample_series();
+    test_resample_calendar_rules();
     test_downsample();
   } catch (std::exception const& e) {
     std::printf("EXCEPTION: %s\n", e.what());

@@ -53,20 +53,24 @@ def test_reference_golden_resample(pab, closed_right, label_right, labels, sums)
 
 
 def _compare(pab, orc, ts, frame, freq, aggs, **kw):
+    idx = pa.array(ts, pa.timestamp("ns"))
+    return _compare_impl(pab, orc, frame, aggs, lambda fr: pab.resample(fr, idx, freq, **kw), lambda rb: orc.resample(rb, idx, freq, **kw))
+
+
+def _compare_impl(pab, orc, frame, aggs, make_ours, make_oracle):
     """Bucket ORDER: the CUDA path emits buckets in time order (= strict first appearance).  The
     reference inherits arrow::compute::Grouper's id order, which may swap buckets that first appear
     inside the same internal mini-batch, so results are aligned by label before comparing.  When the
     reference's own bin generation throws (resample.cpp:28-41), the CUDA path must fail as well."""
     from util import abs_scale, assert_exact, assert_fp_close, with_abs
-    idx = pa.array(ts, pa.timestamp("ns"))
     rb = with_abs(frame)
     try:
-        ora = orc.resample(rb, idx, freq, **kw)
+        ora = make_oracle(rb)
     except orc.OracleError as e:
         with pytest.raises(pab.PaError):
-            pab.resample(frame, idx, freq, **kw).sum()
+            make_ours(frame).sum()
         return None
-    r = pab.resample(frame, idx, freq, **kw)
+    r = make_ours(frame)
     assert r.groupSize() == ora.num_groups
     ours = r.index().cast(pa.int64()).to_numpy()
     theirs = ora.unique().cast(pa.int64()).to_numpy()
@@ -209,3 +213,67 @@ def test_resample_non_nanosecond_index(pab, orc, unit, per):
     if per > 1:
         with pytest.raises(pab.PaError, match="whole multiples"):
             pab.resample(frame, pa.array(ts_ns // per, pa.timestamp(unit)), 1500 if unit != "us" else 1500 + 1)
+
+
+# ---------------- DateOffset (calendar) rules: makeGroupInfo's DateOffset branch, resample.cpp:248-267 ----------------
+def _calendar(pab, orc, ts, frame, code, mult, aggs, label_right=False, closed_right=True):
+    import pandasarrow_b200.groupby as G
+    idx = pa.array(ts, pa.timestamp("ns"))
+    rule = f"{mult}{code}"
+    return _compare_impl(pab, orc, frame, aggs,
+                         lambda fr: G.resample_calendar(fr, idx, rule, closed_right=closed_right, label_right=label_right),
+                         lambda rb: orc.resample_calendar(rb, idx, code, mult, closed_right=closed_right, label_right=label_right))
+
+
+@pytest.mark.parametrize("code,mult", [("D", 1), ("D", 3), ("WS", 1), ("WS", 2), ("MS", 1), ("MS", 5), ("YS", 1)])
+@pytest.mark.parametrize("label_right", [False, True])
+def test_calendar_rules_vs_oracle(pab, orc, code, mult, label_right):
+    # ~3.3 years of irregular ticks (bursts, gaps of days, duplicates, ticks exactly at midnight)
+    rng = np.random.default_rng(sum(map(ord, code)) * 31 + mult)
+    n = 150_000
+    gaps = rng.choice([1, 10**9, 3600 * 10**9, 86400 * 10**9, 9 * 86400 * 10**9], size=n, p=[0.2, 0.5, 0.288, 0.01, 0.002])
+    t0 = int(dt.datetime(2019, 11, 28, 17, 5, tzinfo=dt.timezone.utc).timestamp()) * 10**9
+    ts = t0 + np.cumsum(gaps)
+    day = 86400 * 10**9
+    ts[5000:5003] = (ts[5000] // day) * day            # exactly midnight: belongs to the bucket that ENDS there
+    ts = np.sort(ts)
+    frame = {"px": pa.array(rng.random(n) * 100), "qty": pa.array(rng.integers(0, 1000, n), pa.int64(), mask=rng.random(n) < 0.05)}
+    r = _calendar(pab, orc, ts, frame, code, mult, ALL, label_right=label_right)
+    assert r is not None and r.groupSize() > 3
+
+
+def test_calendar_quarter_start(pab, orc):
+    # date_range only accepts a quarter rule whose first bin starts in January / February (core.cpp:247-250):
+    # first tick in Q2 -> first - 1 quarter = January 1st: accepted; first tick in Q3 -> April 1st: rejected
+    day = 86400 * 10**9
+    ok0 = int(dt.datetime(2021, 5, 10, tzinfo=dt.timezone.utc).timestamp()) * 10**9
+    bad0 = int(dt.datetime(2021, 8, 10, tzinfo=dt.timezone.utc).timestamp()) * 10**9
+    n = 20_000
+    rng = np.random.default_rng(4)
+    frame = {"v": pa.array(rng.standard_normal(n))}
+    r = _calendar(pab, orc, ok0 + np.arange(n, dtype=np.int64) * (day // 40), frame, "QS", 1, ALL)
+    assert r is not None and r.groupSize() >= 5
+    assert _calendar(pab, orc, bad0 + np.arange(n, dtype=np.int64) * (day // 40), frame, "QS", 1, ALL) is None
+
+
+def test_calendar_errors_like_the_reference(pab, orc):
+    import pandasarrow_b200.groupby as G
+    day = 86400 * 10**9
+    idx = pa.array(1_600_000_000 * 10**9 + np.arange(1000, dtype=np.int64) * day, pa.timestamp("ns"))
+    frame = {"v": pa.array(np.arange(1000, dtype=np.float64))}
+    for rule, msg in (("M", "MonthEnd not supported"), ("Q", "QuarterEnd not supported"), ("W", "WeekEnd not supported"), ("Y", "YearEnd not supported")):
+        with pytest.raises(pab.PaError, match=msg):
+            G.resample_calendar(frame, idx, rule, closed_right=True)
+        with pytest.raises(orc.OracleError, match=msg):
+            orc.resample_labels_calendar(idx, rule, 1, True)
+    with pytest.raises(pab.PaError, match="closed_left is not currently supported"):
+        G.resample_calendar(frame, idx, "MS", closed_right=False)
+    # fewer rows than buckets: upSampling (resample.h:102-105)
+    sparse = pa.array(1_600_000_000 * 10**9 + np.arange(5, dtype=np.int64) * 40 * day, pa.timestamp("ns"))
+    with pytest.raises(pab.PaError, match="upSampling"):
+        G.resample_calendar({"v": pa.array(np.arange(5.0))}, sparse, "D", closed_right=True)
+    with pytest.raises(orc.OracleError, match="upSampling"):
+        orc.resample_labels_calendar(sparse, "D", 1, True)
+    us = pa.array(np.arange(1000, dtype=np.int64) * 86400 * 10**6, pa.timestamp("us"))
+    with pytest.raises(pab.PaError, match=r"timestamp\[ns\]"):
+        G.resample_calendar(frame, us, "MS", closed_right=True)
