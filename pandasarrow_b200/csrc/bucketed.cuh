@@ -1,32 +1,42 @@
 // Medium / high cardinality (more groups than one shared-memory table holds): radix-partition the rows into
 // buckets whose distinct keys fit a CTA's shared-memory table, then aggregate bucket by bucket in shared memory.
-// No global-memory atomics per row, no global hash table: every key lives in exactly one bucket, so a bucket's
-// groups are final when its rows are done and are appended to the output as they are.
+// No global-memory atomics per row, no global hash table in the steady state: every key lives in exactly one bucket.
 //
-//   m = rp_mix(key)                 bijective 64-bit mix; its TOP bits pick the bucket, the next bits the table slot
-//   k_rp_hist1      level 1: rows per bucket (1024 buckets = top 10 bits) + a HyperLogLog sketch of the keys
-//                   (4096 registers, fed by the 1/8 of the key space whose mix ends in 000) -> estimated group count,
-//                   from which the host picks the total number of bucket bits B (buckets of ~CAP/4 keys)
-//   k_rp_offsets1   exclusive prefix of the 1024 counts -> write cursors
-//   k_rp_scatter    per tile of 4096 rows: shared-memory histogram gives every row its rank inside the tile's run for
-//                   its bucket, the tile is regrouped in shared memory and written out as contiguous runs (one global
-//                   cursor add per bucket and tile) together with the ORIGINAL ROW NUMBERS (first / last need them)
-//   B > 10 (more than ~2 M groups): level 2 inside every level-1 bucket on the next B - 10 bits —
-//   k_rp_tiles      tiles per level-1 bucket (tiles never straddle a bucket) -> prefix
-//   k_rp_hist2      rows per (level-1 bucket, sub-bucket): shared-memory histogram of the current parent, flushed
-//                   when a CTA's contiguous tile range moves on to the next parent
-//   (device-wide exclusive scan, order.cuh) and k_rp_scatter again, reading the level-1 output
-//   k_bucket_agg    one CTA per bucket at a time (buckets handed out by an atomic counter): CTA-shared open-addressing
-//                   table in shared memory (8192 slots narrow / 4096 wide), ATOMS.CAS.64 to claim a key, shared-memory
-//                   atomics for sum / count / first / last / min / max exactly like k_smemtab_scan; when the bucket's
-//                   rows are done its groups are appended to the unordered result (one global counter add per
-//                   bucket) and the slots are reset in the same sweep
-//   k_bm_rank_scatter  first-appearance order by bitmap rank (order.cuh), writing the GroupResult directly
+//   m = rp_mix(key)               bijective 64-bit mix; its TOP bits pick the bucket, the next bits the table slot
+//   k_rp_hist<true>               rows per (chunk of 65 536 rows, one of 1024 fine buckets) + a HyperLogLog sketch of the
+//                                 keys (4096 registers, fed by the 1/8 of the key space whose mix ends in 000) -> estimated
+//                                 group count, from which the host picks B = log2(#buckets) (buckets of ~CAP/2 keys).
+//                                 Keys only: computed ONCE per handle (a handle's keys never change) and reused by every
+//                                 later aggregate on it, like the reference reuses its constructor's groupings.
+//   k_rp_fold + scan + k_rp_ends  fine counts -> "flat" layout [bucket][chunk] -> ONE exclusive scan = the output position
+//                                 of every chunk's first row of every bucket (buckets contiguous, chunks in row order)
+//   k_rp_scatter                  per chunk: cursors loaded into shared memory and advanced privately; per tile of 4096
+//                                 rows a shared-memory histogram ranks the rows, the tile is regrouped in shared memory
+//                                 and written out as contiguous runs together with the ORIGINAL ROW NUMBERS (first / last
+//                                 need them).  No global atomics, stable at tile granularity, same output every pass.
+//                                 Cost grows with the fan-out (runs of 4096 / fan rows): 7.7 / 8.4 / 10.5 / 15 / 25 / 43 ms
+//                                 per 1 B rows at 32 / 64 / 128 / 256 / 512 / 1024 ways (DRAM sees 128-byte pieces)
+//   B <= 7 : one level.   B > 7 : two levels, ceil(B/2) bits then the rest inside every level-1 bucket
+//   k_rp_cprefix, k_rp_hist<false>, scan, k_rp_ends, k_rp_scatter again, reading the level-1 output (retaken every pass:
+//                                 inside a tile's run the level-1 scatter orders rows by atomic arrival)
+//   k_bucket_agg                  CTA-shared open-addressing table in shared memory (8192 slots narrow / 4096 wide),
+//                                 ATOMS.CAS.64 to claim a key, shared-memory atomics for sum / count / first / last / min /
+//                                 max exactly like k_smemtab_scan.  Two modes:
+//                                   whole buckets (>= 4 x #SM buckets): one CTA per bucket at a time (atomic work counter);
+//                                     a finished bucket's groups are appended to the unordered result as sector-sized
+//                                     records and the slots are reset in the same sweep;
+//                                   ranged (fewer buckets): every CTA takes an equal, contiguous share of the partitioned
+//                                     rows and flushes its table into the global table (gtable.cuh) at every bucket
+//                                     boundary — a few L2 atomics per group and CTA, none per row — after which the
+//                                     ordinary compaction / ordering of the global path runs.
+//   k_bm_* + k_bm_rank + k_bk_gather  first-appearance order by bitmap rank (order.cuh): a 4-byte permutation is scattered,
+//                                 then every output position fetches its group's record (one or two adjacent sectors)
 //
-// DRAM traffic per row (8-byte key + 8-byte value): hist 8 B, scatter 16 + 20 B, aggregate 20 B = 64 B for one level
-// (+ 8 + 20 + 20 B for the second level) against 16 B algorithmic: the floor of this design is 0.25 (0.14) of the
-// 16 B/row roofline.  Only for 8-byte keys and values without validity bitmaps; anything else, and any bucket that
-// turns out to hold more keys than its table (ST_OVERFLOW), goes to the global-table path (gtable.cuh).
+// DRAM traffic per row (8-byte key + 8-byte value): scatter 16 + 20 B, aggregate 20 B = 56 B for one level (+ 8 B for
+// the histogram on a handle's first pass); + 8 + 20 + 20 B for the second level = 104 B, against 16 B algorithmic: the
+// floor of this design is 0.29 (one level) / 0.15 (two levels) of the 16 B/row roofline.  Only for 8-byte keys and
+// values without validity bitmaps; anything else, and any bucket that turns out to hold more keys than its table
+// (ST_OVERFLOW), goes to the global-table path (gtable.cuh).
 // Replaces Grouper::Consume + per-group CallFunction (/root/reference/src/dataframe.cpp:1582-1584,
 // pd_core_macros.h:114-147) for the cardinalities where the reference's per-group loop takes seconds.
 #pragma once

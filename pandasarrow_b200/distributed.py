@@ -144,7 +144,7 @@ def exchange_padded(send_blocks, group=None):
 
 
 def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_format: str, group=None, stream=None,
-                      padded: Optional[bool] = None, wait: bool = True):
+                      padded: Optional[bool] = None, wait: bool = True, tail_stream=None):
     """Run the whole multi-GPU step for this rank.  `gb` is this rank's GroupBy over its row shard
     (created with row_base = first global row of the shard).  Returns the owner-side MergedGroupBy.
 
@@ -155,7 +155,11 @@ def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_fo
 
     wait=False (padded path only): nothing is read back at all — local pass, export, exchange and merge are just
     queued, so consecutive steps pipeline; the first call on the returned handle that needs a result completes
-    it (and raises PaError if a rank had overflowed: rerun that step with wait=True)."""
+    it (and raises PaError if a rank had overflowed: rerun that step with wait=True).
+
+    tail_stream (a torch.cuda.Stream, padded path only): the exchange and the merge run on it, behind an event recorded
+    after the export — the handle's own stream is free for the next step's local pass while this step's records travel
+    and merge (the serial tail is launch / NCCL latency on a handful of CTAs)."""
     import torch
     import torch.distributed as dist
     from .groupby import MergedGroupBy, PaError
@@ -171,10 +175,20 @@ def sharded_aggregate(gb, values, aggs: Sequence[str], value_format: str, key_fo
         cap = PADDED_BLOCK_RECORDS
         send = torch.empty((world, cap + 1, PA_PARTIAL_WORDS), dtype=torch.int64, device=dev)
         gb.partials_export_padded(world, send.data_ptr(), cap)
-        recv = exchange_padded(send, group)
         try:
-            merged = MergedGroupBy(recv.data_ptr(), [0] * world, aggs, value_format, key_format, device=dev.index,
-                                   stream=stream, padded_block_records=cap)
+            if tail_stream is None:
+                recv = exchange_padded(send, group)
+                merged = MergedGroupBy(recv.data_ptr(), [0] * world, aggs, value_format, key_format, device=dev.index,
+                                       stream=stream, padded_block_records=cap)
+            else:
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream(dev))
+                send.record_stream(tail_stream)
+                with torch.cuda.stream(tail_stream):
+                    tail_stream.wait_event(done)
+                    recv = exchange_padded(send, group)
+                    merged = MergedGroupBy(recv.data_ptr(), [0] * world, aggs, value_format, key_format, device=dev.index,
+                                           stream=tail_stream.cuda_stream, padded_block_records=cap)
             merged._keep = (send, recv)
             if wait:
                 merged.groupSize()          # completes the merge; raises if any rank sent the overflow marker
