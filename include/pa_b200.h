@@ -273,6 +273,25 @@ int pa_downsample_create(const struct ArrowDeviceArray* index, const struct Arro
                          char unit, int32_t closed_label_right, int32_t week_starts_monday, int32_t calendar_based_origin,
                          const pa_options* opt, pa_groupby** out);
 
+/* ---- ingest: DataFrame::readBinary / readParquet (dataframe.cpp:757-791, 646-683) leave host
+ * Arrow arrays (an IPC blob, a decoded Parquet table).  pa_column_to_device copies one such array to the device ONCE —
+ * pageable memory through the library's pinned, multi-threaded staging pipeline, i.e. at the PCIe rate — and returns an
+ * ArrowDeviceArray with device_type ARROW_DEVICE_CUDA that owns its device buffers (out->array.release frees them;
+ * `schema` keeps describing it).  Every other entry point then uses the column in place: the constructor and every
+ * aggregate after it stop paying PCIe.  Fixed-width, boolean and (large_)utf8 columns; slices are honoured. */
+int pa_column_to_device(const struct ArrowDeviceArray* host, const struct ArrowSchema* schema, const pa_options* opt,
+                        struct ArrowDeviceArray* out);
+
+/* ---- stable argsort: Series::argsort / Series::sort / DataFrame::sort_index / sort_values
+ * (series.cpp:864-868,978-992, dataframe.cpp:1062-1071,1188-1208), which the reference gets from arrow::compute
+ * "array_sort_indices" + Take.  Same ordering rules: stable, NaNs after every number and nulls after the NaNs in BOTH
+ * orders.  Numeric and 64-bit temporal columns, < 2^31 rows.  The returned handle is a pa_groupby in "sorted" state:
+ * pa_sort_indices returns the uint64 indices, pa_groupby_take_grouped(handle, column) returns any column of the same
+ * length in sorted order (scatter-shaped take, fixed-width and boolean columns), pa_groupby_destroy frees it. */
+int pa_sort_create(const struct ArrowDeviceArray* values, const struct ArrowSchema* schema, int32_t ascending,
+                   const pa_options* opt, pa_groupby** out);
+int pa_sort_indices(pa_groupby* sorted, struct ArrowArray* out, struct ArrowSchema* out_schema);
+
 /* ---- multi-GPU: row-range shards, hash-partitioned partial aggregates, merge ----
  * The reference has no multi-device path.  Each rank aggregates its shard (pa_options.row_base =
  * global row number of its first row), buckets its groups by owner = hash(key) % n_parts into

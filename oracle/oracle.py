@@ -57,6 +57,7 @@ def lib():
         L.orc_resample_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                           C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_resample_labels_calendar.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_array_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_downsample_labels.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char, C.c_int, C.c_int,
                                             C.c_int, C.c_void_p, C.c_void_p]
         L.orc_scalar_agg.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -181,6 +182,15 @@ def resample_labels_calendar(index: pa.Array, code: str, multiplier: int = 1, cl
 def resample_calendar(frame: pa.RecordBatch, index: pa.Array, code: str, multiplier: int = 1, **kw) -> "OracleGroupBy":
     labels = resample_labels_calendar(index, code, multiplier, **kw)
     return OracleGroupBy(frame, "__resampler_idx__", index=labels)
+
+
+def array_sort(values: pa.Array, ascending: bool = True, take: bool = False) -> pa.Array:
+    """Series::argsort (take=False: the uint64 indices) / Series::sort (take=True: the sorted values): arrow's
+    array_sort_indices [+ Take] exactly as series.cpp:864-868,978-992 call them."""
+    ia, isch = _export(values)
+    a, s = _ArrowArray(), _ArrowSchema()
+    _check(lib().orc_array_sort(C.addressof(ia), C.addressof(isch), int(ascending), int(take), C.addressof(a), C.addressof(s)))
+    return _import_array(a, s)
 
 
 def downsample_labels(index: pa.Array, multiple: int, unit: str, closed_label_right=False,

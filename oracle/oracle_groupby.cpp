@@ -702,6 +702,26 @@ int orc_resample_labels_calendar(ArrowArray* index, ArrowSchema* index_schema, i
   return st.ok() ? 0 : fail(st);
 }
 
+// Series::argsort / Series::sort (series.cpp:864-868, 978-992): CallFunction("array_sort_indices", {array},
+// ArraySortOptions{order}) and Take(array, indices) — DataFrame::sort_index (dataframe.cpp:1062-1071) applies the same
+// indices to every column.  take_sorted = 1 returns Take(values, indices) instead of the indices.
+int orc_array_sort(ArrowArray* values, ArrowSchema* schema, int ascending, int take_sorted, ArrowArray* out, ArrowSchema* out_schema) {
+  ensure_compute_initialized();
+  auto arr = arrow::ImportArray(values, schema);
+  if (!arr.ok()) return fail(arr.status());
+  ac::ArraySortOptions opt{ascending ? ac::SortOrder::Ascending : ac::SortOrder::Descending};
+  auto idx = ac::CallFunction("array_sort_indices", {*arr}, &opt);
+  if (!idx.ok()) return fail(idx.status());
+  std::shared_ptr<Array> res = idx->make_array();
+  if (take_sorted) {
+    auto t = ac::Take(*arr, idx->make_array());
+    if (!t.ok()) return fail(t.status());
+    res = t->make_array();
+  }
+  auto st = export_array(res, out, out_schema);
+  return st.ok() ? 0 : fail(st);
+}
+
 int orc_downsample_labels(ArrowArray* index, ArrowSchema* index_schema, int multiple, char unit,
                           int closed_label_right, int week_starts_monday, int start_epoch,
                           ArrowArray* out, ArrowSchema* out_schema) {

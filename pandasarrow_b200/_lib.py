@@ -23,7 +23,7 @@ EXPORTS = [
     "pa_groupby_fetch", "pa_column_aggregate",
     "pa_groupby_row_ids", "pa_groupby_groupings", "pa_groupby_take_grouped", "pa_groupby_groupings_timing", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
     "pa_groupby_sync",
-    "pa_groupby_destroy", "pa_resample_create", "pa_resample_create_calendar", "pa_downsample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
+    "pa_groupby_destroy", "pa_column_to_device", "pa_sort_create", "pa_sort_indices", "pa_resample_create", "pa_resample_create_calendar", "pa_downsample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
     "pa_merge_create", "pa_groupby_partials_export_padded", "pa_merge_create_padded", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
     "pa_synth_validity", "pa_synth_timestamps",
     "pa_comm_unique_id", "pa_comm_create", "pa_comm_adopt", "pa_comm_destroy", "pa_groupby_sharded_aggregate", "pa_comm_last_phases",
@@ -119,6 +119,9 @@ def load():
     L.pa_groupby_destroy.restype = None
     L.pa_resample_create.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_int64, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.POINTER(PaOptions), C.POINTER(P)]
+    L.pa_column_to_device.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.POINTER(PaOptions), C.POINTER(ArrowDeviceArray)]
+    L.pa_sort_create.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_int32, C.POINTER(PaOptions), C.POINTER(P)]
+    L.pa_sort_indices.argtypes = [P, C.POINTER(ArrowArray), C.POINTER(ArrowSchema)]
     L.pa_resample_create_calendar.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_int32, C.c_int32,
                                               C.c_int32, C.c_int32, C.POINTER(PaOptions), C.POINTER(P)]
     L.pa_downsample_create.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_int32, C.c_char, C.c_int32,

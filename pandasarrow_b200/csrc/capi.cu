@@ -15,6 +15,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pa_b200.h"
@@ -32,6 +33,7 @@
 #include "temporal.cuh"
 #include "order.cuh"
 #include "csort.cuh"
+#include "sort.cuh"
 #include "strkeys.cuh"
 
 using namespace pa;
@@ -155,6 +157,106 @@ int parse_format(const char* f, int* width, int* vc) {
   return set_err(PA_ERR_INVALID, "unsupported Arrow format '%s' (fixed-width numeric / temporal only)", f);
 }
 
+// Host -> device copy of a column buffer.  Pinned source: one cudaMemcpyAsync at the PCIe rate.  Pageable source
+// (ordinary Arrow heap buffers — what pd::DataFrame holds —, an IPC blob, Parquet-decoded columns): the driver would
+// bounce it through its own small staging area at a fraction of that rate, so anything large goes through the
+// library's two pinned staging buffers, filled by a few host threads while the previous chunk is on the wire.
+namespace {
+constexpr size_t H2D_CHUNK = 8u << 20;            // bytes per staging buffer (two per worker)
+constexpr size_t H2D_STAGED_MIN = 16u << 20;      // smaller copies are not worth the pipeline
+constexpr int H2D_MAX_WORKERS = 16;
+struct H2dWorker {
+  void* pin[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {};
+  cudaEvent_t fin = nullptr;
+  cudaStream_t stream = nullptr;
+};
+struct H2dStage {
+  std::mutex mu;
+  H2dWorker w[H2D_MAX_WORKERS];
+  cudaEvent_t start = nullptr;
+  bool ok = false, tried = false;
+  int workers = 1;
+};
+H2dStage g_h2d_dev[16];   // one per device: streams and events belong to a device
+
+bool h2d_stage_ready(H2dStage& g) {
+  if (g.tried) return g.ok;
+  g.tried = true;
+  if (const char* e = getenv("PA_H2D_STAGED")) { if (atoi(e) == 0) return false; }
+  const unsigned hc = std::thread::hardware_concurrency();
+  g.workers = static_cast<int>(std::max(1u, std::min(8u, hc ? hc / 2 : 4u)));
+  if (const char* e = getenv("PA_H2D_THREADS")) g.workers = std::max(1, std::min(H2D_MAX_WORKERS, atoi(e)));
+  if (cudaEventCreateWithFlags(&g.start, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+  for (int i = 0; i < g.workers; ++i) {
+    H2dWorker& w = g.w[i];
+    bool good = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&w.fin, cudaEventDisableTiming) == cudaSuccess;
+    for (int b = 0; b < 2 && good; ++b)
+      good = cudaHostAlloc(&w.pin[b], H2D_CHUNK, cudaHostAllocPortable) == cudaSuccess &&
+             cudaEventCreateWithFlags(&w.done[b], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) { cudaGetLastError(); return false; }
+  }
+  g.ok = true;
+  return true;
+}
+}  // namespace
+
+// Every worker thread owns a contiguous slice of the copy, two pinned buffers and a stream: it copies a chunk into
+// one buffer while the DMA engine drains the other.  The destination was allocated in stream order on `st`, so the
+// worker streams start behind an event on `st`, and `st` continues behind the workers' last copies.
+int h2d_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return PA_OK;
+  bool pageable = false;
+  if (bytes >= H2D_STAGED_MIN) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, src) != cudaSuccess) { cudaGetLastError(); pageable = true; }
+    else pageable = at.type == cudaMemoryTypeUnregistered;
+  }
+  if (!pageable) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return PA_OK;
+  }
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  H2dStage& g = g_h2d_dev[dev & 15];
+  std::lock_guard<std::mutex> lock(g.mu);
+  if (!h2d_stage_ready(g)) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return PA_OK;
+  }
+  CUDA_TRY(cudaEventRecord(g.start, st));
+  const int T = g.workers;
+  const size_t per = ((bytes + T - 1) / T + 4095) & ~static_cast<size_t>(4095);
+  std::vector<cudaError_t> err(T, cudaSuccess);
+  auto work = [&](int t) {
+    H2dWorker& w = g.w[t];
+    cudaError_t e = cudaSetDevice(dev);
+    const size_t lo = per * t, hi = std::min(bytes, lo + per);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(w.stream, g.start, 0);
+    int b = 0;
+    for (size_t off = lo; off < hi && e == cudaSuccess; off += H2D_CHUNK, b ^= 1) {
+      const size_t len = std::min(H2D_CHUNK, hi - off);
+      e = cudaEventSynchronize(w.done[b]);                 // the previous copy out of this buffer has finished
+      if (e != cudaSuccess) break;
+      memcpy(w.pin[b], static_cast<const char*>(src) + off, len);
+      e = cudaMemcpyAsync(static_cast<char*>(dst) + off, w.pin[b], len, cudaMemcpyHostToDevice, w.stream);
+      if (e == cudaSuccess) e = cudaEventRecord(w.done[b], w.stream);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(w.fin, w.stream);
+    err[t] = e;
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < T; ++t) {
+    if (err[t] != cudaSuccess) return set_err(PA_ERR_CUDA, "staged host-to-device copy failed: %s", cudaGetErrorString(err[t]));
+    CUDA_TRY(cudaStreamWaitEvent(st, g.w[t].fin, 0));
+  }
+  return PA_OK;
+}
+
 // Bring one primitive Arrow array onto the device (or borrow it when it already is there).
 int load_column(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t st, int device, Column* out) {
   const ArrowArray& a = da->array;
@@ -180,7 +282,7 @@ int load_column(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t 
     const uint8_t* bits = reinterpret_cast<const uint8_t*>(values) + first_byte;
     if (!on_dev) {
       PA_TRY(out->own_bits.alloc(std::max<size_t>(nbytes, 1), st));
-      if (nbytes) CUDA_TRY(cudaMemcpyAsync(out->own_bits.p, bits, nbytes, cudaMemcpyHostToDevice, st));
+      PA_TRY(h2d_copy(out->own_bits.p, bits, nbytes, st));
       bits = out->own_bits.as<uint8_t>();
     }
     PA_TRY(out->own_data.alloc(static_cast<size_t>(std::max<int64_t>(a.length, 1)), st));
@@ -196,7 +298,7 @@ int load_column(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t 
         out->bit_off = a.offset;
       } else {
         PA_TRY(out->own_valid.alloc(nbytes, st));
-        CUDA_TRY(cudaMemcpyAsync(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, cudaMemcpyHostToDevice, st));
+        PA_TRY(h2d_copy(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, st));
         out->valid = out->own_valid.as<uint8_t>();
         out->bit_off = a.offset % 8;
       }
@@ -212,14 +314,14 @@ int load_column(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStream_t 
   } else if (da->device_type == ARROW_DEVICE_CPU || da->device_type == ARROW_DEVICE_CUDA_HOST) {
     const size_t bytes = static_cast<size_t>(a.length) * out->width;
     PA_TRY(out->own_data.alloc(bytes, st));
-    if (bytes) CUDA_TRY(cudaMemcpyAsync(out->own_data.p, values + a.offset * out->width, bytes, cudaMemcpyHostToDevice, st));
+    PA_TRY(h2d_copy(out->own_data.p, values + a.offset * out->width, bytes, st));
     out->data = out->own_data.p;
     if (has_nulls) {
       // copy the bytes that cover bits [offset, offset+length); keep the sub-byte offset
       const int64_t first_byte = a.offset / 8;
       const size_t nbytes = static_cast<size_t>((a.offset + a.length + 7) / 8 - first_byte);
       PA_TRY(out->own_valid.alloc(nbytes, st));
-      CUDA_TRY(cudaMemcpyAsync(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, cudaMemcpyHostToDevice, st));
+      PA_TRY(h2d_copy(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, st));
       out->valid = out->own_valid.as<uint8_t>();
       out->bit_off = a.offset % 8;
     }
@@ -270,17 +372,17 @@ int load_string_key(const ArrowDeviceArray* da, const ArrowSchema* sc, cudaStrea
       last = wide ? reinterpret_cast<const int64_t*>(offs)[n] : reinterpret_cast<const int32_t*>(offs)[n];
     }
     PA_TRY(out->own_offsets.alloc(static_cast<size_t>(n + 1) * ow, st));
-    if (a.buffers[1]) CUDA_TRY(cudaMemcpyAsync(out->own_offsets.p, offs, static_cast<size_t>(n + 1) * ow, cudaMemcpyHostToDevice, st));
+    if (a.buffers[1]) PA_TRY(h2d_copy(out->own_offsets.p, offs, static_cast<size_t>(n + 1) * ow, st));
     else CUDA_TRY(cudaMemsetAsync(out->own_offsets.p, 0, static_cast<size_t>(n + 1) * ow, st));
     PA_TRY(out->own_bytes.alloc(static_cast<size_t>(std::max<int64_t>(last - first, 1)), st));
-    if (last > first) CUDA_TRY(cudaMemcpyAsync(out->own_bytes.p, bytes + first, static_cast<size_t>(last - first), cudaMemcpyHostToDevice, st));
+    if (last > first) PA_TRY(h2d_copy(out->own_bytes.p, bytes + first, static_cast<size_t>(last - first), st));
     out->str.offsets = out->own_offsets.p;
     out->str.bytes = out->own_bytes.as<uint8_t>() - first;       // offsets stay absolute
     if (has_nulls) {
       const int64_t first_byte = a.offset / 8;
       const size_t nbytes = static_cast<size_t>((a.offset + a.length + 7) / 8 - first_byte);
       PA_TRY(out->own_valid.alloc(nbytes, st));
-      CUDA_TRY(cudaMemcpyAsync(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, cudaMemcpyHostToDevice, st));
+      PA_TRY(h2d_copy(out->own_valid.p, static_cast<const uint8_t*>(a.buffers[0]) + first_byte, nbytes, st));
       out->valid = out->own_valid.as<uint8_t>();
       out->bit_off = a.offset % 8;
     }
@@ -369,6 +471,7 @@ struct pa_groupby {
   // group materialisation (groupings.cuh), built on first use; keys are immutable so it never goes stale
   DevBuf grp_order, grp_offsets, grp_dest;
   bool have_groupings = false;
+  bool sorted_state = false;              // handle made by pa_sort_create: grp_order / grp_dest hold the sorted row order
   // Scratch of the global-table / resample passes, kept between calls on the handle: returning multi-GB blocks to
   // the stream-ordered pool and asking for them again fragments it (cudaMallocAsync then takes 50-1700 ms per call
   // at 100 M groups); a repeated aggregate on the same handle reuses these without touching the allocator.
@@ -2527,6 +2630,222 @@ int pa_downsample_create(const struct ArrowDeviceArray* index, const struct Arro
   return PA_OK;
 }
 
+// ---- ingest: one host Arrow array -> device-resident ArrowDeviceArray ----
+// What DataFrame::readBinary / readParquet (dataframe.cpp:757-791, 646-683) produce are host Arrow arrays inside an IPC
+// blob or a decoded table; this puts a column on the device ONCE (pageable memory through the pinned staging pipeline of
+// h2d_copy) and hands back an ArrowDeviceArray(CUDA) that every other entry point uses in place, so that the
+// constructor and every aggregate after it stop paying PCIe.
+namespace {
+struct DevArrayPriv {
+  void* owned[3] = {nullptr, nullptr, nullptr};
+  const void* bufs[3] = {nullptr, nullptr, nullptr};
+};
+void dev_array_release(struct ArrowArray* a) {
+  if (!a || !a->release) return;
+  auto* p = static_cast<DevArrayPriv*>(a->private_data);
+  if (p) {
+    for (void* q : p->owned) if (q) cudaFree(q);
+    delete p;
+  }
+  a->release = nullptr;
+}
+}  // namespace
+
+int pa_column_to_device(const struct ArrowDeviceArray* host, const struct ArrowSchema* schema, const pa_options* opt,
+                        struct ArrowDeviceArray* out) {
+  if (!host || !schema || !out || !schema->format) return set_err(PA_ERR_INVALID, "pa_column_to_device: null argument");
+  if (host->device_type != ARROW_DEVICE_CPU && host->device_type != ARROW_DEVICE_CUDA_HOST)
+    return set_err(PA_ERR_INVALID, "pa_column_to_device: the input must be a host array");
+  if (schema->dictionary) return set_err(PA_ERR_NOT_IMPLEMENTED, "pa_column_to_device: dictionary-encoded columns (ingest the indices)");
+  const ArrowArray& a = host->array;
+  const char f0 = schema->format[0];
+  const bool is_str = f0 == 'u' || f0 == 'U';
+  const bool is_bool = f0 == 'b';
+  int width = 0, vc = 0;
+  if (!is_str) PA_TRY(parse_format(schema->format, &width, &vc));
+  if (a.n_buffers < (is_str ? 3 : 2)) return set_err(PA_ERR_INVALID, "unexpected buffer count %lld for format '%s'", (long long)a.n_buffers, schema->format);
+  int device = 0;
+  if (opt && opt->device >= 0) device = opt->device; else CUDA_TRY(cudaGetDevice(&device));
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = opt && opt->cuda_stream ? static_cast<cudaStream_t>(opt->cuda_stream) : nullptr;
+  std::unique_ptr<DevArrayPriv> p(new DevArrayPriv());
+  struct Guard { DevArrayPriv* p; ~Guard() { if (p) for (void* q : p->owned) if (q) cudaFree(q); } } guard{p.get()};
+  const int64_t k = a.offset % 8, start = a.offset - k, n = a.length;
+  const bool has_nulls = a.null_count != 0 && a.buffers[0] != nullptr;
+  const size_t bit_bytes = static_cast<size_t>((k + n + 7) / 8);
+  if (has_nulls) {
+    CUDA_TRY(cudaMalloc(&p->owned[0], std::max<size_t>(bit_bytes, 16)));
+    PA_TRY(h2d_copy(p->owned[0], static_cast<const uint8_t*>(a.buffers[0]) + start / 8, bit_bytes, st));
+    p->bufs[0] = p->owned[0];
+  }
+  if (is_str) {
+    const int ow = f0 == 'U' ? 8 : 4;
+    const char* offs = static_cast<const char*>(a.buffers[1]) + start * ow;
+    const size_t obytes = static_cast<size_t>(k + n + 1) * ow;
+    CUDA_TRY(cudaMalloc(&p->owned[1], std::max<size_t>(obytes, 16)));
+    int64_t first = 0, last = 0;
+    if (a.buffers[1]) {
+      PA_TRY(h2d_copy(p->owned[1], offs, obytes, st));
+      first = ow == 8 ? reinterpret_cast<const int64_t*>(offs)[0] : reinterpret_cast<const int32_t*>(offs)[0];
+      last = ow == 8 ? reinterpret_cast<const int64_t*>(offs)[k + n] : reinterpret_cast<const int32_t*>(offs)[k + n];
+    } else {
+      CUDA_TRY(cudaMemsetAsync(p->owned[1], 0, obytes, st));
+    }
+    CUDA_TRY(cudaMalloc(&p->owned[2], static_cast<size_t>(std::max<int64_t>(last - first, 16))));
+    if (last > first) PA_TRY(h2d_copy(p->owned[2], static_cast<const uint8_t*>(a.buffers[2]) + first, static_cast<size_t>(last - first), st));
+    p->bufs[1] = p->owned[1];
+    p->bufs[2] = static_cast<const uint8_t*>(p->owned[2]) - first;     // offsets stay absolute
+  } else if (is_bool) {
+    CUDA_TRY(cudaMalloc(&p->owned[1], std::max<size_t>(bit_bytes, 16)));
+    if (a.buffers[1]) PA_TRY(h2d_copy(p->owned[1], static_cast<const uint8_t*>(a.buffers[1]) + start / 8, bit_bytes, st));
+    p->bufs[1] = p->owned[1];
+  } else {
+    const size_t bytes = static_cast<size_t>(k + n) * width;
+    CUDA_TRY(cudaMalloc(&p->owned[1], std::max<size_t>(bytes, 16)));
+    if (a.buffers[1]) PA_TRY(h2d_copy(p->owned[1], static_cast<const char*>(a.buffers[1]) + start * width, bytes, st));
+    p->bufs[1] = p->owned[1];
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memset(out, 0, sizeof *out);
+  out->array.length = n;
+  out->array.null_count = has_nulls ? a.null_count : 0;
+  out->array.offset = k;
+  out->array.n_buffers = is_str ? 3 : 2;
+  out->array.n_children = 0;
+  out->array.buffers = p->bufs;
+  out->array.release = dev_array_release;
+  out->device_id = device;
+  out->device_type = ARROW_DEVICE_CUDA;
+  out->sync_event = nullptr;
+  guard.p = nullptr;
+  out->array.private_data = p.release();
+  return PA_OK;
+}
+
+// ---- stable argsort of one column (sort.cuh): Series::sort / argsort, DataFrame::sort_index / sort_values ----
+// The result lives on a pa_groupby handle in "sorted" state: its row order / inverse order are what a groupings build
+// leaves there, so pa_groupby_take_grouped takes any column into sorted order with the scatter-shaped kernel.
+}  // extern "C"
+template <int VC>
+static int sort_build_t(pa_groupby* g, const Column& col, bool descending) {
+  cudaStream_t st = g->stream;
+  const int64_t n = g->n;
+  const size_t nb4 = static_cast<size_t>(std::max<int64_t>(n, 1)) * 4, nb8 = nb4 * 2;
+  PA_TRY(g->grp_order.alloc(nb4, st));
+  PA_TRY(g->grp_dest.alloc(nb4, st));
+  if (n == 0) return PA_OK;
+  DevBuf keys_a, keys_b, pay_a, pay_b, cls, hist, counts, tile_sums;
+  PA_TRY(keys_a.alloc(nb8, st));
+  PA_TRY(cls.alloc(static_cast<size_t>(n), st));
+  PA_TRY(hist.alloc(sizeof(uint32_t) * (LS_DIGITS * CS_R + 4), st));
+  CUDA_TRY(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * (LS_DIGITS * CS_R + 4), st));
+  SortKeyArgs ka{};
+  ka.vals = col.data; ka.valid = col.valid; ka.voff = col.bit_off; ka.n = n; ka.vw = col.width; ka.descending = descending ? 1 : 0;
+  ka.keys = keys_a.as<uint64_t>(); ka.cls = cls.as<uint8_t>(); ka.hist = hist.as<uint32_t>(); ka.flags = hist.as<uint32_t>() + LS_DIGITS * CS_R;
+  const int kgrid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 511) / 512, static_cast<int64_t>(g->num_sms) * 4)));
+  k_sort_keys<VC><<<kgrid, 512, 0, st>>>(ka);
+  CUDA_TRY(cudaGetLastError());
+  std::vector<uint32_t> h(LS_DIGITS * CS_R + 4);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), hist.p, h.size() * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  // passes: every digit that is not constant over the column, then the class byte when NaNs / nulls exist
+  std::vector<int> passes;
+  for (int d = 0; d < LS_DIGITS; ++d) {
+    bool constant = false;
+    for (int b = 0; b < CS_R; ++b) if (h[d * CS_R + b] == static_cast<uint64_t>(n)) { constant = true; break; }
+    if (!constant) passes.push_back(d);
+  }
+  if (h[LS_DIGITS * CS_R] & 1u) passes.push_back(-1);
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+  if (passes.empty()) {
+    k_ls_identity<<<grid, 256, 0, st>>>(g->grp_order.as<uint32_t>(), g->grp_dest.as<uint32_t>(), n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return PA_OK;
+  }
+  const int64_t ntiles = (n + CS_TILE - 1) / CS_TILE;
+  const int nb = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, static_cast<int64_t>(g->num_sms) * 4)));
+  const int64_t chunk = ((ntiles + nb - 1) / nb) * CS_TILE;
+  PA_TRY(counts.alloc(sizeof(uint32_t) * CS_R * static_cast<size_t>(nb), st));
+  if (passes.size() > 1) {
+    PA_TRY(keys_b.alloc(nb8, st));
+    PA_TRY(pay_a.alloc(nb4, st));
+    if (passes.size() > 2) PA_TRY(pay_b.alloc(nb4, st));
+  }
+  CUDA_TRY(cudaFuncSetAttribute(k_ls_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CS_SMEM)));
+  const uint64_t* in_keys = keys_a.as<uint64_t>();
+  const uint32_t* in_pay = nullptr;
+  for (size_t p = 0; p < passes.size(); ++p) {
+    const bool last = p + 1 == passes.size();
+    LsArgs a{};
+    a.keys = in_keys; a.payload = in_pay; a.n = n; a.nb = nb; a.chunk = chunk;
+    a.cls = passes[p] < 0 ? cls.as<uint8_t>() : nullptr;
+    a.shift = passes[p] < 0 ? 0 : passes[p] * CS_BITS;
+    a.counts = counts.as<uint32_t>();
+    DevBuf& ok = (p % 2 == 0) ? keys_b : keys_a;          // (keys_a holds the input of pass 0)
+    DevBuf& op = (p % 2 == 0) ? pay_a : pay_b;
+    a.out_keys = last ? nullptr : ok.as<uint64_t>();
+    a.out_payload = last ? g->grp_order.as<uint32_t>() : op.as<uint32_t>();
+    a.out_dest = last ? g->grp_dest.as<uint32_t>() : nullptr;
+    k_ls_hist<<<nb, CS_THREADS, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    PA_TRY(scan_u32_on(g, counts.as<uint32_t>(), static_cast<uint64_t>(CS_R) * nb, &tile_sums));
+    k_ls_scatter<<<nb, CS_THREADS, CS_SMEM, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    in_keys = a.out_keys;
+    in_pay = a.out_payload;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));   // the ping-pong buffers are released here
+  return PA_OK;
+}
+extern "C" {
+
+int pa_sort_create(const struct ArrowDeviceArray* values, const struct ArrowSchema* schema, int32_t ascending,
+                   const pa_options* opt, pa_groupby** out) {
+  if (!values || !schema || !out) return set_err(PA_ERR_INVALID, "pa_sort_create: null argument");
+  if (schema->dictionary) return set_err(PA_ERR_NOT_IMPLEMENTED, "sorting dictionary-encoded columns");
+  HandlePtr g(new pa_groupby());
+  PA_TRY(handle_init(g.get(), opt));
+  cudaStream_t st = g->stream;
+  g->keys.resize(1);
+  Column& col = g->keys[0];
+  PA_TRY(load_column(values, schema, st, g->device, &col));
+  if (col.is_str || col.is_bool) return set_err(PA_ERR_NOT_IMPLEMENTED, "sorting '%s' columns (numeric and temporal types only)", schema->format);
+  g->n = col.n;
+  if (g->n >= (1ll << 31)) return set_err(PA_ERR_INVALID, "sort uses 32-bit row numbers: at most 2^31 - 1 rows");
+  CUDA_TRY(cudaEventRecord(g->ev[6], st));
+  int rc;
+  if (col.vc == VC_F) rc = sort_build_t<VC_F>(g.get(), col, !ascending);
+  else if (col.vc == VC_I) rc = sort_build_t<VC_I>(g.get(), col, !ascending);
+  else rc = sort_build_t<VC_U>(g.get(), col, !ascending);
+  PA_TRY(rc);
+  CUDA_TRY(cudaEventRecord(g->ev[7], st));
+  CUDA_TRY(cudaEventRecord(g->ev[8], st));
+  CUDA_TRY(cudaEventRecord(g->ev[9], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  g->sorted_state = true;
+  g->have_groups = true;
+  g->G = 0;
+  g->have_groupings = true;
+  *out = g.release();
+  return PA_OK;
+}
+
+int pa_sort_indices(pa_groupby* g, struct ArrowArray* out, struct ArrowSchema* out_schema) {
+  if (!g || !out || !out_schema) return set_err(PA_ERR_INVALID, "null argument");
+  if (!g->sorted_state) return set_err(PA_ERR_STATE, "not a handle made by pa_sort_create");
+  cudaStream_t st = g->stream;
+  CUDA_TRY(cudaSetDevice(g->device));
+  DevBuf wide;
+  PA_TRY(wide.alloc(static_cast<size_t>(std::max<int64_t>(g->n, 1)) * 8, st));
+  if (g->n > 0) {
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->n + 255) / 256, static_cast<int64_t>(g->num_sms) * 16)));
+    k_ls_widen<<<grid, 256, 0, st>>>(g->grp_order.as<uint32_t>(), wide.as<uint64_t>(), g->n);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return export_host(st, "L", 8, static_cast<uint32_t>(g->n), wide.p, nullptr, out, out_schema);
+}
+
 // ---- multi-GPU partial export / merge ----
 int pa_groupby_partials_count(pa_groupby* g, int32_t n_parts, int64_t* counts_host) {
   if (!g || !counts_host || n_parts < 1 || n_parts > 64) return set_err(PA_ERR_INVALID, "bad argument (1 <= n_parts <= 64)");
@@ -2589,7 +2908,8 @@ int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records
 struct MergeScratch { DevBuf tkeys, idx, m_first, m_slot, s_first, s_slot, cub_tmp; };
 
 static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d_off, int32_t n_sources, uint64_t nrec_max,
-                       uint32_t agg_mask, const char* value_format, const char* key_format, MergeScratch* keep = nullptr) {
+                       uint32_t agg_mask, const char* value_format, const char* key_format, MergeScratch* keep = nullptr,
+                       uint64_t row_bound = 0) {
   cudaStream_t st = g->stream;
   g->merged = true;
   g->keys.resize(1);
@@ -2629,7 +2949,7 @@ static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d
     k_merge_insert<<<static_cast<int>((nrec_max + 255) / 256), 256, 0, st>>>(a);
     CUDA_TRY(cudaGetLastError());
   }
-  k_merge_compact<<<static_cast<int>((nslots + 255) / 256), 256, 0, st>>>(a);
+  k_merge_compact<<<static_cast<int>((nslots + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(g->ev[2], st));
   uint32_t h_status[ST_WORDS];
@@ -2653,9 +2973,12 @@ static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d
     PA_TRY(s_first.alloc(static_cast<size_t>(G) * 8, st));
     PA_TRY(s_slot.alloc(static_cast<size_t>(G) * 4, st));
     size_t tmp_bytes = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, m_first.as<uint64_t>(), s_first.as<uint64_t>(), m_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 64, st));
+    // (global first rows are below row_bound when the caller knows the shards: sort only the bits that can differ)
+    int end_bit = 64;
+    if (row_bound) { end_bit = 1; while (end_bit < 64 && (row_bound >> end_bit)) ++end_bit; }
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, m_first.as<uint64_t>(), s_first.as<uint64_t>(), m_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, end_bit, st));
     PA_TRY(cub_tmp.alloc(tmp_bytes, st));
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, m_first.as<uint64_t>(), s_first.as<uint64_t>(), m_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, 64, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, m_first.as<uint64_t>(), s_first.as<uint64_t>(), m_slot.as<uint32_t>(), s_slot.as<uint32_t>(), static_cast<int>(G), 0, end_bit, st));
     a.order = s_slot.as<uint32_t>();
     a.G = G;
     a.out = g->res;
@@ -2837,6 +3160,7 @@ struct pa_comm {
   MergeScratch merge;
   double phase_ms[5] = {0, 0, 0, 0, 0};   // last step: local pass, count + export, exchange, merge, total
   cudaEvent_t ev[6] = {};
+  uint64_t h_bound = 0;                   // end of this rank's row shard (staging for the async copy)
 };
 
 #define NCCL_TRY(expr)                                                                                          \
@@ -2920,9 +3244,14 @@ int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDe
   PA_TRY(aggregate_entry(g, values, value_schema, agg_mask, false));
   CUDA_TRY(cudaEventRecord(c->ev[1], st));
   // 2. counts per owner, all ranks' counts to everybody
-  PA_TRY(c->d_counts.alloc(sizeof(uint64_t) * W, st));
-  PA_TRY(c->d_all.alloc(sizeof(uint64_t) * W * W, st));
-  CUDA_TRY(cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint64_t) * W, st));
+  // (every rank also tells the others where its row shard ends: the merge orders by GLOBAL first row and only has
+  // to sort the bits below the largest one)
+  const int W1 = W + 1;
+  PA_TRY(c->d_counts.alloc(sizeof(uint64_t) * W1, st));
+  PA_TRY(c->d_all.alloc(sizeof(uint64_t) * W1 * W, st));
+  CUDA_TRY(cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint64_t) * W1, st));
+  c->h_bound = static_cast<uint64_t>(g->opt.row_base) + static_cast<uint64_t>(g->n);
+  CUDA_TRY(cudaMemcpyAsync(c->d_counts.as<uint64_t>() + W, &c->h_bound, sizeof(uint64_t), cudaMemcpyHostToDevice, st));
   {
     PartialsArgs a{};
     a.r = g->res; a.G = g->G; a.nparts = W; a.counts = c->d_counts.as<unsigned long long>();
@@ -2931,17 +3260,18 @@ int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDe
       CUDA_TRY(cudaGetLastError());
     }
   }
-  NCCL_TRY(ncclAllGather(c->d_counts.p, c->d_all.p, W, ncclUint64, c->comm, st));
-  std::vector<uint64_t> all(static_cast<size_t>(W) * W);
-  CUDA_TRY(cudaMemcpyAsync(all.data(), c->d_all.p, sizeof(uint64_t) * W * W, cudaMemcpyDeviceToHost, st));
+  NCCL_TRY(ncclAllGather(c->d_counts.p, c->d_all.p, W1, ncclUint64, c->comm, st));
+  std::vector<uint64_t> all(static_cast<size_t>(W1) * W);
+  CUDA_TRY(cudaMemcpyAsync(all.data(), c->d_all.p, sizeof(uint64_t) * W1 * W, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   std::vector<int64_t> send_cnt(W), recv_cnt(W);
-  uint64_t send_total = 0, recv_total = 0;
+  uint64_t send_total = 0, recv_total = 0, row_bound = 1;
   for (int p = 0; p < W; ++p) {
-    send_cnt[p] = static_cast<int64_t>(all[static_cast<size_t>(c->rank) * W + p]);
-    recv_cnt[p] = static_cast<int64_t>(all[static_cast<size_t>(p) * W + c->rank]);
+    send_cnt[p] = static_cast<int64_t>(all[static_cast<size_t>(c->rank) * W1 + p]);
+    recv_cnt[p] = static_cast<int64_t>(all[static_cast<size_t>(p) * W1 + c->rank]);
     send_total += send_cnt[p];
     recv_total += recv_cnt[p];
+    row_bound = std::max(row_bound, all[static_cast<size_t>(p) * W1 + W]);
   }
   // 3. export the records grouped by owner
   PA_TRY(c->send.alloc(std::max<uint64_t>(send_total, 1) * PA_PARTIAL_WORDS * 8, st));
@@ -2978,7 +3308,7 @@ int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDe
   CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(uint64_t) * (W + 1), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(m->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
   CUDA_TRY(cudaEventRecord(m->ev[0], st));
-  PA_TRY(merge_build(m.get(), c->recv.p, d_off.as<uint64_t>(), W, recv_total, agg_mask, value_schema->format, kfmt.c_str(), &c->merge));
+  PA_TRY(merge_build(m.get(), c->recv.p, d_off.as<uint64_t>(), W, recv_total, agg_mask, value_schema->format, kfmt.c_str(), &c->merge, row_bound));
   CUDA_TRY(cudaEventRecord(c->ev[4], st));
   CUDA_TRY(cudaEventSynchronize(c->ev[4]));
   float t = 0;

@@ -57,6 +57,41 @@ class DeviceColumn:
                             keepalive=(t, valid))
 
 
+class _Ingested:
+    """Owner of the device buffers pa_column_to_device made (released when the last DeviceColumn drops it)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def __del__(self):
+        try:
+            if self.dev.array.release:
+                _RELEASE_ARRAY(self.dev.array.release)(C.byref(self.dev.array))
+        except Exception:
+            pass
+
+
+def to_device(array: pa.Array, device: Optional[int] = None, stream: Optional[int] = None) -> DeviceColumn:
+    """Ingest: copy one host Arrow array (fixed-width numeric / temporal) to the device once (pa_column_to_device:
+    pageable memory goes through the library's pinned staging pipeline) and use it in place from then on."""
+    if isinstance(array, pa.ChunkedArray):
+        array = array.combine_chunks()
+    src = _CArg(array)
+    out = ArrowDeviceArray()
+    opt = _options(0, "auto", device, stream)
+    try:
+        _check(_lib.load().pa_column_to_device(C.byref(src.dev), C.byref(src.schema), C.byref(opt), C.byref(out)))
+        fmt = src.schema.format.decode()
+    finally:
+        src.close()
+    if out.array.n_buffers != 2:
+        _RELEASE_ARRAY(out.array.release)(C.byref(out.array))
+        raise PaError(3, "to_device(): primitive columns only in the Python harness")
+    owner = _Ingested(out)
+    return DeviceColumn(out.array.buffers[1], out.array.length, fmt, out.device_id, valid_ptr=out.array.buffers[0],
+                        null_count=out.array.null_count, offset=out.array.offset, keepalive=owner)
+
+
 class _CArg:
     """ArrowDeviceArray + ArrowSchema pair ready to pass to the library; releases exports on close."""
 
@@ -490,6 +525,58 @@ def downsample(frame, index: Column, rule: str, closed_label_right: bool = True,
     r = Resampler(None, frame, _handle=h)
     r._key_args = [arg]
     return r
+
+
+class Sorted:
+    """Stable argsort of one column on the device (pa_sort_create): what Series::argsort / Series::sort /
+    DataFrame::sort_index get from arrow's array_sort_indices + Take (series.cpp:864-868,978-992,
+    dataframe.cpp:1062-1071).  indices(): the uint64 sort indices; take(column): a column in sorted order."""
+
+    def __init__(self, column: Column, ascending: bool = True, *, device: Optional[int] = None, stream: Optional[int] = None):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        arg = _CArg(column)
+        opt = _options(0, "auto", device, stream)
+        try:
+            _check(self._L.pa_sort_create(C.byref(arg.dev), C.byref(arg.schema), int(bool(ascending)), C.byref(opt), C.byref(self._h)))
+        finally:
+            arg.close()
+
+    def indices(self) -> pa.Array:
+        a, s = ArrowArray(), ArrowSchema()
+        _check(self._L.pa_sort_indices(self._h, C.byref(a), C.byref(s)))
+        return _import(a, s)
+
+    def take(self, column: Column) -> pa.Array:
+        arg = _CArg(column)
+        a, s = ArrowArray(), ArrowSchema()
+        try:
+            _check(self._L.pa_groupby_take_grouped(self._h, C.byref(arg.dev), C.byref(arg.schema), C.byref(a), C.byref(s)))
+        finally:
+            arg.close()
+        return _import(a, s)
+
+    def timing(self) -> dict:
+        b, t = C.c_double(), C.c_double()
+        _check(self._L.pa_groupby_groupings_timing(self._h, C.byref(b), C.byref(t)))
+        return {"sort_ms": b.value, "take_ms": t.value}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.pa_groupby_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class synth:
