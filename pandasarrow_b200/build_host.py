@@ -22,7 +22,7 @@ def _arrow():
     import pyarrow
     inc = pyarrow.get_include()
     libdir = pyarrow.get_library_dirs()[0]
-    libs = sorted(f for f in os.listdir(libdir) if f.startswith(("libarrow.so.", "libarrow_compute.so.")) and f.count(".") == 2)
+    libs = sorted(f for f in os.listdir(libdir) if f.startswith(("libarrow.so.", "libarrow_compute.so.", "libparquet.so.")) and f.count(".") == 2)
     return inc, libdir, [f"-l:{l}" for l in libs]
 
 

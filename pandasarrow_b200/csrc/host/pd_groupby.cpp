@@ -5,11 +5,18 @@
 #include <arrow/c/bridge.h>
 #include <arrow/compute/api.h>
 #include <arrow/compute/row/grouper.h>
+#include <arrow/io/api.h>
+#include <arrow/ipc/api.h>
+#include <arrow/table.h>
+#include <parquet/arrow/reader.h>
 
 #include <algorithm>
 #include <cctype>
 #include <iostream>
 #include <limits>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <stdexcept>
 
 #include "../../../include/pa_b200.h"
@@ -26,11 +33,51 @@ const bool g_compute_initialised = [] { return arrow::compute::Initialize().ok()
 
 arrow::Status pa_status(const char* what) { return arrow::Status::Invalid(what, ": ", pa_last_error()); }
 
-// RAII export of one host Arrow array as ArrowDeviceArray(CPU) + ArrowSchema
+// Device copies made by DataFrame::to_device(), found again by (data buffer address, offset, length) of the host
+// array: a Series or a key column taken from an ingested frame shares its buffers, so every export below sees the copy.
+struct DeviceColumn {
+  ArrowDeviceArray dev{};
+  std::shared_ptr<arrow::ArrayData> host;     // keeps the host buffers (and therefore the key) alive
+  ~DeviceColumn() { if (dev.array.release) dev.array.release(&dev.array); }
+};
+using DeviceKey = std::tuple<const void*, int64_t, int64_t>;
+std::mutex g_device_mutex;
+std::map<DeviceKey, std::weak_ptr<DeviceColumn>> g_device_registry;
+
+DeviceKey device_key(const arrow::ArrayData& d) {
+  const void* p = d.buffers.size() > 1 && d.buffers[1] ? static_cast<const void*>(d.buffers[1]->data()) : nullptr;
+  return {p, d.offset, d.length};
+}
+std::shared_ptr<DeviceColumn> find_device_copy(const arrow::Array& a) {
+  std::lock_guard<std::mutex> lock(g_device_mutex);
+  auto it = g_device_registry.find(device_key(*a.data()));
+  if (it == g_device_registry.end()) return nullptr;
+  auto sp = it->second.lock();
+  if (!sp) g_device_registry.erase(it);
+  return sp;
+}
+struct DeviceColumns {
+  std::vector<std::shared_ptr<DeviceColumn>> cols;
+  ~DeviceColumns() {
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    for (auto& c : cols) g_device_registry.erase(device_key(*c->host));
+  }
+};
+
+// RAII export of one Arrow array as ArrowDeviceArray + ArrowSchema: the device copy when the array was ingested
+// (to_device()), else the host buffers (copied by the library)
 struct Exported {
   ArrowDeviceArray dev{};
   ArrowSchema schema{};
+  std::shared_ptr<DeviceColumn> resident;
   explicit Exported(const arrow::Array& a) {
+    resident = find_device_copy(a);
+    if (resident) {
+      ThrowOnFailure(arrow::ExportType(*a.type(), &schema));
+      dev = resident->dev;
+      dev.array.release = nullptr;              // borrowed: the registry entry owns the device buffers
+      return;
+    }
     ThrowOnFailure(arrow::ExportArray(a, &dev.array, &schema));
     dev.device_id = -1;
     dev.device_type = ARROW_DEVICE_CPU;
@@ -650,6 +697,137 @@ Resampler resample(Series const& s, std::string const& rule, bool closed_right, 
                    time_duration const& offset, std::string const& tz) {
   if (auto d = rule_to_duration(rule)) return resample(s, *d, closed_right, label_right, origin, offset, tz);
   return resample(s, rule_to_offset(rule), closed_right, label_right, origin, offset, tz);
+}
+
+// ------------------------------ sort, ingest ------------------------------
+namespace {
+struct SortHandle {
+  pa_groupby* h = nullptr;
+  SortHandle(const arrow::Array& values, bool ascending) {
+    Exported v(values);
+    pa_options opt;
+    pa_options_init(&opt);
+    if (pa_sort_create(&v.dev, &v.schema, ascending, &opt, &h) != PA_OK) throw_pa("sort");
+  }
+  ~SortHandle() { pa_groupby_destroy(h); }
+  ArrayPtr indices() const {
+    ArrowArray a;
+    ArrowSchema s;
+    if (pa_sort_indices(h, &a, &s) != PA_OK) throw_pa("pa_sort_indices");
+    return ReturnOrThrowOnFailure(import_result(&a, &s));
+  }
+  ArrayPtr take(const ArrayPtr& col, const ArrayPtr& idx) const {
+    if (device_takeable(*col->type())) {
+      Exported v(*col);
+      ArrowArray a;
+      ArrowSchema s;
+      if (pa_groupby_take_grouped(h, &v.dev, &v.schema, &a, &s) != PA_OK) throw_pa("pa_groupby_take_grouped");
+      auto out = ReturnOrThrowOnFailure(import_result(&a, &s));
+      if (!out->type()->Equals(col->type())) out = ReturnOrThrowOnFailure(out->View(col->type()));
+      return out;
+    }
+    return ReturnOrThrowOnFailure(arrow::compute::Take(*col, *idx));   // strings / nested: host take on the device-made order
+  }
+};
+}  // namespace
+
+Series Series::argsort(bool ascending) const {
+  SortHandle sh(*m_array, ascending);
+  return Series(sh.indices(), m_index, m_name);
+}
+
+Series Series::sort(bool ascending) const {
+  if (!m_index) throw std::runtime_error("Cannot sort a Series without an index");   // series.cpp:979-982
+  SortHandle sh(*m_array, ascending);
+  ArrayPtr idx;
+  if (!device_takeable(*m_array->type()) || !device_takeable(*m_index->type())) idx = sh.indices();
+  return Series(sh.take(m_array, idx), sh.take(m_index, idx), m_name);
+}
+
+DataFrame DataFrame::sort_index(bool ascending, bool ignore_index) const {
+  SortHandle sh(*m_index, ascending);
+  ArrayPtr idx;
+  for (auto const& c : m_array->columns()) if (!device_takeable(*c->type())) { idx = sh.indices(); break; }
+  arrow::ArrayVector cols;
+  for (auto const& c : m_array->columns()) cols.push_back(sh.take(c, idx));
+  auto rb = arrow::RecordBatch::Make(m_array->schema(), m_array->num_rows(), cols);
+  return DataFrame(rb, ignore_index ? nullptr : sh.take(m_index, idx));
+}
+
+DataFrame DataFrame::sort_values(std::vector<std::string> const& by, bool ascending) const {
+  auto array = m_array;
+  for (auto const& field : by) {
+    const int i = m_array->schema()->GetFieldIndex(field);
+    if (i < 0) throw std::runtime_error(field + " not in schema");
+    auto col = m_array->column(i);
+    array = ReturnOrThrowOnFailure(array->SetColumn(i, arrow::field(field, col->type()), Series(col, m_index).sort(ascending).array()));
+  }
+  return DataFrame(array);
+}
+
+DataFrame DataFrame::readBinary(std::basic_string_view<uint8_t> const& blob, std::optional<std::string> const& index) {
+  auto buffer = std::make_shared<arrow::Buffer>(blob.data(), static_cast<int64_t>(blob.size()));
+  auto reader = ReturnOrThrowOnFailure(arrow::ipc::RecordBatchStreamReader::Open(std::make_shared<arrow::io::BufferReader>(buffer)));
+  auto batches = ReturnOrThrowOnFailure(reader->ToRecordBatches());
+  if (batches.size() != 1)
+    throw std::invalid_argument("PandasArrow Cannot ReadBinary from a Table or Array of RecordBatches yet. Always Assume Single RecordBatch.");
+  ArrayPtr indexPtr;
+  if (index) {
+    const int pos = batches[0]->schema()->GetFieldIndex(*index);
+    if (pos != -1) {
+      indexPtr = batches[0]->column(pos);
+      if (indexPtr->type_id() == arrow::Type::INT64) indexPtr = ReturnOrThrowOnFailure(indexPtr->View(arrow::timestamp(arrow::TimeUnit::NANO)));
+      batches[0] = ReturnOrThrowOnFailure(batches[0]->RemoveColumn(pos));
+    }
+  }
+  return DataFrame(batches[0], indexPtr);
+}
+
+DataFrame DataFrame::readParquet(std::string const& path) {
+  auto infile = ReturnOrThrowOnFailure(arrow::io::ReadableFile::Open(path));
+  auto reader = ReturnOrThrowOnFailure(parquet::arrow::OpenFile(infile, arrow::default_memory_pool()));
+  std::shared_ptr<arrow::Table> table;
+  ThrowOnFailure(reader->ReadTable(&table));
+  arrow::TableBatchReader tbr(*table);
+  auto rb = ReturnOrThrowOnFailure(tbr.ToRecordBatches());
+  if (rb.empty()) throw std::runtime_error("Cannot Initialize DataFrame with empty parquet table");
+  if (rb.size() != 1)
+    throw std::runtime_error("DataFrame Only supports Parquet Table with single record batch\nFound " + std::to_string(rb.size()) + " record batches\n");
+  return DataFrame(rb[0]);
+}
+
+DataFrame DataFrame::to_device() const {
+  auto set = std::make_shared<DeviceColumns>();
+  auto ingest = [&](const ArrayPtr& a) {
+    if (!a || a->length() == 0) return;
+    const auto id = a->type_id();
+    const bool str = id == arrow::Type::STRING || id == arrow::Type::LARGE_STRING;
+    if (!str && !device_takeable(*a->type())) return;                        // nested / dictionary columns stay on the host
+    if (find_device_copy(*a)) return;
+    ArrowDeviceArray host{};
+    ArrowSchema sc{};
+    ThrowOnFailure(arrow::ExportArray(*a, &host.array, &sc));
+    host.device_id = -1;
+    host.device_type = ARROW_DEVICE_CPU;
+    auto col = std::make_shared<DeviceColumn>();
+    pa_options opt;
+    pa_options_init(&opt);
+    const int rc = pa_column_to_device(&host, &sc, &opt, &col->dev);
+    host.array.release(&host.array);
+    sc.release(&sc);
+    if (rc != PA_OK) throw_pa("to_device");
+    col->host = a->data();
+    {
+      std::lock_guard<std::mutex> lock(g_device_mutex);
+      g_device_registry[device_key(*a->data())] = col;
+    }
+    set->cols.push_back(std::move(col));
+  };
+  ingest(m_index);
+  if (m_array) for (auto const& c : m_array->columns()) ingest(c);
+  DataFrame out(*this);
+  out.m_device = set;
+  return out;
 }
 
 // ------------------------------ helpers ------------------------------

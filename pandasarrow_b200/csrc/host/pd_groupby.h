@@ -28,6 +28,7 @@
 #include <memory>
 #include <optional>
 #include <string>
+#include <string_view>
 #include <utility>
 #include <vector>
 
@@ -117,6 +118,10 @@ class Series {
   std::pair<Scalar, Scalar> min_max(bool skip_null = true) const;
   int64_t count() const;
   Scalar sum_on_device(bool skip_null = true) const;   // (kept for callers of round 1: same as sum())
+  // series.cpp:864-868 / 978-992: arrow's array_sort_indices (+ Take) — a stable device argsort here (sort.cuh);
+  // sort() throws without an index, like the reference
+  Series argsort(bool ascending = true) const;
+  Series sort(bool ascending = true) const;
   // series.cpp:351-359
   Resampler resample(std::string const& rule, bool closed_right = false, bool label_right = false,
                      TimeGrouperOrigin const& origin = {}, time_duration const& offset = time_duration(0),
@@ -161,6 +166,21 @@ class DataFrame {
   DataFrame setIndex(ArrayPtr const& index) const { return DataFrame(m_array, index); }
   Scalar sum() const;   // ndframe.cpp:220 over all columns concatenated (ndframe.h:329-335)
 
+  // dataframe.cpp:1062-1071: rows reordered by the sorted index (device argsort + scatter-shaped take of every column)
+  DataFrame sort_index(bool ascending = true, bool ignore_index = false) const;
+  // dataframe.cpp:1188-1208: every column named in `by` is replaced by its own sorted values (the reference sorts the
+  // listed columns independently and drops the index)
+  DataFrame sort_values(std::vector<std::string> const& by, bool ascending = true) const;
+  // dataframe.cpp:757-791 / 646-683: one record batch out of an Arrow IPC stream / a Parquet file; `index` names the
+  // column that becomes the index (int64 -> timestamp[ns], as the reference casts it)
+  static DataFrame readBinary(std::basic_string_view<uint8_t> const& blob, std::optional<std::string> const& index = std::nullopt);
+  static DataFrame readParquet(std::string const& path);
+  // Ingest: every fixed-width / boolean / utf8 column and the index are copied to the device ONCE
+  // (pa_column_to_device); group_by / resample / sort / the aggregates on the returned frame — and on the Series taken
+  // from it — then use the device copies in place instead of uploading a column per call.
+  DataFrame to_device() const;
+  bool on_device() const { return static_cast<bool>(m_device); }
+
   // dataframe.cpp:1227-1235
   GroupBy group_by(const std::string& key) const;
   GroupBy group_by(const ArrayPtr& keyArray) const;
@@ -174,6 +194,7 @@ class DataFrame {
 
   std::shared_ptr<arrow::RecordBatch> m_array;
   ArrayPtr m_index;
+  std::shared_ptr<void> m_device;   // device copies of the columns (to_device()); shared by copies of the frame
 
  private:
   template <class T>

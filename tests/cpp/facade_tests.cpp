@@ -8,6 +8,10 @@
 #include <string>
 
 #include <arrow/compute/api.h>
+#include <arrow/io/api.h>
+#include <arrow/ipc/api.h>
+#include <arrow/table.h>
+#include <parquet/arrow/writer.h>
 
 #include "../../pandasarrow_b200/csrc/host/pd_groupby.h"
 
@@ -300,6 +304,80 @@ static void test_resample_calendar_rules() {
   REQUIRE_THROWS(pd::resample(series, "bogus", true));
 }
 
+// Series::sort / argsort (series.cpp:864-868,978-992), DataFrame::sort_index / sort_values
+// (dataframe.cpp:1062-1071,1188-1208), readBinary / readParquet (:757-791, :646-683) and device-resident frames.
+// Expected values: arrow's array_sort_indices / Take on the same data (the calls the reference makes).
+static void test_sort_and_ingest() {
+  auto idx = pd::date_range(pd::ns_from_ymd(2021, 3, 1), 8, pd::minutes(1));
+  pd::DataFrame df(idx, std::pair{"k"s, std::vector<int64_t>{5, 3, 5, 1, 3, 9, 1, 5}},
+                   std::pair{"v"s, std::vector<double>{1.5, 2.5, 3.5, 4.5, 5.5, 6.5, 7.5, 8.5}});
+  {
+    auto k = df["k"];
+    auto order = k.argsort();
+    arrow::compute::ArraySortOptions asc{arrow::compute::SortOrder::Ascending}, desc{arrow::compute::SortOrder::Descending};
+    auto want = pd::ReturnOrThrowOnFailure(arrow::compute::CallFunction("array_sort_indices", {k.array()}, &asc)).make_array();
+    REQUIRE(order.array()->Equals(want));                      // stable: 3, 6, 1, 4, 0, 2, 7, 5
+    auto want_d = pd::ReturnOrThrowOnFailure(arrow::compute::CallFunction("array_sort_indices", {k.array()}, &desc)).make_array();
+    REQUIRE(k.argsort(false).array()->Equals(want_d));
+    auto sorted = k.sort();
+    REQUIRE(sorted.array()->Equals(pd::ReturnOrThrowOnFailure(arrow::compute::Take(*k.array(), *want))));
+    REQUIRE(sorted.indexArray()->Equals(pd::ReturnOrThrowOnFailure(arrow::compute::Take(*k.indexArray(), *want))));
+    REQUIRE_THROWS(pd::Series(k.array(), nullptr).sort());     // "Cannot sort a Series without an index"
+  }
+  {
+    // sort_index on a reversed frame restores time order in every column
+    auto rev = pd::ReturnOrThrowOnFailure(arrow::compute::CallFunction("array_sort_indices", {idx},
+                                          std::make_shared<arrow::compute::ArraySortOptions>(arrow::compute::SortOrder::Descending).get())).make_array();
+    auto rb = pd::ReturnOrThrowOnFailure(arrow::compute::Take(arrow::Datum(df.array()), arrow::Datum(rev))).record_batch();
+    pd::DataFrame shuffled(rb, pd::ReturnOrThrowOnFailure(arrow::compute::Take(*idx, *rev)));
+    auto back = shuffled.sort_index();
+    REQUIRE(back.indexArray()->Equals(idx));
+    REQUIRE(back.array()->Equals(*df.array()));
+    auto sv = df.sort_values({"k"});
+    REQUIRE(sv["k"].values<int64_t>() == (std::vector<int64_t>{1, 1, 3, 3, 5, 5, 5, 9}));
+    REQUIRE(sv["v"].values<double>() == df["v"].values<double>());          // other columns untouched (reference semantics)
+    REQUIRE_THROWS(df.sort_values({"nope"}));
+  }
+  {
+    // IPC stream blob -> readBinary(blob, index column)
+    auto with_ts = pd::ReturnOrThrowOnFailure(df.array()->AddColumn(0, "ts", pd::ReturnOrThrowOnFailure(idx->View(arrow::int64()))));
+    auto sink = pd::ReturnOrThrowOnFailure(arrow::io::BufferOutputStream::Create());
+    auto writer = pd::ReturnOrThrowOnFailure(arrow::ipc::MakeStreamWriter(sink, with_ts->schema()));
+    pd::ThrowOnFailure(writer->WriteRecordBatch(*with_ts));
+    pd::ThrowOnFailure(writer->Close());
+    auto buf = pd::ReturnOrThrowOnFailure(sink->Finish());
+    auto read = pd::DataFrame::readBinary(std::basic_string_view<uint8_t>(buf->data(), static_cast<size_t>(buf->size())), "ts");
+    REQUIRE(read.num_columns() == 2);
+    REQUIRE(read.indexArray()->Equals(idx));                   // int64 index column cast to timestamp[ns]
+    auto host_sum = pd::ReturnOrThrowOnFailure(read.group_by("k"s).sum("v"));
+    // the same frame ingested once: group_by / aggregates / resample use the device copies
+    auto dev = read.to_device();
+    REQUIRE(dev.on_device());
+    auto gb = dev.group_by("k"s);
+    auto dev_sum = pd::ReturnOrThrowOnFailure(gb.sum("v"));
+    REQUIRE(dev_sum.array()->Equals(host_sum.array()));
+    REQUIRE(pd::ReturnOrThrowOnFailure(gb.mean("v")).array()->Equals(pd::ReturnOrThrowOnFailure(read.group_by("k"s).mean("v")).array()));
+    auto r_dev = pd::ReturnOrThrowOnFailure(dev.resample("4T").sum());
+    auto r_host = pd::ReturnOrThrowOnFailure(read.resample("4T").sum());
+    REQUIRE(r_dev.array()->Equals(*r_host.array()));
+    REQUIRE(dev["v"].sum().as<double>() == read["v"].sum().as<double>());
+    REQUIRE(dev.sort_index(false).array()->Equals(*read.sort_index(false).array()));
+  }
+  {
+    // Parquet file -> readParquet
+    auto table = pd::ReturnOrThrowOnFailure(arrow::Table::FromRecordBatches({df.array()}));
+    const std::string path = "/tmp/pa_b200_facade_test.parquet";
+    auto out = pd::ReturnOrThrowOnFailure(arrow::io::FileOutputStream::Open(path));
+    pd::ThrowOnFailure(parquet::arrow::WriteTable(*table, arrow::default_memory_pool(), out, 1 << 20));
+    pd::ThrowOnFailure(out->Close());
+    auto pq = pd::DataFrame::readParquet(path);
+    REQUIRE(pq.array()->Equals(*df.array()));
+    auto s = pd::ReturnOrThrowOnFailure(pq.to_device().group_by("k"s).count("v"));
+    REQUIRE(s.values<int64_t>() == (std::vector<int64_t>{3, 2, 2, 1}));
+    REQUIRE_THROWS(pd::DataFrame::readParquet("/tmp/does_not_exist.parquet"));
+  }
+}
+
 static void test_downsample() {
   auto index = pd::date_range(pd::ns_from_ymd(2000, 1, 1), 9);
   pd::DataFrame df(arrow::schema({arrow::field("i", arrow::int64())}), 9, {pd::range(0L, 9L)}, index);
@@ -333,6 +411,7 @@ int main() {
     test_second_stage_aggregates();
     test_resample_series();
     test_resample_calendar_rules();
+    test_sort_and_ingest();
     test_downsample();
   } catch (std::exception const& e) {
     std::printf("EXCEPTION: %s\n", e.what());
