@@ -323,6 +323,15 @@ int pa_groupby_partials_export_padded(pa_groupby* g, int32_t n_parts, void* dev_
 int pa_merge_create_padded(const void* dev_blocks, int32_t n_sources, int64_t block_records, uint32_t agg_mask,
                            const char* value_format, const char* key_format, const pa_options* opt, pa_groupby** out);
 
+/* Host frames larger than free device memory (or than 2^32-2 rows): the columns are aggregated chunk_rows rows at a
+ * time — each chunk copied through the pinned staging pipeline, aggregated with row_base = its first row and exported as
+ * partial records — and the chunks' records are merged like ranks' (sources folded in row order, groups in global
+ * first-appearance order).  Single key column; sum / mean / count / min / max / first / last.  `merged_out` answers
+ * num_groups / unique / fetch like a merged multi-GPU handle.  At most 64 chunks. */
+int pa_groupby_aggregate_chunked(const struct ArrowDeviceArray* keys, const struct ArrowSchema* key_schema,
+                                 const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
+                                 uint32_t agg_mask, int64_t chunk_rows, const pa_options* opt, pa_groupby** merged_out);
+
 /* ---- the same exchange driven from C: communicator handle + one call per step.
  * pa_comm wraps an NCCL communicator over the GPUs of one node (NVLink / NVSwitch).  Rank 0 obtains an id with
  * pa_comm_unique_id (PA_COMM_ID_BYTES bytes), every rank receives it by any out-of-band channel (MPI, a file,

@@ -9,6 +9,6 @@ from . import _lib
 
 _lib.load()
 
-from .groupby import DeviceColumn, GroupBy, MergedGroupBy, PaError, Resampler, Sorted, to_device, downsample, resample, resample_calendar, synth  # noqa: E402
+from .groupby import DeviceColumn, GroupBy, MergedGroupBy, PaError, Resampler, Sorted, aggregate_chunked, to_device, downsample, resample, resample_calendar, synth  # noqa: E402
 
-__all__ = ["DeviceColumn", "GroupBy", "MergedGroupBy", "Resampler", "Sorted", "to_device", "resample", "resample_calendar", "downsample", "PaError", "synth"]
+__all__ = ["DeviceColumn", "GroupBy", "MergedGroupBy", "Resampler", "Sorted", "aggregate_chunked", "to_device", "resample", "resample_calendar", "downsample", "PaError", "synth"]

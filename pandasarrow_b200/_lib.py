@@ -24,7 +24,7 @@ EXPORTS = [
     "pa_groupby_row_ids", "pa_groupby_groupings", "pa_groupby_take_grouped", "pa_groupby_groupings_timing", "pa_groupby_last_timing", "pa_groupby_last_path", "pa_groupby_last_detail",
     "pa_groupby_sync",
     "pa_groupby_destroy", "pa_column_to_device", "pa_sort_create", "pa_sort_indices", "pa_resample_create", "pa_resample_create_calendar", "pa_downsample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
-    "pa_merge_create", "pa_groupby_partials_export_padded", "pa_merge_create_padded", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
+    "pa_merge_create", "pa_groupby_aggregate_chunked", "pa_groupby_partials_export_padded", "pa_merge_create_padded", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
     "pa_synth_validity", "pa_synth_timestamps",
     "pa_comm_unique_id", "pa_comm_create", "pa_comm_adopt", "pa_comm_destroy", "pa_groupby_sharded_aggregate", "pa_comm_last_phases",
 ]
@@ -130,6 +130,8 @@ def load():
     L.pa_groupby_partials_export.argtypes = [P, C.c_int32, P, C.c_int64]
     L.pa_merge_create.argtypes = [P, C.POINTER(C.c_int64), C.c_int32, C.c_uint32, C.c_char_p, C.c_char_p,
                                   C.POINTER(PaOptions), C.POINTER(P)]
+    L.pa_groupby_aggregate_chunked.argtypes = [C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema),
+                                               C.c_uint32, C.c_int64, C.POINTER(PaOptions), C.POINTER(P)]
     L.pa_groupby_partials_export_padded.argtypes = [P, C.c_int32, P, C.c_int64]
     L.pa_merge_create_padded.argtypes = [P, C.c_int32, C.c_int64, C.c_uint32, C.c_char_p, C.c_char_p,
                                          C.POINTER(PaOptions), C.POINTER(P)]

@@ -3152,6 +3152,67 @@ int merge_padded_general(pa_groupby* g, const void* dev_blocks, int32_t n_source
 
 // ---- multi-GPU through the C ABI: communicator + the whole sharded step (SURVEY.md §8b "multi-GPU variants taking a
 // communicator handle", §8e) ----
+// ---- host frames larger than the device (or than 2^32-2 rows): aggregate chunk by chunk, merge the partials ----
+// The row-range shards of the multi-GPU path, executed one after the other on ONE device: every chunk of the host
+// columns is copied (staged, §h2d_copy), aggregated with row_base = its first row, and exported as partial records;
+// the owner-side merge then joins the chunks' records exactly as it joins ranks' — sources folded in chunk (= row)
+// order, groups ordered by global first row.  Device memory in use: one chunk of keys and values + the records.
+int pa_groupby_aggregate_chunked(const struct ArrowDeviceArray* keys, const struct ArrowSchema* key_schema,
+                                 const struct ArrowDeviceArray* values, const struct ArrowSchema* value_schema,
+                                 uint32_t agg_mask, int64_t chunk_rows, const pa_options* opt, pa_groupby** merged_out) {
+  if (!keys || !key_schema || !values || !value_schema || !merged_out) return set_err(PA_ERR_INVALID, "null argument");
+  if (agg_mask == 0 || (agg_mask & ~PA_AGG_ALL)) return set_err(PA_ERR_NOT_IMPLEMENTED, "chunked aggregates: sum / mean / count / min / max / first / last");
+  if (keys->device_type == ARROW_DEVICE_CUDA || values->device_type == ARROW_DEVICE_CUDA)
+    return set_err(PA_ERR_INVALID, "chunked aggregation is for HOST columns (device columns already fit the device)");
+  const int64_t n = keys->array.length;
+  if (values->array.length != n) return set_err(PA_ERR_INVALID, "key and value columns differ in length");
+  if (chunk_rows <= 0) chunk_rows = 1ll << 30;
+  if (chunk_rows >= 0xFFFFFFFEll) return set_err(PA_ERR_INVALID, "chunk_rows must be below 2^32 - 2");
+  const int64_t n_chunks = std::max<int64_t>(1, (n + chunk_rows - 1) / chunk_rows);
+  if (n_chunks > 64) return set_err(PA_ERR_INVALID, "%lld chunks: at most 64 (raise chunk_rows)", (long long)n_chunks);
+  pa_options o;
+  if (opt) o = *opt; else pa_options_init(&o);
+  const int64_t base0 = o.row_base;
+  DevBuf records;                      // all chunks' records, chunk after chunk
+  records.plain = true;
+  std::vector<int64_t> counts(static_cast<size_t>(n_chunks), 0);
+  uint64_t total = 0;
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int64_t lo = c * chunk_rows, len = std::min(chunk_rows, n - lo);
+    ArrowDeviceArray kc = *keys, vc = *values;           // views: same buffers, shifted window
+    kc.array.offset += lo; kc.array.length = len;
+    vc.array.offset += lo; vc.array.length = len;
+    if (kc.array.null_count > 0) kc.array.null_count = -1;
+    if (vc.array.null_count > 0) vc.array.null_count = -1;
+    kc.array.release = nullptr; vc.array.release = nullptr;
+    o.row_base = base0 + lo;
+    pa_groupby* h = nullptr;
+    PA_TRY(pa_groupby_create(&kc, key_schema, 1, &o, &h));
+    HandlePtr guard(h);
+    PA_TRY(pa_groupby_aggregate(h, &vc, value_schema, agg_mask));
+    int64_t cnt = 0;
+    PA_TRY(pa_groupby_partials_count(h, 1, &cnt));
+    counts[static_cast<size_t>(c)] = cnt;
+    // grow the record buffer (plain allocation: it outlives the per-chunk handles and their streams)
+    const size_t need = (total + static_cast<uint64_t>(cnt)) * PA_PARTIAL_WORDS * 8;
+    if (need > records.bytes) {
+      DevBuf bigger;
+      bigger.plain = true;
+      PA_TRY(bigger.alloc(std::max<size_t>(need * 2, 1u << 20), nullptr));
+      if (total) CUDA_TRY(cudaMemcpy(bigger.p, records.p, total * PA_PARTIAL_WORDS * 8, cudaMemcpyDeviceToDevice));
+      records = std::move(bigger);
+    }
+    if (cnt) PA_TRY(pa_groupby_partials_export(h, 1, static_cast<char*>(records.p) + total * PA_PARTIAL_WORDS * 8, cnt));
+    PA_TRY(pa_groupby_sync(h));
+    total += static_cast<uint64_t>(cnt);
+  }
+  o.row_base = base0;
+  const std::string kfmt = key_schema->format;
+  PA_TRY(pa_merge_create(records.p, counts.data(), static_cast<int32_t>(n_chunks), agg_mask, value_schema->format, kfmt.c_str(), &o, merged_out));
+  CUDA_TRY(cudaDeviceSynchronize());   // `records` is released on return
+  return PA_OK;
+}
+
 struct pa_comm {
   ncclComm_t comm = nullptr;
   int world = 1, rank = 0, device = 0;

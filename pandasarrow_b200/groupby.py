@@ -428,6 +428,24 @@ def _merged_from_handle(h) -> "MergedGroupBy":
 MergedGroupBy._from_handle = staticmethod(_merged_from_handle)
 
 
+def aggregate_chunked(keys: pa.Array, values: pa.Array, aggs: Sequence[str], chunk_rows: int, *, device: Optional[int] = None,
+                      row_base: int = 0) -> "MergedGroupBy":
+    """Host columns larger than the device (or than 2^32-2 rows): pa_groupby_aggregate_chunked — the columns are
+    aggregated `chunk_rows` rows at a time and the chunks' partial records merged like ranks'."""
+    mask = 0
+    for a in aggs:
+        mask |= PA_AGG[a]
+    ka, va = _CArg(keys), _CArg(values)
+    h = C.c_void_p()
+    opt = _options(0, "auto", device, None, row_base=row_base)
+    try:
+        _check(_lib.load().pa_groupby_aggregate_chunked(C.byref(ka.dev), C.byref(ka.schema), C.byref(va.dev), C.byref(va.schema),
+                                                        mask, int(chunk_rows), C.byref(opt), C.byref(h)))
+    finally:
+        ka.close(); va.close()
+    return MergedGroupBy._from_handle(h)
+
+
 class Resampler(GroupBy):
     """pd::Resampler (group_by.h:255-299): every aggregate runs over all columns of the frame and
     the result is indexed by the bucket labels (`index()`)."""

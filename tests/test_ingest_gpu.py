@@ -77,3 +77,33 @@ def test_ipc_blob_zero_copy_columns(pab, orc):
         rh = compare_all(h, ora, frame, "px", ALL, "ipc blob", key_cols=[frame["sym"]])
         assert h.unique().equals(d.unique())
         _same(rh, d.aggregate(dv, ALL))
+
+
+@pytest.mark.parametrize("n,chunk,G", [(1_000_003, 100_000, 500), (1_000_003, 333_334, 40_000), (250_000, 1 << 30, 1000), (700_001, 11_000, 3)])
+def test_chunked_aggregate_of_host_columns(pab, orc, n, chunk, G):
+    """pa_groupby_aggregate_chunked (frames larger than the device): chunks aggregated one after the other and merged like
+    the row-range shards of the multi-GPU path — against the ORACLE on the whole columns, group order included."""
+    from util import abs_scale, align_to, assert_exact, assert_fp_close, first_appearance_order, with_abs
+    rng = np.random.default_rng(n + chunk)
+    k = pa.array(rng.integers(-G // 2, G - G // 2, n) * 7919, pa.int64())
+    v = pa.array(rng.standard_normal(n), pa.float64(), mask=rng.random(n) < 0.03)
+    frame = {"k": k, "v": v}
+    ora = orc.OracleGroupBy(with_abs(frame), "k")
+    m = pab.aggregate_chunked(k, v, ALL, chunk)
+    try:
+        ours = [(x,) for x in m.unique().to_pylist()]
+        theirs = [(x,) for x in ora.unique().to_pylist()]
+        assert ours == first_appearance_order([k]), "not in global first-appearance order"
+        perm = pa.array(align_to(ours, theirs))
+        for a in ALL:
+            got = m.fetch(a).take(perm)
+            if a == "mean":
+                want, valid = ora.agg("mean", "v", nthreads=8, with_validity=True)
+                want = pa.array(want.to_numpy(zero_copy_only=False), pa.float64(), mask=~np.asarray(valid.to_numpy(zero_copy_only=False), dtype=bool))
+                assert_fp_close(got, want, "mean", abs_scale(ora, "v", mean=True))
+            elif a == "sum":
+                assert_fp_close(got, ora.agg("sum", "v", nthreads=8), "sum", abs_scale(ora, "v"))
+            else:
+                assert_exact(got, ora.agg(a, "v", nthreads=8), a)
+    finally:
+        m.close()
