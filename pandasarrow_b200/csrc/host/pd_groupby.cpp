@@ -327,6 +327,30 @@ DataFrame GroupBy::MakeSubDataFrame(ScalarPtr const& key, std::shared_ptr<arrow:
   return MakeSubDataFrame(g, schema);
 }
 
+arrow::Result<DataFrame> GroupBy::apply_chunk(std::function<DataFrame(DataFrame const&)> fn) {
+  const std::shared_ptr<arrow::Schema> schema = df.m_array->schema();
+  const int64_t G = static_cast<int64_t>(groupSize());
+  if (G == 0) return arrow::Status::Invalid("no groups");
+  std::vector<DataFrame> parts;
+  parts.reserve(G);
+  for (int64_t g = 0; g < G; ++g) parts.push_back(fn(MakeSubDataFrame(g, schema)));
+  // pd::concat(frames, AxisType::Index) for frames of one schema: column-wise arrow::Concatenate, index included
+  const auto out_schema = parts[0].array()->schema();
+  arrow::ArrayVector index_parts;
+  std::vector<arrow::ArrayVector> col_parts(out_schema->num_fields());
+  int64_t rows = 0;
+  for (auto const& p : parts) {
+    if (!p.array()->schema()->Equals(*out_schema, false)) return arrow::Status::Invalid("apply_chunk: the callback returned frames of different schemas");
+    index_parts.push_back(p.indexArray());
+    for (int c = 0; c < out_schema->num_fields(); ++c) col_parts[c].push_back(p.array()->column(c));
+    rows += p.num_rows();
+  }
+  arrow::ArrayVector cols;
+  for (auto const& cp : col_parts) { ARROW_ASSIGN_OR_RAISE(auto col, arrow::Concatenate(cp)); cols.push_back(col); }
+  ARROW_ASSIGN_OR_RAISE(auto index, arrow::Concatenate(index_parts));
+  return DataFrame(out_schema, rows, cols, index);
+}
+
 static arrow::Result<ArrayPtr> build_array(arrow::ScalarVector const& scalars) {   // group_by.h:191-217
   if (scalars.empty()) return arrow::Status::Invalid("no groups");
   ARROW_ASSIGN_OR_RAISE(auto builder, arrow::MakeBuilder(scalars.back()->type));

@@ -263,6 +263,9 @@ class GroupBy {
   arrow::Result<Series> apply(std::function<ScalarPtr(DataFrame const&)> fn);
   arrow::Result<Series> apply(std::function<ArrayPtr(DataFrame const&)> fn);
   arrow::Result<DataFrame> apply(std::function<ScalarPtr(Series const&)> fn);
+  // group_by.h:77, dataframe.cpp:1411-1428: fn on every group's sub-frame, results concatenated row-wise (pd::concat along
+  // the index; the results must share one schema)
+  arrow::Result<DataFrame> apply_chunk(std::function<DataFrame(DataFrame const&)> fn);
   arrow::Result<Series> apply_async(std::function<ScalarPtr(DataFrame const&)> fn) { return apply(std::move(fn)); }
   arrow::Result<DataFrame> apply_async(std::function<ScalarPtr(Series const&)> fn) { return apply(std::move(fn)); }
   template <class IndexType>

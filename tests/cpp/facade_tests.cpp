@@ -151,6 +151,21 @@ static void test_apply_callbacks_and_groups() {
   auto df = pd::DataFrame(std::map<std::string, std::vector<int32_t>>{{"a", {1, 1, 3, 1, 1, 1, 3, 8, 2, 2}}, {"b", {10, 9, 8, 7, 6, 5, 4, 3, 2, 1}}});
   auto groupby = df.group_by("a"s);
   REQUIRE(groupby.groupSize() == 4);
+  {
+    // apply_chunk (dataframe.cpp:1411-1428): the callback's per-group frames concatenated in group order.  Here: every
+    // group reduced to its first row -> one row per group, in first-appearance order of the keys 1, 3, 8, 2
+    auto first_rows = pd::ReturnOrThrowOnFailure(groupby.apply_chunk([](pd::DataFrame const& g) {
+      return pd::DataFrame(g.array()->Slice(0, 1), g.indexArray()->Slice(0, 1));
+    }));
+    REQUIRE(first_rows.num_rows() == 4);
+    REQUIRE(first_rows["a"].values<int32_t>() == (std::vector<int32_t>{1, 3, 8, 2}));
+    REQUIRE(first_rows["b"].values<int32_t>() == (std::vector<int32_t>{10, 8, 3, 2}));
+    // identity callback: all rows back, grouped
+    auto all = pd::ReturnOrThrowOnFailure(groupby.apply_chunk([](pd::DataFrame const& g) { return g; }));
+    REQUIRE(all.num_rows() == 10);
+    REQUIRE(all["a"].values<int32_t>() == (std::vector<int32_t>{1, 1, 1, 1, 1, 3, 3, 8, 2, 2}));
+    REQUIRE(all["b"].values<int32_t>() == (std::vector<int32_t>{10, 9, 7, 6, 5, 8, 4, 3, 2, 1}));
+  }
   auto col_sum = [](pd::Series const& s) -> std::shared_ptr<arrow::Scalar> { return s.sum().scalar; };
   auto result = pd::ReturnOrThrowOnFailure(groupby.apply(col_sum));
   REQUIRE(result.num_rows() == 4);
