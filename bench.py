@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--config5-groups", type=int, default=100_000_000, help="N>1: groups of the config-5 extra (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sm-reserve", type=int, default=-1, help="SMs the scan leaves free (pa_options.sm_reserve; default 0: measured slower at N=2 — 3.57 / 3.59 / 3.61 / 3.65 ms per step with 0 / 1 / 2 / 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=100_000_000, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--extras", action="store_true", help="(default at N=1) config 3 (multi-key, nullable), config 4 (resample OHLC), scattered keys, ...")
@@ -231,7 +232,8 @@ def main():
     # N = 1: one fused pass (stages 1-3 + merge + emit).  N > 1: the same on this rank's row shard, then
     # partial records -> NCCL all-to-all -> owner-side merge (pandasarrow_b200/distributed.py).
     from pandasarrow_b200 import distributed as D
-    gb = pab.GroupBy("k", {"k": dk, "v": dv}, stream=stream.cuda_stream, device=local, row_base=first_row)
+    sm_reserve = max(args.sm_reserve, 0)
+    gb = pab.GroupBy("k", {"k": dk, "v": dv}, stream=stream.cuda_stream, device=local, row_base=first_row, sm_reserve=sm_reserve)
     scan_ms, launches, merged_groups = [], 0, 0
 
     # N > 1: the serial tail of a step (all-to-all of ~1000 partial records -> single-CTA merge: ~0.15 ms of launch and

@@ -129,7 +129,9 @@ typedef struct pa_options {
   int64_t lowcard_no_dense;  /* 1 = the shared-memory path never uses dense (key - base) addressing, always hashes */
   int64_t no_partition;      /* 1 = never radix-partition the rows (bucketed path / table regions): plain global-table scan */
   int64_t bucket_bits;       /* tuning / tests: 0 = automatic; else level-1 bits | level-2 bits << 8 of the bucketed path */
-  int64_t reserved[1];
+  int64_t sm_reserve;        /* SMs the persistent shared-memory scan leaves free (0 = none): room for a concurrent NCCL
+                                kernel / the merge of the previous multi-GPU step, whose CTAs cannot co-reside with a
+                                scan CTA that owns ~200 KB of the SM's shared memory */
 } pa_options;
 
 typedef struct pa_groupby pa_groupby;      /* opaque: key columns + device group table */

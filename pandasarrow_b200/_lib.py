@@ -58,7 +58,7 @@ class ArrowDeviceArray(C.Structure):
 class PaOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("path", C.c_int32), ("expected_groups", C.c_int64),
                 ("cuda_stream", C.c_void_p), ("row_base", C.c_int64), ("lowcard_no_dense", C.c_int64),
-                ("no_partition", C.c_int64), ("bucket_bits", C.c_int64), ("reserved", C.c_int64 * 1)]
+                ("no_partition", C.c_int64), ("bucket_bits", C.c_int64), ("sm_reserve", C.c_int64)]
 
 
 _lib = None

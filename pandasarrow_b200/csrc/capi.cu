@@ -558,7 +558,7 @@ int launch_lowcard_t(pa_groupby* g, const LcArgs& a, const LmArgs& m, int grid, 
 int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool force_hash, LcOutcome* outcome,
                 bool deferred = false) {
   cudaStream_t st = g->stream;
-  const int grid = g->num_sms;
+  const int grid = std::max<int>(1, g->num_sms - static_cast<int>(std::max<int64_t>(0, std::min<int64_t>(g->opt.sm_reserve, g->num_sms - 1))));
   const int vc = val ? val->vc : VC_I;
   const bool kwide = lc_is_wide(mask, vc);
   const bool dsum = kwide && vc != VC_F;

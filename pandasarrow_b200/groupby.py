@@ -145,7 +145,7 @@ def _import(out_a, out_s) -> pa.Array:
 
 
 def _options(expected_groups=0, path="auto", device=None, stream=None, row_base=0, no_dense=False,
-             no_partition=False, bucket_bits=0) -> PaOptions:
+             no_partition=False, bucket_bits=0, sm_reserve=0) -> PaOptions:
     o = PaOptions()
     _lib.load().pa_options_init(C.byref(o))
     o.expected_groups = int(expected_groups)
@@ -154,6 +154,7 @@ def _options(expected_groups=0, path="auto", device=None, stream=None, row_base=
     o.lowcard_no_dense = 1 if no_dense else 0
     o.no_partition = 1 if no_partition else 0
     o.bucket_bits = int(bucket_bits)
+    o.sm_reserve = int(sm_reserve)
     if device is not None:
         o.device = int(device)
     if stream is not None:
@@ -173,7 +174,7 @@ class GroupBy:
 
     def __init__(self, key, frame=None, *, key_arrays: Optional[Sequence[Column]] = None, expected_groups: int = 0,
                  path: str = "auto", device: Optional[int] = None, stream: Optional[int] = None, row_base: int = 0,
-                 no_dense: bool = False, no_partition: bool = False, bucket_bits: int = 0, _handle=None):
+                 no_dense: bool = False, no_partition: bool = False, bucket_bits: int = 0, sm_reserve: int = 0, _handle=None):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self._frame = self._as_dict(frame)
@@ -192,7 +193,7 @@ class GroupBy:
         key_arrays = [self._normalise_key(k) for k in key_arrays]
         args, devs, schemas = _pack_args(key_arrays)
         self._key_args = args          # keys are borrowed until destroy
-        opt = _options(expected_groups, path, device, stream, row_base, no_dense, no_partition, bucket_bits)
+        opt = _options(expected_groups, path, device, stream, row_base, no_dense, no_partition, bucket_bits, sm_reserve)
         try:
             _check(self._L.pa_groupby_create(devs, schemas, len(args), C.byref(opt), C.byref(self._h)))
         except Exception:
