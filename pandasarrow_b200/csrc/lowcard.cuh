@@ -14,17 +14,17 @@
 //      dense : all sampled keys lie in a window of <= GMAX values -> id = key - base, no table at all.
 //              Keys not dense (declined before the first row) or a key outside the window met later
 //              (ST_DENSE_MISS): the host launches the hash-mode kernel.
-//      hash  : CTA-shared open-addressing table in shared memory, 4096 PACKED 8-byte entries
-//              {52 key bits | 2-bit displacement | 10-bit id}: the key is first mixed by a BIJECTION of
-//              64 bits whose top 12 bits are the home slot, so home slot + displacement + the other 52
-//              bits identify the key exactly and ONE LDS.64 per probe answers "which id" (round 1: LDS.128
-//              of a two-key bucket + LDS.U16 of the id = 14 wavefronts per 32 rows against 6 now; the
-//              shared-memory pipe is what bounds this kernel).  Read-only in steady state; 12 % of the
-//              keys sit one slot past home (second probe, those lanes only), keys displaced by more than
-//              three slots (~2 in 1000) live in a 16-entry overflow list.  New keys take an out-of-line
-//              slow path (ATOMS.CAS.64) that also obtains a GLOBAL id for the key from a small directory
-//              in global memory, so that ids mean the same group in every CTA and the merge needs no
-//              join.  Null keys and the key equal to the directory sentinel have dedicated ids.
+//      hash  : CTA-shared open-addressing table in shared memory: 2048 buckets of two PACKED 8-byte entries
+//              {53 key bits | 1-bit bucket displacement | 10-bit id}: the key is first mixed by a BIJECTION of 64 bits
+//              whose top 11 bits are the home bucket, so home + displacement + the other 53 bits identify the key
+//              exactly and ONE LDS.128 per probe answers "which id" for both entries of a bucket (round 1: LDS.128 of
+//              a two-key bucket + LDS.U16 of the id; round 2's first table: single entries, LDS.64, three predicated
+//              rounds for the 12 % of displaced keys — the kernel is bound by instruction issue, 133 warp instructions
+//              per 32 rows, so the rounds were what had to go).  Read-only in steady state; 3 % of a 1000-key set sit in
+//              the next bucket (second probe, those lanes only), ~0.2 % in a 16-entry overflow list.  New keys take an
+//              out-of-line slow path (ATOMS.CAS.64) that also obtains a GLOBAL id for the key from a small directory
+//              in global memory, so that ids mean the same group in every CTA and the merge needs no join.  Null keys
+//              and the key equal to the directory sentinel have dedicated ids.
 //  * Stage 3: accumulators are WARP-PRIVATE arrays in shared memory (sum 8 B + count word 4 B per
 //    id; the wide variant adds last row, {min, max} and a double sum), updated with plain loads and
 //    stores — no atomics (sm_100a has no native 64-bit shared-memory atomics: f64/u64 adds compile
@@ -48,9 +48,10 @@
 
 namespace pa {
 
-constexpr int LC_HT_LOG2 = 12;
-constexpr int LC_HT = 1 << LC_HT_LOG2;       // packed entries of the hash-mode table
-constexpr int LC_HT_MAXD = 3;                // largest displacement an entry can record (2 bits)
+constexpr int LC_HB_LOG2 = 11;
+constexpr int LC_HB = 1 << LC_HB_LOG2;       // buckets of the hash-mode table: two packed 8-byte entries each (one LDS.128)
+constexpr int LC_HT = 2 * LC_HB;             // packed entries
+constexpr int LC_HT_MAXD = 1;                // largest bucket displacement an entry can record (1 bit)
 constexpr int LC_OVF = 16;                   // overflow list: keys displaced further than that
 constexpr uint64_t LC_HE_EMPTY = ~0ull;      // (id field 0x3FF is never assigned)
 constexpr uint32_t LC_HE_PENDING = 0x3FEu;   // id field while the inserting lane fetches the global id
@@ -208,16 +209,20 @@ struct LcCtx {
   uint32_t window, rlog, rmask;       // dense mode: accumulator replication (slot = id << rlog | lane & rmask)
 };
 
-// Hash mode: bijective mix of the key; the top LC_HT_LOG2 bits are the home slot, the rest is what an entry stores.
+// Hash mode: bijective mix of the key; the top LC_HB_LOG2 bits are the home bucket, the rest is what an entry stores.
 __device__ __forceinline__ uint64_t lc_mix(uint64_t key) { return (key ^ (key >> 32)) * 0x9E3779B97F4A7C15ull; }
 
-// One probe of the packed table at displacement `d`: LDS.64.  Returns the id, or a value >= LC_HE_OVF when this
-// slot does not hold the key (or its id is not published yet).
+// One probe of the packed table at bucket displacement `d`: ONE LDS.128 fetches both entries of the bucket.  Returns the
+// id, or a value >= LC_HE_OVF when neither entry holds the key (or its id is not published yet).
 __device__ __forceinline__ uint32_t lc_probe(uint64_t m, uint32_t d, uint32_t tab) {
-  const uint32_t slot = (static_cast<uint32_t>(m >> (64 - LC_HT_LOG2)) + d) & (LC_HT - 1);
-  const uint64_t en = lds64(tab + slot * 8u);
-  const uint64_t want = (m << LC_HT_LOG2) | (static_cast<uint64_t>(d) << 10);
-  return ((en ^ want) >> 10) == 0 ? (static_cast<uint32_t>(en) & 0x3FFu) : static_cast<uint32_t>(LC_ID_UNSET);
+  const uint32_t b = (static_cast<uint32_t>(m >> (64 - LC_HB_LOG2)) + d) & (LC_HB - 1);
+  const uint4 e = lds128(tab + b * 16u);
+  const uint64_t want = (m << LC_HB_LOG2) | (static_cast<uint64_t>(d) << 10);
+  const uint32_t wl = static_cast<uint32_t>(want), wh = static_cast<uint32_t>(want >> 32);
+  const bool hit0 = (((e.x ^ wl) & ~0x3FFu) | (e.y ^ wh)) == 0u;
+  const bool hit1 = (((e.z ^ wl) & ~0x3FFu) | (e.w ^ wh)) == 0u;
+  const uint32_t id = (hit0 ? e.x : e.z) & 0x3FFu;
+  return (hit0 || hit1) ? id : static_cast<uint32_t>(LC_ID_UNSET);
 }
 
 // Global id of a key that this CTA sees for the first time.  LC_NOID when more than gmax keys exist.
@@ -261,10 +266,11 @@ __device__ __forceinline__ void lc_give_up(uint32_t* misc, uint32_t* status) {
 __device__ __noinline__ uint32_t lc_miss_resolve(uint64_t key, const LcCtx& c, LcDir dir, uint32_t gmax, uint32_t* status) {
   if (*reinterpret_cast<volatile uint32_t*>(c.misc + 1)) return LC_NOID;   // this CTA already gave up
   const uint64_t m = lc_mix(key);
-  const uint32_t home = static_cast<uint32_t>(m >> (64 - LC_HT_LOG2));
-  for (uint32_t d = 0; d <= LC_HT_MAXD; ++d) {
-    volatile unsigned long long* slot = c.tab_p + ((home + d) & (LC_HT - 1));
-    const uint64_t mine = (m << LC_HT_LOG2) | (static_cast<uint64_t>(d) << 10);
+  const uint32_t home = static_cast<uint32_t>(m >> (64 - LC_HB_LOG2));
+  for (uint32_t q = 0; q < 2u * (LC_HT_MAXD + 1); ++q) {      // home bucket entry 0, 1, next bucket entry 0, 1
+    const uint32_t d = q >> 1;
+    volatile unsigned long long* slot = c.tab_p + (((home + d) & (LC_HB - 1)) * 2u + (q & 1u));
+    const uint64_t mine = (m << LC_HB_LOG2) | (static_cast<uint64_t>(d) << 10);
     uint64_t en = *slot;
     if (en == LC_HE_EMPTY) {
       en = atomicCAS(const_cast<unsigned long long*>(slot), static_cast<unsigned long long>(LC_HE_EMPTY),
@@ -596,8 +602,8 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
       return false;
     }
   } else {
-    // probe 0 of every batch (8 independent LDS.64 in flight), then — lanes that missed only — the displaced keys:
-    // of a 1000-key set 9.4 % sit one slot past home, 2.0 % two, 0.5 % three, 0.2 % in the overflow list.  All four
+    // probe 0 of every batch (8 independent LDS.128 in flight), then — lanes that missed only — the displaced keys:
+    // of a 1000-key set 3 % sit in the next bucket, 0.2 % in the overflow list.  Both
     // rounds are straight-line predicated code (nearly every 256-row group has a lane in every round; a loop with
     // votes per batch measured 8.8 ms per 1 B rows against 6.4 ms for round 1's bucket table); only keys that
     // are not in the table yet leave it for the out-of-line insert.
@@ -607,12 +613,12 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
     for (int e = 0; e < LC_NB; ++e) {
       const bool act = CLEAN ? true : ((b.act >> e) & 1u) != 0;
       const bool kvalid = CLEAN ? true : ((b.kv >> e) & 1u) != 0;
-      const bool special = !kvalid || b.key[e] == kEmptyKey;
+      // (the sentinel key value is never inserted, so it misses every probe and is given its id with the rare cases below)
       mix[e] = lc_mix(b.key[e]);
       id[e] = lc_probe(mix[e], 0u, c.tab);
-      if (special) id[e] = kvalid ? Cfg::GMAX_H + 1 : Cfg::GMAX_H;
+      if (!kvalid) id[e] = Cfg::GMAX_H;
       if (!act) id[e] = LC_NOID;
-      if (act && !special && id[e] >= LC_HE_OVF) missmask |= 1u << e;
+      if (act && kvalid && id[e] >= LC_HE_OVF) missmask |= 1u << e;
     }
 #pragma unroll
     for (uint32_t d = 1; d <= LC_HT_MAXD; ++d) {
@@ -625,11 +631,12 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
       }
     }
     if (__any_sync(FULL, missmask != 0)) {
-      // overflow list (published entries), then the insert path
+      // the sentinel key value, the overflow list (published entries), then the insert path
       const uint32_t novf = *reinterpret_cast<volatile uint32_t*>(c.misc + 2);
 #pragma unroll
       for (int e = 0; e < LC_NB; ++e) {
         if ((missmask >> e) & 1u) {
+          if (b.key[e] == kEmptyKey) { id[e] = Cfg::GMAX_H + 1; missmask &= ~(1u << e); continue; }
           for (uint32_t i = 0; i < novf; ++i) {
             if (lds64(smem_u32(c.ovf_keys + i)) == b.key[e]) {
               const uint32_t oid = *reinterpret_cast<volatile uint32_t*>(c.ovf_ids + i);
@@ -645,6 +652,12 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
           if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c, a.dir, Cfg::GMAX_H, a.status);
         }
         __syncwarp();
+        // a key that got no id (more than GMAX keys, overflow list full): the pass is abandoned before anything of this
+        // row group is accumulated — lc_miss_resolve has raised the abort flags, the host reruns on the global path
+        bool lost = false;
+#pragma unroll
+        for (int e = 0; e < LC_NB; ++e) lost |= id[e] == LC_NOID && (CLEAN || ((b.act >> e) & 1u) != 0);
+        if (__any_sync(FULL, lost)) return false;
       }
     }
   }
@@ -657,7 +670,7 @@ __device__ __forceinline__ void lc_accumulate_group(const LcBuf& b, const uint32
 #pragma unroll
   for (int e = 0; e < LC_NB; ++e) {
     const uint32_t row = static_cast<uint32_t>(g0) + e * 32 + lane;
-    constexpr bool ACLEAN = CLEAN && DENSE;   // (hash mode may leave LC_NOID in a lane after an overflow)
+    constexpr bool ACLEAN = CLEAN;            // (hash mode: a row group with an unresolved key never gets here)
     const bool vvalid = CLEAN ? true : ((b.vv >> e) & 1u) != 0;
     lc_accumulate<VC, WIDE, ACLEAN, DENSE>(id[e], b.val[e], vvalid && (ACLEAN || id[e] != LC_NOID), row, a.agg_mask, c);
   }
