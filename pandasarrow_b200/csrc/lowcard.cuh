@@ -607,15 +607,13 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
     // rounds are straight-line predicated code (nearly every 256-row group has a lane in every round; a loop with
     // votes per batch measured 8.8 ms per 1 B rows against 6.4 ms for round 1's bucket table); only keys that
     // are not in the table yet leave it for the out-of-line insert.
-    uint64_t mix[LC_NB];
     uint32_t missmask = 0;
 #pragma unroll
     for (int e = 0; e < LC_NB; ++e) {
       const bool act = CLEAN ? true : ((b.act >> e) & 1u) != 0;
       const bool kvalid = CLEAN ? true : ((b.kv >> e) & 1u) != 0;
       // (the sentinel key value is never inserted, so it misses every probe and is given its id with the rare cases below)
-      mix[e] = lc_mix(b.key[e]);
-      id[e] = lc_probe(mix[e], 0u, c.tab);
+      id[e] = lc_probe(lc_mix(b.key[e]), 0u, c.tab);
       if (!kvalid) id[e] = Cfg::GMAX_H;
       if (!act) id[e] = LC_NOID;
       if (act && kvalid && id[e] >= LC_HE_OVF) missmask |= 1u << e;
@@ -625,7 +623,7 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
 #pragma unroll
       for (int e = 0; e < LC_NB; ++e) {
         if ((missmask >> e) & 1u) {
-          const uint32_t id2 = lc_probe(mix[e], d, c.tab);
+          const uint32_t id2 = lc_probe(lc_mix(b.key[e]), d, c.tab);   // (recomputed: eight live 64-bit mixes cost 16 registers)
           if (id2 < LC_HE_OVF) { id[e] = id2; missmask &= ~(1u << e); }
         }
       }
