@@ -595,6 +595,14 @@ int run_lowcard(pa_groupby* g, const Column* val, uint32_t mask, bool wide, bool
   a.vw = val ? val->width : 8;
   a.n = g->n;
   a.force_hash = force_hash ? 1 : 0;
+  a.hash_rlog = 0;
+  if (force_hash) {
+    // replicas per id for few scattered keys, from a group count this handle already knows (its keys never change) or
+    // the caller's hint; a count that turns out too small overflows to the global path like any other overflow
+    const uint64_t known = g->have_groups ? g->G : static_cast<uint64_t>(std::max<int64_t>(g->opt.expected_groups, 0));
+    const uint64_t cap = static_cast<uint64_t>(lc_gmax_hash(vc, kwide));
+    if (known > 0) while (a.hash_rlog < 5 && ((known + 1) << (a.hash_rlog + 1)) <= cap) ++a.hash_rlog;
+  }
   a.agg_mask = mask;
   char* d = dir.as<char>();
   a.dir.prep = reinterpret_cast<LcPrep*>(d);

@@ -145,6 +145,7 @@ struct LcArgs {
   int64_t n;
   int kw, vw;              // element widths in bytes (generic loader)
   int force_hash;
+  int hash_rlog;           // hash-mode kernel: log2 of the accumulator replicas per id (host: from the known group count)
   uint32_t agg_mask;
   LcDir dir;
   // per-CTA partial tables, [grid][GP]
@@ -439,7 +440,7 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
   const uint32_t ida = live ? id : 0u;
   const uint32_t cw_addr = c.cw + ida * 4u, sum_addr = c.sum + ida * 8u;
   const bool vv = CLEAN ? true : vvalid;
-  const uint32_t gid = (DENSE && ida < static_cast<uint32_t>(Cfg::GMAX)) ? (ida >> c.rlog) : ida;
+  const uint32_t gid = ida < static_cast<uint32_t>(DENSE ? Cfg::GMAX : Cfg::GMAX_H) ? (ida >> c.rlog) : ida;
   LcContrib<Cfg::DSUM> k;
   k.sum = vv ? vbits : 0ull;
   k.cnt = vv ? 1u : 0u;
@@ -647,7 +648,7 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
       if (__any_sync(FULL, missmask != 0)) {
 #pragma unroll
         for (int e = 0; e < LC_NB; ++e) {
-          if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c, a.dir, Cfg::GMAX_H, a.status);
+          if ((missmask >> e) & 1u) id[e] = lc_miss_resolve(b.key[e], c, a.dir, c.window, a.status);
         }
         __syncwarp();
         // a key that got no id (more than GMAX keys, overflow list full): the pass is abandoned before anything of this
@@ -656,6 +657,12 @@ __device__ __forceinline__ bool lc_resolve_group(const LcBuf& b, uint32_t (&id)[
 #pragma unroll
         for (int e = 0; e < LC_NB; ++e) lost |= id[e] == LC_NOID && (CLEAN || ((b.act >> e) & 1u) != 0);
         if (__any_sync(FULL, lost)) return false;
+      }
+    }
+    if (c.rlog) {   // group id -> this lane's replica of the group's slot (the two special ids have no replicas)
+#pragma unroll
+      for (int e = 0; e < LC_NB; ++e) {
+        if (id[e] < static_cast<uint32_t>(Cfg::GMAX_H)) id[e] = (id[e] << c.rlog) | (lane & c.rmask);
       }
     }
   }
@@ -762,6 +769,14 @@ __global__ void __launch_bounds__(LcSmem<VC, WIDE, !DENSEK>::WARPS * 32, 1) k_lo
   if (DENSEK && !dense) {   // not a dense key set: hand over to the hash-mode kernel
     if (threadIdx.x == 0) { atomicExch(a.status + ST_DENSE_MISS, 2u); atomicExch(a.status + ST_ABORT, 1u); }
     return;
+  }
+  if constexpr (!DENSEK) {
+    // Few SCATTERED keys (hashed utf8 keys with a handful of values): without replicas most lanes of a batch hit the
+    // same slot and every batch takes the out-of-line ordered fold (2 keys: 21 ms per 1 B rows).  When the host knows
+    // the group count it asks for 2^rlog replicas per id, exactly like the dense kernel's small windows; ids beyond
+    // GMAX >> rlog overflow to the global path.
+    c.rlog = static_cast<uint32_t>(a.hash_rlog);
+    c.window = static_cast<uint32_t>(GMAXK) >> c.rlog;
   }
   // lane-private replicas (32 per id) of the narrow layout are conflict free and 12 warps already saturate HBM
   // (2.99 against 3.05 ms at 16 groups); everything else wants all 16 warps (wide set: 3.6 against 4.2 ms at 16

@@ -306,8 +306,9 @@ def _keys_with_home(home, count, seed):
 
 @pytest.mark.parametrize("clash,path", [(4, "lowcard"), (14, "lowcard"), (40, "global")])
 def test_lowcard_hash_mode_displaced_keys_and_overflow_list(pab, orc, clash, path):
-    # `clash` keys share one home slot of the packed table: 4 fill the probe window (displacements 0..3), the next
-    # 16 go to the overflow list, more than that and the kernel gives up in favour of the global-table path
+    # `clash` keys share one home bucket of the packed table (they agree in the top 12 bits of lc_mix(key), the bucket is
+    # the top 11): 4 fill the home bucket and the next one (two entries each), the next 16 go to the overflow list, more
+    # than that and the kernel gives up in favour of the global-table path
     rng = np.random.default_rng(clash)
     n = 300_000
     pool = np.concatenate([_keys_with_home(1234, clash, clash), rng.integers(-2**62, 2**62, 300, dtype=np.int64)])
@@ -317,6 +318,32 @@ def test_lowcard_hash_mode_displaced_keys_and_overflow_list(pab, orc, clash, pat
     assert gb.timing()["path"] == path
     _cmp(gb, ora, rb, "v", ALL, f"clash={clash} all")
     assert gb.timing()["path"] == path
+
+
+@pytest.mark.parametrize("G,nulls", [(2, False), (3, True), (17, False), (60, True), (130, False), (400, False)])
+def test_lowcard_hash_mode_few_scattered_keys_replicated(pab, orc, G, nulls):
+    # few SCATTERED keys (what hashed utf8 keys with a handful of values look like): the first pass on a handle runs
+    # without accumulator replicas, every later one with 2^r replicas per id chosen from the now known group count
+    # (lowcard.cuh, hash_rlog) — both against the oracle, both bit-identical to each other in everything but fp sums,
+    # and each run-to-run deterministic
+    rng = np.random.default_rng(G)
+    n = 400_003
+    pool = rng.integers(-2**62, 2**62, G, dtype=np.int64)
+    k = pa.array(pool[rng.integers(0, G, n)], pa.int64(), mask=(rng.random(n) < 0.01) if nulls else None)
+    frame = {"k": k, "v": _rand_vals(rng, n), "i": pa.array(rng.integers(-1000, 1000, n), pa.int64(), mask=rng.random(n) < 0.05)}
+    gb, ora, rb = _both(pab, orc, frame, "k")
+    _cmp(gb, ora, rb, "v", ALL, f"G={G} first pass")
+    t1 = gb.timing()
+    assert t1["path"] == "lowcard" and t1["mode"] == "hash" and t1["replication"] == 1
+    r2 = _cmp(gb, ora, rb, "v", ALL, f"G={G} replicated pass")
+    t2 = gb.timing()
+    groups = G + (1 if nulls else 0)
+    assert t2["path"] == "lowcard" and t2["mode"] == "hash" and t2["replication"] == (1 << min(5, int(np.log2(1000 // (groups + 1))))), t2
+    _cmp(gb, ora, rb, "i", ALL, f"G={G} replicated pass, integers (double sum)")
+    from util import assert_exact
+    r3 = gb.aggregate(rb.column("v"), ALL)
+    for a in ALL:
+        assert_exact(r3[a], r2[a], f"run-to-run {a}")           # the replicated pass is deterministic too
 
 
 def test_lowcard_dense_miss_reruns_in_hash_mode(pab, orc):
