@@ -2881,7 +2881,8 @@ int pa_groupby_partials_count(pa_groupby* g, int32_t n_parts, int64_t* counts_ho
   return PA_OK;
 }
 
-int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records, int64_t capacity_records) {
+// `compact`: REC_WORDS_COMPACT-word records (merge.cuh) — the sharded step's own format for narrow aggregate sets
+static int partials_export(pa_groupby* g, int32_t n_parts, void* dev_records, int64_t capacity_records, bool compact) {
   if (!g || !dev_records) return set_err(PA_ERR_INVALID, "null argument");
   if (g->parts_n != n_parts) return set_err(PA_ERR_STATE, "call pa_groupby_partials_count(n_parts=%d) first", n_parts);
   if (capacity_records < static_cast<int64_t>(g->G)) return set_err(PA_ERR_INVALID, "record buffer too small");
@@ -2895,6 +2896,7 @@ int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records
   PartialsArgs a{};
   a.r = g->res; a.G = g->G; a.nparts = n_parts; a.row_base = g->opt.row_base;
   a.vw = g->last_vw; a.wide = g->last_wide;
+  a.compact = compact;
   for (auto& o : g->outs) {
     if (o.bit == AGG_FIRST) { a.first_vals = o.values.p; a.first_valid = o.valid.as<uint32_t>(); }
     if (o.bit == AGG_LAST) { a.last_vals = o.values.p; a.last_valid = o.valid.as<uint32_t>(); }
@@ -2909,6 +2911,10 @@ int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records
   return PA_OK;
 }
 
+int pa_groupby_partials_export(pa_groupby* g, int32_t n_parts, void* dev_records, int64_t capacity_records) {
+  return partials_export(g, n_parts, dev_records, capacity_records, false);
+}
+
 // Common part of the two merge entry points.  `d_off` = device array [n_sources + 1], exclusive prefix
 // of the per-source record counts (the exact total is d_off[n_sources]); nrec_max = host-side upper bound.
 // Scratch of one merge (key table, per-source index, compaction / sort buffers).  A communicator keeps one between
@@ -2917,7 +2923,7 @@ struct MergeScratch { DevBuf tkeys, idx, m_first, m_slot, s_first, s_slot, cub_t
 
 static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d_off, int32_t n_sources, uint64_t nrec_max,
                        uint32_t agg_mask, const char* value_format, const char* key_format, MergeScratch* keep = nullptr,
-                       uint64_t row_bound = 0) {
+                       uint64_t row_bound = 0, bool compact = false, uint64_t distinct_hint = 0) {
   cudaStream_t st = g->stream;
   g->merged = true;
   g->keys.resize(1);
@@ -2931,40 +2937,56 @@ static int merge_build(pa_groupby* g, const void* dev_records, const uint64_t* d
   PA_TRY(parse_format(value_format, &g->last_vw, &g->last_vc));
   g->last_vfmt = value_format;
   if (nrec_max >= 0xFFFFFFFFull) return set_err(PA_ERR_NOT_IMPLEMENTED, "more than 2^32-1 partial records per rank");
-  uint64_t cap = 1024;
-  while (cap < nrec_max * 2) cap <<= 1;
-  const uint64_t nslots = cap + 2;
   MergeScratch local_scratch;
   MergeScratch& ms = keep ? *keep : local_scratch;
   DevBuf &tkeys = ms.tkeys, &idx = ms.idx, &m_first = ms.m_first, &m_slot = ms.m_slot, &s_first = ms.s_first, &s_slot = ms.s_slot, &cub_tmp = ms.cub_tmp;
-  PA_TRY(tkeys.alloc(nslots * 8, st));
-  PA_TRY(idx.alloc(nslots * n_sources * 4, st));
-  const int fgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
-  k_fill_u64<<<fgrid, 256, 0, st>>>(tkeys.as<unsigned long long>(), nslots, kEmptyKey);
-  CUDA_TRY(cudaMemsetAsync(idx.p, 0xFF, nslots * n_sources * 4, st));
   PA_TRY(m_first.alloc(std::max<uint64_t>(nrec_max, 1) * 8, st));
   PA_TRY(m_slot.alloc(std::max<uint64_t>(nrec_max, 1) * 4, st));
   MergeArgs a{};
   a.records = static_cast<const uint64_t*>(dev_records);
   a.src_offset = d_off;
-  a.nsrc = n_sources; a.nrec = nrec_max;
-  a.tkeys = tkeys.as<unsigned long long>(); a.cap_mask = cap - 1; a.idx = idx.as<uint32_t>();
+  a.nsrc = n_sources; a.nrec = nrec_max; a.compact = compact;
   a.status = g->status.as<uint32_t>();
   a.m_first_row = m_first.as<uint64_t>(); a.m_slot = m_slot.as<uint32_t>();
   a.vc = g->last_vc;
-  CUDA_TRY(cudaEventRecord(g->ev[1], st));
-  if (nrec_max) {
-    k_merge_insert<<<static_cast<int>((nrec_max + 255) / 256), 256, 0, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-  }
-  k_merge_compact<<<static_cast<int>((nslots + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(g->ev[2], st));
+  // Join table: 2^k >= 2 x the number of distinct keys.  A source holds every key at most once, so the count lies
+  // between the largest source and the sum; sources that saw (nearly) the same keys — row-range shards of one column —
+  // are the common case, so the table is sized by `distinct_hint` (the largest source; 0 = unknown) first: 8 sources of
+  // 12.5 M records fill 2^25 slots instead of 2^28 (index array 1 GB instead of 8.6 GB per step).  Too small shows as a
+  // probe sequence beyond max_probe; then the merge is redone with the table every key set fits.
   uint32_t h_status[ST_WORDS];
-  CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  if (h_status[ST_PEER_OVERFLOW]) return set_err(PA_ERR_STATE, "a source rank had more groups than a padded block holds; use the counted exchange");
-  if (h_status[ST_OVERFLOW]) return set_err(PA_ERR_CUDA, "merge table overflow");
+  uint64_t sized_for = distinct_hint ? std::min<uint64_t>(std::max<uint64_t>(distinct_hint + distinct_hint / 4, 512), std::max<uint64_t>(nrec_max, 512)) : std::max<uint64_t>(nrec_max, 512);
+  for (;;) {
+    uint64_t cap = 1024;
+    while (cap < sized_for * 2) cap <<= 1;
+    const uint64_t nslots = cap + 2;
+    PA_TRY(tkeys.alloc(nslots * 8, st));
+    PA_TRY(idx.alloc(nslots * n_sources * 4, st));
+    const int fgrid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
+    k_fill_u64<<<fgrid, 256, 0, st>>>(tkeys.as<unsigned long long>(), nslots, kEmptyKey);
+    CUDA_TRY(cudaMemsetAsync(idx.p, 0xFF, nslots * n_sources * 4, st));
+    a.tkeys = tkeys.as<unsigned long long>(); a.cap_mask = cap - 1; a.idx = idx.as<uint32_t>();
+    a.max_probe = sized_for >= nrec_max ? cap : std::min<uint64_t>(cap, 2048);
+    CUDA_TRY(cudaEventRecord(g->ev[1], st));
+    if (nrec_max) {
+      k_merge_insert<<<static_cast<int>((nrec_max + 255) / 256), 256, 0, st>>>(a);
+      CUDA_TRY(cudaGetLastError());
+    }
+    k_merge_compact<<<static_cast<int>((nslots + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(g->ev[2], st));
+    CUDA_TRY(cudaMemcpyAsync(h_status, g->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_status[ST_PEER_OVERFLOW]) return set_err(PA_ERR_STATE, "a source rank had more groups than a padded block holds; use the counted exchange");
+    if (h_status[ST_OVERFLOW] && sized_for < nrec_max) {   // the hint was too small: every key set fits a table sized by the record count
+      sized_for = nrec_max;
+      CUDA_TRY(cudaMemsetAsync(a.status + ST_OVERFLOW, 0, sizeof(uint32_t), st));
+      CUDA_TRY(cudaMemsetAsync(a.status + ST_COUNTER, 0, sizeof(uint32_t), st));
+      continue;
+    }
+    if (h_status[ST_OVERFLOW]) return set_err(PA_ERR_CUDA, "merge table overflow");
+    break;
+  }
   const uint32_t G = h_status[ST_COUNTER];
   g->G = G;
   const bool wide = is_wide(agg_mask, g->last_vc);
@@ -3025,7 +3047,8 @@ int pa_merge_create(const void* dev_records, const int64_t* counts_by_source, in
   CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(uint64_t) * (n_sources + 1), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
   CUDA_TRY(cudaEventRecord(g->ev[0], st));
-  PA_TRY(merge_build(g.get(), dev_records, d_off.as<uint64_t>(), n_sources, nrec, agg_mask, value_format, key_format));
+  PA_TRY(merge_build(g.get(), dev_records, d_off.as<uint64_t>(), n_sources, nrec, agg_mask, value_format, key_format, nullptr, 0, false,
+                     static_cast<uint64_t>(*std::max_element(counts_by_source, counts_by_source + n_sources))));
   *out = g.release();
   return PA_OK;
 }
@@ -3342,20 +3365,23 @@ int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDe
     recv_total += recv_cnt[p];
     row_bound = std::max(row_bound, all[static_cast<size_t>(p) * W1 + W]);
   }
-  // 3. export the records grouped by owner
-  PA_TRY(c->send.alloc(std::max<uint64_t>(send_total, 1) * PA_PARTIAL_WORDS * 8, st));
-  PA_TRY(c->recv.alloc(std::max<uint64_t>(recv_total, 1) * PA_PARTIAL_WORDS * 8, st));
+  // 3. export the records grouped by owner (sum / mean of floats / count need one 32-byte sector per group, everything
+  // else the full record)
+  const bool compact = !g->last_wide && !(agg_mask & (AGG_FIRST | AGG_LAST));
+  const size_t RW = static_cast<size_t>(rec_words(compact));
+  PA_TRY(c->send.alloc(std::max<uint64_t>(send_total, 1) * RW * 8, st));
+  PA_TRY(c->recv.alloc(std::max<uint64_t>(recv_total, 1) * RW * 8, st));
   g->parts_n = W;
   g->parts_counts.assign(send_cnt.begin(), send_cnt.end());
-  PA_TRY(pa_groupby_partials_export(g, W, c->send.p, static_cast<int64_t>(std::max<uint64_t>(send_total, g->G))));
+  PA_TRY(partials_export(g, W, c->send.p, static_cast<int64_t>(std::max<uint64_t>(send_total, g->G)), compact));
   CUDA_TRY(cudaEventRecord(c->ev[2], st));
   // 4. all-to-all of the records
   NCCL_TRY(ncclGroupStart());
   {
     uint64_t so = 0, ro = 0;
     for (int p = 0; p < W; ++p) {
-      if (send_cnt[p]) NCCL_TRY(ncclSend(c->send.as<uint64_t>() + so * PA_PARTIAL_WORDS, static_cast<size_t>(send_cnt[p]) * PA_PARTIAL_WORDS, ncclUint64, p, c->comm, st));
-      if (recv_cnt[p]) NCCL_TRY(ncclRecv(c->recv.as<uint64_t>() + ro * PA_PARTIAL_WORDS, static_cast<size_t>(recv_cnt[p]) * PA_PARTIAL_WORDS, ncclUint64, p, c->comm, st));
+      if (send_cnt[p]) NCCL_TRY(ncclSend(c->send.as<uint64_t>() + so * RW, static_cast<size_t>(send_cnt[p]) * RW, ncclUint64, p, c->comm, st));
+      if (recv_cnt[p]) NCCL_TRY(ncclRecv(c->recv.as<uint64_t>() + ro * RW, static_cast<size_t>(recv_cnt[p]) * RW, ncclUint64, p, c->comm, st));
       so += send_cnt[p];
       ro += recv_cnt[p];
     }
@@ -3377,7 +3403,8 @@ int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDe
   CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(uint64_t) * (W + 1), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemsetAsync(m->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
   CUDA_TRY(cudaEventRecord(m->ev[0], st));
-  PA_TRY(merge_build(m.get(), c->recv.p, d_off.as<uint64_t>(), W, recv_total, agg_mask, value_schema->format, kfmt.c_str(), &c->merge, row_bound));
+  PA_TRY(merge_build(m.get(), c->recv.p, d_off.as<uint64_t>(), W, recv_total, agg_mask, value_schema->format, kfmt.c_str(), &c->merge, row_bound, compact,
+                      static_cast<uint64_t>(*std::max_element(recv_cnt.begin(), recv_cnt.end()))));
   CUDA_TRY(cudaEventRecord(c->ev[4], st));
   CUDA_TRY(cudaEventSynchronize(c->ev[4]));
   float t = 0;

@@ -201,3 +201,85 @@ def test_sharded_resample_equals_single_gpu(world, closed_right, label_right):
     for a in ALL:
         got = pa.concat_arrays(out[a]).take(order)
         (assert_fp_close if a in ("sum", "mean") else assert_exact)(got, want[a], f"{a} P={world}")
+
+
+@pytest.fixture(scope="module")
+def single_rank_comm(tmp_path_factory):
+    """A pa_comm of world size 1 (NCCL communicator with one rank) over a one-process gloo group: the whole sharded
+    step — count, export, self send/recv, merge — through pa_groupby_sharded_aggregate on a single GPU."""
+    import torch.distributed as dist
+    from pandasarrow_b200 import distributed as D
+    own_group = not dist.is_initialized()
+    if own_group:
+        store = dist.FileStore(str(tmp_path_factory.mktemp("pg") / "store"), 1)
+        dist.init_process_group("gloo", store=store, rank=0, world_size=1)
+    comm = D.Comm(device=0)
+    yield comm
+    comm.close()
+    if own_group:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("aggs", [["sum", "mean", "count"], ["count"], ALL], ids=["compact", "compact-count", "full"])
+@pytest.mark.parametrize("G,nulls,vtype", [(700, False, "f64"), (40_000, True, "f64"), (3000, True, "i64"), (500, False, "f32")])
+def test_communicator_step_compact_and_full_records(single_rank_comm, aggs, G, nulls, vtype):
+    """sum / mean-of-floats / count travel as 32-byte compact records, everything else as the full 88-byte record
+    (merge.cuh); both against the oracle, with a null key group, null values and global row numbers beyond 32 bits."""
+    import pandasarrow_b200 as pab
+    from oracle import oracle as orc
+    from util import abs_scale, align_to, assert_exact, assert_fp_close, first_appearance_order, with_abs
+    rng = np.random.default_rng(G)
+    n = 300_007
+    k = pa.array(rng.integers(-G // 2, G // 2, n), pa.int64(), mask=(rng.random(n) < 0.01) if nulls else None)
+    vmask = (rng.random(n) < 0.05) if nulls else None
+    if vtype == "i64":
+        v = pa.array(rng.integers(-10**6, 10**6, n), pa.int64(), mask=vmask)
+    else:
+        v = pa.array(rng.normal(size=n).astype(np.float32 if vtype == "f32" else np.float64), mask=vmask)
+    rb = pa.record_batch({"k": k, "v": v})
+    row_base = 5_000_000_000
+    gb = pab.GroupBy("k", rb, row_base=row_base)
+    m = single_rank_comm.sharded_aggregate(gb, rb.column("v"), aggs)
+    ora = orc.OracleGroupBy(with_abs(rb), "k")
+    ours = [(x,) for x in m.unique().to_pylist()]
+    assert ours == first_appearance_order([rb.column("k")]), "global first-appearance order"
+    perm = pa.array(align_to(ours, [(x,) for x in ora.unique().to_pylist()]))
+    fr = m.first_rows().to_numpy()
+    assert (np.diff(fr) > 0).all() and fr[0] == row_base
+    for a in aggs:
+        got = m.fetch(a).take(perm)
+        if a == "mean":
+            want, valid = ora.agg("mean", "v", nthreads=8, with_validity=True)
+            want = pa.array(want.to_numpy(zero_copy_only=False), pa.float64(), mask=~np.asarray(valid.to_numpy(zero_copy_only=False), dtype=bool))
+            assert_fp_close(got, want, "mean", abs_scale(ora, "v", mean=True))
+        elif a == "sum" and vtype != "i64":
+            assert_fp_close(got, ora.agg("sum", "v", nthreads=8), "sum", abs_scale(ora, "v"))
+        else:
+            assert_exact(got, ora.agg(a, "v", nthreads=8), a)
+    m.close(); gb.close(); ora.close()
+
+
+@pytest.mark.parametrize("world", [3, 8])
+def test_merge_of_disjoint_key_sets_outgrows_the_hinted_table(world):
+    """The join table of a merge is sized by its largest source first (row-range shards of one column mostly share
+    their keys); shards with DISJOINT key sets hold `world` times as many keys, the probe bound trips and the merge is
+    redone with the table sized by the record count — same result as the single-GPU pass."""
+    import pandasarrow_b200 as pab
+    from oracle import oracle as orc
+    from util import abs_scale, align_to, assert_exact, assert_fp_close, first_appearance_order, with_abs
+    rng = np.random.default_rng(world)
+    per, G = 120_000, 50_000
+    k = np.concatenate([rng.integers(0, G, per) * world + r for r in range(world)]).astype(np.int64)   # shard r: keys = r mod world
+    rb = pa.record_batch({"k": pa.array(k), "v": pa.array(rng.normal(size=per * world))})
+    keys, res, _ = _run_sharded(pab, rb, "k", "v", ALL, world)
+    ora = orc.OracleGroupBy(with_abs(rb), "k")
+    ours = [(x,) for x in keys.to_pylist()]
+    assert ours == first_appearance_order([rb.column("k")])
+    perm = pa.array(align_to(ours, [(x,) for x in ora.unique().to_pylist()]))
+    for a in ALL:
+        got, want = res[a].take(perm), ora.agg(a, "v", nthreads=8)
+        if a in ("sum", "mean"):
+            assert_fp_close(got, want, a, abs_scale(ora, "v", mean=(a == "mean")))
+        else:
+            assert_exact(got, want, a)
+    ora.close()
