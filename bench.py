@@ -479,8 +479,11 @@ def main():
             tg5 = torch.tensor([found], device=dev, dtype=torch.int64)
             dist.all_reduce(tg5)
             ph = {k: sorted(p_[k] for p_ in phases)[len(phases) // 2] for k in phases[0]}
+            xi = comm.exchange_info()
             extras["config5"] = {"rows_per_gpu": n, "groups": g5, "groups_found_global": int(tg5.item()), "aggs": AGGS,
                                  "exchange": "pa_comm (C ABI): ncclAllGather of counts + grouped ncclSend/ncclRecv of records",
+                                 "record_bytes": xi["record_bytes"], "unordered_export": xi["unordered_export"],
+                                 "merge_table_slots": xi["merge_table_slots"],
                                  "steps": k5, "ms_per_step": t5[0].item(),
                                  "local_pass_ms": t5[1].item(), "rows_per_s": world * n / (t5[0].item() * 1e-3),
                                  "efficiency_vs_local_pass": t5[1].item() / t5[0].item(), "phases_rank0_ms": ph}

@@ -353,6 +353,10 @@ int pa_groupby_sharded_aggregate(pa_groupby* g, pa_comm* c, const struct ArrowDe
                                  const struct ArrowSchema* value_schema, uint32_t agg_mask, pa_groupby** merged_out);
 /* Device time (ms) of the last step's phases: [0] local pass, [1] count + export, [2] exchange, [3] merge, [4] total. */
 int pa_comm_last_phases(pa_comm* c, double phase_ms[5]);
+/* How the last step's partial aggregates travelled: bytes per group record (32: compact records of sum / mean of floats /
+ * count; 88: the full PA_PARTIAL_WORDS record), whether the local pass handed over the bucketed path's unordered group
+ * records without ordering them first (0 / 1), and the slots of the merge's join table. */
+int pa_comm_last_exchange(pa_comm* c, int32_t* record_bytes, int32_t* unordered_export, int64_t* merge_table_slots);
 
 /* ---- synthetic workload generator, used by bench.py and the tests so that the
  * same counter-based splitmix64 streams exist on host and device without PCIe staging.

@@ -26,7 +26,7 @@ EXPORTS = [
     "pa_groupby_destroy", "pa_column_to_device", "pa_sort_create", "pa_sort_indices", "pa_resample_create", "pa_resample_create_calendar", "pa_downsample_create", "pa_groupby_partials_count", "pa_groupby_partials_export",
     "pa_merge_create", "pa_groupby_aggregate_chunked", "pa_groupby_partials_export_padded", "pa_merge_create_padded", "pa_groupby_first_rows", "pa_synth_keys_i64", "pa_synth_vals_f64",
     "pa_synth_validity", "pa_synth_timestamps",
-    "pa_comm_unique_id", "pa_comm_create", "pa_comm_adopt", "pa_comm_destroy", "pa_groupby_sharded_aggregate", "pa_comm_last_phases",
+    "pa_comm_unique_id", "pa_comm_create", "pa_comm_adopt", "pa_comm_destroy", "pa_groupby_sharded_aggregate", "pa_comm_last_phases", "pa_comm_last_exchange",
 ]
 
 
@@ -142,6 +142,7 @@ def load():
     L.pa_comm_destroy.restype = None
     L.pa_groupby_sharded_aggregate.argtypes = [P, P, C.POINTER(ArrowDeviceArray), C.POINTER(ArrowSchema), C.c_uint32, C.POINTER(P)]
     L.pa_comm_last_phases.argtypes = [P, C.POINTER(C.c_double)]
+    L.pa_comm_last_exchange.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
     L.pa_synth_keys_i64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, P]
     L.pa_synth_vals_f64.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, P]
     L.pa_synth_validity.argtypes = [P, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32, P]

@@ -41,6 +41,7 @@
 // pd_core_macros.h:114-147) for the cardinalities where the reference's per-group loop takes seconds.
 #pragma once
 #include "gtable.cuh"
+#include "merge.cuh"
 #include "order.cuh"
 
 namespace pa {
@@ -633,6 +634,53 @@ __global__ void __launch_bounds__(256) k_bk_gather(const void* recs, const uint3
     if (out.dsum) out.dsum[r] = rec.dsum;
   } else {
     out.last_row[r] = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded step with compact partial records (merge.cuh): the unordered group records of the bucket aggregation go
+// straight to their owners — no ranking, no gather into the GroupResult, no second read of it by the export.
+// Same owner function, same per-CTA cursor claim as k_partials_count / k_partials_scatter.  nparts <= 64.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bkrec_count(const BkRec32* recs, uint32_t G, uint32_t nparts, unsigned long long* counts) {
+  __shared__ unsigned int s_cnt[64];
+  if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) atomicAdd(&s_cnt[owner_of(recs[g].key, KK_REGULAR, nparts)], 1u);
+  __syncthreads();
+  if (threadIdx.x < nparts && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+}
+
+__global__ void __launch_bounds__(256) k_bkrec_scatter(const BkRec32* recs, uint32_t G, uint32_t nparts, int64_t row_base,
+                                                       unsigned long long* cursor, uint64_t* records) {
+  __shared__ unsigned int s_cnt[64];
+  __shared__ unsigned long long s_base[64];
+  if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t o = 0, local = 0;
+  uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+  if (g < G) {
+    const uint4* src = reinterpret_cast<const uint4*>(recs + g);
+    lo = __ldg(src);          // key, sum
+    hi = __ldg(src + 1);      // count, first row, pad
+    o = owner_of(static_cast<uint64_t>(lo.x) | (static_cast<uint64_t>(lo.y) << 32), KK_REGULAR, nparts);
+    local = atomicAdd(&s_cnt[o], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nparts && s_cnt[threadIdx.x])
+    s_base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+  __syncthreads();
+  if (g < G) {
+    ulonglong2 a, b;
+    a.x = static_cast<uint64_t>(lo.x) | (static_cast<uint64_t>(lo.y) << 32);
+    a.y = static_cast<uint64_t>(lo.z) | (static_cast<uint64_t>(lo.w) << 32);
+    b.x = static_cast<uint64_t>(hi.x);                                        // count (a bucket record never has a null key)
+    b.y = static_cast<uint64_t>(row_base + static_cast<int64_t>(hi.y));       // global first row
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(records + (s_base[o] + local) * REC_WORDS_COMPACT);
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 

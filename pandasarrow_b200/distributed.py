@@ -118,6 +118,14 @@ class Comm:
         _check(self._L.pa_comm_last_phases(self._h, p))
         return {"local_ms": p[0], "export_ms": p[1], "exchange_ms": p[2], "merge_ms": p[3], "total_ms": p[4]}
 
+    def exchange_info(self) -> Dict[str, int]:
+        """Record format of the last step (pa_comm_last_exchange)."""
+        import ctypes as C
+        from .groupby import _check
+        rb, un, slots = C.c_int32(), C.c_int32(), C.c_int64()
+        _check(self._L.pa_comm_last_exchange(self._h, C.byref(rb), C.byref(un), C.byref(slots)))
+        return {"record_bytes": rb.value, "unordered_export": bool(un.value), "merge_table_slots": slots.value}
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._L.pa_comm_destroy(self._h)
