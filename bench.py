@@ -498,10 +498,14 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            hk = torch.empty(n, dtype=torch.int64, pin_memory=True)
-            hv = torch.empty(n, dtype=torch.float64, pin_memory=True)
-            hk.copy_(keys); hv.copy_(vals)
-            torch.cuda.synchronize()
+            # one process per GPU, each on the NUMA node of its GPU while it allocates (first-touches) the pinned host
+            # columns: with 4-8 ranks the host -> device copies otherwise share one node's DRAM and the socket link
+            from pandasarrow_b200.numa import bind_to_device_numa
+            with bind_to_device_numa(local) as numa_bind:
+                hk = torch.empty(n, dtype=torch.int64, pin_memory=True)
+                hv = torch.empty(n, dtype=torch.float64, pin_memory=True)
+                hk.copy_(keys); hv.copy_(vals)
+                torch.cuda.synchronize()
             ak = pa.Array.from_buffers(pa.int64(), n, [None, pa.py_buffer(hk.numpy())])
             av = pa.Array.from_buffers(pa.float64(), n, [None, pa.py_buffer(hv.numpy())])
 
@@ -523,7 +527,8 @@ def main():
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e = {"value": world * n / tt.item(), "unit": UNIT, "h2d_bytes_per_step": 16 * n,
                    "d2h_bytes_per_step": d2h, "ms_per_step": tt.item() * 1e3, "steps": e2e_steps,
-                   "note": "pinned host Arrow buffers -> pa_groupby_create/aggregate/fetch; wall clock around synchronous calls"}
+                   "note": "pinned host Arrow buffers -> pa_groupby_create/aggregate/fetch; wall clock around synchronous calls",
+                   "host_numa": numa_bind.info}
             # the same call with ORDINARY (pageable) host memory — what an Arrow heap buffer / an IPC blob is: the library
             # stages it through its own pinned double buffer with a few copy threads (h2d_copy in capi.cu)
             if world == 1:
