@@ -231,30 +231,43 @@ __global__ void __launch_bounds__(1024) k_rp_cprefix(const unsigned int* ends, i
   if (t == n_parents - 1) cprefix[n_parents] = s[t];
 }
 
-struct RpSmem {
+template <int THREADS>
+struct RpSmemT {
+  static constexpr int TILE = THREADS * RP_ROWS;
   static constexpr size_t OFF_KEY = 0;
-  static constexpr size_t OFF_VAL = OFF_KEY + sizeof(uint64_t) * RP_TILE;
-  static constexpr size_t OFF_ROW = OFF_VAL + sizeof(uint64_t) * RP_TILE;
-  static constexpr size_t OFF_HIST = OFF_ROW + sizeof(uint32_t) * RP_TILE;
+  static constexpr size_t OFF_VAL = OFF_KEY + sizeof(uint64_t) * TILE;
+  static constexpr size_t OFF_ROW = OFF_VAL + sizeof(uint64_t) * TILE;
+  static constexpr size_t OFF_HIST = OFF_ROW + sizeof(uint32_t) * TILE;
   static constexpr size_t OFF_OFF = OFF_HIST + sizeof(uint32_t) * RP_MAX_FAN;
   static constexpr size_t OFF_DELTA = OFF_OFF + sizeof(uint32_t) * RP_MAX_FAN;
   static constexpr size_t OFF_CUR = OFF_DELTA + sizeof(uint32_t) * RP_MAX_FAN;
   static constexpr size_t TOTAL = OFF_CUR + sizeof(uint32_t) * RP_MAX_FAN;
 };
+using RpSmem = RpSmemT<RP_THREADS>;
+constexpr int RP_THREADS_BIG = 1024;          // 8192-row tiles, one CTA per SM: runs twice as long at the same fan-out
+using RpSmemBig = RpSmemT<RP_THREADS_BIG>;
 static_assert(2 * (RpSmem::TOTAL + 1024) <= 227 * 1024, "two scatter CTAs per SM");
+static_assert(RpSmemBig::TOTAL + 1024 <= 227 * 1024, "one big-tile scatter CTA per SM");
+static_assert(RP_CHUNK_ROWS % RpSmemBig::TILE == 0 && RpSmemBig::TILE <= (1 << 13), "tile ranks are 13 bits");
 
 // Two CTAs per SM: the phases of a tile are separated by barriers (load -> rank -> offsets -> regroup -> write), so a
 // second resident CTA keeps the memory system busy while the first one regroups.
-__global__ void __launch_bounds__(RP_THREADS, 2) k_rp_scatter(RpArgs a) {
+// THREADS = 1024 (8192-row tiles, one CTA per SM) for fan-outs whose 4096-row runs would be 128 bytes or shorter
+// (launch_rp_scatter in capi.cu picks; measured there).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1) k_rp_scatter_t(RpArgs a) {
+  using S = RpSmemT<THREADS>;
+  constexpr int RP_THREADS = THREADS;                // (shadows the namespace constants inside this kernel)
+  constexpr int RP_TILE = S::TILE;
   extern __shared__ __align__(16) unsigned char rp_smem[];
-  uint64_t* st_key = reinterpret_cast<uint64_t*>(rp_smem + RpSmem::OFF_KEY);
-  uint64_t* st_val = reinterpret_cast<uint64_t*>(rp_smem + RpSmem::OFF_VAL);
-  uint32_t* st_row = reinterpret_cast<uint32_t*>(rp_smem + RpSmem::OFF_ROW);
-  unsigned int* s_hist = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_HIST);
-  unsigned int* s_off = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_OFF);
+  uint64_t* st_key = reinterpret_cast<uint64_t*>(rp_smem + S::OFF_KEY);
+  uint64_t* st_val = reinterpret_cast<uint64_t*>(rp_smem + S::OFF_VAL);
+  uint32_t* st_row = reinterpret_cast<uint32_t*>(rp_smem + S::OFF_ROW);
+  unsigned int* s_hist = reinterpret_cast<unsigned int*>(rp_smem + S::OFF_HIST);
+  unsigned int* s_off = reinterpret_cast<unsigned int*>(rp_smem + S::OFF_OFF);
   // s_delta[b] = (start of this tile's run for b in the output) - (start of the run in the regrouped tile)
-  unsigned int* s_delta = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_DELTA);
-  unsigned int* s_cur = reinterpret_cast<unsigned int*>(rp_smem + RpSmem::OFF_CUR);   // this chunk's write cursors
+  unsigned int* s_delta = reinterpret_cast<unsigned int*>(rp_smem + S::OFF_DELTA);
+  unsigned int* s_cur = reinterpret_cast<unsigned int*>(rp_smem + S::OFF_CUR);   // this chunk's write cursors
   __shared__ unsigned int s_wsum[RP_THREADS / 32];
   constexpr int BINS = RP_MAX_FAN / RP_THREADS;      // histogram bins per thread in the scan
   const int fan = 1 << a.log_fan;

@@ -729,6 +729,27 @@ double hll_estimate(const uint32_t* reg) {
   return e * static_cast<double>(1u << HLL_SAMPLE_LOG2);
 }
 
+// One partition level.  At 256 ways and more a 4096-row tile leaves runs of <= 16 rows (128-byte pieces of the key / value
+// arrays, 64 of the row numbers): those take 8192-row tiles on one 1024-thread CTA per SM instead of two 512-thread CTAs
+// with 4096-row tiles.  Measured per 1 B rows: 100 M groups (256 x 256) 45.0 -> 43.2 ms; at 128 ways the lost overlap
+// between the two CTAs costs more than the longer runs give (16 M groups, 128 x 128: 32.0 -> 34.4 ms), so the threshold
+// is 2^8.  PA_RP_BIG_TILE_LOG (environment, read once) moves it for A/B runs.
+int launch_rp_scatter(pa_groupby* g, const RpArgs& a) {
+  static const int big_from = [] { const char* e = std::getenv("PA_RP_BIG_TILE_LOG"); return e ? std::atoi(e) : 8; }();
+  cudaStream_t st = g->stream;
+  if (a.log_fan >= big_from) {
+    auto kern = k_rp_scatter_t<RP_THREADS_BIG>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RpSmemBig::TOTAL)));
+    kern<<<g->num_sms, RP_THREADS_BIG, RpSmemBig::TOTAL, st>>>(a);
+  } else {
+    auto kern = k_rp_scatter_t<RP_THREADS>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RpSmem::TOTAL)));
+    kern<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return PA_OK;
+}
+
 // The bucketed path (bucketed.cuh).  *declined = true: the estimate says a single shared-memory table holds the
 // groups, or a bucket overflowed its table — the caller continues on the global-table path.
 template <int VC, bool WIDE>
@@ -809,9 +830,7 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
     CUDA_TRY(cudaGetLastError());
     g->last_launches += 1;
   }
-  CUDA_TRY(cudaFuncSetAttribute(k_rp_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RpSmem::TOTAL)));
-  k_rp_scatter<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a1);
-  CUDA_TRY(cudaGetLastError());
+  PA_TRY(launch_rp_scatter(g, a1));
   g->last_launches += 1;
   BkArgs b{};
   b.keys = sc.p_keys.as<uint64_t>(); b.vals = vals ? sc.p_vals.as<uint64_t>() : nullptr; b.rows = sc.p_rows.as<uint32_t>();
@@ -848,8 +867,7 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
     k_rp_ends<<<(nb + 255) / 256, 256, 0, st>>>(a2, sc.rp_ends2.as<unsigned int>());
     CUDA_TRY(cudaGetLastError());
     g->last_launches += 1;
-    k_rp_scatter<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a2);
-    CUDA_TRY(cudaGetLastError());
+    PA_TRY(launch_rp_scatter(g, a2));
     g->last_launches += 1;
     b.keys = sc.q_keys.as<uint64_t>(); b.vals = vals ? sc.q_vals.as<uint64_t>() : nullptr; b.rows = sc.q_rows.as<uint32_t>();
     b.bucket_end = sc.rp_ends2.as<unsigned int>();
