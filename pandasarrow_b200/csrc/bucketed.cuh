@@ -34,9 +34,10 @@
 //
 // DRAM traffic per row (8-byte key + 8-byte value): scatter 16 + 20 B, aggregate 20 B = 56 B for one level (+ 8 B for
 // the histogram on a handle's first pass); + 8 + 20 + 20 B for the second level = 104 B, against 16 B algorithmic: the
-// floor of this design is 0.29 (one level) / 0.15 (two levels) of the 16 B/row roofline.  Only for 8-byte keys and
-// values without validity bitmaps; anything else, and any bucket that turns out to hold more keys than its table
-// (ST_OVERFLOW), goes to the global-table path (gtable.cuh).
+// floor of this design is 0.29 (one level) / 0.15 (two levels) of the 16 B/row roofline.  Only for 8-byte keys without
+// a validity bitmap and 8-byte values (a nullable value column below 2^31 rows: the validity bit travels as RP_NULL_BIT
+// of the row numbers); anything else, and any bucket that turns out to hold more keys than its table (ST_OVERFLOW), goes
+// to the global-table path (gtable.cuh).
 // Replaces Grouper::Consume + per-group CallFunction (/root/reference/src/dataframe.cpp:1582-1584,
 // pd_core_macros.h:114-147) for the cardinalities where the reference's per-group loop takes seconds.
 #pragma once
@@ -62,6 +63,7 @@ constexpr int HLL_M = 1 << HLL_LOG2;
 constexpr int HLL_SAMPLE_LOG2 = 3;                    // one key value in 8 feeds the sketch
 constexpr int BK_THREADS = 768;
 constexpr int BK_MAX_PROBE = 64;
+constexpr uint32_t RP_NULL_BIT = 0x80000000u;         // row-number word of the partitioned rows: the row's value is null
 
 __device__ __forceinline__ uint64_t rp_mix(uint64_t key) { return (key ^ (key >> 32)) * 0x9E3779B97F4A7C15ull; }
 
@@ -90,6 +92,8 @@ struct RpArgs {
   const uint64_t* keys;
   const uint64_t* vals;          // may be null (keys-only pass)
   const uint32_t* rows;          // original row numbers of the source rows; null = the source IS the original order
+  const uint8_t* vvalid;         // level 1 only: validity bitmap of the value column (or null); a null value travels as
+  int64_t voff;                  //   bit 31 of the row number (RP_NULL_BIT; the host admits < 2^31 rows then)
   int64_t n;
   int shift;                     // bucket inside the parent = (rp_mix(key) >> shift) & (fan - 1)
   int log_fan;
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1) k_rp_scatter_
         const int r = threadIdx.x + j * RP_THREADS;
         row[j] = static_cast<uint32_t>(row0 + r);
         if (a.rows && pr[j] != 0xFFFFFFFFu) row[j] = ldg_stream_u32_na(a.rows + row0 + r);
+        if (!a.rows && a.vvalid && pr[j] != 0xFFFFFFFFu && !bit_at(a.vvalid, a.voff + row0 + r)) row[j] |= RP_NULL_BIT;
       }
 #pragma unroll
       for (int j = 0; j < RP_ROWS; ++j) {
@@ -396,6 +401,7 @@ struct BkArgs {
   unsigned int* next_bucket;     // work counter
   uint32_t agg_mask;
   uint32_t max_keys;             // keys a bucket's table admits
+  int nullable;                  // the row-number words carry RP_NULL_BIT for rows whose value is null
   // unordered groups: one record per group (BkRec: whole sectors, so the ordering pass reads a group with one or two
   // adjacent sector fetches) + their first rows as a plain array (bitmap / rank passes)
   void* u_rec;
@@ -487,8 +493,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
         const uint64_t idx = base + j;
         if (idx < start || idx >= end) continue;
         const uint64_t key = keyv[j];
-        const uint32_t row = rowv[j];
-        uint32_t s;
+        uint32_t row = rowv[j];
+        bool vvalid = true;
+        if (a.nullable) { vvalid = (row & RP_NULL_BIT) == 0u; row &= ~RP_NULL_BIT; }   // a null value: the row still makes
+        uint32_t s;                                                                    // the group and counts for first / last
         bool found = false;
         if (key == kEmptyKey) { s = T::CAP + 1; found = true; }
         else {
@@ -510,7 +518,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
         if constexpr (WIDE) {
           if ((a.agg_mask & AGG_LAST) && row > *reinterpret_cast<volatile uint32_t*>(s_last + s)) atomicMax(s_last + s, row);
         }
-        if (!a.vals) continue;
+        if (!a.vals || !vvalid) continue;
         atomicAdd(s_cnt + s, 1u);
         if constexpr (VC == VC_F) atomicAdd(reinterpret_cast<double*>(s_sum + s), __longlong_as_double(static_cast<long long>(valv[j])));
         else atomicAdd(s_sum + s, static_cast<unsigned long long>(valv[j]));

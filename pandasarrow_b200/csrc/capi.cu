@@ -771,6 +771,7 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
   CUDA_TRY(cudaMemsetAsync(g->status.p, 0, sizeof(uint32_t) * ST_WORDS, st));
   RpArgs a1{};
   a1.keys = keys; a1.vals = vals; a1.rows = nullptr; a1.n = n;
+  a1.vvalid = val ? val->valid : nullptr; a1.voff = val ? val->bit_off : 0;
   a1.n_parents = 1; a1.n_chunks1 = nchunks1;
   if (!g->bk_have_hist) {
     PA_TRY(sc.rp_fine.alloc(sizeof(uint32_t) * RP_MAX_FAN * static_cast<size_t>(nchunks1), st));
@@ -835,6 +836,7 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
   BkArgs b{};
   b.keys = sc.p_keys.as<uint64_t>(); b.vals = vals ? sc.p_vals.as<uint64_t>() : nullptr; b.rows = sc.p_rows.as<uint32_t>();
   b.bucket_end = sc.rp_ends1.as<unsigned int>();
+  b.nullable = (val && val->valid) ? 1 : 0;
   if (b2 > 0) {
     // ---- level 2 inside every level-1 bucket ----
     const int np = 1 << b1;
@@ -999,7 +1001,8 @@ int run_global_t(pa_groupby* g, const Column* val, uint32_t mask) {
     // More groups than one shared-memory table holds (or nobody knows how many): partition into buckets and
     // aggregate those in shared memory (bucketed.cuh); it declines when its own estimate says the front table is enough
     const uint64_t known0 = g->opt.expected_groups > 0 ? static_cast<uint64_t>(g->opt.expected_groups) : (g->have_groups ? g->G : 0);
-    const bool plain = g->key_width == 8 && (!val || val->width == 8) && !g->key_valid && (!val || !val->valid) &&
+    // (a nullable VALUE column is fine below 2^31 rows: the validity bit rides in the row-number word of the partition)
+    const bool plain = g->key_width == 8 && (!val || val->width == 8) && !g->key_valid && (!val || !val->valid || g->n < (1ll << 31)) &&
                        reinterpret_cast<uintptr_t>(g->key_data) % 32 == 0 && (!val || reinterpret_cast<uintptr_t>(val->data) % 32 == 0);
     if (plain && !g->opt.no_partition && g->n >= (1ll << 22) && (known0 == 0 || known0 > static_cast<uint64_t>(SmTab<VC, WIDE>::CAP))) {
       bool declined = false;

@@ -189,6 +189,58 @@ def test_bucketed_path_vs_oracle(env, n, G, scattered, hint, ints, aggs):
     ora.close()
 
 
+@pytest.mark.parametrize("n,G,ints", [(6_000_000, 50_000, False), (8_000_000, 3_000_000, False), (8_000_000, 3_000_000, True)])
+def test_bucketed_path_nullable_values_vs_oracle(env, n, G, ints):
+    """A nullable VALUE column on the bucketed path: the validity bit travels in bit 31 of the partitioned row numbers.
+    One level (ranged aggregation into the global table) and two levels (whole buckets, records); with ~2.7 rows per
+    group at G = 3 M many groups hold nothing but nulls (sum / min / max / mean null, count 0, first / last positional)."""
+    pab, orc, torch = env
+    k, v = _gen(pab, torch, n, G, scattered=True)
+    if ints:
+        v = ((v * 2001.0).to(torch.int64) - 1000)
+    bits = torch.empty((n + 7) // 8, dtype=torch.uint8, device="cuda"); pab.synth.validity(bits, n, 0, 77, 3)   # every third value null
+    torch.cuda.synchronize()
+    kh = k.cpu().numpy()
+    vmask = pa.py_buffer(bits.cpu().numpy())
+    hv = pa.Array.from_buffers(pa.int64() if ints else pa.float64(), n, [vmask, pa.py_buffer(v.cpu().numpy())])
+    rb = pa.record_batch({"k": pa.array(kh), "v": hv})
+    ora = orc.OracleGroupBy(rb, "k")
+    dk = pab.DeviceColumn.from_torch(k)
+    dv = pab.DeviceColumn.from_torch(v, valid=bits, null_count=-1)
+    aggs = ["sum", "mean", "count", "min", "max", "first", "last"]
+    with pab.GroupBy("k", {"k": dk, "v": dv}, expected_groups=G) as gb:
+        res = gb.aggregate(dv, aggs)
+        ours = _np(gb.unique())
+        t = gb.timing()
+        assert t["mode"] == "bucketed", t
+    assert np.array_equal(ours, _first_appearance(kh)), "not in strict first-appearance order"
+    theirs = _np(ora.unique())
+    so, st = np.argsort(ours, kind="stable"), np.argsort(theirs, kind="stable")
+    assert np.array_equal(ours[so], theirs[st])
+    n_all_null = 0
+    for a in aggs:
+        if a == "mean":
+            want, valid = ora.agg("mean", "v", nthreads=THREADS, with_validity=True)
+            wv = np.asarray(_np(valid), dtype=bool)[st]
+        else:
+            want = ora.agg(a, "v", nthreads=THREADS)
+            wv = np.asarray(want.is_valid())[st]
+        got = res[a]
+        assert got.type == want.type, a
+        gv = np.asarray(got.is_valid())[so]
+        assert np.array_equal(gv, wv), a
+        if a == "sum":
+            n_all_null = int((~wv).sum())
+        g, w = _np(got)[so][gv], _np(want)[st][wv]
+        if a in ("sum", "mean") and pa.types.is_floating(got.type):
+            assert (np.abs(g - w) <= (FP_RTOL * np.maximum(np.abs(w), 1e-300) if not ints else 1e-9 * np.maximum(np.abs(w), 1.0))).all(), a
+        else:
+            assert np.array_equal(g, w), a
+    if G >= 1_000_000:
+        assert n_all_null > 1000          # the all-null-group case really occurred
+    ora.close()
+
+
 def test_config3_100m_rows_multi_key_nullable(env):
     pab, orc, torch = env
     n = 100_000_000
