@@ -142,6 +142,23 @@ struct RsLane {
       }
     }
   }
+  // the same without a branch (the steady state of the scan: every row of the batch is valid and in the open run);
+  // `want_mm` is warp-uniform
+  __device__ __forceinline__ void add_row_nb(uint64_t vb, bool want_mm) {
+    if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(sum)) +
+                                                                             __longlong_as_double(static_cast<long long>(vb))));
+    else sum += vb;
+    ++cnt;
+    if constexpr (WIDE) {
+      if constexpr (VC != VC_F) dsum += Wide<VC>::as_double(vb);
+      if (want_mm) {
+        const bool num = !Wide<VC>::is_nan(vb);
+        const uint64_t o = Wide<VC>::ord(vb);
+        mn = (num && o < mn) ? o : mn;
+        mx = (num && o > mx) ? o : mx;
+      }
+    }
+  }
   // all lanes end up with the warp total
   __device__ __forceinline__ void warp_total(RsAcc<VC, WIDE>& out) const {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -229,6 +246,27 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
       uint64_t vv[RS_U];
       bool ok[RS_U];
       const bool full = g0 + 32 * RS_U <= row_end;
+      if (full && fast_vals) {
+        // Steady state (a run is ~1000 rows in config 4, an iteration 128): unguarded loads, ONE vote for the whole
+        // iteration, straight-line branch-free folds.  (The per-batch code below costs ~95 warp instructions per 32 rows
+        // — votes, reconvergence points, guarded loads — and made the kernel issue bound at 0.60 of the HBM peak.)
+        const int64_t* tp0 = a.ts + g0 + lane;
+        const uint64_t* vp0 = static_cast<const uint64_t*>(a.vals) + g0 + lane;
+#pragma unroll
+        for (int u = 0; u < RS_U; ++u) tt[u] = tp0[u * 32];
+#pragma unroll
+        for (int u = 0; u < RS_U; ++u) { vv[u] = vp0[u * 32]; ok[u] = true; }
+        bool in_all = have_run;
+#pragma unroll
+        for (int u = 0; u < RS_U; ++u) in_all = in_all && static_cast<uint64_t>(tt[u] - shift - cur_lo) < freq;
+        if (__all_sync(FULL, in_all)) {
+          const bool want_mm = (a.agg_mask & (AGG_MIN | AGG_MAX)) != 0;
+#pragma unroll
+          for (int u = 0; u < RS_U; ++u) part.add_row_nb(vv[u], want_mm);
+          run_last = static_cast<uint32_t>(g0) + 32u * RS_U - 1u;
+          continue;
+        }
+      } else {
 #pragma unroll
       for (int u = 0; u < RS_U; ++u) {
         const int64_t row = g0 + u * 32 + lane;
@@ -245,6 +283,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
             ok[u] = a.vvalid ? bit_at(a.vvalid, a.voff + row) : true;
           }
         }
+      }
       }
 #pragma unroll
       for (int u = 0; u < RS_U; ++u) {
