@@ -1717,7 +1717,8 @@ int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
   const int init_grid = static_cast<int>(std::min<uint64_t>((nslots + 255) / 256, static_cast<uint64_t>(g->num_sms) * 16));
   k_gtable_init<WIDE><<<init_grid, 256, 0, st>>>(table.as<SlotT>(), nslots);
   CUDA_TRY(cudaGetLastError());
-  const int64_t nchunks = (g->n + RS_CHUNK - 1) / RS_CHUNK;
+  const int64_t chunk = rs_chunk_rows(g->n);
+  const int64_t nchunks = (g->n + chunk - 1) / chunk;
   PA_TRY(bnd.alloc(static_cast<size_t>(std::max<int64_t>(nchunks, 1)) * 2 * sizeof(RsPartial), st));
   if (nchunks > 0) {
     k_rs_init_bnd<<<static_cast<int>((nchunks * 2 + 255) / 256), 256, 0, st>>>(bnd.as<RsPartial>(), nchunks * 2);
@@ -1734,6 +1735,7 @@ int run_resample_t(pa_groupby* g, const Column* val, uint32_t mask) {
   a.table = table.p;
   a.bnd = bnd.as<RsPartial>();
   a.nchunks = nchunks;
+  a.chunk = chunk;
   a.status = g->status.as<uint32_t>();
   a.agg_mask = mask;
   if (nchunks > 0) {

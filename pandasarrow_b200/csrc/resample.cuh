@@ -19,7 +19,11 @@
 
 namespace pa {
 
-constexpr int RS_CHUNK = 1024;     // rows per warp-chunk
+constexpr int RS_CHUNK = 1024;     // rows per warp-chunk (small inputs: enough chunks for every warp of the grid)
+constexpr int RS_CHUNK_BIG = 4096; // from RS_BIG_ROWS rows on: a chunk's first iteration never finds an open run and every chunk
+                                   // leaves two boundary partials to the fixup kernel — a quarter of both
+constexpr int64_t RS_BIG_ROWS = 32 << 20;
+inline int64_t rs_chunk_rows(int64_t n) { return n >= RS_BIG_ROWS ? RS_CHUNK_BIG : RS_CHUNK; }
 constexpr int RS_THREADS = 256;
 
 struct ResampleSpec {
@@ -79,6 +83,7 @@ struct RsArgs {
   void* table;          // nbins (+2) slots
   RsPartial* bnd;       // [nchunks][2]
   int64_t nchunks;
+  int64_t chunk;        // rows per warp-chunk (a multiple of 32 * RS_U)
   uint32_t* status;
   uint32_t agg_mask;
 };
@@ -121,13 +126,33 @@ __device__ __forceinline__ void rs_store_slot(void* table, int64_t b, const Resa
 
 // Lane-private partial of the open run: every lane folds its own rows (row order), the lanes are
 // combined with a fixed xor-shuffle tree only when the run is closed.
+// fp64 values keep min / max as DOUBLES folded with one DSETP + two SEL each (an ordered compare is false for a NaN, which
+// is exactly "NaN is skipped"), converted to order-mapped words when the run closes: the order map + NaN test + two 64-bit
+// integer compare-and-selects cost ~15 instructions per row and made OHLC issue bound (sm_100a has no DMNMX; fmin / fmax
+// compile to DSETP + FSEL + LOP3 + moves, no cheaper).  -0.0 and +0.0 compare equal here, so which zero a lane keeps is
+// the first it met (the lanes are then combined in the order map, -0.0 < +0.0) — the sign of a zero minimum / maximum is
+// the documented tie difference against Arrow's fmin / fmax.  +inf / -inf together mean "no number seen" (a lane that saw
+// +inf only has mx = +inf).
 template <int VC, bool WIDE>
 struct RsLane {
+  static constexpr uint64_t MN0 = VC == VC_F ? 0x7FF0000000000000ull : kMinInit;   // fp64: +inf bits
+  static constexpr uint64_t MX0 = VC == VC_F ? 0xFFF0000000000000ull : kMaxInit;   // fp64: -inf bits
   uint64_t sum = 0;     // double bits or wrapping int
   double dsum = 0.0;
-  uint64_t mn = kMinInit, mx = kMaxInit;
+  uint64_t mn = MN0, mx = MX0;   // fp64 values: double bits; integers: order-mapped
   uint32_t cnt = 0;
-  __device__ __forceinline__ void reset() { sum = 0; dsum = 0.0; mn = kMinInit; mx = kMaxInit; cnt = 0; }
+  __device__ __forceinline__ void reset() { sum = 0; dsum = 0.0; mn = MN0; mx = MX0; cnt = 0; }
+  __device__ __forceinline__ void fold_mm(uint64_t vb) {
+    if constexpr (VC == VC_F) {
+      const double v = __longlong_as_double(static_cast<long long>(vb));
+      mn = v < __longlong_as_double(static_cast<long long>(mn)) ? vb : mn;   // false for a NaN
+      mx = v > __longlong_as_double(static_cast<long long>(mx)) ? vb : mx;
+    } else {
+      const uint64_t o = Wide<VC>::ord(vb);
+      mn = o < mn ? o : mn;
+      mx = o > mx ? o : mx;
+    }
+  }
   __device__ __forceinline__ void add_row(uint64_t vb, uint32_t agg_mask) {
     if constexpr (VC == VC_F) sum = static_cast<uint64_t>(__double_as_longlong(__longlong_as_double(static_cast<long long>(sum)) +
                                                                              __longlong_as_double(static_cast<long long>(vb))));
@@ -135,11 +160,7 @@ struct RsLane {
     ++cnt;
     if constexpr (WIDE) {
       if constexpr (VC != VC_F) dsum += Wide<VC>::as_double(vb);
-      if ((agg_mask & (AGG_MIN | AGG_MAX)) && !Wide<VC>::is_nan(vb)) {
-        const uint64_t o = Wide<VC>::ord(vb);
-        mn = o < mn ? o : mn;
-        mx = o > mx ? o : mx;
-      }
+      if (agg_mask & (AGG_MIN | AGG_MAX)) fold_mm(vb);
     }
   }
   // the same without a branch (the steady state of the scan: every row of the batch is valid and in the open run);
@@ -151,12 +172,7 @@ struct RsLane {
     ++cnt;
     if constexpr (WIDE) {
       if constexpr (VC != VC_F) dsum += Wide<VC>::as_double(vb);
-      if (want_mm) {
-        const bool num = !Wide<VC>::is_nan(vb);
-        const uint64_t o = Wide<VC>::ord(vb);
-        mn = (num && o < mn) ? o : mn;
-        mx = (num && o > mx) ? o : mx;
-      }
+      if (want_mm) fold_mm(vb);
     }
   }
   // all lanes end up with the warp total
@@ -164,6 +180,11 @@ struct RsLane {
     constexpr uint32_t FULL = 0xFFFFFFFFu;
     uint32_t c = cnt;
     uint64_t n = mn, x = mx;
+    if constexpr (VC == VC_F && WIDE) {
+      const bool none = mn == MN0 && mx == MX0;
+      n = none ? kMinInit : f64_to_ord(__longlong_as_double(static_cast<long long>(mn)));
+      x = none ? kMaxInit : f64_to_ord(__longlong_as_double(static_cast<long long>(mx)));
+    }
     double ds = dsum;
     if constexpr (VC == VC_F) {
       double v = __longlong_as_double(static_cast<long long>(sum));
@@ -210,8 +231,8 @@ __global__ void __launch_bounds__(RS_THREADS) k_resample_scan(RsArgs a) {
   const bool fast_vals = a.vals != nullptr && a.vw == 8 && a.vvalid == nullptr;
   const int64_t shift = sp.closed_right ? 1 : 0;
   for (int64_t c = gw; c < a.nchunks; c += nw) {
-    const int64_t row0 = c * RS_CHUNK;
-    const int64_t row_end = row0 + RS_CHUNK < a.n ? row0 + RS_CHUNK : a.n;
+    const int64_t row0 = c * a.chunk;
+    const int64_t row_end = row0 + a.chunk < a.n ? row0 + a.chunk : a.n;
     RsLane<VC, WIDE> part;                         // this lane's share of the open run
     uint32_t run_first = kNoRow, run_last = 0;     // first / last row of the open run (uniform)
     int64_t cur_b = -1;                            // bucket of the open run

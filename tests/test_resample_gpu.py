@@ -277,3 +277,31 @@ def test_calendar_errors_like_the_reference(pab, orc):
     us = pa.array(np.arange(1000, dtype=np.int64) * 86400 * 10**6, pa.timestamp("us"))
     with pytest.raises(pab.PaError, match=r"timestamp\[ns\]"):
         G.resample_calendar(frame, us, "MS", closed_right=True)
+
+
+@pytest.mark.parametrize("nullable", [False, True])
+def test_resample_min_max_special_values(pab, orc, nullable):
+    """min / max of fp64 values are folded as doubles per lane (ordered compares: a NaN never wins) and order-mapped when a
+    run closes: NaN rows, buckets that hold nothing but NaN, +-inf only buckets and signed zeros against the oracle, on the
+    steady-state path (no bitmap) and the per-batch path (bitmap)."""
+    from pandasarrow_b200 import hostgen as hg
+    n = 400_000
+    ts = hg.timestamps(n, step_ns=500_000_000)     # ~120 ticks per minute: runs longer than one 128-row iteration
+    rng = np.random.default_rng(11)
+    v = rng.standard_normal(n) * 50
+    v[rng.random(n) < 0.05] = np.nan
+    v[rng.random(n) < 0.01] = np.inf
+    v[rng.random(n) < 0.01] = -np.inf
+    v[rng.random(n) < 0.03] = 0.0
+    v[rng.random(n) < 0.03] = -0.0
+    b = (np.asarray(ts) - np.asarray(ts)[0]) // MIN
+    v[b == 3] = np.nan                 # nothing but NaN
+    v[b == 5] = np.inf                 # +inf only
+    v[b == 7] = -np.inf                # -inf only
+    v[(b == 9) & (np.arange(n) % 2 == 0)] = np.nan
+    v[(b == 9) & (np.arange(n) % 2 == 1)] = -np.inf
+    mask = (rng.random(n) < 0.1) if nullable else None
+    if nullable:
+        mask[b == 11] = True           # an all-null bucket
+    frame = {"px": pa.array(v, pa.float64(), mask=mask)}
+    _compare(pab, orc, ts, frame, MIN, ["min", "max", "sum", "count", "first", "last"])
