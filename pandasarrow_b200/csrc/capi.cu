@@ -162,12 +162,13 @@ int parse_format(const char* f, int* width, int* vc) {
 // bounce it through its own small staging area at a fraction of that rate, so anything large goes through the
 // library's two pinned staging buffers, filled by a few host threads while the previous chunk is on the wire.
 namespace {
-constexpr size_t H2D_CHUNK = 8u << 20;            // bytes per staging buffer (two per worker)
+constexpr size_t H2D_CHUNK = 8u << 20;            // bytes per staging buffer (two per worker); PA_H2D_CHUNK_MB overrides
 constexpr size_t H2D_STAGED_MIN = 16u << 20;      // smaller copies are not worth the pipeline
 constexpr int H2D_MAX_WORKERS = 16;
+constexpr int H2D_MAX_BUFS = 4;
 struct H2dWorker {
-  void* pin[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {};
+  void* pin[H2D_MAX_BUFS] = {};
+  cudaEvent_t done[H2D_MAX_BUFS] = {};
   cudaEvent_t fin = nullptr;
   cudaStream_t stream = nullptr;
 };
@@ -177,6 +178,8 @@ struct H2dStage {
   cudaEvent_t start = nullptr;
   bool ok = false, tried = false;
   int workers = 1;
+  size_t chunk = H2D_CHUNK;
+  int bufs = 2;                                    // staging buffers per worker; PA_H2D_BUFS overrides
 };
 H2dStage g_h2d_dev[16];   // one per device: streams and events belong to a device
 
@@ -187,13 +190,15 @@ bool h2d_stage_ready(H2dStage& g) {
   const unsigned hc = std::thread::hardware_concurrency();
   g.workers = static_cast<int>(std::max(1u, std::min(8u, hc ? hc / 2 : 4u)));
   if (const char* e = getenv("PA_H2D_THREADS")) g.workers = std::max(1, std::min(H2D_MAX_WORKERS, atoi(e)));
+  if (const char* e = getenv("PA_H2D_BUFS")) g.bufs = std::max(2, std::min(H2D_MAX_BUFS, atoi(e)));
+  if (const char* e = getenv("PA_H2D_CHUNK_MB")) g.chunk = static_cast<size_t>(std::max(1, std::min(64, atoi(e)))) << 20;
   if (cudaEventCreateWithFlags(&g.start, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
   for (int i = 0; i < g.workers; ++i) {
     H2dWorker& w = g.w[i];
     bool good = cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) == cudaSuccess &&
                 cudaEventCreateWithFlags(&w.fin, cudaEventDisableTiming) == cudaSuccess;
-    for (int b = 0; b < 2 && good; ++b)
-      good = cudaHostAlloc(&w.pin[b], H2D_CHUNK, cudaHostAllocPortable) == cudaSuccess &&
+    for (int b = 0; b < g.bufs && good; ++b)
+      good = cudaHostAlloc(&w.pin[b], g.chunk, cudaHostAllocPortable) == cudaSuccess &&
              cudaEventCreateWithFlags(&w.done[b], cudaEventDisableTiming) == cudaSuccess;
     if (!good) { cudaGetLastError(); return false; }
   }
@@ -235,8 +240,8 @@ int h2d_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
     const size_t lo = per * t, hi = std::min(bytes, lo + per);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(w.stream, g.start, 0);
     int b = 0;
-    for (size_t off = lo; off < hi && e == cudaSuccess; off += H2D_CHUNK, b ^= 1) {
-      const size_t len = std::min(H2D_CHUNK, hi - off);
+    for (size_t off = lo; off < hi && e == cudaSuccess; off += g.chunk, b = b + 1 == g.bufs ? 0 : b + 1) {
+      const size_t len = std::min(g.chunk, hi - off);
       e = cudaEventSynchronize(w.done[b]);                 // the previous copy out of this buffer has finished
       if (e != cudaSuccess) break;
       memcpy(w.pin[b], static_cast<const char*>(src) + off, len);
