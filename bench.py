@@ -442,6 +442,16 @@ def main():
             h.close()
         except Exception as ex:  # noqa: BLE001
             extras["error"] = repr(ex)[:300]
+        # the same roofline figure for the general (hash-table) mode of the headline kernel and for config 4's scan,
+        # next to the dense-key headline: 16 B/row of the same workload / that scan's duration / the same peak
+        if "scattered_keys" in extras:
+            sk = extras["scattered_keys"]
+            roofline["scattered_keys"] = {"kernel": "k_lowcard_scan (hash mode)", "kernel_ms": sk["scan_ms"],
+                                          "achieved": sk["scan_GBps"], "frac": sk["frac"]}
+        if "resample_ohlc_sum" in extras:
+            rk = extras["resample_ohlc_sum"]
+            roofline["resample_ohlc_sum"] = {"kernel": "k_resample_scan", "kernel_ms": rk["scan_ms"],
+                                             "achieved": rk["scan_GBps"], "frac": rk["frac"]}
 
     # ---------------- N > 1: config 5 (BASELINE configs[4]): 1 B rows per GPU, 100 M groups, counted exchange ----------------
     if world > 1 and args.config5_groups > 0 and not args.no_extras:
