@@ -171,7 +171,9 @@ struct LcSmem {
   static constexpr size_t OFF_MM = 16;                                           // GP x {min, max} (wide)
   static constexpr size_t OFF_FIRST = OFF_MM + (WIDE ? GP * 16 : 0);             // GP u32
   static constexpr size_t OFF_LAST = OFF_FIRST + GP * 4;                         // GP u32 (wide)
-  static constexpr size_t OFF_TAB = ((OFF_LAST + (WIDE ? GP * 4 : 0) + 15) / 16) * 16;   // LC_HT packed entries (hash)
+  static constexpr bool BOUNDS = WIDE && !HASHK && VC == VC_F;                   // fp32 {min, max} pre-check words (lc_wide_update)
+  static constexpr size_t OFF_BND = ((OFF_LAST + (WIDE ? GP * 4 : 0) + 7) / 8) * 8;      // GP x {float, float}
+  static constexpr size_t OFF_TAB = ((OFF_BND + (BOUNDS ? GP * 8 : 0) + 15) / 16) * 16;  // LC_HT packed entries (hash)
   static constexpr size_t OFF_OVFK = OFF_TAB + (HASHK ? LC_HT * 8 : 0);          // LC_OVF keys (hash)
   static constexpr size_t OFF_OVFI = OFF_OVFK + (HASHK ? LC_OVF * 8 : 0);        // LC_OVF ids (hash)
   static constexpr size_t OFF_ACC = ((OFF_OVFI + (HASHK ? LC_OVF * 4 : 0) + 15) / 16) * 16;
@@ -199,6 +201,8 @@ struct LcCtx {
   uint32_t mm;                        // CTA-shared {min, max} array (wide), shared-memory address
   unsigned long long* mm_p;           // the same, generic pointer (atomics)
   uint32_t* last_p;                   // CTA-shared last-row array (wide)
+  uint32_t bnd;                       // CTA-shared fp32 {min rounded up, max rounded down} pre-check words (wide fp64, dense mode)
+  uint32_t* bnd_p;                    // the same, generic pointer (atomics)
   uint32_t tab;                       // hash mode: packed table, shared-memory address
   unsigned long long* tab_p;          // the same, generic pointer (atomics)
   unsigned long long* ovf_keys;       // hash mode: overflow list
@@ -409,17 +413,55 @@ __device__ __noinline__ LcContrib<DSUM> lc_fold_general(LcContrib<DSUM> k, uint3
   return k;
 }
 
-// min / max / last row are order independent: CTA-shared arrays, plain pre-check, rare atomic
-template <int VC>
+// min / max / last row of one row into the CTA-shared arrays (order independent: plain pre-check, rare atomic).  BOUNDS (fp64 values, dense-mode kernel): the pre-check reads
+// 8 bytes instead of 16 — {the group's minimum rounded UP to fp32, its maximum rounded DOWN to fp32} (NaN = no number seen
+// yet) against the row's value rounded down / up: rd(v) >= ru(min) implies v >= min, ru(v) <= rd(max) implies v <= max, so
+// a row that passes both cannot change either and is done after one LDS.64 (~5.8 shared-memory wavefronts per 32-row batch
+// on random slots against ~10.5 for the LDS.128 of the exact pair: profiles/r2_lowcard_wide_ncu_full.md).  Everything
+// else — a new extreme, a value within fp32 rounding of one, the first number of a group — takes the exact path below and
+// then tightens the fp32 words (CAS loops on a rare path).  The words only ever move towards the exact pair and are
+// written AFTER it, so a stale word is merely conservative.
+template <int VC, bool BOUNDS>
 __device__ __forceinline__ void lc_wide_update(uint32_t gid, uint64_t vbits, bool vv, uint32_t row, uint32_t agg_mask, const LcCtx& c) {
   if (agg_mask & AGG_LAST) atomicMax(c.last_p + gid, row);
   if (vv && (agg_mask & (AGG_MIN | AGG_MAX)) && !Wide<VC>::is_nan(vbits)) {
+    float lo = 0.f, hi = 0.f;
+    if constexpr (BOUNDS) {
+      const double v = __longlong_as_double(static_cast<long long>(vbits));
+      lo = __double2float_rd(v);
+      hi = __double2float_ru(v);
+      const uint64_t b = lds64(c.bnd + gid * 8u);
+      const uint32_t bmn = static_cast<uint32_t>(b), bmx = static_cast<uint32_t>(b >> 32);
+      // equal counts only bit for bit: -0.0 against a +0.0 word goes on to the exact pair, whose order map tells the two
+      // zeros apart — the result must not depend on which zero a CTA met first.  All four tests fail on a NaN word.
+      const bool in_lo = lo > __uint_as_float(bmn) || __float_as_uint(lo) == bmn;
+      const bool in_hi = hi < __uint_as_float(bmx) || __float_as_uint(hi) == bmx;
+      if (in_lo && in_hi) return;
+    }
     const uint64_t o = Wide<VC>::ord(vbits);
     const uint4 m4 = lds128(c.mm + gid * 16u);
     const uint64_t mn = static_cast<uint64_t>(m4.x) | (static_cast<uint64_t>(m4.y) << 32);
     const uint64_t mx = static_cast<uint64_t>(m4.z) | (static_cast<uint64_t>(m4.w) << 32);
     if (o < mn) atomicMin(c.mm_p + 2 * gid, static_cast<unsigned long long>(o));
     if (o > mx) atomicMax(c.mm_p + 2 * gid + 1, static_cast<unsigned long long>(o));
+    if constexpr (BOUNDS) {
+      // fp32 words: min word = the smallest ru(v) seen, max word = the largest rd(v) seen (>= / <= the exact pair)
+      __threadfence_block();                            // the exact pair first, then the words that vouch for it
+      volatile uint32_t* bp = c.bnd_p + 2 * gid;
+      uint32_t cur = bp[0];
+      // smaller wins; of two equal zeros the negative one (the smaller in the exact pair's order)
+      while (!(__uint_as_float(cur) < hi || cur == __float_as_uint(hi) || (__uint_as_float(cur) == hi && (cur >> 31)))) {
+        const uint32_t seen = atomicCAS(c.bnd_p + 2 * gid, cur, __float_as_uint(hi));   // word is NaN (unset) or above ru(v)
+        if (seen == cur) break;
+        cur = seen;
+      }
+      cur = bp[1];
+      while (!(__uint_as_float(cur) > lo || cur == __float_as_uint(lo) || (__uint_as_float(cur) == lo && !(cur >> 31)))) {
+        const uint32_t seen = atomicCAS(c.bnd_p + 2 * gid + 1, cur, __float_as_uint(lo));
+        if (seen == cur) break;
+        cur = seen;
+      }
+    }
   }
 }
 
@@ -451,7 +493,7 @@ __device__ __forceinline__ void lc_accumulate(uint32_t id, uint64_t vbits, bool 
   const uint32_t cw = lds32(cw_addr);
   uint64_t s = lds64(sum_addr);
   if constexpr (WIDE) {
-    if (live) lc_wide_update<VC>(gid, vbits, vv, row, agg_mask, c);
+    if (live) lc_wide_update<VC, DENSE && VC == VC_F>(gid, vbits, vv, row, agg_mask, c);
   }
   const uint32_t tag = cw >> 24;
   const bool winner = live && (tag == lane);
@@ -791,6 +833,8 @@ __global__ void __launch_bounds__(LcSmem<VC, WIDE, !DENSEK>::WARPS * 32, 1) k_lo
   c.mm_p = reinterpret_cast<unsigned long long*>(smem + L::OFF_MM);
   c.mm = smem_u32(c.mm_p);
   c.last_p = reinterpret_cast<uint32_t*>(smem + L::OFF_LAST);
+  c.bnd_p = reinterpret_cast<uint32_t*>(smem + L::OFF_BND);
+  c.bnd = smem_u32(c.bnd_p);
   c.rmask = (1u << c.rlog) - 1u;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.status[ST_MODE] = dense ? 1u : 2u;
@@ -808,6 +852,7 @@ __global__ void __launch_bounds__(LcSmem<VC, WIDE, !DENSEK>::WARPS * 32, 1) k_lo
       c.mm_p[2 * i] = kMinInit;
       c.mm_p[2 * i + 1] = kMaxInit;
       c.last_p[i] = 0u;
+      if constexpr (L::BOUNDS) { c.bnd_p[2 * i] = 0x7FC00000u; c.bnd_p[2 * i + 1] = 0x7FC00000u; }   // NaN: no number yet
     }
   }
   if (threadIdx.x < 4) c.misc[threadIdx.x] = 0;

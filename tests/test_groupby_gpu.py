@@ -489,3 +489,63 @@ def test_async_aggregate_equals_sync(pab, G, expect):
     if G == 1000:
         assert c.timing()["mode"] == "hash"
         assert c.fetch("count").equals(a.fetch("count"))
+
+
+@pytest.mark.parametrize("groups", [7, 16, 256, 1000])
+@pytest.mark.parametrize("nullable", [False, True])
+def test_min_max_fp32_bounds_precheck(pab, orc, groups, nullable):
+    """Dense-mode wide kernel, fp64 values: the {min, max} pre-check reads fp32 bounds (min rounded up, max rounded down)
+    and only rows outside them reach the exact pair.  Values chosen to sit ON the rounding edges: doubles that no fp32
+    holds repeated as a group's minimum / maximum, neighbours of such values one ulp away, magnitudes beyond fp32's range
+    (round to +-inf / +-FLT_MAX), fp64 subnormals (round to +-0 / the smallest fp32 subnormal), signed zeros, +-inf, NaN,
+    all-NaN groups.  Exact against the oracle, bit-identical (sign of zero included) against the hash-mode kernel — which
+    keeps the plain exact pre-check — on the same values, and from run to run."""
+    n = 600_000
+    rng = np.random.default_rng(groups * 2 + nullable)
+    k = rng.integers(0, groups, n)
+    base = np.array([100.01, -100.01, 1.0 + 2.0**-30, 1.0 - 2.0**-31, 3.0e300, -3.0e300, 1.0e-310, -1.0e-310, 1.0e-45, -1.0e-45,
+                     0.0, -0.0, np.inf, -np.inf, np.nan, 16777217.0, -16777217.0, 0.1, 0.3, 2.5])
+    v = base[rng.integers(0, len(base), n)]
+    # one ulp (of the double) around the edge values, so that rd / ru of neighbours land on the same fp32 pair
+    step = rng.integers(-2, 3, n)
+    fin = np.isfinite(v) & (v != 0)
+    v[fin] = v[fin] * (1.0 + step[fin] * 2.0**-52)
+    cont = rng.random(n) < 0.5
+    v[cont] = rng.standard_normal(int(cont.sum())) * 1e3           # ordinary continuous values in between
+    # which edge value is a group's extreme depends on the group: +-inf (k % 4 == 0), +-3e300 (1), +-16777217 (2), +-100.01 (3)
+    c = k % 4
+    v[(c >= 1) & np.isinf(v)] = 2.5
+    v[(c >= 2) & (np.abs(v) > 1e299)] = 0.3
+    v[(c == 3) & (np.abs(v) > 1.6e7)] = 0.1
+    v[(c == 3) & cont] *= 1e-2
+    v[k == 3] = np.nan                                              # a group with nothing but NaN
+    v[k == 5] = np.where(rng.random(int((k == 5).sum())) < 0.5, 0.0, -0.0)   # nothing but zeros of both signs
+    v[k == 6] = 100.01                                              # one value no fp32 holds, a million times
+    mask = (rng.random(n) < 0.1) if nullable else None
+    frame = {"k": pa.array(k, pa.int64()), "v": pa.array(v, pa.float64(), mask=mask)}
+    aggs = ["sum", "min", "max", "count", "last"]
+    gb, ora, rb = _both(pab, orc, frame, "k")
+    res = _cmp(gb, ora, rb, "v", aggs, f"bounds pre-check G={groups}")
+    assert gb.timing()["path"] == "lowcard" and gb.timing()["mode"] == "dense"
+    res2 = gb.aggregate(frame["v"], aggs)
+    # the same rows under scattered 64-bit keys: hash mode, exact pre-check only
+    ks = (k.astype(np.uint64) * np.uint64(0x2545F4914F6CDD1D) + np.uint64(0x1234567)).astype(np.int64)
+    gh = pab.GroupBy("k", pa.record_batch({"k": pa.array(ks, pa.int64()), "v": frame["v"]}))
+    resh = gh.aggregate(frame["v"], aggs)
+    assert gh.timing()["mode"] == "hash"
+    order = {key: i for i, key in enumerate(gb.unique(0).to_pylist())}
+    perm = pa.array([order[_unscramble(x)] for x in gh.unique(0).to_pylist()])
+    for a in ("min", "max"):
+        b1 = res[a].to_numpy(zero_copy_only=False).view(np.uint64)
+        b2 = res2[a].to_numpy(zero_copy_only=False).view(np.uint64)
+        assert np.array_equal(b1, b2), f"{a}: differs from run to run"
+        bh = np.empty_like(b1)
+        bh[np.asarray(perm)] = resh[a].to_numpy(zero_copy_only=False).view(np.uint64)
+        nan = np.isnan(b1.view(np.float64))
+        assert np.array_equal(b1[~nan], bh[~nan]), f"{a}: dense and hash mode differ (bits)"
+        assert np.array_equal(np.asarray(res[a].is_valid()), np.asarray(res2[a].is_valid()))
+
+
+def _unscramble(x):
+    inv = pow(0x2545F4914F6CDD1D, -1, 2**64)
+    return ((int(x) % 2**64 - 0x1234567) * inv) % 2**64
