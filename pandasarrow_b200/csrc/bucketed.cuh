@@ -258,7 +258,10 @@ static_assert(RP_CHUNK_ROWS % RpSmemBig::TILE == 0 && RpSmemBig::TILE <= (1 << 1
 // second resident CTA keeps the memory system busy while the first one regroups.
 // THREADS = 1024 (8192-row tiles, one CTA per SM) for fan-outs whose 4096-row runs would be 128 bytes or shorter
 // (launch_rp_scatter in capi.cu picks; measured there).
-template <int THREADS>
+// NULLABLE is a template parameter of the scatter and of k_bucket_agg: as a run-time test inside their row loops the
+// handling of null values cost the plain path 5-8 % (64 K / 1 M / 100 M groups 15.0 / 25.1 / 53.9 -> 15.9 / 27.4 / 57.1 ms
+// per 1 B rows, scripts/r2_run51.sh).
+template <int THREADS, bool NULLABLE>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1) k_rp_scatter_t(RpArgs a) {
   using S = RpSmemT<THREADS>;
   constexpr int RP_THREADS = THREADS;                // (shadows the namespace constants inside this kernel)
@@ -358,7 +361,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1) k_rp_scatter_
         const int r = threadIdx.x + j * RP_THREADS;
         row[j] = static_cast<uint32_t>(row0 + r);
         if (a.rows && pr[j] != 0xFFFFFFFFu) row[j] = ldg_stream_u32_na(a.rows + row0 + r);
-        if (!a.rows && a.vvalid && pr[j] != 0xFFFFFFFFu && !bit_at(a.vvalid, a.voff + row0 + r)) row[j] |= RP_NULL_BIT;
+        if constexpr (NULLABLE) {
+          if (!a.rows && a.vvalid && pr[j] != 0xFFFFFFFFu && !bit_at(a.vvalid, a.voff + row0 + r)) row[j] |= RP_NULL_BIT;
+        }
       }
 #pragma unroll
       for (int j = 0; j < RP_ROWS; ++j) {
@@ -418,7 +423,7 @@ struct BkArgs {
   int shift;
 };
 
-template <int VC, bool WIDE>
+template <int VC, bool WIDE, bool NULLABLE>
 __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
   using T = SmTab<VC, WIDE>;
   extern __shared__ __align__(16) unsigned char st_smem[];
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) k_bucket_agg(BkArgs a) {
         const uint64_t key = keyv[j];
         uint32_t row = rowv[j];
         bool vvalid = true;
-        if (a.nullable) { vvalid = (row & RP_NULL_BIT) == 0u; row &= ~RP_NULL_BIT; }   // a null value: the row still makes
+        if constexpr (NULLABLE) { vvalid = (row & RP_NULL_BIT) == 0u; row &= ~RP_NULL_BIT; }   // a null value: the row still makes
         uint32_t s;                                                                    // the group and counts for first / last
         bool found = false;
         if (key == kEmptyKey) { s = T::CAP + 1; found = true; }

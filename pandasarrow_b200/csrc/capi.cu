@@ -742,12 +742,13 @@ double hll_estimate(const uint32_t* reg) {
 int launch_rp_scatter(pa_groupby* g, const RpArgs& a) {
   static const int big_from = [] { const char* e = std::getenv("PA_RP_BIG_TILE_LOG"); return e ? std::atoi(e) : 8; }();
   cudaStream_t st = g->stream;
+  const bool nullable = !a.rows && a.vvalid;          // level 1 of a nullable value column: validity bit -> row-number word
   if (a.log_fan >= big_from) {
-    auto kern = k_rp_scatter_t<RP_THREADS_BIG>;
+    auto kern = nullable ? k_rp_scatter_t<RP_THREADS_BIG, true> : k_rp_scatter_t<RP_THREADS_BIG, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RpSmemBig::TOTAL)));
     kern<<<g->num_sms, RP_THREADS_BIG, RpSmemBig::TOTAL, st>>>(a);
   } else {
-    auto kern = k_rp_scatter_t<RP_THREADS>;
+    auto kern = nullable ? k_rp_scatter_t<RP_THREADS, true> : k_rp_scatter_t<RP_THREADS, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(RpSmem::TOTAL)));
     kern<<<g->num_sms * 2, RP_THREADS, RpSmem::TOTAL, st>>>(a);
   }
@@ -899,7 +900,7 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
     bref.table = sc.table.p; bref.cap_mask = cap - 1; bref.shift = 64 - __builtin_ctzll(cap);
     bref.n_buckets = nb; bref.part_bits = bits; bref.agg_mask = mask; bref.max_keys = T::MAX_KEYS;
     bref.status = g->status.as<uint32_t>();
-    auto kern = k_bucket_agg<VC, WIDE>;
+    auto kern = bref.nullable ? k_bucket_agg<VC, WIDE, true> : k_bucket_agg<VC, WIDE, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::TOTAL)));
     kern<<<g->num_sms, BK_THREADS, T::TOTAL, st>>>(bref);
     CUDA_TRY(cudaGetLastError());
@@ -926,7 +927,7 @@ int run_bucketed_t(pa_groupby* g, const Column* val, uint32_t mask, uint64_t* ca
   b.u_rec = sc.u_rec.p; b.u_first = sc.u_first.as<uint32_t>();
   b.u_cap = u_cap; b.status = g->status.as<uint32_t>();
   {
-    auto kern = k_bucket_agg<VC, WIDE>;
+    auto kern = b.nullable ? k_bucket_agg<VC, WIDE, true> : k_bucket_agg<VC, WIDE, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(T::TOTAL)));
     kern<<<g->num_sms, BK_THREADS, T::TOTAL, st>>>(b);
     CUDA_TRY(cudaGetLastError());
